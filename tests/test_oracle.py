@@ -1,0 +1,127 @@
+"""The oracle against the reference's own outputs (tests/golden/, produced by
+oracle/gen_golden.py running the unmodified reference in float64)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import gnnae_oracle as O
+from golden_cases import CASES, make_input, make_params
+from conftest import GOLDEN
+
+
+def rel(a, b):
+    return float(np.linalg.norm(np.asarray(a, np.float64).ravel() - np.asarray(b, np.float64).ravel())
+                 / (np.linalg.norm(np.asarray(b, np.float64).ravel()) + 1e-300))
+
+
+def test_index_lists_every_case():
+    idx = json.load(open(os.path.join(GOLDEN, "index.json")))
+    assert sorted(idx["cases"]) == sorted(CASES)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_oracle_matches_reference(name):
+    case = CASES[name]
+    g = np.load(os.path.join(GOLDEN, f"{name}.npz"))
+    ep, dp = make_params(case)
+    x = make_input(case)
+    loss, z, y, eg, dg = O.loss_and_grads(
+        x, ep, dp, case["enc"], case["dec"], metric=case["metric"], loss_norm_choice=case["loss_norm_choice"],
+        jet_features_weight=case["jet_features_weight"], l1_lambda=case["l1_lambda"])
+    tol = 1e-12 if case["store64"] else 2e-7   # float32-stored fixtures carry 6e-8 rounding
+    assert z.shape == g["latent"].shape and y.shape == g["recon"].shape
+    assert rel(z, g["latent"]) < 1e-12
+    assert rel(y, g["recon"]) < 1e-12
+    assert abs(loss - g["loss_intended"]) <= 1e-11 * abs(g["loss_intended"])
+    egf = np.concatenate([eg[k].ravel() for k in sorted(ep)])
+    dgf = np.concatenate([dg[k].ravel() for k in sorted(dp)])
+    assert rel(egf, g["enc_grad"]) < tol
+    assert rel(dgf, g["dec_grad"]) < tol
+    # the value the reference actually returns (jet term only) and the two terms separately
+    cham, jet, _, _ = O.chamfer_terms(y, x, case["loss_norm_choice"])
+    assert abs(cham - g["chamfer_term"]) <= 1e-11 * max(1.0, abs(g["chamfer_term"]))
+    assert abs(jet - g["jet_term"]) <= 1e-11 * max(1.0, abs(g["jet_term"]))
+    ret, _ = O.chamfer_loss(y, x, case["loss_norm_choice"], case["jet_features_weight"], mode="reference")
+    assert abs(ret - g["returned"]) <= 1e-11 * max(1.0, abs(g["returned"]))
+
+
+def test_reference_mode_raises_on_zero_weight():
+    x = O.synthetic_jets(2, 5, dtype=np.float64)
+    with pytest.raises(UnboundLocalError):
+        O.chamfer_loss(x, x[:, ::-1], jet_features_weight=0, mode="reference")
+
+
+def test_pairwise_distance_validation():
+    p = np.zeros((2, 4, 3))
+    with pytest.raises(ValueError):
+        O.pairwise_distance_sq(p, np.zeros((3, 4, 3)))
+    with pytest.raises(ValueError):
+        O.pairwise_distance_sq(np.zeros((2, 4, 5)), np.zeros((2, 4, 5)))
+    with pytest.raises(ValueError):
+        O.pairwise_distance_sq(p, np.zeros((2, 4, 4)))
+
+
+def test_adjust_var_list_semantics():
+    assert O.adjust_var_list([[1], [2]], 4) == [[1], [2], [2], [2]]
+    assert O.adjust_var_list([[1], [2], [3]], 2) == [[1], [2]]
+    assert O.adjust_var_list(0.2, 3) == [0.2, 0.2, 0.2]
+
+
+def test_backward_matches_finite_differences():
+    rng = np.random.default_rng(0)
+    case = CASES["max_n5"]
+    ep, dp = make_params(case)
+    x = make_input(case)
+    kw = dict(metric="euclidean", l1_lambda=0.0)
+    loss, *_, eg, dg = O.loss_and_grads(x, ep, dp, case["enc"], case["dec"], **kw)
+    for params, grads in ((ep, eg), (dp, dg)):
+        for k in list(params)[::3]:
+            idx = tuple(rng.integers(0, s) for s in params[k].shape)
+            old = params[k][idx]
+            h = 1e-6
+            params[k][idx] = old + h
+            lp = O.loss_and_grads(x, ep, dp, case["enc"], case["dec"], **kw)[0]
+            params[k][idx] = old - h
+            lm = O.loss_and_grads(x, ep, dp, case["enc"], case["dec"], **kw)[0]
+            params[k][idx] = old
+            fd = (lp - lm) / (2 * h)
+            assert abs(fd - grads[k][idx]) <= 1e-5 * max(1.0, abs(fd)), (k, idx, fd, grads[k][idx])
+
+
+def test_permutation_equivariance_of_oracle():
+    """utils/permutation.py:76-109 semantics: decoder(encoder(Px)) vs P decoder(encoder(x)) for the
+    per-node ('local mix') map, and invariance of the latent for 'mean'."""
+    case = CASES["local_mix_us_n8"]
+    ep, dp = make_params(case)
+    x = make_input(case)
+    perm = np.random.default_rng(1).permutation(case["N"])
+    z, _ = O.encoder_forward(x, ep, case["enc"])
+    y, _ = O.decoder_forward(z, dp, case["dec"])
+    zp, _ = O.encoder_forward(x[:, perm], ep, case["enc"])
+    yp, _ = O.decoder_forward(zp, dp, case["dec"])
+    assert O.relative_deviation(yp, y[:, perm]).max() < 1e-9
+    case = CASES["trainsh_n30"]
+    ep, dp = make_params(case)
+    x = make_input(case)
+    perm = np.random.default_rng(2).permutation(case["N"])
+    z, _ = O.encoder_forward(x, ep, case["enc"])
+    zp, _ = O.encoder_forward(x[:, perm], ep, case["enc"])
+    assert np.abs(zp - z).max() < 1e-12
+
+
+def test_adam_matches_torch():
+    import torch
+    rng = np.random.default_rng(3)
+    p0 = rng.normal(size=(7, 5))
+    params = {"w": p0.copy()}
+    state = {}
+    tp = torch.nn.Parameter(torch.from_numpy(p0.copy()))
+    opt = torch.optim.Adam([tp], 1e-3)
+    for _ in range(5):
+        g = rng.normal(size=p0.shape)
+        O.adam_update(params, {"w": g}, state, lr=1e-3)
+        tp.grad = torch.from_numpy(g.copy())
+        opt.step()
+    assert np.abs(params["w"] - tp.detach().numpy()).max() < 1e-14
