@@ -1,0 +1,146 @@
+// C-ABI entry points declared in include/gnnjet_b200.h: argument checks, dispatch on precision,
+// error reporting.  No torch types; raw device pointers + sizes + cudaStream_t.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "gj_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void gj_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int gj_num_sms() {
+  static int sms[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (sms[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    sms[dev] = v;
+  }
+  return sms[dev];
+}
+
+// launchers implemented in the kernel translation units
+int gj_mp_fwd_simt(const gj_mp_desc*, const float*, const float*, float*, float*, cudaStream_t);
+size_t gj_mp_bwd_simt_workspace(const gj_mp_desc*);
+int gj_mp_bwd_simt(const gj_mp_desc*, const float*, const float*, const float*, const float*, float*, float*, void*, size_t,
+                   cudaStream_t);
+int gj_mp_fwd_tc(const gj_mp_desc*, const float*, const float*, float*, float*, cudaStream_t);
+size_t gj_mp_bwd_tc_workspace(const gj_mp_desc*);
+int gj_mp_bwd_tc(const gj_mp_desc*, const float*, const float*, const float*, const float*, float*, float*, void*, size_t,
+                 cudaStream_t);
+int gj_umma_selftest_launch(int, int, int, int, int, const float*, const float*, float*, cudaStream_t);
+int gj_chamfer_launch(int, int, int, int, int, float, float, const float*, const float*, float*, float*, float*, cudaStream_t);
+int gj_linear_fwd_launch(int, int, int, const float*, const float*, const float*, float*, cudaStream_t);
+size_t gj_linear_bwd_ws_bytes(int, int, int);
+int gj_linear_bwd_launch(int, int, int, const float*, const float*, const float*, float*, float*, float*, void*, size_t, cudaStream_t);
+int gj_adam_launch(float*, const float*, float*, float*, size_t, float, float, float, float, int, float, float, float,
+                   cudaStream_t);
+size_t gj_norms_ws_bytes(size_t);
+int gj_norms_launch(const float*, size_t, float*, void*, size_t, cudaStream_t);
+int gj_latent_mean_fwd_launch(int, int, int, const float*, float*, cudaStream_t);
+int gj_latent_mean_bwd_launch(int, int, int, const float*, float*, cudaStream_t);
+
+extern "C" {
+
+const char* gj_last_error(void) { return g_err; }
+int32_t gj_abi_version(void) { return 1; }
+const char* gj_build_arch(void) { return "sm_100a"; }
+
+size_t gj_mp_param_count(const gj_mp_desc* d) {
+  MPLayout L; const char* why;
+  if (gj_fill_arch(d, &L, &why)) return 0;
+  return (size_t)L.nparams;
+}
+
+int gj_mp_step_fwd(const gj_mp_desc* d, const float* h, const float* params, float* h_out, float* e_out, void* stream) {
+  g_err[0] = 0;
+  if (!d || !h || !params || !h_out) { gj_set_error("gj_mp_step_fwd: null pointer"); return GJ_ERR_INVALID; }
+  if (d->precision == GJ_PREC_FP32) return gj_mp_fwd_simt(d, h, params, h_out, e_out, (cudaStream_t)stream);
+  if (d->precision == GJ_PREC_BF16) return gj_mp_fwd_tc(d, h, params, h_out, e_out, (cudaStream_t)stream);
+  gj_set_error("gj_mp_step_fwd: unknown precision %d", d->precision);
+  return GJ_ERR_INVALID;
+}
+
+size_t gj_mp_step_bwd_workspace(const gj_mp_desc* d) {
+  if (!d) return 0;
+  return d->precision == GJ_PREC_BF16 ? gj_mp_bwd_tc_workspace(d) : gj_mp_bwd_simt_workspace(d);
+}
+
+int gj_mp_step_bwd(const gj_mp_desc* d, const float* h, const float* e, const float* params, const float* dh_out, float* dh,
+                   float* dparams, void* workspace, size_t workspace_bytes, void* stream) {
+  g_err[0] = 0;
+  if (!d || !h || !e || !params || !dh_out || !dh || !dparams || !workspace) { gj_set_error("gj_mp_step_bwd: null pointer"); return GJ_ERR_INVALID; }
+  if (d->precision == GJ_PREC_FP32) return gj_mp_bwd_simt(d, h, e, params, dh_out, dh, dparams, workspace, workspace_bytes, (cudaStream_t)stream);
+  if (d->precision == GJ_PREC_BF16) return gj_mp_bwd_tc(d, h, e, params, dh_out, dh, dparams, workspace, workspace_bytes, (cudaStream_t)stream);
+  gj_set_error("gj_mp_step_bwd: unknown precision %d", d->precision);
+  return GJ_ERR_INVALID;
+}
+
+int gj_chamfer_fwd_bwd(int32_t batch, int32_t np_, int32_t nq, int32_t dim, int32_t norm, float w_chamfer, float w_jet,
+                       const float* p, const float* q, float* jet_terms, float* terms, float* dp, void* stream) {
+  g_err[0] = 0;
+  if (!p || !q || !jet_terms || !terms) { gj_set_error("gj_chamfer_fwd_bwd: null pointer"); return GJ_ERR_INVALID; }
+  return gj_chamfer_launch(batch, np_, nq, dim, norm, w_chamfer, w_jet, p, q, jet_terms, terms, dp, (cudaStream_t)stream);
+}
+
+int gj_linear_fwd(int32_t rows, int32_t in_f, int32_t out_f, const float* x, const float* w, const float* b, float* y,
+                  void* stream) {
+  g_err[0] = 0;
+  if (rows < 0 || in_f < 1 || out_f < 1) { gj_set_error("gj_linear_fwd: bad shape"); return GJ_ERR_INVALID; }
+  if (rows && (!x || !w || !y)) { gj_set_error("gj_linear_fwd: null pointer"); return GJ_ERR_INVALID; }
+  return gj_linear_fwd_launch(rows, in_f, out_f, x, w, b, y, (cudaStream_t)stream);
+}
+
+size_t gj_linear_bwd_workspace(int32_t rows, int32_t in_f, int32_t out_f) { return gj_linear_bwd_ws_bytes(rows, in_f, out_f); }
+
+int gj_linear_bwd(int32_t rows, int32_t in_f, int32_t out_f, const float* x, const float* w, const float* dy, float* dx,
+                  float* dw, float* db, void* workspace, size_t workspace_bytes, void* stream) {
+  g_err[0] = 0;
+  if (rows < 0 || in_f < 1 || out_f < 1) { gj_set_error("gj_linear_bwd: bad shape"); return GJ_ERR_INVALID; }
+  if (!w || !dw || !workspace || (rows && (!x || !dy))) { gj_set_error("gj_linear_bwd: null pointer"); return GJ_ERR_INVALID; }
+  return gj_linear_bwd_launch(rows, in_f, out_f, x, w, dy, dx, dw, db, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int gj_adam_step_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
+                      float beta2, float eps, int32_t step, float grad_scale, float l1_lambda, float l2_lambda, void* stream) {
+  g_err[0] = 0;
+  if (n && (!param || !grad || !exp_avg || !exp_avg_sq)) { gj_set_error("gj_adam_step_flat: null pointer"); return GJ_ERR_INVALID; }
+  return gj_adam_launch(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, grad_scale, l1_lambda, l2_lambda,
+                        (cudaStream_t)stream);
+}
+
+size_t gj_param_norms_workspace(size_t n) { return gj_norms_ws_bytes(n); }
+
+int gj_param_norms(const float* param, size_t n, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  g_err[0] = 0;
+  if (!out || !workspace || (n && !param)) { gj_set_error("gj_param_norms: null pointer"); return GJ_ERR_INVALID; }
+  return gj_norms_launch(param, n, out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int gj_latent_mean_fwd(int32_t batch, int32_t num_nodes, int32_t width, const float* y, float* z, void* stream) {
+  g_err[0] = 0;
+  if (batch < 0 || num_nodes < 1 || width < 1) { gj_set_error("gj_latent_mean_fwd: bad shape"); return GJ_ERR_INVALID; }
+  return gj_latent_mean_fwd_launch(batch, num_nodes, width, y, z, (cudaStream_t)stream);
+}
+
+int gj_latent_mean_bwd(int32_t batch, int32_t num_nodes, int32_t width, const float* dz, float* dy, void* stream) {
+  g_err[0] = 0;
+  if (batch < 0 || num_nodes < 1 || width < 1) { gj_set_error("gj_latent_mean_bwd: bad shape"); return GJ_ERR_INVALID; }
+  return gj_latent_mean_bwd_launch(batch, num_nodes, width, dz, dy, (cudaStream_t)stream);
+}
+
+int gj_umma_selftest(int32_t m, int32_t n, int32_t k, int32_t a_major, int32_t b_major, const float* a, const float* b,
+                     float* out, void* stream) {
+  g_err[0] = 0;
+  if (!a || !b || !out) { gj_set_error("gj_umma_selftest: null pointer"); return GJ_ERR_INVALID; }
+  return gj_umma_selftest_launch(m, n, k, a_major, b_major, a, b, out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,363 @@
+"""The batch body of reference utils/train.py:51-85 (encoder -> decoder -> Chamfer (+L1/L2) -> backward ->
+two Adams) as a fixed sequence of fused kernels over flat buffers.
+
+* all parameters of encoder and decoder live in ONE flat fp32 buffer (the nn.Linear parameters are
+  re-homed as views, so ``state_dict`` / checkpoints are unaffected); gradients, Adam moments likewise;
+* forward + loss + backward is a fixed list of C-ABI launches with preallocated activations -- captured
+  once into a CUDA graph and replayed (the reference pays ~10^3 ATen launches and a ``.item()`` sync per
+  batch, utils/train.py:77);
+* data parallel: jets are independent, each rank runs its shard and the only collective is ONE
+  all-reduce(sum) of the flat gradient buffer (the loss is a sum over jets, chamfer_loss.py:35,40, so sum
+  reproduces the single-process gradient); the two reference Adams (utils/initialize.py:152-153) have equal
+  hyper-parameters and are elementwise, so one fused flat Adam is identical to both.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from .losses import _norm_id
+from .models.const import GLOBAL_MIX, LOCAL_MIX
+
+
+# --------------------------------------------------------------------------------------------------
+# host-side helpers (no CUDA needed: covered by the CPU / gloo tests)
+# --------------------------------------------------------------------------------------------------
+def synthetic_jets(batch: int, num_particles: int, seed: int = 1234, dtype=np.float32) -> np.ndarray:
+    """JetNet-shaped jets (B,N,3) = [pt_rel, eta_rel, phi_rel] (feature order of the reference's
+    utils/data/preprocess.py:75-76): eta,phi ~ N(0, 0.1^2) clipped to +-0.5; pt_rel ~ Dirichlet(0.5) sorted
+    descending (JetNet is pT ordered); n ~ UniformInt[N/3, N] real particles, the rest zero padded."""
+    rng = np.random.default_rng(seed)
+    eta = np.clip(rng.normal(0.0, 0.1, (batch, num_particles)), -0.5, 0.5)
+    phi = np.clip(rng.normal(0.0, 0.1, (batch, num_particles)), -0.5, 0.5)
+    pt = rng.dirichlet(np.full(num_particles, 0.5), size=batch)
+    pt = -np.sort(-pt, axis=1)
+    n = rng.integers(max(1, num_particles // 3), num_particles + 1, size=batch)
+    mask = np.arange(num_particles)[None, :] < n[:, None]
+    x = np.stack([pt, eta, phi], axis=-1) * mask[..., None]
+    return x.astype(dtype)
+
+
+def shard_range(global_batch: int, rank: int, world_size: int):
+    """Jets [lo, hi) of rank ``rank``: contiguous shards, the remainder spread over the first ranks."""
+    base, rem = divmod(global_batch, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def flat_layout(encoder, decoder) -> "OrderedDict[str, tuple]":
+    """name -> (offset, shape) of every parameter in the flat buffer.  Order: encoder GraphNet steps in kernel
+    packing order, encoder mix layer, decoder input linear, decoder GraphNet steps."""
+    out, off = OrderedDict(), 0
+
+    def add(name, p):
+        nonlocal off
+        out[name] = (off, tuple(p.shape))
+        off += p.numel()
+
+    def add_graphnet(prefix, g):
+        for t in range(g.num_mps):
+            for kind, net in (("edge_net", g.edge_net[t]), ("node_net", g.node_net[t])):
+                for k, layer in enumerate(net):
+                    add(f"{prefix}{kind}.{t}.{k}.weight", layer.weight)
+                    add(f"{prefix}{kind}.{t}.{k}.bias", layer.bias)
+
+    add_graphnet("encoder.encoder.", encoder.encoder)
+    if hasattr(encoder, "mix_layer"):
+        add("encoder.mix_layer.weight", encoder.mix_layer.weight)
+        if encoder.mix_layer.bias is not None:
+            add("encoder.mix_layer.bias", encoder.mix_layer.bias)
+    add("decoder.linear.weight", decoder.linear.weight)
+    add("decoder.linear.bias", decoder.linear.bias)
+    add_graphnet("decoder.decoder.", decoder.decoder)
+    return out
+
+
+def layout_size(layout) -> int:
+    return sum(int(np.prod(s)) for _, s in layout.values())
+
+
+def allreduce_flat_(grad: torch.Tensor, group=None) -> torch.Tensor:
+    """The path's only collective: sum the flat gradient buffer over the data-parallel ranks."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=group)
+    return grad
+
+
+# --------------------------------------------------------------------------------------------------
+# the fused step
+# --------------------------------------------------------------------------------------------------
+class GNNAETrainer:
+    """One optimisation step per call, on the caller's CUDA device.
+
+    >>> tr = GNNAETrainer(encoder, decoder, batch_size=4096)
+    >>> loss = tr.step(x_host_pinned)          # float; H2D copy, graph replay, all-reduce, Adam, D2H of the loss
+
+    Supported latent maps: 'mean', the GLOBAL_MIX and LOCAL_MIX spellings.  'max'/'min', ``normalize_output``,
+    dropout and batch-norm go through the nn.Module path (autograd) instead.
+    """
+
+    def __init__(self, encoder, decoder, batch_size: int, *, lr: float = 1e-5, betas=(0.9, 0.999), eps: float = 1e-8,
+                 l1_lambda: float = 1e-8, l2_lambda: float = 0.0, loss_norm_choice: str = "cartesian",
+                 jet_features_weight: float = 1.0, chamfer_mode: str = "intended", encoder_metric: str = "euclidean",
+                 decoder_metric: str = "euclidean", process_group=None, use_cuda_graph: bool = True):
+        self.enc, self.dec = encoder, decoder
+        g_e, g_d = encoder.encoder, decoder.decoder
+        dev = next(encoder.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("GNNAETrainer needs the models on a CUDA device (there is no CPU fallback)")
+        if g_e.batch_norm or g_d.batch_norm or g_e.dropout_p > 0 or g_d.dropout_p > 0 or decoder.normalize_output:
+            raise NotImplementedError("batch_norm / dropout / normalize_output are not part of the fused step")
+        canon = encoder.latent_map.lower().replace(" ", "_")
+        if canon in GLOBAL_MIX:
+            self.map = "global"
+        elif canon in LOCAL_MIX:
+            self.map = "local"
+        elif canon in ("max", "min"):
+            raise NotImplementedError("latent_map 'max'/'min' is served by the nn.Module path only")
+        else:
+            self.map = "mean"
+        if chamfer_mode == "reference" and jet_features_weight == 0:
+            raise UnboundLocalError("jet_loss referenced before assignment (reference chamfer_loss.py:42)")
+        self.dev, self.B, self.N = dev, int(batch_size), encoder.num_nodes
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.l1, self.l2 = float(l1_lambda), float(l2_lambda)
+        self.wc, self.wj = (0.0, 1.0) if chamfer_mode == "reference" else (1.0, float(jet_features_weight))
+        self.norm_choice = loss_norm_choice
+        self.group = process_group
+        self.step_count = 0
+        self.lib = _lib.load()
+
+        # ---- flat parameter / gradient / moment buffers; modules re-homed as views ----
+        self.layout = flat_layout(encoder, decoder)
+        n = layout_size(self.layout)
+        self.flat = torch.empty(n, device=dev, dtype=torch.float32)
+        self.grad = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.exp_avg = torch.zeros(n, device=dev, dtype=torch.float32)
+        self.exp_avg_sq = torch.zeros(n, device=dev, dtype=torch.float32)
+        named = OrderedDict([("encoder." + k, p) for k, p in encoder.named_parameters()] +
+                            [("decoder." + k, p) for k, p in decoder.named_parameters()])
+        assert set(named) == set(self.layout), "flat layout does not cover the models' parameters"
+        n_e = g_e.num_flat_params
+        g_e.flatten_parameters(self.flat[:n_e])
+        with torch.no_grad():
+            for name, (off, shape) in self.layout.items():
+                p = named[name]
+                seg = self.flat[off:off + p.numel()].view(shape)
+                if p.data_ptr() != seg.data_ptr():
+                    seg.copy_(p.detach().to(torch.float32))
+                    p.data = seg
+                p.grad = self.grad[off:off + p.numel()].view(shape)
+        off_d = self.layout["decoder.decoder.edge_net.0.0.weight"][0]
+        g_d._flat = self.flat[off_d:off_d + g_d.num_flat_params]
+        g_d._step_offsets, o = [], 0
+        for t in range(g_d.num_mps):
+            c = sum(p.numel() for p in g_d.step_parameters(t))
+            g_d._step_offsets.append((o, c))
+            o += c
+        assert g_e._flat_ok() and g_d._flat_ok()
+
+        # ---- activations ----
+        B, N = self.B, self.N
+        f32 = dict(device=dev, dtype=torch.float32)
+        self.F = encoder.input_node_size
+        self.x = torch.zeros((B, N, self.F), **f32)
+        self.enc_steps = self._plan_graphnet(g_e, 0, self.F, encoder_metric)
+        self.dec_steps = self._plan_graphnet(g_d, off_d, decoder.node_sizes[0][0], decoder_metric)
+        self.enc_out_w = g_e.output_node_size
+        self.latent_w = encoder.latent_node_size
+        self.h0 = decoder.node_sizes[0][0]
+        zshape = (B, N * self.latent_w) if self.map == "local" else (B, self.latent_w)
+        self.latent = torch.empty(zshape, **f32)
+        self.dlatent = torch.empty(zshape, **f32)
+        self.dec_in = torch.empty((B, N, self.h0), **f32)
+        self.d_dec_in = torch.empty((B, N, self.h0), **f32)
+        self.d_enc_out = torch.empty((B, N, self.enc_out_w), **f32)
+        self.dx = torch.zeros((B, N, self.F), **f32)
+        self.recon = self.dec_steps[-1]["out"]
+        self.dp = torch.empty_like(self.recon)
+        self.jet_terms = torch.empty((B, 2), **f32)
+        self.stats = torch.zeros(8, **f32)     # [chamfer, jet, wc*chamfer + wj*jet, sum|p|, sum p^2]
+        self.stats_host = torch.zeros(8, dtype=torch.float32).pin_memory()
+        ws = max([self.lib.gj_mp_step_bwd_workspace(s["desc"]) for s in self.enc_steps + self.dec_steps] +
+                 [self.lib.gj_linear_bwd_workspace(B * N, max(self.latent_w, self.enc_out_w), max(self.h0, self.latent_w)),
+                  self.lib.gj_linear_bwd_workspace(B, max(self.latent_w, N * self.enc_out_w), max(N * self.h0, self.latent_w)),
+                  self.lib.gj_param_norms_workspace(n), 16])
+        self.ws_bytes = int(ws)
+        self.ws = torch.empty((self.ws_bytes + 3) // 4, **f32)
+        self.graph = None
+        self.use_graph = use_cuda_graph
+        self.launches_per_step = None
+
+    def _plan_graphnet(self, g, flat_off, in_width, metric):
+        steps, off, width_in = [], flat_off, in_width
+        B, N = self.B, self.N
+        for t in range(g.num_mps):
+            cfg = g.step_config(t, metric)
+            _, H, ew, nw, alpha, mid, prec = cfg
+            desc = _lib.make_desc(B, N, H, ew, nw, alpha, mid, prec, h_ld=width_in, h_cols=min(width_in, H))
+            count = self.lib.gj_mp_param_count(desc)
+            assert count == sum(p.numel() for p in g.step_parameters(t))
+            steps.append(dict(desc=desc, off=off, count=count,
+                              out=torch.empty((B, N, nw[-1]), device=self.dev, dtype=torch.float32),
+                              e=torch.empty((B, N, ew[-1]), device=self.dev, dtype=torch.float32),
+                              din=None))
+            off += count
+            width_in = nw[-1]
+        # gradient w.r.t. each step's input (the first step's input gradient is produced by the kernel but unused)
+        for t in range(1, g.num_mps):
+            steps[t]["din"] = torch.empty_like(steps[t - 1]["out"])
+        return steps
+
+    # ---- the launch sequence ------------------------------------------------------------------------
+    def _fwd(self, st):
+        lib, P = self.lib, self.flat.data_ptr()
+        B, N = self.B, self.N
+        h = self.x
+        for s in self.enc_steps:
+            ops.raw_mp_fwd(s["desc"], h.data_ptr(), P + 4 * s["off"], s["out"].data_ptr(), s["e"].data_ptr(), st)
+            h = s["out"]
+        L = self.layout
+        if self.map == "mean":
+            _lib.check(lib.gj_latent_mean_fwd(B, N, self.enc_out_w, h.data_ptr(), self.latent.data_ptr(), st), "latent_mean_fwd")
+        elif self.map == "global":
+            _lib.check(lib.gj_linear_fwd(B, N * self.enc_out_w, self.latent_w, h.data_ptr(),
+                                         P + 4 * L["encoder.mix_layer.weight"][0], None, self.latent.data_ptr(), st), "mix fwd")
+        else:
+            _lib.check(lib.gj_linear_fwd(B * N, self.enc_out_w, self.latent_w, h.data_ptr(),
+                                         P + 4 * L["encoder.mix_layer.weight"][0], P + 4 * L["encoder.mix_layer.bias"][0],
+                                         self.latent.data_ptr(), st), "mix fwd")
+        ops.LAUNCHES["count"] += 1
+        wl, bl = P + 4 * L["decoder.linear.weight"][0], P + 4 * L["decoder.linear.bias"][0]
+        if self.map == "local":
+            _lib.check(lib.gj_linear_fwd(B * N, self.latent_w, self.h0, self.latent.data_ptr(), wl, bl, self.dec_in.data_ptr(), st), "dec linear fwd")
+        else:
+            _lib.check(lib.gj_linear_fwd(B, self.latent_w, N * self.h0, self.latent.data_ptr(), wl, bl, self.dec_in.data_ptr(), st), "dec linear fwd")
+        ops.LAUNCHES["count"] += 1
+        h = self.dec_in
+        for s in self.dec_steps:
+            ops.raw_mp_fwd(s["desc"], h.data_ptr(), P + 4 * s["off"], s["out"].data_ptr(), s["e"].data_ptr(), st)
+            h = s["out"]
+
+    def _loss_and_bwd(self, st):
+        lib, P, G = self.lib, self.flat.data_ptr(), self.grad.data_ptr()
+        B, N, L = self.B, self.N, self.layout
+        D = self.recon.shape[-1]
+        _lib.check(lib.gj_chamfer_fwd_bwd(B, N, N, D, _norm_id(self.recon, self.norm_choice), self.wc, self.wj,
+                                          self.recon.data_ptr(), self.x.data_ptr(), self.jet_terms.data_ptr(),
+                                          self.stats.data_ptr(), self.dp.data_ptr(), st), "chamfer")
+        _lib.check(lib.gj_param_norms(P, self.flat.numel(), self.stats.data_ptr() + 12, self.ws.data_ptr(), self.ws_bytes, st), "norms")
+        ops.LAUNCHES["count"] += 4
+        # decoder GraphNet, last step first
+        g = self.dp
+        for t in reversed(range(len(self.dec_steps))):
+            s = self.dec_steps[t]
+            hin = self.dec_in if t == 0 else self.dec_steps[t - 1]["out"]
+            din = self.d_dec_in if t == 0 else s["din"]
+            ops.raw_mp_bwd(s["desc"], hin.data_ptr(), s["e"].data_ptr(), P + 4 * s["off"], g.data_ptr(), din.data_ptr(),
+                           G + 4 * s["off"], self.ws.data_ptr(), self.ws_bytes, st)
+            g = din
+        wl = L["decoder.linear.weight"][0]
+        bl = L["decoder.linear.bias"][0]
+        if self.map == "local":
+            _lib.check(lib.gj_linear_bwd(B * N, self.latent_w, self.h0, self.latent.data_ptr(), P + 4 * wl, g.data_ptr(),
+                                         self.dlatent.data_ptr(), G + 4 * wl, G + 4 * bl, self.ws.data_ptr(), self.ws_bytes, st), "dec linear bwd")
+        else:
+            _lib.check(lib.gj_linear_bwd(B, self.latent_w, N * self.h0, self.latent.data_ptr(), P + 4 * wl, g.data_ptr(),
+                                         self.dlatent.data_ptr(), G + 4 * wl, G + 4 * bl, self.ws.data_ptr(), self.ws_bytes, st), "dec linear bwd")
+        ops.LAUNCHES["count"] += 3
+        y = self.enc_steps[-1]["out"]
+        if self.map == "mean":
+            _lib.check(lib.gj_latent_mean_bwd(B, N, self.enc_out_w, self.dlatent.data_ptr(), self.d_enc_out.data_ptr(), st), "latent_mean_bwd")
+            ops.LAUNCHES["count"] += 1
+        elif self.map == "global":
+            wm = L["encoder.mix_layer.weight"][0]
+            _lib.check(lib.gj_linear_bwd(B, N * self.enc_out_w, self.latent_w, y.data_ptr(), P + 4 * wm, self.dlatent.data_ptr(),
+                                         self.d_enc_out.data_ptr(), G + 4 * wm, None, self.ws.data_ptr(), self.ws_bytes, st), "mix bwd")
+            ops.LAUNCHES["count"] += 3
+        else:
+            wm, bm = L["encoder.mix_layer.weight"][0], L["encoder.mix_layer.bias"][0]
+            _lib.check(lib.gj_linear_bwd(B * N, self.enc_out_w, self.latent_w, y.data_ptr(), P + 4 * wm, self.dlatent.data_ptr(),
+                                         self.d_enc_out.data_ptr(), G + 4 * wm, G + 4 * bm, self.ws.data_ptr(), self.ws_bytes, st), "mix bwd")
+            ops.LAUNCHES["count"] += 3
+        g = self.d_enc_out
+        for t in reversed(range(len(self.enc_steps))):
+            s = self.enc_steps[t]
+            hin = self.x if t == 0 else self.enc_steps[t - 1]["out"]
+            din = self.dx if t == 0 else s["din"]
+            ops.raw_mp_bwd(s["desc"], hin.data_ptr(), s["e"].data_ptr(), P + 4 * s["off"], g.data_ptr(), din.data_ptr(),
+                           G + 4 * s["off"], self.ws.data_ptr(), self.ws_bytes, st)
+            g = din
+
+    def _fwd_bwd(self):
+        st = torch.cuda.current_stream().cuda_stream
+        self._fwd(st)
+        self._loss_and_bwd(st)
+
+    # ---- public API ---------------------------------------------------------------------------------
+    def forward_only(self, x: torch.Tensor):
+        """encoder + decoder forward on a (B,N,F) batch (host or device); returns (latent, recon) device views."""
+        self.x.copy_(x.reshape(self.x.shape), non_blocking=True)
+        self._fwd(torch.cuda.current_stream().cuda_stream)
+        return self.latent, self.recon
+
+    def load_batch(self, x: torch.Tensor) -> None:
+        """Host (ideally pinned) or device batch -> the step's resident input buffer."""
+        self.x.copy_(x.reshape(self.x.shape), non_blocking=True)
+
+    def compute_gradients(self) -> None:
+        """forward + loss + backward on the resident batch; the flat gradient buffer holds d(sum loss)/dp."""
+        if not self.use_graph:
+            self._fwd_bwd()
+            return
+        if self.graph is None:
+            before = ops.LAUNCHES["count"]
+            self._fwd_bwd()                      # eager warm-up: loads the kernels outside the capture
+            self.launches_per_step = ops.LAUNCHES["count"] - before + 1   # + Adam
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._fwd_bwd()
+            ops.LAUNCHES["count"] -= self.launches_per_step - 1    # the capture pass launched nothing
+            self.graph = g
+        self.graph.replay()
+        ops.LAUNCHES["count"] += self.launches_per_step - 1
+
+    def apply_gradients(self) -> None:
+        allreduce_flat_(self.grad, self.group)
+        self.step_count += 1
+        ops.adam_step_flat_(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr, self.betas,
+                            self.eps, 1.0, self.l1, self.l2)
+
+    def step_async(self, x: torch.Tensor) -> None:
+        self.load_batch(x)
+        self.compute_gradients()
+        self.stats_host.copy_(self.stats, non_blocking=True)
+        self.apply_gradients()
+
+    def loss_from_stats(self, stats) -> float:
+        """train.py:376-384: batch loss = chamfer value + l1_lambda * sum|p| + l2_lambda * sum p^2 (this rank's shard)."""
+        v = float(stats[2])
+        if self.l1 > 0:
+            v += self.l1 * float(stats[3])
+        if self.l2 > 0:
+            v += self.l2 * float(stats[4])
+        return v
+
+    def step(self, x: torch.Tensor) -> float:
+        """One optimisation step; returns this rank's batch loss (a device->host read, like train.py:77)."""
+        self.step_async(x)
+        torch.cuda.current_stream().synchronize()
+        return self.loss_from_stats(self.stats_host)
+
+    def flat_gradient(self) -> torch.Tensor:
+        return self.grad
+
+    def named_gradients(self):
+        return OrderedDict((name, self.grad[off:off + int(np.prod(shape))].view(shape))
+                           for name, (off, shape) in self.layout.items())

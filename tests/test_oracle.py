@@ -125,3 +125,27 @@ def test_adam_matches_torch():
         tp.grad = torch.from_numpy(g.copy())
         opt.step()
     assert np.abs(params["w"] - tp.detach().numpy()).max() < 1e-14
+
+
+@pytest.mark.parametrize("name", ["default_n30", "trainsh_n30", "local_mix_sp_n8", "global_mix_n8", "max_n5", "mink_n6",
+                                  "broadcast_crop_n7", "n1"])
+def test_torch_port_matches_reference(name):
+    """oracle/torch_port.py (the CPU-baseline restatement timed by bench.py) against the reference's outputs."""
+    import torch
+    import torch_port as TP
+    case = CASES[name]
+    g = np.load(os.path.join(GOLDEN, f"{name}.npz"))
+    ep, dp = make_params(case)
+    x = torch.from_numpy(make_input(case))
+    tep, tdp = TP.make_params(ep, torch.float64), TP.make_params(dp, torch.float64)
+    loss, z, y = TP.loss_fn(x, tep, tdp, case["enc"], case["dec"], metric=case["metric"],
+                            loss_norm_choice=case["loss_norm_choice"], jet_features_weight=case["jet_features_weight"],
+                            l1_lambda=case["l1_lambda"])
+    loss.backward()
+    assert rel(z.detach().numpy(), g["latent"]) < 1e-12
+    assert rel(y.detach().numpy(), g["recon"]) < 1e-12
+    assert abs(loss.item() - g["loss_intended"]) <= 1e-11 * abs(g["loss_intended"])
+    eg = np.concatenate([tep[k].grad.numpy().ravel() for k in sorted(ep)])
+    dg = np.concatenate([tdp[k].grad.numpy().ravel() for k in sorted(dp)])
+    tol = 1e-11 if case["store64"] else 2e-7
+    assert rel(eg, g["enc_grad"]) < tol and rel(dg, g["dec_grad"]) < tol
