@@ -27,14 +27,21 @@ int gj_num_sms() {
 }
 
 // launchers implemented in the kernel translation units
-int gj_mp_fwd_simt(const gj_mp_desc*, const float*, const float*, float*, float*, cudaStream_t);
-size_t gj_mp_bwd_simt_workspace(const gj_mp_desc*);
-int gj_mp_bwd_simt(const gj_mp_desc*, const float*, const float*, const float*, const float*, float*, float*, void*, size_t,
+int gj_node_pre_fwd(const MPLayout&, const float*, const float*, float*, cudaStream_t);
+size_t gj_node_pre_bwd_ws_floats(const MPLayout&);
+int gj_node_pre_bwd(const MPLayout&, const float*, const float*, const float*, float*, float*, float*, cudaStream_t);
+int gj_node_post_fwd(const MPLayout&, const float*, const float*, const float*, float*, cudaStream_t);
+size_t gj_node_post_bwd_ws_floats(const MPLayout&);
+int gj_node_post_bwd(const MPLayout&, const float*, const float*, const float*, const float*, float*, float*, float*, float*,
+                     cudaStream_t);
+int gj_edge_grid(int);
+int gj_edge_fwd_simt(MPLayout, const float*, const float*, const float*, float*, cudaStream_t);
+int gj_edge_bwd_simt(MPLayout, const float*, const float*, const float*, const float*, float*, float*, float*, float*,
+                     cudaStream_t);
+int gj_edge_fwd_tc(MPLayout, const float*, const float*, const float*, float*, cudaStream_t);
+size_t gj_edge_bwd_tc_ws_floats(const MPLayout&);
+int gj_edge_bwd_tc(MPLayout, const float*, const float*, const float*, const float*, float*, float*, float*, float*,
                    cudaStream_t);
-int gj_mp_fwd_tc(const gj_mp_desc*, const float*, const float*, float*, float*, cudaStream_t);
-size_t gj_mp_bwd_tc_workspace(const gj_mp_desc*);
-int gj_mp_bwd_tc(const gj_mp_desc*, const float*, const float*, const float*, const float*, float*, float*, void*, size_t,
-                 cudaStream_t);
 int gj_umma_selftest_launch(int, int, int, int, int, const float*, const float*, float*, cudaStream_t);
 int gj_chamfer_launch(int, int, int, int, int, float, float, const float*, const float*, float*, float*, float*, cudaStream_t);
 int gj_linear_fwd_launch(int, int, int, const float*, const float*, const float*, float*, cudaStream_t);
@@ -59,28 +66,87 @@ size_t gj_mp_param_count(const gj_mp_desc* d) {
   return (size_t)L.nparams;
 }
 
-int gj_mp_step_fwd(const gj_mp_desc* d, const float* h, const float* params, float* h_out, float* e_out, void* stream) {
+static size_t align_floats(size_t n) { return (n + 63) & ~(size_t)63; }   // keep every region 256-byte aligned
+
+struct StepWs {   // offsets in floats
+  size_t pq, dpq, de, part, total;
+};
+
+static bool use_tc(const MPLayout& L, int precision) { return precision == GJ_PREC_BF16 && L.Le > 1; }
+
+static StepWs plan_ws(const MPLayout& L, int precision, bool backward) {
+  StepWs w; size_t off = 0;
+  const size_t rows = (size_t)L.B * L.N;
+  w.pq = off; off += align_floats(rows * 2 * L.E0p);
+  w.dpq = w.de = w.part = off;
+  if (backward) {
+    w.dpq = off; off += align_floats(rows * 2 * L.E0p);
+    w.de = off; off += align_floats(rows * L.EL);
+    size_t p = gj_node_post_bwd_ws_floats(L);
+    size_t q = gj_node_pre_bwd_ws_floats(L);
+    size_t r = use_tc(L, precision) ? gj_edge_bwd_tc_ws_floats(L) : (size_t)gj_edge_grid(L.B) * L.pV[0];
+    if (q > p) p = q;
+    if (r > p) p = r;
+    w.part = off; off += align_floats(p);
+  }
+  w.total = off;
+  return w;
+}
+
+size_t gj_mp_step_fwd_workspace(const gj_mp_desc* d) {
+  MPLayout L; const char* why;
+  if (gj_fill_arch(d, &L, &why)) return 0;
+  return plan_ws(L, d->precision, false).total * sizeof(float);
+}
+
+int gj_mp_step_fwd(const gj_mp_desc* d, const float* h, const float* params, float* h_out, float* e_out, void* workspace,
+                   size_t workspace_bytes, void* stream) {
   g_err[0] = 0;
-  if (!d || !h || !params || !h_out) { gj_set_error("gj_mp_step_fwd: null pointer"); return GJ_ERR_INVALID; }
-  if (d->precision == GJ_PREC_FP32) return gj_mp_fwd_simt(d, h, params, h_out, e_out, (cudaStream_t)stream);
-  if (d->precision == GJ_PREC_BF16) return gj_mp_fwd_tc(d, h, params, h_out, e_out, (cudaStream_t)stream);
-  gj_set_error("gj_mp_step_fwd: unknown precision %d", d->precision);
-  return GJ_ERR_INVALID;
+  if (!d || !h || !params || !h_out || !e_out || !workspace) { gj_set_error("gj_mp_step_fwd: null pointer"); return GJ_ERR_INVALID; }
+  if (d->precision != GJ_PREC_FP32 && d->precision != GJ_PREC_BF16) { gj_set_error("gj_mp_step_fwd: unknown precision %d", d->precision); return GJ_ERR_INVALID; }
+  MPLayout L; const char* why;
+  int rc = gj_fill_arch(d, &L, &why);
+  if (rc) { gj_set_error("gj_mp_step_fwd: %s", why); return rc; }
+  if (L.B == 0) return GJ_OK;
+  const StepWs w = plan_ws(L, d->precision, false);
+  if (workspace_bytes < w.total * sizeof(float)) { gj_set_error("gj_mp_step_fwd: workspace too small"); return GJ_ERR_WORKSPACE; }
+  float* ws = (float*)workspace;
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = gj_node_pre_fwd(L, h, params, ws + w.pq, st))) return rc;
+  rc = use_tc(L, d->precision) ? gj_edge_fwd_tc(L, h, ws + w.pq, params, e_out, st)
+                               : gj_edge_fwd_simt(L, h, ws + w.pq, params, e_out, st);
+  if (rc) return rc;
+  return gj_node_post_fwd(L, e_out, h, params, h_out, st);
 }
 
 size_t gj_mp_step_bwd_workspace(const gj_mp_desc* d) {
-  if (!d) return 0;
-  return d->precision == GJ_PREC_BF16 ? gj_mp_bwd_tc_workspace(d) : gj_mp_bwd_simt_workspace(d);
+  MPLayout L; const char* why;
+  if (gj_fill_arch(d, &L, &why)) return 0;
+  return plan_ws(L, d->precision, true).total * sizeof(float);
 }
 
 int gj_mp_step_bwd(const gj_mp_desc* d, const float* h, const float* e, const float* params, const float* dh_out, float* dh,
                    float* dparams, void* workspace, size_t workspace_bytes, void* stream) {
   g_err[0] = 0;
   if (!d || !h || !e || !params || !dh_out || !dh || !dparams || !workspace) { gj_set_error("gj_mp_step_bwd: null pointer"); return GJ_ERR_INVALID; }
-  if (d->precision == GJ_PREC_FP32) return gj_mp_bwd_simt(d, h, e, params, dh_out, dh, dparams, workspace, workspace_bytes, (cudaStream_t)stream);
-  if (d->precision == GJ_PREC_BF16) return gj_mp_bwd_tc(d, h, e, params, dh_out, dh, dparams, workspace, workspace_bytes, (cudaStream_t)stream);
-  gj_set_error("gj_mp_step_bwd: unknown precision %d", d->precision);
-  return GJ_ERR_INVALID;
+  if (d->precision != GJ_PREC_FP32 && d->precision != GJ_PREC_BF16) { gj_set_error("gj_mp_step_bwd: unknown precision %d", d->precision); return GJ_ERR_INVALID; }
+  MPLayout L; const char* why;
+  int rc = gj_fill_arch(d, &L, &why);
+  if (rc) { gj_set_error("gj_mp_step_bwd: %s", why); return rc; }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (L.B == 0) { cudaMemsetAsync(dparams, 0, (size_t)L.nparams * sizeof(float), st); return GJ_OK; }
+  const StepWs w = plan_ws(L, d->precision, true);
+  if (workspace_bytes < w.total * sizeof(float)) { gj_set_error("gj_mp_step_bwd: workspace too small"); return GJ_ERR_WORKSPACE; }
+  float* ws = (float*)workspace;
+  // node MLP adjoint: de, node-path dh, node parameter gradients
+  if ((rc = gj_node_post_bwd(L, e, h, params, dh_out, ws + w.de, dh, dparams, ws + w.part, st))) return rc;
+  // recompute P|Q, then the edge adjoint: dP|dQ, distance-path dh, edge parameter gradients
+  if ((rc = gj_node_pre_fwd(L, h, params, ws + w.pq, st))) return rc;
+  rc = use_tc(L, d->precision) ? gj_edge_bwd_tc(L, h, ws + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.part, st)
+                               : gj_edge_bwd_simt(L, h, ws + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.part, st);
+  if (rc) return rc;
+  // first-layer projections' adjoint: dh += Wa^T dP + Wb^T dQ, dWa, dWb, db0
+  return gj_node_pre_bwd(L, h, params, ws + w.dpq, dh, dparams, ws + w.part, st);
 }
 
 int gj_chamfer_fwd_bwd(int32_t batch, int32_t np_, int32_t nq, int32_t dim, int32_t norm, float w_chamfer, float w_jet,

@@ -1,30 +1,21 @@
-// bf16 (GJ_PREC_BF16) message-passing step on tcgen05 tensor cores with TMEM accumulators.
+// bf16 (GJ_PREC_BF16) edge kernels on tcgen05 tensor cores with TMEM accumulators.
 //
 // Work decomposition: a CTA holds NWG independent warpgroups (128 threads = 128 TMEM lanes each).  Every
-// warpgroup walks whole jets on its own: node-level work and all epilogues on its CUDA cores, the dense edge
-// layers l >= 1 as tcgen05.mma (M = 128 edge rows = 4 i's x 32 j's, N = layer width, K = previous width) issued
-// by one elected thread, accumulator in the warpgroup's private TMEM columns.  While one warpgroup runs an
-// epilogue, the other's MMAs occupy the tensor pipe.  Edge activations never leave the SM: bf16 operands in
-// shared memory (interleaved layout, see umma.cuh), fp32 accumulators in TMEM, sum over j by warp shuffles.
-// Replaces reference models/graphnet.py:154-168 and its autograd adjoint.
-#include "mp_helpers.cuh"
+// warpgroup walks whole jets on its own: for a jet the N x N pair set is visited as (32 i's) x (32 j's) blocks,
+// each block as tiles of 128 edge rows (4 i's x 32 j's, j on the lanes).  Per tile:
+//   a0 = leaky(P_i + Q_j + wd d_ij)            CUDA cores, fp32 -> bf16 A operand in shared memory
+//   a_l = leaky(W_l a_{l-1} + b_l), l >= 1     tcgen05.mma (M = 128 rows, N = layer width, K = previous width)
+//                                              issued by one elected thread, accumulator in the warpgroup's TMEM
+//                                              columns, epilogue tcgen05.ld -> bias + LeakyReLU -> bf16 -> smem
+//   e_i = sum_j a_last                         warp shuffles (fp32)
+// While one warpgroup runs an epilogue, the other's MMAs occupy the tensor pipe.  Edge activations never leave
+// the SM.  Replaces the edge part of reference models/graphnet.py:154-168 and its autograd adjoint.
+#include "gj_common.cuh"
 #include "umma.cuh"
 
 namespace {
 
 using namespace umma;
-
-struct TCPlan {
-  int nwg;
-  int o_bar, o_tmem_slot;
-  int o_wT[GJ_MAX_LAYERS];  // bf16 interleaved edge weights, layers >= 1 (bytes from smem base)
-  int o_shared_f32;         // float region shared by all warpgroups (small fp32 weights)
-  int wg_base, wg_stride;   // per-warpgroup region
-  int w_act[GJ_MAX_LAYERS]; // bf16 activation buffers inside the warpgroup region (bytes)
-  int w_f32;                // float region inside the warpgroup region
-  int tmem_cols_per_wg, tmem_cols_total;
-  int smem_bytes;
-};
 
 struct Carver {
   int off = 0;
@@ -33,23 +24,31 @@ struct Carver {
 
 int next_pow2_cols(int c) { int p = 32; while (p < c) p <<= 1; return p; }
 
+struct TCPlan {
+  int nwg;
+  int o_bar, o_tmem_slot;
+  int o_wT[GJ_MAX_LAYERS];  // bf16 interleaved edge weights, layers >= 1 (bytes from smem base)
+  int o_shared_f32;         // float region shared by all warpgroups (biases, wd)
+  int wg_base, wg_stride;   // per-warpgroup region
+  int w_act[GJ_MAX_LAYERS]; // bf16 activation buffers inside the warpgroup region (bytes)
+  int w_f32;                // float region inside the warpgroup region
+  int tmem_cols_per_wg, tmem_cols_total;
+  int smem_bytes;
+};
+
 // Fills the float offsets of L relative to the two float regions and the byte plan T.
 void plan_tc_fwd(MPLayout* L, TCPlan* T, int nwg) {
   L->R = 128; L->Rs = 0;
   T->nwg = nwg;
   Carver c;
-  for (int l = 0; l < L->Le; ++l) L->o_bE[l] = c.take(L->Ep[l]);
-  L->o_wa = c.take(L->E0p * L->Hs);
-  L->o_wb = c.take(L->E0p * L->Hs);
+  for (int l = 1; l < L->Le; ++l) L->o_bE[l] = c.take(L->Ep[l]);
   L->o_wd = c.take(L->E0p);
-  for (int m = 0; m < L->Ln; ++m) { L->o_V[m] = c.take(L->O[m] * L->Is[m]); L->o_c[m] = c.take(L->O[m]); }
   Carver w;
-  L->o_h = w.take(L->N * L->Hs);
-  L->o_Q = w.take(L->N * L->E0s);
+  L->o_h = w.take(GJ_IB * L->Hs);
+  L->o_hj = w.take(32 * L->Hs);
   L->o_P = w.take(GJ_IB * L->E0s);
+  L->o_Q = w.take(32 * L->E0s);
   L->o_e = w.take(GJ_IB * L->ELs);
-  L->o_node[0] = w.take(GJ_IB * L->Ws);
-  L->o_node[1] = w.take(GJ_IB * L->Ws);
   int off = 0;
   T->o_bar = off; off += 64;
   T->o_tmem_slot = off; off += 64;
@@ -69,6 +68,12 @@ void plan_tc_fwd(MPLayout* L, TCPlan* T, int nwg) {
   T->tmem_cols_total = next_pow2_cols(T->tmem_cols_per_wg * nwg);
 }
 
+__device__ void stage_small(const MPLayout& L, const float* __restrict__ params, float* smf, int tid, int nthr) {
+  for (int l = 1; l < L.Le; ++l)
+    for (int c = tid; c < L.Ep[l]; c += nthr) smf[L.o_bE[l] + c] = c < L.E[l] ? __ldg(params + L.pb[l] + c) : 0.f;
+  for (int c = tid; c < L.E0p; c += nthr) smf[L.o_wd + c] = c < L.E[0] ? __ldg(params + L.pW[0] + c * L.K[0] + 2 * L.H) : 0.f;
+}
+
 // bf16 interleaved staging of edge weights l >= 1 as the K-major B operand (N = out feature rows, K = in).
 __device__ void stage_edge_weights_bf16(const MPLayout& L, const TCPlan& T, const float* __restrict__ params, uint8_t* smem,
                                         int tid, int nthr) {
@@ -83,6 +88,19 @@ __device__ void stage_edge_weights_bf16(const MPLayout& L, const TCPlan& T, cons
   }
 }
 
+// rows [r0, r0 + 32) of h (zero padded) and of the P or Q half of PQ, by one warpgroup
+__device__ void wg_load_block(const MPLayout& L, const float* __restrict__ hjet, const float* __restrict__ pqjet, int half,
+                              int r0, float* sh, float* spq, int t) {
+  for (int idx = t; idx < 32 * L.H; idx += 128) {
+    int n = idx / L.H, k = idx - n * L.H;
+    sh[n * L.Hs + k] = (r0 + n < L.N && k < L.cols) ? __ldg(hjet + (size_t)(r0 + n) * L.ld + k) : 0.f;
+  }
+  for (int idx = t; idx < 32 * L.E0p; idx += 128) {
+    int n = idx / L.E0p, c = idx - n * L.E0p;
+    spq[n * L.E0s + c] = (r0 + n < L.N) ? __ldg(pqjet + (size_t)(r0 + n) * 2 * L.E0p + half * L.E0p + c) : 0.f;
+  }
+}
+
 // D[128 x N](tmem) = A[128 x K](smem, K-major, 128 rows) * W[N x K]^T (smem, K-major, N rows)
 __device__ __forceinline__ void issue_layer_mma(uint32_t d_tmem, uint32_t a_saddr, uint32_t w_saddr, int N, int K) {
   const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
@@ -93,10 +111,33 @@ __device__ __forceinline__ void issue_layer_mma(uint32_t d_tmem, uint32_t a_sadd
   }
 }
 
+// first edge layer of one tile on CUDA cores: thread t owns row (i = it*4 + wq, j = lane); returns d_ij
+__device__ __forceinline__ float tc_layer0(const MPLayout& L, const float* sm_h, const float* sm_hj, const float* sm_P,
+                                           const float* sm_Q, const float* wd, uint8_t* a0, int il, int lane, int t) {
+  const float* hi = sm_h + il * L.Hs;
+  const float* hj = sm_hj + lane * L.Hs;
+  float d = 0.f;
+  for (int k = 0; k < L.H; ++k) {
+    float x = hj[k] - hi[k] + GJ_EPS;
+    float s = (L.mink && k > 0) ? -1.f : 1.f;
+    d = fmaf(s * x, x, d);
+  }
+  const float* P = sm_P + il * L.E0s;
+  const float* Q = sm_Q + lane * L.E0s;
+  for (int c0 = 0; c0 < L.E0p; c0 += 8) {
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = gj_leaky(P[c0 + q] + Q[c0 + q] + wd[c0 + q] * d, L.alpha);
+    uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    *reinterpret_cast<uint4*>(a0 + (c0 >> 3) * 2048 + t * 16) = pk;
+  }
+  return d;
+}
+
 template <int NWG>
 __global__ void __launch_bounds__(NWG * 128, 1)
-mp_fwd_tc_kernel(const MPLayout L, const TCPlan T, const float* __restrict__ h, const float* __restrict__ params,
-                 float* __restrict__ h_out, float* __restrict__ e_out) {
+edge_fwd_tc_kernel(const MPLayout L, const TCPlan T, const float* __restrict__ h, const float* __restrict__ pq,
+                   const float* __restrict__ params, float* __restrict__ e_out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int NT = NWG * 128;
   const int tid = threadIdx.x, wg = tid >> 7, t = tid & 127, wq = t >> 5, lane = t & 31;
@@ -106,7 +147,7 @@ mp_fwd_tc_kernel(const MPLayout L, const TCPlan T, const float* __restrict__ h, 
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + T.o_bar) + wg;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + T.o_tmem_slot);
 
-  gj_stage_small_weights(L, params, smf, tid, NT);
+  stage_small(L, params, smf, tid, NT);
   stage_edge_weights_bf16(L, T, params, smem, tid, NT);
   if (tid == 0) {
     for (int w = 0; w < NWG; ++w) mbar_init(reinterpret_cast<uint64_t*>(smem + T.o_bar) + w, 1);
@@ -123,56 +164,32 @@ mp_fwd_tc_kernel(const MPLayout L, const TCPlan T, const float* __restrict__ h, 
   uint32_t phase = 0;
   const int bar_id = 1 + wg;
   float* sm_h = wgf + L.o_h;
+  float* sm_hj = wgf + L.o_hj;
   float* sm_Q = wgf + L.o_Q;
   float* sm_P = wgf + L.o_P;
   float* sm_e = wgf + L.o_e;
+  const float* wd = smf + L.o_wd;
 
   for (int jet = blockIdx.x * NWG + wg; jet < L.B; jet += gridDim.x * NWG) {
-    const float* hg = h + (size_t)jet * L.N * L.ld;
-    for (int idx = t; idx < L.N * L.H; idx += 128) {
-      int n = idx / L.H, k = idx - n * L.H;
-      sm_h[n * L.Hs + k] = k < L.cols ? __ldg(hg + n * L.ld + k) : 0.f;
-    }
-    named_bar_sync(bar_id, 128);
-    gj_node_project(L, smf + L.o_wb, nullptr, sm_h, L.N, sm_Q, t, 128);
+    const float* hjet = h + (size_t)jet * L.N * L.ld;
+    const float* pqjet = pq + (size_t)jet * L.N * 2 * L.E0p;
     for (int i0 = 0; i0 < L.N; i0 += GJ_IB) {
       const int ni = min(GJ_IB, L.N - i0);
-      gj_node_project(L, smf + L.o_wa, smf + L.o_bE[0], sm_h + i0 * L.Hs, ni, sm_P, t, 128);
-      for (int idx = t; idx < GJ_IB * L.ELs; idx += 128) sm_e[idx] = 0.f;
       named_bar_sync(bar_id, 128);
-      const int nit = (ni + 3) / 4;
-      for (int it = 0; it < nit; ++it) {
-        for (int jb = 0; jb < L.Npad / 32; ++jb) {
-          // ---- first edge layer on CUDA cores: a0 = leaky(P_i + Q_j + wd d_ij) -> bf16 A operand ----
-          const int ilu = it * 4 + wq;
-          const int il = min(ilu, ni - 1);
-          const int ju = jb * 32 + lane;
-          const int j = min(ju, L.N - 1);
-          const bool valid = ilu < ni && ju < L.N;
-          {
-            const float* hi = sm_h + (i0 + il) * L.Hs;
-            const float* hj = sm_h + j * L.Hs;
-            float d = 0.f;
-            for (int k = 0; k < L.H; ++k) {
-              float x = hj[k] - hi[k] + GJ_EPS;
-              float s = (L.mink && k > 0) ? -1.f : 1.f;
-              d = fmaf(s * x, x, d);
-            }
-            const float* P = sm_P + il * L.E0s;
-            const float* Q = sm_Q + j * L.E0s;
-            const float* wd = smf + L.o_wd;
-            uint8_t* a0 = wgb + T.w_act[0];
-            for (int c0 = 0; c0 < L.E0p; c0 += 8) {
-              float v[8];
-#pragma unroll
-              for (int q = 0; q < 8; ++q) v[q] = gj_leaky(P[c0 + q] + Q[c0 + q] + wd[c0 + q] * d, L.alpha);
-              uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-              *reinterpret_cast<uint4*>(a0 + (c0 >> 3) * 2048 + t * 16) = pk;
-            }
-          }
+      wg_load_block(L, hjet, pqjet, 0, i0, sm_h, sm_P, t);
+      for (int idx = t; idx < GJ_IB * L.ELs; idx += 128) sm_e[idx] = 0.f;
+      for (int j0 = 0; j0 < L.N; j0 += 32) {
+        const int nj = min(32, L.N - j0);
+        named_bar_sync(bar_id, 128);
+        wg_load_block(L, hjet, pqjet, 1, j0, sm_hj, sm_Q, t);
+        named_bar_sync(bar_id, 128);
+        const int nit = (ni + 3) / 4;
+        for (int it = 0; it < nit; ++it) {
+          const int il = it * 4 + wq;
+          const bool valid = il < ni && lane < nj;
+          tc_layer0(L, sm_h, sm_hj, sm_P, sm_Q, wd, wgb + T.w_act[0], il, lane, t);
           fence_proxy_async();
           named_bar_sync(bar_id, 128);
-          // ---- dense edge layers on the tensor core ----
           for (int l = 1; l < L.Le; ++l) {
             if (t == 0) {
               tc_fence_after();
@@ -201,7 +218,7 @@ mp_fwd_tc_kernel(const MPLayout L, const TCPlan T, const float* __restrict__ h, 
 #pragma unroll
                 for (int q = 0; q < 16; ++q) {
                   float s = gj_warp_sum(valid ? v[q] : 0.f);
-                  if (lane == 0) sm_e[ilu * L.ELs + c0 + q] += s;
+                  if (lane == 0) sm_e[il * L.ELs + c0 + q] += s;
                 }
               }
             }
@@ -211,27 +228,11 @@ mp_fwd_tc_kernel(const MPLayout L, const TCPlan T, const float* __restrict__ h, 
           }
         }
       }
-      // ---- node MLP on [e_i | h_i] ----
-      float* bufA = wgf + L.o_node[0];
-      float* bufB = wgf + L.o_node[1];
-      const int I0 = L.EL + L.H;
-      for (int idx = t; idx < ni * I0; idx += 128) {
-        int n = idx / I0, k = idx - n * I0;
-        float v = k < L.EL ? sm_e[n * L.ELs + k] : sm_h[(i0 + n) * L.Hs + (k - L.EL)];
-        bufA[n * L.Ws + k] = v;
-        if (e_out && k < L.EL) e_out[((size_t)jet * L.N + i0 + n) * L.EL + k] = v;
-      }
       named_bar_sync(bar_id, 128);
-      for (int m = 0; m < L.Ln; ++m) {
-        gj_node_layer_fwd(L, smf, m, bufA, bufB, ni, t, 128);
-        named_bar_sync(bar_id, 128);
-        float* tp = bufA; bufA = bufB; bufB = tp;
+      for (int idx = t; idx < ni * L.EL; idx += 128) {
+        int n = idx / L.EL, c = idx - n * L.EL;
+        e_out[((size_t)jet * L.N + i0 + n) * L.EL + c] = sm_e[n * L.ELs + c];
       }
-      for (int idx = t; idx < ni * L.Hout; idx += 128) {
-        int n = idx / L.Hout, o = idx - n * L.Hout;
-        h_out[((size_t)jet * L.N + i0 + n) * L.Hout + o] = bufA[n * L.Ws + o];
-      }
-      named_bar_sync(bar_id, 128);
     }
   }
   tc_fence_before();
@@ -297,17 +298,11 @@ umma_selftest_kernel(int M, int N, int K, int a_mn, int b_mn, const float* __res
 
 int gj_num_sms();
 void gj_set_error(const char* fmt, ...);
-int gj_mp_fwd_simt(const gj_mp_desc*, const float*, const float*, float*, float*, cudaStream_t);
-size_t gj_mp_bwd_simt_workspace(const gj_mp_desc*);
-int gj_mp_bwd_simt(const gj_mp_desc*, const float*, const float*, const float*, const float*, float*, float*, void*, size_t,
-                   cudaStream_t);
+int gj_edge_grid(int);
+int gj_edge_bwd_simt(MPLayout, const float*, const float*, const float*, const float*, float*, float*, float*, float*,
+                     cudaStream_t);
 
-int gj_mp_fwd_tc(const gj_mp_desc* d, const float* h, const float* params, float* h_out, float* e_out, cudaStream_t stream) {
-  MPLayout L; const char* why;
-  int rc = gj_fill_arch(d, &L, &why);
-  if (rc) { gj_set_error("gj_mp_step_fwd: %s", why); return rc; }
-  if (L.B == 0) return GJ_OK;
-  if (L.Le == 1) return gj_mp_fwd_simt(d, h, params, h_out, e_out, stream);  // no dense edge layer: nothing for the tensor core
+int gj_edge_fwd_tc(MPLayout L, const float* h, const float* pq, const float* params, float* e_out, cudaStream_t stream) {
   for (int l = 1; l < L.Le; ++l)
     if (L.Ep[l] > 256 || L.Kp[l] > 256) { gj_set_error("gj_mp_step_fwd(bf16): edge widths above 256 unsupported"); return GJ_ERR_INVALID; }
   TCPlan T;
@@ -317,23 +312,23 @@ int gj_mp_fwd_tc(const gj_mp_desc* d, const float* h, const float* params, float
     gj_set_error("gj_mp_step_fwd(bf16): needs %d B shared memory / %d TMEM columns (limits 232448 / 512)", T.smem_bytes, T.tmem_cols_total);
     return GJ_ERR_SMEM;
   }
-  auto kern = mp_fwd_tc_kernel<NWG>;
+  auto kern = edge_fwd_tc_kernel<NWG>;
   cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T.smem_bytes);
   if (ce != cudaSuccess) { gj_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   int sms = gj_num_sms();
   int grid = (L.B + NWG - 1) / NWG; if (grid > sms) grid = sms;
-  kern<<<grid, NWG * 128, T.smem_bytes, stream>>>(L, T, h, params, h_out, e_out);
+  kern<<<grid, NWG * 128, T.smem_bytes, stream>>>(L, T, h, pq, params, e_out);
   ce = cudaGetLastError();
-  if (ce != cudaSuccess) { gj_set_error("mp_fwd_tc launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
+  if (ce != cudaSuccess) { gj_set_error("edge_fwd_tc launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   return GJ_OK;
 }
 
-size_t gj_mp_bwd_tc_workspace(const gj_mp_desc* d) { return gj_mp_bwd_simt_workspace(d); }
+size_t gj_edge_bwd_tc_ws_floats(const MPLayout& L) { return (size_t)gj_edge_grid(L.B) * L.pV[0]; }
 
-int gj_mp_bwd_tc(const gj_mp_desc* d, const float* h, const float* e, const float* params, const float* dh_out, float* dh,
-                 float* dparams, void* workspace, size_t ws_bytes, cudaStream_t stream) {
-  // Round-1 interim: the tensor-core backward is not written yet; the bf16 mode's gradient runs the fp32 SIMT kernel.
-  return gj_mp_bwd_simt(d, h, e, params, dh_out, dh, dparams, workspace, ws_bytes, stream);
+int gj_edge_bwd_tc(MPLayout L, const float* h, const float* pq, const float* params, const float* de, float* dpq, float* dh,
+                   float* dparams, float* part, cudaStream_t stream) {
+  // interim: the tensor-core backward is being written; the bf16 mode's gradient runs the fp32 SIMT kernel.
+  return gj_edge_bwd_simt(L, h, pq, params, de, dpq, dh, dparams, part, stream);
 }
 
 int gj_umma_selftest_launch(int M, int N, int K, int a_mn, int b_mn, const float* a, const float* b, float* out,

@@ -36,7 +36,8 @@ struct MPLayout {
   int o_wE[GJ_MAX_LAYERS], o_bE[GJ_MAX_LAYERS];
   int o_wa, o_wb, o_wd;
   int o_V[GJ_MAX_LAYERS], o_c[GJ_MAX_LAYERS];
-  int o_h, o_Q, o_P, o_e;
+  int o_h, o_hj, o_Q, o_P, o_e;
+  int n_edge_dpar;
   int o_act[GJ_MAX_LAYERS];
   int o_node[GJ_MAX_LAYERS + 3];
   // backward only

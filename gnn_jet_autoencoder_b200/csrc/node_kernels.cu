@@ -1,0 +1,529 @@
+// Node-level kernels of one message-passing step (fp32 SIMT, shared by both precision modes).
+//
+// Everything in reference models/graphnet.py:154-168 that is O(N) per jet -- as opposed to the O(N^2) edge MLP --
+// runs here, over all B*N node rows at once (rows are independent), so that the edge kernels hold nothing but
+// pair tiles:
+//   node_pre_fwd   : P_i = Wa h_i + b0, Q_j = Wb h_j    (the factorised first edge layer, W0 [h_i|h_j|d] =
+//                    Wa h_i + Wb h_j + wd d, column order of graphnet.py:220)
+//   node_post_fwd  : h'_i = NodeNet([e_i | h_i])          (graphnet.py:243-246, 266-268)
+//   node_post_bwd  : adjoint of node_post_fwd -> de, dh (node path), dV, dc
+//   node_pre_bwd   : dh += Wa^T dP + Wb^T dQ ; dWa, dWb, db0
+// A CTA stages R node rows at a time in shared memory and runs register-tiled small GEMMs on them; parameter
+// gradients accumulate in shared memory across the CTA's row blocks and leave as one partial per CTA
+// (deterministic fixed-order reduction afterwards).
+#include "gj_common.cuh"
+
+#define NK_THREADS 256
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------
+// register-tiled helpers on shared-memory operands (all strides multiples of 4 floats, (stride/4) odd)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float dot4(const float4& a, const float4& b, float acc) {
+  acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); return fmaf(a.w, b.w, acc);
+}
+
+// out[r][o] = epi( bias[o] + sum_k X[r][k] W[o][k] ),  r < R (even), o < Op (mult of 4), k < Kp (mult of 4).
+// EPI 0: identity; 1: leaky; 2: multiply by leaky'(aux[r][o]) (aux has stride os).
+template <int EPI>
+__device__ void nk_gemm_rows(const float* __restrict__ X, int xs, const float* __restrict__ W, int ws,
+                             const float* __restrict__ bias, float* __restrict__ out, int os, const float* __restrict__ aux,
+                             int R, int Op, int Kp, float alpha) {
+  const int half = R >> 1;
+  const int items = half * (Op >> 2);
+  for (int item = threadIdx.x; item < items; item += NK_THREADS) {
+    const int rp = item % half, oq = item / half;
+    float acc[2][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { float b = bias ? bias[oq * 4 + q] : 0.f; acc[0][q] = b; acc[1][q] = b; }
+    const float* x0 = X + rp * xs;
+    const float* x1 = X + (rp + half) * xs;
+    const float* w = W + (oq * 4) * ws;
+    for (int k = 0; k < Kp; k += 4) {
+      const float4 a0 = *reinterpret_cast<const float4*>(x0 + k);
+      const float4 a1 = *reinterpret_cast<const float4*>(x1 + k);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 wv = *reinterpret_cast<const float4*>(w + q * ws + k);
+        acc[0][q] = dot4(a0, wv, acc[0][q]);
+        acc[1][q] = dot4(a1, wv, acc[1][q]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int r = rp + i * half;
+      float4 o = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      if (EPI == 1) { o.x = gj_leaky(o.x, alpha); o.y = gj_leaky(o.y, alpha); o.z = gj_leaky(o.z, alpha); o.w = gj_leaky(o.w, alpha); }
+      if (EPI == 2) {
+        const float4 y = *reinterpret_cast<const float4*>(aux + r * os + oq * 4);
+        o.x *= gj_slope(y.x, alpha); o.y *= gj_slope(y.y, alpha); o.z *= gj_slope(y.z, alpha); o.w *= gj_slope(y.w, alpha);
+      }
+      *reinterpret_cast<float4*>(out + r * os + oq * 4) = o;
+    }
+  }
+}
+
+// dW[o][k] += sum_r G[r][o] Y[r][k] (o < O, k < K, stored unpadded with row length K at dW), db[o] += sum_r G[r][o].
+// An item (4 o x 4 k) is owned by 8 consecutive lanes that split the rows and combine by shuffles (fixed order).
+__device__ void nk_wgrad(const float* __restrict__ G, int gs, const float* __restrict__ Y, int ys, float* __restrict__ dW,
+                         float* __restrict__ db, int R, int O, int K) {
+  const int Oq = (O + 3) >> 2, Kq = (K + 3) >> 2;
+  const int items = Oq * Kq;
+  const int grp = threadIdx.x >> 3, sub = threadIdx.x & 7;
+  const int rounds = (items + (NK_THREADS / 8) - 1) / (NK_THREADS / 8);
+  for (int it = 0; it < rounds; ++it) {
+    const int item = it * (NK_THREADS / 8) + grp;
+    const bool live = item < items;
+    const int kq = live ? item % Kq : 0, oq = live ? item / Kq : 0;
+    float acc[4][4];
+    float bs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int a = 0; a < 4; ++a) { acc[a][0] = 0.f; acc[a][1] = 0.f; acc[a][2] = 0.f; acc[a][3] = 0.f; }
+    if (live) {
+      for (int r = sub; r < R; r += 8) {
+        const float4 g = *reinterpret_cast<const float4*>(G + r * gs + oq * 4);
+        const float4 y = *reinterpret_cast<const float4*>(Y + r * ys + kq * 4);
+        const float gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          acc[a][0] = fmaf(gv[a], y.x, acc[a][0]); acc[a][1] = fmaf(gv[a], y.y, acc[a][1]);
+          acc[a][2] = fmaf(gv[a], y.z, acc[a][2]); acc[a][3] = fmaf(gv[a], y.w, acc[a][3]);
+          bs[a] += gv[a];
+        }
+      }
+    }
+#pragma unroll
+    for (int s = 1; s < 8; s <<= 1) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] += __shfl_xor_sync(0xffffffffu, acc[a][b], s);
+        bs[a] += __shfl_xor_sync(0xffffffffu, bs[a], s);
+      }
+    }
+    if (live && sub == 0) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int o = oq * 4 + a;
+        if (o < O) {
+#pragma unroll
+          for (int b = 0; b < 4; ++b) { const int k = kq * 4 + b; if (k < K) dW[o * K + k] += acc[a][b]; }
+          if (kq == 0 && db) db[o] += bs[a];
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ int rup4(int x) { return (x + 3) & ~3; }
+__host__ __device__ __forceinline__ int nk_stride(int w) { return ((w + 7) & ~7) + 4; }   // (stride/4) odd
+
+// ---------------------------------------------------------------------------------------------------------
+// node_pre: P|Q projections and their adjoint
+// ---------------------------------------------------------------------------------------------------------
+struct PreArgs {
+  int rows, H, ld, cols, E0, E0p, K0;   // K0 = 2H+1 (row length of edge_net[t][0].weight)
+  int R, hs, ws, ps;                    // rows per block; smem strides of h rows, weight rows, PQ rows
+  int o_w, o_b, o_h, o_pq, o_dpar, smem_floats;
+};
+
+// PQ[row][0..E0p) = Wa h + b0 ; PQ[row][E0p..2E0p) = Wb h
+__global__ void __launch_bounds__(NK_THREADS) node_pre_fwd_kernel(const PreArgs A, const float* __restrict__ h,
+                                                                   const float* __restrict__ w0, const float* __restrict__ b0,
+                                                                   float* __restrict__ pq) {
+  extern __shared__ float4 nk_smem_raw[];
+  float* sm = reinterpret_cast<float*>(nk_smem_raw);
+  float* W = sm + A.o_w;     // [2*E0p][ws]: rows 0..E0p-1 = Wa, E0p.. = Wb, zero padded
+  float* bias = sm + A.o_b;  // [2*E0p]: b0 | 0
+  const int Hp = rup4(A.H);
+  for (int idx = threadIdx.x; idx < 2 * A.E0p * A.ws; idx += NK_THREADS) {
+    const int o = idx / A.ws, k = idx - o * A.ws;
+    const int c = o < A.E0p ? o : o - A.E0p;
+    float v = 0.f;
+    if (c < A.E0 && k < A.H) v = __ldg(w0 + c * A.K0 + (o < A.E0p ? k : A.H + k));
+    W[idx] = v;
+  }
+  for (int o = threadIdx.x; o < 2 * A.E0p; o += NK_THREADS) bias[o] = (o < A.E0) ? __ldg(b0 + o) : 0.f;
+  float* X = sm + A.o_h;
+  float* O = sm + A.o_pq;
+  const int width = 2 * A.E0p;
+  for (int r0 = blockIdx.x * A.R; r0 < A.rows; r0 += gridDim.x * A.R) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < A.R * Hp; idx += NK_THREADS) {
+      const int r = idx / Hp, k = idx - r * Hp;
+      const int row = r0 + r;
+      X[r * A.hs + k] = (row < A.rows && k < A.cols) ? __ldg(h + (size_t)row * A.ld + k) : 0.f;
+    }
+    __syncthreads();
+    nk_gemm_rows<0>(X, A.hs, W, A.ws, bias, O, A.ps, nullptr, A.R, width, Hp, 0.f);
+    __syncthreads();
+    const int nvalid = min(A.R, A.rows - r0);
+    const int w4 = width >> 2;
+    for (int idx = threadIdx.x; idx < nvalid * w4; idx += NK_THREADS) {
+      const int r = idx / w4, q = idx - r * w4;
+      *reinterpret_cast<float4*>(pq + (size_t)(r0 + r) * width + q * 4) = *reinterpret_cast<const float4*>(O + r * A.ps + q * 4);
+    }
+  }
+}
+
+// dh[row][k] += sum_c dP[row][c] Wa[c][k] + dQ[row][c] Wb[c][k]   (k < cols)
+// dW0[c][k] += sum_rows dP h ; dW0[c][H+k] += sum_rows dQ h ; db0[c] += sum_rows dP     (partial per CTA)
+__global__ void __launch_bounds__(NK_THREADS) node_pre_bwd_kernel(const PreArgs A, const float* __restrict__ h,
+                                                                   const float* __restrict__ w0, const float* __restrict__ dpq,
+                                                                   float* __restrict__ dh, float* __restrict__ part) {
+  extern __shared__ float4 nk_smem_raw[];
+  float* sm = reinterpret_cast<float*>(nk_smem_raw);
+  // Wt[k][c'] with c' over 2*E0p (dP | dQ channels): dh[r][k] = sum_c' dPQ[r][c'] Wt[k][c']
+  float* Wt = sm + A.o_w;
+  const int Hp = rup4(A.H), width = 2 * A.E0p;
+  for (int idx = threadIdx.x; idx < Hp * A.ws; idx += NK_THREADS) {
+    const int k = idx / A.ws, o = idx - k * A.ws;
+    float v = 0.f;
+    if (o < width && k < A.H) {
+      const int c = o < A.E0p ? o : o - A.E0p;
+      if (c < A.E0) v = __ldg(w0 + c * A.K0 + (o < A.E0p ? k : A.H + k));
+    }
+    Wt[idx] = v;
+  }
+  float* dpar = sm + A.o_dpar;   // [E0][2H] (Wa | Wb gradients, row length 2H) then [E0] bias gradient
+  const int ndpar = A.E0 * 2 * A.H + A.E0;
+  for (int idx = threadIdx.x; idx < ndpar; idx += NK_THREADS) dpar[idx] = 0.f;
+  float* X = sm + A.o_h;    // h rows [R][hs]
+  float* G = sm + A.o_pq;   // dPQ rows [R][ps]
+  float* D = X;             // dh rows reuse... (kept separate below)
+  (void)D;
+  float* Dh = sm + A.o_b;   // [R][hs] output staging
+  for (int r0 = blockIdx.x * A.R; r0 < A.rows; r0 += gridDim.x * A.R) {
+    __syncthreads();
+    const int nvalid = min(A.R, A.rows - r0);
+    for (int idx = threadIdx.x; idx < A.R * Hp; idx += NK_THREADS) {
+      const int r = idx / Hp, k = idx - r * Hp;
+      const int row = r0 + r;
+      X[r * A.hs + k] = (row < A.rows && k < A.cols) ? __ldg(h + (size_t)row * A.ld + k) : 0.f;
+    }
+    const int w4 = width >> 2;
+    for (int idx = threadIdx.x; idx < A.R * w4; idx += NK_THREADS) {
+      const int r = idx / w4, q = idx - r * w4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < nvalid) v = *reinterpret_cast<const float4*>(dpq + (size_t)(r0 + r) * width + q * 4);
+      *reinterpret_cast<float4*>(G + r * A.ps + q * 4) = v;
+    }
+    __syncthreads();
+    nk_gemm_rows<0>(G, A.ps, Wt, A.ws, nullptr, Dh, A.hs, nullptr, A.R, Hp, width, 0.f);
+    // dWa: G[:, 0:E0p] x h ; dWb: G[:, E0p:] x h
+    nk_wgrad(G, A.ps, X, A.hs, dpar, dpar + A.E0 * 2 * A.H, A.R, A.E0, A.H);          // placeholder layout fixed below
+    __syncthreads();
+    nk_wgrad(G + A.E0p, A.ps, X, A.hs, dpar + A.E0 * A.H, nullptr, A.R, A.E0, A.H);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nvalid * A.cols; idx += NK_THREADS) {
+      const int r = idx / A.cols, k = idx - r * A.cols;
+      float* p = dh + (size_t)(r0 + r) * A.ld + k;
+      *p += Dh[r * A.hs + k];
+    }
+  }
+  __syncthreads();
+  // partial layout: [Wa grads E0*H][Wb grads E0*H][b0 grads E0]
+  float* out = part + (size_t)blockIdx.x * ndpar;
+  for (int idx = threadIdx.x; idx < ndpar; idx += NK_THREADS) out[idx] = dpar[idx];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// node_post: the node MLP and its adjoint
+// ---------------------------------------------------------------------------------------------------------
+struct PostArgs {
+  int rows, H, ld, cols, EL, Ln;
+  int O[GJ_MAX_LAYERS], I[GJ_MAX_LAYERS], pV[GJ_MAX_LAYERS], pc[GJ_MAX_LAYERS];   // offsets in the packed params
+  int p_first;                 // offset of the first node parameter in the packed block
+  int n_node_params;
+  float alpha;
+  int R, S;                    // rows per block, activation row stride
+  int o_V[GJ_MAX_LAYERS], vs[GJ_MAX_LAYERS], o_c[GJ_MAX_LAYERS];     // weights [Op][vs]
+  int o_Vt[GJ_MAX_LAYERS], vts[GJ_MAX_LAYERS];                        // transposed weights [Ip][vts] (bwd only)
+  int o_Y[GJ_MAX_LAYERS + 1], o_g0, o_g1, o_dpar, smem_floats;
+};
+
+__device__ void post_stage_weights(const PostArgs& A, const float* __restrict__ params, float* sm, bool transposed) {
+  for (int m = 0; m < A.Ln; ++m) {
+    const int O = A.O[m], I = A.I[m], Op = rup4(O), Ip = rup4(I);
+    for (int idx = threadIdx.x; idx < Op * A.vs[m]; idx += NK_THREADS) {
+      const int o = idx / A.vs[m], k = idx - o * A.vs[m];
+      sm[A.o_V[m] + idx] = (o < O && k < I) ? __ldg(params + A.pV[m] + o * I + k) : 0.f;
+    }
+    for (int o = threadIdx.x; o < Op; o += NK_THREADS) sm[A.o_c[m] + o] = o < O ? __ldg(params + A.pc[m] + o) : 0.f;
+    if (transposed) {
+      for (int idx = threadIdx.x; idx < Ip * A.vts[m]; idx += NK_THREADS) {
+        const int k = idx / A.vts[m], o = idx - k * A.vts[m];
+        sm[A.o_Vt[m] + idx] = (o < O && k < I) ? __ldg(params + A.pV[m] + o * I + k) : 0.f;
+      }
+    }
+  }
+}
+
+// Y0[r] = [e | h | 0-pad]
+__device__ void post_load_rows(const PostArgs& A, const float* __restrict__ e, const float* __restrict__ h, float* Y0, int r0) {
+  const int I0 = A.EL + A.H, I0p = rup4(I0);
+  for (int idx = threadIdx.x; idx < A.R * I0p; idx += NK_THREADS) {
+    const int r = idx / I0p, k = idx - r * I0p;
+    const int row = r0 + r;
+    float v = 0.f;
+    if (row < A.rows) {
+      if (k < A.EL) v = __ldg(e + (size_t)row * A.EL + k);
+      else if (k - A.EL < A.cols) v = __ldg(h + (size_t)row * A.ld + (k - A.EL));
+    }
+    Y0[r * A.S + k] = v;
+  }
+}
+
+__global__ void __launch_bounds__(NK_THREADS) node_post_fwd_kernel(const PostArgs A, const float* __restrict__ e,
+                                                                    const float* __restrict__ h, const float* __restrict__ params,
+                                                                    float* __restrict__ h_out) {
+  extern __shared__ float4 nk_smem_raw[];
+  float* sm = reinterpret_cast<float*>(nk_smem_raw);
+  post_stage_weights(A, params, sm, false);
+  const int Hout = A.O[A.Ln - 1];
+  for (int r0 = blockIdx.x * A.R; r0 < A.rows; r0 += gridDim.x * A.R) {
+    __syncthreads();
+    post_load_rows(A, e, h, sm + A.o_Y[0], r0);
+    __syncthreads();
+    for (int m = 0; m < A.Ln; ++m) {
+      nk_gemm_rows<1>(sm + A.o_Y[m & 1], A.S, sm + A.o_V[m], A.vs[m], sm + A.o_c[m], sm + A.o_Y[(m + 1) & 1], A.S, nullptr, A.R,
+                      rup4(A.O[m]), rup4(A.I[m]), A.alpha);
+      __syncthreads();
+    }
+    const float* Y = sm + A.o_Y[A.Ln & 1];
+    const int nvalid = min(A.R, A.rows - r0);
+    for (int idx = threadIdx.x; idx < nvalid * Hout; idx += NK_THREADS) {
+      const int r = idx / Hout, o = idx - r * Hout;
+      h_out[(size_t)(r0 + r) * Hout + o] = Y[r * A.S + o];
+    }
+  }
+}
+
+// in : e, h, dh_out ; out: de (rows, EL), dh (rows, ld; first `cols` columns OVERWRITTEN with the node-path gradient),
+//      per-CTA partial of the node parameters (packed order, n_node_params floats).
+__global__ void __launch_bounds__(NK_THREADS) node_post_bwd_kernel(const PostArgs A, const float* __restrict__ e,
+                                                                    const float* __restrict__ h, const float* __restrict__ params,
+                                                                    const float* __restrict__ dh_out, float* __restrict__ de,
+                                                                    float* __restrict__ dh, float* __restrict__ part) {
+  extern __shared__ float4 nk_smem_raw[];
+  float* sm = reinterpret_cast<float*>(nk_smem_raw);
+  post_stage_weights(A, params, sm, true);
+  float* dpar = sm + A.o_dpar;
+  for (int idx = threadIdx.x; idx < A.n_node_params; idx += NK_THREADS) dpar[idx] = 0.f;
+  const int Hout = A.O[A.Ln - 1], Houtp = rup4(Hout);
+  for (int r0 = blockIdx.x * A.R; r0 < A.rows; r0 += gridDim.x * A.R) {
+    __syncthreads();
+    const int nvalid = min(A.R, A.rows - r0);
+    post_load_rows(A, e, h, sm + A.o_Y[0], r0);
+    __syncthreads();
+    for (int m = 0; m < A.Ln; ++m) {
+      nk_gemm_rows<1>(sm + A.o_Y[m], A.S, sm + A.o_V[m], A.vs[m], sm + A.o_c[m], sm + A.o_Y[m + 1], A.S, nullptr, A.R,
+                      rup4(A.O[m]), rup4(A.I[m]), A.alpha);
+      __syncthreads();
+    }
+    float* g = sm + A.o_g0;
+    float* gp = sm + A.o_g1;
+    {  // gz = dh_out * leaky'(y_last); rows beyond the batch and padded columns are zero
+      const float* Yl = sm + A.o_Y[A.Ln];
+      for (int idx = threadIdx.x; idx < A.R * Houtp; idx += NK_THREADS) {
+        const int r = idx / Houtp, o = idx - r * Houtp;
+        float v = 0.f;
+        if (r < nvalid && o < Hout) v = __ldg(dh_out + (size_t)(r0 + r) * Hout + o) * gj_slope(Yl[r * A.S + o], A.alpha);
+        g[r * A.S + o] = v;
+      }
+    }
+    __syncthreads();
+    for (int m = A.Ln - 1; m >= 0; --m) {
+      const int O = A.O[m], I = A.I[m];
+      nk_wgrad(g, A.S, sm + A.o_Y[m], A.S, dpar + (A.pV[m] - A.p_first), dpar + (A.pc[m] - A.p_first), A.R, O, I);
+      if (m > 0) nk_gemm_rows<2>(g, A.S, sm + A.o_Vt[m], A.vts[m], nullptr, gp, A.S, sm + A.o_Y[m], A.R, rup4(I), rup4(O), A.alpha);
+      else       nk_gemm_rows<0>(g, A.S, sm + A.o_Vt[m], A.vts[m], nullptr, gp, A.S, nullptr, A.R, rup4(I), rup4(O), A.alpha);
+      __syncthreads();
+      float* t = g; g = gp; gp = t;
+    }
+    // g = d[e | h]
+    for (int idx = threadIdx.x; idx < nvalid * A.EL; idx += NK_THREADS) {
+      const int r = idx / A.EL, k = idx - r * A.EL;
+      de[(size_t)(r0 + r) * A.EL + k] = g[r * A.S + k];
+    }
+    for (int idx = threadIdx.x; idx < nvalid * A.cols; idx += NK_THREADS) {
+      const int r = idx / A.cols, k = idx - r * A.cols;
+      dh[(size_t)(r0 + r) * A.ld + k] = g[r * A.S + A.EL + k];
+    }
+  }
+  __syncthreads();
+  float* out = part + (size_t)blockIdx.x * A.n_node_params;
+  for (int idx = threadIdx.x; idx < A.n_node_params; idx += NK_THREADS) out[idx] = dpar[idx];
+}
+
+// out[dst_off + p] = sum_c part[c][p]   (fixed order => deterministic)
+__global__ void reduce_partials_kernel(const float* __restrict__ part, int nparts, int n, float* __restrict__ out) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  float acc = 0.f;
+  for (int c = 0; c < nparts; ++c) acc += part[(size_t)c * n + p];
+  out[p] = acc;
+}
+
+// dW0 scatter: the node_pre partials are [Wa E0*H][Wb E0*H][b0 E0]; the packed layout is W0 (E0, 2H+1) then b0.
+__global__ void reduce_pre_partials_kernel(const float* __restrict__ part, int nparts, int E0, int H, float* __restrict__ dW0,
+                                           float* __restrict__ db0) {
+  const int n = E0 * 2 * H + E0;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  float acc = 0.f;
+  for (int c = 0; c < nparts; ++c) acc += part[(size_t)c * n + p];
+  const int K0 = 2 * H + 1;
+  if (p < E0 * H) { const int c = p / H, k = p - c * H; dW0[c * K0 + k] = acc; }
+  else if (p < 2 * E0 * H) { const int q = p - E0 * H; const int c = q / H, k = q - c * H; dW0[c * K0 + H + k] = acc; }
+  else db0[p - 2 * E0 * H] = acc;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+int gj_num_sms();
+void gj_set_error(const char* fmt, ...);
+
+static const int kSmemLimit = 227 * 1024;
+
+static int pre_plan(const MPLayout& L, PreArgs* A, bool backward) {
+  memset(A, 0, sizeof(*A));
+  A->rows = L.B * L.N; A->H = L.H; A->ld = L.ld; A->cols = L.cols; A->E0 = L.E[0]; A->E0p = L.E0p; A->K0 = L.K[0];
+  const int Hp = (L.H + 3) & ~3, width = 2 * L.E0p;
+  A->hs = nk_stride(L.H);
+  A->ps = nk_stride(width);
+  for (int R = 128; R >= 8; R >>= 1) {
+    A->R = R;
+    int off = 0;
+    auto take = [&](int n) { int o = off; off += (n + 3) & ~3; return o; };
+    if (!backward) {
+      A->ws = nk_stride(L.H);
+      A->o_w = take(width * A->ws);
+      A->o_b = take(width);
+      A->o_h = take(R * A->hs);
+      A->o_pq = take(R * A->ps);
+    } else {
+      A->ws = nk_stride(width);
+      A->o_w = take(Hp * A->ws);
+      A->o_b = take(R * A->hs);      // dh staging
+      A->o_h = take(R * A->hs);
+      A->o_pq = take(R * A->ps);
+      A->o_dpar = take(L.E[0] * 2 * L.H + L.E[0]);
+    }
+    A->smem_floats = off;
+    if (off * 4 <= kSmemLimit) return off * 4;
+  }
+  return -1;
+}
+
+static int post_plan(const MPLayout& L, PostArgs* A, bool backward) {
+  memset(A, 0, sizeof(*A));
+  A->rows = L.B * L.N; A->H = L.H; A->ld = L.ld; A->cols = L.cols; A->EL = L.EL; A->Ln = L.Ln; A->alpha = L.alpha;
+  int wmax = L.EL + L.H;
+  for (int m = 0; m < L.Ln; ++m) {
+    A->O[m] = L.O[m]; A->I[m] = L.I[m]; A->pV[m] = L.pV[m]; A->pc[m] = L.pc[m];
+    if (L.O[m] > wmax) wmax = L.O[m];
+  }
+  A->p_first = L.pV[0];
+  A->n_node_params = L.nparams - L.pV[0];
+  A->S = nk_stride(wmax);
+  for (int R = 128; R >= 8; R >>= 1) {
+    A->R = R;
+    int off = 0;
+    auto take = [&](int n) { int o = off; off += (n + 3) & ~3; return o; };
+    for (int m = 0; m < L.Ln; ++m) {
+      const int Op = (L.O[m] + 3) & ~3, Ip = (L.I[m] + 3) & ~3;
+      A->vs[m] = nk_stride(L.I[m]);
+      A->o_V[m] = take(Op * A->vs[m]);
+      A->o_c[m] = take(Op);
+      if (backward) { A->vts[m] = nk_stride(L.O[m]); A->o_Vt[m] = take(Ip * A->vts[m]); }
+    }
+    const int nY = backward ? L.Ln + 1 : 2;
+    for (int m = 0; m < nY; ++m) A->o_Y[m] = take(R * A->S);
+    if (backward) { A->o_g0 = take(R * A->S); A->o_g1 = take(R * A->S); A->o_dpar = take(A->n_node_params); }
+    A->smem_floats = off;
+    if (off * 4 <= kSmemLimit) return off * 4;
+  }
+  return -1;
+}
+
+static int nk_grid(int rows, int R) {
+  int blocks = (rows + R - 1) / R;
+  int cap = gj_num_sms();
+  return blocks < cap ? (blocks > 0 ? blocks : 1) : cap;
+}
+
+#define NK_CHECK_LAUNCH(what)                                                                         \
+  do { cudaError_t ce_ = cudaGetLastError();                                                          \
+       if (ce_ != cudaSuccess) { gj_set_error(what ": %s", cudaGetErrorString(ce_)); return GJ_ERR_CUDA; } } while (0)
+
+template <typename K>
+static int nk_set_smem(K kern, int bytes) {
+  cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (ce != cudaSuccess) { gj_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
+  return GJ_OK;
+}
+
+int gj_node_pre_fwd(const MPLayout& L, const float* h, const float* params, float* pq, cudaStream_t st) {
+  PreArgs A; int bytes = pre_plan(L, &A, false);
+  if (bytes < 0) { gj_set_error("node_pre_fwd: widths do not fit shared memory"); return GJ_ERR_SMEM; }
+  if (int rc = nk_set_smem(node_pre_fwd_kernel, bytes)) return rc;
+  node_pre_fwd_kernel<<<nk_grid(A.rows, A.R), NK_THREADS, bytes, st>>>(A, h, params + L.pW[0], params + L.pb[0], pq);
+  NK_CHECK_LAUNCH("node_pre_fwd launch");
+  return GJ_OK;
+}
+
+size_t gj_node_pre_bwd_ws_floats(const MPLayout& L) {
+  PreArgs A; if (pre_plan(L, &A, true) < 0) return 0;
+  return (size_t)nk_grid(A.rows, A.R) * (L.E[0] * 2 * L.H + L.E[0]);
+}
+
+int gj_node_pre_bwd(const MPLayout& L, const float* h, const float* params, const float* dpq, float* dh, float* dparams,
+                    float* part, cudaStream_t st) {
+  PreArgs A; int bytes = pre_plan(L, &A, true);
+  if (bytes < 0) { gj_set_error("node_pre_bwd: widths do not fit shared memory"); return GJ_ERR_SMEM; }
+  if (int rc = nk_set_smem(node_pre_bwd_kernel, bytes)) return rc;
+  const int grid = nk_grid(A.rows, A.R);
+  node_pre_bwd_kernel<<<grid, NK_THREADS, bytes, st>>>(A, h, params + L.pW[0], dpq, dh, part);
+  const int n = L.E[0] * 2 * L.H + L.E[0];
+  reduce_pre_partials_kernel<<<(n + 255) / 256, 256, 0, st>>>(part, grid, L.E[0], L.H, dparams + L.pW[0], dparams + L.pb[0]);
+  NK_CHECK_LAUNCH("node_pre_bwd launch");
+  return GJ_OK;
+}
+
+int gj_node_post_fwd(const MPLayout& L, const float* e, const float* h, const float* params, float* h_out, cudaStream_t st) {
+  PostArgs A; int bytes = post_plan(L, &A, false);
+  if (bytes < 0) { gj_set_error("node_post_fwd: widths do not fit shared memory"); return GJ_ERR_SMEM; }
+  if (int rc = nk_set_smem(node_post_fwd_kernel, bytes)) return rc;
+  node_post_fwd_kernel<<<nk_grid(A.rows, A.R), NK_THREADS, bytes, st>>>(A, e, h, params, h_out);
+  NK_CHECK_LAUNCH("node_post_fwd launch");
+  return GJ_OK;
+}
+
+size_t gj_node_post_bwd_ws_floats(const MPLayout& L) {
+  PostArgs A; if (post_plan(L, &A, true) < 0) return 0;
+  return (size_t)nk_grid(A.rows, A.R) * A.n_node_params;
+}
+
+int gj_node_post_bwd(const MPLayout& L, const float* e, const float* h, const float* params, const float* dh_out, float* de,
+                     float* dh, float* dparams, float* part, cudaStream_t st) {
+  PostArgs A; int bytes = post_plan(L, &A, true);
+  if (bytes < 0) { gj_set_error("node_post_bwd: widths do not fit shared memory"); return GJ_ERR_SMEM; }
+  if (int rc = nk_set_smem(node_post_bwd_kernel, bytes)) return rc;
+  const int grid = nk_grid(A.rows, A.R);
+  node_post_bwd_kernel<<<grid, NK_THREADS, bytes, st>>>(A, e, h, params, dh_out, de, dh, part);
+  reduce_partials_kernel<<<(A.n_node_params + 255) / 256, 256, 0, st>>>(part, grid, A.n_node_params, dparams + A.p_first);
+  NK_CHECK_LAUNCH("node_post_bwd launch");
+  return GJ_OK;
+}
+
+int gj_reduce_partials(const float* part, int nparts, int n, float* out, cudaStream_t st) {
+  if (n <= 0) return GJ_OK;
+  reduce_partials_kernel<<<(n + 255) / 256, 256, 0, st>>>(part, nparts, n, out);
+  NK_CHECK_LAUNCH("reduce_partials launch");
+  return GJ_OK;
+}

@@ -49,17 +49,21 @@ def metric_id(metric) -> int:
 # --------------------------------------------------------------------------------------------------
 # pointer-level calls
 # --------------------------------------------------------------------------------------------------
-def raw_mp_fwd(desc, h_ptr, params_ptr, hout_ptr, e_ptr, stream):
+FWD_LAUNCHES = 3   # node projections, fused edge kernel, node MLP
+BWD_LAUNCHES = 8   # node MLP adjoint + reduce, node projections, edge adjoint + reduce, projections' adjoint + reduce
+
+
+def raw_mp_fwd(desc, h_ptr, params_ptr, hout_ptr, e_ptr, ws_ptr, ws_bytes, stream):
     lib = _lib.load()
-    _lib.check(lib.gj_mp_step_fwd(desc, h_ptr, params_ptr, hout_ptr, e_ptr, stream), "gj_mp_step_fwd")
-    LAUNCHES["count"] += 1
+    _lib.check(lib.gj_mp_step_fwd(desc, h_ptr, params_ptr, hout_ptr, e_ptr, ws_ptr, ws_bytes, stream), "gj_mp_step_fwd")
+    LAUNCHES["count"] += FWD_LAUNCHES
 
 
 def raw_mp_bwd(desc, h_ptr, e_ptr, params_ptr, dhout_ptr, dh_ptr, dparams_ptr, ws_ptr, ws_bytes, stream):
     lib = _lib.load()
     _lib.check(lib.gj_mp_step_bwd(desc, h_ptr, e_ptr, params_ptr, dhout_ptr, dh_ptr, dparams_ptr, ws_ptr, ws_bytes,
                                   stream), "gj_mp_step_bwd")
-    LAUNCHES["count"] += 2  # step kernel + deterministic partial reduction
+    LAUNCHES["count"] += BWD_LAUNCHES
 
 
 # --------------------------------------------------------------------------------------------------
@@ -87,7 +91,9 @@ def mp_step_fwd(h: Tensor, params: Tensor, num_nodes: int, node_in: int, edge_wi
     B, N, _ = h.shape
     h_out = torch.empty((B, N, node_widths[-1]), device=h.device, dtype=torch.float32)
     e = torch.empty((B, N, edge_widths[-1]), device=h.device, dtype=torch.float32)
-    raw_mp_fwd(d, h.data_ptr(), params.data_ptr(), h_out.data_ptr(), e.data_ptr(), _stream())
+    ws_bytes = lib.gj_mp_step_fwd_workspace(d)
+    ws = torch.empty((max(ws_bytes, 4) + 3) // 4, device=h.device, dtype=torch.float32)
+    raw_mp_fwd(d, h.data_ptr(), params.data_ptr(), h_out.data_ptr(), e.data_ptr(), ws.data_ptr(), ws_bytes, _stream())
     return h_out, e
 
 
@@ -169,6 +175,8 @@ def chamfer(p: Tensor, q: Tensor, norm: int, w_chamfer: float, w_jet: float) -> 
         raise ValueError("p and q must both be 3- or 4-vectors (distance_sq.py:31-42)")
     B, Np, D = p.shape
     Nq = q.shape[1]
+    if B == 0:
+        return torch.zeros(3, device=p.device, dtype=torch.float32), torch.empty_like(p)
     terms = torch.empty(3, device=p.device, dtype=torch.float32)
     jet_terms = torch.empty((max(B, 1), 2), device=p.device, dtype=torch.float32)
     dp = torch.empty_like(p)

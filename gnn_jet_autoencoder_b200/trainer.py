@@ -185,6 +185,7 @@ class GNNAETrainer:
         self.stats = torch.zeros(8, **f32)     # [chamfer, jet, wc*chamfer + wj*jet, sum|p|, sum p^2]
         self.stats_host = torch.zeros(8, dtype=torch.float32).pin_memory()
         ws = max([self.lib.gj_mp_step_bwd_workspace(s["desc"]) for s in self.enc_steps + self.dec_steps] +
+                 [self.lib.gj_mp_step_fwd_workspace(s["desc"]) for s in self.enc_steps + self.dec_steps] +
                  [self.lib.gj_linear_bwd_workspace(B * N, max(self.latent_w, self.enc_out_w), max(self.h0, self.latent_w)),
                   self.lib.gj_linear_bwd_workspace(B, max(self.latent_w, N * self.enc_out_w), max(N * self.h0, self.latent_w)),
                   self.lib.gj_param_norms_workspace(n), 16])
@@ -220,7 +221,8 @@ class GNNAETrainer:
         B, N = self.B, self.N
         h = self.x
         for s in self.enc_steps:
-            ops.raw_mp_fwd(s["desc"], h.data_ptr(), P + 4 * s["off"], s["out"].data_ptr(), s["e"].data_ptr(), st)
+            ops.raw_mp_fwd(s["desc"], h.data_ptr(), P + 4 * s["off"], s["out"].data_ptr(), s["e"].data_ptr(),
+                           self.ws.data_ptr(), self.ws_bytes, st)
             h = s["out"]
         L = self.layout
         if self.map == "mean":
@@ -241,7 +243,8 @@ class GNNAETrainer:
         ops.LAUNCHES["count"] += 1
         h = self.dec_in
         for s in self.dec_steps:
-            ops.raw_mp_fwd(s["desc"], h.data_ptr(), P + 4 * s["off"], s["out"].data_ptr(), s["e"].data_ptr(), st)
+            ops.raw_mp_fwd(s["desc"], h.data_ptr(), P + 4 * s["off"], s["out"].data_ptr(), s["e"].data_ptr(),
+                           self.ws.data_ptr(), self.ws_bytes, st)
             h = s["out"]
 
     def _loss_and_bwd(self, st):

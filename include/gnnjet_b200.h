@@ -75,19 +75,23 @@ typedef struct gj_mp_desc {
 /* Number of floats in the packed parameter block of one step (0 on invalid desc). */
 size_t gj_mp_param_count(const gj_mp_desc* d);
 
-/* Forward of one step.  h (B,N,H) -> h_out (B,N,node_widths[last]).
- * e_out, if not NULL, receives the edge aggregate sum_j EdgeNet(A_ij) (B,N,edge_widths[last]),
- * which gj_mp_step_bwd needs (it is the only tensor saved for backward besides h). */
-int gj_mp_step_fwd(const gj_mp_desc* d, const float* h, const float* params,
-                   float* h_out, float* e_out, void* stream);
+/* Workspace bytes needed by gj_mp_step_fwd (the per-node projections P|Q of the factorised first edge layer). */
+size_t gj_mp_step_fwd_workspace(const gj_mp_desc* d);
 
-/* Workspace bytes needed by gj_mp_step_bwd (per-CTA parameter-gradient partials). */
+/* Forward of one step.  h (B,N,h_ld) -> h_out (B,N,node_widths[last]).
+ * e_out (required) receives the edge aggregate sum_j EdgeNet(A_ij) (B,N,edge_widths[last]), which
+ * gj_mp_step_bwd needs (it is the only tensor saved for backward besides h).
+ * Launch sequence: node projections -> fused edge kernel (pair tiles in shared memory / TMEM only) -> node MLP. */
+int gj_mp_step_fwd(const gj_mp_desc* d, const float* h, const float* params,
+                   float* h_out, float* e_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Workspace bytes needed by gj_mp_step_bwd (P|Q, their gradients, de, per-CTA parameter-gradient partials). */
 size_t gj_mp_step_bwd_workspace(const gj_mp_desc* d);
 
 /* Backward of one step: recomputes the edge MLP per tile (nothing N^2-sized is ever stored).
  * in : h, e (saved by forward), params, dh_out (B,N,out)
- * out: dh (B,N,H), dparams (packed like params; OVERWRITTEN with the batch-summed gradient,
- *      deterministic reduction order). */
+ * out: dh (B,N,h_ld; the first h_cols columns of every row are OVERWRITTEN, others untouched),
+ *      dparams (packed like params; OVERWRITTEN with the batch-summed gradient, deterministic reduction order). */
 int gj_mp_step_bwd(const gj_mp_desc* d, const float* h, const float* e, const float* params,
                    const float* dh_out, float* dh, float* dparams,
                    void* workspace, size_t workspace_bytes, void* stream);
