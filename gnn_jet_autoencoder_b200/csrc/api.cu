@@ -43,6 +43,7 @@ size_t gj_edge_bwd_tc_ws_floats(const MPLayout&);
 int gj_edge_bwd_tc(MPLayout, const float*, const float*, const float*, const float*, float*, float*, float*, float*,
                    cudaStream_t);
 int gj_umma_selftest_launch(int, int, int, int, int, const float*, const float*, float*, cudaStream_t);
+void gj_tc_plan_info(MPLayout, int*);
 int gj_chamfer_launch(int, int, int, int, int, float, float, const float*, const float*, float*, float*, float*, cudaStream_t);
 int gj_linear_fwd_launch(int, int, int, const float*, const float*, const float*, float*, cudaStream_t);
 size_t gj_linear_bwd_ws_bytes(int, int, int);
@@ -200,6 +201,15 @@ int gj_latent_mean_bwd(int32_t batch, int32_t num_nodes, int32_t width, const fl
   g_err[0] = 0;
   if (batch < 0 || num_nodes < 1 || width < 1) { gj_set_error("gj_latent_mean_bwd: bad shape"); return GJ_ERR_INVALID; }
   return gj_latent_mean_bwd_launch(batch, num_nodes, width, dz, dy, (cudaStream_t)stream);
+}
+
+int gj_mp_plan_info(const gj_mp_desc* d, int32_t* info) {
+  g_err[0] = 0;
+  MPLayout L; const char* why;
+  int rc = gj_fill_arch(d, &L, &why);
+  if (rc || !info) { gj_set_error("gj_mp_plan_info: %s", rc ? why : "null pointer"); return GJ_ERR_INVALID; }
+  gj_tc_plan_info(L, info);
+  return GJ_OK;
 }
 
 int gj_umma_selftest(int32_t m, int32_t n, int32_t k, int32_t a_major, int32_t b_major, const float* a, const float* b,

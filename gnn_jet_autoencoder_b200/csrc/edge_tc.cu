@@ -75,10 +75,10 @@ __device__ void stage_small(const MPLayout& L, const float* __restrict__ params,
 }
 
 // bf16 interleaved staging of edge weights l >= 1 as the K-major B operand (N = out feature rows, K = in).
-__device__ void stage_edge_weights_bf16(const MPLayout& L, const TCPlan& T, const float* __restrict__ params, uint8_t* smem,
+__device__ void stage_edge_weights_bf16(const MPLayout& L, const int* o_wT, const float* __restrict__ params, uint8_t* smem,
                                         int tid, int nthr) {
   for (int l = 1; l < L.Le; ++l) {
-    uint8_t* w = smem + T.o_wT[l];
+    uint8_t* w = smem + o_wT[l];
     const int Ep = L.Ep[l], Kp = L.Kp[l], E = L.E[l], K = L.K[l];
     for (int idx = tid; idx < Ep * Kp; idx += nthr) {
       int n = idx / Kp, k = idx - n * Kp;
@@ -148,7 +148,7 @@ edge_fwd_tc_kernel(const MPLayout L, const TCPlan T, const float* __restrict__ h
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + T.o_tmem_slot);
 
   stage_small(L, params, smf, tid, NT);
-  stage_edge_weights_bf16(L, T, params, smem, tid, NT);
+  stage_edge_weights_bf16(L, T.o_wT, params, smem, tid, NT);
   if (tid == 0) {
     for (int w = 0; w < NWG; ++w) mbar_init(reinterpret_cast<uint64_t*>(smem + T.o_bar) + w, 1);
     fence_barrier_init();
@@ -241,6 +241,518 @@ edge_fwd_tc_kernel(const MPLayout L, const TCPlan T, const float* __restrict__ h
 }
 
 // ------------------------------------------------------------------------------------------------
+// backward: recompute + dgrad + wgrad on tensor cores
+// ------------------------------------------------------------------------------------------------
+// CTA = NWG compute warpgroups + one MMA-issuer warp.  A warpgroup owns the tiles of its jets and only ever
+// touches shared memory and its TMEM accumulator; ALL tcgen05.mma are issued by one thread of the issuer warp,
+// strictly round-robin over the warpgroups (fixed accumulation order => deterministic gradients), which lets the
+// weight-gradient accumulators be shared by the warpgroups and stay resident in TMEM for the whole kernel.
+// Per tile and warpgroup the issuer runs 2(Le-1) stages, each followed by a warpgroup epilogue:
+//   F_l (l = 1..Le-1): acc = a_{l-1} W_l^T                     epilogue: a_l -> bf16 smem (last: dz_last = de*leaky')
+//   B_l (l = Le-1..1): dW_l += dz_l^T a_{l-1} ; acc = dz_l W_l  epilogue: dz_{l-1} = acc * leaky'(a_{l-1}) in place
+//                      (at l = 1 also the bias gradients: column sums of ALL dz_l as one M=128 MMA per 128 columns
+//                       against a ones operand, the dz_l buffers being contiguous in shared memory)
+// The first layer's adjoint (dP, dQ, distance gradient, d wd) is reduced on the CUDA cores from dz_0 in fp32.
+struct BwdPlan {
+  int nwg, Le;
+  // shared regions (bytes from smem base)
+  int o_bar, o_tmem_slot, o_ones, o_shared_f32;
+  int o_wT[GJ_MAX_LAYERS];
+  int wg_base, wg_stride;
+  // per-warpgroup (bytes from the warpgroup base)
+  int w_a0, w_comb, w_f32;
+  int coff[GJ_MAX_LAYERS];      // column offset of layer l's buffer inside the combined dz buffer (l >= 1)
+  int ctot;
+  // TMEM (columns from the allocation base)
+  int nacc;                     // per-warpgroup forward/dgrad accumulator width
+  int t_wg[GJ_MAX_LAYERS];      // weight-gradient accumulator of layer l
+  int wg_orient[GJ_MAX_LAYERS]; // 0: lanes = out features (M from dz_l), 1: lanes = in features (M from a_{l-1})
+  int wg_M[GJ_MAX_LAYERS], wg_N[GJ_MAX_LAYERS];
+  int nbias, t_bias[4], bias_M[4];
+  int tmem_cols;
+  int smem_bytes;
+};
+
+// returns 0 if the configuration is supported by the tensor-core backward
+int plan_tc_bwd(MPLayout* L, BwdPlan* T, int nwg) {
+  memset(T, 0, sizeof(*T));
+  T->nwg = nwg; T->Le = L->Le;
+  L->R = 128;
+  if (L->Le < 2) return 1;
+  if (L->E0p != 16 && L->E0p != 32 && L->E0p != 48 && L->E0p != 64) return 1;
+  int ctot = 0, nacc = 32;
+  for (int l = 1; l < L->Le; ++l) {
+    if (L->Ep[l] > 256 || L->Kp[l] > 256) return 1;
+    T->coff[l] = ctot; ctot += L->Ep[l];
+    if (L->Ep[l] > nacc) nacc = L->Ep[l];
+    if (L->Kp[l] > nacc) nacc = L->Kp[l];
+  }
+  T->ctot = ctot; T->nacc = nacc;
+  int tcol = nwg * nacc;
+  for (int l = 1; l < L->Le; ++l) {
+    const int Ma = gj_round_up(L->Ep[l], 64), Mb = gj_round_up(L->Kp[l], 64);
+    const bool oka = Ma <= 128, okb = Mb <= 128;
+    if (!oka && !okb) return 1;
+    int orient;
+    if (oka && okb) {
+      if (L->Kp[l] != L->Ep[l]) orient = L->Kp[l] < L->Ep[l] ? 0 : 1;      // fewer TMEM columns
+      else orient = (Ma == L->Ep[l] || Mb != L->Kp[l]) ? 0 : 1;             // prefer an unpadded M
+    } else orient = oka ? 0 : 1;
+    T->wg_orient[l] = orient;
+    T->wg_M[l] = orient == 0 ? Ma : Mb;
+    T->wg_N[l] = orient == 0 ? L->Kp[l] : L->Ep[l];
+    T->t_wg[l] = tcol; tcol += T->wg_N[l];
+  }
+  int rem = ctot, nb = 0;
+  while (rem > 0) {
+    if (nb >= 4) return 1;
+    T->bias_M[nb] = rem > 64 ? 128 : 64;
+    T->t_bias[nb] = tcol; tcol += 16;
+    rem -= 128; ++nb;
+  }
+  T->nbias = nb;
+  if (tcol > 512) return 1;
+  T->tmem_cols = next_pow2_cols(tcol);
+  // shared floats
+  Carver c;
+  for (int l = 1; l < L->Le; ++l) L->o_bE[l] = c.take(L->Ep[l]);
+  L->o_wd = c.take(L->E0p);
+  L->o_dpar = c.take(nwg * L->E0p);     // per-warpgroup d(wd) partials at kernel end
+  // per-warpgroup floats
+  Carver w;
+  L->o_h = w.take(GJ_IB * L->Hs);
+  L->o_hj = w.take(32 * L->Hs);
+  L->o_P = w.take(GJ_IB * L->E0s);
+  L->o_Q = w.take(32 * L->E0s);
+  L->o_e = w.take(GJ_IB * L->ELs);
+  L->o_dP = w.take(GJ_IB * L->E0s);
+  L->o_dQ = w.take(32 * L->E0s);
+  L->o_dh = w.take(GJ_IB * L->Hs);
+  L->Gs = 33;
+  L->o_G = w.take(GJ_IB * L->Gs);
+  int off = 0;
+  T->o_bar = off; off += 64;
+  T->o_tmem_slot = off; off += 64;
+  T->o_ones = off; off += 16 * 128 * 2;
+  for (int l = 1; l < L->Le; ++l) { T->o_wT[l] = off; off += L->Ep[l] * L->Kp[l] * 2; }
+  T->o_shared_f32 = off; off += c.off * 4;
+  off = gj_round_up(off, 128);
+  T->wg_base = off;
+  int wo = 0;
+  T->w_a0 = wo; wo += L->E0p * 256;
+  T->w_comb = wo; wo += ctot * 256;
+  T->w_f32 = wo; wo += w.off * 4;
+  // MN-major operands with a padded M read up to 127 columns past their buffer: keep those reads inside the
+  // warpgroup's own region (what they fetch only lands in accumulator rows nobody reads)
+  const int overshoot = 128 * 256;
+  if (w.off * 4 < overshoot) wo += overshoot - w.off * 4;
+  wo = gj_round_up(wo, 128);
+  T->wg_stride = wo;
+  T->smem_bytes = T->wg_base + nwg * wo;
+  return T->smem_bytes > 227 * 1024 ? 1 : 0;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// transpose-reduce of 16 per-lane values over the 32 lanes of a warp: returns, in every lane, the sum over all lanes
+// of channel (lane >> 1) & 15   (31 adds + 16 shuffles instead of 80 + 80)
+__device__ __forceinline__ float warp_transpose_sum16(const float (&v)[16], int lane) {
+  float w8[8], w4[4], w2[2];
+  bool up = lane & 16;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    float send = up ? v[q] : v[q + 8], keep = up ? v[q + 8] : v[q];
+    w8[q] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+  up = lane & 8;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float send = up ? w8[q] : w8[q + 4], keep = up ? w8[q + 4] : w8[q];
+    w4[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  up = lane & 4;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    float send = up ? w4[q] : w4[q + 2], keep = up ? w4[q + 2] : w4[q];
+    w2[q] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  up = lane & 2;
+  float send = up ? w2[0] : w2[1], keep = up ? w2[1] : w2[0];
+  float w1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  return w1 + __shfl_xor_sync(0xffffffffu, w1, 1);
+}
+
+__device__ __forceinline__ void unpack_bf16x8(const uint4& u, float* f) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+
+// ---- the issuer's MMA batches -----------------------------------------------------------------------------
+// A/B K-major buffer with nrows rows: next 8 rows +128 B (SBO), next 8 columns +nrows*16 B (LBO), 16 columns per MMA
+// A/B MN-major view of the same bytes (MN = column, K = row): next 8 columns +nrows*16 B (SBO), next 8 rows +128 B (LBO)
+__device__ __forceinline__ void issue_fwd(uint32_t d, uint32_t a, uint32_t w, int N, int K) {
+  const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
+  for (int ks = 0; ks < K / 16; ++ks)
+    mma_bf16_ss(d, make_smem_desc(a + ks * 4096, 2048, 128), make_smem_desc(w + ks * (2 * N * 16), N * 16, 128), idesc, ks > 0);
+}
+// acc[128 x Kin] = dz[128 x Eout] * W[Eout x Kin]: A = dz K-major, B = W viewed MN-major (MN = in feature, K = out feature)
+__device__ __forceinline__ void issue_dgrad(uint32_t d, uint32_t dz, uint32_t w, int Kin, int Eout) {
+  const uint32_t idesc = make_idesc_bf16(128, Kin, 0, 1);
+  for (int ks = 0; ks < Eout / 16; ++ks)
+    mma_bf16_ss(d, make_smem_desc(dz + ks * 4096, 2048, 128), make_smem_desc(w + ks * 256, 128, Eout * 16), idesc, ks > 0);
+}
+// D[M x N] (+)= X^T Y over the 128 tile rows: both operands MN-major views of 128-row buffers
+__device__ __forceinline__ void issue_wgrad(uint32_t d, uint32_t x, uint32_t y, int M, int N, bool accumulate) {
+  const uint32_t idesc = make_idesc_bf16(M, N, 1, 1);
+  for (int ks = 0; ks < 8; ++ks)
+    mma_bf16_ss(d, make_smem_desc(x + ks * 256, 128, 2048), make_smem_desc(y + ks * 256, 128, 2048), idesc, accumulate || ks > 0);
+}
+// D[M x 16] (+)= X^T 1: column sums of a 128-row buffer (ones operand: K-major [16][128])
+__device__ __forceinline__ void issue_colsum(uint32_t d, uint32_t x, uint32_t ones, int M, bool accumulate) {
+  const uint32_t idesc = make_idesc_bf16(M, 16, 1, 0);
+  for (int ks = 0; ks < 8; ++ks)
+    mma_bf16_ss(d, make_smem_desc(x + ks * 256, 128, 2048), make_smem_desc(ones + ks * 512, 256, 128), idesc, accumulate || ks > 0);
+}
+
+__device__ __forceinline__ int tiles_of_jet(const MPLayout& L) {
+  int n = 0;
+  const int njb = (L.N + 31) / 32;
+  for (int i0 = 0; i0 < L.N; i0 += GJ_IB) n += ((min(GJ_IB, L.N - i0) + 3) / 4) * njb;
+  return n;
+}
+
+template <int NWG, int E0P>
+__global__ void __launch_bounds__(NWG * 128 + 32, 1)
+edge_bwd_tc_kernel(const MPLayout L, const BwdPlan T, const float* __restrict__ h, const float* __restrict__ pq,
+                   const float* __restrict__ params, const float* __restrict__ de, float* __restrict__ dpq,
+                   float* __restrict__ dh, float* __restrict__ part) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int NT = NWG * 128 + 32;
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const bool is_issuer = warp == NWG * 4;
+  float* smf = reinterpret_cast<float*>(smem + T.o_shared_f32);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T.o_bar);   // ready[wg] = bars[wg], done[wg] = bars[NWG + wg]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + T.o_tmem_slot);
+  const int Le = L.Le;
+
+  stage_small(L, params, smf, tid, NT);
+  stage_edge_weights_bf16(L, T.o_wT, params, smem, tid, NT);
+  for (int idx = tid; idx < 16 * 128; idx += NT) reinterpret_cast<__nv_bfloat16*>(smem + T.o_ones)[idx] = __float2bfloat16_rn(1.f);
+  if (tid == 0) {
+    for (int w = 0; w < NWG; ++w) { mbar_init(bars + w, 128); mbar_init(bars + NWG + w, 1); }
+    fence_barrier_init();
+  }
+  if (is_issuer) tmem_alloc(tmem_slot, (uint32_t)T.tmem_cols);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int jets_total = L.B;
+
+  if (is_issuer) {
+    // =================================== MMA issuer ===================================
+    if (lane == 0) {
+      const int S = 2 * (Le - 1);
+      const int tpj = tiles_of_jet(L);
+      int total[NWG], done_st[NWG];
+      uint32_t par[NWG];
+      bool any = false;
+      for (int w = 0; w < NWG; ++w) {
+        const int first = blockIdx.x * NWG + w;
+        const int njets = first < jets_total ? (jets_total - first + gridDim.x * NWG - 1) / (gridDim.x * NWG) : 0;
+        total[w] = njets * tpj * S; done_st[w] = 0; par[w] = 0;
+        any |= total[w] > 0;
+      }
+      uint32_t inited = 0;    // bit l: weight-gradient accumulator l has been written; bit 31: the bias accumulators
+      while (any) {
+        any = false;
+        for (int w = 0; w < NWG; ++w) {
+          if (done_st[w] >= total[w]) continue;
+          mbar_wait(bars + w, par[w]);
+          par[w] ^= 1u;
+          tc_fence_after();
+          const uint32_t wgb = smem_u32(smem + T.wg_base + w * T.wg_stride);
+          const uint32_t a0 = wgb + T.w_a0, comb = wgb + T.w_comb;
+          const uint32_t acc = tmem_base + (uint32_t)(w * T.nacc);
+          const int s = done_st[w] % S;
+          if (s < Le - 1) {
+            const int l = s + 1;
+            const uint32_t ain = l == 1 ? a0 : comb + (T.coff[l - 1] >> 3) * 2048;
+            issue_fwd(acc, ain, smem_u32(smem + T.o_wT[l]), L.Ep[l], L.Kp[l]);
+          } else {
+            const int l = Le - 1 - (s - (Le - 1));
+            const uint32_t dz = comb + (T.coff[l] >> 3) * 2048;
+            const uint32_t ain = l == 1 ? a0 : comb + (T.coff[l - 1] >> 3) * 2048;
+            const bool accumulate = (inited >> l) & 1u;          // the first batch into an accumulator initialises it
+            inited |= 1u << l;
+            if (T.wg_orient[l] == 0) issue_wgrad(tmem_base + T.t_wg[l], dz, ain, T.wg_M[l], T.wg_N[l], accumulate);
+            else                     issue_wgrad(tmem_base + T.t_wg[l], ain, dz, T.wg_M[l], T.wg_N[l], accumulate);
+            issue_dgrad(acc, dz, smem_u32(smem + T.o_wT[l]), L.Kp[l], L.Ep[l]);
+            if (l == 1) {
+              const bool bacc = (inited >> 31) & 1u;
+              inited |= 1u << 31;
+              for (int b = 0; b < T.nbias; ++b)
+                issue_colsum(tmem_base + T.t_bias[b], comb + b * 16 * 2048, smem_u32(smem + T.o_ones), T.bias_M[b], bacc);
+            }
+          }
+          mma_commit(bars + NWG + w);
+          ++done_st[w];
+          any |= done_st[w] < total[w];
+        }
+        for (int w = 0; w < NWG; ++w) any |= done_st[w] < total[w];
+      }
+    }
+    __syncwarp();
+  } else {
+    // =================================== compute warpgroups ===================================
+    const int wg = tid >> 7, t = tid & 127, wq = t >> 5;
+    uint8_t* wgb = smem + T.wg_base + wg * T.wg_stride;
+    float* wgf = reinterpret_cast<float*>(wgb + T.w_f32);
+    uint8_t* A0 = wgb + T.w_a0;
+    uint8_t* COMB = wgb + T.w_comb;
+    uint64_t* ready = bars + wg;
+    uint64_t* done = bars + NWG + wg;
+    const uint32_t tmem_row = tmem_base + (uint32_t)(wg * T.nacc) + ((uint32_t)(wq * 32) << 16);
+    uint32_t phase = 0;
+    const int bar_id = 1 + wg;
+    float* sm_h = wgf + L.o_h;
+    float* sm_hj = wgf + L.o_hj;
+    float* sm_Q = wgf + L.o_Q;
+    float* sm_P = wgf + L.o_P;
+    float* sm_de = wgf + L.o_e;
+    float* sm_dP = wgf + L.o_dP;
+    float* sm_dQ = wgf + L.o_dQ;
+    float* sm_dh = wgf + L.o_dh;
+    float* sm_G = wgf + L.o_G;
+    const float* wd = smf + L.o_wd;
+    const int H = L.H, W2 = 2 * L.E0p;
+    float dwd[E0P];
+#pragma unroll
+    for (int c = 0; c < E0P; ++c) dwd[c] = 0.f;
+
+    for (int jet = blockIdx.x * NWG + wg; jet < L.B; jet += gridDim.x * NWG) {
+      const float* hjet = h + (size_t)jet * L.N * L.ld;
+      const float* pqjet = pq + (size_t)jet * L.N * W2;
+      float* dpqjet = dpq + (size_t)jet * L.N * W2;
+      float* dhjet = dh + (size_t)jet * L.N * L.ld;
+      for (int i0 = 0; i0 < L.N; i0 += GJ_IB) {
+        const int ni = min(GJ_IB, L.N - i0);
+        named_bar_sync(bar_id, 128);
+        wg_load_block(L, hjet, pqjet, 0, i0, sm_h, sm_P, t);
+        for (int idx = t; idx < GJ_IB * L.ELs; idx += 128) {
+          int n = idx / L.ELs, c = idx - n * L.ELs;
+          sm_de[idx] = (n < ni && c < L.EL) ? __ldg(de + ((size_t)jet * L.N + i0 + n) * L.EL + c) : 0.f;
+        }
+        for (int idx = t; idx < GJ_IB * L.E0s; idx += 128) sm_dP[idx] = 0.f;
+        for (int idx = t; idx < GJ_IB * L.Hs; idx += 128) sm_dh[idx] = 0.f;
+        for (int j0 = 0; j0 < L.N; j0 += 32) {
+          const int nj = min(32, L.N - j0);
+          named_bar_sync(bar_id, 128);
+          wg_load_block(L, hjet, pqjet, 1, j0, sm_hj, sm_Q, t);
+          for (int idx = t; idx < 32 * L.E0s; idx += 128) sm_dQ[idx] = 0.f;
+          for (int idx = t; idx < GJ_IB * L.Gs; idx += 128) sm_G[idx] = 0.f;
+          float dq[E0P];
+#pragma unroll
+          for (int c = 0; c < E0P; ++c) dq[c] = 0.f;
+          named_bar_sync(bar_id, 128);
+          const int nit = (ni + 3) / 4;
+          for (int it = 0; it < nit; ++it) {
+            const int il = it * 4 + wq;
+            const bool valid = il < ni && lane < nj;
+            const float dij = tc_layer0(L, sm_h, sm_hj, sm_P, sm_Q, wd, A0, il, lane, t);
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(ready);
+            // ---- forward stages ----
+            for (int l = 1; l < Le; ++l) {
+              mbar_wait(done, phase); phase ^= 1u;
+              tc_fence_after();
+              const bool last = (l == Le - 1);
+              const float* bias = smf + L.o_bE[l];
+              uint8_t* out = COMB + (T.coff[l] >> 3) * 2048 + t * 16;
+              for (int c0 = 0; c0 < L.Ep[l]; c0 += 16) {
+                float v[16];
+                tmem_ld16(tmem_row + (uint32_t)c0, v);
+                if (!last) {
+#pragma unroll
+                  for (int q = 0; q < 16; ++q) v[q] = gj_leaky(v[q] + bias[c0 + q], L.alpha);
+                } else {
+                  // dz_last = de_i * leaky'(z_last), zero on padded rows (this masks everything downstream)
+                  const float* dei = sm_de + il * L.ELs + c0;
+#pragma unroll
+                  for (int q = 0; q < 16; ++q) {
+                    const float z = v[q] + bias[c0 + q];
+                    v[q] = valid ? dei[q] * (z > 0.f ? 1.f : L.alpha) : 0.f;
+                  }
+                }
+                uint4 p0 = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                uint4 p1 = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+                *reinterpret_cast<uint4*>(out + (c0 >> 3) * 2048) = p0;
+                *reinterpret_cast<uint4*>(out + ((c0 >> 3) + 1) * 2048) = p1;
+              }
+              fence_proxy_async();
+              tc_fence_before();
+              mbar_arrive(ready);
+            }
+            // ---- backward stages ----
+            for (int l = Le - 1; l >= 1; --l) {
+              mbar_wait(done, phase); phase ^= 1u;
+              tc_fence_after();
+              if (l > 1) {
+                // dz_{l-1} = da_{l-1} * leaky'(a_{l-1}), in place over a_{l-1}
+                uint8_t* buf = COMB + (T.coff[l - 1] >> 3) * 2048 + t * 16;
+                for (int c0 = 0; c0 < L.Kp[l]; c0 += 16) {
+                  float v[16], a[16];
+                  tmem_ld16(tmem_row + (uint32_t)c0, v);
+                  unpack_bf16x8(*reinterpret_cast<const uint4*>(buf + (c0 >> 3) * 2048), a);
+                  unpack_bf16x8(*reinterpret_cast<const uint4*>(buf + ((c0 >> 3) + 1) * 2048), a + 8);
+#pragma unroll
+                  for (int q = 0; q < 16; ++q) v[q] *= (a[q] > 0.f ? 1.f : L.alpha);
+                  uint4 p0 = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                  uint4 p1 = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+                  *reinterpret_cast<uint4*>(buf + (c0 >> 3) * 2048) = p0;
+                  *reinterpret_cast<uint4*>(buf + ((c0 >> 3) + 1) * 2048) = p1;
+                }
+                fence_proxy_async();
+                tc_fence_before();
+                mbar_arrive(ready);
+              } else {
+                // dz_0 = da_0 * leaky'(a_0), consumed in fp32: G_ij, dQ_j, dP_i, d(wd)
+                float g = 0.f;
+#pragma unroll
+                for (int c0 = 0; c0 < E0P; c0 += 16) {
+                  float v[16], a[16];
+                  tmem_ld16(tmem_row + (uint32_t)c0, v);
+                  unpack_bf16x8(*reinterpret_cast<const uint4*>(A0 + (c0 >> 3) * 2048 + t * 16), a);
+                  unpack_bf16x8(*reinterpret_cast<const uint4*>(A0 + ((c0 >> 3) + 1) * 2048 + t * 16), a + 8);
+#pragma unroll
+                  for (int q = 0; q < 16; ++q) {
+                    v[q] *= (a[q] > 0.f ? 1.f : L.alpha);
+                    g = fmaf(v[q], wd[c0 + q], g);
+                    dq[c0 + q] += v[q];
+                    dwd[c0 + q] = fmaf(v[q], dij, dwd[c0 + q]);
+                  }
+                  const float s = warp_transpose_sum16(v, lane);
+                  if ((lane & 1) == 0) sm_dP[il * L.E0s + c0 + (lane >> 1)] += s;
+                }
+                sm_G[il * L.Gs + lane] = g;
+                tc_fence_before();
+              }
+            }
+          }
+          // ---- (i block, j block) epilogue ----
+          for (int w = 0; w < 4; ++w) {           // dQ_j: the four warps hold different i's of the same j
+            if (wq == w) {
+#pragma unroll
+              for (int c = 0; c < E0P; ++c) sm_dQ[lane * L.E0s + c] += dq[c];
+            }
+            named_bar_sync(bar_id, 128);
+          }
+          for (int idx = t; idx < nj * L.E0p; idx += 128) {
+            int n = idx / L.E0p, c = idx - n * L.E0p;
+            float* p = dpqjet + (size_t)(j0 + n) * W2 + L.E0p + c;
+            float v = sm_dQ[n * L.E0s + c];
+            *p = (i0 == 0) ? v : (*p + v);
+          }
+          for (int idx = t; idx < nj * H; idx += 128) {
+            int n = idx / H, k = idx - n * H;
+            const float sgn = (L.mink && k > 0) ? -2.f : 2.f;
+            const float hjk = sm_hj[n * L.Hs + k];
+            float acc = 0.f;
+            for (int i = 0; i < ni; ++i) acc = fmaf(sm_G[i * L.Gs + n], hjk - sm_h[i * L.Hs + k] + GJ_EPS, acc);
+            if (k < L.cols) dhjet[(size_t)(j0 + n) * L.ld + k] += sgn * acc;
+          }
+          for (int idx = t; idx < ni * H; idx += 128) {
+            int n = idx / H, k = idx - n * H;
+            const float sgn = (L.mink && k > 0) ? -2.f : 2.f;
+            const float hik = sm_h[n * L.Hs + k];
+            float acc = 0.f;
+            for (int j = 0; j < nj; ++j) acc = fmaf(sm_G[n * L.Gs + j], sm_hj[j * L.Hs + k] - hik + GJ_EPS, acc);
+            sm_dh[n * L.Hs + k] -= sgn * acc;
+          }
+        }
+        named_bar_sync(bar_id, 128);
+        for (int idx = t; idx < ni * L.E0p; idx += 128) {
+          int n = idx / L.E0p, c = idx - n * L.E0p;
+          dpqjet[(size_t)(i0 + n) * W2 + c] = sm_dP[n * L.E0s + c];
+        }
+        for (int idx = t; idx < ni * L.cols; idx += 128) {
+          int n = idx / L.cols, k = idx - n * L.cols;
+          dhjet[(size_t)(i0 + n) * L.ld + k] += sm_dh[n * L.Hs + k];
+        }
+      }
+    }
+    // d(wd)[c] = sum over this warpgroup's rows: lanes by shuffles, warps through shared memory (fixed order)
+    named_bar_sync(bar_id, 128);
+    float* red = sm_dQ;    // [4][E0P]
+#pragma unroll
+    for (int c = 0; c < E0P; ++c) {
+      const float s = gj_warp_sum(dwd[c]);
+      if (lane == 0) red[wq * E0P + c] = s;
+    }
+    named_bar_sync(bar_id, 128);
+    for (int c = t; c < E0P; c += 128) smf[L.o_dpar + wg * L.E0p + c] = (red[c] + red[E0P + c]) + (red[2 * E0P + c] + red[3 * E0P + c]);
+  }
+
+  // =================================== gradient read-out ===================================
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  float* out = part + (size_t)blockIdx.x * L.pV[0];
+  if (!is_issuer) {
+    const int wq = warp & 3, wgi = warp >> 2;
+    const bool wrote = (blockIdx.x * NWG) < jets_total;     // a CTA without jets never initialised its accumulators
+    // wd column
+    for (int c = tid; c < L.E[0]; c += NWG * 128) {
+      float s = 0.f;
+      for (int w = 0; w < NWG; ++w) s += smf[L.o_dpar + w * L.E0p + c];
+      out[L.pW[0] + c * L.K[0] + 2 * L.H] = wrote ? s : 0.f;
+    }
+    // weight gradients: accumulator row m <-> lane (M = 128: lane m; M = 64: lane (m / 16) * 32 + m % 16)
+    for (int l = 1; l < Le; ++l) {
+      const int M = T.wg_M[l], N = T.wg_N[l];
+      const int m = M == 128 ? wq * 32 + lane : (lane < 16 ? wq * 16 + lane : -1);
+      const int nchunks = N / 16;
+      for (int ch = wgi; ch < nchunks; ch += NWG) {       // warp-uniform: every lane of the warp issues the load
+        float v[16];
+        tmem_ld16(tmem_base + (uint32_t)(T.t_wg[l] + ch * 16) + ((uint32_t)(wq * 32) << 16), v);
+        if (m < 0) continue;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const int n = ch * 16 + q;
+          const int c = T.wg_orient[l] == 0 ? m : n;       // out feature
+          const int k = T.wg_orient[l] == 0 ? n : m;       // in feature
+          if (c < L.E[l] && k < L.K[l]) out[L.pW[l] + c * L.K[l] + k] = wrote ? v[q] : 0.f;
+        }
+      }
+    }
+    // bias gradients: column sums of the combined dz buffer, chunk b covers columns [128 b, 128 b + M)
+    if (wgi == 0) {
+      for (int b = 0; b < T.nbias; ++b) {
+        float v[16];
+        tmem_ld16(tmem_base + (uint32_t)T.t_bias[b] + ((uint32_t)(wq * 32) << 16), v);
+        const int M = T.bias_M[b];
+        const int m = M == 128 ? wq * 32 + lane : (lane < 16 ? wq * 16 + lane : -1);
+        if (m < 0) continue;
+        const int col = b * 128 + m;
+        for (int l = 1; l < Le; ++l) {
+          const int c = col - T.coff[l];
+          if (c >= 0 && c < L.E[l]) out[L.pb[l] + c] = wrote ? v[0] : 0.f;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (is_issuer) tmem_dealloc(tmem_base, (uint32_t)T.tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------
 // tcgen05 self-test: one CTA, D = A * B^T with selectable operand major-ness; dumps raw TMEM.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128, 1)
@@ -323,12 +835,61 @@ int gj_edge_fwd_tc(MPLayout L, const float* h, const float* pq, const float* par
   return GJ_OK;
 }
 
-size_t gj_edge_bwd_tc_ws_floats(const MPLayout& L) { return (size_t)gj_edge_grid(L.B) * L.pV[0]; }
+int gj_reduce_edge_partials(const MPLayout& L, const float* part, int nparts, float* dparams, cudaStream_t stream);
+
+static int tc_bwd_grid(int batch, int nwg) {
+  int sms = gj_num_sms();
+  int grid = (batch + nwg - 1) / nwg;
+  return grid > sms ? sms : (grid < 1 ? 1 : grid);
+}
+
+size_t gj_edge_bwd_tc_ws_floats(const MPLayout& L) {
+  // large enough for either backward (tensor-core or the SIMT fallback for unsupported widths)
+  size_t a = (size_t)gj_edge_grid(L.B) * L.pV[0], b = (size_t)tc_bwd_grid(L.B, 2) * L.pV[0];
+  return a > b ? a : b;
+}
+
+template <int E0P>
+static int launch_tc_bwd(const MPLayout& L, const BwdPlan& T, const float* h, const float* pq, const float* params,
+                         const float* de, float* dpq, float* dh, float* part, int grid, cudaStream_t stream) {
+  constexpr int NWG = 2;
+  auto kern = edge_bwd_tc_kernel<NWG, E0P>;
+  cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T.smem_bytes);
+  if (ce != cudaSuccess) { gj_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
+  kern<<<grid, NWG * 128 + 32, T.smem_bytes, stream>>>(L, T, h, pq, params, de, dpq, dh, part);
+  ce = cudaGetLastError();
+  if (ce != cudaSuccess) { gj_set_error("edge_bwd_tc launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
+  return GJ_OK;
+}
 
 int gj_edge_bwd_tc(MPLayout L, const float* h, const float* pq, const float* params, const float* de, float* dpq, float* dh,
                    float* dparams, float* part, cudaStream_t stream) {
-  // interim: the tensor-core backward is being written; the bf16 mode's gradient runs the fp32 SIMT kernel.
-  return gj_edge_bwd_simt(L, h, pq, params, de, dpq, dh, dparams, part, stream);
+  BwdPlan T;
+  MPLayout Lt = L;
+  if (plan_tc_bwd(&Lt, &T, 2)) {
+    // widths the tensor-core backward does not cover (first layer wider than 64, layers wider than 128 on both sides,
+    // more than 512 combined dz columns): the fp32 kernel computes the gradient instead
+    return gj_edge_bwd_simt(L, h, pq, params, de, dpq, dh, dparams, part, stream);
+  }
+  const int grid = tc_bwd_grid(Lt.B, 2);
+  int rc;
+  switch (Lt.E0p) {
+    case 16: rc = launch_tc_bwd<16>(Lt, T, h, pq, params, de, dpq, dh, part, grid, stream); break;
+    case 32: rc = launch_tc_bwd<32>(Lt, T, h, pq, params, de, dpq, dh, part, grid, stream); break;
+    case 48: rc = launch_tc_bwd<48>(Lt, T, h, pq, params, de, dpq, dh, part, grid, stream); break;
+    default: rc = launch_tc_bwd<64>(Lt, T, h, pq, params, de, dpq, dh, part, grid, stream); break;
+  }
+  if (rc) return rc;
+  return gj_reduce_edge_partials(Lt, part, grid, dparams, stream);
+}
+
+// info[0..3]: forward smem bytes, forward TMEM columns, backward smem bytes (0 = fp32 fallback), backward TMEM columns
+void gj_tc_plan_info(MPLayout L, int* info) {
+  TCPlan F; MPLayout Lf = L; plan_tc_fwd(&Lf, &F, 2);
+  info[0] = F.smem_bytes; info[1] = F.tmem_cols_total;
+  BwdPlan T; MPLayout Lb = L;
+  if (L.Le < 2 || plan_tc_bwd(&Lb, &T, 2)) { info[2] = 0; info[3] = 0; }
+  else { info[2] = T.smem_bytes; info[3] = T.tmem_cols; }
 }
 
 int gj_umma_selftest_launch(int M, int N, int K, int a_mn, int b_mn, const float* a, const float* b, float* out,

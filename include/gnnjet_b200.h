@@ -135,6 +135,11 @@ size_t gj_linear_bwd_workspace(int32_t rows, int32_t in_f, int32_t out_f);
 int gj_linear_bwd(int32_t rows, int32_t in_f, int32_t out_f, const float* x, const float* w, const float* dy,
                   float* dx, float* dw, float* db, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Resource plan of the tensor-core (GJ_PREC_BF16) edge kernels for this step (host only, no device work):
+ * info[0] forward shared-memory bytes per CTA, info[1] forward TMEM columns, info[2] backward shared-memory bytes
+ * (0: these widths are not covered and the backward runs the fp32 kernel), info[3] backward TMEM columns. */
+int gj_mp_plan_info(const gj_mp_desc* d, int32_t* info);
+
 /* tcgen05 self-test: D(128 x n) = A(128 x k) * B(n x k)^T on one CTA with bf16 operands laid out
  * in the kernels' interleaved shared-memory layout; a_major/b_major: 0 = K-major, 1 = MN-major.
  * a_host_layout: A given as (128,k) row-major floats, B as (n,k) row-major floats (device pointers);

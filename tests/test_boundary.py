@@ -154,6 +154,17 @@ def test_c_abi_library_exports_every_declared_symbol():
     assert ctypes.sizeof(_lib.MPDesc) == 4 * (3 + 1 + 8 + 1 + 8 + 1 + 2 + 2)
 
 
+def test_tensor_core_plans_fit_the_sm():
+    """Shared-memory / TMEM plans of the tcgen05 kernels for the BASELINE architecture (host-only entry point)."""
+    lib = _lib.load()
+    for N, H, nw in ((30, 16, [16, 32]), (30, 32, [32, 8]), (30, 8, [8, 20]), (150, 32, [32, 8])):
+        d = _lib.make_desc(4096, N, H, [32, 128, 64, 16], nw, 0.2, 0, 1)
+        info = (ctypes.c_int32 * 4)()
+        assert lib.gj_mp_plan_info(d, info) == 0
+        assert 0 < info[0] <= 227 * 1024 and info[1] <= 512
+        assert 0 < info[2] <= 227 * 1024 and info[3] <= 512, list(info)   # tensor-core backward covers these widths
+
+
 def test_sass_uses_tcgen05_and_tmem():
     """The built library must contain Blackwell tensor-core SASS (UTC*MMA / LDTM), B200_PROFILING.md."""
     import shutil
