@@ -11,6 +11,8 @@
 // While one warpgroup runs an epilogue, the other's MMAs occupy the tensor pipe.  Edge activations never leave
 // the SM.  Replaces the edge part of reference models/graphnet.py:154-168 and its autograd adjoint.
 #include "gj_common.cuh"
+#include <stdlib.h>
+
 #include "umma.cuh"
 
 namespace {
@@ -26,7 +28,7 @@ int next_pow2_cols(int c) { int p = 32; while (p < c) p <<= 1; return p; }
 
 struct TCPlan {
   int nwg;
-  int o_bar, o_tmem_slot;
+  int o_bar, o_tmem_slot, o_tbl;
   int o_wT[GJ_MAX_LAYERS];  // bf16 interleaved edge weights, layers >= 1 (bytes from smem base)
   int o_shared_f32;         // float region shared by all warpgroups (biases, wd)
   int wg_base, wg_stride;   // per-warpgroup region
@@ -52,6 +54,7 @@ void plan_tc_fwd(MPLayout* L, TCPlan* T, int nwg) {
   int off = 0;
   T->o_bar = off; off += 64;
   T->o_tmem_slot = off; off += 64;
+  T->o_tbl = off; off += gj_round_up(nwg * GJ_MAX_LAYERS * 40, 128);
   for (int l = 1; l < L->Le; ++l) { T->o_wT[l] = off; off += L->Ep[l] * L->Kp[l] * 2; }
   T->o_shared_f32 = off; off += c.off * 4;
   off = gj_round_up(off, 128);
@@ -88,26 +91,23 @@ __device__ void stage_edge_weights_bf16(const MPLayout& L, const int* o_wT, cons
   }
 }
 
-// rows [r0, r0 + 32) of h (zero padded) and of the P or Q half of PQ, by one warpgroup
+// rows [r0, r0 + 32) of h (zero padded) and of the P or Q half of PQ, by one warpgroup.  Loads are batched
+// (all of a thread's global loads are issued before the first use) and 16 bytes wide where the layout allows.
 __device__ void wg_load_block(const MPLayout& L, const float* __restrict__ hjet, const float* __restrict__ pqjet, int half,
                               int r0, float* sh, float* spq, int t) {
+  const int q4 = L.E0p >> 2;                       // float4 per P/Q row (E0p is a multiple of 16)
+#pragma unroll 2
+  for (int idx = t; idx < 32 * q4; idx += 128) {
+    const int n = idx / q4, c = (idx - n * q4) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r0 + n < L.N) v = __ldg(reinterpret_cast<const float4*>(pqjet + (size_t)(r0 + n) * 2 * L.E0p + half * L.E0p + c));
+    float* d = spq + n * L.E0s + c;
+    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+  }
+#pragma unroll 4
   for (int idx = t; idx < 32 * L.H; idx += 128) {
     int n = idx / L.H, k = idx - n * L.H;
     sh[n * L.Hs + k] = (r0 + n < L.N && k < L.cols) ? __ldg(hjet + (size_t)(r0 + n) * L.ld + k) : 0.f;
-  }
-  for (int idx = t; idx < 32 * L.E0p; idx += 128) {
-    int n = idx / L.E0p, c = idx - n * L.E0p;
-    spq[n * L.E0s + c] = (r0 + n < L.N) ? __ldg(pqjet + (size_t)(r0 + n) * 2 * L.E0p + half * L.E0p + c) : 0.f;
-  }
-}
-
-// D[128 x N](tmem) = A[128 x K](smem, K-major, 128 rows) * W[N x K]^T (smem, K-major, N rows)
-__device__ __forceinline__ void issue_layer_mma(uint32_t d_tmem, uint32_t a_saddr, uint32_t w_saddr, int N, int K) {
-  const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
-  for (int ks = 0; ks < K / 16; ++ks) {
-    uint64_t ad = make_smem_desc(a_saddr + ks * (2 * 128 * 16), 128 * 16, 128);
-    uint64_t bd = make_smem_desc(w_saddr + ks * (2 * N * 16), N * 16, 128);
-    mma_bf16_ss(d_tmem, ad, bd, idesc, ks > 0 ? 1u : 0u);
   }
 }
 
@@ -127,117 +127,267 @@ __device__ __forceinline__ float tc_layer0(const MPLayout& L, const float* sm_h,
   for (int c0 = 0; c0 < L.E0p; c0 += 8) {
     float v[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) v[q] = gj_leaky(P[c0 + q] + Q[c0 + q] + wd[c0 + q] * d, L.alpha);
+    for (int q = 0; q < 8; ++q) v[q] = gj_leaky2(fmaf(wd[c0 + q], d, P[c0 + q] + Q[c0 + q]), L.alpha, L.alpha <= 1.f);
     uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
     *reinterpret_cast<uint4*>(a0 + (c0 >> 3) * 2048 + t * 16) = pk;
   }
   return d;
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// transpose-reduce of 16 per-lane values over the 32 lanes of a warp: returns, in every lane, the sum over all lanes
+// of channel (lane >> 1) & 15   (31 adds + 16 shuffles instead of 80 + 80)
+__device__ __forceinline__ float warp_transpose_sum16(const float (&v)[16], int lane) {
+  float w8[8], w4[4], w2[2];
+  bool up = lane & 16;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    float send = up ? v[q] : v[q + 8], keep = up ? v[q + 8] : v[q];
+    w8[q] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+  up = lane & 8;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float send = up ? w8[q] : w8[q + 4], keep = up ? w8[q + 4] : w8[q];
+    w4[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  up = lane & 4;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    float send = up ? w4[q] : w4[q + 2], keep = up ? w4[q + 2] : w4[q];
+    w2[q] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  up = lane & 2;
+  float send = up ? w2[0] : w2[1], keep = up ? w2[1] : w2[0];
+  float w1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  return w1 + __shfl_xor_sync(0xffffffffu, w1, 1);
+}
+
+// ---- the issuer's MMA batches -----------------------------------------------------------------------------
+// A/B K-major buffer with nrows rows: next 8 rows +128 B (SBO), next 8 columns +nrows*16 B (LBO), 16 columns per MMA
+// A/B MN-major view of the same bytes (MN = column, K = row): next 8 columns +nrows*16 B (SBO), next 8 rows +128 B (LBO)
+// One group = the k-steps of one GEMM: descriptors of k-step 0 plus the per-step advance, built once per kernel.
+struct MmaGroup {
+  unsigned long long a, b;
+  uint32_t d, idesc, astep, bstep;   // astep/bstep in 16-byte units
+  int nk, accbit;                    // accbit >= 0: shared accumulator id (accumulate unless it is the first write)
+};
+
+static_assert(sizeof(MmaGroup) == 40, "plan_tc_bwd reserves 40 bytes per group");
+
+__device__ __forceinline__ MmaGroup grp_fwd(uint32_t d, uint32_t a, uint32_t w, int N, int K) {
+  // acc[128 x N] = act[128 x K] W[N x K]^T, both K-major
+  return MmaGroup{make_smem_desc(a, 2048, 128), make_smem_desc(w, N * 16, 128), d, make_idesc_bf16(128, N, 0, 0), 4096u >> 4,
+                  (uint32_t)(2 * N * 16) >> 4, K / 16, -1};
+}
+__device__ __forceinline__ MmaGroup grp_dgrad(uint32_t d, uint32_t dz, uint32_t w, int Kin, int Eout) {
+  // acc[128 x Kin] = dz[128 x Eout] W[Eout x Kin]: A = dz K-major, B = W viewed MN-major (MN = in feature, K = out feature)
+  return MmaGroup{make_smem_desc(dz, 2048, 128), make_smem_desc(w, 128, Eout * 16), d, make_idesc_bf16(128, Kin, 0, 1), 4096u >> 4,
+                  256u >> 4, Eout / 16, -1};
+}
+__device__ __forceinline__ MmaGroup grp_wgrad(uint32_t d, uint32_t x, uint32_t y, int M, int N, int accbit) {
+  // D[M x N] += X^T Y over the 128 tile rows: both operands MN-major views of 128-row buffers
+  return MmaGroup{make_smem_desc(x, 128, 2048), make_smem_desc(y, 128, 2048), d, make_idesc_bf16(M, N, 1, 1), 256u >> 4, 256u >> 4, 8,
+                  accbit};
+}
+__device__ __forceinline__ MmaGroup grp_colsum(uint32_t d, uint32_t x, uint32_t ones, int M, int accbit) {
+  // D[M x 16] += X^T 1: column sums of a 128-row buffer (ones operand: K-major [16][128])
+  return MmaGroup{make_smem_desc(x, 128, 2048), make_smem_desc(ones, 256, 128), d, make_idesc_bf16(M, 16, 1, 0), 256u >> 4, 512u >> 4, 8,
+                  accbit};
+}
+// executed by all 32 lanes of the issuer warp (convergent); fields are broadcast so they live in uniform registers
+__device__ __forceinline__ void run_group(const MmaGroup* g, uint32_t& inited) {
+  const uint64_t a = uni64(g->a), b = uni64(g->b);
+  const uint32_t d = uni(g->d), idesc = uni(g->idesc), astep = uni(g->astep), bstep = uni(g->bstep);
+  const int nk = (int)uni((uint32_t)g->nk), accbit = (int)uni((uint32_t)g->accbit);
+  uint32_t accumulate = 0;
+  if (accbit >= 0) { accumulate = (inited >> accbit) & 1u; inited |= 1u << accbit; }
+  for (int ks = 0; ks < nk; ++ks)
+    mma_bf16_ss_elect(d, desc_advance(a, astep, ks), desc_advance(b, bstep, ks), idesc, (accumulate | (uint32_t)(ks > 0)));
+}
+
+__device__ __forceinline__ int tiles_of_jet(const MPLayout& L) {
+  int n = 0;
+  const int njb = (L.N + 31) / 32;
+  for (int i0 = 0; i0 < L.N; i0 += GJ_IB) n += ((min(GJ_IB, L.N - i0) + 3) / 4) * njb;
+  return n;
+}
+
+// Handshake between the compute warpgroups and the MMA-issuer warp (both tensor-core kernels):
+//   warpgroup: write operands to smem -> fence.proxy.async -> arrive(ready[wg])      wait(done[wg]) -> epilogue from TMEM
+//   issuer   : wait(ready[wg]) -> issue the stage's tcgen05.mma batch -> tcgen05.commit -> arrive(done[wg])
+// The issuer warp runs warp-convergent code only, so its descriptors stay in uniform registers.
+
 template <int NWG>
-__global__ void __launch_bounds__(NWG * 128, 1)
+__global__ void __launch_bounds__(NWG * 128 + 32, 1)
 edge_fwd_tc_kernel(const MPLayout L, const TCPlan T, const float* __restrict__ h, const float* __restrict__ pq,
                    const float* __restrict__ params, float* __restrict__ e_out) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  constexpr int NT = NWG * 128;
-  const int tid = threadIdx.x, wg = tid >> 7, t = tid & 127, wq = t >> 5, lane = t & 31;
+  constexpr int NT = NWG * 128 + 32;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = (int)uni((uint32_t)(tid >> 5));     // provably warp-uniform
+  const bool is_issuer = warp == NWG * 4;
   float* smf = reinterpret_cast<float*>(smem + T.o_shared_f32);
-  uint8_t* wgb = smem + T.wg_base + wg * T.wg_stride;
-  float* wgf = reinterpret_cast<float*>(wgb + T.w_f32);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + T.o_bar) + wg;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T.o_bar);   // ready[wg] = bars[wg], done[wg] = bars[NWG + wg]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + T.o_tmem_slot);
+  const int Le = L.Le;
 
   stage_small(L, params, smf, tid, NT);
   stage_edge_weights_bf16(L, T.o_wT, params, smem, tid, NT);
   if (tid == 0) {
-    for (int w = 0; w < NWG; ++w) mbar_init(reinterpret_cast<uint64_t*>(smem + T.o_bar) + w, 1);
+    for (int w = 0; w < NWG; ++w) { mbar_init(bars + w, 128); mbar_init(bars + NWG + w, 1); }
     fence_barrier_init();
   }
-  if (tid < 32) tmem_alloc(tmem_slot, (uint32_t)T.tmem_cols_total);
+  if (is_issuer) tmem_alloc(tmem_slot, (uint32_t)T.tmem_cols_total);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_d = tmem_base + (uint32_t)(wg * T.tmem_cols_per_wg);
-  const uint32_t tmem_row = tmem_d + ((uint32_t)(wq * 32) << 16);
-  uint32_t phase = 0;
-  const int bar_id = 1 + wg;
-  float* sm_h = wgf + L.o_h;
-  float* sm_hj = wgf + L.o_hj;
-  float* sm_Q = wgf + L.o_Q;
-  float* sm_P = wgf + L.o_P;
-  float* sm_e = wgf + L.o_e;
-  const float* wd = smf + L.o_wd;
 
-  for (int jet = blockIdx.x * NWG + wg; jet < L.B; jet += gridDim.x * NWG) {
-    const float* hjet = h + (size_t)jet * L.N * L.ld;
-    const float* pqjet = pq + (size_t)jet * L.N * 2 * L.E0p;
-    for (int i0 = 0; i0 < L.N; i0 += GJ_IB) {
-      const int ni = min(GJ_IB, L.N - i0);
-      named_bar_sync(bar_id, 128);
-      wg_load_block(L, hjet, pqjet, 0, i0, sm_h, sm_P, t);
-      for (int idx = t; idx < GJ_IB * L.ELs; idx += 128) sm_e[idx] = 0.f;
-      for (int j0 = 0; j0 < L.N; j0 += 32) {
-        const int nj = min(32, L.N - j0);
+  if (is_issuer) {
+    // =================================== MMA issuer (warp-convergent) ===================================
+    const int S = Le - 1;
+    const int tpj = tiles_of_jet(L);
+    int total[NWG], done_st[NWG];
+    uint32_t par[NWG];
+    bool any = false;
+#pragma unroll
+    for (int w = 0; w < NWG; ++w) {
+      const int first = blockIdx.x * NWG + w;
+      const int njets = first < L.B ? (L.B - first + gridDim.x * NWG - 1) / (gridDim.x * NWG) : 0;
+      total[w] = njets * tpj * S; done_st[w] = 0; par[w] = 0;
+      any |= total[w] > 0;
+    }
+    MmaGroup* tbl = reinterpret_cast<MmaGroup*>(smem + T.o_tbl);      // [NWG][S]
+    if (lane == 0) {
+      for (int w = 0; w < NWG; ++w) {
+        const uint32_t wgb = smem_u32(smem + T.wg_base + w * T.wg_stride);
+        for (int l = 1; l < Le; ++l)
+          tbl[w * S + l - 1] = grp_fwd(tmem_base + (uint32_t)(w * T.tmem_cols_per_wg), wgb + T.w_act[l - 1],
+                                       smem_u32(smem + T.o_wT[l]), L.Ep[l], L.Kp[l]);
+      }
+    }
+    __syncwarp();
+    uint32_t unused = 0;
+    while (any) {
+#pragma unroll
+      for (int w = 0; w < NWG; ++w) {
+        if (done_st[w] >= total[w]) continue;
+        mbar_wait(bars + w, par[w]);
+        par[w] ^= 1u;
+        __syncwarp();
+        tc_fence_after();
+        run_group(tbl + w * S + done_st[w] % S, unused);
+        mma_commit_elect(bars + NWG + w);
+        ++done_st[w];
+      }
+      any = false;
+#pragma unroll
+      for (int w = 0; w < NWG; ++w) any |= done_st[w] < total[w];
+    }
+  } else {
+    // =================================== compute warpgroups ===================================
+    const int wg = warp >> 2, t = tid & 127, wq = warp & 3;
+    uint8_t* wgb = smem + T.wg_base + wg * T.wg_stride;
+    float* wgf = reinterpret_cast<float*>(wgb + T.w_f32);
+    uint64_t* ready = bars + wg;
+    uint64_t* done = bars + NWG + wg;
+    const uint32_t tmem_row = tmem_base + (uint32_t)(wg * T.tmem_cols_per_wg) + ((uint32_t)(wq * 32) << 16);
+    uint32_t phase = 0;
+    const int bar_id = 1 + wg;
+    float* sm_h = wgf + L.o_h;
+    float* sm_hj = wgf + L.o_hj;
+    float* sm_Q = wgf + L.o_Q;
+    float* sm_P = wgf + L.o_P;
+    float* sm_e = wgf + L.o_e;
+    const float* wd = smf + L.o_wd;
+    const bool a_le_1 = L.alpha <= 1.f;
+
+    for (int jet = blockIdx.x * NWG + wg; jet < L.B; jet += gridDim.x * NWG) {
+      const float* hjet = h + (size_t)jet * L.N * L.ld;
+      const float* pqjet = pq + (size_t)jet * L.N * 2 * L.E0p;
+      for (int i0 = 0; i0 < L.N; i0 += GJ_IB) {
+        const int ni = min(GJ_IB, L.N - i0);
         named_bar_sync(bar_id, 128);
-        wg_load_block(L, hjet, pqjet, 1, j0, sm_hj, sm_Q, t);
-        named_bar_sync(bar_id, 128);
-        const int nit = (ni + 3) / 4;
-        for (int it = 0; it < nit; ++it) {
-          const int il = it * 4 + wq;
-          const bool valid = il < ni && lane < nj;
-          tc_layer0(L, sm_h, sm_hj, sm_P, sm_Q, wd, wgb + T.w_act[0], il, lane, t);
-          fence_proxy_async();
+        wg_load_block(L, hjet, pqjet, 0, i0, sm_h, sm_P, t);
+        for (int idx = t; idx < GJ_IB * L.ELs; idx += 128) sm_e[idx] = 0.f;
+        for (int j0 = 0; j0 < L.N; j0 += 32) {
+          const int nj = min(32, L.N - j0);
           named_bar_sync(bar_id, 128);
-          for (int l = 1; l < L.Le; ++l) {
-            if (t == 0) {
+          wg_load_block(L, hjet, pqjet, 1, j0, sm_hj, sm_Q, t);
+          named_bar_sync(bar_id, 128);
+          const int nit = (ni + 3) / 4;
+          for (int it = 0; it < nit; ++it) {
+            const int il = it * 4 + wq;
+            const bool valid = il < ni && lane < nj;
+            tc_layer0(L, sm_h, sm_hj, sm_P, sm_Q, wd, wgb + T.w_act[0], il, lane, t);
+            fence_proxy_async();
+            tc_fence_before();
+            mbar_arrive(ready);
+            for (int l = 1; l < Le; ++l) {
+              mbar_wait(done, phase); phase ^= 1u;
               tc_fence_after();
-              issue_layer_mma(tmem_d, smem_u32(wgb + T.w_act[l - 1]), smem_u32(smem + T.o_wT[l]), L.Ep[l], L.Kp[l]);
-              mma_commit(bar);
-            }
-            __syncwarp();
-            mbar_wait(bar, phase);
-            phase ^= 1u;
-            tc_fence_after();
-            const bool last = (l == L.Le - 1);
-            const float* bias = smf + L.o_bE[l];
-            for (int c0 = 0; c0 < L.Ep[l]; c0 += 16) {
-              float v[16];
-              tmem_ld16(tmem_row + (uint32_t)c0, v);
+              const bool last = (l == Le - 1);
+              const float* bias = smf + L.o_bE[l];
+              uint8_t* al = wgb + T.w_act[l] + t * 16;
+              const int nch = L.Ep[l] >> 4;
+              auto process = [&](float (&v)[16], int c0) {
+                float bq[16];
 #pragma unroll
-              for (int q = 0; q < 16; ++q) v[q] = gj_leaky(v[q] + bias[c0 + q], L.alpha);
-              if (!last) {
-                uint8_t* al = wgb + T.w_act[l];
-                uint4 p0 = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
-                uint4 p1 = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
-                *reinterpret_cast<uint4*>(al + (c0 >> 3) * 2048 + t * 16) = p0;
-                *reinterpret_cast<uint4*>(al + ((c0 >> 3) + 1) * 2048 + t * 16) = p1;
-              } else {
-                // e_i += sum_j a_last (padded rows masked AFTER the activation: leaky(b) != 0)
+                for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(bq + 4 * q) = *reinterpret_cast<const float4*>(bias + c0 + 4 * q);
 #pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                  float s = gj_warp_sum(valid ? v[q] : 0.f);
-                  if (lane == 0) sm_e[il * L.ELs + c0 + q] += s;
+                for (int q = 0; q < 16; ++q) v[q] = gj_leaky2(v[q] + bq[q], L.alpha, a_le_1);
+                if (!last) {
+                  uint4 p0 = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                  uint4 p1 = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
+                  *reinterpret_cast<uint4*>(al + (c0 >> 3) * 2048) = p0;
+                  *reinterpret_cast<uint4*>(al + ((c0 >> 3) + 1) * 2048) = p1;
+                } else {
+                  // e_i += sum_j a_last (padded rows masked AFTER the activation: leaky(b) != 0); transpose-reduce over
+                  // the 32 j's of the warp: lane L ends up with channel c0 + (L >> 1)
+#pragma unroll
+                  for (int q = 0; q < 16; ++q) v[q] = valid ? v[q] : 0.f;
+                  const float s = warp_transpose_sum16(v, lane);
+                  if ((lane & 1) == 0) sm_e[il * L.ELs + c0 + (lane >> 1)] += s;
+                }
+              };
+              float va[16], vb[16];
+              tmem_ld16_issue(tmem_row, va);
+              for (int ch = 0; ch < nch; ch += 2) {
+                tmem_wait16(va);
+                if (ch + 1 < nch) tmem_ld16_issue(tmem_row + (uint32_t)((ch + 1) << 4), vb);
+                process(va, ch << 4);
+                if (ch + 1 < nch) {
+                  tmem_wait16(vb);
+                  if (ch + 2 < nch) tmem_ld16_issue(tmem_row + (uint32_t)((ch + 2) << 4), va);
+                  process(vb, (ch + 1) << 4);
                 }
               }
+              if (!last) {
+                fence_proxy_async();
+                tc_fence_before();
+                mbar_arrive(ready);
+              } else {
+                tc_fence_before();
+              }
             }
-            if (!last) fence_proxy_async();
-            tc_fence_before();
-            named_bar_sync(bar_id, 128);
           }
         }
-      }
-      named_bar_sync(bar_id, 128);
-      for (int idx = t; idx < ni * L.EL; idx += 128) {
-        int n = idx / L.EL, c = idx - n * L.EL;
-        e_out[((size_t)jet * L.N + i0 + n) * L.EL + c] = sm_e[n * L.ELs + c];
+        named_bar_sync(bar_id, 128);
+        for (int idx = t; idx < ni * L.EL; idx += 128) {
+          int n = idx / L.EL, c = idx - n * L.EL;
+          e_out[((size_t)jet * L.N + i0 + n) * L.EL + c] = sm_e[n * L.ELs + c];
+        }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (tid < 32) tmem_dealloc(tmem_base, (uint32_t)T.tmem_cols_total);
+  if (is_issuer) tmem_dealloc(tmem_base, (uint32_t)T.tmem_cols_total);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -253,10 +403,17 @@ edge_fwd_tc_kernel(const MPLayout L, const TCPlan T, const float* __restrict__ h
 //                      (at l = 1 also the bias gradients: column sums of ALL dz_l as one M=128 MMA per 128 columns
 //                       against a ones operand, the dz_l buffers being contiguous in shared memory)
 // The first layer's adjoint (dP, dQ, distance gradient, d wd) is reduced on the CUDA cores from dz_0 in fp32.
+// Optional timeline of the issuer / warpgroup handshake (GJ_TRACE=1 in the environment): (tag, clock) pairs of CTA 0.
+__device__ long long g_trace[8192];
+__device__ int g_trace_n[4];
+#define GJ_TRACE_PT(who, tag)                                                                         \
+  do { if (T.trace && blockIdx.x == 0) { int i_ = g_trace_n[who]; if (i_ < 1024) { g_trace[(who) * 2048 + 2 * i_] = (tag);  \
+         g_trace[(who) * 2048 + 2 * i_ + 1] = clock64(); g_trace_n[who] = i_ + 1; } } } while (0)
+
 struct BwdPlan {
-  int nwg, Le;
+  int nwg, Le, trace;
   // shared regions (bytes from smem base)
-  int o_bar, o_tmem_slot, o_ones, o_shared_f32;
+  int o_bar, o_tmem_slot, o_ones, o_shared_f32, o_tbl, groups_per_wg;
   int o_wT[GJ_MAX_LAYERS];
   int wg_base, wg_stride;
   // per-warpgroup (bytes from the warpgroup base)
@@ -334,6 +491,9 @@ int plan_tc_bwd(MPLayout* L, BwdPlan* T, int nwg) {
   T->o_bar = off; off += 64;
   T->o_tmem_slot = off; off += 64;
   T->o_ones = off; off += 16 * 128 * 2;
+  T->groups_per_wg = (L->Le - 1) + 2 * (L->Le - 1) + nb;
+  T->o_tbl = off; off += nwg * T->groups_per_wg * 40 + (2 * GJ_MAX_LAYERS + 2) * 4;
+  off = gj_round_up(off, 16);
   for (int l = 1; l < L->Le; ++l) { T->o_wT[l] = off; off += L->Ep[l] * L->Kp[l] * 2; }
   T->o_shared_f32 = off; off += c.off * 4;
   off = gj_round_up(off, 128);
@@ -352,76 +512,10 @@ int plan_tc_bwd(MPLayout* L, BwdPlan* T, int nwg) {
   return T->smem_bytes > 227 * 1024 ? 1 : 0;
 }
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// transpose-reduce of 16 per-lane values over the 32 lanes of a warp: returns, in every lane, the sum over all lanes
-// of channel (lane >> 1) & 15   (31 adds + 16 shuffles instead of 80 + 80)
-__device__ __forceinline__ float warp_transpose_sum16(const float (&v)[16], int lane) {
-  float w8[8], w4[4], w2[2];
-  bool up = lane & 16;
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    float send = up ? v[q] : v[q + 8], keep = up ? v[q + 8] : v[q];
-    w8[q] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-  }
-  up = lane & 8;
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    float send = up ? w8[q] : w8[q + 4], keep = up ? w8[q + 4] : w8[q];
-    w4[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-  }
-  up = lane & 4;
-#pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    float send = up ? w4[q] : w4[q + 2], keep = up ? w4[q + 2] : w4[q];
-    w2[q] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-  up = lane & 2;
-  float send = up ? w2[0] : w2[1], keep = up ? w2[1] : w2[0];
-  float w1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  return w1 + __shfl_xor_sync(0xffffffffu, w1, 1);
-}
-
 __device__ __forceinline__ void unpack_bf16x8(const uint4& u, float* f) {
   const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
   for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
-}
-
-// ---- the issuer's MMA batches -----------------------------------------------------------------------------
-// A/B K-major buffer with nrows rows: next 8 rows +128 B (SBO), next 8 columns +nrows*16 B (LBO), 16 columns per MMA
-// A/B MN-major view of the same bytes (MN = column, K = row): next 8 columns +nrows*16 B (SBO), next 8 rows +128 B (LBO)
-__device__ __forceinline__ void issue_fwd(uint32_t d, uint32_t a, uint32_t w, int N, int K) {
-  const uint32_t idesc = make_idesc_bf16(128, N, 0, 0);
-  for (int ks = 0; ks < K / 16; ++ks)
-    mma_bf16_ss(d, make_smem_desc(a + ks * 4096, 2048, 128), make_smem_desc(w + ks * (2 * N * 16), N * 16, 128), idesc, ks > 0);
-}
-// acc[128 x Kin] = dz[128 x Eout] * W[Eout x Kin]: A = dz K-major, B = W viewed MN-major (MN = in feature, K = out feature)
-__device__ __forceinline__ void issue_dgrad(uint32_t d, uint32_t dz, uint32_t w, int Kin, int Eout) {
-  const uint32_t idesc = make_idesc_bf16(128, Kin, 0, 1);
-  for (int ks = 0; ks < Eout / 16; ++ks)
-    mma_bf16_ss(d, make_smem_desc(dz + ks * 4096, 2048, 128), make_smem_desc(w + ks * 256, 128, Eout * 16), idesc, ks > 0);
-}
-// D[M x N] (+)= X^T Y over the 128 tile rows: both operands MN-major views of 128-row buffers
-__device__ __forceinline__ void issue_wgrad(uint32_t d, uint32_t x, uint32_t y, int M, int N, bool accumulate) {
-  const uint32_t idesc = make_idesc_bf16(M, N, 1, 1);
-  for (int ks = 0; ks < 8; ++ks)
-    mma_bf16_ss(d, make_smem_desc(x + ks * 256, 128, 2048), make_smem_desc(y + ks * 256, 128, 2048), idesc, accumulate || ks > 0);
-}
-// D[M x 16] (+)= X^T 1: column sums of a 128-row buffer (ones operand: K-major [16][128])
-__device__ __forceinline__ void issue_colsum(uint32_t d, uint32_t x, uint32_t ones, int M, bool accumulate) {
-  const uint32_t idesc = make_idesc_bf16(M, 16, 1, 0);
-  for (int ks = 0; ks < 8; ++ks)
-    mma_bf16_ss(d, make_smem_desc(x + ks * 256, 128, 2048), make_smem_desc(ones + ks * 512, 256, 128), idesc, accumulate || ks > 0);
-}
-
-__device__ __forceinline__ int tiles_of_jet(const MPLayout& L) {
-  int n = 0;
-  const int njb = (L.N + 31) / 32;
-  for (int i0 = 0; i0 < L.N; i0 += GJ_IB) n += ((min(GJ_IB, L.N - i0) + 3) / 4) * njb;
-  return n;
 }
 
 template <int NWG, int E0P>
@@ -432,7 +526,7 @@ edge_bwd_tc_kernel(const MPLayout L, const BwdPlan T, const float* __restrict__ 
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int NT = NWG * 128 + 32;
   const int tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
+  const int warp = (int)uni((uint32_t)(tid >> 5)), lane = tid & 31;     // provably warp-uniform
   const bool is_issuer = warp == NWG * 4;
   float* smf = reinterpret_cast<float*>(smem + T.o_shared_f32);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T.o_bar);   // ready[wg] = bars[wg], done[wg] = bars[NWG + wg]
@@ -456,61 +550,79 @@ edge_bwd_tc_kernel(const MPLayout L, const BwdPlan T, const float* __restrict__ 
 
   if (is_issuer) {
     // =================================== MMA issuer ===================================
-    if (lane == 0) {
+    // The whole warp runs this code convergently; only the tcgen05 instructions themselves are elected to one lane.
+    {
       const int S = 2 * (Le - 1);
       const int tpj = tiles_of_jet(L);
       int total[NWG], done_st[NWG];
       uint32_t par[NWG];
       bool any = false;
+#pragma unroll
       for (int w = 0; w < NWG; ++w) {
         const int first = blockIdx.x * NWG + w;
         const int njets = first < jets_total ? (jets_total - first + gridDim.x * NWG - 1) / (gridDim.x * NWG) : 0;
         total[w] = njets * tpj * S; done_st[w] = 0; par[w] = 0;
         any |= total[w] > 0;
       }
-      uint32_t inited = 0;    // bit l: weight-gradient accumulator l has been written; bit 31: the bias accumulators
+      // group table in shared memory: per warpgroup, stage s owns groups [gbeg[s], gbeg[s + 1])
+      MmaGroup* tbl = reinterpret_cast<MmaGroup*>(smem + T.o_tbl);
+      int* gbeg = reinterpret_cast<int*>(smem + T.o_tbl + NWG * T.groups_per_wg * 40);
+      if (lane == 0) {
+        for (int w = 0; w < NWG; ++w) {
+          const uint32_t wgb = smem_u32(smem + T.wg_base + w * T.wg_stride);
+          const uint32_t a0 = wgb + T.w_a0, comb = wgb + T.w_comb;
+          const uint32_t acc = tmem_base + (uint32_t)(w * T.nacc);
+          int ng = 0;
+          MmaGroup* tw = tbl + w * T.groups_per_wg;
+          for (int s2 = 0; s2 < S; ++s2) {
+            gbeg[s2] = ng;
+            if (s2 < Le - 1) {
+              const int l = s2 + 1;
+              const uint32_t ain = l == 1 ? a0 : comb + (T.coff[l - 1] >> 3) * 2048;
+              tw[ng++] = grp_fwd(acc, ain, smem_u32(smem + T.o_wT[l]), L.Ep[l], L.Kp[l]);
+            } else {
+              const int l = Le - 1 - (s2 - (Le - 1));
+              const uint32_t dz = comb + (T.coff[l] >> 3) * 2048;
+              const uint32_t ain = l == 1 ? a0 : comb + (T.coff[l - 1] >> 3) * 2048;
+              tw[ng++] = T.wg_orient[l] == 0 ? grp_wgrad(tmem_base + T.t_wg[l], dz, ain, T.wg_M[l], T.wg_N[l], l)
+                                             : grp_wgrad(tmem_base + T.t_wg[l], ain, dz, T.wg_M[l], T.wg_N[l], l);
+              tw[ng++] = grp_dgrad(acc, dz, smem_u32(smem + T.o_wT[l]), L.Kp[l], L.Ep[l]);
+              if (l == 1)
+                for (int b = 0; b < T.nbias; ++b)
+                  tw[ng++] = grp_colsum(tmem_base + T.t_bias[b], comb + b * 16 * 2048, smem_u32(smem + T.o_ones), T.bias_M[b], 16 + b);
+            }
+          }
+          gbeg[S] = ng;
+        }
+      }
+      __syncwarp();
+      uint32_t inited = 0;    // bit id: that shared gradient accumulator has been written
       while (any) {
-        any = false;
+#pragma unroll
         for (int w = 0; w < NWG; ++w) {
           if (done_st[w] >= total[w]) continue;
           mbar_wait(bars + w, par[w]);
           par[w] ^= 1u;
+          __syncwarp();
           tc_fence_after();
-          const uint32_t wgb = smem_u32(smem + T.wg_base + w * T.wg_stride);
-          const uint32_t a0 = wgb + T.w_a0, comb = wgb + T.w_comb;
-          const uint32_t acc = tmem_base + (uint32_t)(w * T.nacc);
-          const int s = done_st[w] % S;
-          if (s < Le - 1) {
-            const int l = s + 1;
-            const uint32_t ain = l == 1 ? a0 : comb + (T.coff[l - 1] >> 3) * 2048;
-            issue_fwd(acc, ain, smem_u32(smem + T.o_wT[l]), L.Ep[l], L.Kp[l]);
-          } else {
-            const int l = Le - 1 - (s - (Le - 1));
-            const uint32_t dz = comb + (T.coff[l] >> 3) * 2048;
-            const uint32_t ain = l == 1 ? a0 : comb + (T.coff[l - 1] >> 3) * 2048;
-            const bool accumulate = (inited >> l) & 1u;          // the first batch into an accumulator initialises it
-            inited |= 1u << l;
-            if (T.wg_orient[l] == 0) issue_wgrad(tmem_base + T.t_wg[l], dz, ain, T.wg_M[l], T.wg_N[l], accumulate);
-            else                     issue_wgrad(tmem_base + T.t_wg[l], ain, dz, T.wg_M[l], T.wg_N[l], accumulate);
-            issue_dgrad(acc, dz, smem_u32(smem + T.o_wT[l]), L.Kp[l], L.Ep[l]);
-            if (l == 1) {
-              const bool bacc = (inited >> 31) & 1u;
-              inited |= 1u << 31;
-              for (int b = 0; b < T.nbias; ++b)
-                issue_colsum(tmem_base + T.t_bias[b], comb + b * 16 * 2048, smem_u32(smem + T.o_ones), T.bias_M[b], bacc);
-            }
-          }
-          mma_commit(bars + NWG + w);
+          const int s2 = done_st[w] % S;
+          if (lane == 0) GJ_TRACE_PT(2, w * 100 + s2);
+          const MmaGroup* tw = tbl + w * T.groups_per_wg;
+          const int g0 = (int)uni((uint32_t)gbeg[s2]), g1 = (int)uni((uint32_t)gbeg[s2 + 1]);
+          for (int g = g0; g < g1; ++g) run_group(tw + g, inited);
+          mma_commit_elect(bars + NWG + w);
+          if (lane == 0) GJ_TRACE_PT(2, 1000 + w * 100 + s2);
           ++done_st[w];
-          any |= done_st[w] < total[w];
         }
+        any = false;
+#pragma unroll
         for (int w = 0; w < NWG; ++w) any |= done_st[w] < total[w];
       }
     }
     __syncwarp();
   } else {
     // =================================== compute warpgroups ===================================
-    const int wg = tid >> 7, t = tid & 127, wq = t >> 5;
+    const int wg = warp >> 2, t = tid & 127, wq = warp & 3;     // warp-uniform
     uint8_t* wgb = smem + T.wg_base + wg * T.wg_stride;
     float* wgf = reinterpret_cast<float*>(wgb + T.w_f32);
     uint8_t* A0 = wgb + T.w_a0;
@@ -531,6 +643,7 @@ edge_bwd_tc_kernel(const MPLayout L, const BwdPlan T, const float* __restrict__ 
     float* sm_G = wgf + L.o_G;
     const float* wd = smf + L.o_wd;
     const int H = L.H, W2 = 2 * L.E0p;
+    const bool a_le_1 = L.alpha <= 1.f;
     float dwd[E0P];
 #pragma unroll
     for (int c = 0; c < E0P; ++c) dwd[c] = 0.f;
@@ -544,6 +657,7 @@ edge_bwd_tc_kernel(const MPLayout L, const BwdPlan T, const float* __restrict__ 
         const int ni = min(GJ_IB, L.N - i0);
         named_bar_sync(bar_id, 128);
         wg_load_block(L, hjet, pqjet, 0, i0, sm_h, sm_P, t);
+#pragma unroll 4
         for (int idx = t; idx < GJ_IB * L.ELs; idx += 128) {
           int n = idx / L.ELs, c = idx - n * L.ELs;
           sm_de[idx] = (n < ni && c < L.EL) ? __ldg(de + ((size_t)jet * L.N + i0 + n) * L.EL + c) : 0.f;
@@ -568,25 +682,29 @@ edge_bwd_tc_kernel(const MPLayout L, const BwdPlan T, const float* __restrict__ 
             fence_proxy_async();
             tc_fence_before();
             mbar_arrive(ready);
+            if (t == 0) GJ_TRACE_PT(wg, 10);
             // ---- forward stages ----
             for (int l = 1; l < Le; ++l) {
               mbar_wait(done, phase); phase ^= 1u;
               tc_fence_after();
+              if (t == 0) GJ_TRACE_PT(wg, 20 + l);
               const bool last = (l == Le - 1);
               const float* bias = smf + L.o_bE[l];
               uint8_t* out = COMB + (T.coff[l] >> 3) * 2048 + t * 16;
-              for (int c0 = 0; c0 < L.Ep[l]; c0 += 16) {
-                float v[16];
-                tmem_ld16(tmem_row + (uint32_t)c0, v);
+              const int nch = L.Ep[l] >> 4;
+              auto process = [&](float (&v)[16], int c0) {
+                float bq[16];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(bq + 4 * q) = *reinterpret_cast<const float4*>(bias + c0 + 4 * q);
                 if (!last) {
 #pragma unroll
-                  for (int q = 0; q < 16; ++q) v[q] = gj_leaky(v[q] + bias[c0 + q], L.alpha);
+                  for (int q = 0; q < 16; ++q) v[q] = gj_leaky2(v[q] + bq[q], L.alpha, a_le_1);
                 } else {
                   // dz_last = de_i * leaky'(z_last), zero on padded rows (this masks everything downstream)
                   const float* dei = sm_de + il * L.ELs + c0;
 #pragma unroll
                   for (int q = 0; q < 16; ++q) {
-                    const float z = v[q] + bias[c0 + q];
+                    const float z = v[q] + bq[q];
                     v[q] = valid ? dei[q] * (z > 0.f ? 1.f : L.alpha) : 0.f;
                   }
                 }
@@ -594,33 +712,61 @@ edge_bwd_tc_kernel(const MPLayout L, const BwdPlan T, const float* __restrict__ 
                 uint4 p1 = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
                 *reinterpret_cast<uint4*>(out + (c0 >> 3) * 2048) = p0;
                 *reinterpret_cast<uint4*>(out + ((c0 >> 3) + 1) * 2048) = p1;
+              };
+              // two register sets: the next chunk's TMEM load flies while the current chunk is processed
+              float va[16], vb[16];
+              tmem_ld16_issue(tmem_row, va);
+              for (int ch = 0; ch < nch; ch += 2) {
+                tmem_wait16(va);
+                if (ch + 1 < nch) tmem_ld16_issue(tmem_row + (uint32_t)((ch + 1) << 4), vb);
+                process(va, ch << 4);
+                if (ch + 1 < nch) {
+                  tmem_wait16(vb);
+                  if (ch + 2 < nch) tmem_ld16_issue(tmem_row + (uint32_t)((ch + 2) << 4), va);
+                  process(vb, (ch + 1) << 4);
+                }
               }
               fence_proxy_async();
               tc_fence_before();
               mbar_arrive(ready);
+              if (t == 0) GJ_TRACE_PT(wg, 30 + l);
             }
             // ---- backward stages ----
             for (int l = Le - 1; l >= 1; --l) {
               mbar_wait(done, phase); phase ^= 1u;
               tc_fence_after();
+              if (t == 0) GJ_TRACE_PT(wg, 40 + l);
               if (l > 1) {
                 // dz_{l-1} = da_{l-1} * leaky'(a_{l-1}), in place over a_{l-1}
                 uint8_t* buf = COMB + (T.coff[l - 1] >> 3) * 2048 + t * 16;
-                for (int c0 = 0; c0 < L.Kp[l]; c0 += 16) {
-                  float v[16], a[16];
-                  tmem_ld16(tmem_row + (uint32_t)c0, v);
+                const int nch = L.Kp[l] >> 4;
+                auto process = [&](float (&v)[16], int c0) {
+                  float a[16];
                   unpack_bf16x8(*reinterpret_cast<const uint4*>(buf + (c0 >> 3) * 2048), a);
                   unpack_bf16x8(*reinterpret_cast<const uint4*>(buf + ((c0 >> 3) + 1) * 2048), a + 8);
 #pragma unroll
-                  for (int q = 0; q < 16; ++q) v[q] *= (a[q] > 0.f ? 1.f : L.alpha);
+                  for (int q = 0; q < 16; ++q) v[q] = a[q] > 0.f ? v[q] : L.alpha * v[q];
                   uint4 p0 = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
                   uint4 p1 = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
                   *reinterpret_cast<uint4*>(buf + (c0 >> 3) * 2048) = p0;
                   *reinterpret_cast<uint4*>(buf + ((c0 >> 3) + 1) * 2048) = p1;
+                };
+                float va[16], vb[16];
+                tmem_ld16_issue(tmem_row, va);
+                for (int ch = 0; ch < nch; ch += 2) {
+                  tmem_wait16(va);
+                  if (ch + 1 < nch) tmem_ld16_issue(tmem_row + (uint32_t)((ch + 1) << 4), vb);
+                  process(va, ch << 4);
+                  if (ch + 1 < nch) {
+                    tmem_wait16(vb);
+                    if (ch + 2 < nch) tmem_ld16_issue(tmem_row + (uint32_t)((ch + 2) << 4), va);
+                    process(vb, (ch + 1) << 4);
+                  }
                 }
                 fence_proxy_async();
                 tc_fence_before();
                 mbar_arrive(ready);
+                if (t == 0) GJ_TRACE_PT(wg, 50 + l);
               } else {
                 // dz_0 = da_0 * leaky'(a_0), consumed in fp32: G_ij, dQ_j, dP_i, d(wd)
                 float g = 0.f;
@@ -642,6 +788,7 @@ edge_bwd_tc_kernel(const MPLayout L, const BwdPlan T, const float* __restrict__ 
                 }
                 sm_G[il * L.Gs + lane] = g;
                 tc_fence_before();
+                if (t == 0) GJ_TRACE_PT(wg, 60);
               }
             }
           }
@@ -829,7 +976,7 @@ int gj_edge_fwd_tc(MPLayout L, const float* h, const float* pq, const float* par
   if (ce != cudaSuccess) { gj_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   int sms = gj_num_sms();
   int grid = (L.B + NWG - 1) / NWG; if (grid > sms) grid = sms;
-  kern<<<grid, NWG * 128, T.smem_bytes, stream>>>(L, T, h, pq, params, e_out);
+  kern<<<grid, NWG * 128 + 32, T.smem_bytes, stream>>>(L, T, h, pq, params, e_out);
   ce = cudaGetLastError();
   if (ce != cudaSuccess) { gj_set_error("edge_fwd_tc launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   return GJ_OK;
@@ -872,6 +1019,9 @@ int gj_edge_bwd_tc(MPLayout L, const float* h, const float* pq, const float* par
     return gj_edge_bwd_simt(L, h, pq, params, de, dpq, dh, dparams, part, stream);
   }
   const int grid = tc_bwd_grid(Lt.B, 2);
+  static const int trace_env = getenv("GJ_TRACE") ? atoi(getenv("GJ_TRACE")) : 0;
+  T.trace = trace_env;
+  if (trace_env) { int z[4] = {0, 0, 0, 0}; cudaMemcpyToSymbolAsync(g_trace_n, z, sizeof(z), 0, cudaMemcpyHostToDevice, stream); }
   int rc;
   switch (Lt.E0p) {
     case 16: rc = launch_tc_bwd<16>(Lt, T, h, pq, params, de, dpq, dh, part, grid, stream); break;
@@ -890,6 +1040,14 @@ void gj_tc_plan_info(MPLayout L, int* info) {
   BwdPlan T; MPLayout Lb = L;
   if (L.Le < 2 || plan_tc_bwd(&Lb, &T, 2)) { info[2] = 0; info[3] = 0; }
   else { info[2] = T.smem_bytes; info[3] = T.tmem_cols; }
+}
+
+// debugging aid (not part of the ABI header): copies the handshake timeline of the last traced launch
+extern "C" int gj_debug_read_trace(long long* out, int* counts) {
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * 8192) != cudaSuccess) return 1;
+  if (cudaMemcpyFromSymbol(counts, g_trace_n, sizeof(int) * 4) != cudaSuccess) return 1;
+  return 0;
 }
 
 int gj_umma_selftest_launch(int M, int N, int K, int a_mn, int b_mn, const float* a, const float* b, float* out,

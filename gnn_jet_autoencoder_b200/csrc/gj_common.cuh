@@ -93,6 +93,8 @@ static inline int gj_fill_arch(const gj_mp_desc* d, MPLayout* L, const char** wh
 
 #ifdef __CUDACC__
 __device__ __forceinline__ float gj_leaky(float z, float a) { return z > 0.f ? z : a * z; }
+// LeakyReLU as FMUL + FMNMX: max(z, a z) for a <= 1, min(z, a z) for a > 1 (a >= 0 is validated on the host)
+__device__ __forceinline__ float gj_leaky2(float z, float a, bool a_le_1) { const float y = a * z; return a_le_1 ? fmaxf(z, y) : fminf(z, y); }
 __device__ __forceinline__ float gj_slope(float y, float a) { return y > 0.f ? 1.f : a; }
 __device__ __forceinline__ float gj_warp_sum(float v) {
 #pragma unroll

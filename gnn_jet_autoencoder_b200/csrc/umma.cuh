@@ -34,13 +34,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a lost arrival traps instead of hanging the GPU box.
+// Bounded wait: the try_wait suspends in hardware up to the hint (10 ms) per attempt, so the loop body runs once in
+// normal operation; a lost arrival traps after ~2 s instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) { printf("gnnjet: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
-  }
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok;
+  int attempts = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity), "r"(10000000u)
+        : "memory");
+    if (!ok && ++attempts > 200) { printf("gnnjet: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+  } while (!ok);
 }
 
 // ---- proxies / fences ----
@@ -93,6 +102,31 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, ui
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Warp-convergent variants: ALL 32 lanes execute these with warp-uniform operands; one elected lane issues.  Keeping the
+// issuing code convergent lets ptxas hold descriptors in uniform registers -- issuing from inside an `if (lane == 0)`
+// costs an ELECT + 7x R2UR.BROADCAST waterfall loop per MMA (~100 cycles each, measured).
+__device__ __forceinline__ void mma_bf16_ss_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_elect(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(smem_u32(bar)) : "memory");
+}
+// broadcast from lane 0: tells the compiler the value is warp-uniform
+__device__ __forceinline__ uint32_t uni(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ uint64_t uni64(uint64_t v) {
+  return ((uint64_t)__shfl_sync(0xffffffffu, (uint32_t)(v >> 32), 0) << 32) | __shfl_sync(0xffffffffu, (uint32_t)v, 0);
+}
+
 // Arrives on the mbarrier when all previously issued MMAs of this thread have completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
@@ -100,7 +134,9 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
 }
 
 // ---- TMEM -> registers: 32 lanes x 32-bit, 16 consecutive columns per thread ----
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+// The load is asynchronous: the registers may be read only after tmem_wait16 on the same array.  Splitting issue and
+// wait lets the next chunk's load fly while the current chunk is processed.
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, float* v) {
   uint32_t r[16];
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -108,15 +144,29 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// waits for ALL outstanding tcgen05.ld of this thread; the "+f" operands pin the data dependence for the compiler
+__device__ __forceinline__ void tmem_wait16(float* v) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]), "+f"(v[8]),
+                 "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]), "+f"(v[15])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  tmem_ld16_issue(taddr, v);
+  tmem_wait16(v);
 }
 
 // Interleaved-layout byte offset of (row, col) in a buffer with nrows rows.
 __device__ __forceinline__ uint32_t il_off(int row, int col, int nrows) {
   return (uint32_t)((col >> 3) * (nrows * 16) + row * 16 + (col & 7) * 2);
 }
+
+// descriptor for k-step ks of an operand whose k-steps are `step16` 16-byte units apart (address field = bits 0..13)
+__device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t step16, int ks) { return desc + (uint64_t)(step16 * (uint32_t)ks); }
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);   // .x (low half) = a
