@@ -34,12 +34,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: the try_wait suspends in hardware up to the hint (10 ms) per attempt, so the loop body runs once in
-// normal operation; a lost arrival traps after ~2 s instead of hanging the GPU box.
+// Bounded wait: try_wait suspends in hardware for a while per attempt; wall time is checked only every 256 failed
+// attempts, and a lost arrival traps after 20 s instead of hanging the GPU box (profilers can slow a kernel by orders
+// of magnitude, so the bound is generous).
+__device__ __forceinline__ unsigned long long gj_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t ok;
-  int attempts = 0;
+  uint32_t attempts = 0;
+  unsigned long long t0 = 0;
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -48,7 +55,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok)
         : "r"(addr), "r"(parity), "r"(10000000u)
         : "memory");
-    if (!ok && ++attempts > 200) { printf("gnnjet: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+    if (!ok && (++attempts & 255u) == 0) {
+      const unsigned long long now = gj_globaltimer();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 20000000000ull) { printf("gnnjet: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+    }
   } while (!ok);
 }
 
