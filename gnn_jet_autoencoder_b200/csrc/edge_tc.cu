@@ -39,8 +39,18 @@ struct TCPlan {
 };
 
 // Fills the float offsets of L relative to the two float regions and the byte plan T.
+// row strides of the fp32 blocks: multiples of 4 floats with (stride / 4) odd, so that per-lane rows can be read with
+// conflict-free 16-byte loads
+static void tc_strides(MPLayout* L) {
+  L->Hs = ((L->H + 7) & ~7) + 4;
+  L->E0s = L->E0p + 4;
+  L->ELs = L->ELp + 4;
+  L->Gs = 36;
+}
+
 void plan_tc_fwd(MPLayout* L, TCPlan* T, int nwg) {
   L->R = 128; L->Rs = 0;
+  tc_strides(L);
   T->nwg = nwg;
   Carver c;
   for (int l = 1; l < L->Le; ++l) L->o_bE[l] = c.take(L->Ep[l]);
@@ -101,8 +111,7 @@ __device__ void wg_load_block(const MPLayout& L, const float* __restrict__ hjet,
     const int n = idx / q4, c = (idx - n * q4) * 4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (r0 + n < L.N) v = __ldg(reinterpret_cast<const float4*>(pqjet + (size_t)(r0 + n) * 2 * L.E0p + half * L.E0p + c));
-    float* d = spq + n * L.E0s + c;
-    d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    *reinterpret_cast<float4*>(spq + n * L.E0s + c) = v;
   }
 #pragma unroll 4
   for (int idx = t; idx < 32 * L.H; idx += 128) {
@@ -111,23 +120,39 @@ __device__ void wg_load_block(const MPLayout& L, const float* __restrict__ hjet,
   }
 }
 
-// first edge layer of one tile on CUDA cores: thread t owns row (i = it*4 + wq, j = lane); returns d_ij
+// first edge layer of one tile on CUDA cores: thread t owns row (i = it*4 + wq, j = lane); returns d_ij.
+// All shared-memory rows are read 16 bytes at a time (h_i, P_i, wd: warp broadcasts; h_j, Q_j: one row per lane).
 __device__ __forceinline__ float tc_layer0(const MPLayout& L, const float* sm_h, const float* sm_hj, const float* sm_P,
                                            const float* sm_Q, const float* wd, uint8_t* a0, int il, int lane, int t) {
   const float* hi = sm_h + il * L.Hs;
   const float* hj = sm_hj + lane * L.Hs;
   float d = 0.f;
-  for (int k = 0; k < L.H; ++k) {
-    float x = hj[k] - hi[k] + GJ_EPS;
-    float s = (L.mink && k > 0) ? -1.f : 1.f;
-    d = fmaf(s * x, x, d);
+  if (L.mink) {          // width 4 only: x0^2 - x1^2 - x2^2 - x3^2 (graphnet.py:320-323)
+    const float4 a = *reinterpret_cast<const float4*>(hi), b = *reinterpret_cast<const float4*>(hj);
+    const float x0 = b.x - a.x + GJ_EPS, x1 = b.y - a.y + GJ_EPS, x2 = b.z - a.z + GJ_EPS, x3 = b.w - a.w + GJ_EPS;
+    d = x0 * x0 - x1 * x1 - x2 * x2 - x3 * x3;
+  } else {
+    const int H4 = L.H & ~3;
+    for (int k = 0; k < H4; k += 4) {
+      const float4 a = *reinterpret_cast<const float4*>(hi + k), b = *reinterpret_cast<const float4*>(hj + k);
+      const float x0 = b.x - a.x + GJ_EPS, x1 = b.y - a.y + GJ_EPS, x2 = b.z - a.z + GJ_EPS, x3 = b.w - a.w + GJ_EPS;
+      d = fmaf(x0, x0, d); d = fmaf(x1, x1, d); d = fmaf(x2, x2, d); d = fmaf(x3, x3, d);
+    }
+    for (int k = H4; k < L.H; ++k) { const float x = hj[k] - hi[k] + GJ_EPS; d = fmaf(x, x, d); }
   }
   const float* P = sm_P + il * L.E0s;
   const float* Q = sm_Q + lane * L.E0s;
+  const bool a_le_1 = L.alpha <= 1.f;
   for (int c0 = 0; c0 < L.E0p; c0 += 8) {
-    float v[8];
+    float p[8], q[8], w[8], v[8];
+    *reinterpret_cast<float4*>(p) = *reinterpret_cast<const float4*>(P + c0);
+    *reinterpret_cast<float4*>(p + 4) = *reinterpret_cast<const float4*>(P + c0 + 4);
+    *reinterpret_cast<float4*>(q) = *reinterpret_cast<const float4*>(Q + c0);
+    *reinterpret_cast<float4*>(q + 4) = *reinterpret_cast<const float4*>(Q + c0 + 4);
+    *reinterpret_cast<float4*>(w) = *reinterpret_cast<const float4*>(wd + c0);
+    *reinterpret_cast<float4*>(w + 4) = *reinterpret_cast<const float4*>(wd + c0 + 4);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) v[q] = gj_leaky2(fmaf(wd[c0 + q], d, P[c0 + q] + Q[c0 + q]), L.alpha, L.alpha <= 1.f);
+    for (int i = 0; i < 8; ++i) v[i] = gj_leaky2(fmaf(w[i], d, p[i] + q[i]), L.alpha, a_le_1);
     uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
     *reinterpret_cast<uint4*>(a0 + (c0 >> 3) * 2048 + t * 16) = pk;
   }
@@ -435,6 +460,7 @@ int plan_tc_bwd(MPLayout* L, BwdPlan* T, int nwg) {
   memset(T, 0, sizeof(*T));
   T->nwg = nwg; T->Le = L->Le;
   L->R = 128;
+  tc_strides(L);
   if (L->Le < 2) return 1;
   if (L->E0p != 16 && L->E0p != 32 && L->E0p != 48 && L->E0p != 64) return 1;
   int ctot = 0, nacc = 32;
@@ -483,9 +509,8 @@ int plan_tc_bwd(MPLayout* L, BwdPlan* T, int nwg) {
   L->o_Q = w.take(32 * L->E0s);
   L->o_e = w.take(GJ_IB * L->ELs);
   L->o_dP = w.take(GJ_IB * L->E0s);
-  L->o_dQ = w.take(32 * L->E0s);
+  L->o_dQ = L->o_Q;                    // dQ_j is flushed after the block's last tile, when Q_j is dead: same storage
   L->o_dh = w.take(GJ_IB * L->Hs);
-  L->Gs = 33;
   L->o_G = w.take(GJ_IB * L->Gs);
   int off = 0;
   T->o_bar = off; off += 64;
@@ -668,7 +693,6 @@ edge_bwd_tc_kernel(const MPLayout L, const BwdPlan T, const float* __restrict__ 
           const int nj = min(32, L.N - j0);
           named_bar_sync(bar_id, 128);
           wg_load_block(L, hjet, pqjet, 1, j0, sm_hj, sm_Q, t);
-          for (int idx = t; idx < 32 * L.E0s; idx += 128) sm_dQ[idx] = 0.f;
           for (int idx = t; idx < GJ_IB * L.Gs; idx += 128) sm_G[idx] = 0.f;
           float dq[E0P];
 #pragma unroll
@@ -793,10 +817,16 @@ edge_bwd_tc_kernel(const MPLayout L, const BwdPlan T, const float* __restrict__ 
             }
           }
           // ---- (i block, j block) epilogue ----
-          for (int w = 0; w < 4; ++w) {           // dQ_j: the four warps hold different i's of the same j
+          named_bar_sync(bar_id, 128);            // every warp is done reading Q_j: its storage now receives dQ_j
+          for (int w = 0; w < 4; ++w) {           // the four warps hold different i's of the same j: fixed order 0..3
             if (wq == w) {
 #pragma unroll
-              for (int c = 0; c < E0P; ++c) sm_dQ[lane * L.E0s + c] += dq[c];
+              for (int c = 0; c < E0P; c += 4) {
+                float4* p = reinterpret_cast<float4*>(sm_dQ + lane * L.E0s + c);
+                float4 v = w == 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : *p;
+                v.x += dq[c]; v.y += dq[c + 1]; v.z += dq[c + 2]; v.w += dq[c + 3];
+                *p = v;
+              }
             }
             named_bar_sync(bar_id, 128);
           }

@@ -389,6 +389,7 @@ int gj_num_sms();
 void gj_set_error(const char* fmt, ...);
 
 static const int kSmemLimit = 227 * 1024;
+static const int kSmemTarget = 54 * 1024;   // <= this many bytes per CTA lets 4 CTAs share an SM (latency hiding)
 
 static int pre_plan(const MPLayout& L, PreArgs* A, bool backward) {
   memset(A, 0, sizeof(*A));
@@ -415,7 +416,7 @@ static int pre_plan(const MPLayout& L, PreArgs* A, bool backward) {
       A->o_dpar = take(L.E[0] * 2 * L.H + L.E[0]);
     }
     A->smem_floats = off;
-    if (off * 4 <= kSmemLimit) return off * 4;
+    if (off * 4 <= (R > 16 ? kSmemTarget : kSmemLimit)) return off * 4;
   }
   return -1;
 }
@@ -446,14 +447,17 @@ static int post_plan(const MPLayout& L, PostArgs* A, bool backward) {
     for (int m = 0; m < nY; ++m) A->o_Y[m] = take(R * A->S);
     if (backward) { A->o_g0 = take(R * A->S); A->o_g1 = take(R * A->S); A->o_dpar = take(A->n_node_params); }
     A->smem_floats = off;
-    if (off * 4 <= kSmemLimit) return off * 4;
+    if (off * 4 <= (R > 16 ? kSmemTarget : kSmemLimit)) return off * 4;
   }
   return -1;
 }
 
-static int nk_grid(int rows, int R) {
+static int nk_grid(int rows, int R, int smem_bytes) {
   int blocks = (rows + R - 1) / R;
-  int cap = gj_num_sms();
+  int per_sm = kSmemLimit / (smem_bytes + 1024);
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 4) per_sm = 4;
+  int cap = gj_num_sms() * per_sm;
   return blocks < cap ? (blocks > 0 ? blocks : 1) : cap;
 }
 
@@ -472,14 +476,15 @@ int gj_node_pre_fwd(const MPLayout& L, const float* h, const float* params, floa
   PreArgs A; int bytes = pre_plan(L, &A, false);
   if (bytes < 0) { gj_set_error("node_pre_fwd: widths do not fit shared memory"); return GJ_ERR_SMEM; }
   if (int rc = nk_set_smem(node_pre_fwd_kernel, bytes)) return rc;
-  node_pre_fwd_kernel<<<nk_grid(A.rows, A.R), NK_THREADS, bytes, st>>>(A, h, params + L.pW[0], params + L.pb[0], pq);
+  node_pre_fwd_kernel<<<nk_grid(A.rows, A.R, bytes), NK_THREADS, bytes, st>>>(A, h, params + L.pW[0], params + L.pb[0], pq);
   NK_CHECK_LAUNCH("node_pre_fwd launch");
   return GJ_OK;
 }
 
 size_t gj_node_pre_bwd_ws_floats(const MPLayout& L) {
-  PreArgs A; if (pre_plan(L, &A, true) < 0) return 0;
-  return (size_t)nk_grid(A.rows, A.R) * (L.E[0] * 2 * L.H + L.E[0]);
+  PreArgs A; int bytes = pre_plan(L, &A, true);
+  if (bytes < 0) return 0;
+  return (size_t)nk_grid(A.rows, A.R, bytes) * (L.E[0] * 2 * L.H + L.E[0]);
 }
 
 int gj_node_pre_bwd(const MPLayout& L, const float* h, const float* params, const float* dpq, float* dh, float* dparams,
@@ -487,7 +492,7 @@ int gj_node_pre_bwd(const MPLayout& L, const float* h, const float* params, cons
   PreArgs A; int bytes = pre_plan(L, &A, true);
   if (bytes < 0) { gj_set_error("node_pre_bwd: widths do not fit shared memory"); return GJ_ERR_SMEM; }
   if (int rc = nk_set_smem(node_pre_bwd_kernel, bytes)) return rc;
-  const int grid = nk_grid(A.rows, A.R);
+  const int grid = nk_grid(A.rows, A.R, bytes);
   node_pre_bwd_kernel<<<grid, NK_THREADS, bytes, st>>>(A, h, params + L.pW[0], dpq, dh, part);
   const int n = L.E[0] * 2 * L.H + L.E[0];
   reduce_pre_partials_kernel<<<(n + 255) / 256, 256, 0, st>>>(part, grid, L.E[0], L.H, dparams + L.pW[0], dparams + L.pb[0]);
@@ -499,14 +504,15 @@ int gj_node_post_fwd(const MPLayout& L, const float* e, const float* h, const fl
   PostArgs A; int bytes = post_plan(L, &A, false);
   if (bytes < 0) { gj_set_error("node_post_fwd: widths do not fit shared memory"); return GJ_ERR_SMEM; }
   if (int rc = nk_set_smem(node_post_fwd_kernel, bytes)) return rc;
-  node_post_fwd_kernel<<<nk_grid(A.rows, A.R), NK_THREADS, bytes, st>>>(A, e, h, params, h_out);
+  node_post_fwd_kernel<<<nk_grid(A.rows, A.R, bytes), NK_THREADS, bytes, st>>>(A, e, h, params, h_out);
   NK_CHECK_LAUNCH("node_post_fwd launch");
   return GJ_OK;
 }
 
 size_t gj_node_post_bwd_ws_floats(const MPLayout& L) {
-  PostArgs A; if (post_plan(L, &A, true) < 0) return 0;
-  return (size_t)nk_grid(A.rows, A.R) * A.n_node_params;
+  PostArgs A; int bytes = post_plan(L, &A, true);
+  if (bytes < 0) return 0;
+  return (size_t)nk_grid(A.rows, A.R, bytes) * A.n_node_params;
 }
 
 int gj_node_post_bwd(const MPLayout& L, const float* e, const float* h, const float* params, const float* dh_out, float* de,
@@ -514,7 +520,7 @@ int gj_node_post_bwd(const MPLayout& L, const float* e, const float* h, const fl
   PostArgs A; int bytes = post_plan(L, &A, true);
   if (bytes < 0) { gj_set_error("node_post_bwd: widths do not fit shared memory"); return GJ_ERR_SMEM; }
   if (int rc = nk_set_smem(node_post_bwd_kernel, bytes)) return rc;
-  const int grid = nk_grid(A.rows, A.R);
+  const int grid = nk_grid(A.rows, A.R, bytes);
   node_post_bwd_kernel<<<grid, NK_THREADS, bytes, st>>>(A, e, h, params, dh_out, de, dh, part);
   reduce_partials_kernel<<<(A.n_node_params + 255) / 256, 256, 0, st>>>(part, grid, A.n_node_params, dparams + A.p_first);
   NK_CHECK_LAUNCH("node_post_bwd launch");
