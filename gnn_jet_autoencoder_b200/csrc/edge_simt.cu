@@ -413,13 +413,21 @@ edge_bwd_simt_kernel(const MPLayout L, const float* __restrict__ h, const float*
 // (the Wa | Wb columns of W0 and b0): of the first layer only the wd column (index 2H of each row) is ours.
 __global__ void reduce_edge_partials_kernel(const float* __restrict__ part, int nparts, int n, int E0, int K0,
                                             float* __restrict__ out) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n) return;
+  __shared__ float red[8][33];
+  const int p = blockIdx.x * 32 + threadIdx.x;
   const int first = E0 * K0 + E0;          // W0 then b0
-  if (p < first && !(p < E0 * K0 && (p % K0) == K0 - 1)) return;
+  const bool mine = p < n && !(p < first && !(p < E0 * K0 && (p % K0) == K0 - 1));
   float acc = 0.f;
-  for (int c = 0; c < nparts; ++c) acc += part[(size_t)c * n + p];
-  out[p] = acc;
+  if (mine)
+    for (int c = threadIdx.y; c < nparts; c += 8) acc += part[(size_t)c * n + p];
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && mine) {
+    float tot = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) tot += red[y][threadIdx.x];     // fixed order => deterministic
+    out[p] = tot;
+  }
 }
 
 }  // namespace
@@ -469,7 +477,7 @@ int gj_edge_bwd_simt(MPLayout L, const float* h, const float* pq, const float* p
 
 int gj_reduce_edge_partials(const MPLayout& L, const float* part, int nparts, float* dparams, cudaStream_t stream) {
   const int n = L.pV[0];
-  reduce_edge_partials_kernel<<<(n + 255) / 256, 256, 0, stream>>>(part, nparts, n, L.E[0], L.K[0], dparams);
+  reduce_edge_partials_kernel<<<(n + 31) / 32, dim3(32, 8), 0, stream>>>(part, nparts, n, L.E[0], L.K[0], dparams);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) { gj_set_error("edge_bwd launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   return GJ_OK;

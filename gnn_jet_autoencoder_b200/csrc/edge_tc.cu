@@ -26,8 +26,15 @@ struct Carver {
 
 int next_pow2_cols(int c) { int p = 32; while (p < c) p <<= 1; return p; }
 
+// Optional timeline of the issuer / warpgroup handshake (GJ_TRACE=1 in the environment): (tag, clock) pairs of CTA 0.
+__device__ long long g_trace[8192];
+__device__ int g_trace_n[4];
+#define GJ_TRACE_PT(who, tag)                                                                         \
+  do { if (T.trace && blockIdx.x == 0) { int i_ = g_trace_n[who]; if (i_ < 1024) { g_trace[(who) * 2048 + 2 * i_] = (tag);  \
+         g_trace[(who) * 2048 + 2 * i_ + 1] = clock64(); g_trace_n[who] = i_ + 1; } } } while (0)
+
 struct TCPlan {
-  int nwg;
+  int nwg, trace;
   int o_bar, o_tmem_slot, o_tbl;
   int o_wT[GJ_MAX_LAYERS];  // bf16 interleaved edge weights, layers >= 1 (bytes from smem base)
   int o_shared_f32;         // float region shared by all warpgroups (biases, wd)
@@ -51,7 +58,7 @@ static void tc_strides(MPLayout* L) {
 void plan_tc_fwd(MPLayout* L, TCPlan* T, int nwg) {
   L->R = 128; L->Rs = 0;
   tc_strides(L);
-  T->nwg = nwg;
+  T->nwg = nwg; T->trace = 0;
   Carver c;
   for (int l = 1; l < L->Le; ++l) L->o_bE[l] = c.take(L->Ep[l]);
   L->o_wd = c.take(L->E0p);
@@ -104,17 +111,17 @@ __device__ void stage_edge_weights_bf16(const MPLayout& L, const int* o_wT, cons
 // rows [r0, r0 + 32) of h (zero padded) and of the P or Q half of PQ, by one warpgroup.  Loads are batched
 // (all of a thread's global loads are issued before the first use) and 16 bytes wide where the layout allows.
 __device__ void wg_load_block(const MPLayout& L, const float* __restrict__ hjet, const float* __restrict__ pqjet, int half,
-                              int r0, float* sh, float* spq, int t) {
+                              int r0, float* sh, float* spq, int t, int nthr = 128) {
   const int q4 = L.E0p >> 2;                       // float4 per P/Q row (E0p is a multiple of 16)
 #pragma unroll 2
-  for (int idx = t; idx < 32 * q4; idx += 128) {
+  for (int idx = t; idx < 32 * q4; idx += nthr) {
     const int n = idx / q4, c = (idx - n * q4) * 4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (r0 + n < L.N) v = __ldg(reinterpret_cast<const float4*>(pqjet + (size_t)(r0 + n) * 2 * L.E0p + half * L.E0p + c));
     *reinterpret_cast<float4*>(spq + n * L.E0s + c) = v;
   }
 #pragma unroll 4
-  for (int idx = t; idx < 32 * L.H; idx += 128) {
+  for (int idx = t; idx < 32 * L.H; idx += nthr) {
     int n = idx / L.H, k = idx - n * L.H;
     sh[n * L.Hs + k] = (r0 + n < L.N && k < L.cols) ? __ldg(hjet + (size_t)(r0 + n) * L.ld + k) : 0.f;
   }
@@ -122,8 +129,10 @@ __device__ void wg_load_block(const MPLayout& L, const float* __restrict__ hjet,
 
 // first edge layer of one tile on CUDA cores: thread t owns row (i = it*4 + wq, j = lane); returns d_ij.
 // All shared-memory rows are read 16 bytes at a time (h_i, P_i, wd: warp broadcasts; h_j, Q_j: one row per lane).
+// With two warps per TMEM lane quadrant (NH = 2) the warp pair of a row splits the channels 8 by 8 (part = 0 / 1).
 __device__ __forceinline__ float tc_layer0(const MPLayout& L, const float* sm_h, const float* sm_hj, const float* sm_P,
-                                           const float* sm_Q, const float* wd, uint8_t* a0, int il, int lane, int t) {
+                                           const float* sm_Q, const float* wd, uint8_t* a0, int il, int lane, int t,
+                                           int part = 0, int nparts = 1) {
   const float* hi = sm_h + il * L.Hs;
   const float* hj = sm_hj + lane * L.Hs;
   float d = 0.f;
@@ -143,7 +152,7 @@ __device__ __forceinline__ float tc_layer0(const MPLayout& L, const float* sm_h,
   const float* P = sm_P + il * L.E0s;
   const float* Q = sm_Q + lane * L.E0s;
   const bool a_le_1 = L.alpha <= 1.f;
-  for (int c0 = 0; c0 < L.E0p; c0 += 8) {
+  for (int c0 = 8 * part; c0 < L.E0p; c0 += 8 * nparts) {
     float p[8], q[8], w[8], v[8];
     *reinterpret_cast<float4*>(p) = *reinterpret_cast<const float4*>(P + c0);
     *reinterpret_cast<float4*>(p + 4) = *reinterpret_cast<const float4*>(P + c0 + 4);
@@ -161,6 +170,11 @@ __device__ __forceinline__ float tc_layer0(const MPLayout& L, const float* sm_h,
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// one arrival per warp (the barrier counts warps): 128-256 same-address arrivals would serialise in the smem atomic unit
+__device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
 }
 
 // transpose-reduce of 16 per-lane values over the 32 lanes of a warp: returns, in every lane, the sum over all lanes
@@ -195,6 +209,26 @@ __device__ __forceinline__ float warp_transpose_sum16(const float (&v)[16], int 
 // A/B K-major buffer with nrows rows: next 8 rows +128 B (SBO), next 8 columns +nrows*16 B (LBO), 16 columns per MMA
 // A/B MN-major view of the same bytes (MN = column, K = row): next 8 columns +nrows*16 B (SBO), next 8 rows +128 B (LBO)
 // One group = the k-steps of one GEMM: descriptors of k-step 0 plus the per-step advance, built once per kernel.
+// Epilogue walk over a thread's 16-column accumulator chunks (chunk = part, part + nparts, ...) with two register
+// sets: the next chunk's TMEM load flies while the current one is processed.
+template <typename F>
+__device__ __forceinline__ void for_chunks(uint32_t tmem_row, int nch, int part, int nparts, F&& process) {
+  float va[16], vb[16];
+  int ch = part;
+  if (ch >= nch) return;
+  tmem_ld16_issue(tmem_row + (uint32_t)(ch << 4), va);
+  for (; ch < nch; ch += 2 * nparts) {
+    tmem_wait16(va);
+    if (ch + nparts < nch) tmem_ld16_issue(tmem_row + (uint32_t)((ch + nparts) << 4), vb);
+    process(va, ch << 4);
+    if (ch + nparts < nch) {
+      tmem_wait16(vb);
+      if (ch + 2 * nparts < nch) tmem_ld16_issue(tmem_row + (uint32_t)((ch + 2 * nparts) << 4), va);
+      process(vb, (ch + nparts) << 4);
+    }
+  }
+}
+
 struct MmaGroup {
   unsigned long long a, b;
   uint32_t d, idesc, astep, bstep;   // astep/bstep in 16-byte units
@@ -246,15 +280,17 @@ __device__ __forceinline__ int tiles_of_jet(const MPLayout& L) {
 //   issuer   : wait(ready[wg]) -> issue the stage's tcgen05.mma batch -> tcgen05.commit -> arrive(done[wg])
 // The issuer warp runs warp-convergent code only, so its descriptors stay in uniform registers.
 
-template <int NWG>
-__global__ void __launch_bounds__(NWG * 128 + 32, 1)
+// NH = warps per TMEM lane quadrant of a tile: 1 -> 128 threads per tile, 2 -> 256 (the pair splits the columns)
+template <int NWG, int NH>
+__global__ void __launch_bounds__(NWG * 128 * NH + 32, 1)
 edge_fwd_tc_kernel(const MPLayout L, const TCPlan T, const float* __restrict__ h, const float* __restrict__ pq,
                    const float* __restrict__ params, float* __restrict__ e_out) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  constexpr int NT = NWG * 128 + 32;
+  constexpr int TGT = 128 * NH;            // threads per tile group
+  constexpr int NT = NWG * TGT + 32;
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = (int)uni((uint32_t)(tid >> 5));     // provably warp-uniform
-  const bool is_issuer = warp == NWG * 4;
+  const bool is_issuer = warp == NWG * 4 * NH;
   float* smf = reinterpret_cast<float*>(smem + T.o_shared_f32);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T.o_bar);   // ready[wg] = bars[wg], done[wg] = bars[NWG + wg]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + T.o_tmem_slot);
@@ -263,7 +299,7 @@ edge_fwd_tc_kernel(const MPLayout L, const TCPlan T, const float* __restrict__ h
   stage_small(L, params, smf, tid, NT);
   stage_edge_weights_bf16(L, T.o_wT, params, smem, tid, NT);
   if (tid == 0) {
-    for (int w = 0; w < NWG; ++w) { mbar_init(bars + w, 128); mbar_init(bars + NWG + w, 1); }
+    for (int w = 0; w < NWG; ++w) { mbar_init(bars + w, TGT / 32); mbar_init(bars + NWG + w, 1); }
     fence_barrier_init();
   }
   if (is_issuer) tmem_alloc(tmem_slot, (uint32_t)T.tmem_cols_total);
@@ -306,8 +342,10 @@ edge_fwd_tc_kernel(const MPLayout L, const TCPlan T, const float* __restrict__ h
         par[w] ^= 1u;
         __syncwarp();
         tc_fence_after();
+        if (lane == 0) GJ_TRACE_PT(2, w * 100 + done_st[w] % S);
         run_group(tbl + w * S + done_st[w] % S, unused);
         mma_commit_elect(bars + NWG + w);
+        if (lane == 0) GJ_TRACE_PT(2, 1000 + w * 100 + done_st[w] % S);
         ++done_st[w];
       }
       any = false;
@@ -316,7 +354,8 @@ edge_fwd_tc_kernel(const MPLayout L, const TCPlan T, const float* __restrict__ h
     }
   } else {
     // =================================== compute warpgroups ===================================
-    const int wg = warp >> 2, t = tid & 127, wq = warp & 3;
+    const int wg = warp / (4 * NH), w8 = warp % (4 * NH), wq = w8 & 3, part = w8 >> 2;
+    const int t = tid - wg * TGT, row = wq * 32 + lane;
     uint8_t* wgb = smem + T.wg_base + wg * T.wg_stride;
     float* wgf = reinterpret_cast<float*>(wgb + T.w_f32);
     uint64_t* ready = bars + wg;
@@ -337,28 +376,30 @@ edge_fwd_tc_kernel(const MPLayout L, const TCPlan T, const float* __restrict__ h
       const float* pqjet = pq + (size_t)jet * L.N * 2 * L.E0p;
       for (int i0 = 0; i0 < L.N; i0 += GJ_IB) {
         const int ni = min(GJ_IB, L.N - i0);
-        named_bar_sync(bar_id, 128);
-        wg_load_block(L, hjet, pqjet, 0, i0, sm_h, sm_P, t);
-        for (int idx = t; idx < GJ_IB * L.ELs; idx += 128) sm_e[idx] = 0.f;
+        named_bar_sync(bar_id, TGT);
+        wg_load_block(L, hjet, pqjet, 0, i0, sm_h, sm_P, t, TGT);
+        for (int idx = t; idx < GJ_IB * L.ELs; idx += TGT) sm_e[idx] = 0.f;
         for (int j0 = 0; j0 < L.N; j0 += 32) {
           const int nj = min(32, L.N - j0);
-          named_bar_sync(bar_id, 128);
-          wg_load_block(L, hjet, pqjet, 1, j0, sm_hj, sm_Q, t);
-          named_bar_sync(bar_id, 128);
+          named_bar_sync(bar_id, TGT);
+          wg_load_block(L, hjet, pqjet, 1, j0, sm_hj, sm_Q, t, TGT);
+          named_bar_sync(bar_id, TGT);
           const int nit = (ni + 3) / 4;
           for (int it = 0; it < nit; ++it) {
             const int il = it * 4 + wq;
             const bool valid = il < ni && lane < nj;
-            tc_layer0(L, sm_h, sm_hj, sm_P, sm_Q, wd, wgb + T.w_act[0], il, lane, t);
+            tc_layer0(L, sm_h, sm_hj, sm_P, sm_Q, wd, wgb + T.w_act[0], il, lane, row, part, NH);
             fence_proxy_async();
             tc_fence_before();
-            mbar_arrive(ready);
+            warp_arrive(ready, lane);
+            if (t == 0) GJ_TRACE_PT(wg, 10);
             for (int l = 1; l < Le; ++l) {
               mbar_wait(done, phase); phase ^= 1u;
               tc_fence_after();
+              if (t == 0) GJ_TRACE_PT(wg, 20 + l);
               const bool last = (l == Le - 1);
               const float* bias = smf + L.o_bE[l];
-              uint8_t* al = wgb + T.w_act[l] + t * 16;
+              uint8_t* al = wgb + T.w_act[l] + row * 16;
               const int nch = L.Ep[l] >> 4;
               auto process = [&](float (&v)[16], int c0) {
                 float bq[16];
@@ -380,30 +421,21 @@ edge_fwd_tc_kernel(const MPLayout L, const TCPlan T, const float* __restrict__ h
                   if ((lane & 1) == 0) sm_e[il * L.ELs + c0 + (lane >> 1)] += s;
                 }
               };
-              float va[16], vb[16];
-              tmem_ld16_issue(tmem_row, va);
-              for (int ch = 0; ch < nch; ch += 2) {
-                tmem_wait16(va);
-                if (ch + 1 < nch) tmem_ld16_issue(tmem_row + (uint32_t)((ch + 1) << 4), vb);
-                process(va, ch << 4);
-                if (ch + 1 < nch) {
-                  tmem_wait16(vb);
-                  if (ch + 2 < nch) tmem_ld16_issue(tmem_row + (uint32_t)((ch + 2) << 4), va);
-                  process(vb, (ch + 1) << 4);
-                }
-              }
+              for_chunks(tmem_row, nch, part, NH, process);
               if (!last) {
                 fence_proxy_async();
                 tc_fence_before();
-                mbar_arrive(ready);
+                warp_arrive(ready, lane);
+                if (t == 0) GJ_TRACE_PT(wg, 30 + l);
               } else {
                 tc_fence_before();
+                if (t == 0) GJ_TRACE_PT(wg, 60);
               }
             }
           }
         }
-        named_bar_sync(bar_id, 128);
-        for (int idx = t; idx < ni * L.EL; idx += 128) {
+        named_bar_sync(bar_id, TGT);
+        for (int idx = t; idx < ni * L.EL; idx += TGT) {
           int n = idx / L.EL, c = idx - n * L.EL;
           e_out[((size_t)jet * L.N + i0 + n) * L.EL + c] = sm_e[n * L.ELs + c];
         }
@@ -428,13 +460,6 @@ edge_fwd_tc_kernel(const MPLayout L, const TCPlan T, const float* __restrict__ h
 //                      (at l = 1 also the bias gradients: column sums of ALL dz_l as one M=128 MMA per 128 columns
 //                       against a ones operand, the dz_l buffers being contiguous in shared memory)
 // The first layer's adjoint (dP, dQ, distance gradient, d wd) is reduced on the CUDA cores from dz_0 in fp32.
-// Optional timeline of the issuer / warpgroup handshake (GJ_TRACE=1 in the environment): (tag, clock) pairs of CTA 0.
-__device__ long long g_trace[8192];
-__device__ int g_trace_n[4];
-#define GJ_TRACE_PT(who, tag)                                                                         \
-  do { if (T.trace && blockIdx.x == 0) { int i_ = g_trace_n[who]; if (i_ < 1024) { g_trace[(who) * 2048 + 2 * i_] = (tag);  \
-         g_trace[(who) * 2048 + 2 * i_ + 1] = clock64(); g_trace_n[who] = i_ + 1; } } } while (0)
-
 struct BwdPlan {
   int nwg, Le, trace;
   // shared regions (bytes from smem base)
@@ -562,7 +587,7 @@ edge_bwd_tc_kernel(const MPLayout L, const BwdPlan T, const float* __restrict__ 
   stage_edge_weights_bf16(L, T.o_wT, params, smem, tid, NT);
   for (int idx = tid; idx < 16 * 128; idx += NT) reinterpret_cast<__nv_bfloat16*>(smem + T.o_ones)[idx] = __float2bfloat16_rn(1.f);
   if (tid == 0) {
-    for (int w = 0; w < NWG; ++w) { mbar_init(bars + w, 128); mbar_init(bars + NWG + w, 1); }
+    for (int w = 0; w < NWG; ++w) { mbar_init(bars + w, 4); mbar_init(bars + NWG + w, 1); }
     fence_barrier_init();
   }
   if (is_issuer) tmem_alloc(tmem_slot, (uint32_t)T.tmem_cols);
@@ -705,7 +730,7 @@ edge_bwd_tc_kernel(const MPLayout L, const BwdPlan T, const float* __restrict__ 
             const float dij = tc_layer0(L, sm_h, sm_hj, sm_P, sm_Q, wd, A0, il, lane, t);
             fence_proxy_async();
             tc_fence_before();
-            mbar_arrive(ready);
+            warp_arrive(ready, lane);
             if (t == 0) GJ_TRACE_PT(wg, 10);
             // ---- forward stages ----
             for (int l = 1; l < Le; ++l) {
@@ -752,7 +777,7 @@ edge_bwd_tc_kernel(const MPLayout L, const BwdPlan T, const float* __restrict__ 
               }
               fence_proxy_async();
               tc_fence_before();
-              mbar_arrive(ready);
+              warp_arrive(ready, lane);
               if (t == 0) GJ_TRACE_PT(wg, 30 + l);
             }
             // ---- backward stages ----
@@ -789,7 +814,7 @@ edge_bwd_tc_kernel(const MPLayout L, const BwdPlan T, const float* __restrict__ 
                 }
                 fence_proxy_async();
                 tc_fence_before();
-                mbar_arrive(ready);
+                warp_arrive(ready, lane);
                 if (t == 0) GJ_TRACE_PT(wg, 50 + l);
               } else {
                 // dz_0 = da_0 * leaky'(a_0), consumed in fp32: G_ij, dQ_j, dP_i, d(wd)
@@ -1001,12 +1026,17 @@ int gj_edge_fwd_tc(MPLayout L, const float* h, const float* pq, const float* par
     gj_set_error("gj_mp_step_fwd(bf16): needs %d B shared memory / %d TMEM columns (limits 232448 / 512)", T.smem_bytes, T.tmem_cols_total);
     return GJ_ERR_SMEM;
   }
-  auto kern = edge_fwd_tc_kernel<NWG>;
+  static const int nh_env = getenv("GJ_TC_NH") ? atoi(getenv("GJ_TC_NH")) : 2;
+  static const int trace_fwd = getenv("GJ_TRACE") ? atoi(getenv("GJ_TRACE")) : 0;
+  T.trace = trace_fwd == 2;
+  if (T.trace) { int z[4] = {0, 0, 0, 0}; cudaMemcpyToSymbolAsync(g_trace_n, z, sizeof(z), 0, cudaMemcpyHostToDevice, stream); }
+  const int NH = nh_env == 1 ? 1 : 2;
+  auto kern = NH == 1 ? edge_fwd_tc_kernel<NWG, 1> : edge_fwd_tc_kernel<NWG, 2>;
   cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T.smem_bytes);
   if (ce != cudaSuccess) { gj_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   int sms = gj_num_sms();
   int grid = (L.B + NWG - 1) / NWG; if (grid > sms) grid = sms;
-  kern<<<grid, NWG * 128 + 32, T.smem_bytes, stream>>>(L, T, h, pq, params, e_out);
+  kern<<<grid, NWG * 128 * NH + 32, T.smem_bytes, stream>>>(L, T, h, pq, params, e_out);
   ce = cudaGetLastError();
   if (ce != cudaSuccess) { gj_set_error("edge_fwd_tc launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   return GJ_OK;
@@ -1050,8 +1080,8 @@ int gj_edge_bwd_tc(MPLayout L, const float* h, const float* pq, const float* par
   }
   const int grid = tc_bwd_grid(Lt.B, 2);
   static const int trace_env = getenv("GJ_TRACE") ? atoi(getenv("GJ_TRACE")) : 0;
-  T.trace = trace_env;
-  if (trace_env) { int z[4] = {0, 0, 0, 0}; cudaMemcpyToSymbolAsync(g_trace_n, z, sizeof(z), 0, cudaMemcpyHostToDevice, stream); }
+  T.trace = trace_env == 1;
+  if (T.trace) { int z[4] = {0, 0, 0, 0}; cudaMemcpyToSymbolAsync(g_trace_n, z, sizeof(z), 0, cudaMemcpyHostToDevice, stream); }
   int rc;
   switch (Lt.E0p) {
     case 16: rc = launch_tc_bwd<16>(Lt, T, h, pq, params, de, dpq, dh, part, grid, stream); break;

@@ -357,23 +357,37 @@ __global__ void __launch_bounds__(NK_THREADS) node_post_bwd_kernel(const PostArg
   for (int idx = threadIdx.x; idx < A.n_node_params; idx += NK_THREADS) out[idx] = dpar[idx];
 }
 
-// out[dst_off + p] = sum_c part[c][p]   (fixed order => deterministic)
-__global__ void reduce_partials_kernel(const float* __restrict__ part, int nparts, int n, float* __restrict__ out) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n) return;
+// Fixed-order reduction of per-CTA partials: block = 32 outputs x 8 slices; slice y sums partials y, y+8, ... and the
+// 8 slice sums are combined through shared memory in slice order (deterministic for a given grid size).
+#define RED_SLICES 8
+__device__ __forceinline__ float reduce_column(const float* __restrict__ part, int nparts, int n, int p) {
+  __shared__ float red[RED_SLICES][33];
   float acc = 0.f;
-  for (int c = 0; c < nparts; ++c) acc += part[(size_t)c * n + p];
-  out[p] = acc;
+  if (p < n)
+    for (int c = threadIdx.y; c < nparts; c += RED_SLICES) acc += part[(size_t)c * n + p];
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  float tot = 0.f;
+  if (threadIdx.y == 0) {
+#pragma unroll
+    for (int y = 0; y < RED_SLICES; ++y) tot += red[y][threadIdx.x];
+  }
+  return tot;
+}
+
+__global__ void reduce_partials_kernel(const float* __restrict__ part, int nparts, int n, float* __restrict__ out) {
+  const int p = blockIdx.x * 32 + threadIdx.x;
+  const float v = reduce_column(part, nparts, n, p);
+  if (threadIdx.y == 0 && p < n) out[p] = v;
 }
 
 // dW0 scatter: the node_pre partials are [Wa E0*H][Wb E0*H][b0 E0]; the packed layout is W0 (E0, 2H+1) then b0.
 __global__ void reduce_pre_partials_kernel(const float* __restrict__ part, int nparts, int E0, int H, float* __restrict__ dW0,
                                            float* __restrict__ db0) {
   const int n = E0 * 2 * H + E0;
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n) return;
-  float acc = 0.f;
-  for (int c = 0; c < nparts; ++c) acc += part[(size_t)c * n + p];
+  const int p = blockIdx.x * 32 + threadIdx.x;
+  const float acc = reduce_column(part, nparts, n, p);
+  if (threadIdx.y != 0 || p >= n) return;
   const int K0 = 2 * H + 1;
   if (p < E0 * H) { const int c = p / H, k = p - c * H; dW0[c * K0 + k] = acc; }
   else if (p < 2 * E0 * H) { const int q = p - E0 * H; const int c = q / H, k = q - c * H; dW0[c * K0 + H + k] = acc; }
@@ -390,6 +404,7 @@ void gj_set_error(const char* fmt, ...);
 
 static const int kSmemLimit = 227 * 1024;
 static const int kSmemTarget = 54 * 1024;   // <= this many bytes per CTA lets 4 CTAs share an SM (latency hiding)
+static const int kSmemTargetBwd = 110 * 1024;   // backward: 2 CTAs per SM, larger row blocks (fewer partials, longer wgrad loops)
 
 static int pre_plan(const MPLayout& L, PreArgs* A, bool backward) {
   memset(A, 0, sizeof(*A));
@@ -416,7 +431,7 @@ static int pre_plan(const MPLayout& L, PreArgs* A, bool backward) {
       A->o_dpar = take(L.E[0] * 2 * L.H + L.E[0]);
     }
     A->smem_floats = off;
-    if (off * 4 <= (R > 16 ? kSmemTarget : kSmemLimit)) return off * 4;
+    if (off * 4 <= (R > 16 ? (backward ? kSmemTargetBwd : kSmemTarget) : kSmemLimit)) return off * 4;
   }
   return -1;
 }
@@ -447,7 +462,7 @@ static int post_plan(const MPLayout& L, PostArgs* A, bool backward) {
     for (int m = 0; m < nY; ++m) A->o_Y[m] = take(R * A->S);
     if (backward) { A->o_g0 = take(R * A->S); A->o_g1 = take(R * A->S); A->o_dpar = take(A->n_node_params); }
     A->smem_floats = off;
-    if (off * 4 <= (R > 16 ? kSmemTarget : kSmemLimit)) return off * 4;
+    if (off * 4 <= (R > 16 ? (backward ? kSmemTargetBwd : kSmemTarget) : kSmemLimit)) return off * 4;
   }
   return -1;
 }
@@ -495,7 +510,7 @@ int gj_node_pre_bwd(const MPLayout& L, const float* h, const float* params, cons
   const int grid = nk_grid(A.rows, A.R, bytes);
   node_pre_bwd_kernel<<<grid, NK_THREADS, bytes, st>>>(A, h, params + L.pW[0], dpq, dh, part);
   const int n = L.E[0] * 2 * L.H + L.E[0];
-  reduce_pre_partials_kernel<<<(n + 255) / 256, 256, 0, st>>>(part, grid, L.E[0], L.H, dparams + L.pW[0], dparams + L.pb[0]);
+  reduce_pre_partials_kernel<<<(n + 31) / 32, dim3(32, RED_SLICES), 0, st>>>(part, grid, L.E[0], L.H, dparams + L.pW[0], dparams + L.pb[0]);
   NK_CHECK_LAUNCH("node_pre_bwd launch");
   return GJ_OK;
 }
@@ -522,14 +537,14 @@ int gj_node_post_bwd(const MPLayout& L, const float* e, const float* h, const fl
   if (int rc = nk_set_smem(node_post_bwd_kernel, bytes)) return rc;
   const int grid = nk_grid(A.rows, A.R, bytes);
   node_post_bwd_kernel<<<grid, NK_THREADS, bytes, st>>>(A, e, h, params, dh_out, de, dh, part);
-  reduce_partials_kernel<<<(A.n_node_params + 255) / 256, 256, 0, st>>>(part, grid, A.n_node_params, dparams + A.p_first);
+  reduce_partials_kernel<<<(A.n_node_params + 31) / 32, dim3(32, RED_SLICES), 0, st>>>(part, grid, A.n_node_params, dparams + A.p_first);
   NK_CHECK_LAUNCH("node_post_bwd launch");
   return GJ_OK;
 }
 
 int gj_reduce_partials(const float* part, int nparts, int n, float* out, cudaStream_t st) {
   if (n <= 0) return GJ_OK;
-  reduce_partials_kernel<<<(n + 255) / 256, 256, 0, st>>>(part, nparts, n, out);
+  reduce_partials_kernel<<<(n + 31) / 32, dim3(32, RED_SLICES), 0, st>>>(part, nparts, n, out);
   NK_CHECK_LAUNCH("reduce_partials launch");
   return GJ_OK;
 }

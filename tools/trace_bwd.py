@@ -1,6 +1,6 @@
 """GJ_TRACE=1 python tools/trace_bwd.py : prints the issuer / warpgroup handshake timeline of one backward launch."""
 import ctypes, os, sys
-os.environ["GJ_TRACE"] = "1"
+os.environ.setdefault("GJ_TRACE", "1")   # 1: backward kernel, 2: forward kernel
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from gnn_jet_autoencoder_b200 import _lib, ops
@@ -15,7 +15,10 @@ args = (N, H, ew, nw, 0.2, 0, 1)
 y, e = torch.ops.gnnjet.mp_step_fwd(h, flat, *args)
 dy = torch.randn_like(y)
 for _ in range(2):
-    torch.ops.gnnjet.mp_step_bwd(h, e, flat, dy, *args)
+    if os.environ["GJ_TRACE"] == "2":
+        torch.ops.gnnjet.mp_step_fwd(h, flat, *args)
+    else:
+        torch.ops.gnnjet.mp_step_bwd(h, e, flat, dy, *args)
 torch.cuda.synchronize()
 buf = (ctypes.c_longlong * 8192)()
 cnt = (ctypes.c_int * 4)()
