@@ -30,8 +30,9 @@ int next_pow2_cols(int c) { int p = 32; while (p < c) p <<= 1; return p; }
 __device__ long long g_trace[8192];
 __device__ int g_trace_n[4];
 #define GJ_TRACE_PT(who, tag)                                                                         \
-  do { if (T.trace && blockIdx.x == 0) { int i_ = g_trace_n[who]; if (i_ < 1024) { g_trace[(who) * 2048 + 2 * i_] = (tag);  \
-         g_trace[(who) * 2048 + 2 * i_ + 1] = clock64(); g_trace_n[who] = i_ + 1; } } } while (0)
+  do { if (T.trace && blockIdx.x == 0 && tr_i < 1024) { g_trace[(who) * 2048 + 2 * tr_i] = (tag);     \
+         g_trace[(who) * 2048 + 2 * tr_i + 1] = clock64(); ++tr_i; } } while (0)
+#define GJ_TRACE_END(who) do { if (T.trace && blockIdx.x == 0) g_trace_n[who] = tr_i; } while (0)
 
 struct TCPlan {
   int nwg, trace;
@@ -41,7 +42,7 @@ struct TCPlan {
   int wg_base, wg_stride;   // per-warpgroup region
   int w_act[GJ_MAX_LAYERS]; // bf16 activation buffers inside the warpgroup region (bytes)
   int w_f32;                // float region inside the warpgroup region
-  int tmem_cols_per_wg, tmem_cols_total;
+  int acc_cols, tmem_cols_per_wg, tmem_cols_total;   // two accumulator buffers of acc_cols columns per warpgroup
   int smem_bytes;
 };
 
@@ -69,7 +70,7 @@ void plan_tc_fwd(MPLayout* L, TCPlan* T, int nwg) {
   L->o_Q = w.take(32 * L->E0s);
   L->o_e = w.take(GJ_IB * L->ELs);
   int off = 0;
-  T->o_bar = off; off += 64;
+  T->o_bar = off; off += gj_round_up(nwg * (1 + 16) * 8, 64);
   T->o_tmem_slot = off; off += 64;
   T->o_tbl = off; off += gj_round_up(nwg * GJ_MAX_LAYERS * 40, 128);
   for (int l = 1; l < L->Le; ++l) { T->o_wT[l] = off; off += L->Ep[l] * L->Kp[l] * 2; }
@@ -84,7 +85,8 @@ void plan_tc_fwd(MPLayout* L, TCPlan* T, int nwg) {
   T->smem_bytes = T->wg_base + nwg * wo;
   int mx = 32;
   for (int l = 1; l < L->Le; ++l) if (L->Ep[l] > mx) mx = L->Ep[l];
-  T->tmem_cols_per_wg = gj_round_up(mx, 32);
+  T->acc_cols = gj_round_up(mx, 32);
+  T->tmem_cols_per_wg = 2 * T->acc_cols;
   T->tmem_cols_total = next_pow2_cols(T->tmem_cols_per_wg * nwg);
 }
 
@@ -161,7 +163,7 @@ __device__ __forceinline__ float tc_layer0(const MPLayout& L, const float* sm_h,
     *reinterpret_cast<float4*>(w) = *reinterpret_cast<const float4*>(wd + c0);
     *reinterpret_cast<float4*>(w + 4) = *reinterpret_cast<const float4*>(wd + c0 + 4);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = gj_leaky2(fmaf(w[i], d, p[i] + q[i]), L.alpha, a_le_1);
+    for (int i = 0; i < 8; ++i) { const float z = fmaf(w[i], d, p[i] + q[i]); v[i] = fmaxf(z, L.alpha * z); }
     uint4 pk = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
     *reinterpret_cast<uint4*>(a0 + (c0 >> 3) * 2048 + t * 16) = pk;
   }
@@ -171,6 +173,14 @@ __device__ __forceinline__ float tc_layer0(const MPLayout& L, const float* sm_h,
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Wait of a whole tile group on an mbarrier: only its first warp polls (a polling warp burns issue slots every time
+// the hardware sleep is woken by unrelated barrier traffic); the other warps block on a hardware named barrier, which
+// costs no issue slots, and are released when the polling warp joins it.
+__device__ __forceinline__ void group_wait(uint64_t* bar, uint32_t parity, bool poller, int bar_id, int nthreads) {
+  if (poller) mbar_wait(bar, parity);
+  named_bar_sync(bar_id, nthreads);
+}
+
 // one arrival per warp (the barrier counts warps): 128-256 same-address arrivals would serialise in the smem atomic unit
 __device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
   __syncwarp();
@@ -209,6 +219,13 @@ __device__ __forceinline__ float warp_transpose_sum16(const float (&v)[16], int 
 // A/B K-major buffer with nrows rows: next 8 rows +128 B (SBO), next 8 columns +nrows*16 B (LBO), 16 columns per MMA
 // A/B MN-major view of the same bytes (MN = column, K = row): next 8 columns +nrows*16 B (SBO), next 8 rows +128 B (LBO)
 // One group = the k-steps of one GEMM: descriptors of k-step 0 plus the per-step advance, built once per kernel.
+// v[q] = leaky(v[q] + b[q]) for 16 values; the alpha <= 1 test is taken once, not per value (FADD + FMUL + FMNMX each)
+// (the tensor-core kernels are only launched for 0 <= alpha <= 1, where LeakyReLU(z) = max(z, alpha z))
+__device__ __forceinline__ void bias_leaky16(float (&v)[16], const float* bq, float alpha, bool) {
+#pragma unroll
+  for (int q = 0; q < 16; ++q) { const float z = v[q] + bq[q]; v[q] = fmaxf(z, alpha * z); }
+}
+
 // Epilogue walk over a thread's 16-column accumulator chunks (chunk = part, part + nparts, ...) with two register
 // sets: the next chunk's TMEM load flies while the current one is processed.
 template <typename F>
@@ -232,7 +249,8 @@ __device__ __forceinline__ void for_chunks(uint32_t tmem_row, int nch, int part,
 struct MmaGroup {
   unsigned long long a, b;
   uint32_t d, idesc, astep, bstep;   // astep/bstep in 16-byte units
-  int nk, accbit;                    // accbit >= 0: shared accumulator id (accumulate unless it is the first write)
+  short nk, commit;                  // commit: after this group, tcgen05.commit to 0 nothing / 1 done[wg] / 2 done2[wg]
+  int accbit;                        // accbit >= 0: shared accumulator id (accumulate unless it is the first write)
 };
 
 static_assert(sizeof(MmaGroup) == 40, "plan_tc_bwd reserves 40 bytes per group");
@@ -240,32 +258,33 @@ static_assert(sizeof(MmaGroup) == 40, "plan_tc_bwd reserves 40 bytes per group")
 __device__ __forceinline__ MmaGroup grp_fwd(uint32_t d, uint32_t a, uint32_t w, int N, int K) {
   // acc[128 x N] = act[128 x K] W[N x K]^T, both K-major
   return MmaGroup{make_smem_desc(a, 2048, 128), make_smem_desc(w, N * 16, 128), d, make_idesc_bf16(128, N, 0, 0), 4096u >> 4,
-                  (uint32_t)(2 * N * 16) >> 4, K / 16, -1};
+                  (uint32_t)(2 * N * 16) >> 4, (short)(K / 16), 0, -1};
 }
 __device__ __forceinline__ MmaGroup grp_dgrad(uint32_t d, uint32_t dz, uint32_t w, int Kin, int Eout) {
   // acc[128 x Kin] = dz[128 x Eout] W[Eout x Kin]: A = dz K-major, B = W viewed MN-major (MN = in feature, K = out feature)
   return MmaGroup{make_smem_desc(dz, 2048, 128), make_smem_desc(w, 128, Eout * 16), d, make_idesc_bf16(128, Kin, 0, 1), 4096u >> 4,
-                  256u >> 4, Eout / 16, -1};
+                  256u >> 4, (short)(Eout / 16), 0, -1};
 }
 __device__ __forceinline__ MmaGroup grp_wgrad(uint32_t d, uint32_t x, uint32_t y, int M, int N, int accbit) {
   // D[M x N] += X^T Y over the 128 tile rows: both operands MN-major views of 128-row buffers
-  return MmaGroup{make_smem_desc(x, 128, 2048), make_smem_desc(y, 128, 2048), d, make_idesc_bf16(M, N, 1, 1), 256u >> 4, 256u >> 4, 8,
+  return MmaGroup{make_smem_desc(x, 128, 2048), make_smem_desc(y, 128, 2048), d, make_idesc_bf16(M, N, 1, 1), 256u >> 4, 256u >> 4, 8, 0,
                   accbit};
 }
 __device__ __forceinline__ MmaGroup grp_colsum(uint32_t d, uint32_t x, uint32_t ones, int M, int accbit) {
   // D[M x 16] += X^T 1: column sums of a 128-row buffer (ones operand: K-major [16][128])
-  return MmaGroup{make_smem_desc(x, 128, 2048), make_smem_desc(ones, 256, 128), d, make_idesc_bf16(M, 16, 1, 0), 256u >> 4, 512u >> 4, 8,
+  return MmaGroup{make_smem_desc(x, 128, 2048), make_smem_desc(ones, 256, 128), d, make_idesc_bf16(M, 16, 1, 0), 256u >> 4, 512u >> 4, 8, 0,
                   accbit};
 }
 // executed by all 32 lanes of the issuer warp (convergent); fields are broadcast so they live in uniform registers
-__device__ __forceinline__ void run_group(const MmaGroup* g, uint32_t& inited) {
+__device__ __forceinline__ int run_group(const MmaGroup* g, uint32_t& inited) {
   const uint64_t a = uni64(g->a), b = uni64(g->b);
   const uint32_t d = uni(g->d), idesc = uni(g->idesc), astep = uni(g->astep), bstep = uni(g->bstep);
-  const int nk = (int)uni((uint32_t)g->nk), accbit = (int)uni((uint32_t)g->accbit);
+  const int nk = (int)uni((uint32_t)g->nk), accbit = (int)uni((uint32_t)g->accbit), commit = (int)uni((uint32_t)g->commit);
   uint32_t accumulate = 0;
   if (accbit >= 0) { accumulate = (inited >> accbit) & 1u; inited |= 1u << accbit; }
   for (int ks = 0; ks < nk; ++ks)
     mma_bf16_ss_elect(d, desc_advance(a, astep, ks), desc_advance(b, bstep, ks), idesc, (accumulate | (uint32_t)(ks > 0)));
+  return commit;
 }
 
 __device__ __forceinline__ int tiles_of_jet(const MPLayout& L) {
@@ -275,92 +294,136 @@ __device__ __forceinline__ int tiles_of_jet(const MPLayout& L) {
   return n;
 }
 
+// pieces of the first edge layer for the streaming forward kernel
+__device__ __forceinline__ float tc_pair_distance(const MPLayout& L, const float* hi, const float* hj) {
+  float d = 0.f;
+  if (L.mink) {
+    const float4 a = *reinterpret_cast<const float4*>(hi), b = *reinterpret_cast<const float4*>(hj);
+    const float x0 = b.x - a.x + GJ_EPS, x1 = b.y - a.y + GJ_EPS, x2 = b.z - a.z + GJ_EPS, x3 = b.w - a.w + GJ_EPS;
+    d = x0 * x0 - x1 * x1 - x2 * x2 - x3 * x3;
+  } else {
+    const int H4 = L.H & ~3;
+    for (int k = 0; k < H4; k += 4) {
+      const float4 a = *reinterpret_cast<const float4*>(hi + k), b = *reinterpret_cast<const float4*>(hj + k);
+      const float x0 = b.x - a.x + GJ_EPS, x1 = b.y - a.y + GJ_EPS, x2 = b.z - a.z + GJ_EPS, x3 = b.w - a.w + GJ_EPS;
+      d = fmaf(x0, x0, d); d = fmaf(x1, x1, d); d = fmaf(x2, x2, d); d = fmaf(x3, x3, d);
+    }
+    for (int k = H4; k < L.H; ++k) { const float x = hj[k] - hi[k] + GJ_EPS; d = fmaf(x, x, d); }
+  }
+  return d;
+}
+// channels [c0, c0 + 16) of a0 = leaky(P_i + Q_j + wd d_ij) for one row -> bf16 A operand (dst already points at the row)
+__device__ __forceinline__ void tc_layer0_chunk(const MPLayout& L, const float* P, const float* Q, const float* wd, uint8_t* dst,
+                                                int c0, float d, bool a_le_1) {
+#pragma unroll
+  for (int h8 = 0; h8 < 2; ++h8) {
+    const int c = c0 + 8 * h8;
+    float p[8], q[8], w[8], v[8];
+    *reinterpret_cast<float4*>(p) = *reinterpret_cast<const float4*>(P + c);
+    *reinterpret_cast<float4*>(p + 4) = *reinterpret_cast<const float4*>(P + c + 4);
+    *reinterpret_cast<float4*>(q) = *reinterpret_cast<const float4*>(Q + c);
+    *reinterpret_cast<float4*>(q + 4) = *reinterpret_cast<const float4*>(Q + c + 4);
+    *reinterpret_cast<float4*>(w) = *reinterpret_cast<const float4*>(wd + c);
+    *reinterpret_cast<float4*>(w + 4) = *reinterpret_cast<const float4*>(wd + c + 4);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float z = fmaf(w[i], d, p[i] + q[i]); v[i] = fmaxf(z, L.alpha * z); }
+    *reinterpret_cast<uint4*>(dst + (c >> 3) * 2048) =
+        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  }
+}
+
 // Handshake between the compute warpgroups and the MMA-issuer warp (both tensor-core kernels):
 //   warpgroup: write operands to smem -> fence.proxy.async -> arrive(ready[wg])      wait(done[wg]) -> epilogue from TMEM
 //   issuer   : wait(ready[wg]) -> issue the stage's tcgen05.mma batch -> tcgen05.commit -> arrive(done[wg])
 // The issuer warp runs warp-convergent code only, so its descriptors stay in uniform registers.
 
-// NH = warps per TMEM lane quadrant of a tile: 1 -> 128 threads per tile, 2 -> 256 (the pair splits the columns)
+// NH = warps per TMEM lane quadrant of a tile: 1 -> 128 threads per tile, 2 -> 256 (the pair splits the column chunks).
+//
+// The forward kernel STREAMS layer l+1's MMA behind layer l's epilogue: the epilogue publishes every 16-column chunk of
+// a_l (one k-step of layer l+1) on its own mbarrier, the issuer issues that k-step as soon as the chunk is complete, and
+// the accumulators alternate between two TMEM buffers (layer l reads buffer l&1 while layer l+1 fills the other), so a
+// warpgroup only waits for the tail of an MMA batch instead of the whole batch.
+#define GJ_MAX_CHUNKS 16
 template <int NWG, int NH>
-__global__ void __launch_bounds__(NWG * 128 * NH + 32, 1)
+__global__ void __launch_bounds__(NWG * 128 * NH + NWG * 32, 1)
 edge_fwd_tc_kernel(const MPLayout L, const TCPlan T, const float* __restrict__ h, const float* __restrict__ pq,
                    const float* __restrict__ params, float* __restrict__ e_out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int TGT = 128 * NH;            // threads per tile group
-  constexpr int NT = NWG * TGT + 32;
+  constexpr int NT = NWG * TGT + NWG * 32;
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = (int)uni((uint32_t)(tid >> 5));     // provably warp-uniform
-  const bool is_issuer = warp == NWG * 4 * NH;
+  const bool is_issuer = warp >= NWG * 4 * NH;
   float* smf = reinterpret_cast<float*>(smem + T.o_shared_f32);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T.o_bar);   // ready[wg] = bars[wg], done[wg] = bars[NWG + wg]
+  // barriers: done[wg] = bars[wg]; chunk[wg][c] = bars[NWG + wg * GJ_MAX_CHUNKS + c]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T.o_bar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + T.o_tmem_slot);
   const int Le = L.Le;
 
   stage_small(L, params, smf, tid, NT);
   stage_edge_weights_bf16(L, T.o_wT, params, smem, tid, NT);
   if (tid == 0) {
-    for (int w = 0; w < NWG; ++w) { mbar_init(bars + w, TGT / 32); mbar_init(bars + NWG + w, 1); }
+    for (int w = 0; w < NWG; ++w) {
+      mbar_init(bars + w, 1);
+      for (int c = 0; c < GJ_MAX_CHUNKS; ++c) mbar_init(bars + NWG + w * GJ_MAX_CHUNKS + c, 4);   // the 4 row quadrants
+    }
     fence_barrier_init();
   }
-  if (is_issuer) tmem_alloc(tmem_slot, (uint32_t)T.tmem_cols_total);
+  if (warp == NWG * 4 * NH) tmem_alloc(tmem_slot, (uint32_t)T.tmem_cols_total);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  int tr_i = 0;      // trace cursor (register; written back once at the end)
 
   if (is_issuer) {
-    // =================================== MMA issuer (warp-convergent) ===================================
+    // =================================== MMA issuers (warp-convergent) ===================================
+    // One issuer warp per warpgroup (the forward kernel has no shared accumulators, so no ordering between them is
+    // needed): it sleeps on the next chunk barrier and issues that k-step the moment the chunk is complete.
+    const int w = warp - NWG * 4 * NH;
     const int S = Le - 1;
     const int tpj = tiles_of_jet(L);
-    int total[NWG], done_st[NWG];
-    uint32_t par[NWG];
-    bool any = false;
-#pragma unroll
-    for (int w = 0; w < NWG; ++w) {
-      const int first = blockIdx.x * NWG + w;
-      const int njets = first < L.B ? (L.B - first + gridDim.x * NWG - 1) / (gridDim.x * NWG) : 0;
-      total[w] = njets * tpj * S; done_st[w] = 0; par[w] = 0;
-      any |= total[w] > 0;
-    }
-    MmaGroup* tbl = reinterpret_cast<MmaGroup*>(smem + T.o_tbl);      // [NWG][S]
+    MmaGroup* tbl = reinterpret_cast<MmaGroup*>(smem + T.o_tbl) + w * S;      // [NWG][S]
     if (lane == 0) {
-      for (int w = 0; w < NWG; ++w) {
-        const uint32_t wgb = smem_u32(smem + T.wg_base + w * T.wg_stride);
-        for (int l = 1; l < Le; ++l)
-          tbl[w * S + l - 1] = grp_fwd(tmem_base + (uint32_t)(w * T.tmem_cols_per_wg), wgb + T.w_act[l - 1],
-                                       smem_u32(smem + T.o_wT[l]), L.Ep[l], L.Kp[l]);
-      }
+      const uint32_t wgb = smem_u32(smem + T.wg_base + w * T.wg_stride);
+      for (int l = 1; l < Le; ++l)
+        tbl[l - 1] = grp_fwd(tmem_base + (uint32_t)(w * T.tmem_cols_per_wg + (l & 1) * T.acc_cols), wgb + T.w_act[l - 1],
+                             smem_u32(smem + T.o_wT[l]), L.Ep[l], L.Kp[l]);
     }
     __syncwarp();
-    uint32_t unused = 0;
-    while (any) {
-#pragma unroll
-      for (int w = 0; w < NWG; ++w) {
-        if (done_st[w] >= total[w]) continue;
-        mbar_wait(bars + w, par[w]);
-        par[w] ^= 1u;
-        __syncwarp();
-        tc_fence_after();
-        if (lane == 0) GJ_TRACE_PT(2, w * 100 + done_st[w] % S);
-        run_group(tbl + w * S + done_st[w] % S, unused);
-        mma_commit_elect(bars + NWG + w);
-        if (lane == 0) GJ_TRACE_PT(2, 1000 + w * 100 + done_st[w] % S);
-        ++done_st[w];
+    const int first = blockIdx.x * NWG + w;
+    const int njets = first < L.B ? (L.B - first + gridDim.x * NWG - 1) / (gridDim.x * NWG) : 0;
+    uint64_t* chunk = bars + NWG + w * GJ_MAX_CHUNKS;
+    uint32_t cpar = 0;                     // parity bit per chunk barrier
+    for (int tile = 0; tile < njets * tpj; ++tile) {
+      for (int st = 0; st < S; ++st) {
+        const MmaGroup* g = tbl + st;
+        const uint64_t ga = uni64(g->a), gb = uni64(g->b);
+        const uint32_t gd = uni(g->d), gi = uni(g->idesc), gas = uni(g->astep), gbs = uni(g->bstep);
+        const int gnk = (int)uni((uint32_t)g->nk);
+        for (int ck = 0; ck < gnk; ++ck) {
+          mbar_wait(chunk + ck, (cpar >> ck) & 1u);
+          __syncwarp();
+          tc_fence_after();
+          if (lane == 0 && ck == 0 && w == 0) GJ_TRACE_PT(2, st);
+          mma_bf16_ss_elect(gd, desc_advance(ga, gas, ck), desc_advance(gb, gbs, ck), gi, ck > 0 ? 1u : 0u);
+        }
+        cpar ^= (1u << gnk) - 1u;
+        mma_commit_elect(bars + w);
+        if (lane == 0 && w == 0) GJ_TRACE_PT(2, 1000 + st);
       }
-      any = false;
-#pragma unroll
-      for (int w = 0; w < NWG; ++w) any |= done_st[w] < total[w];
     }
+    if (lane == 0 && w == 0) GJ_TRACE_END(2);
   } else {
     // =================================== compute warpgroups ===================================
     const int wg = warp / (4 * NH), w8 = warp % (4 * NH), wq = w8 & 3, part = w8 >> 2;
     const int t = tid - wg * TGT, row = wq * 32 + lane;
     uint8_t* wgb = smem + T.wg_base + wg * T.wg_stride;
     float* wgf = reinterpret_cast<float*>(wgb + T.w_f32);
-    uint64_t* ready = bars + wg;
-    uint64_t* done = bars + NWG + wg;
-    const uint32_t tmem_row = tmem_base + (uint32_t)(wg * T.tmem_cols_per_wg) + ((uint32_t)(wq * 32) << 16);
+    uint64_t* done = bars + wg;
+    uint64_t* chunk = bars + NWG + wg * GJ_MAX_CHUNKS;
+    const uint32_t tmem_row0 = tmem_base + (uint32_t)(wg * T.tmem_cols_per_wg) + ((uint32_t)(wq * 32) << 16);
     uint32_t phase = 0;
     const int bar_id = 1 + wg;
     float* sm_h = wgf + L.o_h;
@@ -388,30 +451,39 @@ edge_fwd_tc_kernel(const MPLayout L, const TCPlan T, const float* __restrict__ h
           for (int it = 0; it < nit; ++it) {
             const int il = it * 4 + wq;
             const bool valid = il < ni && lane < nj;
-            tc_layer0(L, sm_h, sm_hj, sm_P, sm_Q, wd, wgb + T.w_act[0], il, lane, row, part, NH);
-            fence_proxy_async();
-            tc_fence_before();
-            warp_arrive(ready, lane);
+            // first layer: 16-column chunks, published one by one (each is one k-step of layer 1)
+            {
+              const float dij = tc_pair_distance(L, sm_h + il * L.Hs, sm_hj + lane * L.Hs);
+              const int nch0 = L.E0p >> 4;
+              for (int ch = part; ch < nch0; ch += NH) {
+                tc_layer0_chunk(L, sm_P + il * L.E0s, sm_Q + lane * L.E0s, wd, wgb + T.w_act[0] + row * 16, ch << 4, dij, a_le_1);
+                fence_proxy_async();
+                warp_arrive(chunk + ch, lane);
+              }
+            }
             if (t == 0) GJ_TRACE_PT(wg, 10);
             for (int l = 1; l < Le; ++l) {
-              mbar_wait(done, phase); phase ^= 1u;
+              group_wait(done, phase, w8 == 0, 8 + wg, TGT); phase ^= 1u;
               tc_fence_after();
               if (t == 0) GJ_TRACE_PT(wg, 20 + l);
               const bool last = (l == Le - 1);
               const float* bias = smf + L.o_bE[l];
               uint8_t* al = wgb + T.w_act[l] + row * 16;
               const int nch = L.Ep[l] >> 4;
+              const uint32_t tmem_row = tmem_row0 + (uint32_t)((l & 1) * T.acc_cols);
               auto process = [&](float (&v)[16], int c0) {
                 float bq[16];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(bq + 4 * q) = *reinterpret_cast<const float4*>(bias + c0 + 4 * q);
-#pragma unroll
-                for (int q = 0; q < 16; ++q) v[q] = gj_leaky2(v[q] + bq[q], L.alpha, a_le_1);
+                bias_leaky16(v, bq, L.alpha, a_le_1);
                 if (!last) {
                   uint4 p0 = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
                   uint4 p1 = make_uint4(pack_bf16(v[8], v[9]), pack_bf16(v[10], v[11]), pack_bf16(v[12], v[13]), pack_bf16(v[14], v[15]));
                   *reinterpret_cast<uint4*>(al + (c0 >> 3) * 2048) = p0;
                   *reinterpret_cast<uint4*>(al + ((c0 >> 3) + 1) * 2048) = p1;
+                  fence_proxy_async();
+                  tc_fence_before();
+                  warp_arrive(chunk + (c0 >> 4), lane);      // this chunk is one k-step of the next layer
                 } else {
                   // e_i += sum_j a_last (padded rows masked AFTER the activation: leaky(b) != 0); transpose-reduce over
                   // the 32 j's of the warp: lane L ends up with channel c0 + (L >> 1)
@@ -422,15 +494,8 @@ edge_fwd_tc_kernel(const MPLayout L, const TCPlan T, const float* __restrict__ h
                 }
               };
               for_chunks(tmem_row, nch, part, NH, process);
-              if (!last) {
-                fence_proxy_async();
-                tc_fence_before();
-                warp_arrive(ready, lane);
-                if (t == 0) GJ_TRACE_PT(wg, 30 + l);
-              } else {
-                tc_fence_before();
-                if (t == 0) GJ_TRACE_PT(wg, 60);
-              }
+              if (last) { tc_fence_before(); if (t == 0) GJ_TRACE_PT(wg, 60); }
+              else if (t == 0) GJ_TRACE_PT(wg, 30 + l);
             }
           }
         }
@@ -441,10 +506,11 @@ edge_fwd_tc_kernel(const MPLayout L, const TCPlan T, const float* __restrict__ h
         }
       }
     }
+    if (t == 0) GJ_TRACE_END(wg);
   }
   tc_fence_before();
   __syncthreads();
-  if (is_issuer) tmem_dealloc(tmem_base, (uint32_t)T.tmem_cols_total);
+  if (warp == NWG * 4 * NH) tmem_dealloc(tmem_base, (uint32_t)T.tmem_cols_total);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -587,7 +653,7 @@ edge_bwd_tc_kernel(const MPLayout L, const BwdPlan T, const float* __restrict__ 
   stage_edge_weights_bf16(L, T.o_wT, params, smem, tid, NT);
   for (int idx = tid; idx < 16 * 128; idx += NT) reinterpret_cast<__nv_bfloat16*>(smem + T.o_ones)[idx] = __float2bfloat16_rn(1.f);
   if (tid == 0) {
-    for (int w = 0; w < NWG; ++w) { mbar_init(bars + w, 4); mbar_init(bars + NWG + w, 1); }
+    for (int w = 0; w < NWG; ++w) { mbar_init(bars + w, 4); mbar_init(bars + NWG + w, 1); mbar_init(bars + 2 * NWG + w, 1); }
     fence_barrier_init();
   }
   if (is_issuer) tmem_alloc(tmem_slot, (uint32_t)T.tmem_cols);
@@ -597,6 +663,7 @@ edge_bwd_tc_kernel(const MPLayout L, const BwdPlan T, const float* __restrict__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int jets_total = L.B;
+  int tr_i = 0;      // trace cursor (register; written back once at the end)
 
   if (is_issuer) {
     // =================================== MMA issuer ===================================
@@ -629,17 +696,30 @@ edge_bwd_tc_kernel(const MPLayout L, const BwdPlan T, const float* __restrict__ 
             if (s2 < Le - 1) {
               const int l = s2 + 1;
               const uint32_t ain = l == 1 ? a0 : comb + (T.coff[l - 1] >> 3) * 2048;
-              tw[ng++] = grp_fwd(acc, ain, smem_u32(smem + T.o_wT[l]), L.Ep[l], L.Kp[l]);
+              tw[ng] = grp_fwd(acc, ain, smem_u32(smem + T.o_wT[l]), L.Ep[l], L.Kp[l]);
+              tw[ng++].commit = 1;
             } else {
               const int l = Le - 1 - (s2 - (Le - 1));
               const uint32_t dz = comb + (T.coff[l] >> 3) * 2048;
               const uint32_t ain = l == 1 ? a0 : comb + (T.coff[l - 1] >> 3) * 2048;
-              tw[ng++] = T.wg_orient[l] == 0 ? grp_wgrad(tmem_base + T.t_wg[l], dz, ain, T.wg_M[l], T.wg_N[l], l)
-                                             : grp_wgrad(tmem_base + T.t_wg[l], ain, dz, T.wg_M[l], T.wg_N[l], l);
-              tw[ng++] = grp_dgrad(acc, dz, smem_u32(smem + T.o_wT[l]), L.Kp[l], L.Ep[l]);
-              if (l == 1)
+              const MmaGroup wgrad = T.wg_orient[l] == 0 ? grp_wgrad(tmem_base + T.t_wg[l], dz, ain, T.wg_M[l], T.wg_N[l], l)
+                                                         : grp_wgrad(tmem_base + T.t_wg[l], ain, dz, T.wg_M[l], T.wg_N[l], l);
+              MmaGroup dgrad = grp_dgrad(acc, dz, smem_u32(smem + T.o_wT[l]), L.Kp[l], L.Ep[l]);
+              if (l > 1) {
+                // the epilogue overwrites a_{l-1} in place, which the weight gradient reads: both must complete first
+                tw[ng++] = wgrad;
+                dgrad.commit = 1;
+                tw[ng++] = dgrad;
+              } else {
+                // nothing the last epilogue writes is read by an MMA: release the warpgroup after dgrad and let the
+                // weight-gradient and bias column-sum batches run behind its epilogue (done2 gates the next tile)
+                dgrad.commit = 1;
+                tw[ng++] = dgrad;
+                tw[ng++] = wgrad;
                 for (int b = 0; b < T.nbias; ++b)
                   tw[ng++] = grp_colsum(tmem_base + T.t_bias[b], comb + b * 16 * 2048, smem_u32(smem + T.o_ones), T.bias_M[b], 16 + b);
+                tw[ng - 1].commit = 2;
+              }
             }
           }
           gbeg[S] = ng;
@@ -659,8 +739,11 @@ edge_bwd_tc_kernel(const MPLayout L, const BwdPlan T, const float* __restrict__ 
           if (lane == 0) GJ_TRACE_PT(2, w * 100 + s2);
           const MmaGroup* tw = tbl + w * T.groups_per_wg;
           const int g0 = (int)uni((uint32_t)gbeg[s2]), g1 = (int)uni((uint32_t)gbeg[s2 + 1]);
-          for (int g = g0; g < g1; ++g) run_group(tw + g, inited);
-          mma_commit_elect(bars + NWG + w);
+          for (int g = g0; g < g1; ++g) {
+            const int commit = run_group(tw + g, inited);
+            if (commit == 1) mma_commit_elect(bars + NWG + w);
+            else if (commit == 2) mma_commit_elect(bars + 2 * NWG + w);
+          }
           if (lane == 0) GJ_TRACE_PT(2, 1000 + w * 100 + s2);
           ++done_st[w];
         }
@@ -668,6 +751,7 @@ edge_bwd_tc_kernel(const MPLayout L, const BwdPlan T, const float* __restrict__ 
 #pragma unroll
         for (int w = 0; w < NWG; ++w) any |= done_st[w] < total[w];
       }
+      if (lane == 0) GJ_TRACE_END(2);
     }
     __syncwarp();
   } else {
@@ -679,8 +763,10 @@ edge_bwd_tc_kernel(const MPLayout L, const BwdPlan T, const float* __restrict__ 
     uint8_t* COMB = wgb + T.w_comb;
     uint64_t* ready = bars + wg;
     uint64_t* done = bars + NWG + wg;
+    uint64_t* done2 = bars + 2 * NWG + wg;     // the previous tile's background weight-gradient batch has completed
     const uint32_t tmem_row = tmem_base + (uint32_t)(wg * T.nacc) + ((uint32_t)(wq * 32) << 16);
-    uint32_t phase = 0;
+    uint32_t phase = 0, phase2 = 0;
+    bool pending2 = false;
     const int bar_id = 1 + wg;
     float* sm_h = wgf + L.o_h;
     float* sm_hj = wgf + L.o_hj;
@@ -727,6 +813,8 @@ edge_bwd_tc_kernel(const MPLayout L, const BwdPlan T, const float* __restrict__ 
           for (int it = 0; it < nit; ++it) {
             const int il = it * 4 + wq;
             const bool valid = il < ni && lane < nj;
+            if (pending2) { group_wait(done2, phase2, wq == 0, 8 + wg, 128); phase2 ^= 1u; }     // A0 / dz buffers are free again
+            pending2 = true;
             const float dij = tc_layer0(L, sm_h, sm_hj, sm_P, sm_Q, wd, A0, il, lane, t);
             fence_proxy_async();
             tc_fence_before();
@@ -734,7 +822,7 @@ edge_bwd_tc_kernel(const MPLayout L, const BwdPlan T, const float* __restrict__ 
             if (t == 0) GJ_TRACE_PT(wg, 10);
             // ---- forward stages ----
             for (int l = 1; l < Le; ++l) {
-              mbar_wait(done, phase); phase ^= 1u;
+              group_wait(done, phase, wq == 0, 8 + wg, 128); phase ^= 1u;
               tc_fence_after();
               if (t == 0) GJ_TRACE_PT(wg, 20 + l);
               const bool last = (l == Le - 1);
@@ -746,8 +834,7 @@ edge_bwd_tc_kernel(const MPLayout L, const BwdPlan T, const float* __restrict__ 
 #pragma unroll
                 for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(bq + 4 * q) = *reinterpret_cast<const float4*>(bias + c0 + 4 * q);
                 if (!last) {
-#pragma unroll
-                  for (int q = 0; q < 16; ++q) v[q] = gj_leaky2(v[q] + bq[q], L.alpha, a_le_1);
+                  bias_leaky16(v, bq, L.alpha, a_le_1);
                 } else {
                   // dz_last = de_i * leaky'(z_last), zero on padded rows (this masks everything downstream)
                   const float* dei = sm_de + il * L.ELs + c0;
@@ -782,7 +869,7 @@ edge_bwd_tc_kernel(const MPLayout L, const BwdPlan T, const float* __restrict__ 
             }
             // ---- backward stages ----
             for (int l = Le - 1; l >= 1; --l) {
-              mbar_wait(done, phase); phase ^= 1u;
+              group_wait(done, phase, wq == 0, 8 + wg, 128); phase ^= 1u;
               tc_fence_after();
               if (t == 0) GJ_TRACE_PT(wg, 40 + l);
               if (l > 1) {
@@ -889,6 +976,8 @@ edge_bwd_tc_kernel(const MPLayout L, const BwdPlan T, const float* __restrict__ 
         }
       }
     }
+    if (t == 0) GJ_TRACE_END(wg);
+    if (pending2) { mbar_wait(done2, phase2); phase2 ^= 1u; }       // all of this warpgroup's MMAs have completed
     // d(wd)[c] = sum over this warpgroup's rows: lanes by shuffles, warps through shared memory (fixed order)
     named_bar_sync(bar_id, 128);
     float* red = sm_dQ;    // [4][E0P]
@@ -1016,12 +1105,17 @@ int gj_edge_grid(int);
 int gj_edge_bwd_simt(MPLayout, const float*, const float*, const float*, const float*, float*, float*, float*, float*,
                      cudaStream_t);
 
+int gj_edge_fwd_simt(MPLayout, const float*, const float*, const float*, float*, cudaStream_t);
+
 int gj_edge_fwd_tc(MPLayout L, const float* h, const float* pq, const float* params, float* e_out, cudaStream_t stream) {
+  if (L.alpha > 1.f) return gj_edge_fwd_simt(L, h, pq, params, e_out, stream);   // max(z, alpha z) form needs alpha <= 1
   for (int l = 1; l < L.Le; ++l)
     if (L.Ep[l] > 256 || L.Kp[l] > 256) { gj_set_error("gj_mp_step_fwd(bf16): edge widths above 256 unsupported"); return GJ_ERR_INVALID; }
   TCPlan T;
   constexpr int NWG = 2;
   plan_tc_fwd(&L, &T, NWG);
+  for (int l = 0; l < L.Le; ++l)
+    if (L.Ep[l] > 16 * GJ_MAX_CHUNKS) { gj_set_error("gj_mp_step_fwd(bf16): edge widths above 256 unsupported"); return GJ_ERR_INVALID; }
   if (T.smem_bytes > 227 * 1024 || T.tmem_cols_total > 512) {
     gj_set_error("gj_mp_step_fwd(bf16): needs %d B shared memory / %d TMEM columns (limits 232448 / 512)", T.smem_bytes, T.tmem_cols_total);
     return GJ_ERR_SMEM;
@@ -1036,7 +1130,7 @@ int gj_edge_fwd_tc(MPLayout L, const float* h, const float* pq, const float* par
   if (ce != cudaSuccess) { gj_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   int sms = gj_num_sms();
   int grid = (L.B + NWG - 1) / NWG; if (grid > sms) grid = sms;
-  kern<<<grid, NWG * 128 * NH + 32, T.smem_bytes, stream>>>(L, T, h, pq, params, e_out);
+  kern<<<grid, NWG * 128 * NH + NWG * 32, T.smem_bytes, stream>>>(L, T, h, pq, params, e_out);
   ce = cudaGetLastError();
   if (ce != cudaSuccess) { gj_set_error("edge_fwd_tc launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   return GJ_OK;
@@ -1073,7 +1167,7 @@ int gj_edge_bwd_tc(MPLayout L, const float* h, const float* pq, const float* par
                    float* dparams, float* part, cudaStream_t stream) {
   BwdPlan T;
   MPLayout Lt = L;
-  if (plan_tc_bwd(&Lt, &T, 2)) {
+  if (L.alpha > 1.f || plan_tc_bwd(&Lt, &T, 2)) {
     // widths the tensor-core backward does not cover (first layer wider than 64, layers wider than 128 on both sides,
     // more than 512 combined dz columns): the fp32 kernel computes the gradient instead
     return gj_edge_bwd_simt(L, h, pq, params, de, dpq, dh, dparams, part, stream);
