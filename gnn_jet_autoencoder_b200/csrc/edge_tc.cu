@@ -634,16 +634,19 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4& u, float* f) {
   for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
 }
 
-template <int NWG, int E0P>
-__global__ void __launch_bounds__(NWG * 128 + 32, 1)
+template <int NWG, int NH, int E0P>
+__global__ void __launch_bounds__(NWG * 128 * NH + 32, 1)
 edge_bwd_tc_kernel(const MPLayout L, const BwdPlan T, const float* __restrict__ h, const float* __restrict__ pq,
                    const float* __restrict__ params, const float* __restrict__ de, float* __restrict__ dpq,
                    float* __restrict__ dh, float* __restrict__ part) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  constexpr int NT = NWG * 128 + 32;
+  constexpr int TGT = 128 * NH;                    // threads per tile group (NH warps per TMEM lane quadrant)
+  constexpr int NT = NWG * TGT + 32;
+  constexpr int NCH0 = E0P / 16;                   // 16-column chunks of the first layer
+  constexpr int OWN = ((NCH0 + NH - 1) / NH) * 16; // first-layer channels a thread owns (chunks part, part + NH, ...)
   const int tid = threadIdx.x;
   const int warp = (int)uni((uint32_t)(tid >> 5)), lane = tid & 31;     // provably warp-uniform
-  const bool is_issuer = warp == NWG * 4;
+  const bool is_issuer = warp == NWG * 4 * NH;
   float* smf = reinterpret_cast<float*>(smem + T.o_shared_f32);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + T.o_bar);   // ready[wg] = bars[wg], done[wg] = bars[NWG + wg]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + T.o_tmem_slot);
@@ -653,7 +656,7 @@ edge_bwd_tc_kernel(const MPLayout L, const BwdPlan T, const float* __restrict__ 
   stage_edge_weights_bf16(L, T.o_wT, params, smem, tid, NT);
   for (int idx = tid; idx < 16 * 128; idx += NT) reinterpret_cast<__nv_bfloat16*>(smem + T.o_ones)[idx] = __float2bfloat16_rn(1.f);
   if (tid == 0) {
-    for (int w = 0; w < NWG; ++w) { mbar_init(bars + w, 4); mbar_init(bars + NWG + w, 1); mbar_init(bars + 2 * NWG + w, 1); }
+    for (int w = 0; w < NWG; ++w) { mbar_init(bars + w, 4 * NH); mbar_init(bars + NWG + w, 1); mbar_init(bars + 2 * NWG + w, 1); }
     fence_barrier_init();
   }
   if (is_issuer) tmem_alloc(tmem_slot, (uint32_t)T.tmem_cols);
@@ -756,7 +759,8 @@ edge_bwd_tc_kernel(const MPLayout L, const BwdPlan T, const float* __restrict__ 
     __syncwarp();
   } else {
     // =================================== compute warpgroups ===================================
-    const int wg = warp >> 2, t = tid & 127, wq = warp & 3;     // warp-uniform
+    const int wg = warp / (4 * NH), w8 = warp % (4 * NH), wq = w8 & 3, part = w8 >> 2;     // warp-uniform
+    const int t = tid - wg * TGT, row = wq * 32 + lane;
     uint8_t* wgb = smem + T.wg_base + wg * T.wg_stride;
     float* wgf = reinterpret_cast<float*>(wgb + T.w_f32);
     uint8_t* A0 = wgb + T.w_a0;
@@ -780,9 +784,9 @@ edge_bwd_tc_kernel(const MPLayout L, const BwdPlan T, const float* __restrict__ 
     const float* wd = smf + L.o_wd;
     const int H = L.H, W2 = 2 * L.E0p;
     const bool a_le_1 = L.alpha <= 1.f;
-    float dwd[E0P];
+    float dwd[OWN];
 #pragma unroll
-    for (int c = 0; c < E0P; ++c) dwd[c] = 0.f;
+    for (int c = 0; c < OWN; ++c) dwd[c] = 0.f;
 
     for (int jet = blockIdx.x * NWG + wg; jet < L.B; jet += gridDim.x * NWG) {
       const float* hjet = h + (size_t)jet * L.N * L.ld;
@@ -791,43 +795,43 @@ edge_bwd_tc_kernel(const MPLayout L, const BwdPlan T, const float* __restrict__ 
       float* dhjet = dh + (size_t)jet * L.N * L.ld;
       for (int i0 = 0; i0 < L.N; i0 += GJ_IB) {
         const int ni = min(GJ_IB, L.N - i0);
-        named_bar_sync(bar_id, 128);
-        wg_load_block(L, hjet, pqjet, 0, i0, sm_h, sm_P, t);
+        named_bar_sync(bar_id, TGT);
+        wg_load_block(L, hjet, pqjet, 0, i0, sm_h, sm_P, t, TGT);
 #pragma unroll 4
-        for (int idx = t; idx < GJ_IB * L.ELs; idx += 128) {
+        for (int idx = t; idx < GJ_IB * L.ELs; idx += TGT) {
           int n = idx / L.ELs, c = idx - n * L.ELs;
           sm_de[idx] = (n < ni && c < L.EL) ? __ldg(de + ((size_t)jet * L.N + i0 + n) * L.EL + c) : 0.f;
         }
-        for (int idx = t; idx < GJ_IB * L.E0s; idx += 128) sm_dP[idx] = 0.f;
-        for (int idx = t; idx < GJ_IB * L.Hs; idx += 128) sm_dh[idx] = 0.f;
+        for (int idx = t; idx < GJ_IB * L.E0s; idx += TGT) sm_dP[idx] = 0.f;
+        for (int idx = t; idx < GJ_IB * L.Hs; idx += TGT) sm_dh[idx] = 0.f;
         for (int j0 = 0; j0 < L.N; j0 += 32) {
           const int nj = min(32, L.N - j0);
-          named_bar_sync(bar_id, 128);
-          wg_load_block(L, hjet, pqjet, 1, j0, sm_hj, sm_Q, t);
-          for (int idx = t; idx < GJ_IB * L.Gs; idx += 128) sm_G[idx] = 0.f;
-          float dq[E0P];
+          named_bar_sync(bar_id, TGT);
+          wg_load_block(L, hjet, pqjet, 1, j0, sm_hj, sm_Q, t, TGT);
+          for (int idx = t; idx < GJ_IB * L.Gs; idx += TGT) sm_G[idx] = 0.f;
+          float dq[OWN];
 #pragma unroll
-          for (int c = 0; c < E0P; ++c) dq[c] = 0.f;
-          named_bar_sync(bar_id, 128);
+          for (int c = 0; c < OWN; ++c) dq[c] = 0.f;
+          named_bar_sync(bar_id, TGT);
           const int nit = (ni + 3) / 4;
           for (int it = 0; it < nit; ++it) {
             const int il = it * 4 + wq;
             const bool valid = il < ni && lane < nj;
-            if (pending2) { group_wait(done2, phase2, wq == 0, 8 + wg, 128); phase2 ^= 1u; }     // A0 / dz buffers are free again
+            if (pending2) { group_wait(done2, phase2, w8 == 0, 8 + wg, TGT); phase2 ^= 1u; }     // A0 / dz buffers are free again
             pending2 = true;
-            const float dij = tc_layer0(L, sm_h, sm_hj, sm_P, sm_Q, wd, A0, il, lane, t);
+            const float dij = tc_layer0(L, sm_h, sm_hj, sm_P, sm_Q, wd, A0, il, lane, row, part, NH);
             fence_proxy_async();
             tc_fence_before();
             warp_arrive(ready, lane);
             if (t == 0) GJ_TRACE_PT(wg, 10);
             // ---- forward stages ----
             for (int l = 1; l < Le; ++l) {
-              group_wait(done, phase, wq == 0, 8 + wg, 128); phase ^= 1u;
+              group_wait(done, phase, w8 == 0, 8 + wg, TGT); phase ^= 1u;
               tc_fence_after();
               if (t == 0) GJ_TRACE_PT(wg, 20 + l);
               const bool last = (l == Le - 1);
               const float* bias = smf + L.o_bE[l];
-              uint8_t* out = COMB + (T.coff[l] >> 3) * 2048 + t * 16;
+              uint8_t* out = COMB + (T.coff[l] >> 3) * 2048 + row * 16;
               const int nch = L.Ep[l] >> 4;
               auto process = [&](float (&v)[16], int c0) {
                 float bq[16];
@@ -849,19 +853,7 @@ edge_bwd_tc_kernel(const MPLayout L, const BwdPlan T, const float* __restrict__ 
                 *reinterpret_cast<uint4*>(out + (c0 >> 3) * 2048) = p0;
                 *reinterpret_cast<uint4*>(out + ((c0 >> 3) + 1) * 2048) = p1;
               };
-              // two register sets: the next chunk's TMEM load flies while the current chunk is processed
-              float va[16], vb[16];
-              tmem_ld16_issue(tmem_row, va);
-              for (int ch = 0; ch < nch; ch += 2) {
-                tmem_wait16(va);
-                if (ch + 1 < nch) tmem_ld16_issue(tmem_row + (uint32_t)((ch + 1) << 4), vb);
-                process(va, ch << 4);
-                if (ch + 1 < nch) {
-                  tmem_wait16(vb);
-                  if (ch + 2 < nch) tmem_ld16_issue(tmem_row + (uint32_t)((ch + 2) << 4), va);
-                  process(vb, (ch + 1) << 4);
-                }
-              }
+              for_chunks(tmem_row, nch, part, NH, process);
               fence_proxy_async();
               tc_fence_before();
               warp_arrive(ready, lane);
@@ -869,12 +861,12 @@ edge_bwd_tc_kernel(const MPLayout L, const BwdPlan T, const float* __restrict__ 
             }
             // ---- backward stages ----
             for (int l = Le - 1; l >= 1; --l) {
-              group_wait(done, phase, wq == 0, 8 + wg, 128); phase ^= 1u;
+              group_wait(done, phase, w8 == 0, 8 + wg, TGT); phase ^= 1u;
               tc_fence_after();
               if (t == 0) GJ_TRACE_PT(wg, 40 + l);
               if (l > 1) {
                 // dz_{l-1} = da_{l-1} * leaky'(a_{l-1}), in place over a_{l-1}
-                uint8_t* buf = COMB + (T.coff[l - 1] >> 3) * 2048 + t * 16;
+                uint8_t* buf = COMB + (T.coff[l - 1] >> 3) * 2048 + row * 16;
                 const int nch = L.Kp[l] >> 4;
                 auto process = [&](float (&v)[16], int c0) {
                   float a[16];
@@ -887,18 +879,7 @@ edge_bwd_tc_kernel(const MPLayout L, const BwdPlan T, const float* __restrict__ 
                   *reinterpret_cast<uint4*>(buf + (c0 >> 3) * 2048) = p0;
                   *reinterpret_cast<uint4*>(buf + ((c0 >> 3) + 1) * 2048) = p1;
                 };
-                float va[16], vb[16];
-                tmem_ld16_issue(tmem_row, va);
-                for (int ch = 0; ch < nch; ch += 2) {
-                  tmem_wait16(va);
-                  if (ch + 1 < nch) tmem_ld16_issue(tmem_row + (uint32_t)((ch + 1) << 4), vb);
-                  process(va, ch << 4);
-                  if (ch + 1 < nch) {
-                    tmem_wait16(vb);
-                    if (ch + 2 < nch) tmem_ld16_issue(tmem_row + (uint32_t)((ch + 2) << 4), va);
-                    process(vb, (ch + 1) << 4);
-                  }
-                }
+                for_chunks(tmem_row, nch, part, NH, process);
                 fence_proxy_async();
                 tc_fence_before();
                 warp_arrive(ready, lane);
@@ -907,48 +888,58 @@ edge_bwd_tc_kernel(const MPLayout L, const BwdPlan T, const float* __restrict__ 
                 // dz_0 = da_0 * leaky'(a_0), consumed in fp32: G_ij, dQ_j, dP_i, d(wd)
                 float g = 0.f;
 #pragma unroll
-                for (int c0 = 0; c0 < E0P; c0 += 16) {
-                  float v[16], a[16];
-                  tmem_ld16(tmem_row + (uint32_t)c0, v);
-                  unpack_bf16x8(*reinterpret_cast<const uint4*>(A0 + (c0 >> 3) * 2048 + t * 16), a);
-                  unpack_bf16x8(*reinterpret_cast<const uint4*>(A0 + ((c0 >> 3) + 1) * 2048 + t * 16), a + 8);
+                for (int kk = 0; kk < OWN / 16; ++kk) {
+                  const int c0 = 16 * (part + NH * kk);            // this thread's kk-th chunk
+                  if (c0 < E0P) {
+                    float v[16], a[16];
+                    tmem_ld16(tmem_row + (uint32_t)c0, v);
+                    unpack_bf16x8(*reinterpret_cast<const uint4*>(A0 + (c0 >> 3) * 2048 + row * 16), a);
+                    unpack_bf16x8(*reinterpret_cast<const uint4*>(A0 + ((c0 >> 3) + 1) * 2048 + row * 16), a + 8);
 #pragma unroll
-                  for (int q = 0; q < 16; ++q) {
-                    v[q] *= (a[q] > 0.f ? 1.f : L.alpha);
-                    g = fmaf(v[q], wd[c0 + q], g);
-                    dq[c0 + q] += v[q];
-                    dwd[c0 + q] = fmaf(v[q], dij, dwd[c0 + q]);
+                    for (int q = 0; q < 16; ++q) {
+                      v[q] *= (a[q] > 0.f ? 1.f : L.alpha);
+                      g = fmaf(v[q], wd[c0 + q], g);
+                      dq[16 * kk + q] += v[q];
+                      dwd[16 * kk + q] = fmaf(v[q], dij, dwd[16 * kk + q]);
+                    }
+                    const float s = warp_transpose_sum16(v, lane);
+                    if ((lane & 1) == 0) sm_dP[il * L.E0s + c0 + (lane >> 1)] += s;
                   }
-                  const float s = warp_transpose_sum16(v, lane);
-                  if ((lane & 1) == 0) sm_dP[il * L.E0s + c0 + (lane >> 1)] += s;
                 }
-                sm_G[il * L.Gs + lane] = g;
+                if (NH == 1) sm_G[il * L.Gs + lane] = g;
+                else atomicAdd(sm_G + il * L.Gs + lane, g);   // two addends onto a zeroed cell: order-independent, deterministic
                 tc_fence_before();
                 if (t == 0) GJ_TRACE_PT(wg, 60);
               }
             }
           }
           // ---- (i block, j block) epilogue ----
-          named_bar_sync(bar_id, 128);            // every warp is done reading Q_j: its storage now receives dQ_j
+          named_bar_sync(bar_id, TGT);            // every warp is done reading Q_j: its storage now receives dQ_j
           for (int w = 0; w < 4; ++w) {           // the four warps hold different i's of the same j: fixed order 0..3
             if (wq == w) {
 #pragma unroll
-              for (int c = 0; c < E0P; c += 4) {
-                float4* p = reinterpret_cast<float4*>(sm_dQ + lane * L.E0s + c);
-                float4 v = w == 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : *p;
-                v.x += dq[c]; v.y += dq[c + 1]; v.z += dq[c + 2]; v.w += dq[c + 3];
-                *p = v;
+              for (int kk = 0; kk < OWN / 16; ++kk) {
+                const int c0 = 16 * (part + NH * kk);
+                if (c0 < E0P) {
+#pragma unroll
+                  for (int c = 0; c < 16; c += 4) {
+                    float4* p = reinterpret_cast<float4*>(sm_dQ + lane * L.E0s + c0 + c);
+                    float4 v = w == 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : *p;
+                    v.x += dq[16 * kk + c]; v.y += dq[16 * kk + c + 1]; v.z += dq[16 * kk + c + 2]; v.w += dq[16 * kk + c + 3];
+                    *p = v;
+                  }
+                }
               }
             }
-            named_bar_sync(bar_id, 128);
+            named_bar_sync(bar_id, TGT);
           }
-          for (int idx = t; idx < nj * L.E0p; idx += 128) {
+          for (int idx = t; idx < nj * L.E0p; idx += TGT) {
             int n = idx / L.E0p, c = idx - n * L.E0p;
             float* p = dpqjet + (size_t)(j0 + n) * W2 + L.E0p + c;
             float v = sm_dQ[n * L.E0s + c];
             *p = (i0 == 0) ? v : (*p + v);
           }
-          for (int idx = t; idx < nj * H; idx += 128) {
+          for (int idx = t; idx < nj * H; idx += TGT) {
             int n = idx / H, k = idx - n * H;
             const float sgn = (L.mink && k > 0) ? -2.f : 2.f;
             const float hjk = sm_hj[n * L.Hs + k];
@@ -956,7 +947,7 @@ edge_bwd_tc_kernel(const MPLayout L, const BwdPlan T, const float* __restrict__ 
             for (int i = 0; i < ni; ++i) acc = fmaf(sm_G[i * L.Gs + n], hjk - sm_h[i * L.Hs + k] + GJ_EPS, acc);
             if (k < L.cols) dhjet[(size_t)(j0 + n) * L.ld + k] += sgn * acc;
           }
-          for (int idx = t; idx < ni * H; idx += 128) {
+          for (int idx = t; idx < ni * H; idx += TGT) {
             int n = idx / H, k = idx - n * H;
             const float sgn = (L.mink && k > 0) ? -2.f : 2.f;
             const float hik = sm_h[n * L.Hs + k];
@@ -965,12 +956,12 @@ edge_bwd_tc_kernel(const MPLayout L, const BwdPlan T, const float* __restrict__ 
             sm_dh[n * L.Hs + k] -= sgn * acc;
           }
         }
-        named_bar_sync(bar_id, 128);
-        for (int idx = t; idx < ni * L.E0p; idx += 128) {
+        named_bar_sync(bar_id, TGT);
+        for (int idx = t; idx < ni * L.E0p; idx += TGT) {
           int n = idx / L.E0p, c = idx - n * L.E0p;
           dpqjet[(size_t)(i0 + n) * W2 + c] = sm_dP[n * L.E0s + c];
         }
-        for (int idx = t; idx < ni * L.cols; idx += 128) {
+        for (int idx = t; idx < ni * L.cols; idx += TGT) {
           int n = idx / L.cols, k = idx - n * L.cols;
           dhjet[(size_t)(i0 + n) * L.ld + k] += sm_dh[n * L.Hs + k];
         }
@@ -979,15 +970,19 @@ edge_bwd_tc_kernel(const MPLayout L, const BwdPlan T, const float* __restrict__ 
     if (t == 0) GJ_TRACE_END(wg);
     if (pending2) { mbar_wait(done2, phase2); phase2 ^= 1u; }       // all of this warpgroup's MMAs have completed
     // d(wd)[c] = sum over this warpgroup's rows: lanes by shuffles, warps through shared memory (fixed order)
-    named_bar_sync(bar_id, 128);
+    named_bar_sync(bar_id, TGT);
     float* red = sm_dQ;    // [4][E0P]
 #pragma unroll
-    for (int c = 0; c < E0P; ++c) {
-      const float s = gj_warp_sum(dwd[c]);
-      if (lane == 0) red[wq * E0P + c] = s;
+    for (int kk = 0; kk < OWN / 16; ++kk) {
+      const int c0 = 16 * (part + NH * kk);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const float s = gj_warp_sum(dwd[16 * kk + q]);
+        if (lane == 0 && c0 < E0P) red[wq * E0P + c0 + q] = s;
+      }
     }
-    named_bar_sync(bar_id, 128);
-    for (int c = t; c < E0P; c += 128) smf[L.o_dpar + wg * L.E0p + c] = (red[c] + red[E0P + c]) + (red[2 * E0P + c] + red[3 * E0P + c]);
+    named_bar_sync(bar_id, TGT);
+    for (int c = t; c < E0P; c += TGT) smf[L.o_dpar + wg * L.E0p + c] = (red[c] + red[E0P + c]) + (red[2 * E0P + c] + red[3 * E0P + c]);
   }
 
   // =================================== gradient read-out ===================================
@@ -996,10 +991,10 @@ edge_bwd_tc_kernel(const MPLayout L, const BwdPlan T, const float* __restrict__ 
   tc_fence_after();
   float* out = part + (size_t)blockIdx.x * L.pV[0];
   if (!is_issuer) {
-    const int wq = warp & 3, wgi = warp >> 2;
+    const int wq = warp & 3, wgi = warp >> 2;      // wgi: 0 .. NWG*NH-1, every one of them covers the 128 lanes
     const bool wrote = (blockIdx.x * NWG) < jets_total;     // a CTA without jets never initialised its accumulators
     // wd column
-    for (int c = tid; c < L.E[0]; c += NWG * 128) {
+    for (int c = tid; c < L.E[0]; c += NWG * TGT) {
       float s = 0.f;
       for (int w = 0; w < NWG; ++w) s += smf[L.o_dpar + w * L.E0p + c];
       out[L.pW[0] + c * L.K[0] + 2 * L.H] = wrote ? s : 0.f;
@@ -1009,7 +1004,7 @@ edge_bwd_tc_kernel(const MPLayout L, const BwdPlan T, const float* __restrict__ 
       const int M = T.wg_M[l], N = T.wg_N[l];
       const int m = M == 128 ? wq * 32 + lane : (lane < 16 ? wq * 16 + lane : -1);
       const int nchunks = N / 16;
-      for (int ch = wgi; ch < nchunks; ch += NWG) {       // warp-uniform: every lane of the warp issues the load
+      for (int ch = wgi; ch < nchunks; ch += NWG * NH) {       // warp-uniform: every lane of the warp issues the load
         float v[16];
         tmem_ld16(tmem_base + (uint32_t)(T.t_wg[l] + ch * 16) + ((uint32_t)(wq * 32) << 16), v);
         if (m < 0) continue;
@@ -1154,10 +1149,14 @@ template <int E0P>
 static int launch_tc_bwd(const MPLayout& L, const BwdPlan& T, const float* h, const float* pq, const float* params,
                          const float* de, float* dpq, float* dh, float* part, int grid, cudaStream_t stream) {
   constexpr int NWG = 2;
-  auto kern = edge_bwd_tc_kernel<NWG, E0P>;
+  // NH = 2 (256 threads per tile) is measured slower for the backward kernel: 17 warps cap the kernel at 96 registers and
+  // the first-layer adjoint spills; it stays selectable for experiments
+  static const int nh_env = getenv("GJ_TC_NH_BWD") ? atoi(getenv("GJ_TC_NH_BWD")) : 1;
+  const int NH = nh_env == 2 ? 2 : 1;
+  auto kern = NH == 1 ? edge_bwd_tc_kernel<NWG, 1, E0P> : edge_bwd_tc_kernel<NWG, 2, E0P>;
   cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T.smem_bytes);
   if (ce != cudaSuccess) { gj_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
-  kern<<<grid, NWG * 128 + 32, T.smem_bytes, stream>>>(L, T, h, pq, params, de, dpq, dh, part);
+  kern<<<grid, NWG * 128 * NH + 32, T.smem_bytes, stream>>>(L, T, h, pq, params, de, dpq, dh, part);
   ce = cudaGetLastError();
   if (ce != cudaSuccess) { gj_set_error("edge_bwd_tc launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   return GJ_OK;
