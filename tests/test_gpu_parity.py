@@ -100,6 +100,36 @@ def test_mp_step_matches_oracle(precision, N, H, edge, node, B, metric):
     assert rel(dflat.cpu().numpy(), gflat_ref) < gtol
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("alpha", [0.0, 1.0, 1.7])
+def test_mp_step_alpha_range(precision, alpha):
+    """LeakyReLU slopes at and beyond the edges of (0, 1): alpha > 1 takes the min(z, alpha z) form (the tensor-core
+    kernels hand such steps to the fp32 kernels)."""
+    rng = np.random.default_rng(7)
+    N, H, edge, node, B = 12, 8, [32, 64, 16], [8, 6], 3
+    shapes_e = [(o, i) for i, o in zip([2 * H + 1] + edge[:-1], edge)]
+    shapes_n = [(o, i) for i, o in zip([edge[-1] + H] + node[:-1], node)]
+    ew = [rng.uniform(-1, 1, s) / np.sqrt(s[1]) for s in shapes_e]
+    eb = [rng.uniform(-1, 1, s[0]) / np.sqrt(s[1]) for s in shapes_e]
+    nw = [rng.uniform(-1, 1, s) / np.sqrt(s[1]) for s in shapes_n]
+    nb = [rng.uniform(-1, 1, s[0]) / np.sqrt(s[1]) for s in shapes_n]
+    h = rng.normal(0, 0.5, (B, N, H))
+    dy = rng.normal(0, 1.0, (B, N, node[-1]))
+    y_ref, cache = O.mp_step_forward(h, ew, eb, nw, nb, alpha)
+    dh_ref, dew, deb, dnw, dnb = O.mp_step_backward(dy, cache, ew, nw)
+    pack = lambda ws, bs: [np.concatenate([w.ravel(), b.ravel()]) for w, b in zip(ws, bs)]
+    flat = torch.from_numpy(np.concatenate(pack(ew, eb) + pack(nw, nb))).float().to(DEV)
+    gref = np.concatenate(pack(dew, deb) + pack(dnw, dnb))
+    ht = torch.from_numpy(h).float().to(DEV)
+    args = (N, H, edge, node, alpha, 0, ops.PRECISIONS[precision])
+    y, e = torch.ops.gnnjet.mp_step_fwd(ht, flat, *args)
+    dh, dflat = torch.ops.gnnjet.mp_step_bwd(ht, e, flat, torch.from_numpy(dy).float().to(DEV), *args)
+    tol = 1e-5 if precision == "fp32" else (2e-2 if alpha > 0 else 0.1)
+    assert rel(y.cpu().numpy(), y_ref) < tol
+    assert rel(dh.cpu().numpy(), dh_ref) < (1e-5 if precision == "fp32" else 0.1)
+    assert rel(dflat.cpu().numpy(), gref) < (1e-5 if precision == "fp32" else 0.1)
+
+
 # ---- whole model through the nn.Module (autograd) path, all golden cases --------------------------------
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 @pytest.mark.parametrize("name", sorted(CASES))
