@@ -2,6 +2,7 @@
 // error reporting.  No torch types; raw device pointers + sizes + cudaStream_t.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "gj_common.cuh"
 
@@ -13,6 +14,8 @@ void gj_set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+bool gj_tc_v1_forced() { static const bool v = getenv("GJ_TC_V1") && atoi(getenv("GJ_TC_V1")) != 0; return v; }
 
 int gj_num_sms() {
   static int sms[64] = {0};
@@ -39,6 +42,10 @@ int gj_edge_fwd_simt(MPLayout, const float*, const float*, const float*, float*,
 int gj_edge_bwd_simt(MPLayout, const float*, const float*, const float*, const float*, float*, float*, float*, float*,
                      cudaStream_t);
 int gj_edge_fwd_tc(MPLayout, const float*, const float*, const float*, float*, cudaStream_t);
+bool gj_fwd2_supported(const MPLayout&);
+size_t gj_fwd2_ws_floats(const MPLayout&);
+int gj_edge_fwd2(const MPLayout&, const float*, const float*, const float*, float*, float*, cudaStream_t);
+bool gj_tc_v1_forced();
 size_t gj_edge_bwd_tc_ws_floats(const MPLayout&);
 int gj_edge_bwd_tc(MPLayout, const float*, const float*, const float*, const float*, float*, float*, float*, float*,
                    cudaStream_t);
@@ -70,7 +77,7 @@ size_t gj_mp_param_count(const gj_mp_desc* d) {
 static size_t align_floats(size_t n) { return (n + 63) & ~(size_t)63; }   // keep every region 256-byte aligned
 
 struct StepWs {   // offsets in floats
-  size_t pq, dpq, de, part, total;
+  size_t pq, dpq, de, part, epart, total;
 };
 
 static bool use_tc(const MPLayout& L, int precision) { return precision == GJ_PREC_BF16 && L.Le > 1; }
@@ -79,6 +86,8 @@ static StepWs plan_ws(const MPLayout& L, int precision, bool backward) {
   StepWs w; size_t off = 0;
   const size_t rows = (size_t)L.B * L.N;
   w.pq = off; off += align_floats(rows * 2 * L.E0p);
+  w.epart = off;
+  if (!backward && use_tc(L, precision) && gj_fwd2_supported(L)) off += align_floats(gj_fwd2_ws_floats(L));   // per-j-block partial aggregates (N > 32)
   w.dpq = w.de = w.part = off;
   if (backward) {
     w.dpq = off; off += align_floats(rows * 2 * L.E0p);
@@ -114,8 +123,9 @@ int gj_mp_step_fwd(const gj_mp_desc* d, const float* h, const float* params, flo
   float* ws = (float*)workspace;
   cudaStream_t st = (cudaStream_t)stream;
   if ((rc = gj_node_pre_fwd(L, h, params, ws + w.pq, st))) return rc;
-  rc = use_tc(L, d->precision) ? gj_edge_fwd_tc(L, h, ws + w.pq, params, e_out, st)
-                               : gj_edge_fwd_simt(L, h, ws + w.pq, params, e_out, st);
+  if (use_tc(L, d->precision) && gj_fwd2_supported(L) && !gj_tc_v1_forced()) rc = gj_edge_fwd2(L, h, ws + w.pq, params, e_out, ws + w.epart, st);
+  else rc = use_tc(L, d->precision) ? gj_edge_fwd_tc(L, h, ws + w.pq, params, e_out, st)
+                                    : gj_edge_fwd_simt(L, h, ws + w.pq, params, e_out, st);
   if (rc) return rc;
   return gj_node_post_fwd(L, e_out, h, params, h_out, st);
 }

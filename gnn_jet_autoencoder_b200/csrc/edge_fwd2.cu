@@ -1,0 +1,401 @@
+// Forward edge kernel, second generation (GJ_PREC_BF16, four edge layers with compile-time widths).
+//
+// Replaces the edge part of one iteration of reference models/graphnet.py:154-168 (_getA :186-223, _edge_conv :273-289,
+// the sum over j of _concat :243):  e_i = sum_j EdgeNet([h_i | h_j | d_ij]).
+//
+// Decomposition.  A WARP owns a (jet, j block) pair -- lane = j, so Q_j (registers) and h_j (a per-lane shared-memory
+// row) are loaded once -- and walks i = 0..N-1.  A TILE GROUP is four such warps (one TMEM lane quadrant each, possibly
+// four different jets) moving in lock step: one tile = 128 edge rows = 4 (jet, i) x 32 j.  A CTA runs NWG tile groups,
+// each with a private TMEM slot, so that the tensor pipe works on one group's GEMM while the others run epilogues.
+// Per tile:
+//   a0 = leaky(P_i + Q_j + wd d_ij)                    CUDA cores (packed fp32), bf16 pairs -> TMEM (tcgen05.st)
+//   a_l = leaky(W_l a_{l-1} + b_l), l = 1, 2, 3         tcgen05.mma, A from TMEM, W_l (bf16, K-major) from shared memory,
+//                                                      bias as one extra k-step against a constant (1,1,0..) A chunk;
+//                                                      epilogue tcgen05.ld -> cvt bf16x2 -> HMUL2/HMNMX2 -> tcgen05.st
+//                                                      in place over the accumulator columns just read
+//   e_i = sum_j a_3                                    transpose-reduce over the warp's lanes, one 64-byte store
+// Nothing but P|Q, h and e touches HBM; activations never touch shared memory.
+//
+// TMEM slot of a tile group (160 columns):   [0,128) acc1 -> a1 packed in [0,64) -> acc2 in [64,128) -> a2 in [0,32)
+//                                            [128,144) a0 (packed)      [144,160) acc3
+// column 480..487: the constant bias A chunk shared by all groups.
+#include <stdlib.h>
+
+#include "tc2_common.cuh"
+
+namespace {
+using namespace tc2;
+
+struct Fwd2Args {
+  const float* h; const float* pq; const float* params; float* e_out;
+  int B, N, NJB, cols, ld, mink;
+  int Hb, Hs;            // h_i row length (multiple of 4 floats), h_j per-lane row stride (floats, (Hs/4) odd)
+  int pW1, pb1, pW2, pb2, pW3, pb3, pWd, K0;
+  float alpha;
+  int tiles_total;       // ceil(B * NJB / 4) * N
+};
+
+constexpr int F2_IC = 32;          // i's staged per refill
+constexpr int F2_SLOT = 160;
+constexpr int F2_ONES_COL = 480;
+
+template <int E0, int E1, int E2, int E3, int NWG>
+struct Fwd2Smem {
+  static constexpr int o_bar = 0;                       // NWG * 3 mbarriers
+  static constexpr int o_slot = 128;
+  static constexpr int o_wd = 256;                      // E0 floats
+  static constexpr int o_w1 = 1024;
+  static constexpr int o_w2 = o_w1 + E1 * E0 * 2;
+  static constexpr int o_w3 = o_w2 + E2 * E1 * 2;
+  static constexpr int o_b1 = o_w3 + E3 * E2 * 2;
+  static constexpr int o_b2 = o_b1 + E1 * 32;
+  static constexpr int o_b3 = o_b2 + E2 * 32;
+  static constexpr int o_warp = ((o_b3 + E3 * 32 + 127) / 128) * 128;
+  __host__ __device__ static int warp_bytes(int Hb, int Hs) { return (F2_IC * (E0 + Hb) + 32 * Hs) * 4; }
+  __host__ __device__ static int total(int Hb, int Hs) { return o_warp + NWG * 4 * warp_bytes(Hb, Hs); }
+};
+
+// transpose-reduce of 16 per-lane values over the 32 lanes of a warp: every lane returns the sum over all lanes of
+// channel (lane >> 1) & 15
+__device__ __forceinline__ float warp_transpose_sum16(const float (&v)[16], int lane) {
+  float w8[8], w4[4], w2[2];
+  bool up = lane & 16;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float send = up ? v[q] : v[q + 8], keep = up ? v[q + 8] : v[q];
+    w8[q] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+  up = lane & 8;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float send = up ? w8[q] : w8[q + 4], keep = up ? w8[q + 4] : w8[q];
+    w4[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  up = lane & 4;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const float send = up ? w4[q] : w4[q + 2], keep = up ? w4[q + 2] : w4[q];
+    w2[q] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  up = lane & 2;
+  const float send = up ? w2[0] : w2[1], keep = up ? w2[1] : w2[0];
+  const float w1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  return w1 + __shfl_xor_sync(0xffffffffu, w1, 1);
+}
+
+// epilogue of a hidden layer: NCOL fp32 accumulator columns at acc -> leaky -> NCOL/2 packed bf16 columns at dst
+template <int NCOL>
+__device__ __forceinline__ void epilogue_hidden(uint32_t acc, uint32_t dst, __nv_bfloat162 alpha2) {
+  static_assert(NCOL % 32 == 0, "hidden widths are multiples of 32");
+  constexpr int NCH = NCOL / 32;
+  uint32_t va[32], vb[32];
+  tmem_ld32_u(acc, va);
+#pragma unroll
+  for (int ch = 0; ch < NCH; ch += 2) {
+    tmem_ld_wait(); tmem_pin32(va);
+    if (ch + 1 < NCH) tmem_ld32_u(acc + (uint32_t)((ch + 1) * 32), vb);
+    {
+      uint32_t o[16];
+#pragma unroll
+      for (int p = 0; p < 16; ++p) o[p] = leaky_pack(__uint_as_float(va[2 * p]), __uint_as_float(va[2 * p + 1]), alpha2);
+      tmem_st16(dst + (uint32_t)(ch * 16), o);
+    }
+    if (ch + 1 < NCH) {
+      tmem_ld_wait(); tmem_pin32(vb);
+      if (ch + 2 < NCH) tmem_ld32_u(acc + (uint32_t)((ch + 2) * 32), va);
+      uint32_t o[16];
+#pragma unroll
+      for (int p = 0; p < 16; ++p) o[p] = leaky_pack(__uint_as_float(vb[2 * p]), __uint_as_float(vb[2 * p + 1]), alpha2);
+      tmem_st16(dst + (uint32_t)((ch + 1) * 16), o);
+    }
+  }
+}
+
+// optional stage timeline of tile group 0 of CTA 0 (GJ_TRACE=3): 8 clock stamps per tile
+__device__ long long g_f2_trace[8 * 256];
+#define F2_STAMP(s) do { if (TRACE && blockIdx.x == 0 && tid == 0 && tr_n < 256) g_f2_trace[tr_n * 8 + (s)] = clock64(); } while (0)
+
+template <int E0, int E1, int E2, int E3, int NWG, bool TRACE>
+__global__ void __launch_bounds__(NWG * 128, 1) edge_fwd2_kernel(const Fwd2Args A) {
+  static_assert(E0 == 32 && E3 == 16, "TMEM slot map assumes a 32-wide first and a 16-wide last edge layer");
+  static_assert(E1 % 32 == 0 && E1 <= 128 && E2 % 32 == 0 && E1 / 2 + E2 <= 128 && E2 / 2 <= E1 / 2, "TMEM slot map");
+  using S = Fwd2Smem<E0, E1, E2, E3, NWG>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = (int)uni((uint32_t)(tid >> 5));
+  const int wg = warp >> 2, wq = warp & 3;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::o_bar) + wg * 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::o_slot);
+  float* s_wd = reinterpret_cast<float*>(smem + S::o_wd);
+
+  // ---- one-time staging: weights / biases as bf16 B operands, wd, barriers, TMEM ----
+  stage_weight_kmajor<E1, E0>(smem + S::o_w1, A.params + A.pW1, tid, NWG * 128);
+  stage_weight_kmajor<E2, E1>(smem + S::o_w2, A.params + A.pW2, tid, NWG * 128);
+  stage_weight_kmajor<E3, E2>(smem + S::o_w3, A.params + A.pW3, tid, NWG * 128);
+  stage_bias_slab<E1>(smem + S::o_b1, A.params + A.pb1, tid, NWG * 128);
+  stage_bias_slab<E2>(smem + S::o_b2, A.params + A.pb2, tid, NWG * 128);
+  stage_bias_slab<E3>(smem + S::o_b3, A.params + A.pb3, tid, NWG * 128);
+  for (int c = tid; c < E0; c += NWG * 128) s_wd[c] = __ldg(A.params + A.pWd + c * A.K0);
+  if (tid == 0) {
+    for (int b = 0; b < NWG * 3; ++b) mbar_init(reinterpret_cast<uint64_t*>(smem + S::o_bar) + b, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16);
+  if (wg == 0) {     // constant bias A chunk: k = 0, 1 -> 1.0 (bias hi + lo), k = 2..15 -> 0
+    uint32_t ones[8] = {0x3F803F80u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+    tmem_st8(lane_base + F2_ONES_COL, ones);
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  const uint32_t slot = lane_base + (uint32_t)(wg * F2_SLOT);       // this thread's row of the group's slot
+  const uint32_t slot0 = tmem_base + (uint32_t)(wg * F2_SLOT);      // lane 0 (MMA operand addresses)
+  const __nv_bfloat162 alpha2 = __float2bfloat162_rn(A.alpha);
+  const float alpha = A.alpha;
+
+  // MMA constants (warp-uniform)
+  const uint32_t idesc1 = make_idesc_bf16(128, E1, 0, 0), idesc2 = make_idesc_bf16(128, E2, 0, 0), idesc3 = make_idesc_bf16(128, E3, 0, 0);
+  const uint64_t dW1 = wdesc_kmajor(smem_u32(smem + S::o_w1), E1), dW2 = wdesc_kmajor(smem_u32(smem + S::o_w2), E2),
+                 dW3 = wdesc_kmajor(smem_u32(smem + S::o_w3), E3);
+  const uint64_t dB1 = wdesc_kmajor(smem_u32(smem + S::o_b1), E1), dB2 = wdesc_kmajor(smem_u32(smem + S::o_b2), E2),
+                 dB3 = wdesc_kmajor(smem_u32(smem + S::o_b3), E3);
+  const uint32_t ones_addr = tmem_base + F2_ONES_COL;
+
+  // per-warp staging
+  const int Hb = A.Hb, Hs = A.Hs, RS = E0 + Hb;
+  float* s_pi = reinterpret_cast<float*>(smem + S::o_warp + warp * S::warp_bytes(Hb, Hs));      // [F2_IC][E0 + Hb]
+  float* s_hj = s_pi + F2_IC * RS;                                                              // [32][Hs]
+  const int H4 = Hb >> 2;
+
+  // tile range of this group: tiles are (group task k, i), k-major
+  const int ngroups = gridDim.x * NWG, gidx = blockIdx.x * NWG + wg;
+  const long long T = A.tiles_total;
+  const int g0 = (int)(T * gidx / ngroups), g1 = (int)(T * (gidx + 1) / ngroups);
+  const int N = A.N;
+  const int ntasks = A.B * A.NJB;
+  int k = g0 / N, i = g0 - k * N;
+  bool fresh = true;
+  int ibase = 0;
+  float q[E0];
+  bool active = false, valid = false;
+  size_t node0 = 0;      // first node row of the warp's jet
+  float* e_dst = nullptr;
+  uint32_t ph = 0;
+  int tr_n = 0;
+
+  for (int g = g0; g < g1; ++g) {
+    F2_STAMP(0);
+    if (fresh) {
+      // ---- new (jet, j block): Q_j -> registers, h_j -> per-lane shared row ----
+      const int task = 4 * k + wq;
+      active = task < ntasks;
+      const int tk = active ? task : 0;
+      const int jet = tk / A.NJB, jb = tk - jet * A.NJB;
+      const int j = jb * 32 + lane;
+      valid = active && j < N;
+      node0 = (size_t)jet * N;
+      e_dst = A.e_out + ((size_t)jb * A.B + jet) * N * E3;
+      __syncwarp();
+      if (j < N) {
+        const float4* src = reinterpret_cast<const float4*>(A.pq + (node0 + j) * (2 * E0) + E0);
+#pragma unroll
+        for (int c = 0; c < E0 / 4; ++c) { const float4 v = __ldg(src + c); q[4 * c] = v.x; q[4 * c + 1] = v.y; q[4 * c + 2] = v.z; q[4 * c + 3] = v.w; }
+        const float* hsrc = A.h + (node0 + j) * A.ld;
+        for (int kk = 0; kk < Hb; ++kk) s_hj[lane * Hs + kk] = kk < A.cols ? __ldg(hsrc + kk) : 0.f;
+      } else {
+#pragma unroll
+        for (int c = 0; c < E0; ++c) q[c] = 0.f;
+        for (int kk = 0; kk < Hb; ++kk) s_hj[lane * Hs + kk] = 0.f;
+      }
+    }
+    if (fresh || i - ibase == F2_IC) {
+      // ---- refill P_i | h_i for the next F2_IC i's (warp-private, no cross-warp sync) ----
+      __syncwarp();
+      ibase = i;
+      const int n = min(F2_IC, N - i);
+      for (int idx = lane; idx < n * (E0 / 4); idx += 32) {
+        const int r = idx / (E0 / 4), c4 = idx - r * (E0 / 4);
+        const float4 v = __ldg(reinterpret_cast<const float4*>(A.pq + (node0 + i + r) * (2 * E0)) + c4);
+        *reinterpret_cast<float4*>(s_pi + r * RS + 4 * c4) = v;
+      }
+      for (int idx = lane; idx < n * Hb; idx += 32) {
+        const int r = idx / Hb, kk = idx - r * Hb;
+        s_pi[r * RS + E0 + kk] = kk < A.cols ? __ldg(A.h + (node0 + i + r) * A.ld + kk) : 0.f;
+      }
+      __syncwarp();
+    }
+    fresh = false;
+    F2_STAMP(1);
+
+    // ---- first edge layer on the CUDA cores ----
+    {
+      const float* Pi = s_pi + (i - ibase) * RS;
+      const float4* hi4 = reinterpret_cast<const float4*>(Pi + E0);
+      const float4* hj4 = reinterpret_cast<const float4*>(s_hj + lane * Hs);
+      float d;
+      if (A.mink) {       // width 4 only: x0^2 - x1^2 - x2^2 - x3^2 (graphnet.py:320-323)
+        const float4 a = hi4[0], b = hj4[0];
+        const float x0 = b.x - a.x, x1 = b.y - a.y, x2 = b.z - a.z, x3 = b.w - a.w;
+        d = x0 * x0 - x1 * x1 - x2 * x2 - x3 * x3;
+      } else {
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll 2
+        for (int k4 = 0; k4 < H4; ++k4) {
+          const float4 a = hi4[k4], b = hj4[k4];
+          const float2 x = make_float2(b.x - a.x, b.y - a.y), y = make_float2(b.z - a.z, b.w - a.w);
+          acc = fma2(x, x, acc); acc = fma2(y, y, acc);
+        }
+        d = acc.x + acc.y;
+      }
+      const float2 d2 = make_float2(d, d);
+      uint32_t a0[E0 / 2];
+#pragma unroll
+      for (int c = 0; c < E0; c += 4) {
+        const float4 p = *reinterpret_cast<const float4*>(Pi + c);
+        const float4 w = *reinterpret_cast<const float4*>(s_wd + c);
+        const float2 z0 = fma2(make_float2(w.x, w.y), d2, add2(make_float2(p.x, p.y), make_float2(q[c], q[c + 1])));
+        const float2 z1 = fma2(make_float2(w.z, w.w), d2, add2(make_float2(p.z, p.w), make_float2(q[c + 2], q[c + 3])));
+        a0[c / 2] = leaky_pack(z0.x, z0.y, alpha2);
+        a0[c / 2 + 1] = leaky_pack(z1.x, z1.y, alpha2);
+      }
+      tmem_st16(slot + 128, a0);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    F2_STAMP(2);
+    named_bar_sync(1 + wg, 128);
+    if (wq == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int s = 0; s < E0 / 16; ++s) mma_ts_elect(slot0, slot0 + 128 + 8 * s, dW1 + (uint64_t)(s * ((2 * E1 * 16) >> 4)), idesc1, s > 0);
+      mma_ts_elect(slot0, ones_addr, dB1, idesc1, 1u);
+      mma_commit_elect(bars + 0);
+    }
+    mbar_wait_all(bars + 0, ph);
+    tc_fence_after();
+    F2_STAMP(3);
+    epilogue_hidden<E1>(slot, slot, alpha2);
+    tmem_st_wait();
+    tc_fence_before();
+    F2_STAMP(4);
+    named_bar_sync(1 + wg, 128);
+    if (wq == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int s = 0; s < E1 / 16; ++s) mma_ts_elect(slot0 + E1 / 2, slot0 + 8 * s, dW2 + (uint64_t)(s * ((2 * E2 * 16) >> 4)), idesc2, s > 0);
+      mma_ts_elect(slot0 + E1 / 2, ones_addr, dB2, idesc2, 1u);
+      mma_commit_elect(bars + 1);
+    }
+    mbar_wait_all(bars + 1, ph);
+    tc_fence_after();
+    F2_STAMP(5);
+    epilogue_hidden<E2>(slot + E1 / 2, slot, alpha2);
+    tmem_st_wait();
+    tc_fence_before();
+    F2_STAMP(6);
+    named_bar_sync(1 + wg, 128);
+    if (wq == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int s = 0; s < E2 / 16; ++s) mma_ts_elect(slot0 + 144, slot0 + 8 * s, dW3 + (uint64_t)(s * ((2 * E3 * 16) >> 4)), idesc3, s > 0);
+      mma_ts_elect(slot0 + 144, ones_addr, dB3, idesc3, 1u);
+      mma_commit_elect(bars + 2);
+    }
+    mbar_wait_all(bars + 2, ph);
+    tc_fence_after();
+    F2_STAMP(7);
+    ++tr_n;
+    {
+      uint32_t r[16];
+      tmem_ld16_u(slot + 144, r);
+      tmem_ld_wait(); tmem_pin16(r);
+      float v[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) { const float z = __uint_as_float(r[c]); v[c] = valid ? fmaxf(z, alpha * z) : 0.f; }
+      const float s = warp_transpose_sum16(v, lane);
+      if (active && (lane & 1) == 0) e_dst[(size_t)i * E3 + (lane >> 1)] = s;
+    }
+    tc_fence_before();      // orders this tile's TMEM reads before the next tile's MMA (through the next bar.sync)
+    ph ^= 1u;
+    if (++i == N) { i = 0; ++k; fresh = true; }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// sums the NJB per-j-block partial aggregates in a fixed order
+__global__ void sum_jblocks_kernel(const float* __restrict__ part, int njb, size_t n, float* __restrict__ out) {
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int b = 0; b < njb; ++b) s += part[(size_t)b * n + idx];
+    out[idx] = s;
+  }
+}
+
+}  // namespace
+
+int gj_num_sms();
+void gj_set_error(const char* fmt, ...);
+
+// debugging aid (not part of the ABI header): stage timeline of the last traced forward launch
+extern "C" int gj_debug_read_fwd2_trace(long long* out) {
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(out, g_f2_trace, sizeof(long long) * 8 * 256) == cudaSuccess ? 0 : 1;
+}
+
+// widths covered by the specialised kernels
+bool gj_fwd2_supported(const MPLayout& L) {
+  return L.Le == 4 && L.E[0] == 32 && L.E[1] == 128 && L.E[2] == 64 && L.E[3] == 16 && L.alpha <= 1.f && L.cols <= 64;
+}
+size_t gj_fwd2_ws_floats(const MPLayout& L) {
+  const int njb = (L.N + 31) / 32;
+  return njb > 1 ? (size_t)njb * L.B * L.N * L.E[3] : 0;
+}
+
+int gj_edge_fwd2(const MPLayout& L, const float* h, const float* pq, const float* params, float* e_out, float* ws,
+                 cudaStream_t stream) {
+  constexpr int NWG = 3;
+  Fwd2Args A;
+  A.h = h; A.pq = pq; A.params = params;
+  A.B = L.B; A.N = L.N; A.NJB = (L.N + 31) / 32; A.cols = L.cols; A.ld = L.ld; A.mink = L.mink;
+  A.e_out = A.NJB > 1 ? ws : e_out;
+  A.Hb = (L.cols + 3) & ~3;
+  A.Hs = 4 * ((A.Hb >> 2) | 1);
+  A.pW1 = L.pW[1]; A.pb1 = L.pb[1]; A.pW2 = L.pW[2]; A.pb2 = L.pb[2]; A.pW3 = L.pW[3]; A.pb3 = L.pb[3];
+  A.pWd = L.pW[0] + 2 * L.H; A.K0 = L.K[0];
+  A.alpha = L.alpha;
+  const long long tasks4 = ((long long)L.B * A.NJB + 3) / 4;
+  if (tasks4 * L.N > 0x7fffffffLL) { gj_set_error("gj_mp_step_fwd(bf16): batch * nodes too large"); return GJ_ERR_INVALID; }
+  A.tiles_total = (int)(tasks4 * L.N);
+  using S = Fwd2Smem<32, 128, 64, 16, NWG>;
+  const int smem = S::total(A.Hb, A.Hs);
+  if (smem > 227 * 1024) { gj_set_error("gj_mp_step_fwd(bf16): needs %d B shared memory", smem); return GJ_ERR_SMEM; }
+  static const int trace_env = getenv("GJ_TRACE") ? atoi(getenv("GJ_TRACE")) : 0;
+  auto kern = trace_env == 3 ? edge_fwd2_kernel<32, 128, 64, 16, NWG, true> : edge_fwd2_kernel<32, 128, 64, 16, NWG, false>;
+  cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (ce != cudaSuccess) { gj_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
+  int grid = gj_num_sms();
+  const int max_grid = (A.tiles_total + NWG - 1) / NWG;
+  if (grid > max_grid) grid = max_grid;
+  kern<<<grid, NWG * 128, smem, stream>>>(A);
+  ce = cudaGetLastError();
+  if (ce != cudaSuccess) { gj_set_error("edge_fwd2 launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
+  if (A.NJB > 1) {
+    const size_t n = (size_t)L.B * L.N * L.E[3];
+    int blocks = (int)((n + 255) / 256); if (blocks > 4 * gj_num_sms()) blocks = 4 * gj_num_sms();
+    sum_jblocks_kernel<<<blocks, 256, 0, stream>>>(ws, A.NJB, n, e_out);
+    ce = cudaGetLastError();
+    if (ce != cudaSuccess) { gj_set_error("sum_jblocks launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
+  }
+  return GJ_OK;
+}

@@ -1,0 +1,136 @@
+// Building blocks of the second-generation tensor-core edge kernels (edge_fwd2.cu / edge_bwd2.cu).
+//
+// What differs from the first-generation kernels in edge_tc.cu:
+//   * widths are template parameters, so every MMA batch, descriptor advance and epilogue loop is unrolled;
+//   * the A operand of the forward and dgrad GEMMs lives in TENSOR MEMORY (tcgen05.mma "TS" form): an epilogue writes
+//     the next layer's bf16 operand straight back into TMEM with tcgen05.st (thread = row = TMEM lane), in place over
+//     the accumulator columns it has just read, so forward activations never touch shared memory;
+//   * a warp owns a (jet, 32-wide j block) for all i: Q_j lives in registers, P_i / h_i are staged by the warp itself,
+//     and the four warps of a tile group (one TMEM lane quadrant each) may belong to four different jets;
+//   * the LeakyReLU runs on packed bf16 pairs (cvt.rn.bf16x2.f32 + HMUL2 + HMNMX2: 1.5 instructions per element).
+#pragma once
+#include "gj_common.cuh"
+#include "umma.cuh"
+
+namespace tc2 {
+using namespace umma;
+
+// ---- TMEM <-> registers -------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_ld16_u(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_u(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+// Completes ALL outstanding tcgen05.ld of the thread.  The register arrays of those loads must be passed through
+// tmem_pin*() right after, which orders every later use behind the wait for the compiler (no instruction is emitted).
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_pin16(uint32_t (&r)[16]) {
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                    "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :: "memory");
+}
+__device__ __forceinline__ void tmem_pin32(uint32_t (&r)[32]) {
+  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                    "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :: "memory");
+  asm volatile("" : "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                    "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :: "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+         "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// ---- MMA issue (warp-convergent: all 32 lanes execute with warp-uniform operands, one elected lane issues) ----
+// D[tmem] (+)= A[tmem] * B[smem]^T : A is 128 lanes x 16 bf16 (8 columns, two K elements per 32-bit column)
+__device__ __forceinline__ void mma_ts_elect(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// ---- packed arithmetic ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t bf2_as_u32(__nv_bfloat162 v) { return *reinterpret_cast<uint32_t*>(&v); }
+__device__ __forceinline__ __nv_bfloat162 u32_as_bf2(uint32_t v) { return *reinterpret_cast<__nv_bfloat162*>(&v); }
+// {lo, hi} -> bf16x2 (lo in bits 0..15 = the lower K index), LeakyReLU(x) = max(x, alpha x) for 0 <= alpha <= 1
+__device__ __forceinline__ uint32_t leaky_pack(float lo, float hi, __nv_bfloat162 alpha2) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  v = __hmax2(v, __hmul2(v, alpha2));
+  return bf2_as_u32(v);
+}
+// (a.x + b.x, a.y + b.y) and (a * b + c) on the packed fp32 pipe
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 r;
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rc, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rc;\n\t}"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 r;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\t"
+      "mov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+      "mov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return r;
+}
+
+// ---- weights: bf16 K-major B operand (N = out feature rows, K = in features), interleaved SWIZZLE_NONE layout ----
+// element (n, k) at (k / 8) * (NOUT * 16) + n * 16 + (k % 8) * 2
+template <int NOUT, int KIN>
+__device__ __forceinline__ void stage_weight_kmajor(uint8_t* dst, const float* __restrict__ W, int tid, int nthr) {
+  for (int idx = tid; idx < NOUT * KIN; idx += nthr) {
+    const int n = idx / KIN, k = idx - n * KIN;
+    *reinterpret_cast<__nv_bfloat16*>(dst + (k >> 3) * (NOUT * 16) + n * 16 + (k & 7) * 2) = __float2bfloat16_rn(__ldg(W + idx));
+  }
+}
+// bias as one extra k-step of the same GEMM: B rows [NOUT][16], column 0 = bias (split hi + lo over columns 0 and 1 so
+// the bias enters the fp32 accumulator to ~16 bits), the matching A chunk is the constant (1, 1, 0, ..., 0)
+template <int NOUT>
+__device__ __forceinline__ void stage_bias_slab(uint8_t* dst, const float* __restrict__ b, int tid, int nthr) {
+  for (int idx = tid; idx < NOUT * 16; idx += nthr) {
+    const int n = idx >> 4, k = idx & 15;
+    const float v = __ldg(b + n);
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    const __nv_bfloat16 z = __float2bfloat16_rn(0.f);
+    *reinterpret_cast<__nv_bfloat16*>(dst + (k >> 3) * (NOUT * 16) + n * 16 + (k & 7) * 2) = k == 0 ? hi : (k == 1 ? lo : z);
+  }
+}
+__device__ __forceinline__ uint64_t wdesc_kmajor(uint32_t saddr, int nout) { return make_smem_desc(saddr, (uint32_t)nout * 16u, 128u); }
+
+// all threads of a tile group wait on the barrier (hardware-suspended try_wait)
+__device__ __forceinline__ void mbar_wait_all(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
+
+}  // namespace tc2

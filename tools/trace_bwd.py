@@ -31,7 +31,8 @@ for who in range(3):
 ev.sort()
 t0 = ev[0][0]
 names = {10: "arrive(L0 done)", 60: "B1 epilogue done"}
-for tcl, who, tag in ev[:260]:
+limit = int(os.environ.get('GJ_TRACE_LINES', '260'))
+for tcl, who, tag in ev[:limit]:
     who_s = ["WG0", "WG1", "ISS"][who]
     if who == 2:
         w, s = (tag % 1000) // 100, tag % 100
