@@ -46,6 +46,9 @@ bool gj_fwd2_supported(const MPLayout&);
 size_t gj_fwd2_ws_floats(const MPLayout&);
 int gj_edge_fwd2(const MPLayout&, const float*, const float*, const float*, float*, float*, cudaStream_t);
 bool gj_tc_v1_forced();
+bool gj_bwd2_supported(const MPLayout&);
+size_t gj_bwd2_ws_floats(const MPLayout&);
+int gj_edge_bwd2(const MPLayout&, const float*, const float*, const float*, const float*, float*, float*, float*, float*, cudaStream_t);
 size_t gj_edge_bwd_tc_ws_floats(const MPLayout&);
 int gj_edge_bwd_tc(MPLayout, const float*, const float*, const float*, const float*, float*, float*, float*, float*,
                    cudaStream_t);
@@ -95,6 +98,7 @@ static StepWs plan_ws(const MPLayout& L, int precision, bool backward) {
     size_t p = gj_node_post_bwd_ws_floats(L);
     size_t q = gj_node_pre_bwd_ws_floats(L);
     size_t r = use_tc(L, precision) ? gj_edge_bwd_tc_ws_floats(L) : (size_t)gj_edge_grid(L.B) * L.pV[0];
+    if (use_tc(L, precision) && gj_bwd2_supported(L)) { const size_t r2 = gj_bwd2_ws_floats(L); if (r2 > r) r = r2; }
     if (q > p) p = q;
     if (r > p) p = r;
     w.part = off; off += align_floats(p);
@@ -153,8 +157,11 @@ int gj_mp_step_bwd(const gj_mp_desc* d, const float* h, const float* e, const fl
   if ((rc = gj_node_post_bwd(L, e, h, params, dh_out, ws + w.de, dh, dparams, ws + w.part, st))) return rc;
   // recompute P|Q, then the edge adjoint: dP|dQ, distance-path dh, edge parameter gradients
   if ((rc = gj_node_pre_fwd(L, h, params, ws + w.pq, st))) return rc;
-  rc = use_tc(L, d->precision) ? gj_edge_bwd_tc(L, h, ws + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.part, st)
-                               : gj_edge_bwd_simt(L, h, ws + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.part, st);
+  if (use_tc(L, d->precision) && gj_bwd2_supported(L) && !gj_tc_v1_forced())
+    rc = gj_edge_bwd2(L, h, ws + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.part, st);
+  else
+    rc = use_tc(L, d->precision) ? gj_edge_bwd_tc(L, h, ws + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.part, st)
+                                 : gj_edge_bwd_simt(L, h, ws + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.part, st);
   if (rc) return rc;
   // first-layer projections' adjoint: dh += Wa^T dP + Wb^T dQ, dWa, dWb, db0
   return gj_node_pre_bwd(L, h, params, ws + w.dpq, dh, dparams, ws + w.part, st);

@@ -1,0 +1,786 @@
+// Backward edge kernel, second generation (GJ_PREC_BF16, four edge layers with compile-time widths): recompute +
+// dgrad + wgrad of the edge MLP of one message-passing step on tcgen05, nothing N^2-sized leaves the SM except the
+// scalar G_ij = dL/d(d_ij).  Adjoint of the edge part of reference models/graphnet.py:154-168 (_getA :186-223,
+// _edge_conv :273-289, the sum over j of _concat :243).
+//
+// Decomposition (same as edge_fwd2.cu).  A warp owns a (jet, j block) -- lane = j, Q_j and the dQ_j accumulator live in
+// registers -- and walks i; four warps (four TMEM lane quadrants, possibly four jets) form a TILE GROUP of 128 edge
+// rows per tile; a CTA runs NWG groups, each with a private 128-column TMEM slot.  A group issues its own GEMMs (one
+// warp, rotating with the stage, after a group-wide named barrier), so the groups drift freely against each other:
+// while one group's GEMMs occupy the tensor pipe the others run epilogues.  The weight-gradient accumulators are
+// shared by all groups and stay in TMEM for the whole kernel (tcgen05.mma from different warps execute one after the
+// other in the SM's single tensor pipe, so concurrent accumulation is safe); the order in which tiles are added depends
+// on timing, i.e. parameter gradients are reproducible to fp32 rounding, not bitwise.  (A dedicated issuer warp that
+// serves the groups round-robin would restore bitwise reproducibility, but a 13th warp caps the kernel at 128
+// registers per thread -- 16 K registers per SM sub-partition / 4 warps -- and round-robin issue locks the groups'
+// stages together.)
+//
+// Stages of one tile (thread = edge row = TMEM lane; all operands bf16, accumulation fp32):
+//   L0  a0 = leaky(P_i + Q_j + wd d_ij)                      CUDA cores -> shared A0 (A of F1, B of the layer-1 wgrad)
+//   F1  acc[0,128) = A0 W1^T           (SS)                  epi: +b1, leaky -> a1: TMEM [0,64) (A of F2) + shared X1
+//   F2  acc[64,128) = a1 W2^T          (TS)                  epi: +b2, leaky -> a2: TMEM [0,32) (A of F3) + shared X2
+//   F3  acc[32,48) = a2 W3^T           (TS)                  epi: dz3 = de_i leaky'(z3) [valid] -> TMEM [48,56) + shared D3
+//   B3  acc[64,128) = dz3 W3 (TS);  dW3 += a2^T dz3 (SS)      epi: dz2 = acc leaky'(a2) -> shared X2 (in place over a2)
+//   B2  acc[0,128) = dz2 W2 (SS);   dW2 += a1^T dz2;  db2 += dz2^T 1        epi: dz1 = acc leaky'(a1) -> TMEM [0,64) +
+//                                                                                shared X1 (in place over a1)
+//   B1  acc[64,96) = dz1 W1 (TS);   [dW1 | db1] += dz1^T [a0 | 1] (SS, completes behind the epilogue)
+//                                                            epi: dz0 = acc leaky'(a0) in fp32 -> dP_i (lane reduce),
+//                                                                 dQ_j, d(wd), G_ij = dz0 . wd
+// The first layer is factorised (W0 [h_i | h_j | d] = Wa h_i + Wb h_j + wd d, graphnet.py:220): P, Q come from
+// node_pre_fwd, d from pair_dist_fwd, and dP, dQ, G go back to node_pre_bwd / pair_dist_bwd.
+//
+// TMEM: columns [128 g, 128 g + 128) = slot of group g;  [384,432) dW1 (lane = out feature, column = in feature, column 32
+// = db1);  [432,496) dW2 (lane = in feature, column = out feature);  [496,512) dW3 (M = 64: in feature k at lane
+// (k / 16) * 32 + k % 16, column = out feature) and, at lane offset 16 of the same columns, db2 (M = 64, column 496).
+#include <stdlib.h>
+
+#include "tc2_common.cuh"
+
+namespace {
+using namespace tc2;
+
+struct Bwd2Args {
+  const float* pq; const float* d; const float* params; const float* de;
+  float* dpq; float* dp_part; float* G; float* part;
+  int B, N, NJB, NJ32;
+  int pW1, pb1, pW2, pb2, pW3, pb3, pWd, K0, nedge;
+  float alpha;
+  int tiles_total, ngroups;
+};
+
+constexpr int B2_IC = 2;           // i's per staged P_i chunk (double buffered, cp.async)
+
+template <int E0, int E1, int E2, int E3, int NWG>
+struct Bwd2Smem {
+  static constexpr int o_bar = 0;                        // per group: done, done2
+  static constexpr int o_slot = 256;
+  static constexpr int o_f32 = 512;                      // b1 | b2 | b3 | wd | reduction scratch
+  static constexpr int n_f32 = E1 + E2 + E3 + E0;
+  static constexpr int o_red = o_f32 + n_f32 * 4;        // [NWG * 4 warps][E0 + E3] floats
+  static constexpr int o_ones = ((o_red + NWG * 4 * (E0 + E3) * 4 + 127) / 128) * 128;     // [8][16] bf16 ones (B of the db2 column sum)
+  static constexpr int o_w1 = ((o_ones + 256 + 1023) / 1024) * 1024;
+  static constexpr int o_w2 = o_w1 + E1 * E0 * 2;
+  static constexpr int o_w3 = o_w2 + E2 * E1 * 2;
+  static constexpr int o_grp = o_w3 + E3 * E2 * 2;
+  // per group: A0 = [a0: E0/8 slabs][ones slab][dz3: E3/8 slabs], X1 (a1 / dz1), X2 (a2 / dz2); one slab = [128 rows][8] bf16
+  static constexpr int g_a0 = 0;
+  static constexpr int g_ones = (E0 / 8) * 2048;
+  static constexpr int g_d3 = g_ones + 2048;
+  static constexpr int g_x1 = g_d3 + (E3 / 8) * 2048;
+  static constexpr int g_x2 = g_x1 + (E1 / 8) * 2048;
+  static constexpr int grp_bytes = g_x2 + (E2 / 8) * 2048;
+  static constexpr int o_warp = o_grp + NWG * grp_bytes;
+  static constexpr int warp_bytes = 2 * B2_IC * E0 * 4;
+  static constexpr int total = o_warp + NWG * 4 * warp_bytes;
+};
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// transpose-reduce of 16 per-lane values over the 32 lanes of a warp: every lane returns the sum over all lanes of
+// channel (lane >> 1) & 15
+__device__ __forceinline__ float warp_transpose_sum16(const float (&v)[16], int lane) {
+  float w8[8], w4[4], w2[2];
+  bool up = lane & 16;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float send = up ? v[q] : v[q + 8], keep = up ? v[q + 8] : v[q];
+    w8[q] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+  up = lane & 8;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float send = up ? w8[q] : w8[q + 4], keep = up ? w8[q + 4] : w8[q];
+    w4[q] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  up = lane & 4;
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    const float send = up ? w4[q] : w4[q + 2], keep = up ? w4[q + 2] : w4[q];
+    w2[q] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  up = lane & 2;
+  const float send = up ? w2[0] : w2[1], keep = up ? w2[1] : w2[0];
+  const float w1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  return w1 + __shfl_xor_sync(0xffffffffu, w1, 1);
+}
+
+// dz pair (bf16x2) = bf16(da pair) * leaky'(a pair): slope = 1 where a > 0, alpha elsewhere
+__device__ __forceinline__ uint32_t dz_pack(float lo, float hi, uint32_t a_pair, __nv_bfloat162 one_m_alpha2, __nv_bfloat162 alpha2) {
+  const __nv_bfloat162 zero2 = __float2bfloat162_rn(0.f);
+  const __nv_bfloat162 s = __hfma2(__hgt2(u32_as_bf2(a_pair), zero2), one_m_alpha2, alpha2);   // (a > 0) * (1 - alpha) + alpha
+  return bf2_as_u32(__hmul2(__floats2bfloat162_rn(lo, hi), s));
+}
+
+// optional stage timeline of tile group 0 of CTA 0 (GJ_TRACE=4): 16 clock stamps per tile
+__device__ long long g_b2_trace[16 * 128];
+#define B2_STAMP(s) do { if (TRACE && blockIdx.x == 0 && tid == 0 && tr_n < 128) g_b2_trace[tr_n * 16 + (s)] = clock64(); } while (0)
+
+template <int E0, int E1, int E2, int E3, int NWG, bool TRACE>
+__global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args A) {
+  static_assert(E0 == 32 && E1 == 128 && E2 == 64 && E3 == 16, "TMEM / stage map is laid out for the 32-128-64-16 edge network");
+  static_assert(NWG <= 3, "three 128-column slots + 128 gradient columns");
+  using S = Bwd2Smem<E0, E1, E2, E3, NWG>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  constexpr int NT = NWG * 128;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = (int)uni((uint32_t)(tid >> 5));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::o_bar);      // [g][2]: done, done2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::o_slot);
+  float* s_b1 = reinterpret_cast<float*>(smem + S::o_f32);
+  float* s_b2 = s_b1 + E1;
+  float* s_b3 = s_b2 + E2;
+  float* s_wd = s_b3 + E3;
+  float* s_red = reinterpret_cast<float*>(smem + S::o_red);
+
+  // ---- one-time staging ----
+  stage_weight_kmajor<E1, E0>(smem + S::o_w1, A.params + A.pW1, tid, NT);
+  stage_weight_kmajor<E2, E1>(smem + S::o_w2, A.params + A.pW2, tid, NT);
+  stage_weight_kmajor<E3, E2>(smem + S::o_w3, A.params + A.pW3, tid, NT);
+  for (int c = tid; c < E1; c += NT) s_b1[c] = __ldg(A.params + A.pb1 + c);
+  for (int c = tid; c < E2; c += NT) s_b2[c] = __ldg(A.params + A.pb2 + c);
+  for (int c = tid; c < E3; c += NT) s_b3[c] = __ldg(A.params + A.pb3 + c);
+  for (int c = tid; c < E0; c += NT) s_wd[c] = __ldg(A.params + A.pWd + c * A.K0);
+  for (int idx = tid; idx < 64; idx += NT) reinterpret_cast<uint32_t*>(smem + S::o_ones)[idx] = 0x3F803F80u;
+  for (int idx = tid; idx < NWG * 512; idx += NT) {      // ones slab of every group: channel 32 = 1.0, channels 33..39 = 0
+    const int g = idx / 512, w = idx - g * 512;
+    reinterpret_cast<uint32_t*>(smem + S::o_grp + g * S::grp_bytes + S::g_ones)[w] = (w & 3) == 0 ? 0x00003F80u : 0u;
+  }
+  for (int idx = tid; idx < NWG * (E3 / 8) * 512; idx += NT) {      // dz3 slabs start finite (they are read by the first wgrad1)
+    const int g = idx / ((E3 / 8) * 512), w = idx - g * ((E3 / 8) * 512);
+    reinterpret_cast<uint32_t*>(smem + S::o_grp + g * S::grp_bytes + S::g_d3)[w] = 0u;
+  }
+  if (tid == 0) {
+    for (int g = 0; g < 2 * NWG; ++g) mbar_init(bars + g, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (warp < 4) {      // the shared gradient accumulators start at zero: every weight-gradient MMA accumulates
+    uint32_t z[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) z[c] = 0u;
+#pragma unroll
+    for (int c0 = 0; c0 < 128; c0 += 16) tmem_st16(tmem_base + ((uint32_t)(warp * 32) << 16) + 384 + c0, z);
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  // tile ranges: group gidx owns tiles [T gidx / ngroups, T (gidx + 1) / ngroups) of the (group task k, i) list, k-major
+  const long long T = A.tiles_total;
+  const int N = A.N;
+  auto range_lo = [&](int g) { return g < A.ngroups ? (int)(T * g / A.ngroups) : (int)T; };
+
+  {
+    // =================================== compute tile groups ===================================
+    const int wg = warp >> 2, wq = warp & 3;
+    const int row = wq * 32 + lane;
+    uint64_t* done = bars + 2 * wg;
+    uint64_t* done2 = done + 1;
+    // ---- MMA operands of this group (warp-uniform) ----
+    const uint32_t w1a = smem_u32(smem + S::o_w1), w2a = smem_u32(smem + S::o_w2), w3a = smem_u32(smem + S::o_w3);
+    const uint32_t gba = smem_u32(smem + S::o_grp + wg * S::grp_bytes);
+    const uint32_t slot0 = tmem_base + (uint32_t)(wg * 128);
+    const uint32_t ones_a = smem_u32(smem + S::o_ones);
+    // One GEMM stage of the tile, issued by one warp of the group (all 32 lanes run this convergently; a single elected
+    // lane issues each tcgen05 instruction).  Forward B operands are K-major (N = out feature); the dgrad B operands are
+    // the same bytes viewed MN-major (N = in feature); weight-gradient operands are MN-major views (K = tile row).
+    auto issue_stage = [&](int stage) {
+      tc_fence_after();
+      if (stage == 0) {
+        const uint64_t dA0k = make_smem_desc(gba + S::g_a0, 2048, 128), dW1f = wdesc_kmajor(w1a, E1);
+        const uint32_t idesc = make_idesc_bf16(128, E1, 0, 0);
+#pragma unroll
+        for (int s = 0; s < E0 / 16; ++s) mma_bf16_ss_elect(slot0, dA0k + (uint64_t)(s * 256), dW1f + (uint64_t)(s * 2 * E1), idesc, s > 0);
+        mma_commit_elect(done);
+      } else if (stage == 1) {
+        const uint64_t dW2f = wdesc_kmajor(w2a, E2);
+        const uint32_t idesc = make_idesc_bf16(128, E2, 0, 0);
+#pragma unroll
+        for (int s = 0; s < E1 / 16; ++s) mma_ts_elect(slot0 + 64, slot0 + 8 * s, dW2f + (uint64_t)(s * 2 * E2), idesc, s > 0);
+        mma_commit_elect(done);
+      } else if (stage == 2) {
+        const uint64_t dW3f = wdesc_kmajor(w3a, E3);
+        const uint32_t idesc = make_idesc_bf16(128, E3, 0, 0);
+#pragma unroll
+        for (int s = 0; s < E2 / 16; ++s) mma_ts_elect(slot0 + 32, slot0 + 8 * s, dW3f + (uint64_t)(s * 2 * E3), idesc, s > 0);
+        mma_commit_elect(done);
+      } else if (stage == 3) {
+        // dgrad3: acc[64,128) = dz3 (TMEM [48,56)) W3 ; wgrad3: dW3 += a2^T dz3
+        const uint64_t dW3b = make_smem_desc(w3a, 128, E3 * 16);
+        const uint64_t dX2n = make_smem_desc(gba + S::g_x2, 128, 2048), dD3n = make_smem_desc(gba + S::g_d3, 128, 2048);
+        mma_ts_elect(slot0 + 64, slot0 + 48, dW3b, make_idesc_bf16(128, E2, 0, 1), 0u);
+        const uint32_t idesc = make_idesc_bf16(64, E3, 1, 1);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) mma_bf16_ss_elect(tmem_base + 496, dX2n + (uint64_t)(s * 16), dD3n + (uint64_t)(s * 16), idesc, 1u);
+        mma_commit_elect(done);
+      } else if (stage == 4) {
+        // dgrad2: acc[0,128) = dz2 W2 ; wgrad2: dW2 += a1^T dz2 ; db2 += dz2^T 1
+        const uint64_t dW2b = make_smem_desc(w2a, 128, E2 * 16);
+        const uint64_t dX2k = make_smem_desc(gba + S::g_x2, 2048, 128), dX2n = make_smem_desc(gba + S::g_x2, 128, 2048);
+        const uint64_t dX1n = make_smem_desc(gba + S::g_x1, 128, 2048), dOnes = make_smem_desc(ones_a, 128, 128);
+        const uint32_t i_d2 = make_idesc_bf16(128, E1, 0, 1), i_g2 = make_idesc_bf16(128, E2, 1, 1), i_c2 = make_idesc_bf16(64, 8, 1, 0);
+#pragma unroll
+        for (int s = 0; s < E2 / 16; ++s) mma_bf16_ss_elect(slot0, dX2k + (uint64_t)(s * 256), dW2b + (uint64_t)(s * 16), i_d2, s > 0);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) mma_bf16_ss_elect(tmem_base + 432, dX1n + (uint64_t)(s * 16), dX2n + (uint64_t)(s * 16), i_g2, 1u);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) mma_bf16_ss_elect(tmem_base + 496 + (16u << 16), dX2n + (uint64_t)(s * 16), dOnes, i_c2, 1u);
+        mma_commit_elect(done);
+      } else {
+        // dgrad1: acc[64,96) = dz1 (TMEM [0,64)) W1 ; then [dW1 | db1] += dz1^T [a0 | 1] behind the epilogue
+        const uint64_t dW1b = make_smem_desc(w1a, 128, E1 * 16);
+        const uint64_t dX1n = make_smem_desc(gba + S::g_x1, 128, 2048), dA0n = make_smem_desc(gba + S::g_a0, 128, 2048);
+        const uint32_t i_d1 = make_idesc_bf16(128, E0, 0, 1), i_g1 = make_idesc_bf16(128, E0 + 16, 1, 1);
+#pragma unroll
+        for (int s = 0; s < E1 / 16; ++s) mma_ts_elect(slot0 + 64, slot0 + 8 * s, dW1b + (uint64_t)(s * 16), i_d1, s > 0);
+        mma_commit_elect(done);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) mma_bf16_ss_elect(tmem_base + 384, dX1n + (uint64_t)(s * 16), dA0n + (uint64_t)(s * 16), i_g1, 1u);
+        mma_commit_elect(done2);
+      }
+    };
+    // all four warps have written (and fenced) their operands -> the stage's issuing warp launches the GEMMs
+    auto publish = [&](int stage) {
+      tc_fence_before();
+      named_bar_sync(1 + wg, 128);
+      if (wq == (stage & 3)) issue_stage(stage);
+    };
+    const uint32_t slot = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(wg * 128);
+    uint8_t* gb = smem + S::o_grp + wg * S::grp_bytes;
+    uint8_t* a0_row = gb + S::g_a0 + row * 16;
+    uint8_t* d3_row = gb + S::g_d3 + row * 16;
+    uint8_t* x1_row = gb + S::g_x1 + row * 16;
+    uint8_t* x2_row = gb + S::g_x2 + row * 16;
+    float* s_pi = reinterpret_cast<float*>(smem + S::o_warp + warp * S::warp_bytes);      // [2][B2_IC][E0]
+    const __nv_bfloat162 alpha2 = __float2bfloat162_rn(A.alpha);
+    const __nv_bfloat162 oma2 = __float2bfloat162_rn(1.f - A.alpha);
+    const float alpha = A.alpha;
+    const int gidx = blockIdx.x * NWG + wg;
+    const int g0 = range_lo(gidx), g1 = range_lo(gidx + 1);
+    const int ntasks = A.B * A.NJB;
+    int k = g0 / N, i = g0 - k * N;
+    bool fresh = true, active = false, valid = false;
+    size_t node0 = 0;
+    int jb = 0;
+    float q[E0], dq[E0], dwd[E0], db3[E3];
+#pragma unroll
+    for (int c = 0; c < E0; ++c) { dwd[c] = 0.f; dq[c] = 0.f; q[c] = 0.f; }
+#pragma unroll
+    for (int c = 0; c < E3; ++c) db3[c] = 0.f;
+    float d_cur = 0.f;
+    uint32_t ph = 0, ph2 = 0;
+    bool pending2 = false;
+    int tr_n = 0;
+
+    auto stage_chunk = [&](int c) {      // P_i of i in [c * B2_IC, ...) -> buffer c & 1
+      const int ib = c * B2_IC, n = min(B2_IC, N - ib);
+      float* dst = s_pi + (c & 1) * B2_IC * E0;
+      for (int idx = lane; idx < n * (E0 / 4); idx += 32) {
+        const int r = idx / (E0 / 4), c4 = idx - r * (E0 / 4);
+        cp_async16(dst + r * E0 + 4 * c4, A.pq + (node0 + ib + r) * (2 * E0) + 4 * c4);
+      }
+      cp_async_commit();
+    };
+    auto flush_dq = [&]() {      // dQ_j of the (jet, j block) just finished (at most two groups add into one row)
+      if (valid) {
+        float* dst = A.dpq + (node0 + jb * 32 + lane) * (2 * E0) + E0;
+#pragma unroll
+        for (int c = 0; c < E0; ++c) atomicAdd(dst + c, dq[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < E0; ++c) dq[c] = 0.f;
+    };
+
+    for (int g = g0; g < g1; ++g) {
+      B2_STAMP(0);
+      if (fresh) {
+        const int task = 4 * k + wq;
+        active = task < ntasks;
+        const int tk = active ? task : 0;
+        const int jet = tk / A.NJB;
+        jb = tk - jet * A.NJB;
+        const int j = jb * 32 + lane;
+        valid = active && j < N;
+        node0 = (size_t)jet * N;
+        cp_async_wait<0>();
+        __syncwarp();
+        stage_chunk(i / B2_IC);
+        if ((i / B2_IC + 1) * B2_IC < N) stage_chunk(i / B2_IC + 1);
+        if (j < N) {
+          const float4* src = reinterpret_cast<const float4*>(A.pq + (node0 + j) * (2 * E0) + E0);
+#pragma unroll
+          for (int c = 0; c < E0 / 4; ++c) { const float4 v = __ldg(src + c); q[4 * c] = v.x; q[4 * c + 1] = v.y; q[4 * c + 2] = v.z; q[4 * c + 3] = v.w; }
+        } else {
+#pragma unroll
+          for (int c = 0; c < E0; ++c) q[c] = 0.f;
+        }
+        d_cur = __ldg(A.d + (node0 + i) * A.NJ32 + jb * 32 + lane);
+        if ((i / B2_IC + 1) * B2_IC < N) cp_async_wait<1>(); else cp_async_wait<0>();
+        __syncwarp();
+        fresh = false;
+      } else if ((i % B2_IC) == 0) {
+        cp_async_wait<0>();
+        __syncwarp();
+        if ((i / B2_IC + 1) * B2_IC < N) stage_chunk(i / B2_IC + 1);
+      }
+      // de_i (warp-uniform address) for the F3 epilogue and next tile's d_ij: issued now, consumed much later
+      float4 de4[E3 / 4];
+      {
+        const float4* dsrc = reinterpret_cast<const float4*>(A.de + (node0 + i) * E3);
+#pragma unroll
+        for (int c = 0; c < E3 / 4; ++c) de4[c] = __ldg(dsrc + c);
+      }
+      const bool last_i = (i + 1 == N);
+      const float d_next = (!last_i) ? __ldg(A.d + (node0 + i + 1) * A.NJ32 + jb * 32 + lane) : 0.f;
+      const float dij = d_cur;
+
+      // ---- L0: a0 -> shared A0 (needs the previous tile's wgrad1, which reads A0, to have completed) ----
+      if (pending2) { mbar_wait(done2, ph2); ph2 ^= 1u; }
+      B2_STAMP(1);
+      {
+        const float* Pi = s_pi + (((i / B2_IC) & 1) * B2_IC + (i % B2_IC)) * E0;
+        const float2 d2 = make_float2(dij, dij);
+#pragma unroll
+        for (int c = 0; c < E0; c += 8) {
+          uint32_t o[4];
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int cc = c + 4 * hh;
+            const float4 p = *reinterpret_cast<const float4*>(Pi + cc);
+            const float4 w = *reinterpret_cast<const float4*>(s_wd + cc);
+            const float2 z0 = fma2(make_float2(w.x, w.y), d2, add2(make_float2(p.x, p.y), make_float2(q[cc], q[cc + 1])));
+            const float2 z1 = fma2(make_float2(w.z, w.w), d2, add2(make_float2(p.z, p.w), make_float2(q[cc + 2], q[cc + 3])));
+            o[2 * hh] = leaky_pack(z0.x, z0.y, alpha2);
+            o[2 * hh + 1] = leaky_pack(z1.x, z1.y, alpha2);
+          }
+          *reinterpret_cast<uint4*>(a0_row + (c >> 3) * 2048) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        fence_proxy_async();
+        publish(0);
+      }
+      B2_STAMP(2);
+
+      // ---- F1 epilogue: a1 = leaky(acc + b1) -> TMEM [0,64) + shared X1 ----
+      mbar_wait(done, ph); ph ^= 1u;
+      tc_fence_after();
+      B2_STAMP(3);
+      {
+        uint32_t va[16], vb[16];
+        tmem_ld16_u(slot, va);
+#pragma unroll
+        for (int ch = 0; ch < E1 / 16; ch += 2) {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t (&v)[16] = half == 0 ? va : vb;
+            uint32_t (&vn)[16] = half == 0 ? vb : va;
+            const int cc = ch + half;
+            tmem_ld_wait(); tmem_pin16(v);
+            if (cc + 1 < E1 / 16) tmem_ld16_u(slot + (uint32_t)((cc + 1) * 16), vn);
+            uint32_t o[8];
+#pragma unroll
+            for (int p4 = 0; p4 < 4; ++p4) {
+              const float4 b = *reinterpret_cast<const float4*>(s_b1 + cc * 16 + 4 * p4);
+              o[2 * p4] = leaky_pack(__uint_as_float(v[4 * p4]) + b.x, __uint_as_float(v[4 * p4 + 1]) + b.y, alpha2);
+              o[2 * p4 + 1] = leaky_pack(__uint_as_float(v[4 * p4 + 2]) + b.z, __uint_as_float(v[4 * p4 + 3]) + b.w, alpha2);
+            }
+            tmem_st8(slot + (uint32_t)(cc * 8), o);
+            *reinterpret_cast<uint4*>(x1_row + (2 * cc) * 2048) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4*>(x1_row + (2 * cc + 1) * 2048) = make_uint4(o[4], o[5], o[6], o[7]);
+          }
+        }
+        tmem_st_wait();
+        fence_proxy_async();
+        publish(1);
+      }
+      B2_STAMP(4);
+
+      // ---- F2 epilogue: a2 = leaky(acc[64,128) + b2) -> TMEM [0,32) + shared X2 ----
+      mbar_wait(done, ph); ph ^= 1u;
+      tc_fence_after();
+      B2_STAMP(5);
+      {
+        uint32_t va[16], vb[16];
+        tmem_ld16_u(slot + 64, va);
+#pragma unroll
+        for (int ch = 0; ch < E2 / 16; ch += 2) {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t (&v)[16] = half == 0 ? va : vb;
+            uint32_t (&vn)[16] = half == 0 ? vb : va;
+            const int cc = ch + half;
+            tmem_ld_wait(); tmem_pin16(v);
+            if (cc + 1 < E2 / 16) tmem_ld16_u(slot + 64 + (uint32_t)((cc + 1) * 16), vn);
+            uint32_t o[8];
+#pragma unroll
+            for (int p4 = 0; p4 < 4; ++p4) {
+              const float4 b = *reinterpret_cast<const float4*>(s_b2 + cc * 16 + 4 * p4);
+              o[2 * p4] = leaky_pack(__uint_as_float(v[4 * p4]) + b.x, __uint_as_float(v[4 * p4 + 1]) + b.y, alpha2);
+              o[2 * p4 + 1] = leaky_pack(__uint_as_float(v[4 * p4 + 2]) + b.z, __uint_as_float(v[4 * p4 + 3]) + b.w, alpha2);
+            }
+            tmem_st8(slot + (uint32_t)(cc * 8), o);
+            *reinterpret_cast<uint4*>(x2_row + (2 * cc) * 2048) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4*>(x2_row + (2 * cc + 1) * 2048) = make_uint4(o[4], o[5], o[6], o[7]);
+          }
+        }
+        tmem_st_wait();
+        fence_proxy_async();
+        publish(2);
+      }
+      B2_STAMP(6);
+
+      // ---- F3 epilogue: dz3 = de_i * leaky'(acc[32,48) + b3), zero on padded rows -> TMEM [48,56) + shared D3 ----
+      mbar_wait(done, ph); ph ^= 1u;
+      tc_fence_after();
+      B2_STAMP(7);
+      {
+        uint32_t v[16];
+        tmem_ld16_u(slot + 32, v);
+        tmem_ld_wait(); tmem_pin16(v);
+        const float* def = reinterpret_cast<const float*>(de4);
+        uint32_t o[8];
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+          const float z0 = __uint_as_float(v[2 * p]) + s_b3[2 * p], z1 = __uint_as_float(v[2 * p + 1]) + s_b3[2 * p + 1];
+          const float g0v = valid ? def[2 * p] * (z0 > 0.f ? 1.f : alpha) : 0.f;
+          const float g1v = valid ? def[2 * p + 1] * (z1 > 0.f ? 1.f : alpha) : 0.f;
+          db3[2 * p] += g0v; db3[2 * p + 1] += g1v;
+          o[p] = bf2_as_u32(__floats2bfloat162_rn(g0v, g1v));
+        }
+        tmem_st8(slot + 48, o);
+        *reinterpret_cast<uint4*>(d3_row) = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4*>(d3_row + 2048) = make_uint4(o[4], o[5], o[6], o[7]);
+        tmem_st_wait();
+        fence_proxy_async();
+        publish(3);
+      }
+      B2_STAMP(8);
+
+      // ---- B3 epilogue: dz2 = acc[64,128) * leaky'(a2) -> shared X2, in place over a2 (signs from TMEM [0,32)) ----
+      mbar_wait(done, ph); ph ^= 1u;
+      tc_fence_after();
+      B2_STAMP(9);
+      {
+        uint32_t va[16], vb[16], sa[8], sb[8];
+        tmem_ld16_u(slot + 64, va);
+        tmem_ld8_u(slot, sa);
+#pragma unroll
+        for (int ch = 0; ch < E2 / 16; ch += 2) {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t (&v)[16] = half == 0 ? va : vb;
+            uint32_t (&vn)[16] = half == 0 ? vb : va;
+            uint32_t (&sg)[8] = half == 0 ? sa : sb;
+            uint32_t (&sn)[8] = half == 0 ? sb : sa;
+            const int cc = ch + half;
+            tmem_ld_wait(); tmem_pin16(v); tmem_pin8(sg);
+            if (cc + 1 < E2 / 16) { tmem_ld16_u(slot + 64 + (uint32_t)((cc + 1) * 16), vn); tmem_ld8_u(slot + (uint32_t)((cc + 1) * 8), sn); }
+            uint32_t o[8];
+#pragma unroll
+            for (int p = 0; p < 8; ++p) o[p] = dz_pack(__uint_as_float(v[2 * p]), __uint_as_float(v[2 * p + 1]), sg[p], oma2, alpha2);
+            *reinterpret_cast<uint4*>(x2_row + (2 * cc) * 2048) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4*>(x2_row + (2 * cc + 1) * 2048) = make_uint4(o[4], o[5], o[6], o[7]);
+          }
+        }
+        fence_proxy_async();
+        publish(4);
+      }
+      B2_STAMP(10);
+
+      // ---- B2 epilogue: dz1 = acc[0,128) * leaky'(a1) -> TMEM [0,64) + shared X1, in place over a1 ----
+      mbar_wait(done, ph); ph ^= 1u;
+      tc_fence_after();
+      B2_STAMP(11);
+      {
+        uint32_t va[16], vb[16];
+        tmem_ld16_u(slot, va);
+#pragma unroll
+        for (int ch = 0; ch < E1 / 16; ch += 2) {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t (&v)[16] = half == 0 ? va : vb;
+            uint32_t (&vn)[16] = half == 0 ? vb : va;
+            const int cc = ch + half;
+            const uint4 s0 = *reinterpret_cast<const uint4*>(x1_row + (2 * cc) * 2048);
+            const uint4 s1 = *reinterpret_cast<const uint4*>(x1_row + (2 * cc + 1) * 2048);
+            const uint32_t sg[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+            tmem_ld_wait(); tmem_pin16(v);
+            if (cc + 1 < E1 / 16) tmem_ld16_u(slot + (uint32_t)((cc + 1) * 16), vn);
+            uint32_t o[8];
+#pragma unroll
+            for (int p = 0; p < 8; ++p) o[p] = dz_pack(__uint_as_float(v[2 * p]), __uint_as_float(v[2 * p + 1]), sg[p], oma2, alpha2);
+            tmem_st8(slot + (uint32_t)(cc * 8), o);
+            *reinterpret_cast<uint4*>(x1_row + (2 * cc) * 2048) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4*>(x1_row + (2 * cc + 1) * 2048) = make_uint4(o[4], o[5], o[6], o[7]);
+          }
+        }
+        tmem_st_wait();
+        fence_proxy_async();
+        publish(5);
+      }
+      B2_STAMP(12);
+
+      // ---- B1 epilogue: dz0 = acc[64,96) * leaky'(a0) in fp32 -> dP_i, dQ_j, d(wd), G_ij ----
+      mbar_wait(done, ph); ph ^= 1u;
+      tc_fence_after();
+      pending2 = true;
+      B2_STAMP(13);
+      {
+        float gsum = 0.f;
+        float* dp_dst = A.NJB > 1 ? A.dp_part + ((size_t)jb * A.B * N + node0 + i) * E0 : A.dpq + (node0 + i) * (2 * E0);
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t v[16];
+          tmem_ld16_u(slot + 64 + 16 * hf, v);
+          const uint4 s0 = *reinterpret_cast<const uint4*>(a0_row + (2 * hf) * 2048);
+          const uint4 s1 = *reinterpret_cast<const uint4*>(a0_row + (2 * hf + 1) * 2048);
+          const uint32_t sg[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+          tmem_ld_wait(); tmem_pin16(v);
+          float z[16];
+#pragma unroll
+          for (int p = 0; p < 8; ++p) {
+            // bf16 pair: low half = even channel.  a > 0  <=>  sign bit clear and not zero (a0 == 0 only if z == 0)
+            const float alo = __uint_as_float(sg[p] << 16), ahi = __uint_as_float(sg[p] & 0xffff0000u);
+            z[2 * p] = __uint_as_float(v[2 * p]) * (alo > 0.f ? 1.f : alpha);
+            z[2 * p + 1] = __uint_as_float(v[2 * p + 1]) * (ahi > 0.f ? 1.f : alpha);
+          }
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const float4 w = *reinterpret_cast<const float4*>(s_wd + 16 * hf + 4 * c4);
+            gsum = fmaf(z[4 * c4], w.x, gsum); gsum = fmaf(z[4 * c4 + 1], w.y, gsum);
+            gsum = fmaf(z[4 * c4 + 2], w.z, gsum); gsum = fmaf(z[4 * c4 + 3], w.w, gsum);
+          }
+#pragma unroll
+          for (int c = 0; c < 16; ++c) { dq[16 * hf + c] += z[c]; dwd[16 * hf + c] = fmaf(z[c], dij, dwd[16 * hf + c]); }
+          const float s = warp_transpose_sum16(z, lane);
+          if (active && (lane & 1) == 0) dp_dst[16 * hf + (lane >> 1)] = s;
+        }
+        if (active) A.G[(node0 + i) * A.NJ32 + jb * 32 + lane] = valid ? gsum : 0.f;
+      }
+      tc_fence_before();
+      B2_STAMP(14);
+      ++tr_n;
+      d_cur = d_next;
+      if (++i == N) { flush_dq(); i = 0; ++k; fresh = true; }
+    }
+    if (!fresh) flush_dq();      // the group's last (jet, j block) ended mid-way: the next group adds the rest
+    if (pending2) { mbar_wait(done2, ph2); ph2 ^= 1u; }      // all of this group's MMAs have completed
+    cp_async_wait<0>();
+    // d(wd), db3: lanes by shuffles, warps through shared memory (fixed order)
+#pragma unroll
+    for (int c = 0; c < E0; ++c) { const float s = gj_warp_sum(dwd[c]); if (lane == 0) s_red[warp * (E0 + E3) + c] = s; }
+#pragma unroll
+    for (int c = 0; c < E3; ++c) { const float s = gj_warp_sum(db3[c]); if (lane == 0) s_red[warp * (E0 + E3) + E0 + c] = s; }
+  }
+
+  // =================================== gradient read-out ===================================
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  float* out = A.part + (size_t)blockIdx.x * A.nedge;
+  const bool wrote = range_lo(blockIdx.x * NWG + 1) > range_lo(blockIdx.x * NWG);      // group 0 of this CTA had tiles
+  if (tid < E0 + E3) {
+    float s = 0.f;
+    for (int w = 0; w < NWG * 4; ++w) s += s_red[w * (E0 + E3) + tid];
+    if (tid < E0) out[A.pWd + tid * A.K0] = s;
+    else out[A.pb3 + tid - E0] = s;
+  }
+  if (warp < 4) {
+    const uint32_t lb = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int m = warp * 32 + lane;
+    // dW1 (lane = out feature, column = in feature), db1 = column 32
+    for (int c0 = 0; c0 < 48; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16_u(lb + 384 + c0, v);
+      tmem_ld_wait(); tmem_pin16(v);
+      if (c0 < 32) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) out[A.pW1 + m * E0 + c0 + c] = wrote ? __uint_as_float(v[c]) : 0.f;
+      } else {
+        out[A.pb1 + m] = wrote ? __uint_as_float(v[0]) : 0.f;
+      }
+    }
+    // dW2 (lane = in feature, column = out feature)
+    for (int c0 = 0; c0 < E2; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16_u(lb + 432 + c0, v);
+      tmem_ld_wait(); tmem_pin16(v);
+#pragma unroll
+      for (int c = 0; c < 16; ++c) out[A.pW2 + (c0 + c) * E1 + m] = wrote ? __uint_as_float(v[c]) : 0.f;
+    }
+    // dW3 (M = 64: in feature k at lane (k / 16) * 32 + k % 16) and db2 (same columns, lanes + 16)
+    {
+      uint32_t v[16];
+      tmem_ld16_u(lb + 496, v);
+      tmem_ld_wait(); tmem_pin16(v);
+      if (lane < 16) {
+        const int kf = warp * 16 + lane;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) out[A.pW3 + c * E2 + kf] = wrote ? __uint_as_float(v[c]) : 0.f;
+      } else {
+        out[A.pb2 + warp * 16 + lane - 16] = wrote ? __uint_as_float(v[0]) : 0.f;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+// P-half of dpq from the per-j-block partials (N > 32), fixed order
+__global__ void sum_dp_parts_kernel(const float* __restrict__ part, int njb, size_t rows, int E0, float* __restrict__ dpq) {
+  const size_t n = rows * E0;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int b = 0; b < njb; ++b) s += part[(size_t)b * n + idx];
+    const size_t r = idx / E0, c = idx - r * E0;
+    dpq[r * 2 * E0 + c] = s;
+  }
+}
+
+// ---- pair distances (node level, O(N^2 H) per jet): d_ij = metric(h_j - h_i) and its adjoint ----
+// d (B, N, NJ32): row i of jet b at (b N + i) NJ32, columns j >= N are zero
+__global__ void pair_dist_fwd_kernel(const float* __restrict__ h, int rows, int N, int NJ32, int cols, int ld, int mink,
+                                     float* __restrict__ d) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
+    const int b = r / N;
+    const float* hi = h + (size_t)r * ld;
+    for (int j = lane; j < NJ32; j += 32) {
+      float acc = 0.f;
+      if (j < N) {
+        const float* hj = h + ((size_t)b * N + j) * ld;
+        for (int k = 0; k < cols; ++k) {
+          const float x = __ldg(hj + k) - __ldg(hi + k);
+          acc = (mink && k > 0) ? fmaf(-x, x, acc) : fmaf(x, x, acc);
+        }
+      }
+      d[(size_t)r * NJ32 + j] = acc;
+    }
+  }
+}
+// dh[n][k] += 2 s_k sum_m (G[m][n] + G[n][m]) (h[n][k] - h[m][k]),  s_k = -1 for the minkowskian space components
+__global__ void pair_dist_bwd_kernel(const float* __restrict__ h, const float* __restrict__ G, int N, int NJ32, int cols, int ld,
+                                     int mink, float* __restrict__ dh) {
+  extern __shared__ float pd_smem[];
+  float* sh = pd_smem;                  // [N][cols]
+  float* sS = pd_smem + N * cols;       // [N][N + 1]: S[n][m] = G[m][n] + G[n][m]
+  const int b = blockIdx.x;
+  for (int idx = threadIdx.x; idx < N * cols; idx += blockDim.x) {
+    const int n = idx / cols, k = idx - n * cols;
+    sh[idx] = __ldg(h + ((size_t)b * N + n) * ld + k);
+  }
+  const float* Gb = G + (size_t)b * N * NJ32;
+  for (int idx = threadIdx.x; idx < N * N; idx += blockDim.x) {
+    const int n = idx / N, m = idx - n * N;
+    sS[n * (N + 1) + m] = __ldg(Gb + (size_t)n * NJ32 + m);
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < N * cols; idx += blockDim.x) {
+    const int n = idx / cols, k = idx - n * cols;
+    const float hn = sh[idx];
+    float acc = 0.f;
+    for (int m = 0; m < N; ++m) acc = fmaf(sS[n * (N + 1) + m] + sS[m * (N + 1) + n], hn - sh[m * cols + k], acc);
+    const float sgn = (mink && k > 0) ? -2.f : 2.f;
+    dh[((size_t)b * N + n) * ld + k] += sgn * acc;
+  }
+}
+
+}  // namespace
+
+int gj_num_sms();
+void gj_set_error(const char* fmt, ...);
+int gj_reduce_edge_partials(const MPLayout& L, const float* part, int nparts, float* dparams, cudaStream_t stream);
+
+// debugging aid (not part of the ABI header): stage timeline of the last traced backward launch
+extern "C" int gj_debug_read_bwd2_trace(long long* out) {
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(out, g_b2_trace, sizeof(long long) * 16 * 128) == cudaSuccess ? 0 : 1;
+}
+
+bool gj_bwd2_supported(const MPLayout& L) {
+  const int pd_smem = (L.N * L.cols + L.N * (L.N + 1)) * 4;
+  return L.Le == 4 && L.E[0] == 32 && L.E[1] == 128 && L.E[2] == 64 && L.E[3] == 16 && L.alpha <= 1.f && pd_smem <= 200 * 1024;
+}
+
+static int bwd2_grid(const MPLayout& L) { return gj_num_sms(); }
+
+// workspace (floats): d | G (B N NJ32 each) | dP partials (NJB > 1) | per-CTA parameter-gradient partials
+size_t gj_bwd2_ws_floats(const MPLayout& L) {
+  const size_t njb = (L.N + 31) / 32, rows = (size_t)L.B * L.N;
+  size_t n = 2 * rows * njb * 32 + 64;
+  if (njb > 1) n += njb * rows * L.E[0] + 64;
+  n += (size_t)bwd2_grid(L) * L.pV[0] + 64;
+  return n;
+}
+
+int gj_pair_dist_fwd(const MPLayout& L, const float* h, float* d, cudaStream_t stream) {
+  const int rows = L.B * L.N, NJ32 = ((L.N + 31) / 32) * 32;
+  int blocks = (rows + 7) / 8; if (blocks > 8 * gj_num_sms()) blocks = 8 * gj_num_sms();
+  pair_dist_fwd_kernel<<<blocks, 256, 0, stream>>>(h, rows, L.N, NJ32, L.cols, L.ld, L.mink, d);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) { gj_set_error("pair_dist_fwd launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
+  return GJ_OK;
+}
+
+int gj_edge_bwd2(const MPLayout& L, const float* h, const float* pq, const float* params, const float* de, float* dpq, float* dh,
+                 float* dparams, float* ws, cudaStream_t stream) {
+  constexpr int NWG = 3;
+  using S = Bwd2Smem<32, 128, 64, 16, NWG>;
+  static_assert(S::total <= 227 * 1024, "backward shared-memory plan exceeds the 227 KB budget");
+  Bwd2Args A;
+  const size_t njb = (L.N + 31) / 32, rows = (size_t)L.B * L.N;
+  const int NJ32 = (int)njb * 32;
+  float* d = ws;
+  float* G = d + rows * NJ32 + 32;
+  float* dp_part = G + rows * NJ32 + 32;
+  float* part = njb > 1 ? dp_part + njb * rows * L.E[0] + 64 : dp_part;
+  A.pq = pq; A.d = d; A.params = params; A.de = de; A.dpq = dpq; A.dp_part = dp_part; A.G = G; A.part = part;
+  A.B = L.B; A.N = L.N; A.NJB = (int)njb; A.NJ32 = NJ32;
+  A.pW1 = L.pW[1]; A.pb1 = L.pb[1]; A.pW2 = L.pW[2]; A.pb2 = L.pb[2]; A.pW3 = L.pW[3]; A.pb3 = L.pb[3];
+  A.pWd = L.pW[0] + 2 * L.H; A.K0 = L.K[0]; A.nedge = L.pV[0];
+  A.alpha = L.alpha;
+  const long long tasks4 = ((long long)L.B * A.NJB + 3) / 4;
+  if (tasks4 * L.N > 0x7fffffffLL) { gj_set_error("gj_mp_step_bwd(bf16): batch * nodes too large"); return GJ_ERR_INVALID; }
+  A.tiles_total = (int)(tasks4 * L.N);
+  const int grid = bwd2_grid(L);
+  // every (jet, j block) is shared by at most two groups, so that the two-addend atomic dQ sums are order independent
+  long long ng = (long long)grid * NWG;
+  if (ng > tasks4) ng = tasks4;
+  A.ngroups = (int)(ng < 1 ? 1 : ng);
+  int rc = gj_pair_dist_fwd(L, h, d, stream);
+  if (rc) return rc;
+  cudaError_t ce = cudaMemsetAsync(dpq, 0, rows * 2 * L.E[0] * sizeof(float), stream);
+  if (ce != cudaSuccess) { gj_set_error("cudaMemsetAsync: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
+  static const int trace_env = getenv("GJ_TRACE") ? atoi(getenv("GJ_TRACE")) : 0;
+  auto kern = trace_env == 4 ? edge_bwd2_kernel<32, 128, 64, 16, NWG, true> : edge_bwd2_kernel<32, 128, 64, 16, NWG, false>;
+  ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::total);
+  if (ce != cudaSuccess) { gj_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
+  kern<<<grid, NWG * 128, S::total, stream>>>(A);
+  ce = cudaGetLastError();
+  if (ce != cudaSuccess) { gj_set_error("edge_bwd2 launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
+  if (njb > 1) {
+    int blocks = (int)((rows * L.E[0] + 255) / 256); if (blocks > 4 * gj_num_sms()) blocks = 4 * gj_num_sms();
+    sum_dp_parts_kernel<<<blocks, 256, 0, stream>>>(dp_part, (int)njb, rows, L.E[0], dpq);
+  }
+  {
+    const int pd_smem = (L.N * L.cols + L.N * (L.N + 1)) * 4;
+    ce = cudaFuncSetAttribute(pair_dist_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pd_smem);
+    if (ce != cudaSuccess) { gj_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
+    pair_dist_bwd_kernel<<<L.B, 256, pd_smem, stream>>>(h, G, L.N, NJ32, L.cols, L.ld, L.mink, dh);
+  }
+  ce = cudaGetLastError();
+  if (ce != cudaSuccess) { gj_set_error("edge_bwd2 tail launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
+  return gj_reduce_edge_partials(L, part, grid, dparams, stream);
+}

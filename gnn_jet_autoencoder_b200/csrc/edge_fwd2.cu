@@ -35,9 +35,7 @@ struct Fwd2Args {
   int tiles_total;       // ceil(B * NJB / 4) * N
 };
 
-constexpr int F2_IC = 32;          // i's staged per refill
-constexpr int F2_SLOT = 160;
-constexpr int F2_ONES_COL = 480;
+constexpr int F2_IC = 8;           // i's per staged P_i | h_i chunk (double buffered, cp.async)
 
 template <int E0, int E1, int E2, int E3, int NWG>
 struct Fwd2Smem {
@@ -50,8 +48,10 @@ struct Fwd2Smem {
   static constexpr int o_b1 = o_w3 + E3 * E2 * 2;
   static constexpr int o_b2 = o_b1 + E1 * 32;
   static constexpr int o_b3 = o_b2 + E2 * 32;
-  static constexpr int o_warp = ((o_b3 + E3 * 32 + 127) / 128) * 128;
-  __host__ __device__ static int warp_bytes(int Hb, int Hs) { return (F2_IC * (E0 + Hb) + 32 * Hs) * 4; }
+  static constexpr int o_ones = ((o_b3 + E3 * 32 + 127) / 128) * 128;      // [128 rows][16] constant A chunk of the bias k-step
+  static constexpr int o_a0 = o_ones + 4096;                               // NWG x [128 rows][E0] bf16, interleaved
+  static constexpr int o_warp = o_a0 + NWG * 128 * E0 * 2;
+  __host__ __device__ static int warp_bytes(int Hb, int Hs) { return (2 * F2_IC * (E0 + Hb) + 32 * Hs) * 4; }
   __host__ __device__ static int total(int Hb, int Hs) { return o_warp + NWG * 4 * warp_bytes(Hb, Hs); }
 };
 
@@ -84,32 +84,43 @@ __device__ __forceinline__ float warp_transpose_sum16(const float (&v)[16], int 
 }
 
 // epilogue of a hidden layer: NCOL fp32 accumulator columns at acc -> leaky -> NCOL/2 packed bf16 columns at dst
+// (16-column chunks, two register sets: the next chunk's TMEM load flies while the current one is processed)
 template <int NCOL>
 __device__ __forceinline__ void epilogue_hidden(uint32_t acc, uint32_t dst, __nv_bfloat162 alpha2) {
   static_assert(NCOL % 32 == 0, "hidden widths are multiples of 32");
-  constexpr int NCH = NCOL / 32;
-  uint32_t va[32], vb[32];
-  tmem_ld32_u(acc, va);
+  constexpr int NCH = NCOL / 16;
+  uint32_t va[16], vb[16];
+  tmem_ld16_u(acc, va);
 #pragma unroll
   for (int ch = 0; ch < NCH; ch += 2) {
-    tmem_ld_wait(); tmem_pin32(va);
-    if (ch + 1 < NCH) tmem_ld32_u(acc + (uint32_t)((ch + 1) * 32), vb);
+    tmem_ld_wait(); tmem_pin16(va);
+    tmem_ld16_u(acc + (uint32_t)((ch + 1) * 16), vb);
     {
-      uint32_t o[16];
+      uint32_t o[8];
 #pragma unroll
-      for (int p = 0; p < 16; ++p) o[p] = leaky_pack(__uint_as_float(va[2 * p]), __uint_as_float(va[2 * p + 1]), alpha2);
-      tmem_st16(dst + (uint32_t)(ch * 16), o);
+      for (int p = 0; p < 8; ++p) o[p] = leaky_pack(__uint_as_float(va[2 * p]), __uint_as_float(va[2 * p + 1]), alpha2);
+      tmem_st8(dst + (uint32_t)(ch * 8), o);
     }
-    if (ch + 1 < NCH) {
-      tmem_ld_wait(); tmem_pin32(vb);
-      if (ch + 2 < NCH) tmem_ld32_u(acc + (uint32_t)((ch + 2) * 32), va);
-      uint32_t o[16];
+    tmem_ld_wait(); tmem_pin16(vb);
+    if (ch + 2 < NCH) tmem_ld16_u(acc + (uint32_t)((ch + 2) * 16), va);
+    {
+      uint32_t o[8];
 #pragma unroll
-      for (int p = 0; p < 16; ++p) o[p] = leaky_pack(__uint_as_float(vb[2 * p]), __uint_as_float(vb[2 * p + 1]), alpha2);
-      tmem_st16(dst + (uint32_t)((ch + 1) * 16), o);
+      for (int p = 0; p < 8; ++p) o[p] = leaky_pack(__uint_as_float(vb[2 * p]), __uint_as_float(vb[2 * p + 1]), alpha2);
+      tmem_st8(dst + (uint32_t)((ch + 1) * 8), o);
     }
   }
 }
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // optional stage timeline of tile group 0 of CTA 0 (GJ_TRACE=3): 8 clock stamps per tile
 __device__ long long g_f2_trace[8 * 256];
@@ -117,8 +128,9 @@ __device__ long long g_f2_trace[8 * 256];
 
 template <int E0, int E1, int E2, int E3, int NWG, bool TRACE>
 __global__ void __launch_bounds__(NWG * 128, 1) edge_fwd2_kernel(const Fwd2Args A) {
-  static_assert(E0 == 32 && E3 == 16, "TMEM slot map assumes a 32-wide first and a 16-wide last edge layer");
-  static_assert(E1 % 32 == 0 && E1 <= 128 && E2 % 32 == 0 && E1 / 2 + E2 <= 128 && E2 / 2 <= E1 / 2, "TMEM slot map");
+  static_assert(E0 == 32 && E3 == 16, "tile map assumes a 32-wide first and a 16-wide last edge layer");
+  static_assert(E1 % 32 == 0 && E1 <= 128 && E2 % 32 == 0 && E1 / 2 + E2 <= 128 && E2 / 2 + E3 <= E1 / 2, "TMEM slot map");
+  static_assert(NWG * 128 <= 512, "one 128-column TMEM slot per tile group");
   using S = Fwd2Smem<E0, E1, E2, E3, NWG>;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, lane = tid & 31;
@@ -128,7 +140,7 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_fwd2_kernel(const Fwd2Args 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::o_slot);
   float* s_wd = reinterpret_cast<float*>(smem + S::o_wd);
 
-  // ---- one-time staging: weights / biases as bf16 B operands, wd, barriers, TMEM ----
+  // ---- one-time staging: weights / biases as bf16 B operands, wd, the constant bias A chunk, barriers, TMEM ----
   stage_weight_kmajor<E1, E0>(smem + S::o_w1, A.params + A.pW1, tid, NWG * 128);
   stage_weight_kmajor<E2, E1>(smem + S::o_w2, A.params + A.pW2, tid, NWG * 128);
   stage_weight_kmajor<E3, E2>(smem + S::o_w3, A.params + A.pW3, tid, NWG * 128);
@@ -136,6 +148,13 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_fwd2_kernel(const Fwd2Args 
   stage_bias_slab<E2>(smem + S::o_b2, A.params + A.pb2, tid, NWG * 128);
   stage_bias_slab<E3>(smem + S::o_b3, A.params + A.pb3, tid, NWG * 128);
   for (int c = tid; c < E0; c += NWG * 128) s_wd[c] = __ldg(A.params + A.pWd + c * A.K0);
+  for (int idx = tid; idx < 1024; idx += NWG * 128)     // ones chunk: k = 0, 1 -> 1.0 (bias hi + lo), k = 2..15 -> 0
+    reinterpret_cast<uint32_t*>(smem + S::o_ones)[idx] = (idx < 512 && (idx & 3) == 0) ? 0x3F803F80u : 0u;
+  {   // the staging rows' padding columns stay zero for the whole kernel
+    float* wz = reinterpret_cast<float*>(smem + S::o_warp);
+    const int nz = NWG * 4 * S::warp_bytes(A.Hb, A.Hs) / 4;
+    for (int idx = tid; idx < nz; idx += NWG * 128) wz[idx] = 0.f;
+  }
   if (tid == 0) {
     for (int b = 0; b < NWG * 3; ++b) mbar_init(reinterpret_cast<uint64_t*>(smem + S::o_bar) + b, 1);
     fence_barrier_init();
@@ -146,20 +165,12 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_fwd2_kernel(const Fwd2Args 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t lane_base = tmem_base + ((uint32_t)(wq * 32) << 16);
-  if (wg == 0) {     // constant bias A chunk: k = 0, 1 -> 1.0 (bias hi + lo), k = 2..15 -> 0
-    uint32_t ones[8] = {0x3F803F80u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-    tmem_st8(lane_base + F2_ONES_COL, ones);
-    tmem_st_wait();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-
-  const uint32_t slot = lane_base + (uint32_t)(wg * F2_SLOT);       // this thread's row of the group's slot
-  const uint32_t slot0 = tmem_base + (uint32_t)(wg * F2_SLOT);      // lane 0 (MMA operand addresses)
+  const uint32_t slot = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(wg * 128);   // this thread's row of the group's slot
+  const uint32_t slot0 = tmem_base + (uint32_t)(wg * 128);                                // lane 0 (MMA operand addresses)
   const __nv_bfloat162 alpha2 = __float2bfloat162_rn(A.alpha);
   const float alpha = A.alpha;
+  uint8_t* a0 = smem + S::o_a0 + wg * (128 * E0 * 2);
+  uint8_t* a0_row = a0 + (wq * 32 + lane) * 16;
 
   // MMA constants (warp-uniform)
   const uint32_t idesc1 = make_idesc_bf16(128, E1, 0, 0), idesc2 = make_idesc_bf16(128, E2, 0, 0), idesc3 = make_idesc_bf16(128, E3, 0, 0);
@@ -167,13 +178,14 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_fwd2_kernel(const Fwd2Args 
                  dW3 = wdesc_kmajor(smem_u32(smem + S::o_w3), E3);
   const uint64_t dB1 = wdesc_kmajor(smem_u32(smem + S::o_b1), E1), dB2 = wdesc_kmajor(smem_u32(smem + S::o_b2), E2),
                  dB3 = wdesc_kmajor(smem_u32(smem + S::o_b3), E3);
-  const uint32_t ones_addr = tmem_base + F2_ONES_COL;
+  const uint64_t dA0 = make_smem_desc(smem_u32(a0), 2048, 128), dOnes = make_smem_desc(smem_u32(smem + S::o_ones), 2048, 128);
 
   // per-warp staging
   const int Hb = A.Hb, Hs = A.Hs, RS = E0 + Hb;
-  float* s_pi = reinterpret_cast<float*>(smem + S::o_warp + warp * S::warp_bytes(Hb, Hs));      // [F2_IC][E0 + Hb]
-  float* s_hj = s_pi + F2_IC * RS;                                                              // [32][Hs]
+  float* s_pi = reinterpret_cast<float*>(smem + S::o_warp + warp * S::warp_bytes(Hb, Hs));      // [2][F2_IC][E0 + Hb]
+  float* s_hj = s_pi + 2 * F2_IC * RS;                                                          // [32][Hs]
   const int H4 = Hb >> 2;
+  const bool h_vec = (A.ld & 3) == 0 && (A.cols & 3) == 0 && ((reinterpret_cast<uintptr_t>(A.h) & 15) == 0);
 
   // tile range of this group: tiles are (group task k, i), k-major
   const int ngroups = gridDim.x * NWG, gidx = blockIdx.x * NWG + wg;
@@ -181,63 +193,75 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_fwd2_kernel(const Fwd2Args 
   const int g0 = (int)(T * gidx / ngroups), g1 = (int)(T * (gidx + 1) / ngroups);
   const int N = A.N;
   const int ntasks = A.B * A.NJB;
+  // state of the tile being PREPARED (first layer), one tile ahead of the tile in the tensor-core stages
   int k = g0 / N, i = g0 - k * N;
   bool fresh = true;
-  int ibase = 0;
   float q[E0];
-  bool active = false, valid = false;
-  size_t node0 = 0;      // first node row of the warp's jet
+  bool p_active = false, p_valid = false;
+  size_t node0 = 0;
   float* e_dst = nullptr;
-  uint32_t ph = 0;
-  int tr_n = 0;
 
-  for (int g = g0; g < g1; ++g) {
-    F2_STAMP(0);
+  // issues the cp.async copies of chunk c (i in [c * F2_IC, ...)) of the current jet into buffer c & 1
+  auto stage_chunk = [&](int c) {
+    const int ib = c * F2_IC, n = min(F2_IC, N - ib);
+    float* dst = s_pi + (c & 1) * F2_IC * RS;
+    for (int idx = lane; idx < n * (E0 / 4); idx += 32) {
+      const int r = idx / (E0 / 4), c4 = idx - r * (E0 / 4);
+      cp_async16(dst + r * RS + 4 * c4, A.pq + (node0 + ib + r) * (2 * E0) + 4 * c4);
+    }
+    if (h_vec) {
+      const int hq = A.cols >> 2;
+      for (int idx = lane; idx < n * hq; idx += 32) {
+        const int r = idx / hq, c4 = idx - r * hq;
+        cp_async16(dst + r * RS + E0 + 4 * c4, A.h + (node0 + ib + r) * A.ld + 4 * c4);
+      }
+    } else {
+      for (int idx = lane; idx < n * A.cols; idx += 32) {
+        const int r = idx / A.cols, kk = idx - r * A.cols;
+        cp_async4(dst + r * RS + E0 + kk, A.h + (node0 + ib + r) * A.ld + kk);
+      }
+    }
+    cp_async_commit();
+  };
+
+  // first edge layer of the tile (k, i) -> a0 (shared memory, bf16 A operand); advances (k, i)
+  auto prepare = [&](bool& t_active, bool& t_valid, float*& t_erow) {
     if (fresh) {
       // ---- new (jet, j block): Q_j -> registers, h_j -> per-lane shared row ----
       const int task = 4 * k + wq;
-      active = task < ntasks;
-      const int tk = active ? task : 0;
+      p_active = task < ntasks;
+      const int tk = p_active ? task : 0;
       const int jet = tk / A.NJB, jb = tk - jet * A.NJB;
       const int j = jb * 32 + lane;
-      valid = active && j < N;
+      p_valid = p_active && j < N;
       node0 = (size_t)jet * N;
       e_dst = A.e_out + ((size_t)jb * A.B + jet) * N * E3;
+      cp_async_wait<0>();
       __syncwarp();
+      stage_chunk(i / F2_IC);
+      if ((i / F2_IC + 1) * F2_IC < N) stage_chunk(i / F2_IC + 1);
       if (j < N) {
         const float4* src = reinterpret_cast<const float4*>(A.pq + (node0 + j) * (2 * E0) + E0);
 #pragma unroll
         for (int c = 0; c < E0 / 4; ++c) { const float4 v = __ldg(src + c); q[4 * c] = v.x; q[4 * c + 1] = v.y; q[4 * c + 2] = v.z; q[4 * c + 3] = v.w; }
         const float* hsrc = A.h + (node0 + j) * A.ld;
-        for (int kk = 0; kk < Hb; ++kk) s_hj[lane * Hs + kk] = kk < A.cols ? __ldg(hsrc + kk) : 0.f;
+        for (int kk = 0; kk < A.cols; ++kk) s_hj[lane * Hs + kk] = __ldg(hsrc + kk);
       } else {
 #pragma unroll
         for (int c = 0; c < E0; ++c) q[c] = 0.f;
-        for (int kk = 0; kk < Hb; ++kk) s_hj[lane * Hs + kk] = 0.f;
+        for (int kk = 0; kk < A.cols; ++kk) s_hj[lane * Hs + kk] = 0.f;
       }
-    }
-    if (fresh || i - ibase == F2_IC) {
-      // ---- refill P_i | h_i for the next F2_IC i's (warp-private, no cross-warp sync) ----
+      if ((i / F2_IC + 1) * F2_IC < N) cp_async_wait<1>(); else cp_async_wait<0>();
       __syncwarp();
-      ibase = i;
-      const int n = min(F2_IC, N - i);
-      for (int idx = lane; idx < n * (E0 / 4); idx += 32) {
-        const int r = idx / (E0 / 4), c4 = idx - r * (E0 / 4);
-        const float4 v = __ldg(reinterpret_cast<const float4*>(A.pq + (node0 + i + r) * (2 * E0)) + c4);
-        *reinterpret_cast<float4*>(s_pi + r * RS + 4 * c4) = v;
-      }
-      for (int idx = lane; idx < n * Hb; idx += 32) {
-        const int r = idx / Hb, kk = idx - r * Hb;
-        s_pi[r * RS + E0 + kk] = kk < A.cols ? __ldg(A.h + (node0 + i + r) * A.ld + kk) : 0.f;
-      }
+    } else if ((i & (F2_IC - 1)) == 0) {
+      // ---- entering the next chunk (prefetched F2_IC tiles ago); prefetch the one after it into the buffer just left ----
+      cp_async_wait<0>();
       __syncwarp();
+      if ((i / F2_IC + 1) * F2_IC < N) stage_chunk(i / F2_IC + 1);
     }
     fresh = false;
-    F2_STAMP(1);
-
-    // ---- first edge layer on the CUDA cores ----
     {
-      const float* Pi = s_pi + (i - ibase) * RS;
+      const float* Pi = s_pi + (((i / F2_IC) & 1) * F2_IC + (i & (F2_IC - 1))) * RS;
       const float4* hi4 = reinterpret_cast<const float4*>(Pi + E0);
       const float4* hj4 = reinterpret_cast<const float4*>(s_hj + lane * Hs);
       float d;
@@ -256,78 +280,100 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_fwd2_kernel(const Fwd2Args 
         d = acc.x + acc.y;
       }
       const float2 d2 = make_float2(d, d);
-      uint32_t a0[E0 / 2];
 #pragma unroll
-      for (int c = 0; c < E0; c += 4) {
-        const float4 p = *reinterpret_cast<const float4*>(Pi + c);
-        const float4 w = *reinterpret_cast<const float4*>(s_wd + c);
-        const float2 z0 = fma2(make_float2(w.x, w.y), d2, add2(make_float2(p.x, p.y), make_float2(q[c], q[c + 1])));
-        const float2 z1 = fma2(make_float2(w.z, w.w), d2, add2(make_float2(p.z, p.w), make_float2(q[c + 2], q[c + 3])));
-        a0[c / 2] = leaky_pack(z0.x, z0.y, alpha2);
-        a0[c / 2 + 1] = leaky_pack(z1.x, z1.y, alpha2);
+      for (int c = 0; c < E0; c += 8) {
+        uint32_t o[4];
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int cc = c + 4 * hh;
+          const float4 p = *reinterpret_cast<const float4*>(Pi + cc);
+          const float4 w = *reinterpret_cast<const float4*>(s_wd + cc);
+          const float2 z0 = fma2(make_float2(w.x, w.y), d2, add2(make_float2(p.x, p.y), make_float2(q[cc], q[cc + 1])));
+          const float2 z1 = fma2(make_float2(w.z, w.w), d2, add2(make_float2(p.z, p.w), make_float2(q[cc + 2], q[cc + 3])));
+          o[2 * hh] = leaky_pack(z0.x, z0.y, alpha2);
+          o[2 * hh + 1] = leaky_pack(z1.x, z1.y, alpha2);
+        }
+        *reinterpret_cast<uint4*>(a0_row + (c >> 3) * 2048) = make_uint4(o[0], o[1], o[2], o[3]);
       }
-      tmem_st16(slot + 128, a0);
+      fence_proxy_async();
     }
-    tmem_st_wait();
+    t_active = p_active; t_valid = p_valid; t_erow = e_dst + (size_t)i * E3;
+    if (++i == N) { i = 0; ++k; fresh = true; }
+  };
+
+  uint32_t ph = 0;
+  int tr_n = 0;
+  bool n_active = false, n_valid = false;
+  float* n_erow = nullptr;
+  if (g0 < g1) prepare(n_active, n_valid, n_erow);
+
+  for (int g = g0; g < g1; ++g) {
+    F2_STAMP(0);
+    const bool active = n_active, valid = n_valid;
+    float* const erow = n_erow;
+    // ---- layer 1: acc1[0,128) = a0 (shared memory) W1^T + b1 ----
     tc_fence_before();
-    F2_STAMP(2);
     named_bar_sync(1 + wg, 128);
     if (wq == 0) {
       tc_fence_after();
 #pragma unroll
-      for (int s = 0; s < E0 / 16; ++s) mma_ts_elect(slot0, slot0 + 128 + 8 * s, dW1 + (uint64_t)(s * ((2 * E1 * 16) >> 4)), idesc1, s > 0);
-      mma_ts_elect(slot0, ones_addr, dB1, idesc1, 1u);
+      for (int s = 0; s < E0 / 16; ++s)
+        mma_bf16_ss_elect(slot0, dA0 + (uint64_t)(s * (4096 >> 4)), dW1 + (uint64_t)(s * ((2 * E1 * 16) >> 4)), idesc1, s > 0);
+      mma_bf16_ss_elect(slot0, dOnes, dB1, idesc1, 1u);
       mma_commit_elect(bars + 0);
     }
+    F2_STAMP(1);
     mbar_wait_all(bars + 0, ph);
     tc_fence_after();
-    F2_STAMP(3);
+    F2_STAMP(2);
     epilogue_hidden<E1>(slot, slot, alpha2);
     tmem_st_wait();
     tc_fence_before();
-    F2_STAMP(4);
+    F2_STAMP(3);
     named_bar_sync(1 + wg, 128);
-    if (wq == 0) {
+    if (wq == 1) {
       tc_fence_after();
 #pragma unroll
       for (int s = 0; s < E1 / 16; ++s) mma_ts_elect(slot0 + E1 / 2, slot0 + 8 * s, dW2 + (uint64_t)(s * ((2 * E2 * 16) >> 4)), idesc2, s > 0);
-      mma_ts_elect(slot0 + E1 / 2, ones_addr, dB2, idesc2, 1u);
+      mma_bf16_ss_elect(slot0 + E1 / 2, dOnes, dB2, idesc2, 1u);
       mma_commit_elect(bars + 1);
     }
+    // ---- first layer of the NEXT tile while layer 2 runs on the tensor pipe (a0 is free: layer 1 has completed) ----
+    if (g + 1 < g1) prepare(n_active, n_valid, n_erow);
+    F2_STAMP(4);
     mbar_wait_all(bars + 1, ph);
     tc_fence_after();
     F2_STAMP(5);
     epilogue_hidden<E2>(slot + E1 / 2, slot, alpha2);
     tmem_st_wait();
     tc_fence_before();
-    F2_STAMP(6);
     named_bar_sync(1 + wg, 128);
-    if (wq == 0) {
+    if (wq == 2) {
       tc_fence_after();
 #pragma unroll
-      for (int s = 0; s < E2 / 16; ++s) mma_ts_elect(slot0 + 144, slot0 + 8 * s, dW3 + (uint64_t)(s * ((2 * E3 * 16) >> 4)), idesc3, s > 0);
-      mma_ts_elect(slot0 + 144, ones_addr, dB3, idesc3, 1u);
+      for (int s = 0; s < E2 / 16; ++s) mma_ts_elect(slot0 + E2 / 2, slot0 + 8 * s, dW3 + (uint64_t)(s * ((2 * E3 * 16) >> 4)), idesc3, s > 0);
+      mma_bf16_ss_elect(slot0 + E2 / 2, dOnes, dB3, idesc3, 1u);
       mma_commit_elect(bars + 2);
     }
+    F2_STAMP(6);
     mbar_wait_all(bars + 2, ph);
     tc_fence_after();
     F2_STAMP(7);
     ++tr_n;
     {
       uint32_t r[16];
-      tmem_ld16_u(slot + 144, r);
+      tmem_ld16_u(slot + E2 / 2, r);
       tmem_ld_wait(); tmem_pin16(r);
       float v[16];
 #pragma unroll
       for (int c = 0; c < 16; ++c) { const float z = __uint_as_float(r[c]); v[c] = valid ? fmaxf(z, alpha * z) : 0.f; }
       const float s = warp_transpose_sum16(v, lane);
-      if (active && (lane & 1) == 0) e_dst[(size_t)i * E3 + (lane >> 1)] = s;
+      if (active && (lane & 1) == 0) erow[lane >> 1] = s;
     }
-    tc_fence_before();      // orders this tile's TMEM reads before the next tile's MMA (through the next bar.sync)
     ph ^= 1u;
-    if (++i == N) { i = 0; ++k; fresh = true; }
   }
 
+  cp_async_wait<0>();
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem_base, 512);
@@ -364,7 +410,7 @@ size_t gj_fwd2_ws_floats(const MPLayout& L) {
 
 int gj_edge_fwd2(const MPLayout& L, const float* h, const float* pq, const float* params, float* e_out, float* ws,
                  cudaStream_t stream) {
-  constexpr int NWG = 3;
+  constexpr int NWG = 4;
   Fwd2Args A;
   A.h = h; A.pq = pq; A.params = params;
   A.B = L.B; A.N = L.N; A.NJB = (L.N + 31) / 32; A.cols = L.cols; A.ld = L.ld; A.mink = L.mink;

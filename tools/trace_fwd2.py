@@ -15,7 +15,7 @@ buf = (ctypes.c_longlong * (8 * 256))()
 lib = _lib.load()
 assert lib.gj_debug_read_fwd2_trace(buf) == 0
 t = np.array(buf[:], dtype=np.int64).reshape(256, 8)
-names = ["stage/refill", "L0+st", "bar+issue+MMA1 wait", "epi1", "issue+MMA2 wait", "epi2", "issue+MMA3 wait", "epi3+loop"]
+names = ["bar+issue MMA1", "MMA1 wait", "epi1", "bar+issue MMA2+L0(next)", "MMA2 wait (rest)", "epi2+bar+issue MMA3", "MMA3 wait", "epi3+loop"]
 rows = [r for r in range(2, 60) if t[r + 1, 0] > 0]
 d = np.zeros((len(rows), 8))
 for n, r in enumerate(rows):
