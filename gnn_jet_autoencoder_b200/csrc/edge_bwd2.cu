@@ -5,21 +5,21 @@
 //
 // Decomposition (same as edge_fwd2.cu).  A warp owns a (jet, j block) -- lane = j, Q_j and the dQ_j accumulator live in
 // registers -- and walks i; four warps (four TMEM lane quadrants, possibly four jets) form a TILE GROUP of 128 edge
-// rows per tile; a CTA runs NWG groups, each with a private 128-column TMEM slot.  A group issues its own GEMMs (one
-// warp, rotating with the stage, after a group-wide named barrier), so the groups drift freely against each other:
-// while one group's GEMMs occupy the tensor pipe the others run epilogues.  The weight-gradient accumulators are
-// shared by all groups and stay in TMEM for the whole kernel (tcgen05.mma from different warps execute one after the
-// other in the SM's single tensor pipe, so concurrent accumulation is safe); the order in which tiles are added depends
-// on timing, i.e. parameter gradients are reproducible to fp32 rounding, not bitwise.  (A dedicated issuer warp that
-// serves the groups round-robin would restore bitwise reproducibility, but a 13th warp caps the kernel at 128
-// registers per thread -- 16 K registers per SM sub-partition / 4 warps -- and round-robin issue locks the groups'
-// stages together.)
+// rows per tile; a CTA runs NWG groups, each with a private 128-column TMEM slot.  A group issues its own GEMMs (after a
+// group-wide named barrier; see issue_stage), so the groups drift freely against each other: while one group's GEMMs
+// occupy the tensor pipe the others run epilogues.  The weight-gradient accumulators are shared by all groups and stay in
+// TMEM for the whole kernel (tcgen05.mma from different warps execute one after the other in the SM's single tensor
+// pipe, so concurrent accumulation is safe); the order in which tiles are added depends on timing: parameter gradients
+// are reproducible to fp32 rounding, not bitwise.  (Measured alternatives: one dedicated issuer warp serving the groups
+// -- polling or in strict rotation, which would make the sums bitwise reproducible -- is saturated by the issue work of
+// ~70 small MMAs per tile; one issuer warp per group, 16 warps with setmaxnreg register hand-over, costs the compute
+// warps more issue slots than it saves.)
 //
 // Stages of one tile (thread = edge row = TMEM lane; all operands bf16, accumulation fp32):
 //   L0  a0 = leaky(P_i + Q_j + wd d_ij)                      CUDA cores -> shared A0 (A of F1, B of the layer-1 wgrad)
-//   F1  acc[0,128) = A0 W1^T           (SS)                  epi: +b1, leaky -> a1: TMEM [0,64) (A of F2) + shared X1
-//   F2  acc[64,128) = a1 W2^T          (TS)                  epi: +b2, leaky -> a2: TMEM [0,32) (A of F3) + shared X2
-//   F3  acc[32,48) = a2 W3^T           (TS)                  epi: dz3 = de_i leaky'(z3) [valid] -> TMEM [48,56) + shared D3
+//   F1  acc[0,128) = A0 W1^T + b1      (SS)                  epi: leaky -> a1     : TMEM [0,64) (A of F2) + shared X1
+//   F2  acc[64,128) = a1 W2^T + b2     (TS)                  epi: leaky -> a2     : TMEM [0,32) (A of F3) + shared X2
+//   F3  acc[32,48) = a2 W3^T + b3      (TS)                  epi: dz3 = de_i leaky'(z3) [valid] -> TMEM [48,56) + shared D3
 //   B3  acc[64,128) = dz3 W3 (TS);  dW3 += a2^T dz3 (SS)      epi: dz2 = acc leaky'(a2) -> shared X2 (in place over a2)
 //   B2  acc[0,128) = dz2 W2 (SS);   dW2 += a1^T dz2;  db2 += dz2^T 1        epi: dz1 = acc leaky'(a1) -> TMEM [0,64) +
 //                                                                                shared X1 (in place over a1)
@@ -31,7 +31,7 @@
 //
 // TMEM: columns [128 g, 128 g + 128) = slot of group g;  [384,432) dW1 (lane = out feature, column = in feature, column 32
 // = db1);  [432,496) dW2 (lane = in feature, column = out feature);  [496,512) dW3 (M = 64: in feature k at lane
-// (k / 16) * 32 + k % 16, column = out feature) and, at lane offset 16 of the same columns, db2 (M = 64, column 496).
+// (k / 16) * 32 + k % 16, column = out feature) and, at lane offset 16 of the same columns, db2 (M = 64, column 496) and db3 (M = 64, column 504).
 #include <stdlib.h>
 
 #include "tc2_common.cuh"
@@ -52,13 +52,15 @@ constexpr int B2_IC = 2;           // i's per staged P_i chunk (double buffered,
 
 template <int E0, int E1, int E2, int E3, int NWG>
 struct Bwd2Smem {
-  static constexpr int o_bar = 0;                        // per group: done, done2
+  static constexpr int o_bar = 0;                        // per group: (unused), done, done2, doneW
   static constexpr int o_slot = 256;
-  static constexpr int o_f32 = 512;                      // b1 | b2 | b3 | wd | reduction scratch
-  static constexpr int n_f32 = E1 + E2 + E3 + E0;
-  static constexpr int o_red = o_f32 + n_f32 * 4;        // [NWG * 4 warps][E0 + E3] floats
-  static constexpr int o_ones = ((o_red + NWG * 4 * (E0 + E3) * 4 + 127) / 128) * 128;     // [8][16] bf16 ones (B of the db2 column sum)
-  static constexpr int o_w1 = ((o_ones + 256 + 1023) / 1024) * 1024;
+  static constexpr int o_wd = 384;                       // E0 floats
+  static constexpr int o_ones = 512;                     // [8][16] bf16 ones (B of the db2 column sum)
+  // bias k-step B operands: chunk 0 = [N][8] bf16 with (b_hi, b_lo, 0, ...) per row; chunk 1 is the shared zero slab
+  static constexpr int o_b1 = 1024;
+  static constexpr int o_b2 = o_b1 + E1 * 16;
+  static constexpr int o_b3 = o_b2 + E2 * 16;
+  static constexpr int o_w1 = ((o_b3 + E3 * 16 + 1023) / 1024) * 1024;
   static constexpr int o_w2 = o_w1 + E1 * E0 * 2;
   static constexpr int o_w3 = o_w2 + E2 * E1 * 2;
   static constexpr int o_grp = o_w3 + E3 * E2 * 2;
@@ -71,7 +73,9 @@ struct Bwd2Smem {
   static constexpr int grp_bytes = g_x2 + (E2 / 8) * 2048;
   static constexpr int o_warp = o_grp + NWG * grp_bytes;
   static constexpr int warp_bytes = 2 * B2_IC * E0 * 4;
-  static constexpr int total = o_warp + NWG * 4 * warp_bytes;
+  static constexpr int o_zero = o_warp + NWG * 4 * warp_bytes;      // [128 rows][8] zeros: second k-chunk of every bias operand
+  static constexpr int total = o_zero + 2048;
+  static constexpr int o_red = o_grp + g_x1;             // [NWG * 4 warps][E0] floats, over group 0's X1 once all GEMMs are done
 };
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
@@ -129,33 +133,36 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args 
   constexpr int NT = NWG * 128;
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = (int)uni((uint32_t)(tid >> 5));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::o_bar);      // [g][2]: done, done2
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::o_bar);      // [g][4]: ready, done, done2, doneW
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::o_slot);
-  float* s_b1 = reinterpret_cast<float*>(smem + S::o_f32);
-  float* s_b2 = s_b1 + E1;
-  float* s_b3 = s_b2 + E2;
-  float* s_wd = s_b3 + E3;
+  float* s_wd = reinterpret_cast<float*>(smem + S::o_wd);
   float* s_red = reinterpret_cast<float*>(smem + S::o_red);
 
   // ---- one-time staging ----
   stage_weight_kmajor<E1, E0>(smem + S::o_w1, A.params + A.pW1, tid, NT);
   stage_weight_kmajor<E2, E1>(smem + S::o_w2, A.params + A.pW2, tid, NT);
   stage_weight_kmajor<E3, E2>(smem + S::o_w3, A.params + A.pW3, tid, NT);
-  for (int c = tid; c < E1; c += NT) s_b1[c] = __ldg(A.params + A.pb1 + c);
-  for (int c = tid; c < E2; c += NT) s_b2[c] = __ldg(A.params + A.pb2 + c);
-  for (int c = tid; c < E3; c += NT) s_b3[c] = __ldg(A.params + A.pb3 + c);
+  for (int idx = tid; idx < (E1 + E2 + E3) * 4; idx += NT) {      // bias rows: (hi, lo, 0, 0, 0, 0, 0, 0) as four 32-bit words
+    const int n = idx >> 2, w = idx & 3;
+    const float v = __ldg(A.params + (n < E1 ? A.pb1 + n : (n < E1 + E2 ? A.pb2 + n - E1 : A.pb3 + n - E1 - E2)));
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    const uint32_t word = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+    reinterpret_cast<uint32_t*>(smem + S::o_b1)[idx] = w == 0 ? word : 0u;
+  }
+  for (int idx = tid; idx < 512; idx += NT) reinterpret_cast<uint32_t*>(smem + S::o_zero)[idx] = 0u;
   for (int c = tid; c < E0; c += NT) s_wd[c] = __ldg(A.params + A.pWd + c * A.K0);
   for (int idx = tid; idx < 64; idx += NT) reinterpret_cast<uint32_t*>(smem + S::o_ones)[idx] = 0x3F803F80u;
-  for (int idx = tid; idx < NWG * 512; idx += NT) {      // ones slab of every group: channel 32 = 1.0, channels 33..39 = 0
+  for (int idx = tid; idx < NWG * 512; idx += NT) {      // ones slab of every group: channels 32, 33 = 1.0 (bias hi + lo), 34..39 = 0
     const int g = idx / 512, w = idx - g * 512;
-    reinterpret_cast<uint32_t*>(smem + S::o_grp + g * S::grp_bytes + S::g_ones)[w] = (w & 3) == 0 ? 0x00003F80u : 0u;
+    reinterpret_cast<uint32_t*>(smem + S::o_grp + g * S::grp_bytes + S::g_ones)[w] = (w & 3) == 0 ? 0x3F803F80u : 0u;
   }
   for (int idx = tid; idx < NWG * (E3 / 8) * 512; idx += NT) {      // dz3 slabs start finite (they are read by the first wgrad1)
     const int g = idx / ((E3 / 8) * 512), w = idx - g * ((E3 / 8) * 512);
     reinterpret_cast<uint32_t*>(smem + S::o_grp + g * S::grp_bytes + S::g_d3)[w] = 0u;
   }
   if (tid == 0) {
-    for (int g = 0; g < 2 * NWG; ++g) mbar_init(bars + g, 1);
+    for (int g = 0; g < 4 * NWG; ++g) mbar_init(bars + g, 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -185,76 +192,111 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args 
     // =================================== compute tile groups ===================================
     const int wg = warp >> 2, wq = warp & 3;
     const int row = wq * 32 + lane;
-    uint64_t* done = bars + 2 * wg;
+    uint64_t* done = bars + 4 * wg + 1;
     uint64_t* done2 = done + 1;
+    uint64_t* doneW = done + 2;
     // ---- MMA operands of this group (warp-uniform) ----
-    const uint32_t w1a = smem_u32(smem + S::o_w1), w2a = smem_u32(smem + S::o_w2), w3a = smem_u32(smem + S::o_w3);
-    const uint32_t gba = smem_u32(smem + S::o_grp + wg * S::grp_bytes);
+    const uint32_t smem0 = smem_u32(smem);
+    const uint32_t w1a = smem0 + S::o_w1, w2a = smem0 + S::o_w2, w3a = smem0 + S::o_w3, zero_a = smem0 + S::o_zero;
+    const uint32_t b1a = smem0 + S::o_b1, b2a = smem0 + S::o_b2, b3a = smem0 + S::o_b3;
+    const uint32_t gba = smem0 + S::o_grp + (uint32_t)(wg * S::grp_bytes);
     const uint32_t slot0 = tmem_base + (uint32_t)(wg * 128);
-    const uint32_t ones_a = smem_u32(smem + S::o_ones);
-    // One GEMM stage of the tile, issued by one warp of the group (all 32 lanes run this convergently; a single elected
-    // lane issues each tcgen05 instruction).  Forward B operands are K-major (N = out feature); the dgrad B operands are
-    // the same bytes viewed MN-major (N = in feature); weight-gradient operands are MN-major views (K = tile row).
+    // The GEMMs of a stage are issued by the group's own warps right after the group barrier (all 32 lanes run the code
+    // convergently, one elected lane issues each tcgen05 instruction): warp (stage & 3) issues the GEMM whose
+    // accumulator the next epilogue reads and commits it to `done`; warp ((stage + 2) & 3) issues the stage's
+    // weight-gradient GEMMs and commits them to `doneW` (B3, B2: gates the in-place overwrite of their operand) or
+    // `done2` (B1: gates the next tile's L0 / F2 / F3 epilogues).  Issuing costs about seven uniform-datapath
+    // instructions per MMA and a full tensor-core queue blocks the issuing thread, hence the split and the rotation.
+    // Forward B operands are K-major (N = out feature); the dgrad B operands are the same bytes viewed MN-major (N = in
+    // feature); weight-gradient operands are MN-major views (K = tile row).
     auto issue_stage = [&](int stage) {
+      const bool crit = wq == (stage & 3), wgr = wq == ((stage + 2) & 3);
+      if (!crit && !wgr) return;
       tc_fence_after();
+      // bias k-step A operand: (1, 1, 0, ...) per row = the group's ones slab + the shared zero slab
+      const uint64_t dBiasA = make_smem_desc(gba + S::g_ones, zero_a - (gba + S::g_ones), 128);
+      const uint64_t dX1n = make_smem_desc(gba + S::g_x1, 128, 2048), dX2n = make_smem_desc(gba + S::g_x2, 128, 2048);
+      const uint64_t dD3n = make_smem_desc(gba + S::g_d3, 128, 2048);
       if (stage == 0) {
-        const uint64_t dA0k = make_smem_desc(gba + S::g_a0, 2048, 128), dW1f = wdesc_kmajor(w1a, E1);
-        const uint32_t idesc = make_idesc_bf16(128, E1, 0, 0);
+        if (crit) {
+          const uint64_t dA0k = make_smem_desc(gba + S::g_a0, 2048, 128), dW1f = wdesc_kmajor(w1a, E1);
+          const uint32_t idesc = make_idesc_bf16(128, E1, 0, 0);
 #pragma unroll
-        for (int s = 0; s < E0 / 16; ++s) mma_bf16_ss_elect(slot0, dA0k + (uint64_t)(s * 256), dW1f + (uint64_t)(s * 2 * E1), idesc, s > 0);
-        mma_commit_elect(done);
+          for (int s = 0; s < E0 / 16; ++s) mma_bf16_ss_elect(slot0, dA0k + (uint64_t)(s * 256), dW1f + (uint64_t)(s * 2 * E1), idesc, s > 0);
+          mma_bf16_ss_elect(slot0, dBiasA, make_smem_desc(b1a, zero_a - b1a, 128), idesc, 1u);
+          mma_commit_elect(done);
+        }
       } else if (stage == 1) {
-        const uint64_t dW2f = wdesc_kmajor(w2a, E2);
-        const uint32_t idesc = make_idesc_bf16(128, E2, 0, 0);
+        if (crit) {
+          const uint64_t dW2f = wdesc_kmajor(w2a, E2);
+          const uint32_t idesc = make_idesc_bf16(128, E2, 0, 0);
 #pragma unroll
-        for (int s = 0; s < E1 / 16; ++s) mma_ts_elect(slot0 + 64, slot0 + 8 * s, dW2f + (uint64_t)(s * 2 * E2), idesc, s > 0);
-        mma_commit_elect(done);
+          for (int s = 0; s < E1 / 16; ++s) mma_ts_elect(slot0 + 64, slot0 + 8 * s, dW2f + (uint64_t)(s * 2 * E2), idesc, s > 0);
+          mma_bf16_ss_elect(slot0 + 64, dBiasA, make_smem_desc(b2a, zero_a - b2a, 128), idesc, 1u);
+          mma_commit_elect(done);
+        }
       } else if (stage == 2) {
-        const uint64_t dW3f = wdesc_kmajor(w3a, E3);
-        const uint32_t idesc = make_idesc_bf16(128, E3, 0, 0);
+        if (crit) {
+          const uint64_t dW3f = wdesc_kmajor(w3a, E3);
+          const uint32_t idesc = make_idesc_bf16(128, E3, 0, 0);
 #pragma unroll
-        for (int s = 0; s < E2 / 16; ++s) mma_ts_elect(slot0 + 32, slot0 + 8 * s, dW3f + (uint64_t)(s * 2 * E3), idesc, s > 0);
-        mma_commit_elect(done);
+          for (int s = 0; s < E2 / 16; ++s) mma_ts_elect(slot0 + 32, slot0 + 8 * s, dW3f + (uint64_t)(s * 2 * E3), idesc, s > 0);
+          mma_bf16_ss_elect(slot0 + 32, dBiasA, make_smem_desc(b3a, zero_a - b3a, 128), idesc, 1u);
+          mma_commit_elect(done);
+        }
       } else if (stage == 3) {
         // dgrad3: acc[64,128) = dz3 (TMEM [48,56)) W3 ; wgrad3: dW3 += a2^T dz3
-        const uint64_t dW3b = make_smem_desc(w3a, 128, E3 * 16);
-        const uint64_t dX2n = make_smem_desc(gba + S::g_x2, 128, 2048), dD3n = make_smem_desc(gba + S::g_d3, 128, 2048);
-        mma_ts_elect(slot0 + 64, slot0 + 48, dW3b, make_idesc_bf16(128, E2, 0, 1), 0u);
-        const uint32_t idesc = make_idesc_bf16(64, E3, 1, 1);
+        if (crit) {
+          mma_ts_elect(slot0 + 64, slot0 + 48, make_smem_desc(w3a, 128, E3 * 16), make_idesc_bf16(128, E2, 0, 1), 0u);
+          mma_commit_elect(done);
+        } else {
+          const uint32_t idesc = make_idesc_bf16(64, E3, 1, 1);
 #pragma unroll
-        for (int s = 0; s < 8; ++s) mma_bf16_ss_elect(tmem_base + 496, dX2n + (uint64_t)(s * 16), dD3n + (uint64_t)(s * 16), idesc, 1u);
-        mma_commit_elect(done);
+          for (int s = 0; s < 8; ++s) mma_bf16_ss_elect(tmem_base + 496, dX2n + (uint64_t)(s * 16), dD3n + (uint64_t)(s * 16), idesc, 1u);
+          mma_commit_elect(doneW);
+        }
       } else if (stage == 4) {
-        // dgrad2: acc[0,128) = dz2 W2 ; wgrad2: dW2 += a1^T dz2 ; db2 += dz2^T 1
-        const uint64_t dW2b = make_smem_desc(w2a, 128, E2 * 16);
-        const uint64_t dX2k = make_smem_desc(gba + S::g_x2, 2048, 128), dX2n = make_smem_desc(gba + S::g_x2, 128, 2048);
-        const uint64_t dX1n = make_smem_desc(gba + S::g_x1, 128, 2048), dOnes = make_smem_desc(ones_a, 128, 128);
-        const uint32_t i_d2 = make_idesc_bf16(128, E1, 0, 1), i_g2 = make_idesc_bf16(128, E2, 1, 1), i_c2 = make_idesc_bf16(64, 8, 1, 0);
+        // dgrad2: acc[0,128) = dz2 W2 ; wgrad2: dW2 += a1^T dz2
+        if (crit) {
+          const uint64_t dX2k = make_smem_desc(gba + S::g_x2, 2048, 128), dW2b = make_smem_desc(w2a, 128, E2 * 16);
+          const uint32_t i_d2 = make_idesc_bf16(128, E1, 0, 1);
 #pragma unroll
-        for (int s = 0; s < E2 / 16; ++s) mma_bf16_ss_elect(slot0, dX2k + (uint64_t)(s * 256), dW2b + (uint64_t)(s * 16), i_d2, s > 0);
+          for (int s = 0; s < E2 / 16; ++s) mma_bf16_ss_elect(slot0, dX2k + (uint64_t)(s * 256), dW2b + (uint64_t)(s * 16), i_d2, s > 0);
+          mma_commit_elect(done);
+        } else {
+          const uint32_t i_g2 = make_idesc_bf16(128, E2, 1, 1);
 #pragma unroll
-        for (int s = 0; s < 8; ++s) mma_bf16_ss_elect(tmem_base + 432, dX1n + (uint64_t)(s * 16), dX2n + (uint64_t)(s * 16), i_g2, 1u);
-#pragma unroll
-        for (int s = 0; s < 8; ++s) mma_bf16_ss_elect(tmem_base + 496 + (16u << 16), dX2n + (uint64_t)(s * 16), dOnes, i_c2, 1u);
-        mma_commit_elect(done);
+          for (int s = 0; s < 8; ++s) mma_bf16_ss_elect(tmem_base + 432, dX1n + (uint64_t)(s * 16), dX2n + (uint64_t)(s * 16), i_g2, 1u);
+          mma_commit_elect(doneW);
+        }
       } else {
-        // dgrad1: acc[64,96) = dz1 (TMEM [0,64)) W1 ; then [dW1 | db1] += dz1^T [a0 | 1] behind the epilogue
-        const uint64_t dW1b = make_smem_desc(w1a, 128, E1 * 16);
-        const uint64_t dX1n = make_smem_desc(gba + S::g_x1, 128, 2048), dA0n = make_smem_desc(gba + S::g_a0, 128, 2048);
-        const uint32_t i_d1 = make_idesc_bf16(128, E0, 0, 1), i_g1 = make_idesc_bf16(128, E0 + 16, 1, 1);
+        // dgrad1: acc[64,96) = dz1 (TMEM [0,64)) W1 ; behind the epilogue: [dW1 | db1] += dz1^T [a0 | 1], db2 += dz2^T 1,
+        // db3 += dz3^T 1 (X2 / D3 still hold dz2 / dz3: the next tile overwrites them after its F2 / F3, issued later)
+        if (crit) {
+          const uint64_t dW1b = make_smem_desc(w1a, 128, E1 * 16);
+          const uint32_t i_d1 = make_idesc_bf16(128, E0, 0, 1);
 #pragma unroll
-        for (int s = 0; s < E1 / 16; ++s) mma_ts_elect(slot0 + 64, slot0 + 8 * s, dW1b + (uint64_t)(s * 16), i_d1, s > 0);
-        mma_commit_elect(done);
+          for (int s = 0; s < E1 / 16; ++s) mma_ts_elect(slot0 + 64, slot0 + 8 * s, dW1b + (uint64_t)(s * 16), i_d1, s > 0);
+          mma_commit_elect(done);
+        } else {
+          const uint64_t dA0n = make_smem_desc(gba + S::g_a0, 128, 2048), dOnes = make_smem_desc(smem0 + S::o_ones, 128, 128);
+          const uint32_t i_g1 = make_idesc_bf16(128, E0 + 16, 1, 1), i_c2 = make_idesc_bf16(64, 8, 1, 0);
 #pragma unroll
-        for (int s = 0; s < 8; ++s) mma_bf16_ss_elect(tmem_base + 384, dX1n + (uint64_t)(s * 16), dA0n + (uint64_t)(s * 16), i_g1, 1u);
-        mma_commit_elect(done2);
+          for (int s = 0; s < 8; ++s) mma_bf16_ss_elect(tmem_base + 384, dX1n + (uint64_t)(s * 16), dA0n + (uint64_t)(s * 16), i_g1, 1u);
+#pragma unroll
+          for (int s = 0; s < 8; ++s) mma_bf16_ss_elect(tmem_base + 496 + (16u << 16), dX2n + (uint64_t)(s * 16), dOnes, i_c2, 1u);
+          // db3: M = 64 reads 48 channels past the 16 of D3 (the head of X1: finite, rows 16..63 are never read)
+#pragma unroll
+          for (int s = 0; s < 8; ++s) mma_bf16_ss_elect(tmem_base + 504 + (16u << 16), dD3n + (uint64_t)(s * 16), dOnes, i_c2, 1u);
+          mma_commit_elect(done2);
+        }
       }
     };
-    // all four warps have written (and fenced) their operands -> the stage's issuing warp launches the GEMMs
+    // all four warps have written (and fenced) their operands -> the stage's issuing warps launch the GEMMs
     auto publish = [&](int stage) {
       tc_fence_before();
       named_bar_sync(1 + wg, 128);
-      if (wq == (stage & 3)) issue_stage(stage);
+      issue_stage(stage);
     };
     const uint32_t slot = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(wg * 128);
     uint8_t* gb = smem + S::o_grp + wg * S::grp_bytes;
@@ -273,13 +315,14 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args 
     bool fresh = true, active = false, valid = false;
     size_t node0 = 0;
     int jb = 0;
-    float q[E0], dq[E0], dwd[E0], db3[E3];
+    uint32_t q[E0 / 2];      // Q_j as bf16 pairs (the forward kernel rounds Q_j the same way)
+    float dq[E0], dwd[E0];
 #pragma unroll
-    for (int c = 0; c < E0; ++c) { dwd[c] = 0.f; dq[c] = 0.f; q[c] = 0.f; }
+    for (int c = 0; c < E0; ++c) { dwd[c] = 0.f; dq[c] = 0.f; }
 #pragma unroll
-    for (int c = 0; c < E3; ++c) db3[c] = 0.f;
+    for (int c = 0; c < E0 / 2; ++c) q[c] = 0u;
     float d_cur = 0.f;
-    uint32_t ph = 0, ph2 = 0;
+    uint32_t ph = 0, ph2 = 0, phW = 0;
     bool pending2 = false;
     int tr_n = 0;
 
@@ -320,10 +363,13 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args 
         if (j < N) {
           const float4* src = reinterpret_cast<const float4*>(A.pq + (node0 + j) * (2 * E0) + E0);
 #pragma unroll
-          for (int c = 0; c < E0 / 4; ++c) { const float4 v = __ldg(src + c); q[4 * c] = v.x; q[4 * c + 1] = v.y; q[4 * c + 2] = v.z; q[4 * c + 3] = v.w; }
+          for (int c = 0; c < E0 / 4; ++c) {
+            const float4 v = __ldg(src + c);
+            q[2 * c] = bf2_as_u32(__floats2bfloat162_rn(v.x, v.y)); q[2 * c + 1] = bf2_as_u32(__floats2bfloat162_rn(v.z, v.w));
+          }
         } else {
 #pragma unroll
-          for (int c = 0; c < E0; ++c) q[c] = 0.f;
+          for (int c = 0; c < E0 / 2; ++c) q[c] = 0u;
         }
         d_cur = __ldg(A.d + (node0 + i) * A.NJ32 + jb * 32 + lane);
         if ((i / B2_IC + 1) * B2_IC < N) cp_async_wait<1>(); else cp_async_wait<0>();
@@ -334,15 +380,7 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args 
         __syncwarp();
         if ((i / B2_IC + 1) * B2_IC < N) stage_chunk(i / B2_IC + 1);
       }
-      // de_i (warp-uniform address) for the F3 epilogue and next tile's d_ij: issued now, consumed much later
-      float4 de4[E3 / 4];
-      {
-        const float4* dsrc = reinterpret_cast<const float4*>(A.de + (node0 + i) * E3);
-#pragma unroll
-        for (int c = 0; c < E3 / 4; ++c) de4[c] = __ldg(dsrc + c);
-      }
       const bool last_i = (i + 1 == N);
-      const float d_next = (!last_i) ? __ldg(A.d + (node0 + i + 1) * A.NJ32 + jb * 32 + lane) : 0.f;
       const float dij = d_cur;
 
       // ---- L0: a0 -> shared A0 (needs the previous tile's wgrad1, which reads A0, to have completed) ----
@@ -359,8 +397,8 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args 
             const int cc = c + 4 * hh;
             const float4 p = *reinterpret_cast<const float4*>(Pi + cc);
             const float4 w = *reinterpret_cast<const float4*>(s_wd + cc);
-            const float2 z0 = fma2(make_float2(w.x, w.y), d2, add2(make_float2(p.x, p.y), make_float2(q[cc], q[cc + 1])));
-            const float2 z1 = fma2(make_float2(w.z, w.w), d2, add2(make_float2(p.z, p.w), make_float2(q[cc + 2], q[cc + 3])));
+            const float2 z0 = fma2(make_float2(w.x, w.y), d2, add2(make_float2(p.x, p.y), unpack_bf2(q[cc / 2])));
+            const float2 z1 = fma2(make_float2(w.z, w.w), d2, add2(make_float2(p.z, p.w), unpack_bf2(q[cc / 2 + 1])));
             o[2 * hh] = leaky_pack(z0.x, z0.y, alpha2);
             o[2 * hh + 1] = leaky_pack(z1.x, z1.y, alpha2);
           }
@@ -369,9 +407,18 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args 
         fence_proxy_async();
         publish(0);
       }
+      // de_i (warp-uniform address) for the F3 epilogue and the next tile's d_ij: issued here, behind the shared-memory
+      // loads of L0 (a load that shares their scoreboard would stall them), consumed much later
+      float4 de4[E3 / 4];
+      {
+        const float4* dsrc = reinterpret_cast<const float4*>(A.de + (node0 + i) * E3);
+#pragma unroll
+        for (int c = 0; c < E3 / 4; ++c) de4[c] = __ldg(dsrc + c);
+      }
+      const float d_next = (!last_i) ? __ldg(A.d + (node0 + i + 1) * A.NJ32 + jb * 32 + lane) : 0.f;
       B2_STAMP(2);
 
-      // ---- F1 epilogue: a1 = leaky(acc + b1) -> TMEM [0,64) + shared X1 ----
+      // ---- F1 epilogue: a1 = leaky(acc) -> TMEM [0,64) + shared X1 ----
       mbar_wait(done, ph); ph ^= 1u;
       tc_fence_after();
       B2_STAMP(3);
@@ -389,11 +436,7 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args 
             if (cc + 1 < E1 / 16) tmem_ld16_u(slot + (uint32_t)((cc + 1) * 16), vn);
             uint32_t o[8];
 #pragma unroll
-            for (int p4 = 0; p4 < 4; ++p4) {
-              const float4 b = *reinterpret_cast<const float4*>(s_b1 + cc * 16 + 4 * p4);
-              o[2 * p4] = leaky_pack(__uint_as_float(v[4 * p4]) + b.x, __uint_as_float(v[4 * p4 + 1]) + b.y, alpha2);
-              o[2 * p4 + 1] = leaky_pack(__uint_as_float(v[4 * p4 + 2]) + b.z, __uint_as_float(v[4 * p4 + 3]) + b.w, alpha2);
-            }
+            for (int p = 0; p < 8; ++p) o[p] = leaky_pack(__uint_as_float(v[2 * p]), __uint_as_float(v[2 * p + 1]), alpha2);
             tmem_st8(slot + (uint32_t)(cc * 8), o);
             *reinterpret_cast<uint4*>(x1_row + (2 * cc) * 2048) = make_uint4(o[0], o[1], o[2], o[3]);
             *reinterpret_cast<uint4*>(x1_row + (2 * cc + 1) * 2048) = make_uint4(o[4], o[5], o[6], o[7]);
@@ -405,7 +448,7 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args 
       }
       B2_STAMP(4);
 
-      // ---- F2 epilogue: a2 = leaky(acc[64,128) + b2) -> TMEM [0,32) + shared X2 ----
+      // ---- F2 epilogue: a2 = leaky(acc[64,128)) -> TMEM [0,32) + shared X2 ----
       mbar_wait(done, ph); ph ^= 1u;
       tc_fence_after();
       B2_STAMP(5);
@@ -423,11 +466,7 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args 
             if (cc + 1 < E2 / 16) tmem_ld16_u(slot + 64 + (uint32_t)((cc + 1) * 16), vn);
             uint32_t o[8];
 #pragma unroll
-            for (int p4 = 0; p4 < 4; ++p4) {
-              const float4 b = *reinterpret_cast<const float4*>(s_b2 + cc * 16 + 4 * p4);
-              o[2 * p4] = leaky_pack(__uint_as_float(v[4 * p4]) + b.x, __uint_as_float(v[4 * p4 + 1]) + b.y, alpha2);
-              o[2 * p4 + 1] = leaky_pack(__uint_as_float(v[4 * p4 + 2]) + b.z, __uint_as_float(v[4 * p4 + 3]) + b.w, alpha2);
-            }
+            for (int p = 0; p < 8; ++p) o[p] = leaky_pack(__uint_as_float(v[2 * p]), __uint_as_float(v[2 * p + 1]), alpha2);
             tmem_st8(slot + (uint32_t)(cc * 8), o);
             *reinterpret_cast<uint4*>(x2_row + (2 * cc) * 2048) = make_uint4(o[0], o[1], o[2], o[3]);
             *reinterpret_cast<uint4*>(x2_row + (2 * cc + 1) * 2048) = make_uint4(o[4], o[5], o[6], o[7]);
@@ -439,7 +478,7 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args 
       }
       B2_STAMP(6);
 
-      // ---- F3 epilogue: dz3 = de_i * leaky'(acc[32,48) + b3), zero on padded rows -> TMEM [48,56) + shared D3 ----
+      // ---- F3 epilogue: dz3 = de_i * leaky'(acc[32,48)), zero on padded rows -> TMEM [48,56) + shared D3 ----
       mbar_wait(done, ph); ph ^= 1u;
       tc_fence_after();
       B2_STAMP(7);
@@ -451,10 +490,9 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args 
         uint32_t o[8];
 #pragma unroll
         for (int p = 0; p < 8; ++p) {
-          const float z0 = __uint_as_float(v[2 * p]) + s_b3[2 * p], z1 = __uint_as_float(v[2 * p + 1]) + s_b3[2 * p + 1];
+          const float z0 = __uint_as_float(v[2 * p]), z1 = __uint_as_float(v[2 * p + 1]);
           const float g0v = valid ? def[2 * p] * (z0 > 0.f ? 1.f : alpha) : 0.f;
           const float g1v = valid ? def[2 * p + 1] * (z1 > 0.f ? 1.f : alpha) : 0.f;
-          db3[2 * p] += g0v; db3[2 * p + 1] += g1v;
           o[p] = bf2_as_u32(__floats2bfloat162_rn(g0v, g1v));
         }
         tmem_st8(slot + 48, o);
@@ -488,6 +526,7 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args 
             uint32_t o[8];
 #pragma unroll
             for (int p = 0; p < 8; ++p) o[p] = dz_pack(__uint_as_float(v[2 * p]), __uint_as_float(v[2 * p + 1]), sg[p], oma2, alpha2);
+            if (cc == 0) { mbar_wait(doneW, phW); phW ^= 1u; }      // dW3 += a2^T dz3 has read a2: X2 may be overwritten
             *reinterpret_cast<uint4*>(x2_row + (2 * cc) * 2048) = make_uint4(o[0], o[1], o[2], o[3]);
             *reinterpret_cast<uint4*>(x2_row + (2 * cc + 1) * 2048) = make_uint4(o[4], o[5], o[6], o[7]);
           }
@@ -520,6 +559,7 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args 
 #pragma unroll
             for (int p = 0; p < 8; ++p) o[p] = dz_pack(__uint_as_float(v[2 * p]), __uint_as_float(v[2 * p + 1]), sg[p], oma2, alpha2);
             tmem_st8(slot + (uint32_t)(cc * 8), o);
+            if (cc == 0) { mbar_wait(doneW, phW); phW ^= 1u; }      // dW2 += a1^T dz2 has read a1: X1 may be overwritten
             *reinterpret_cast<uint4*>(x1_row + (2 * cc) * 2048) = make_uint4(o[0], o[1], o[2], o[3]);
             *reinterpret_cast<uint4*>(x1_row + (2 * cc + 1) * 2048) = make_uint4(o[4], o[5], o[6], o[7]);
           }
@@ -576,11 +616,12 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args 
     if (!fresh) flush_dq();      // the group's last (jet, j block) ended mid-way: the next group adds the rest
     if (pending2) { mbar_wait(done2, ph2); ph2 ^= 1u; }      // all of this group's MMAs have completed
     cp_async_wait<0>();
-    // d(wd), db3: lanes by shuffles, warps through shared memory (fixed order)
+    // d(wd): lanes by shuffles, warps through shared memory (fixed order); the scratch lies over group 0's X1, which
+    // is free once every group's GEMMs have completed
+    tc_fence_before();
+    __syncthreads();
 #pragma unroll
-    for (int c = 0; c < E0; ++c) { const float s = gj_warp_sum(dwd[c]); if (lane == 0) s_red[warp * (E0 + E3) + c] = s; }
-#pragma unroll
-    for (int c = 0; c < E3; ++c) { const float s = gj_warp_sum(db3[c]); if (lane == 0) s_red[warp * (E0 + E3) + E0 + c] = s; }
+    for (int c = 0; c < E0; ++c) { const float s = gj_warp_sum(dwd[c]); if (lane == 0) s_red[warp * E0 + c] = s; }
   }
 
   // =================================== gradient read-out ===================================
@@ -589,11 +630,10 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args 
   tc_fence_after();
   float* out = A.part + (size_t)blockIdx.x * A.nedge;
   const bool wrote = range_lo(blockIdx.x * NWG + 1) > range_lo(blockIdx.x * NWG);      // group 0 of this CTA had tiles
-  if (tid < E0 + E3) {
+  if (tid < E0) {
     float s = 0.f;
-    for (int w = 0; w < NWG * 4; ++w) s += s_red[w * (E0 + E3) + tid];
-    if (tid < E0) out[A.pWd + tid * A.K0] = s;
-    else out[A.pb3 + tid - E0] = s;
+    for (int w = 0; w < NWG * 4; ++w) s += s_red[w * E0 + tid];
+    out[A.pWd + tid * A.K0] = s;
   }
   if (warp < 4) {
     const uint32_t lb = tmem_base + ((uint32_t)(warp * 32) << 16);
@@ -629,6 +669,7 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args 
         for (int c = 0; c < 16; ++c) out[A.pW3 + c * E2 + kf] = wrote ? __uint_as_float(v[c]) : 0.f;
       } else {
         out[A.pb2 + warp * 16 + lane - 16] = wrote ? __uint_as_float(v[0]) : 0.f;
+        if (warp == 0) out[A.pb3 + lane - 16] = wrote ? __uint_as_float(v[8]) : 0.f;      // db3: M = 64 rows 0..15 at lanes 16..31, column 504
       }
     }
   }

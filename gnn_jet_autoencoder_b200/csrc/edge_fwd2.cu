@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_fwd2_kernel(const Fwd2Args 
   // state of the tile being PREPARED (first layer), one tile ahead of the tile in the tensor-core stages
   int k = g0 / N, i = g0 - k * N;
   bool fresh = true;
-  float q[E0];
+  uint32_t q[E0 / 2];      // Q_j as bf16 pairs
   bool p_active = false, p_valid = false;
   size_t node0 = 0;
   float* e_dst = nullptr;
@@ -243,12 +243,15 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_fwd2_kernel(const Fwd2Args 
       if (j < N) {
         const float4* src = reinterpret_cast<const float4*>(A.pq + (node0 + j) * (2 * E0) + E0);
 #pragma unroll
-        for (int c = 0; c < E0 / 4; ++c) { const float4 v = __ldg(src + c); q[4 * c] = v.x; q[4 * c + 1] = v.y; q[4 * c + 2] = v.z; q[4 * c + 3] = v.w; }
+        for (int c = 0; c < E0 / 4; ++c) {
+          const float4 v = __ldg(src + c);
+          q[2 * c] = bf2_as_u32(__floats2bfloat162_rn(v.x, v.y)); q[2 * c + 1] = bf2_as_u32(__floats2bfloat162_rn(v.z, v.w));
+        }
         const float* hsrc = A.h + (node0 + j) * A.ld;
         for (int kk = 0; kk < A.cols; ++kk) s_hj[lane * Hs + kk] = __ldg(hsrc + kk);
       } else {
 #pragma unroll
-        for (int c = 0; c < E0; ++c) q[c] = 0.f;
+        for (int c = 0; c < E0 / 2; ++c) q[c] = 0u;
         for (int kk = 0; kk < A.cols; ++kk) s_hj[lane * Hs + kk] = 0.f;
       }
       if ((i / F2_IC + 1) * F2_IC < N) cp_async_wait<1>(); else cp_async_wait<0>();
@@ -288,8 +291,8 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_fwd2_kernel(const Fwd2Args 
           const int cc = c + 4 * hh;
           const float4 p = *reinterpret_cast<const float4*>(Pi + cc);
           const float4 w = *reinterpret_cast<const float4*>(s_wd + cc);
-          const float2 z0 = fma2(make_float2(w.x, w.y), d2, add2(make_float2(p.x, p.y), make_float2(q[cc], q[cc + 1])));
-          const float2 z1 = fma2(make_float2(w.z, w.w), d2, add2(make_float2(p.z, p.w), make_float2(q[cc + 2], q[cc + 3])));
+          const float2 z0 = fma2(make_float2(w.x, w.y), d2, add2(make_float2(p.x, p.y), unpack_bf2(q[cc / 2])));
+          const float2 z1 = fma2(make_float2(w.z, w.w), d2, add2(make_float2(p.z, p.w), unpack_bf2(q[cc / 2 + 1])));
           o[2 * hh] = leaky_pack(z0.x, z0.y, alpha2);
           o[2 * hh + 1] = leaky_pack(z1.x, z1.y, alpha2);
         }
