@@ -690,51 +690,72 @@ __global__ void sum_dp_parts_kernel(const float* __restrict__ part, int njb, siz
 }
 
 // ---- pair distances (node level, O(N^2 H) per jet): d_ij = metric(h_j - h_i) and its adjoint ----
+// A CTA of 8 warps stages the node features of JPB jets in shared memory (row stride cols | 1: conflict-free per-lane
+// rows); a warp then owns whole (jet, i) rows, lane = j.
 // d (B, N, NJ32): row i of jet b at (b N + i) NJ32, columns j >= N are zero
-__global__ void pair_dist_fwd_kernel(const float* __restrict__ h, int rows, int N, int NJ32, int cols, int ld, int mink,
-                                     float* __restrict__ d) {
-  const int lane = threadIdx.x & 31;
-  const int wpb = blockDim.x >> 5;
-  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
-    const int b = r / N;
-    const float* hi = h + (size_t)r * ld;
-    for (int j = lane; j < NJ32; j += 32) {
-      float acc = 0.f;
-      if (j < N) {
-        const float* hj = h + ((size_t)b * N + j) * ld;
-        for (int k = 0; k < cols; ++k) {
-          const float x = __ldg(hj + k) - __ldg(hi + k);
-          acc = (mink && k > 0) ? fmaf(-x, x, acc) : fmaf(x, x, acc);
+__global__ void __launch_bounds__(256) pair_dist_fwd_kernel(const float* __restrict__ h, int B, int N, int NJ32, int cols, int ld,
+                                                            int mink, int JPB, float* __restrict__ d) {
+  extern __shared__ float pd_smem[];
+  const int hs = cols | 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int b0 = blockIdx.x * JPB; b0 < B; b0 += gridDim.x * JPB) {
+    const int nj = min(JPB, B - b0);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nj * N * cols; idx += 256) {
+      const int r = idx / cols, k = idx - r * cols;
+      pd_smem[r * hs + k] = __ldg(h + ((size_t)b0 * N + r) * ld + k);
+    }
+    __syncthreads();
+    for (int r = warp; r < nj * N; r += 8) {
+      const int jl = r / N;
+      const float* hi = pd_smem + r * hs;
+      for (int j = lane; j < NJ32; j += 32) {
+        float acc = 0.f;
+        if (j < N) {
+          const float* hj = pd_smem + (jl * N + j) * hs;
+          if (mink) {
+            for (int k = 0; k < cols; ++k) { const float x = hj[k] - hi[k]; acc = k > 0 ? fmaf(-x, x, acc) : fmaf(x, x, acc); }
+          } else {
+#pragma unroll 4
+            for (int k = 0; k < cols; ++k) { const float x = hj[k] - hi[k]; acc = fmaf(x, x, acc); }
+          }
         }
+        d[((size_t)b0 * N + r) * NJ32 + j] = acc;
       }
-      d[(size_t)r * NJ32 + j] = acc;
     }
   }
 }
-// dh[n][k] += 2 s_k sum_m (G[m][n] + G[n][m]) (h[n][k] - h[m][k]),  s_k = -1 for the minkowskian space components
-__global__ void pair_dist_bwd_kernel(const float* __restrict__ h, const float* __restrict__ G, int N, int NJ32, int cols, int ld,
-                                     int mink, float* __restrict__ dh) {
+// dh[n][k] += 2 s_k sum_m S[n][m] (h[n][k] - h[m][k]),  S[n][m] = G[m][n] + G[n][m],  s_k = -1 for the minkowskian space
+// components.  One (jet, node, column) per thread, h and G of the CTA's JPB jets staged in shared memory.
+__global__ void __launch_bounds__(256) pair_dist_bwd_kernel(const float* __restrict__ h, const float* __restrict__ G, int B, int N,
+                                                            int NJ32, int cols, int ld, int mink, int JPB, float* __restrict__ dh) {
   extern __shared__ float pd_smem[];
-  float* sh = pd_smem;                  // [N][cols]
-  float* sS = pd_smem + N * cols;       // [N][N + 1]: S[n][m] = G[m][n] + G[n][m]
-  const int b = blockIdx.x;
-  for (int idx = threadIdx.x; idx < N * cols; idx += blockDim.x) {
-    const int n = idx / cols, k = idx - n * cols;
-    sh[idx] = __ldg(h + ((size_t)b * N + n) * ld + k);
-  }
-  const float* Gb = G + (size_t)b * N * NJ32;
-  for (int idx = threadIdx.x; idx < N * N; idx += blockDim.x) {
-    const int n = idx / N, m = idx - n * N;
-    sS[n * (N + 1) + m] = __ldg(Gb + (size_t)n * NJ32 + m);
-  }
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < N * cols; idx += blockDim.x) {
-    const int n = idx / cols, k = idx - n * cols;
-    const float hn = sh[idx];
-    float acc = 0.f;
-    for (int m = 0; m < N; ++m) acc = fmaf(sS[n * (N + 1) + m] + sS[m * (N + 1) + n], hn - sh[m * cols + k], acc);
-    const float sgn = (mink && k > 0) ? -2.f : 2.f;
-    dh[((size_t)b * N + n) * ld + k] += sgn * acc;
+  const int hs = cols | 1, gs = N | 1;
+  float* sh = pd_smem;                       // [JPB][N][hs]
+  float* sG = pd_smem + JPB * N * hs;        // [JPB][N][gs]
+  for (int b0 = blockIdx.x * JPB; b0 < B; b0 += gridDim.x * JPB) {
+    const int nj = min(JPB, B - b0);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nj * N * cols; idx += 256) {
+      const int r = idx / cols, k = idx - r * cols;
+      sh[r * hs + k] = __ldg(h + ((size_t)b0 * N + r) * ld + k);
+    }
+    for (int idx = threadIdx.x; idx < nj * N * N; idx += 256) {
+      const int r = idx / N, m = idx - r * N;
+      sG[r * gs + m] = __ldg(G + ((size_t)b0 * N + r) * NJ32 + m);
+    }
+    __syncthreads();
+    for (int item = threadIdx.x; item < nj * N * cols; item += 256) {
+      const int r = item / cols, k = item - r * cols;
+      const int jl = r / N, n = r - jl * N;
+      const float* hj = sh + jl * N * hs;
+      const float* Gj = sG + jl * N * gs;
+      const float hn = hj[n * hs + k];
+      float acc = 0.f;
+#pragma unroll 2
+      for (int m = 0; m < N; ++m) acc = fmaf(Gj[m * gs + n] + Gj[n * gs + m], hn - hj[m * hs + k], acc);
+      dh[((size_t)b0 * N + r) * ld + k] += ((mink && k > 0) ? -2.f : 2.f) * acc;
+    }
   }
 }
 
@@ -750,9 +771,12 @@ extern "C" int gj_debug_read_bwd2_trace(long long* out) {
   return cudaMemcpyFromSymbol(out, g_b2_trace, sizeof(long long) * 16 * 128) == cudaSuccess ? 0 : 1;
 }
 
+static int pd_jpb(const MPLayout& L) { int j = 256 / L.N; return j < 1 ? 1 : (j > 8 ? 8 : j); }
+static int pd_smem_fwd(const MPLayout& L) { return pd_jpb(L) * L.N * (L.cols | 1) * 4; }
+static int pd_smem_bwd(const MPLayout& L) { return pd_jpb(L) * L.N * ((L.cols | 1) + (L.N | 1)) * 4; }
+
 bool gj_bwd2_supported(const MPLayout& L) {
-  const int pd_smem = (L.N * L.cols + L.N * (L.N + 1)) * 4;
-  return L.Le == 4 && L.E[0] == 32 && L.E[1] == 128 && L.E[2] == 64 && L.E[3] == 16 && L.alpha <= 1.f && pd_smem <= 200 * 1024;
+  return L.Le == 4 && L.E[0] == 32 && L.E[1] == 128 && L.E[2] == 64 && L.E[3] == 16 && L.alpha <= 1.f && pd_smem_bwd(L) <= 200 * 1024;
 }
 
 static int bwd2_grid(const MPLayout& L) { return gj_num_sms(); }
@@ -767,10 +791,12 @@ size_t gj_bwd2_ws_floats(const MPLayout& L) {
 }
 
 int gj_pair_dist_fwd(const MPLayout& L, const float* h, float* d, cudaStream_t stream) {
-  const int rows = L.B * L.N, NJ32 = ((L.N + 31) / 32) * 32;
-  int blocks = (rows + 7) / 8; if (blocks > 8 * gj_num_sms()) blocks = 8 * gj_num_sms();
-  pair_dist_fwd_kernel<<<blocks, 256, 0, stream>>>(h, rows, L.N, NJ32, L.cols, L.ld, L.mink, d);
-  cudaError_t ce = cudaGetLastError();
+  const int NJ32 = ((L.N + 31) / 32) * 32, jpb = pd_jpb(L), smem = pd_smem_fwd(L);
+  int blocks = (L.B + jpb - 1) / jpb; if (blocks > 8 * gj_num_sms()) blocks = 8 * gj_num_sms();
+  cudaError_t ce = cudaFuncSetAttribute(pair_dist_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (ce != cudaSuccess) { gj_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
+  pair_dist_fwd_kernel<<<blocks, 256, smem, stream>>>(h, L.B, L.N, NJ32, L.cols, L.ld, L.mink, jpb, d);
+  ce = cudaGetLastError();
   if (ce != cudaSuccess) { gj_set_error("pair_dist_fwd launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   return GJ_OK;
 }
@@ -816,10 +842,11 @@ int gj_edge_bwd2(const MPLayout& L, const float* h, const float* pq, const float
     sum_dp_parts_kernel<<<blocks, 256, 0, stream>>>(dp_part, (int)njb, rows, L.E[0], dpq);
   }
   {
-    const int pd_smem = (L.N * L.cols + L.N * (L.N + 1)) * 4;
-    ce = cudaFuncSetAttribute(pair_dist_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pd_smem);
+    const int jpb = pd_jpb(L), smem = pd_smem_bwd(L);
+    int blocks = (L.B + jpb - 1) / jpb; if (blocks > 8 * gj_num_sms()) blocks = 8 * gj_num_sms();
+    ce = cudaFuncSetAttribute(pair_dist_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (ce != cudaSuccess) { gj_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
-    pair_dist_bwd_kernel<<<L.B, 256, pd_smem, stream>>>(h, G, L.N, NJ32, L.cols, L.ld, L.mink, dh);
+    pair_dist_bwd_kernel<<<blocks, 256, smem, stream>>>(h, G, L.B, L.N, NJ32, L.cols, L.ld, L.mink, jpb, dh);
   }
   ce = cudaGetLastError();
   if (ce != cudaSuccess) { gj_set_error("edge_bwd2 tail launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }

@@ -81,6 +81,33 @@ __device__ __forceinline__ void mma_ts_elect(uint32_t d_tmem, uint32_t a_tmem, u
       : "memory");
 }
 
+// Same instructions with the 64-bit shared-memory descriptors passed as (low, high) words: the high word (strides, version)
+// is constant across the k-steps of a GEMM and the low word (address) advances by a small constant, which lets ptxas keep
+// each descriptor in one uniform-register pair and advance it with a single 32-bit add per MMA.
+__device__ __forceinline__ void mma_ss_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_ts_lh(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t.reg .b64 db;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t desc_lo(uint64_t d) { return (uint32_t)d; }
+__device__ __forceinline__ uint32_t desc_hi(uint64_t d) { return (uint32_t)(d >> 32); }
+
 // ---- packed arithmetic ------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t bf2_as_u32(__nv_bfloat162 v) { return *reinterpret_cast<uint32_t*>(&v); }
 __device__ __forceinline__ __nv_bfloat162 u32_as_bf2(uint32_t v) { return *reinterpret_cast<__nv_bfloat162*>(&v); }
