@@ -31,7 +31,7 @@
 //
 // TMEM: columns [128 g, 128 g + 128) = slot of group g;  [384,432) dW1 (lane = out feature, column = in feature, column 32
 // = db1);  [432,496) dW2 (lane = in feature, column = out feature);  [496,512) dW3 (M = 64: in feature k at lane
-// (k / 16) * 32 + k % 16, column = out feature) and, at lane offset 16 of the same columns, db2 (M = 64, column 496) and db3 (M = 64, column 504).
+// (k / 16) * 32 + k % 16, column = out feature) and, at lane offset 16 of the same columns, db2 (M = 64, column 496).
 #include <stdlib.h>
 
 #include "tc2_common.cuh"
@@ -40,7 +40,7 @@ namespace {
 using namespace tc2;
 
 struct Bwd2Args {
-  const float* pq; const float* d; const float* params; const float* de;
+  const float* pq; const float* d; const float* params; const float* de; const uint8_t* wimg;
   float* dpq; float* dp_part; float* G; float* part;
   int B, N, NJB, NJ32;
   int pW1, pb1, pW2, pb2, pW3, pb3, pWd, K0, nedge;
@@ -75,7 +75,7 @@ struct Bwd2Smem {
   static constexpr int warp_bytes = 2 * B2_IC * E0 * 4;
   static constexpr int o_zero = o_warp + NWG * 4 * warp_bytes;      // [128 rows][8] zeros: second k-chunk of every bias operand
   static constexpr int total = o_zero + 2048;
-  static constexpr int o_red = o_grp + g_x1;             // [NWG * 4 warps][E0] floats, over group 0's X1 once all GEMMs are done
+  static constexpr int o_red = o_grp + g_x1;             // [NWG * 4 warps][E0 + E3] floats, over group 0's X1 once all GEMMs are done
 };
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
@@ -139,17 +139,9 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args 
   float* s_red = reinterpret_cast<float*>(smem + S::o_red);
 
   // ---- one-time staging ----
-  stage_weight_kmajor<E1, E0>(smem + S::o_w1, A.params + A.pW1, tid, NT);
-  stage_weight_kmajor<E2, E1>(smem + S::o_w2, A.params + A.pW2, tid, NT);
-  stage_weight_kmajor<E3, E2>(smem + S::o_w3, A.params + A.pW3, tid, NT);
-  for (int idx = tid; idx < (E1 + E2 + E3) * 4; idx += NT) {      // bias rows: (hi, lo, 0, 0, 0, 0, 0, 0) as four 32-bit words
-    const int n = idx >> 2, w = idx & 3;
-    const float v = __ldg(A.params + (n < E1 ? A.pb1 + n : (n < E1 + E2 ? A.pb2 + n - E1 : A.pb3 + n - E1 - E2)));
-    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-    const uint32_t word = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
-    reinterpret_cast<uint32_t*>(smem + S::o_b1)[idx] = w == 0 ? word : 0u;
-  }
+  static_assert(S::o_b2 - S::o_b1 == WImage<E0, E1, E2, E3>::o_b2 && S::o_w1 - S::o_b1 == WImage<E0, E1, E2, E3>::o_w1 &&
+                S::o_grp - S::o_b1 == WImage<E0, E1, E2, E3>::bytes, "shared-memory plan embeds the packed parameter image");
+  load_wimage<WImage<E0, E1, E2, E3>::bytes>(smem + S::o_b1, A.wimg, tid, NT);
   for (int idx = tid; idx < 512; idx += NT) reinterpret_cast<uint32_t*>(smem + S::o_zero)[idx] = 0u;
   for (int c = tid; c < E0; c += NT) s_wd[c] = __ldg(A.params + A.pWd + c * A.K0);
   for (int idx = tid; idx < 64; idx += NT) reinterpret_cast<uint32_t*>(smem + S::o_ones)[idx] = 0x3F803F80u;
@@ -270,8 +262,8 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args 
           mma_commit_elect(doneW);
         }
       } else {
-        // dgrad1: acc[64,96) = dz1 (TMEM [0,64)) W1 ; behind the epilogue: [dW1 | db1] += dz1^T [a0 | 1], db2 += dz2^T 1,
-        // db3 += dz3^T 1 (X2 / D3 still hold dz2 / dz3: the next tile overwrites them after its F2 / F3, issued later)
+        // dgrad1: acc[64,96) = dz1 (TMEM [0,64)) W1 ; behind the epilogue: [dW1 | db1] += dz1^T [a0 | 1] and
+        // db2 += dz2^T 1 (X2 still holds dz2: the next tile overwrites it after its F2, which is issued later)
         if (crit) {
           const uint64_t dW1b = make_smem_desc(w1a, 128, E1 * 16);
           const uint32_t i_d1 = make_idesc_bf16(128, E0, 0, 1);
@@ -285,9 +277,6 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args 
           for (int s = 0; s < 8; ++s) mma_bf16_ss_elect(tmem_base + 384, dX1n + (uint64_t)(s * 16), dA0n + (uint64_t)(s * 16), i_g1, 1u);
 #pragma unroll
           for (int s = 0; s < 8; ++s) mma_bf16_ss_elect(tmem_base + 496 + (16u << 16), dX2n + (uint64_t)(s * 16), dOnes, i_c2, 1u);
-          // db3: M = 64 reads 48 channels past the 16 of D3 (the head of X1: finite, rows 16..63 are never read)
-#pragma unroll
-          for (int s = 0; s < 8; ++s) mma_bf16_ss_elect(tmem_base + 504 + (16u << 16), dD3n + (uint64_t)(s * 16), dOnes, i_c2, 1u);
           mma_commit_elect(done2);
         }
       }
@@ -316,7 +305,9 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args 
     size_t node0 = 0;
     int jb = 0;
     uint32_t q[E0 / 2];      // Q_j as bf16 pairs (the forward kernel rounds Q_j the same way)
-    float dq[E0], dwd[E0];
+    float dq[E0], dwd[E0], db3[E3];
+#pragma unroll
+    for (int c = 0; c < E3; ++c) db3[c] = 0.f;
 #pragma unroll
     for (int c = 0; c < E0; ++c) { dwd[c] = 0.f; dq[c] = 0.f; }
 #pragma unroll
@@ -493,6 +484,7 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args 
           const float z0 = __uint_as_float(v[2 * p]), z1 = __uint_as_float(v[2 * p + 1]);
           const float g0v = valid ? def[2 * p] * (z0 > 0.f ? 1.f : alpha) : 0.f;
           const float g1v = valid ? def[2 * p + 1] * (z1 > 0.f ? 1.f : alpha) : 0.f;
+          db3[2 * p] += g0v; db3[2 * p + 1] += g1v;
           o[p] = bf2_as_u32(__floats2bfloat162_rn(g0v, g1v));
         }
         tmem_st8(slot + 48, o);
@@ -616,12 +608,14 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args 
     if (!fresh) flush_dq();      // the group's last (jet, j block) ended mid-way: the next group adds the rest
     if (pending2) { mbar_wait(done2, ph2); ph2 ^= 1u; }      // all of this group's MMAs have completed
     cp_async_wait<0>();
-    // d(wd): lanes by shuffles, warps through shared memory (fixed order); the scratch lies over group 0's X1, which
+    // d(wd), db3: lanes by shuffles, warps through shared memory (fixed order); the scratch lies over group 0's X1, which
     // is free once every group's GEMMs have completed
     tc_fence_before();
     __syncthreads();
 #pragma unroll
-    for (int c = 0; c < E0; ++c) { const float s = gj_warp_sum(dwd[c]); if (lane == 0) s_red[warp * E0 + c] = s; }
+    for (int c = 0; c < E0; ++c) { const float s = gj_warp_sum(dwd[c]); if (lane == 0) s_red[warp * (E0 + E3) + c] = s; }
+#pragma unroll
+    for (int c = 0; c < E3; ++c) { const float s = gj_warp_sum(db3[c]); if (lane == 0) s_red[warp * (E0 + E3) + E0 + c] = s; }
   }
 
   // =================================== gradient read-out ===================================
@@ -630,10 +624,11 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args 
   tc_fence_after();
   float* out = A.part + (size_t)blockIdx.x * A.nedge;
   const bool wrote = range_lo(blockIdx.x * NWG + 1) > range_lo(blockIdx.x * NWG);      // group 0 of this CTA had tiles
-  if (tid < E0) {
+  if (tid < E0 + E3) {
     float s = 0.f;
-    for (int w = 0; w < NWG * 4; ++w) s += s_red[w * E0 + tid];
-    out[A.pWd + tid * A.K0] = s;
+    for (int w = 0; w < NWG * 4; ++w) s += s_red[w * (E0 + E3) + tid];
+    if (tid < E0) out[A.pWd + tid * A.K0] = s;
+    else out[A.pb3 + tid - E0] = s;
   }
   if (warp < 4) {
     const uint32_t lb = tmem_base + ((uint32_t)(warp * 32) << 16);
@@ -669,7 +664,6 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args 
         for (int c = 0; c < 16; ++c) out[A.pW3 + c * E2 + kf] = wrote ? __uint_as_float(v[c]) : 0.f;
       } else {
         out[A.pb2 + warp * 16 + lane - 16] = wrote ? __uint_as_float(v[0]) : 0.f;
-        if (warp == 0) out[A.pb3 + lane - 16] = wrote ? __uint_as_float(v[8]) : 0.f;      // db3: M = 64 rows 0..15 at lanes 16..31, column 504
       }
     }
   }
@@ -784,7 +778,7 @@ static int bwd2_grid(const MPLayout& L) { return gj_num_sms(); }
 // workspace (floats): d | G (B N NJ32 each) | dP partials (NJB > 1) | per-CTA parameter-gradient partials
 size_t gj_bwd2_ws_floats(const MPLayout& L) {
   const size_t njb = (L.N + 31) / 32, rows = (size_t)L.B * L.N;
-  size_t n = 2 * rows * njb * 32 + 64;
+  size_t n = 2 * rows * njb * 32 + 64 + (WImage<32, 128, 64, 16>::bytes + 255) / 256 * 64;
   if (njb > 1) n += njb * rows * L.E[0] + 64;
   n += (size_t)bwd2_grid(L) * L.pV[0] + 64;
   return n;
@@ -809,10 +803,13 @@ int gj_edge_bwd2(const MPLayout& L, const float* h, const float* pq, const float
   Bwd2Args A;
   const size_t njb = (L.N + 31) / 32, rows = (size_t)L.B * L.N;
   const int NJ32 = (int)njb * 32;
+  uint8_t* wimg = reinterpret_cast<uint8_t*>(ws);      // packed bf16 parameter image (WImage), 16-byte aligned
+  ws += (WImage<32, 128, 64, 16>::bytes + 255) / 256 * 64;
   float* d = ws;
   float* G = d + rows * NJ32 + 32;
   float* dp_part = G + rows * NJ32 + 32;
   float* part = njb > 1 ? dp_part + njb * rows * L.E[0] + 64 : dp_part;
+  A.wimg = wimg;
   A.pq = pq; A.d = d; A.params = params; A.de = de; A.dpq = dpq; A.dp_part = dp_part; A.G = G; A.part = part;
   A.B = L.B; A.N = L.N; A.NJB = (int)njb; A.NJ32 = NJ32;
   A.pW1 = L.pW[1]; A.pb1 = L.pb[1]; A.pW2 = L.pW[2]; A.pb2 = L.pb[2]; A.pW3 = L.pW[3]; A.pb3 = L.pb[3];
@@ -826,6 +823,10 @@ int gj_edge_bwd2(const MPLayout& L, const float* h, const float* pq, const float
   long long ng = (long long)grid * NWG;
   if (ng > tasks4) ng = tasks4;
   A.ngroups = (int)(ng < 1 ? 1 : ng);
+  {
+    WImageSrc P{L.pW[1], L.pb[1], L.pW[2], L.pb[2], L.pW[3], L.pb[3]};
+    pack_edge_weights_kernel<32, 128, 64, 16><<<4, 256, 0, stream>>>(params, P, wimg);
+  }
   int rc = gj_pair_dist_fwd(L, h, d, stream);
   if (rc) return rc;
   cudaError_t ce = cudaMemsetAsync(dpq, 0, rows * 2 * L.E[0] * sizeof(float), stream);

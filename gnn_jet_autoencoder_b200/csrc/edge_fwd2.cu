@@ -27,7 +27,7 @@ namespace {
 using namespace tc2;
 
 struct Fwd2Args {
-  const float* h; const float* pq; const float* params; float* e_out;
+  const float* h; const float* pq; const float* params; float* e_out; const uint8_t* wimg;
   int B, N, NJB, cols, ld, mink;
   int Hb, Hs;            // h_i row length (multiple of 4 floats), h_j per-lane row stride (floats, (Hs/4) odd)
   int pW1, pb1, pW2, pb2, pW3, pb3, pWd, K0;
@@ -42,13 +42,16 @@ struct Fwd2Smem {
   static constexpr int o_bar = 0;                       // NWG * 3 mbarriers
   static constexpr int o_slot = 128;
   static constexpr int o_wd = 256;                      // E0 floats
-  static constexpr int o_w1 = 1024;
-  static constexpr int o_w2 = o_w1 + E1 * E0 * 2;
-  static constexpr int o_w3 = o_w2 + E2 * E1 * 2;
-  static constexpr int o_b1 = o_w3 + E3 * E2 * 2;
-  static constexpr int o_b2 = o_b1 + E1 * 32;
-  static constexpr int o_b3 = o_b2 + E2 * 32;
-  static constexpr int o_ones = ((o_b3 + E3 * 32 + 127) / 128) * 128;      // [128 rows][16] constant A chunk of the bias k-step
+  static constexpr int o_img = 1024;                    // packed parameter image (WImage): bias chunks, W1, W2, W3
+  static constexpr int o_b1 = o_img + WImage<E0, E1, E2, E3>::o_b1;
+  static constexpr int o_b2 = o_img + WImage<E0, E1, E2, E3>::o_b2;
+  static constexpr int o_b3 = o_img + WImage<E0, E1, E2, E3>::o_b3;
+  static constexpr int o_w1 = o_img + WImage<E0, E1, E2, E3>::o_w1;
+  static constexpr int o_w2 = o_img + WImage<E0, E1, E2, E3>::o_w2;
+  static constexpr int o_w3 = o_img + WImage<E0, E1, E2, E3>::o_w3;
+  // [128 rows][16] constant A operand of the bias k-step: chunk 0 = (1, 1, 0, ...) per row, chunk 1 = zeros; chunk 1 doubles
+  // as the second k-chunk of every bias B operand
+  static constexpr int o_ones = o_img + WImage<E0, E1, E2, E3>::bytes;
   static constexpr int o_a0 = o_ones + 4096;                               // NWG x [128 rows][E0] bf16, interleaved
   static constexpr int o_warp = o_a0 + NWG * 128 * E0 * 2;
   __host__ __device__ static int warp_bytes(int Hb, int Hs) { return (2 * F2_IC * (E0 + Hb) + 32 * Hs) * 4; }
@@ -141,12 +144,7 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_fwd2_kernel(const Fwd2Args 
   float* s_wd = reinterpret_cast<float*>(smem + S::o_wd);
 
   // ---- one-time staging: weights / biases as bf16 B operands, wd, the constant bias A chunk, barriers, TMEM ----
-  stage_weight_kmajor<E1, E0>(smem + S::o_w1, A.params + A.pW1, tid, NWG * 128);
-  stage_weight_kmajor<E2, E1>(smem + S::o_w2, A.params + A.pW2, tid, NWG * 128);
-  stage_weight_kmajor<E3, E2>(smem + S::o_w3, A.params + A.pW3, tid, NWG * 128);
-  stage_bias_slab<E1>(smem + S::o_b1, A.params + A.pb1, tid, NWG * 128);
-  stage_bias_slab<E2>(smem + S::o_b2, A.params + A.pb2, tid, NWG * 128);
-  stage_bias_slab<E3>(smem + S::o_b3, A.params + A.pb3, tid, NWG * 128);
+  load_wimage<WImage<E0, E1, E2, E3>::bytes>(smem + S::o_img, A.wimg, tid, NWG * 128);
   for (int c = tid; c < E0; c += NWG * 128) s_wd[c] = __ldg(A.params + A.pWd + c * A.K0);
   for (int idx = tid; idx < 1024; idx += NWG * 128)     // ones chunk: k = 0, 1 -> 1.0 (bias hi + lo), k = 2..15 -> 0
     reinterpret_cast<uint32_t*>(smem + S::o_ones)[idx] = (idx < 512 && (idx & 3) == 0) ? 0x3F803F80u : 0u;
@@ -176,8 +174,10 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_fwd2_kernel(const Fwd2Args 
   const uint32_t idesc1 = make_idesc_bf16(128, E1, 0, 0), idesc2 = make_idesc_bf16(128, E2, 0, 0), idesc3 = make_idesc_bf16(128, E3, 0, 0);
   const uint64_t dW1 = wdesc_kmajor(smem_u32(smem + S::o_w1), E1), dW2 = wdesc_kmajor(smem_u32(smem + S::o_w2), E2),
                  dW3 = wdesc_kmajor(smem_u32(smem + S::o_w3), E3);
-  const uint64_t dB1 = wdesc_kmajor(smem_u32(smem + S::o_b1), E1), dB2 = wdesc_kmajor(smem_u32(smem + S::o_b2), E2),
-                 dB3 = wdesc_kmajor(smem_u32(smem + S::o_b3), E3);
+  const uint32_t zero_a = smem_u32(smem + S::o_ones + 2048);
+  const uint64_t dB1 = make_smem_desc(smem_u32(smem + S::o_b1), zero_a - smem_u32(smem + S::o_b1), 128),
+                 dB2 = make_smem_desc(smem_u32(smem + S::o_b2), zero_a - smem_u32(smem + S::o_b2), 128),
+                 dB3 = make_smem_desc(smem_u32(smem + S::o_b3), zero_a - smem_u32(smem + S::o_b3), 128);
   const uint64_t dA0 = make_smem_desc(smem_u32(a0), 2048, 128), dOnes = make_smem_desc(smem_u32(smem + S::o_ones), 2048, 128);
 
   // per-warp staging
@@ -408,13 +408,19 @@ bool gj_fwd2_supported(const MPLayout& L) {
 }
 size_t gj_fwd2_ws_floats(const MPLayout& L) {
   const int njb = (L.N + 31) / 32;
-  return njb > 1 ? (size_t)njb * L.B * L.N * L.E[3] : 0;
+  return (njb > 1 ? (size_t)njb * L.B * L.N * L.E[3] : 0) + (WImage<32, 128, 64, 16>::bytes + 255) / 256 * 64;
 }
 
 int gj_edge_fwd2(const MPLayout& L, const float* h, const float* pq, const float* params, float* e_out, float* ws,
                  cudaStream_t stream) {
   constexpr int NWG = 4;
   Fwd2Args A;
+  A.wimg = reinterpret_cast<const uint8_t*>(ws);      // packed bf16 parameter image, then the per-j-block partial aggregates
+  {
+    WImageSrc P{L.pW[1], L.pb[1], L.pW[2], L.pb[2], L.pW[3], L.pb[3]};
+    pack_edge_weights_kernel<32, 128, 64, 16><<<4, 256, 0, stream>>>(params, P, reinterpret_cast<uint8_t*>(ws));
+  }
+  ws += (WImage<32, 128, 64, 16>::bytes + 255) / 256 * 64;
   A.h = h; A.pq = pq; A.params = params;
   A.B = L.B; A.N = L.N; A.NJB = (L.N + 31) / 32; A.cols = L.cols; A.ld = L.ld; A.mink = L.mink;
   A.e_out = A.NJB > 1 ? ws : e_out;

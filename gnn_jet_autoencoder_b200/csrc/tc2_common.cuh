@@ -161,6 +161,80 @@ __device__ __forceinline__ void stage_bias_slab(uint8_t* dst, const float* __res
     *reinterpret_cast<__nv_bfloat16*>(dst + (k >> 3) * (NOUT * 16) + n * 16 + (k & 7) * 2) = k == 0 ? hi : (k == 1 ? lo : z);
   }
 }
+// ---- packed image of one step's edge-MLP parameters as the kernels hold it in shared memory ----
+// [ b1 | b2 | b3 : bias k-step B operands, chunk 0 only: per out feature (b_hi, b_lo, 0, 0, 0, 0, 0, 0) bf16 ]
+// [ W1 | W2 | W3 : bf16 K-major B operands (N = out feature), interleaved SWIZZLE_NONE layout ]
+// Built once per launch by pack_edge_weights_kernel (one small CTA) and copied by every CTA of the edge kernels with
+// 16-byte loads -- converting 13 K weights per CTA with scattered 2-byte shared stores cost ~10 % of the forward kernel.
+template <int E0, int E1, int E2, int E3>
+struct WImage {
+  static constexpr int o_b1 = 0;
+  static constexpr int o_b2 = o_b1 + E1 * 16;
+  static constexpr int o_b3 = o_b2 + E2 * 16;
+  static constexpr int o_w1 = ((o_b3 + E3 * 16 + 1023) / 1024) * 1024;
+  static constexpr int o_w2 = o_w1 + E1 * E0 * 2;
+  static constexpr int o_w3 = o_w2 + E2 * E1 * 2;
+  static constexpr int bytes = o_w3 + E3 * E2 * 2;
+};
+struct WImageSrc { int pW1, pb1, pW2, pb2, pW3, pb3; };
+
+template <int NOUT>
+__device__ __forceinline__ void pack_bias_chunk(uint8_t* dst, const float* __restrict__ b, int tid, int nthr) {
+  for (int idx = tid; idx < NOUT * 4; idx += nthr) {      // four 32-bit words per out feature
+    const int n = idx >> 2, w = idx & 3;
+    const float v = __ldg(b + n);
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    reinterpret_cast<uint32_t*>(dst)[idx] = w == 0 ? ((uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16)) : 0u;
+  }
+}
+template <int NOUT, int KIN>
+__device__ __forceinline__ void pack_weight_kmajor(uint8_t* dst, const float* __restrict__ W, int tid, int nthr) {
+  // one 16-byte core-matrix row (8 consecutive k of one out feature) per item: coalesced 32-byte reads, 16-byte writes
+  for (int idx = tid; idx < NOUT * (KIN / 8); idx += nthr) {
+    const int n = idx / (KIN / 8), kc = idx - n * (KIN / 8);
+    const float4 a = __ldg(reinterpret_cast<const float4*>(W + n * KIN + kc * 8));
+    const float4 c = __ldg(reinterpret_cast<const float4*>(W + n * KIN + kc * 8) + 1);
+    uint4 o;
+    o.x = bf2_as_u32(__floats2bfloat162_rn(a.x, a.y)); o.y = bf2_as_u32(__floats2bfloat162_rn(a.z, a.w));
+    o.z = bf2_as_u32(__floats2bfloat162_rn(c.x, c.y)); o.w = bf2_as_u32(__floats2bfloat162_rn(c.z, c.w));
+    *reinterpret_cast<uint4*>(dst + kc * (NOUT * 16) + n * 16) = o;
+  }
+}
+template <int NOUT, int KIN>
+__device__ __forceinline__ void pack_weight_kmajor_unaligned(uint8_t* dst, const float* __restrict__ W, int tid, int nthr) {
+  for (int idx = tid; idx < NOUT * KIN; idx += nthr) {
+    const int n = idx / KIN, k = idx - n * KIN;
+    *reinterpret_cast<__nv_bfloat16*>(dst + (k >> 3) * (NOUT * 16) + n * 16 + (k & 7) * 2) = __float2bfloat16_rn(__ldg(W + idx));
+  }
+}
+template <int E0, int E1, int E2, int E3>
+__global__ void __launch_bounds__(256) pack_edge_weights_kernel(const float* __restrict__ params, WImageSrc P, uint8_t* __restrict__ img) {
+  using I = WImage<E0, E1, E2, E3>;
+  const int tid = blockIdx.x * 256 + threadIdx.x, nthr = gridDim.x * 256;
+  for (int idx = tid; idx < (I::o_w1 - (I::o_b3 + E3 * 16)) / 4; idx += nthr) reinterpret_cast<uint32_t*>(img + I::o_b3 + E3 * 16)[idx] = 0u;
+  pack_bias_chunk<E1>(img + I::o_b1, params + P.pb1, tid, nthr);
+  pack_bias_chunk<E2>(img + I::o_b2, params + P.pb2, tid, nthr);
+  pack_bias_chunk<E3>(img + I::o_b3, params + P.pb3, tid, nthr);
+  // the packed parameter block is only 4-byte aligned in general (odd-sized tensors in front of it)
+  const bool al = ((reinterpret_cast<uintptr_t>(params) | (uintptr_t)(P.pW1 * 4) | (uintptr_t)(P.pW2 * 4) | (uintptr_t)(P.pW3 * 4)) & 15) == 0;
+  if (al) {
+    pack_weight_kmajor<E1, E0>(img + I::o_w1, params + P.pW1, tid, nthr);
+    pack_weight_kmajor<E2, E1>(img + I::o_w2, params + P.pW2, tid, nthr);
+    pack_weight_kmajor<E3, E2>(img + I::o_w3, params + P.pW3, tid, nthr);
+  } else {
+    pack_weight_kmajor_unaligned<E1, E0>(img + I::o_w1, params + P.pW1, tid, nthr);
+    pack_weight_kmajor_unaligned<E2, E1>(img + I::o_w2, params + P.pW2, tid, nthr);
+    pack_weight_kmajor_unaligned<E3, E2>(img + I::o_w3, params + P.pW3, tid, nthr);
+  }
+}
+// every CTA: image (global, 16-byte aligned) -> shared memory
+template <int BYTES>
+__device__ __forceinline__ void load_wimage(uint8_t* dst, const uint8_t* __restrict__ img, int tid, int nthr) {
+  static_assert(BYTES % 16 == 0, "image is copied in 16-byte pieces");
+  for (int idx = tid; idx < BYTES / 16; idx += nthr) reinterpret_cast<uint4*>(dst)[idx] = __ldg(reinterpret_cast<const uint4*>(img) + idx);
+}
+
 __device__ __forceinline__ uint64_t wdesc_kmajor(uint32_t saddr, int nout) { return make_smem_desc(saddr, (uint32_t)nout * 16u, 128u); }
 
 // all threads of a tile group wait on the barrier (hardware-suspended try_wait)
