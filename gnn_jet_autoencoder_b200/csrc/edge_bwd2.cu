@@ -684,34 +684,44 @@ __global__ void sum_dp_parts_kernel(const float* __restrict__ part, int njb, siz
 }
 
 // ---- pair distances (node level, O(N^2 H) per jet): d_ij = metric(h_j - h_i) and its adjoint ----
-// A CTA of 8 warps stages the node features of JPB jets in shared memory (row stride cols | 1: conflict-free per-lane
-// rows); a warp then owns whole (jet, i) rows, lane = j.
+// A CTA of 8 warps stages the node features of JPB jets in shared memory, zero padded to a multiple of 4 columns with a
+// row stride of 4 * odd floats (conflict-free 16-byte per-lane rows); a warp then owns whole (jet, i) rows, lane = j.
 // d (B, N, NJ32): row i of jet b at (b N + i) NJ32, columns j >= N are zero
+__device__ __forceinline__ int pd_stride(int cols) { return 4 * ((((cols + 3) >> 2)) | 1); }
 __global__ void __launch_bounds__(256) pair_dist_fwd_kernel(const float* __restrict__ h, int B, int N, int NJ32, int cols, int ld,
                                                             int mink, int JPB, float* __restrict__ d) {
-  extern __shared__ float pd_smem[];
-  const int hs = cols | 1;
+  extern __shared__ float4 pd_smem4[];
+  float* pd_smem = reinterpret_cast<float*>(pd_smem4);
+  const int hs = pd_stride(cols), c4 = (cols + 3) >> 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int b0 = blockIdx.x * JPB; b0 < B; b0 += gridDim.x * JPB) {
     const int nj = min(JPB, B - b0);
     __syncthreads();
-    for (int idx = threadIdx.x; idx < nj * N * cols; idx += 256) {
-      const int r = idx / cols, k = idx - r * cols;
-      pd_smem[r * hs + k] = __ldg(h + ((size_t)b0 * N + r) * ld + k);
+    for (int idx = threadIdx.x; idx < nj * N * 4 * c4; idx += 256) {
+      const int r = idx / (4 * c4), k = idx - r * (4 * c4);
+      pd_smem[r * hs + k] = k < cols ? __ldg(h + ((size_t)b0 * N + r) * ld + k) : 0.f;
     }
     __syncthreads();
     for (int r = warp; r < nj * N; r += 8) {
       const int jl = r / N;
-      const float* hi = pd_smem + r * hs;
+      const float4* hi = reinterpret_cast<const float4*>(pd_smem + r * hs);
       for (int j = lane; j < NJ32; j += 32) {
         float acc = 0.f;
         if (j < N) {
-          const float* hj = pd_smem + (jl * N + j) * hs;
-          if (mink) {
-            for (int k = 0; k < cols; ++k) { const float x = hj[k] - hi[k]; acc = k > 0 ? fmaf(-x, x, acc) : fmaf(x, x, acc); }
+          const float4* hj = reinterpret_cast<const float4*>(pd_smem + (jl * N + j) * hs);
+          if (mink) {      // width 4 only: x0^2 - x1^2 - x2^2 - x3^2 (graphnet.py:320-323)
+            const float4 a = hi[0], b = hj[0];
+            const float x0 = b.x - a.x, x1 = b.y - a.y, x2 = b.z - a.z, x3 = b.w - a.w;
+            acc = x0 * x0 - x1 * x1 - x2 * x2 - x3 * x3;
           } else {
-#pragma unroll 4
-            for (int k = 0; k < cols; ++k) { const float x = hj[k] - hi[k]; acc = fmaf(x, x, acc); }
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll 2
+            for (int k = 0; k < c4; ++k) {
+              const float4 a = hi[k], b = hj[k];
+              const float x0 = b.x - a.x, x1 = b.y - a.y, x2 = b.z - a.z, x3 = b.w - a.w;
+              a0 = fmaf(x0, x0, a0); a1 = fmaf(x1, x1, a1); a0 = fmaf(x2, x2, a0); a1 = fmaf(x3, x3, a1);
+            }
+            acc = a0 + a1;
           }
         }
         d[((size_t)b0 * N + r) * NJ32 + j] = acc;
@@ -720,35 +730,45 @@ __global__ void __launch_bounds__(256) pair_dist_fwd_kernel(const float* __restr
   }
 }
 // dh[n][k] += 2 s_k sum_m S[n][m] (h[n][k] - h[m][k]),  S[n][m] = G[m][n] + G[n][m],  s_k = -1 for the minkowskian space
-// components.  One (jet, node, column) per thread, h and G of the CTA's JPB jets staged in shared memory.
+// components.  One (jet, node, 4 columns) per thread, h and G of the CTA's JPB jets staged in shared memory.
 __global__ void __launch_bounds__(256) pair_dist_bwd_kernel(const float* __restrict__ h, const float* __restrict__ G, int B, int N,
                                                             int NJ32, int cols, int ld, int mink, int JPB, float* __restrict__ dh) {
-  extern __shared__ float pd_smem[];
-  const int hs = cols | 1, gs = N | 1;
+  extern __shared__ float4 pd_smem4[];
+  float* pd_smem = reinterpret_cast<float*>(pd_smem4);
+  const int hs = pd_stride(cols), c4 = (cols + 3) >> 2, gs = N | 1;
   float* sh = pd_smem;                       // [JPB][N][hs]
   float* sG = pd_smem + JPB * N * hs;        // [JPB][N][gs]
   for (int b0 = blockIdx.x * JPB; b0 < B; b0 += gridDim.x * JPB) {
     const int nj = min(JPB, B - b0);
     __syncthreads();
-    for (int idx = threadIdx.x; idx < nj * N * cols; idx += 256) {
-      const int r = idx / cols, k = idx - r * cols;
-      sh[r * hs + k] = __ldg(h + ((size_t)b0 * N + r) * ld + k);
+    for (int idx = threadIdx.x; idx < nj * N * 4 * c4; idx += 256) {
+      const int r = idx / (4 * c4), k = idx - r * (4 * c4);
+      sh[r * hs + k] = k < cols ? __ldg(h + ((size_t)b0 * N + r) * ld + k) : 0.f;
     }
     for (int idx = threadIdx.x; idx < nj * N * N; idx += 256) {
       const int r = idx / N, m = idx - r * N;
       sG[r * gs + m] = __ldg(G + ((size_t)b0 * N + r) * NJ32 + m);
     }
     __syncthreads();
-    for (int item = threadIdx.x; item < nj * N * cols; item += 256) {
-      const int r = item / cols, k = item - r * cols;
+    for (int item = threadIdx.x; item < nj * N * c4; item += 256) {
+      const int r = item / c4, kq = item - r * c4;
       const int jl = r / N, n = r - jl * N;
-      const float* hj = sh + jl * N * hs;
+      const float* hj = sh + jl * N * hs + 4 * kq;
       const float* Gj = sG + jl * N * gs;
-      const float hn = hj[n * hs + k];
-      float acc = 0.f;
+      const float4 hn = *reinterpret_cast<const float4*>(hj + n * hs);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 2
-      for (int m = 0; m < N; ++m) acc = fmaf(Gj[m * gs + n] + Gj[n * gs + m], hn - hj[m * hs + k], acc);
-      dh[((size_t)b0 * N + r) * ld + k] += ((mink && k > 0) ? -2.f : 2.f) * acc;
+      for (int m = 0; m < N; ++m) {
+        const float sv = Gj[m * gs + n] + Gj[n * gs + m];
+        const float4 hm = *reinterpret_cast<const float4*>(hj + m * hs);
+        acc.x = fmaf(sv, hn.x - hm.x, acc.x); acc.y = fmaf(sv, hn.y - hm.y, acc.y);
+        acc.z = fmaf(sv, hn.z - hm.z, acc.z); acc.w = fmaf(sv, hn.w - hm.w, acc.w);
+      }
+      float* dst = dh + ((size_t)b0 * N + r) * ld + 4 * kq;
+      const float av[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (4 * kq + q < cols) dst[q] += ((mink && 4 * kq + q > 0) ? -2.f : 2.f) * av[q];
     }
   }
 }
@@ -766,8 +786,9 @@ extern "C" int gj_debug_read_bwd2_trace(long long* out) {
 }
 
 static int pd_jpb(const MPLayout& L) { int j = 256 / L.N; return j < 1 ? 1 : (j > 8 ? 8 : j); }
-static int pd_smem_fwd(const MPLayout& L) { return pd_jpb(L) * L.N * (L.cols | 1) * 4; }
-static int pd_smem_bwd(const MPLayout& L) { return pd_jpb(L) * L.N * ((L.cols | 1) + (L.N | 1)) * 4; }
+static int pd_hs(const MPLayout& L) { return 4 * (((L.cols + 3) >> 2) | 1); }
+static int pd_smem_fwd(const MPLayout& L) { return pd_jpb(L) * L.N * pd_hs(L) * 4; }
+static int pd_smem_bwd(const MPLayout& L) { return pd_jpb(L) * L.N * (pd_hs(L) + (L.N | 1)) * 4; }
 
 bool gj_bwd2_supported(const MPLayout& L) {
   return L.Le == 4 && L.E[0] == 32 && L.E[1] == 128 && L.E[2] == 64 && L.E[3] == 16 && L.alpha <= 1.f && pd_smem_bwd(L) <= 200 * 1024;
