@@ -357,6 +357,133 @@ __global__ void __launch_bounds__(NK_THREADS) node_post_bwd_kernel(const PostArg
   for (int idx = threadIdx.x; idx < A.n_node_params; idx += NK_THREADS) out[idx] = dpar[idx];
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// thread-per-row forward kernels for the usual small widths (compile-time sizes: every loop unrolls, activations live in
+// registers, weights are read as warp-broadcast 16-byte shared-memory loads -> FFMA bound)
+// ---------------------------------------------------------------------------------------------------------
+#define NF_THREADS 128
+// y[o] = bias[o] + sum_k W[o][k] x[k]  for o in [o0, o0 + 4): W rows are KP floats long (zero padded), in shared memory
+template <int KP>
+__device__ __forceinline__ float4 nf_dot4(const float (&x)[KP], const float* __restrict__ W, const float* __restrict__ bias, int o0) {
+  float acc[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    acc[q] = bias[o0 + q];
+    const float4* w = reinterpret_cast<const float4*>(W + (o0 + q) * KP);
+#pragma unroll
+    for (int k = 0; k < KP / 4; ++k) { const float4 v = w[k]; acc[q] = dot4(make_float4(x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]), v, acc[q]); }
+  }
+  return make_float4(acc[0], acc[1], acc[2], acc[3]);
+}
+
+// Global traffic goes through shared-memory tiles of NF_THREADS rows so that it is coalesced (a thread reading / writing
+// its own row straight from HBM touches 32 sectors per instruction); tile rows have a stride of 4 * odd floats, so the
+// per-thread 16-byte accesses are conflict free.
+// PQ[row][0..32) = Wa h + b0 ; PQ[row][32..64) = Wb h      (E0 = 32; KP = columns of h present in memory, padded to 4)
+template <int KP>
+__global__ void __launch_bounds__(NF_THREADS) node_pre_fwd_fast_kernel(int rows, int H, int cols, int ld, int K0, const float* __restrict__ h,
+                                                                       const float* __restrict__ w0, const float* __restrict__ b0,
+                                                                       float* __restrict__ pq) {
+  constexpr int XS = KP + 4, OS = 36;
+  __shared__ __align__(16) float W[64 * KP];
+  __shared__ float bias[64];
+  __shared__ __align__(16) float sX[NF_THREADS * XS];
+  __shared__ __align__(16) float sO[NF_THREADS * OS];
+  for (int idx = threadIdx.x; idx < 64 * KP; idx += NF_THREADS) {
+    const int o = idx / KP, k = idx - o * KP;
+    W[idx] = k < cols ? __ldg(w0 + (o & 31) * K0 + (o < 32 ? k : H + k)) : 0.f;
+  }
+  if (threadIdx.x < 64) bias[threadIdx.x] = threadIdx.x < 32 ? __ldg(b0 + threadIdx.x) : 0.f;
+  for (int row0 = blockIdx.x * NF_THREADS; row0 < rows; row0 += gridDim.x * NF_THREADS) {
+    const int nrows = min(NF_THREADS, rows - row0);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nrows * KP; idx += NF_THREADS) {
+      const int r = idx / KP, k = idx - r * KP;
+      sX[r * XS + k] = k < cols ? __ldg(h + (size_t)(row0 + r) * ld + k) : 0.f;
+    }
+    __syncthreads();
+    float x[KP];
+#pragma unroll
+    for (int k = 0; k < KP; k += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(sX + threadIdx.x * XS + k);
+      x[k] = v.x; x[k + 1] = v.y; x[k + 2] = v.z; x[k + 3] = v.w;
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {      // P then Q: 32 outputs per pass through the output tile
+#pragma unroll
+      for (int o0 = 0; o0 < 32; o0 += 4)
+        *reinterpret_cast<float4*>(sO + threadIdx.x * OS + o0) = nf_dot4<KP>(x, W, bias, 32 * half + o0);
+      __syncthreads();
+      for (int idx = threadIdx.x; idx < nrows * 8; idx += NF_THREADS) {
+        const int r = idx >> 3, q = idx & 7;
+        *reinterpret_cast<float4*>(pq + (size_t)(row0 + r) * 64 + 32 * half + 4 * q) = *reinterpret_cast<const float4*>(sO + r * OS + 4 * q);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// h' = leaky(V1 leaky(V0 [e | h] + c0) + c1)      (two node layers; I0P, O0P, O1P = widths padded to 4; EL = 16)
+template <int I0P, int O0P, int O1P>
+__global__ void __launch_bounds__(NF_THREADS) node_post_fwd_fast_kernel(int rows, int EL, int cols, int ld, int I0, int O0, int O1, float alpha,
+                                                                        const float* __restrict__ e, const float* __restrict__ h,
+                                                                        const float* __restrict__ V0, const float* __restrict__ c0,
+                                                                        const float* __restrict__ V1, const float* __restrict__ c1,
+                                                                        float* __restrict__ h_out) {
+  constexpr int XS = 4 * ((I0P / 4) | 1), OS = 4 * ((O1P / 4) | 1);
+  __shared__ __align__(16) float sV0[O0P * I0P];
+  __shared__ __align__(16) float sV1[O1P * O0P];
+  __shared__ float sc0[O0P], sc1[O1P];
+  __shared__ __align__(16) float sX[NF_THREADS * XS];
+  __shared__ __align__(16) float sO[NF_THREADS * OS];
+  for (int idx = threadIdx.x; idx < O0P * I0P; idx += NF_THREADS) {
+    const int o = idx / I0P, k = idx - o * I0P;
+    sV0[idx] = (o < O0 && k < I0) ? __ldg(V0 + o * I0 + k) : 0.f;
+  }
+  for (int idx = threadIdx.x; idx < O1P * O0P; idx += NF_THREADS) {
+    const int o = idx / O0P, k = idx - o * O0P;
+    sV1[idx] = (o < O1 && k < O0) ? __ldg(V1 + o * O0 + k) : 0.f;
+  }
+  for (int o = threadIdx.x; o < O0P; o += NF_THREADS) sc0[o] = o < O0 ? __ldg(c0 + o) : 0.f;
+  for (int o = threadIdx.x; o < O1P; o += NF_THREADS) sc1[o] = o < O1 ? __ldg(c1 + o) : 0.f;
+  for (int row0 = blockIdx.x * NF_THREADS; row0 < rows; row0 += gridDim.x * NF_THREADS) {
+    const int nrows = min(NF_THREADS, rows - row0);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nrows * 16; idx += NF_THREADS) {      // e: 16 columns, rows contiguous
+      const int r = idx >> 4, k = idx & 15;
+      sX[r * XS + k] = __ldg(e + (size_t)(row0 + r) * EL + k);
+    }
+    for (int idx = threadIdx.x; idx < nrows * (I0P - 16); idx += NF_THREADS) {
+      const int r = idx / (I0P - 16), k = idx - r * (I0P - 16);
+      sX[r * XS + 16 + k] = k < cols ? __ldg(h + (size_t)(row0 + r) * ld + k) : 0.f;
+    }
+    __syncthreads();
+    float x[I0P];
+#pragma unroll
+    for (int k = 0; k < I0P; k += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(sX + threadIdx.x * XS + k);
+      x[k] = v.x; x[k + 1] = v.y; x[k + 2] = v.z; x[k + 3] = v.w;
+    }
+    float y0[O0P];
+#pragma unroll
+    for (int o0 = 0; o0 < O0P; o0 += 4) {
+      const float4 v = nf_dot4<I0P>(x, sV0, sc0, o0);
+      y0[o0] = fmaxf(v.x, alpha * v.x); y0[o0 + 1] = fmaxf(v.y, alpha * v.y); y0[o0 + 2] = fmaxf(v.z, alpha * v.z); y0[o0 + 3] = fmaxf(v.w, alpha * v.w);
+    }
+#pragma unroll
+    for (int o0 = 0; o0 < O1P; o0 += 4) {
+      const float4 v = nf_dot4<O0P>(y0, sV1, sc1, o0);
+      *reinterpret_cast<float4*>(sO + threadIdx.x * OS + o0) =
+          make_float4(fmaxf(v.x, alpha * v.x), fmaxf(v.y, alpha * v.y), fmaxf(v.z, alpha * v.z), fmaxf(v.w, alpha * v.w));
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nrows * O1; idx += NF_THREADS) {
+      const int r = idx / O1, o = idx - r * O1;
+      h_out[(size_t)(row0 + r) * O1 + o] = sO[r * OS + o];
+    }
+  }
+}
+
 // Fixed-order reduction of per-CTA partials: block = 32 outputs x 8 slices; slice y sums partials y, y+8, ... and the
 // 8 slice sums are combined through shared memory in slice order (deterministic for a given grid size).
 #define RED_SLICES 8
@@ -487,7 +614,24 @@ static int nk_set_smem(K kern, int bytes) {
   return GJ_OK;
 }
 
+static int nf_grid(int rows) {
+  int blocks = (rows + NF_THREADS - 1) / NF_THREADS, cap = gj_num_sms() * 4;
+  return blocks < cap ? (blocks > 0 ? blocks : 1) : cap;
+}
+
 int gj_node_pre_fwd(const MPLayout& L, const float* h, const float* params, float* pq, cudaStream_t st) {
+  if (L.E[0] == 32 && L.E0p == 32 && L.cols <= 32) {      // thread-per-row kernel (the usual first edge width)
+    const int rows = L.B * L.N, kp = L.cols <= 4 ? 4 : (L.cols <= 8 ? 8 : (L.cols <= 16 ? 16 : 32));
+    const float* w0 = params + L.pW[0];
+    const float* b0 = params + L.pb[0];
+    const int grid = nf_grid(rows);
+    if (kp == 4) node_pre_fwd_fast_kernel<4><<<grid, NF_THREADS, 0, st>>>(rows, L.H, L.cols, L.ld, L.K[0], h, w0, b0, pq);
+    else if (kp == 8) node_pre_fwd_fast_kernel<8><<<grid, NF_THREADS, 0, st>>>(rows, L.H, L.cols, L.ld, L.K[0], h, w0, b0, pq);
+    else if (kp == 16) node_pre_fwd_fast_kernel<16><<<grid, NF_THREADS, 0, st>>>(rows, L.H, L.cols, L.ld, L.K[0], h, w0, b0, pq);
+    else node_pre_fwd_fast_kernel<32><<<grid, NF_THREADS, 0, st>>>(rows, L.H, L.cols, L.ld, L.K[0], h, w0, b0, pq);
+    NK_CHECK_LAUNCH("node_pre_fwd launch");
+    return GJ_OK;
+  }
   PreArgs A; int bytes = pre_plan(L, &A, false);
   if (bytes < 0) { gj_set_error("node_pre_fwd: widths do not fit shared memory"); return GJ_ERR_SMEM; }
   if (int rc = nk_set_smem(node_pre_fwd_kernel, bytes)) return rc;
@@ -515,7 +659,24 @@ int gj_node_pre_bwd(const MPLayout& L, const float* h, const float* params, cons
   return GJ_OK;
 }
 
+template <int I0P, int O0P, int O1P>
+static void nf_post_launch(const MPLayout& L, const float* e, const float* h, const float* params, float* h_out, cudaStream_t st) {
+  const int rows = L.B * L.N;
+  node_post_fwd_fast_kernel<I0P, O0P, O1P><<<nf_grid(rows), NF_THREADS, 0, st>>>(
+      rows, L.EL, L.cols, L.ld, L.I[0], L.O[0], L.O[1], L.alpha, e, h, params + L.pV[0], params + L.pc[0], params + L.pV[1], params + L.pc[1], h_out);
+}
+
 int gj_node_post_fwd(const MPLayout& L, const float* e, const float* h, const float* params, float* h_out, cudaStream_t st) {
+  if (L.Ln == 2 && L.EL == 16 && L.alpha <= 1.f && L.cols <= L.H) {      // thread-per-row kernels for the usual node widths
+    const int i0p = (L.I[0] + 3) & ~3, o0p = (L.O[0] + 3) & ~3, o1p = (L.O[1] + 3) & ~3;
+    bool done = true;
+    if (i0p == 32 && o0p == 16 && o1p == 32) nf_post_launch<32, 16, 32>(L, e, h, params, h_out, st);
+    else if (i0p == 48 && o0p == 32 && o1p == 8) nf_post_launch<48, 32, 8>(L, e, h, params, h_out, st);
+    else if (i0p == 24 && o0p == 8 && o1p == 20) nf_post_launch<24, 8, 20>(L, e, h, params, h_out, st);
+    else if (i0p == 24 && o0p == 8 && o1p == 4) nf_post_launch<24, 8, 4>(L, e, h, params, h_out, st);
+    else done = false;
+    if (done) { NK_CHECK_LAUNCH("node_post_fwd launch"); return GJ_OK; }
+  }
   PostArgs A; int bytes = post_plan(L, &A, false);
   if (bytes < 0) { gj_set_error("node_post_fwd: widths do not fit shared memory"); return GJ_ERR_SMEM; }
   if (int rc = nk_set_smem(node_post_fwd_kernel, bytes)) return rc;
