@@ -54,6 +54,8 @@ SIGNATURES = {
     "gj_linear_fwd": (C.c_int, [_I, _I, _I, _P, _P, _P, _P, _P]),
     "gj_linear_bwd_workspace": (_SZ, [_I, _I, _I]),
     "gj_linear_bwd": (C.c_int, [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "gj_bench_edge_fwd_only": (C.c_int, [C.POINTER(MPDesc), _P, _P, _P, _P, _SZ, _P]),
+    "gj_bench_edge_bwd_only": (C.c_int, [C.POINTER(MPDesc), _P, _P, _P, _P, _P, _SZ, _P]),
     "gj_mp_plan_info": (C.c_int, [C.POINTER(MPDesc), C.POINTER(C.c_int32)]),
     "gj_umma_selftest": (C.c_int, [_I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "gj_last_error": (C.c_char_p, []),

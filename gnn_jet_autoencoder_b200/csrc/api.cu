@@ -44,11 +44,13 @@ int gj_edge_bwd_simt(MPLayout, const float*, const float*, const float*, const f
 int gj_edge_fwd_tc(MPLayout, const float*, const float*, const float*, float*, cudaStream_t);
 bool gj_fwd2_supported(const MPLayout&);
 size_t gj_fwd2_ws_floats(const MPLayout&);
-int gj_edge_fwd2(const MPLayout&, const float*, const float*, const float*, float*, float*, cudaStream_t);
+int gj_edge_fwd2(const MPLayout&, const float*, const float*, const float*, float*, float*, cudaStream_t, bool);
 bool gj_tc_v1_forced();
+void gj_fwd2_plan(const MPLayout&, int*, int*);
+void gj_bwd2_plan(const MPLayout&, int*, int*);
 bool gj_bwd2_supported(const MPLayout&);
 size_t gj_bwd2_ws_floats(const MPLayout&);
-int gj_edge_bwd2(const MPLayout&, const float*, const float*, const float*, const float*, float*, float*, float*, float*, cudaStream_t);
+int gj_edge_bwd2(const MPLayout&, const float*, const float*, const float*, const float*, float*, float*, float*, float*, cudaStream_t, bool);
 size_t gj_edge_bwd_tc_ws_floats(const MPLayout&);
 int gj_edge_bwd_tc(MPLayout, const float*, const float*, const float*, const float*, float*, float*, float*, float*,
                    cudaStream_t);
@@ -127,7 +129,7 @@ int gj_mp_step_fwd(const gj_mp_desc* d, const float* h, const float* params, flo
   float* ws = (float*)workspace;
   cudaStream_t st = (cudaStream_t)stream;
   if ((rc = gj_node_pre_fwd(L, h, params, ws + w.pq, st))) return rc;
-  if (use_tc(L, d->precision) && gj_fwd2_supported(L) && !gj_tc_v1_forced()) rc = gj_edge_fwd2(L, h, ws + w.pq, params, e_out, ws + w.epart, st);
+  if (use_tc(L, d->precision) && gj_fwd2_supported(L) && !gj_tc_v1_forced()) rc = gj_edge_fwd2(L, h, ws + w.pq, params, e_out, ws + w.epart, st, false);
   else rc = use_tc(L, d->precision) ? gj_edge_fwd_tc(L, h, ws + w.pq, params, e_out, st)
                                     : gj_edge_fwd_simt(L, h, ws + w.pq, params, e_out, st);
   if (rc) return rc;
@@ -158,7 +160,7 @@ int gj_mp_step_bwd(const gj_mp_desc* d, const float* h, const float* e, const fl
   // recompute P|Q, then the edge adjoint: dP|dQ, distance-path dh, edge parameter gradients
   if ((rc = gj_node_pre_fwd(L, h, params, ws + w.pq, st))) return rc;
   if (use_tc(L, d->precision) && gj_bwd2_supported(L) && !gj_tc_v1_forced())
-    rc = gj_edge_bwd2(L, h, ws + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.part, st);
+    rc = gj_edge_bwd2(L, h, ws + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.part, st, false);
   else
     rc = use_tc(L, d->precision) ? gj_edge_bwd_tc(L, h, ws + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.part, st)
                                  : gj_edge_bwd_simt(L, h, ws + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.part, st);
@@ -220,12 +222,44 @@ int gj_latent_mean_bwd(int32_t batch, int32_t num_nodes, int32_t width, const fl
   return gj_latent_mean_bwd_launch(batch, num_nodes, width, dz, dy, (cudaStream_t)stream);
 }
 
+/* Measurement hooks (declared in the header under "benchmark support"): relaunch ONLY the fused edge kernel of a step on
+ * the workspace that a preceding full gj_mp_step_fwd / gj_mp_step_bwd call with the same arguments has populated. */
+int gj_bench_edge_fwd_only(const gj_mp_desc* d, const float* h, const float* params, float* e_out, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  g_err[0] = 0;
+  MPLayout L; const char* why;
+  int rc = gj_fill_arch(d, &L, &why);
+  if (rc || !h || !params || !e_out || !workspace) { gj_set_error("gj_bench_edge_fwd_only: %s", rc ? why : "null pointer"); return GJ_ERR_INVALID; }
+  if (!(use_tc(L, d->precision) && gj_fwd2_supported(L))) { gj_set_error("gj_bench_edge_fwd_only: step does not run the fused tensor-core kernel"); return GJ_ERR_INVALID; }
+  const StepWs w = plan_ws(L, d->precision, false);
+  if (workspace_bytes < w.total * sizeof(float)) { gj_set_error("gj_bench_edge_fwd_only: workspace too small"); return GJ_ERR_WORKSPACE; }
+  float* ws = (float*)workspace;
+  return gj_edge_fwd2(L, h, ws + w.pq, params, e_out, ws + w.epart, (cudaStream_t)stream, true);
+}
+
+int gj_bench_edge_bwd_only(const gj_mp_desc* d, const float* h, const float* params, float* dh, float* dparams, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  g_err[0] = 0;
+  MPLayout L; const char* why;
+  int rc = gj_fill_arch(d, &L, &why);
+  if (rc || !h || !params || !dh || !dparams || !workspace) { gj_set_error("gj_bench_edge_bwd_only: %s", rc ? why : "null pointer"); return GJ_ERR_INVALID; }
+  if (!(use_tc(L, d->precision) && gj_bwd2_supported(L))) { gj_set_error("gj_bench_edge_bwd_only: step does not run the fused tensor-core kernel"); return GJ_ERR_INVALID; }
+  const StepWs w = plan_ws(L, d->precision, true);
+  if (workspace_bytes < w.total * sizeof(float)) { gj_set_error("gj_bench_edge_bwd_only: workspace too small"); return GJ_ERR_WORKSPACE; }
+  float* ws = (float*)workspace;
+  return gj_edge_bwd2(L, h, ws + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.part, (cudaStream_t)stream, true);
+}
+
 int gj_mp_plan_info(const gj_mp_desc* d, int32_t* info) {
   g_err[0] = 0;
   MPLayout L; const char* why;
   int rc = gj_fill_arch(d, &L, &why);
   if (rc || !info) { gj_set_error("gj_mp_plan_info: %s", rc ? why : "null pointer"); return GJ_ERR_INVALID; }
   gj_tc_plan_info(L, info);
+  if (!gj_tc_v1_forced()) {      // the second-generation kernels take over where their widths are compiled in
+    if (gj_fwd2_supported(L)) gj_fwd2_plan(L, info + 0, info + 1);
+    if (gj_bwd2_supported(L)) gj_bwd2_plan(L, info + 2, info + 3);
+  }
   return GJ_OK;
 }
 

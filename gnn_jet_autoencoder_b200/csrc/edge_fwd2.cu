@@ -406,17 +406,23 @@ extern "C" int gj_debug_read_fwd2_trace(long long* out) {
 bool gj_fwd2_supported(const MPLayout& L) {
   return L.Le == 4 && L.E[0] == 32 && L.E[1] == 128 && L.E[2] == 64 && L.E[3] == 16 && L.alpha <= 1.f && L.cols <= 64;
 }
+// shared-memory bytes / TMEM columns of the forward kernel for this step (gj_mp_plan_info)
+void gj_fwd2_plan(const MPLayout& L, int* smem_bytes, int* tmem_cols) {
+  const int Hb = (L.cols + 3) & ~3, Hs = 4 * ((Hb >> 2) | 1);
+  *smem_bytes = Fwd2Smem<32, 128, 64, 16, 4>::total(Hb, Hs);
+  *tmem_cols = 512;
+}
 size_t gj_fwd2_ws_floats(const MPLayout& L) {
   const int njb = (L.N + 31) / 32;
   return (njb > 1 ? (size_t)njb * L.B * L.N * L.E[3] : 0) + (WImage<32, 128, 64, 16>::bytes + 255) / 256 * 64;
 }
 
 int gj_edge_fwd2(const MPLayout& L, const float* h, const float* pq, const float* params, float* e_out, float* ws,
-                 cudaStream_t stream) {
+                 cudaStream_t stream, bool kernel_only) {
   constexpr int NWG = 4;
   Fwd2Args A;
   A.wimg = reinterpret_cast<const uint8_t*>(ws);      // packed bf16 parameter image, then the per-j-block partial aggregates
-  {
+  if (!kernel_only) {
     WImageSrc P{L.pW[1], L.pb[1], L.pW[2], L.pb[2], L.pW[3], L.pb[3]};
     pack_edge_weights_kernel<32, 128, 64, 16><<<4, 256, 0, stream>>>(params, P, reinterpret_cast<uint8_t*>(ws));
   }
@@ -445,6 +451,7 @@ int gj_edge_fwd2(const MPLayout& L, const float* h, const float* pq, const float
   kern<<<grid, NWG * 128, smem, stream>>>(A);
   ce = cudaGetLastError();
   if (ce != cudaSuccess) { gj_set_error("edge_fwd2 launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
+  if (kernel_only) return GJ_OK;
   if (A.NJB > 1) {
     const size_t n = (size_t)L.B * L.N * L.E[3];
     int blocks = (int)((n + 255) / 256); if (blocks > 4 * gj_num_sms()) blocks = 4 * gj_num_sms();

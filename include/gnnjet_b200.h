@@ -135,6 +135,16 @@ size_t gj_linear_bwd_workspace(int32_t rows, int32_t in_f, int32_t out_f);
 int gj_linear_bwd(int32_t rows, int32_t in_f, int32_t out_f, const float* x, const float* w, const float* dy,
                   float* dx, float* dw, float* db, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Benchmark support (bench.py times the dominant kernel alone with these): relaunch ONLY the fused tensor-core edge
+ * kernel of the step -- no node-level kernels, no reductions -- on the workspace that a preceding full gj_mp_step_fwd /
+ * gj_mp_step_bwd call with the SAME arguments has populated (P|Q, pair distances, de, packed weights live there).
+ * GJ_ERR_INVALID if the step does not run the fused tensor-core kernels (fp32 mode, other widths).  Results of the
+ * backward relaunch are not meaningful (dQ accumulates onto the previous launch). */
+int gj_bench_edge_fwd_only(const gj_mp_desc* d, const float* h, const float* params, float* e_out,
+                           void* workspace, size_t workspace_bytes, void* stream);
+int gj_bench_edge_bwd_only(const gj_mp_desc* d, const float* h, const float* params, float* dh, float* dparams,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
 /* Resource plan of the tensor-core (GJ_PREC_BF16) edge kernels for this step (host only, no device work):
  * info[0] forward shared-memory bytes per CTA, info[1] forward TMEM columns, info[2] backward shared-memory bytes
  * (0: these widths are not covered and the backward runs the fp32 kernel), info[3] backward TMEM columns. */
