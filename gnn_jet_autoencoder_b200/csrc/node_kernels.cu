@@ -362,6 +362,7 @@ __global__ void __launch_bounds__(NK_THREADS) node_post_bwd_kernel(const PostArg
 // registers, weights are read as warp-broadcast 16-byte shared-memory loads -> FFMA bound)
 // ---------------------------------------------------------------------------------------------------------
 #define NF_THREADS 128
+#define NF_BWD_CTAS_PER_SM 4      // adjoint kernels: CTAs per SM the grid is sized for (one parameter-gradient partial per CTA)
 // y[o] = bias[o] + sum_k W[o][k] x[k]  for o in [o0, o0 + 4): W rows are KP floats long (zero padded), in shared memory
 template <int KP>
 __device__ __forceinline__ float4 nf_dot4(const float (&x)[KP], const float* __restrict__ W, const float* __restrict__ bias, int o0) {
@@ -379,6 +380,19 @@ __device__ __forceinline__ float4 nf_dot4(const float (&x)[KP], const float* __r
 // Global traffic goes through shared-memory tiles of NF_THREADS rows so that it is coalesced (a thread reading / writing
 // its own row straight from HBM touches 32 sectors per instruction); tile rows have a stride of 4 * odd floats, so the
 // per-thread 16-byte accesses are conflict free.
+template <int KP>
+__device__ __forceinline__ float4 nf_dot4_nobias(const float (&x)[KP], const float* __restrict__ W, int o0) {
+  float acc[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    acc[q] = 0.f;
+    const float4* w = reinterpret_cast<const float4*>(W + (o0 + q) * KP);
+#pragma unroll
+    for (int k = 0; k < KP / 4; ++k) { const float4 v = w[k]; acc[q] = dot4(make_float4(x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]), v, acc[q]); }
+  }
+  return make_float4(acc[0], acc[1], acc[2], acc[3]);
+}
+
 // PQ[row][0..32) = Wa h + b0 ; PQ[row][32..64) = Wb h      (E0 = 32; KP = columns of h present in memory, padded to 4)
 template <int KP>
 __global__ void __launch_bounds__(NF_THREADS) node_pre_fwd_fast_kernel(int rows, int H, int cols, int ld, int K0, const float* __restrict__ h,
@@ -482,6 +496,162 @@ __global__ void __launch_bounds__(NF_THREADS) node_post_fwd_fast_kernel(int rows
       h_out[(size_t)(row0 + r) * O1 + o] = sO[r * OS + o];
     }
   }
+}
+
+// ---- thread-per-row adjoints: dgrad per thread from registers, wgrad as a second pass over the CTA's row tile ----
+// Weight gradients: the O x KP outputs are dealt out in units of 4 consecutive k; a thread keeps its units in registers
+// across all tiles of the CTA and sweeps the tile's rows, reading g[r][o] and the 16 bytes y[r][4 k4 ..] from the tiles.
+template <int UNITS>
+struct NfAcc { float4 v[UNITS]; float b[UNITS]; };
+
+// acc[u] += sum_r G[r][o_u] * Y[r][4 k4_u ..] ; bacc[u] += sum_r G[r][o_u] (used only where k4_u == 0)
+template <int KP4, int NOUT, int UNITS>
+__device__ __forceinline__ void nf_wgrad_tile(NfAcc<UNITS>& acc, const float* __restrict__ G, int gs, const float* __restrict__ Y, int ys, int nrows) {
+  int o[UNITS], k4[UNITS];
+#pragma unroll
+  for (int u = 0; u < UNITS; ++u) { const int unit = threadIdx.x + u * NF_THREADS; o[u] = unit / KP4; k4[u] = unit - o[u] * KP4; }
+  for (int r = 0; r < nrows; ++r) {
+#pragma unroll
+    for (int u = 0; u < UNITS; ++u) {
+      if (o[u] < NOUT) {
+        const float g = G[r * gs + o[u]];
+        const float4 y = *reinterpret_cast<const float4*>(Y + r * ys + 4 * k4[u]);
+        acc.v[u].x = fmaf(g, y.x, acc.v[u].x); acc.v[u].y = fmaf(g, y.y, acc.v[u].y);
+        acc.v[u].z = fmaf(g, y.z, acc.v[u].z); acc.v[u].w = fmaf(g, y.w, acc.v[u].w);
+        acc.b[u] += g;
+      }
+    }
+  }
+}
+// per-CTA partial: dW[o][k] (row length K, unpadded) and db[o]
+template <int KP4, int NOUT, int UNITS>
+__device__ __forceinline__ void nf_wgrad_store(const NfAcc<UNITS>& acc, float* __restrict__ dW, float* __restrict__ db, int O, int K) {
+#pragma unroll
+  for (int u = 0; u < UNITS; ++u) {
+    const int unit = threadIdx.x + u * NF_THREADS, o = unit / KP4, k4 = unit - o * KP4;
+    if (o < O && o < NOUT) {
+      const float v[4] = {acc.v[u].x, acc.v[u].y, acc.v[u].z, acc.v[u].w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) if (4 * k4 + q < K) dW[o * K + 4 * k4 + q] = v[q];
+      if (k4 == 0 && db) db[o] = acc.b[u];
+    }
+  }
+}
+
+// adjoint of the two-layer node MLP: de (rows, 16), dh (rows, ld; first `cols` columns OVERWRITTEN), per-CTA partial of the
+// node parameters in packed order [V0 | c0 | V1 | c1]
+template <int I0P, int O0P, int O1P>
+__global__ void __launch_bounds__(NF_THREADS) node_post_bwd_fast_kernel(int rows, int EL, int cols, int ld, int I0, int O0, int O1, float alpha,
+                                                                        int n_node_params, const float* __restrict__ e,
+                                                                        const float* __restrict__ h, const float* __restrict__ V0,
+                                                                        const float* __restrict__ c0, const float* __restrict__ V1,
+                                                                        const float* __restrict__ c1, const float* __restrict__ dh_out,
+                                                                        float* __restrict__ de, float* __restrict__ dh, float* __restrict__ part) {
+  constexpr int XS = 4 * ((I0P / 4) | 1), YS = 4 * ((O0P / 4) | 1), G1S = 4 * ((O1P / 4) | 1);
+  constexpr int U0 = (O0P * (I0P / 4) + NF_THREADS - 1) / NF_THREADS, U1 = (O1P * (O0P / 4) + NF_THREADS - 1) / NF_THREADS;
+  extern __shared__ float4 nk_smem_raw[];
+  float* sm = reinterpret_cast<float*>(nk_smem_raw);
+  float* sV0 = sm;                         // [O0P][I0P]
+  float* sV1 = sV0 + O0P * I0P;            // [O1P][O0P]
+  float* sV0t = sV1 + O1P * O0P;           // [I0P][O0P]
+  float* sV1t = sV0t + I0P * O0P;          // [O0P][O1P]
+  float* sc0 = sV1t + O0P * O1P;           // [O0P]
+  float* sc1 = sc0 + O0P;                  // [O1P]
+  float* sX = sc1 + O1P;                   // [NF_THREADS][XS]   x = [e | h]
+  float* sY0 = sX + NF_THREADS * XS;       // [NF_THREADS][YS]   y0, then (second use) g0
+  float* sG1 = sY0 + NF_THREADS * YS;      // [NF_THREADS][G1S]  dh_out, then g1
+  float* sG0 = sG1 + NF_THREADS * G1S;     // [NF_THREADS][YS]   g0
+  for (int idx = threadIdx.x; idx < O0P * I0P; idx += NF_THREADS) {
+    const int o = idx / I0P, k = idx - o * I0P;
+    const float v = (o < O0 && k < I0) ? __ldg(V0 + o * I0 + k) : 0.f;
+    sV0[idx] = v; sV0t[k * O0P + o] = v;
+  }
+  for (int idx = threadIdx.x; idx < O1P * O0P; idx += NF_THREADS) {
+    const int o = idx / O0P, k = idx - o * O0P;
+    const float v = (o < O1 && k < O0) ? __ldg(V1 + o * O0 + k) : 0.f;
+    sV1[idx] = v; sV1t[k * O1P + o] = v;
+  }
+  for (int o = threadIdx.x; o < O0P; o += NF_THREADS) sc0[o] = o < O0 ? __ldg(c0 + o) : 0.f;
+  for (int o = threadIdx.x; o < O1P; o += NF_THREADS) sc1[o] = o < O1 ? __ldg(c1 + o) : 0.f;
+  NfAcc<U0> acc0;
+  NfAcc<U1> acc1;
+#pragma unroll
+  for (int u = 0; u < U0; ++u) { acc0.v[u] = make_float4(0.f, 0.f, 0.f, 0.f); acc0.b[u] = 0.f; }
+#pragma unroll
+  for (int u = 0; u < U1; ++u) { acc1.v[u] = make_float4(0.f, 0.f, 0.f, 0.f); acc1.b[u] = 0.f; }
+  for (int row0 = blockIdx.x * NF_THREADS; row0 < rows; row0 += gridDim.x * NF_THREADS) {
+    const int nrows = min(NF_THREADS, rows - row0);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < nrows * 16; idx += NF_THREADS) {
+      const int r = idx >> 4, k = idx & 15;
+      sX[r * XS + k] = __ldg(e + (size_t)(row0 + r) * EL + k);
+    }
+    for (int idx = threadIdx.x; idx < nrows * (I0P - 16); idx += NF_THREADS) {
+      const int r = idx / (I0P - 16), k = idx - r * (I0P - 16);
+      sX[r * XS + 16 + k] = k < cols ? __ldg(h + (size_t)(row0 + r) * ld + k) : 0.f;
+    }
+    for (int idx = threadIdx.x; idx < nrows * O1P; idx += NF_THREADS) {
+      const int r = idx / O1P, o = idx - r * O1P;
+      sG1[r * G1S + o] = o < O1 ? __ldg(dh_out + (size_t)(row0 + r) * O1 + o) : 0.f;
+    }
+    __syncthreads();
+    if (threadIdx.x < nrows) {
+      const int t = threadIdx.x;
+      float x[I0P];
+#pragma unroll
+      for (int k = 0; k < I0P; k += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(sX + t * XS + k);
+        x[k] = v.x; x[k + 1] = v.y; x[k + 2] = v.z; x[k + 3] = v.w;
+      }
+      float y0[O0P];
+#pragma unroll
+      for (int o0 = 0; o0 < O0P; o0 += 4) {
+        const float4 v = nf_dot4<I0P>(x, sV0, sc0, o0);
+        y0[o0] = fmaxf(v.x, alpha * v.x); y0[o0 + 1] = fmaxf(v.y, alpha * v.y); y0[o0 + 2] = fmaxf(v.z, alpha * v.z); y0[o0 + 3] = fmaxf(v.w, alpha * v.w);
+        *reinterpret_cast<float4*>(sY0 + t * YS + o0) = make_float4(y0[o0], y0[o0 + 1], y0[o0 + 2], y0[o0 + 3]);
+      }
+      // g1 = dh_out * leaky'(y1)
+      float g1[O1P];
+#pragma unroll
+      for (int o0 = 0; o0 < O1P; o0 += 4) {
+        const float4 v = nf_dot4<O0P>(y0, sV1, sc1, o0);
+        const float4 d = *reinterpret_cast<const float4*>(sG1 + t * G1S + o0);
+        g1[o0] = d.x * (v.x > 0.f ? 1.f : alpha); g1[o0 + 1] = d.y * (v.y > 0.f ? 1.f : alpha);
+        g1[o0 + 2] = d.z * (v.z > 0.f ? 1.f : alpha); g1[o0 + 3] = d.w * (v.w > 0.f ? 1.f : alpha);
+        *reinterpret_cast<float4*>(sG1 + t * G1S + o0) = make_float4(g1[o0], g1[o0 + 1], g1[o0 + 2], g1[o0 + 3]);
+      }
+      // g0 = (V1^T g1) * leaky'(y0)
+      float g0[O0P];
+#pragma unroll
+      for (int o0 = 0; o0 < O0P; o0 += 4) {
+        const float4 v = nf_dot4_nobias<O1P>(g1, sV1t, o0);
+        g0[o0] = v.x; g0[o0 + 1] = v.y; g0[o0 + 2] = v.z; g0[o0 + 3] = v.w;
+      }
+#pragma unroll
+      for (int o = 0; o < O0P; ++o) g0[o] *= (y0[o] > 0.f ? 1.f : alpha);
+#pragma unroll
+      for (int o0 = 0; o0 < O0P; o0 += 4) *reinterpret_cast<float4*>(sG0 + t * YS + o0) = make_float4(g0[o0], g0[o0 + 1], g0[o0 + 2], g0[o0 + 3]);
+      // dx = V0^T g0 -> de | dh
+      float* de_row = de + (size_t)(row0 + t) * EL;
+      float* dh_row = dh + (size_t)(row0 + t) * ld;
+#pragma unroll
+      for (int k0 = 0; k0 < I0P; k0 += 4) {
+        const float4 v = nf_dot4_nobias<O0P>(g0, sV0t, k0);
+        if (k0 < 16) *reinterpret_cast<float4*>(de_row + k0) = v;
+        else {
+          const float r4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) if (k0 - 16 + q < cols) dh_row[k0 - 16 + q] = r4[q];
+        }
+      }
+    }
+    __syncthreads();
+    nf_wgrad_tile<I0P / 4, O0P, U0>(acc0, sG0, YS, sX, XS, nrows);      // dV0 += g0^T x, dc0 += sum g0
+    nf_wgrad_tile<O0P / 4, O1P, U1>(acc1, sG1, G1S, sY0, YS, nrows);    // dV1 += g1^T y0, dc1 += sum g1
+  }
+  float* out = part + (size_t)blockIdx.x * n_node_params;
+  nf_wgrad_store<I0P / 4, O0P, U0>(acc0, out, out + O0 * I0, O0, I0);
+  nf_wgrad_store<O0P / 4, O1P, U1>(acc1, out + O0 * I0 + O0, out + O0 * I0 + O0 + O1 * O0, O1, O0);
 }
 
 // Fixed-order reduction of per-CTA partials: block = 32 outputs x 8 slices; slice y sums partials y, y+8, ... and the
@@ -646,6 +816,11 @@ size_t gj_node_pre_bwd_ws_floats(const MPLayout& L) {
   return (size_t)nk_grid(A.rows, A.R, bytes) * (L.E[0] * 2 * L.H + L.E[0]);
 }
 
+static int nf_bwd_grid(int rows) {      // the per-CTA partials are reduced afterwards: keep their number small
+  int blocks = (rows + NF_THREADS - 1) / NF_THREADS, cap = gj_num_sms() * NF_BWD_CTAS_PER_SM;
+  return blocks < cap ? (blocks > 0 ? blocks : 1) : cap;
+}
+
 int gj_node_pre_bwd(const MPLayout& L, const float* h, const float* params, const float* dpq, float* dh, float* dparams,
                     float* part, cudaStream_t st) {
   PreArgs A; int bytes = pre_plan(L, &A, true);
@@ -686,13 +861,53 @@ int gj_node_post_fwd(const MPLayout& L, const float* e, const float* h, const fl
 }
 
 size_t gj_node_post_bwd_ws_floats(const MPLayout& L) {
+  if (L.Ln == 2 && L.EL == 16) {      // thread-per-row adjoint (see gj_node_post_bwd)
+    int blocks = (L.B * L.N + NF_THREADS - 1) / NF_THREADS, cap = gj_num_sms() * NF_BWD_CTAS_PER_SM;
+    const size_t fast = (size_t)(blocks < cap ? (blocks > 0 ? blocks : 1) : cap) * (size_t)(L.nparams - L.pV[0]);
+    PostArgs A0; int b0 = post_plan(L, &A0, true);
+    const size_t gen = b0 < 0 ? 0 : (size_t)nk_grid(A0.rows, A0.R, b0) * A0.n_node_params;
+    return fast > gen ? fast : gen;
+  }
   PostArgs A; int bytes = post_plan(L, &A, true);
   if (bytes < 0) return 0;
   return (size_t)nk_grid(A.rows, A.R, bytes) * A.n_node_params;
 }
 
+static int nf_post_shape(const MPLayout& L) {      // index of the compiled (I0P, O0P, O1P) combination, -1 if none
+  if (!(L.Ln == 2 && L.EL == 16 && L.alpha <= 1.f && L.cols <= L.H)) return -1;
+  const int i0p = (L.I[0] + 3) & ~3, o0p = (L.O[0] + 3) & ~3, o1p = (L.O[1] + 3) & ~3;
+  if (i0p == 32 && o0p == 16 && o1p == 32) return 0;
+  if (i0p == 48 && o0p == 32 && o1p == 8) return 1;
+  if (i0p == 24 && o0p == 8 && o1p == 20) return 2;
+  if (i0p == 24 && o0p == 8 && o1p == 4) return 3;
+  return -1;
+}
+template <int I0P, int O0P, int O1P>
+static int nf_post_bwd_launch(const MPLayout& L, const float* e, const float* h, const float* params, const float* dh_out, float* de,
+                              float* dh, float* part, int grid, cudaStream_t st) {
+  constexpr int XS = 4 * ((I0P / 4) | 1), YS = 4 * ((O0P / 4) | 1), G1S = 4 * ((O1P / 4) | 1);
+  const int bytes = (2 * O0P * I0P + 2 * O1P * O0P + O0P + O1P + NF_THREADS * (XS + 2 * YS + G1S)) * 4;
+  if (int rc = nk_set_smem(node_post_bwd_fast_kernel<I0P, O0P, O1P>, bytes)) return rc;
+  node_post_bwd_fast_kernel<I0P, O0P, O1P><<<grid, NF_THREADS, bytes, st>>>(
+      L.B * L.N, L.EL, L.cols, L.ld, L.I[0], L.O[0], L.O[1], L.alpha, L.nparams - L.pV[0], e, h, params + L.pV[0], params + L.pc[0],
+      params + L.pV[1], params + L.pc[1], dh_out, de, dh, part);
+  return GJ_OK;
+}
+
 int gj_node_post_bwd(const MPLayout& L, const float* e, const float* h, const float* params, const float* dh_out, float* de,
                      float* dh, float* dparams, float* part, cudaStream_t st) {
+  const int shape = nf_post_shape(L);
+  if (shape >= 0) {
+    const int grid = nf_bwd_grid(L.B * L.N), n = L.nparams - L.pV[0];
+    int rc = shape == 0 ? nf_post_bwd_launch<32, 16, 32>(L, e, h, params, dh_out, de, dh, part, grid, st)
+           : shape == 1 ? nf_post_bwd_launch<48, 32, 8>(L, e, h, params, dh_out, de, dh, part, grid, st)
+           : shape == 2 ? nf_post_bwd_launch<24, 8, 20>(L, e, h, params, dh_out, de, dh, part, grid, st)
+                        : nf_post_bwd_launch<24, 8, 4>(L, e, h, params, dh_out, de, dh, part, grid, st);
+    if (rc) return rc;
+    reduce_partials_kernel<<<(n + 31) / 32, dim3(32, RED_SLICES), 0, st>>>(part, grid, n, dparams + L.pV[0]);
+    NK_CHECK_LAUNCH("node_post_bwd launch");
+    return GJ_OK;
+  }
   PostArgs A; int bytes = post_plan(L, &A, true);
   if (bytes < 0) { gj_set_error("node_post_bwd: widths do not fit shared memory"); return GJ_ERR_SMEM; }
   if (int rc = nk_set_smem(node_post_bwd_kernel, bytes)) return rc;
