@@ -43,6 +43,9 @@ SIGNATURES = {
     "gj_mp_param_count": (_SZ, [C.POINTER(MPDesc)]),
     "gj_mp_step_fwd_workspace": (_SZ, [C.POINTER(MPDesc)]),
     "gj_mp_step_fwd": (C.c_int, [C.POINTER(MPDesc), _P, _P, _P, _P, _P, _SZ, _P]),
+    "gj_mp_step_saved_bytes": (_SZ, [C.POINTER(MPDesc)]),
+    "gj_mp_step_fwd_saving": (C.c_int, [C.POINTER(MPDesc), _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "gj_mp_step_bwd_saved": (C.c_int, [C.POINTER(MPDesc), _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "gj_mp_step_bwd_workspace": (_SZ, [C.POINTER(MPDesc)]),
     "gj_mp_step_bwd": (C.c_int, [C.POINTER(MPDesc), _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "gj_chamfer_fwd_bwd": (C.c_int, [_I, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P]),

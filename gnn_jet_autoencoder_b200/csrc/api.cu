@@ -44,13 +44,15 @@ int gj_edge_bwd_simt(MPLayout, const float*, const float*, const float*, const f
 int gj_edge_fwd_tc(MPLayout, const float*, const float*, const float*, float*, cudaStream_t);
 bool gj_fwd2_supported(const MPLayout&);
 size_t gj_fwd2_ws_floats(const MPLayout&);
-int gj_edge_fwd2(const MPLayout&, const float*, const float*, const float*, float*, float*, cudaStream_t, bool);
+int gj_edge_fwd2(const MPLayout&, const float*, const float*, const float*, float*, float*, float*, float*, cudaStream_t, bool);
+size_t gj_wimage_floats();
 bool gj_tc_v1_forced();
 void gj_fwd2_plan(const MPLayout&, int*, int*);
 void gj_bwd2_plan(const MPLayout&, int*, int*);
 bool gj_bwd2_supported(const MPLayout&);
 size_t gj_bwd2_ws_floats(const MPLayout&);
-int gj_edge_bwd2(const MPLayout&, const float*, const float*, const float*, const float*, float*, float*, float*, float*, cudaStream_t, bool);
+int gj_edge_bwd2(const MPLayout&, const float*, const float*, const float*, const float*, float*, float*, float*, float*, float*, float*, bool,
+                 cudaStream_t, bool);
 size_t gj_edge_bwd_tc_ws_floats(const MPLayout&);
 int gj_edge_bwd_tc(MPLayout, const float*, const float*, const float*, const float*, float*, float*, float*, float*,
                    cudaStream_t);
@@ -82,17 +84,28 @@ size_t gj_mp_param_count(const gj_mp_desc* d) {
 static size_t align_floats(size_t n) { return (n + 63) & ~(size_t)63; }   // keep every region 256-byte aligned
 
 struct StepWs {   // offsets in floats
-  size_t pq, dpq, de, part, epart, total;
+  size_t pq, dpq, de, part, epart, wimg, dist, total;
 };
 
 static bool use_tc(const MPLayout& L, int precision) { return precision == GJ_PREC_BF16 && L.Le > 1; }
+// the step runs the second-generation fused kernels (forward and backward are covered by the same widths)
+static bool tc2_path(const MPLayout& L, int precision) {
+  return use_tc(L, precision) && gj_fwd2_supported(L) && gj_bwd2_supported(L) && !gj_tc_v1_forced();
+}
 
 static StepWs plan_ws(const MPLayout& L, int precision, bool backward) {
   StepWs w; size_t off = 0;
   const size_t rows = (size_t)L.B * L.N;
+  // P|Q, the packed edge-parameter image and the pair distances come first: a caller-owned "saved" buffer of
+  // gj_mp_step_saved_bytes() has exactly this prefix layout
   w.pq = off; off += align_floats(rows * 2 * L.E0p);
+  w.wimg = w.dist = off;
+  if (tc2_path(L, precision)) {
+    w.wimg = off; off += align_floats(gj_wimage_floats());
+    w.dist = off; off += align_floats(rows * (size_t)(((L.N + 31) / 32) * 32));
+  }
   w.epart = off;
-  if (!backward && use_tc(L, precision) && gj_fwd2_supported(L)) off += align_floats(gj_fwd2_ws_floats(L));   // per-j-block partial aggregates (N > 32)
+  if (!backward && tc2_path(L, precision)) off += align_floats(gj_fwd2_ws_floats(L));   // per-j-block partial aggregates (N > 32)
   w.dpq = w.de = w.part = off;
   if (backward) {
     w.dpq = off; off += align_floats(rows * 2 * L.E0p);
@@ -100,7 +113,7 @@ static StepWs plan_ws(const MPLayout& L, int precision, bool backward) {
     size_t p = gj_node_post_bwd_ws_floats(L);
     size_t q = gj_node_pre_bwd_ws_floats(L);
     size_t r = use_tc(L, precision) ? gj_edge_bwd_tc_ws_floats(L) : (size_t)gj_edge_grid(L.B) * L.pV[0];
-    if (use_tc(L, precision) && gj_bwd2_supported(L)) { const size_t r2 = gj_bwd2_ws_floats(L); if (r2 > r) r = r2; }
+    if (tc2_path(L, precision)) { const size_t r2 = gj_bwd2_ws_floats(L); if (r2 > r) r = r2; }
     if (q > p) p = q;
     if (r > p) p = r;
     w.part = off; off += align_floats(p);
@@ -115,25 +128,48 @@ size_t gj_mp_step_fwd_workspace(const gj_mp_desc* d) {
   return plan_ws(L, d->precision, false).total * sizeof(float);
 }
 
-int gj_mp_step_fwd(const gj_mp_desc* d, const float* h, const float* params, float* h_out, float* e_out, void* workspace,
-                   size_t workspace_bytes, void* stream) {
+// saved: optional caller-owned buffer of gj_mp_step_saved_bytes(): receives P|Q, the packed edge parameters and the pair
+// distances, which gj_mp_step_bwd_saved then reuses instead of recomputing them
+static int mp_step_fwd_impl(const gj_mp_desc* d, const float* h, const float* params, float* h_out, float* e_out, void* saved,
+                            void* workspace, size_t workspace_bytes, void* stream, const char* who) {
   g_err[0] = 0;
-  if (!d || !h || !params || !h_out || !e_out || !workspace) { gj_set_error("gj_mp_step_fwd: null pointer"); return GJ_ERR_INVALID; }
-  if (d->precision != GJ_PREC_FP32 && d->precision != GJ_PREC_BF16) { gj_set_error("gj_mp_step_fwd: unknown precision %d", d->precision); return GJ_ERR_INVALID; }
+  if (!d || !h || !params || !h_out || !e_out || !workspace) { gj_set_error("%s: null pointer", who); return GJ_ERR_INVALID; }
+  if (d->precision != GJ_PREC_FP32 && d->precision != GJ_PREC_BF16) { gj_set_error("%s: unknown precision %d", who, d->precision); return GJ_ERR_INVALID; }
   MPLayout L; const char* why;
   int rc = gj_fill_arch(d, &L, &why);
-  if (rc) { gj_set_error("gj_mp_step_fwd: %s", why); return rc; }
+  if (rc) { gj_set_error("%s: %s", who, why); return rc; }
   if (L.B == 0) return GJ_OK;
   const StepWs w = plan_ws(L, d->precision, false);
-  if (workspace_bytes < w.total * sizeof(float)) { gj_set_error("gj_mp_step_fwd: workspace too small"); return GJ_ERR_WORKSPACE; }
+  if (workspace_bytes < w.total * sizeof(float)) { gj_set_error("%s: workspace too small", who); return GJ_ERR_WORKSPACE; }
   float* ws = (float*)workspace;
+  const bool tc2 = tc2_path(L, d->precision);
+  if (saved && !tc2) { gj_set_error("%s: this step has nothing to save (gj_mp_step_saved_bytes is 0)", who); return GJ_ERR_INVALID; }
+  float* pre = saved ? (float*)saved : ws;      // P|Q, parameter image, pair distances: same layout in either buffer
   cudaStream_t st = (cudaStream_t)stream;
-  if ((rc = gj_node_pre_fwd(L, h, params, ws + w.pq, st))) return rc;
-  if (use_tc(L, d->precision) && gj_fwd2_supported(L) && !gj_tc_v1_forced()) rc = gj_edge_fwd2(L, h, ws + w.pq, params, e_out, ws + w.epart, st, false);
+  if ((rc = gj_node_pre_fwd(L, h, params, pre + w.pq, st))) return rc;
+  if (tc2) rc = gj_edge_fwd2(L, h, pre + w.pq, params, e_out, ws + w.epart, pre + w.wimg, saved ? pre + w.dist : nullptr, st, false);
   else rc = use_tc(L, d->precision) ? gj_edge_fwd_tc(L, h, ws + w.pq, params, e_out, st)
                                     : gj_edge_fwd_simt(L, h, ws + w.pq, params, e_out, st);
   if (rc) return rc;
   return gj_node_post_fwd(L, e_out, h, params, h_out, st);
+}
+
+int gj_mp_step_fwd(const gj_mp_desc* d, const float* h, const float* params, float* h_out, float* e_out, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+  return mp_step_fwd_impl(d, h, params, h_out, e_out, nullptr, workspace, workspace_bytes, stream, "gj_mp_step_fwd");
+}
+
+size_t gj_mp_step_saved_bytes(const gj_mp_desc* d) {
+  MPLayout L; const char* why;
+  if (gj_fill_arch(d, &L, &why) || !tc2_path(L, d->precision)) return 0;
+  const StepWs w = plan_ws(L, d->precision, false);
+  return w.epart * sizeof(float);      // the prefix P|Q, parameter image, pair distances
+}
+
+int gj_mp_step_fwd_saving(const gj_mp_desc* d, const float* h, const float* params, float* h_out, float* e_out, void* saved,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+  if (!saved) { g_err[0] = 0; gj_set_error("gj_mp_step_fwd_saving: null pointer"); return GJ_ERR_INVALID; }
+  return mp_step_fwd_impl(d, h, params, h_out, e_out, saved, workspace, workspace_bytes, stream, "gj_mp_step_fwd_saving");
 }
 
 size_t gj_mp_step_bwd_workspace(const gj_mp_desc* d) {
@@ -142,31 +178,46 @@ size_t gj_mp_step_bwd_workspace(const gj_mp_desc* d) {
   return plan_ws(L, d->precision, true).total * sizeof(float);
 }
 
-int gj_mp_step_bwd(const gj_mp_desc* d, const float* h, const float* e, const float* params, const float* dh_out, float* dh,
-                   float* dparams, void* workspace, size_t workspace_bytes, void* stream) {
+static int mp_step_bwd_impl(const gj_mp_desc* d, const float* h, const float* e, const float* params, const float* dh_out, float* dh,
+                            float* dparams, const void* saved, void* workspace, size_t workspace_bytes, void* stream, const char* who) {
   g_err[0] = 0;
-  if (!d || !h || !e || !params || !dh_out || !dh || !dparams || !workspace) { gj_set_error("gj_mp_step_bwd: null pointer"); return GJ_ERR_INVALID; }
-  if (d->precision != GJ_PREC_FP32 && d->precision != GJ_PREC_BF16) { gj_set_error("gj_mp_step_bwd: unknown precision %d", d->precision); return GJ_ERR_INVALID; }
+  if (!d || !h || !e || !params || !dh_out || !dh || !dparams || !workspace) { gj_set_error("%s: null pointer", who); return GJ_ERR_INVALID; }
+  if (d->precision != GJ_PREC_FP32 && d->precision != GJ_PREC_BF16) { gj_set_error("%s: unknown precision %d", who, d->precision); return GJ_ERR_INVALID; }
   MPLayout L; const char* why;
   int rc = gj_fill_arch(d, &L, &why);
-  if (rc) { gj_set_error("gj_mp_step_bwd: %s", why); return rc; }
+  if (rc) { gj_set_error("%s: %s", who, why); return rc; }
   cudaStream_t st = (cudaStream_t)stream;
   if (L.B == 0) { cudaMemsetAsync(dparams, 0, (size_t)L.nparams * sizeof(float), st); return GJ_OK; }
   const StepWs w = plan_ws(L, d->precision, true);
-  if (workspace_bytes < w.total * sizeof(float)) { gj_set_error("gj_mp_step_bwd: workspace too small"); return GJ_ERR_WORKSPACE; }
+  if (workspace_bytes < w.total * sizeof(float)) { gj_set_error("%s: workspace too small", who); return GJ_ERR_WORKSPACE; }
   float* ws = (float*)workspace;
+  const bool tc2 = tc2_path(L, d->precision);
+  if (saved && !tc2) { gj_set_error("%s: this step has nothing saved (gj_mp_step_saved_bytes is 0)", who); return GJ_ERR_INVALID; }
+  float* pre = saved ? (float*)saved : ws;      // read-only when it is the caller's saved buffer
   // node MLP adjoint: de, node-path dh, node parameter gradients
   if ((rc = gj_node_post_bwd(L, e, h, params, dh_out, ws + w.de, dh, dparams, ws + w.part, st))) return rc;
-  // recompute P|Q, then the edge adjoint: dP|dQ, distance-path dh, edge parameter gradients
-  if ((rc = gj_node_pre_fwd(L, h, params, ws + w.pq, st))) return rc;
-  if (use_tc(L, d->precision) && gj_bwd2_supported(L) && !gj_tc_v1_forced())
-    rc = gj_edge_bwd2(L, h, ws + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.part, st, false);
+  // P|Q (recomputed unless saved by the forward call), then the edge adjoint: dP|dQ, distance-path dh, edge parameter gradients
+  if (!saved && (rc = gj_node_pre_fwd(L, h, params, pre + w.pq, st))) return rc;
+  if (tc2)
+    rc = gj_edge_bwd2(L, h, pre + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.part, pre + w.wimg, pre + w.dist, saved != nullptr,
+                      st, false);
   else
     rc = use_tc(L, d->precision) ? gj_edge_bwd_tc(L, h, ws + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.part, st)
                                  : gj_edge_bwd_simt(L, h, ws + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.part, st);
   if (rc) return rc;
   // first-layer projections' adjoint: dh += Wa^T dP + Wb^T dQ, dWa, dWb, db0
   return gj_node_pre_bwd(L, h, params, ws + w.dpq, dh, dparams, ws + w.part, st);
+}
+
+int gj_mp_step_bwd(const gj_mp_desc* d, const float* h, const float* e, const float* params, const float* dh_out, float* dh,
+                   float* dparams, void* workspace, size_t workspace_bytes, void* stream) {
+  return mp_step_bwd_impl(d, h, e, params, dh_out, dh, dparams, nullptr, workspace, workspace_bytes, stream, "gj_mp_step_bwd");
+}
+
+int gj_mp_step_bwd_saved(const gj_mp_desc* d, const float* h, const float* e, const float* params, const float* dh_out, float* dh,
+                         float* dparams, const void* saved, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!saved) { g_err[0] = 0; gj_set_error("gj_mp_step_bwd_saved: null pointer"); return GJ_ERR_INVALID; }
+  return mp_step_bwd_impl(d, h, e, params, dh_out, dh, dparams, saved, workspace, workspace_bytes, stream, "gj_mp_step_bwd_saved");
 }
 
 int gj_chamfer_fwd_bwd(int32_t batch, int32_t np_, int32_t nq, int32_t dim, int32_t norm, float w_chamfer, float w_jet,
@@ -230,11 +281,11 @@ int gj_bench_edge_fwd_only(const gj_mp_desc* d, const float* h, const float* par
   MPLayout L; const char* why;
   int rc = gj_fill_arch(d, &L, &why);
   if (rc || !h || !params || !e_out || !workspace) { gj_set_error("gj_bench_edge_fwd_only: %s", rc ? why : "null pointer"); return GJ_ERR_INVALID; }
-  if (!(use_tc(L, d->precision) && gj_fwd2_supported(L))) { gj_set_error("gj_bench_edge_fwd_only: step does not run the fused tensor-core kernel"); return GJ_ERR_INVALID; }
+  if (!tc2_path(L, d->precision)) { gj_set_error("gj_bench_edge_fwd_only: step does not run the fused tensor-core kernel"); return GJ_ERR_INVALID; }
   const StepWs w = plan_ws(L, d->precision, false);
   if (workspace_bytes < w.total * sizeof(float)) { gj_set_error("gj_bench_edge_fwd_only: workspace too small"); return GJ_ERR_WORKSPACE; }
   float* ws = (float*)workspace;
-  return gj_edge_fwd2(L, h, ws + w.pq, params, e_out, ws + w.epart, (cudaStream_t)stream, true);
+  return gj_edge_fwd2(L, h, ws + w.pq, params, e_out, ws + w.epart, ws + w.wimg, nullptr, (cudaStream_t)stream, true);
 }
 
 int gj_bench_edge_bwd_only(const gj_mp_desc* d, const float* h, const float* params, float* dh, float* dparams, void* workspace,
@@ -243,11 +294,12 @@ int gj_bench_edge_bwd_only(const gj_mp_desc* d, const float* h, const float* par
   MPLayout L; const char* why;
   int rc = gj_fill_arch(d, &L, &why);
   if (rc || !h || !params || !dh || !dparams || !workspace) { gj_set_error("gj_bench_edge_bwd_only: %s", rc ? why : "null pointer"); return GJ_ERR_INVALID; }
-  if (!(use_tc(L, d->precision) && gj_bwd2_supported(L))) { gj_set_error("gj_bench_edge_bwd_only: step does not run the fused tensor-core kernel"); return GJ_ERR_INVALID; }
+  if (!tc2_path(L, d->precision)) { gj_set_error("gj_bench_edge_bwd_only: step does not run the fused tensor-core kernel"); return GJ_ERR_INVALID; }
   const StepWs w = plan_ws(L, d->precision, true);
   if (workspace_bytes < w.total * sizeof(float)) { gj_set_error("gj_bench_edge_bwd_only: workspace too small"); return GJ_ERR_WORKSPACE; }
   float* ws = (float*)workspace;
-  return gj_edge_bwd2(L, h, ws + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.part, (cudaStream_t)stream, true);
+  return gj_edge_bwd2(L, h, ws + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.part, ws + w.wimg, ws + w.dist, true,
+                      (cudaStream_t)stream, true);
 }
 
 int gj_mp_plan_info(const gj_mp_desc* d, int32_t* info) {
@@ -256,9 +308,8 @@ int gj_mp_plan_info(const gj_mp_desc* d, int32_t* info) {
   int rc = gj_fill_arch(d, &L, &why);
   if (rc || !info) { gj_set_error("gj_mp_plan_info: %s", rc ? why : "null pointer"); return GJ_ERR_INVALID; }
   gj_tc_plan_info(L, info);
-  if (!gj_tc_v1_forced()) {      // the second-generation kernels take over where their widths are compiled in
-    if (gj_fwd2_supported(L)) gj_fwd2_plan(L, info + 0, info + 1);
-    if (gj_bwd2_supported(L)) gj_bwd2_plan(L, info + 2, info + 3);
+  {      // the second-generation kernels take over where their widths are compiled in
+    if (tc2_path(L, d->precision)) { gj_fwd2_plan(L, info + 0, info + 1); gj_bwd2_plan(L, info + 2, info + 3); }
   }
   return GJ_OK;
 }

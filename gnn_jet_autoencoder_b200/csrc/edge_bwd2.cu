@@ -802,10 +802,10 @@ void gj_bwd2_plan(const MPLayout&, int* smem_bytes, int* tmem_cols) {
 
 static int bwd2_grid(const MPLayout& L) { return gj_num_sms(); }
 
-// workspace (floats): d | G (B N NJ32 each) | dP partials (NJB > 1) | per-CTA parameter-gradient partials
+// workspace (floats): G (B N NJ32) | dP partials (NJB > 1) | per-CTA parameter-gradient partials
 size_t gj_bwd2_ws_floats(const MPLayout& L) {
   const size_t njb = (L.N + 31) / 32, rows = (size_t)L.B * L.N;
-  size_t n = 2 * rows * njb * 32 + 64 + (WImage<32, 128, 64, 16>::bytes + 255) / 256 * 64;
+  size_t n = rows * njb * 32 + 64;
   if (njb > 1) n += njb * rows * L.E[0] + 64;
   n += (size_t)bwd2_grid(L) * L.pV[0] + 64;
   return n;
@@ -824,18 +824,18 @@ int gj_pair_dist_fwd(const MPLayout& L, const float* h, float* d, cudaStream_t s
 
 // kernel_only: relaunch just the fused edge kernel on a workspace a full call has populated (bench.py times the dominant
 // kernel alone this way; dQ then accumulates onto the previous launch's values, which does not matter for timing)
+// wimg / d: packed parameter image and pair distances; with `have_saved` they were written by gj_edge_fwd2 of the same step
+// and are used as they are, otherwise they are (re)computed here
 int gj_edge_bwd2(const MPLayout& L, const float* h, const float* pq, const float* params, const float* de, float* dpq, float* dh,
-                 float* dparams, float* ws, cudaStream_t stream, bool kernel_only) {
+                 float* dparams, float* ws, float* wimg_f, float* d, bool have_saved, cudaStream_t stream, bool kernel_only) {
   constexpr int NWG = 3;
   using S = Bwd2Smem<32, 128, 64, 16, NWG>;
   static_assert(S::total <= 227 * 1024, "backward shared-memory plan exceeds the 227 KB budget");
   Bwd2Args A;
   const size_t njb = (L.N + 31) / 32, rows = (size_t)L.B * L.N;
   const int NJ32 = (int)njb * 32;
-  uint8_t* wimg = reinterpret_cast<uint8_t*>(ws);      // packed bf16 parameter image (WImage), 16-byte aligned
-  ws += (WImage<32, 128, 64, 16>::bytes + 255) / 256 * 64;
-  float* d = ws;
-  float* G = d + rows * NJ32 + 32;
+  uint8_t* wimg = reinterpret_cast<uint8_t*>(wimg_f);      // packed bf16 parameter image (WImage), 16-byte aligned
+  float* G = ws;
   float* dp_part = G + rows * NJ32 + 32;
   float* part = njb > 1 ? dp_part + njb * rows * L.E[0] + 64 : dp_part;
   A.wimg = wimg;
@@ -854,10 +854,12 @@ int gj_edge_bwd2(const MPLayout& L, const float* h, const float* pq, const float
   A.ngroups = (int)(ng < 1 ? 1 : ng);
   cudaError_t ce = cudaSuccess;
   if (!kernel_only) {
-    WImageSrc P{L.pW[1], L.pb[1], L.pW[2], L.pb[2], L.pW[3], L.pb[3]};
-    pack_edge_weights_kernel<32, 128, 64, 16><<<4, 256, 0, stream>>>(params, P, wimg);
-    int rc = gj_pair_dist_fwd(L, h, d, stream);
-    if (rc) return rc;
+    if (!have_saved) {
+      WImageSrc P{L.pW[1], L.pb[1], L.pW[2], L.pb[2], L.pW[3], L.pb[3]};
+      pack_edge_weights_kernel<32, 128, 64, 16><<<4, 256, 0, stream>>>(params, P, wimg);
+      int rc = gj_pair_dist_fwd(L, h, d, stream);
+      if (rc) return rc;
+    }
     ce = cudaMemsetAsync(dpq, 0, rows * 2 * L.E[0] * sizeof(float), stream);
     if (ce != cudaSuccess) { gj_set_error("cudaMemsetAsync: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   }

@@ -28,11 +28,13 @@ using namespace tc2;
 
 struct Fwd2Args {
   const float* h; const float* pq; const float* params; float* e_out; const uint8_t* wimg;
+  float* d_out;          // optional (B, N, NJ32) pair distances, saved for the backward kernel
   int B, N, NJB, cols, ld, mink;
   int Hb, Hs;            // h_i row length (multiple of 4 floats), h_j per-lane row stride (floats, (Hs/4) odd)
   int pW1, pb1, pW2, pb2, pW3, pb3, pWd, K0;
   float alpha;
   int tiles_total;       // ceil(B * NJB / 4) * N
+  int NJ32;              // row stride of d_out
 };
 
 constexpr int F2_IC = 8;           // i's per staged P_i | h_i chunk (double buffered, cp.async)
@@ -200,6 +202,7 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_fwd2_kernel(const Fwd2Args 
   bool p_active = false, p_valid = false;
   size_t node0 = 0;
   float* e_dst = nullptr;
+  int e_dst_jb = 0;
 
   // issues the cp.async copies of chunk c (i in [c * F2_IC, ...)) of the current jet into buffer c & 1
   auto stage_chunk = [&](int c) {
@@ -236,6 +239,7 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_fwd2_kernel(const Fwd2Args 
       p_valid = p_active && j < N;
       node0 = (size_t)jet * N;
       e_dst = A.e_out + ((size_t)jb * A.B + jet) * N * E3;
+      e_dst_jb = jb;
       cp_async_wait<0>();
       __syncwarp();
       stage_chunk(i / F2_IC);
@@ -282,6 +286,7 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_fwd2_kernel(const Fwd2Args 
         }
         d = acc.x + acc.y;
       }
+      if (A.d_out && p_active) A.d_out[(node0 + i) * A.NJ32 + (e_dst_jb * 32 + lane)] = p_valid ? d : 0.f;
       const float2 d2 = make_float2(d, d);
 #pragma unroll
       for (int c = 0; c < E0; c += 8) {
@@ -414,21 +419,25 @@ void gj_fwd2_plan(const MPLayout& L, int* smem_bytes, int* tmem_cols) {
 }
 size_t gj_fwd2_ws_floats(const MPLayout& L) {
   const int njb = (L.N + 31) / 32;
-  return (njb > 1 ? (size_t)njb * L.B * L.N * L.E[3] : 0) + (WImage<32, 128, 64, 16>::bytes + 255) / 256 * 64;
+  return njb > 1 ? (size_t)njb * L.B * L.N * L.E[3] : 0;
 }
 
-int gj_edge_fwd2(const MPLayout& L, const float* h, const float* pq, const float* params, float* e_out, float* ws,
-                 cudaStream_t stream, bool kernel_only) {
+// wimg: 16-byte aligned buffer of gj_wimage_floats() floats that receives the packed parameter image; d_save: optional
+// (B, N, NJ32) buffer that receives the pair distances (both are reused by gj_edge_bwd2 when the caller keeps them)
+size_t gj_wimage_floats() { return (WImage<32, 128, 64, 16>::bytes + 255) / 256 * 64; }
+
+int gj_edge_fwd2(const MPLayout& L, const float* h, const float* pq, const float* params, float* e_out, float* ws, float* wimg,
+                 float* d_save, cudaStream_t stream, bool kernel_only) {
   constexpr int NWG = 4;
   Fwd2Args A;
-  A.wimg = reinterpret_cast<const uint8_t*>(ws);      // packed bf16 parameter image, then the per-j-block partial aggregates
+  A.wimg = reinterpret_cast<const uint8_t*>(wimg);
+  A.d_out = d_save;
   if (!kernel_only) {
     WImageSrc P{L.pW[1], L.pb[1], L.pW[2], L.pb[2], L.pW[3], L.pb[3]};
-    pack_edge_weights_kernel<32, 128, 64, 16><<<4, 256, 0, stream>>>(params, P, reinterpret_cast<uint8_t*>(ws));
+    pack_edge_weights_kernel<32, 128, 64, 16><<<4, 256, 0, stream>>>(params, P, reinterpret_cast<uint8_t*>(wimg));
   }
-  ws += (WImage<32, 128, 64, 16>::bytes + 255) / 256 * 64;
   A.h = h; A.pq = pq; A.params = params;
-  A.B = L.B; A.N = L.N; A.NJB = (L.N + 31) / 32; A.cols = L.cols; A.ld = L.ld; A.mink = L.mink;
+  A.B = L.B; A.N = L.N; A.NJB = (L.N + 31) / 32; A.NJ32 = A.NJB * 32; A.cols = L.cols; A.ld = L.ld; A.mink = L.mink;
   A.e_out = A.NJB > 1 ? ws : e_out;
   A.Hb = (L.cols + 3) & ~3;
   A.Hs = 4 * ((A.Hb >> 2) | 1);

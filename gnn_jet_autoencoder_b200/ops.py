@@ -49,21 +49,40 @@ def metric_id(metric) -> int:
 # --------------------------------------------------------------------------------------------------
 # pointer-level calls
 # --------------------------------------------------------------------------------------------------
-FWD_LAUNCHES = 3   # node projections, fused edge kernel, node MLP
-BWD_LAUNCHES = 8   # node MLP adjoint + reduce, node projections, edge adjoint + reduce, projections' adjoint + reduce
-
-
-def raw_mp_fwd(desc, h_ptr, params_ptr, hout_ptr, e_ptr, ws_ptr, ws_bytes, stream):
+def _step_launches(desc, backward: bool, saved: bool = False) -> int:
+    """Kernel launches of one gj_mp_step_fwd / gj_mp_step_bwd call (the bench's gpu_launches claim): node projections,
+    parameter packing, fused edge kernel (+ the j-block sum for N > 32), node MLP; backward: node MLP adjoint + reduce,
+    node projections, packing, pair distances, fused edge kernel (+ dP j-block sum), pair-distance adjoint, edge partial
+    reduce, projections' adjoint + reduce (projections, packing and pair distances are skipped when saved by forward)."""
     lib = _lib.load()
-    _lib.check(lib.gj_mp_step_fwd(desc, h_ptr, params_ptr, hout_ptr, e_ptr, ws_ptr, ws_bytes, stream), "gj_mp_step_fwd")
-    LAUNCHES["count"] += FWD_LAUNCHES
+    tc2 = lib.gj_mp_step_saved_bytes(desc) > 0
+    njb_extra = 1 if (tc2 and desc.num_nodes > 32) else 0
+    if not backward:
+        return (4 + njb_extra) if tc2 else 3
+    if not tc2:
+        return 8
+    return 11 + njb_extra - (3 if saved else 0)
 
 
-def raw_mp_bwd(desc, h_ptr, e_ptr, params_ptr, dhout_ptr, dh_ptr, dparams_ptr, ws_ptr, ws_bytes, stream):
+def raw_mp_fwd(desc, h_ptr, params_ptr, hout_ptr, e_ptr, ws_ptr, ws_bytes, stream, saved_ptr=None):
     lib = _lib.load()
-    _lib.check(lib.gj_mp_step_bwd(desc, h_ptr, e_ptr, params_ptr, dhout_ptr, dh_ptr, dparams_ptr, ws_ptr, ws_bytes,
-                                  stream), "gj_mp_step_bwd")
-    LAUNCHES["count"] += BWD_LAUNCHES
+    if saved_ptr:
+        _lib.check(lib.gj_mp_step_fwd_saving(desc, h_ptr, params_ptr, hout_ptr, e_ptr, saved_ptr, ws_ptr, ws_bytes, stream),
+                   "gj_mp_step_fwd_saving")
+    else:
+        _lib.check(lib.gj_mp_step_fwd(desc, h_ptr, params_ptr, hout_ptr, e_ptr, ws_ptr, ws_bytes, stream), "gj_mp_step_fwd")
+    LAUNCHES["count"] += _step_launches(desc, False)
+
+
+def raw_mp_bwd(desc, h_ptr, e_ptr, params_ptr, dhout_ptr, dh_ptr, dparams_ptr, ws_ptr, ws_bytes, stream, saved_ptr=None):
+    lib = _lib.load()
+    if saved_ptr:
+        _lib.check(lib.gj_mp_step_bwd_saved(desc, h_ptr, e_ptr, params_ptr, dhout_ptr, dh_ptr, dparams_ptr, saved_ptr, ws_ptr,
+                                            ws_bytes, stream), "gj_mp_step_bwd_saved")
+    else:
+        _lib.check(lib.gj_mp_step_bwd(desc, h_ptr, e_ptr, params_ptr, dhout_ptr, dh_ptr, dparams_ptr, ws_ptr, ws_bytes,
+                                      stream), "gj_mp_step_bwd")
+    LAUNCHES["count"] += _step_launches(desc, True, bool(saved_ptr))
 
 
 # --------------------------------------------------------------------------------------------------

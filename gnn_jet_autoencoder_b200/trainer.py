@@ -191,6 +191,11 @@ class GNNAETrainer:
                   self.lib.gj_param_norms_workspace(n), 16])
         self.ws_bytes = int(ws)
         self.ws = torch.empty((self.ws_bytes + 3) // 4, **f32)
+        # per-step buffers in which the forward call leaves P|Q, the packed edge parameters and the pair distances for the
+        # backward call of the same step (0 bytes: that step recomputes them)
+        for st_ in self.enc_steps + self.dec_steps:
+            nbytes = int(self.lib.gj_mp_step_saved_bytes(st_["desc"]))
+            st_["saved"] = torch.empty((nbytes + 3) // 4, **f32) if nbytes else None
         self.graph = None
         self.use_graph = use_cuda_graph
         self.launches_per_step = None
@@ -222,7 +227,7 @@ class GNNAETrainer:
         h = self.x
         for s in self.enc_steps:
             ops.raw_mp_fwd(s["desc"], h.data_ptr(), P + 4 * s["off"], s["out"].data_ptr(), s["e"].data_ptr(),
-                           self.ws.data_ptr(), self.ws_bytes, st)
+                           self.ws.data_ptr(), self.ws_bytes, st, s["saved"].data_ptr() if s["saved"] is not None else None)
             h = s["out"]
         L = self.layout
         if self.map == "mean":
@@ -244,7 +249,7 @@ class GNNAETrainer:
         h = self.dec_in
         for s in self.dec_steps:
             ops.raw_mp_fwd(s["desc"], h.data_ptr(), P + 4 * s["off"], s["out"].data_ptr(), s["e"].data_ptr(),
-                           self.ws.data_ptr(), self.ws_bytes, st)
+                           self.ws.data_ptr(), self.ws_bytes, st, s["saved"].data_ptr() if s["saved"] is not None else None)
             h = s["out"]
 
     def _loss_and_bwd(self, st):
@@ -263,7 +268,8 @@ class GNNAETrainer:
             hin = self.dec_in if t == 0 else self.dec_steps[t - 1]["out"]
             din = self.d_dec_in if t == 0 else s["din"]
             ops.raw_mp_bwd(s["desc"], hin.data_ptr(), s["e"].data_ptr(), P + 4 * s["off"], g.data_ptr(), din.data_ptr(),
-                           G + 4 * s["off"], self.ws.data_ptr(), self.ws_bytes, st)
+                           G + 4 * s["off"], self.ws.data_ptr(), self.ws_bytes, st,
+                           s["saved"].data_ptr() if s["saved"] is not None else None)
             g = din
         wl = L["decoder.linear.weight"][0]
         bl = L["decoder.linear.bias"][0]
@@ -294,7 +300,8 @@ class GNNAETrainer:
             hin = self.x if t == 0 else self.enc_steps[t - 1]["out"]
             din = self.dx if t == 0 else s["din"]
             ops.raw_mp_bwd(s["desc"], hin.data_ptr(), s["e"].data_ptr(), P + 4 * s["off"], g.data_ptr(), din.data_ptr(),
-                           G + 4 * s["off"], self.ws.data_ptr(), self.ws_bytes, st)
+                           G + 4 * s["off"], self.ws.data_ptr(), self.ws_bytes, st,
+                           s["saved"].data_ptr() if s["saved"] is not None else None)
             g = din
 
     def _fwd_bwd(self):

@@ -85,6 +85,18 @@ size_t gj_mp_step_fwd_workspace(const gj_mp_desc* d);
 int gj_mp_step_fwd(const gj_mp_desc* d, const float* h, const float* params,
                    float* h_out, float* e_out, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Optional reuse of forward by-products in backward.  gj_mp_step_saved_bytes(d) > 0 means the step runs the fused
+ * tensor-core kernels and gj_mp_step_fwd_saving can leave its per-node projections P|Q, the packed bf16 edge parameters
+ * and the pair distances d_ij in a caller-owned buffer `saved` of that many bytes (256-byte aligned); passing the same
+ * buffer, unmodified, to gj_mp_step_bwd_saved (same desc, h, params) skips their recomputation.  Results are identical to
+ * gj_mp_step_fwd / gj_mp_step_bwd.  Both return GJ_ERR_INVALID where gj_mp_step_saved_bytes is 0. */
+size_t gj_mp_step_saved_bytes(const gj_mp_desc* d);
+int gj_mp_step_fwd_saving(const gj_mp_desc* d, const float* h, const float* params,
+                          float* h_out, float* e_out, void* saved, void* workspace, size_t workspace_bytes, void* stream);
+int gj_mp_step_bwd_saved(const gj_mp_desc* d, const float* h, const float* e, const float* params,
+                         const float* dh_out, float* dh, float* dparams, const void* saved,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
 /* Workspace bytes needed by gj_mp_step_bwd (P|Q, their gradients, de, per-CTA parameter-gradient partials). */
 size_t gj_mp_step_bwd_workspace(const gj_mp_desc* d);
 

@@ -342,6 +342,43 @@ def test_n150_forward_backward_runs_and_matches_fp32_vs_bf16():
     assert rel(out["bf16"][1], out["fp32"][1]) < 3e-2
 
 
+def test_saved_forward_byproducts_reproduce_the_plain_calls():
+    """gj_mp_step_fwd_saving / gj_mp_step_bwd_saved (P|Q, packed weights and pair distances kept from forward) against
+    gj_mp_step_fwd / gj_mp_step_bwd; steps that have nothing to save report 0 bytes and refuse the saving calls."""
+    from gnn_jet_autoencoder_b200 import _lib
+    lib = _lib.load()
+    N, H, edge, node, B = 30, 16, [32, 128, 64, 16], [16, 32], 64
+    rng = np.random.default_rng(3)
+    npar = sum(o * i + o for i, o in zip([2 * H + 1] + edge[:-1], edge)) + sum(o * i + o for i, o in zip([edge[-1] + H] + node[:-1], node))
+    flat = torch.from_numpy(rng.uniform(-0.3, 0.3, npar)).float().to(DEV)
+    h = torch.from_numpy(rng.normal(0, 0.5, (B, N, H))).float().to(DEV)
+    dy = torch.from_numpy(rng.normal(0, 1.0, (B, N, node[-1]))).float().to(DEV)
+    d = _lib.make_desc(B, N, H, edge, node, 0.2, 0, ops.PRECISIONS["bf16"])
+    nsaved = lib.gj_mp_step_saved_bytes(d)
+    assert nsaved > 0
+    ws_bytes = max(lib.gj_mp_step_fwd_workspace(d), lib.gj_mp_step_bwd_workspace(d))
+    ws = torch.empty(ws_bytes // 4 + 1, device=DEV)
+    saved = torch.empty(nsaved // 4 + 1, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    outs = []
+    for use_saved in (False, True):
+        y = torch.empty(B, N, node[-1], device=DEV); e = torch.empty(B, N, edge[-1], device=DEV)
+        dh = torch.zeros(B, N, H, device=DEV); g = torch.empty(npar, device=DEV)
+        sp = saved.data_ptr() if use_saved else None
+        ops.raw_mp_fwd(d, h.data_ptr(), flat.data_ptr(), y.data_ptr(), e.data_ptr(), ws.data_ptr(), ws_bytes, st, sp)
+        ops.raw_mp_bwd(d, h.data_ptr(), e.data_ptr(), flat.data_ptr(), dy.data_ptr(), dh.data_ptr(), g.data_ptr(), ws.data_ptr(), ws_bytes, st, sp)
+        torch.cuda.synchronize()
+        outs.append((y, e, dh, g))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert rel(outs[1][2].cpu().numpy(), outs[0][2].cpu().numpy()) < 1e-5
+    assert rel(outs[1][3].cpu().numpy(), outs[0][3].cpu().numpy()) < 1e-5
+    d32 = _lib.make_desc(B, N, H, edge, node, 0.2, 0, ops.PRECISIONS["fp32"])
+    assert lib.gj_mp_step_saved_bytes(d32) == 0
+    with pytest.raises(_lib.GnnJetError):
+        ops.raw_mp_fwd(d32, h.data_ptr(), flat.data_ptr(), outs[0][0].data_ptr(), outs[0][1].data_ptr(), ws.data_ptr(), ws_bytes, st,
+                       saved.data_ptr())
+
+
 def test_module_path_equals_trainer_path():
     case = CASES["default_n30"]
     enc, dec, ep, dp = build(case, "fp32")
