@@ -64,6 +64,8 @@ def test_umma_selftest(m, n, k, a_mn, b_mn):
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 @pytest.mark.parametrize("N,H,edge,node,B,metric", [
     (30, 16, [32, 128, 64, 16], [16, 32], 3, "euclidean"),
+    (6, 4, [32, 128, 64, 16], [4, 4], 5, "minkowskian"),      # fused tensor-core kernels with the Minkowskian distance
+    (150, 32, [32, 128, 64, 16], [32, 8], 2, "euclidean"),     # five j blocks per jet (per-j-block partial sums)
     (5, 4, [16, 16], [4, 4], 7, "minkowskian"),
     (33, 8, [16, 32, 16], [8, 16, 8], 2, "euclidean"),
     (1, 3, [16], [3, 2], 4, "euclidean"),
@@ -377,6 +379,33 @@ def test_saved_forward_byproducts_reproduce_the_plain_calls():
     with pytest.raises(_lib.GnnJetError):
         ops.raw_mp_fwd(d32, h.data_ptr(), flat.data_ptr(), outs[0][0].data_ptr(), outs[0][1].data_ptr(), ws.data_ptr(), ws_bytes, st,
                        saved.data_ptr())
+
+
+def test_bench_hooks_relaunch_the_fused_kernels():
+    """gj_bench_edge_*_only (bench.py's roofline timing) run on the workspace of a preceding full call; the forward
+    relaunch reproduces e bit for bit; steps outside the fused kernels are refused."""
+    lib = _lib.load()
+    N, H, edge, node, B = 30, 16, [32, 128, 64, 16], [16, 32], 16
+    npar = sum(o * i + o for i, o in zip([2 * H + 1] + edge[:-1], edge)) + sum(o * i + o for i, o in zip([edge[-1] + H] + node[:-1], node))
+    g = torch.Generator(device="cpu").manual_seed(5)
+    flat = ((torch.rand(npar, generator=g) - 0.5) * 0.4).to(DEV)
+    h = (torch.randn(B, N, H, generator=g) * 0.5).to(DEV)
+    dy = torch.randn(B, N, node[-1], generator=g).to(DEV)
+    d = _lib.make_desc(B, N, H, edge, node, 0.2, 0, ops.PRECISIONS["bf16"])
+    ws_bytes = max(lib.gj_mp_step_fwd_workspace(d), lib.gj_mp_step_bwd_workspace(d))
+    ws = torch.empty(ws_bytes // 4 + 1, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    y = torch.empty(B, N, node[-1], device=DEV); e = torch.empty(B, N, edge[-1], device=DEV); e2 = torch.zeros_like(e)
+    dh = torch.zeros(B, N, H, device=DEV); gr = torch.empty(npar, device=DEV)
+    ops.raw_mp_fwd(d, h.data_ptr(), flat.data_ptr(), y.data_ptr(), e.data_ptr(), ws.data_ptr(), ws_bytes, st)
+    assert lib.gj_bench_edge_fwd_only(d, h.data_ptr(), flat.data_ptr(), e2.data_ptr(), ws.data_ptr(), ws_bytes, st) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(e, e2)
+    ops.raw_mp_bwd(d, h.data_ptr(), e.data_ptr(), flat.data_ptr(), dy.data_ptr(), dh.data_ptr(), gr.data_ptr(), ws.data_ptr(), ws_bytes, st)
+    assert lib.gj_bench_edge_bwd_only(d, h.data_ptr(), flat.data_ptr(), dh.data_ptr(), gr.data_ptr(), ws.data_ptr(), ws_bytes, st) == 0
+    torch.cuda.synchronize()
+    d32 = _lib.make_desc(B, N, H, edge, node, 0.2, 0, ops.PRECISIONS["fp32"])
+    assert lib.gj_bench_edge_fwd_only(d32, h.data_ptr(), flat.data_ptr(), e2.data_ptr(), ws.data_ptr(), ws_bytes, st) != 0
 
 
 def test_module_path_equals_trainer_path():
