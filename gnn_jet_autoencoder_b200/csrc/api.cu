@@ -15,6 +15,7 @@ void gj_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static bool node_tc_disabled() { static const bool v = getenv("GJ_NODE_SIMT") && atoi(getenv("GJ_NODE_SIMT")) != 0; return v; }
 bool gj_tc_v1_forced() { static const bool v = getenv("GJ_TC_V1") && atoi(getenv("GJ_TC_V1")) != 0; return v; }
 
 int gj_num_sms() {
@@ -33,6 +34,10 @@ int gj_num_sms() {
 int gj_node_pre_fwd(const MPLayout&, const float*, const float*, float*, cudaStream_t);
 size_t gj_node_pre_bwd_ws_floats(const MPLayout&);
 int gj_node_pre_bwd(const MPLayout&, const float*, const float*, const float*, float*, float*, float*, cudaStream_t);
+bool gj_node_pre_bwd_tc_supported(const MPLayout&);
+size_t gj_node_pre_bwd_tc_ws_floats(const MPLayout&);
+int gj_node_pre_bwd_tc(const MPLayout&, const float*, const float*, const float*, float*, float*, int*, cudaStream_t);
+int gj_reduce_pre_partials(const MPLayout&, const float*, int, float*, cudaStream_t);
 int gj_node_post_fwd(const MPLayout&, const float*, const float*, const float*, float*, cudaStream_t);
 size_t gj_node_post_bwd_ws_floats(const MPLayout&);
 int gj_node_post_bwd(const MPLayout&, const float*, const float*, const float*, const float*, float*, float*, float*, float*,
@@ -112,6 +117,7 @@ static StepWs plan_ws(const MPLayout& L, int precision, bool backward) {
     w.de = off; off += align_floats(rows * L.EL);
     size_t p = gj_node_post_bwd_ws_floats(L);
     size_t q = gj_node_pre_bwd_ws_floats(L);
+    if (tc2_path(L, precision) && gj_node_pre_bwd_tc_supported(L)) { const size_t q2 = gj_node_pre_bwd_tc_ws_floats(L); if (q2 > q) q = q2; }
     size_t r = use_tc(L, precision) ? gj_edge_bwd_tc_ws_floats(L) : (size_t)gj_edge_grid(L.B) * L.pV[0];
     if (tc2_path(L, precision)) { const size_t r2 = gj_bwd2_ws_floats(L); if (r2 > r) r = r2; }
     if (q > p) p = q;
@@ -206,6 +212,11 @@ static int mp_step_bwd_impl(const gj_mp_desc* d, const float* h, const float* e,
                                  : gj_edge_bwd_simt(L, h, ws + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.part, st);
   if (rc) return rc;
   // first-layer projections' adjoint: dh += Wa^T dP + Wb^T dQ, dWa, dWb, db0
+  if (tc2 && gj_node_pre_bwd_tc_supported(L) && !node_tc_disabled()) {      // bf16 mode: the projections' adjoint on tcgen05
+    int nparts = 0;
+    if ((rc = gj_node_pre_bwd_tc(L, h, params, ws + w.dpq, dh, ws + w.part, &nparts, st))) return rc;
+    return gj_reduce_pre_partials(L, ws + w.part, nparts, dparams, st);
+  }
   return gj_node_pre_bwd(L, h, params, ws + w.dpq, dh, dparams, ws + w.part, st);
 }
 

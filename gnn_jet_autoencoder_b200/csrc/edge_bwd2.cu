@@ -731,45 +731,88 @@ __global__ void __launch_bounds__(256) pair_dist_fwd_kernel(const float* __restr
   }
 }
 // dh[n][k] += 2 s_k sum_m S[n][m] (h[n][k] - h[m][k]),  S[n][m] = G[m][n] + G[n][m],  s_k = -1 for the minkowskian space
-// components.  One (jet, node, 4 columns) per thread, h and G of the CTA's JPB jets staged in shared memory.
+// components.  One (jet, node) per thread with C4 float4 accumulators (S[n][m] is read once per m for all of them); h and G
+// of the CTA's JPB jets are staged in shared memory with 16-byte global loads.
+template <int C4>
 __global__ void __launch_bounds__(256) pair_dist_bwd_kernel(const float* __restrict__ h, const float* __restrict__ G, int B, int N,
                                                             int NJ32, int cols, int ld, int mink, int JPB, float* __restrict__ dh) {
   extern __shared__ float4 pd_smem4[];
   float* pd_smem = reinterpret_cast<float*>(pd_smem4);
-  const int hs = pd_stride(cols), c4 = (cols + 3) >> 2, gs = N | 1;
+  const int hs = pd_stride(cols), c4 = (cols + 3) >> 2, gs = N | 1, ld4 = ld >> 2, nj4 = NJ32 >> 2;
   float* sh = pd_smem;                       // [JPB][N][hs]
   float* sG = pd_smem + JPB * N * hs;        // [JPB][N][gs]
+  const bool vec = (ld & 3) == 0 && 4 * c4 <= ld;
   for (int b0 = blockIdx.x * JPB; b0 < B; b0 += gridDim.x * JPB) {
-    const int nj = min(JPB, B - b0);
+    const int nj = min(JPB, B - b0), nr = nj * N;
     __syncthreads();
-    for (int idx = threadIdx.x; idx < nj * N * 4 * c4; idx += 256) {
-      const int r = idx / (4 * c4), k = idx - r * (4 * c4);
-      sh[r * hs + k] = k < cols ? __ldg(h + ((size_t)b0 * N + r) * ld + k) : 0.f;
-    }
-    for (int idx = threadIdx.x; idx < nj * N * N; idx += 256) {
-      const int r = idx / N, m = idx - r * N;
-      sG[r * gs + m] = __ldg(G + ((size_t)b0 * N + r) * NJ32 + m);
-    }
-    __syncthreads();
-    for (int item = threadIdx.x; item < nj * N * c4; item += 256) {
-      const int r = item / c4, kq = item - r * c4;
-      const int jl = r / N, n = r - jl * N;
-      const float* hj = sh + jl * N * hs + 4 * kq;
-      const float* Gj = sG + jl * N * gs;
-      const float4 hn = *reinterpret_cast<const float4*>(hj + n * hs);
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 2
-      for (int m = 0; m < N; ++m) {
-        const float sv = Gj[m * gs + n] + Gj[n * gs + m];
-        const float4 hm = *reinterpret_cast<const float4*>(hj + m * hs);
-        acc.x = fmaf(sv, hn.x - hm.x, acc.x); acc.y = fmaf(sv, hn.y - hm.y, acc.y);
-        acc.z = fmaf(sv, hn.z - hm.z, acc.z); acc.w = fmaf(sv, hn.w - hm.w, acc.w);
+    if (vec) {
+      const float4* src = reinterpret_cast<const float4*>(h + (size_t)b0 * N * ld);
+      for (int idx = threadIdx.x; idx < nr * c4; idx += 256) {
+        const int r = idx / c4, k = idx - r * c4;
+        float4 v = __ldg(src + (size_t)r * ld4 + k);
+        if (4 * k + 1 >= cols) v.y = 0.f;
+        if (4 * k + 2 >= cols) v.z = 0.f;
+        if (4 * k + 3 >= cols) v.w = 0.f;
+        *reinterpret_cast<float4*>(sh + r * hs + 4 * k) = v;
       }
-      float* dst = dh + ((size_t)b0 * N + r) * ld + 4 * kq;
-      const float av[4] = {acc.x, acc.y, acc.z, acc.w};
+    } else {
+      for (int idx = threadIdx.x; idx < nr * 4 * c4; idx += 256) {
+        const int r = idx / (4 * c4), k = idx - r * (4 * c4);
+        sh[r * hs + k] = k < cols ? __ldg(h + ((size_t)b0 * N + r) * ld + k) : 0.f;
+      }
+    }
+    {
+      const float4* src = reinterpret_cast<const float4*>(G + (size_t)b0 * N * NJ32);
+      for (int idx = threadIdx.x; idx < nr * nj4; idx += 256) {
+        const int r = idx / nj4, q = idx - r * nj4;
+        const float4 v = __ldg(src + idx);
+        float* dst = sG + r * gs + 4 * q;
+        if (4 * q < N) dst[0] = v.x;
+        if (4 * q + 1 < N) dst[1] = v.y;
+        if (4 * q + 2 < N) dst[2] = v.z;
+        if (4 * q + 3 < N) dst[3] = v.w;
+      }
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < nr; r += 256) {
+      const int jl = r / N, n = r - jl * N;
+      const float* hj = sh + jl * N * hs;
+      const float* Gj = sG + jl * N * gs;
+      float* dst = dh + ((size_t)b0 * N + r) * ld;
+      for (int k0 = 0; k0 < c4; k0 += C4) {
+        float4 hn[C4], acc[C4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (4 * kq + q < cols) dst[q] += ((mink && 4 * kq + q > 0) ? -2.f : 2.f) * av[q];
+        for (int u = 0; u < C4; ++u) {
+          hn[u] = k0 + u < c4 ? *reinterpret_cast<const float4*>(hj + n * hs + 4 * (k0 + u)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll 2
+        for (int m = 0; m < N; ++m) {
+          const float sv = Gj[m * gs + n] + Gj[n * gs + m];
+#pragma unroll
+          for (int u = 0; u < C4; ++u) {
+            if (C4 > 1 && k0 + u >= c4) break;
+            const float4 hm = *reinterpret_cast<const float4*>(hj + m * hs + 4 * (k0 + u));
+            acc[u].x = fmaf(sv, hn[u].x - hm.x, acc[u].x); acc[u].y = fmaf(sv, hn[u].y - hm.y, acc[u].y);
+            acc[u].z = fmaf(sv, hn[u].z - hm.z, acc[u].z); acc[u].w = fmaf(sv, hn[u].w - hm.w, acc[u].w);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < C4; ++u) {
+          const int k = 4 * (k0 + u);
+          const float s0 = (mink && k > 0) ? -2.f : 2.f, s1 = mink ? -2.f : 2.f;
+          if (vec && k + 3 < cols) {
+            float4 o = *reinterpret_cast<const float4*>(dst + k);
+            o.x = fmaf(s0, acc[u].x, o.x); o.y = fmaf(s1, acc[u].y, o.y); o.z = fmaf(s1, acc[u].z, o.z); o.w = fmaf(s1, acc[u].w, o.w);
+            *reinterpret_cast<float4*>(dst + k) = o;
+          } else {
+            const float av[4] = {acc[u].x, acc[u].y, acc[u].z, acc[u].w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (k + q < cols) dst[k + q] = fmaf(q == 0 ? s0 : s1, av[q], dst[k + q]);
+          }
+        }
+      }
     }
   }
 }
@@ -879,9 +922,11 @@ int gj_edge_bwd2(const MPLayout& L, const float* h, const float* pq, const float
   {
     const int jpb = pd_jpb(L), smem = pd_smem_bwd(L);
     int blocks = (L.B + jpb - 1) / jpb; if (blocks > 8 * gj_num_sms()) blocks = 8 * gj_num_sms();
-    ce = cudaFuncSetAttribute(pair_dist_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    const int c4 = (L.cols + 3) >> 2;
+    auto pdk = c4 <= 1 ? pair_dist_bwd_kernel<1> : c4 <= 2 ? pair_dist_bwd_kernel<2> : c4 <= 4 ? pair_dist_bwd_kernel<4> : pair_dist_bwd_kernel<8>;
+    ce = cudaFuncSetAttribute(pdk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (ce != cudaSuccess) { gj_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
-    pair_dist_bwd_kernel<<<blocks, 256, smem, stream>>>(h, G, L.B, L.N, NJ32, L.cols, L.ld, L.mink, jpb, dh);
+    pdk<<<blocks, 256, smem, stream>>>(h, G, L.B, L.N, NJ32, L.cols, L.ld, L.mink, jpb, dh);
   }
   ce = cudaGetLastError();
   if (ce != cudaSuccess) { gj_set_error("edge_bwd2 tail launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }

@@ -821,6 +821,14 @@ static int nf_bwd_grid(int rows) {      // the per-CTA partials are reduced afte
   return blocks < cap ? (blocks > 0 ? blocks : 1) : cap;
 }
 
+// fixed-order reduction of per-CTA [dWa | dWb | db0] partials into the packed W0 / b0 gradients
+int gj_reduce_pre_partials(const MPLayout& L, const float* part, int nparts, float* dparams, cudaStream_t st) {
+  const int n = L.E[0] * 2 * L.H + L.E[0];
+  reduce_pre_partials_kernel<<<(n + 31) / 32, dim3(32, RED_SLICES), 0, st>>>(part, nparts, L.E[0], L.H, dparams + L.pW[0], dparams + L.pb[0]);
+  NK_CHECK_LAUNCH("reduce_pre_partials launch");
+  return GJ_OK;
+}
+
 int gj_node_pre_bwd(const MPLayout& L, const float* h, const float* params, const float* dpq, float* dh, float* dparams,
                     float* part, cudaStream_t st) {
   PreArgs A; int bytes = pre_plan(L, &A, true);
