@@ -15,6 +15,7 @@ void gj_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static bool node_post_tc_enabled() { static const bool v = !(getenv("GJ_NODE_POST_SIMT") && atoi(getenv("GJ_NODE_POST_SIMT")) != 0); return v && !(getenv("GJ_NODE_SIMT") && atoi(getenv("GJ_NODE_SIMT")) != 0); }
 static bool node_tc_disabled() { static const bool v = getenv("GJ_NODE_SIMT") && atoi(getenv("GJ_NODE_SIMT")) != 0; return v; }
 bool gj_tc_v1_forced() { static const bool v = getenv("GJ_TC_V1") && atoi(getenv("GJ_TC_V1")) != 0; return v; }
 
@@ -40,6 +41,10 @@ int gj_node_pre_bwd_tc(const MPLayout&, const float*, const float*, const float*
 int gj_reduce_pre_partials(const MPLayout&, const float*, int, float*, cudaStream_t);
 int gj_node_post_fwd(const MPLayout&, const float*, const float*, const float*, float*, cudaStream_t);
 size_t gj_node_post_bwd_ws_floats(const MPLayout&);
+bool gj_node_post_bwd_tc_supported(const MPLayout&);
+size_t gj_node_post_bwd_tc_ws_floats(const MPLayout&);
+int gj_node_post_bwd_tc(const MPLayout&, const float*, const float*, const float*, const float*, float*, float*, float*, int*, cudaStream_t);
+int gj_reduce_partials(const float*, int, int, float*, cudaStream_t);
 int gj_node_post_bwd(const MPLayout&, const float*, const float*, const float*, const float*, float*, float*, float*, float*,
                      cudaStream_t);
 int gj_edge_grid(int);
@@ -116,6 +121,7 @@ static StepWs plan_ws(const MPLayout& L, int precision, bool backward) {
     w.dpq = off; off += align_floats(rows * 2 * L.E0p);
     w.de = off; off += align_floats(rows * L.EL);
     size_t p = gj_node_post_bwd_ws_floats(L);
+    if (tc2_path(L, precision) && gj_node_post_bwd_tc_supported(L)) { const size_t p2 = gj_node_post_bwd_tc_ws_floats(L); if (p2 > p) p = p2; }
     size_t q = gj_node_pre_bwd_ws_floats(L);
     if (tc2_path(L, precision) && gj_node_pre_bwd_tc_supported(L)) { const size_t q2 = gj_node_pre_bwd_tc_ws_floats(L); if (q2 > q) q = q2; }
     size_t r = use_tc(L, precision) ? gj_edge_bwd_tc_ws_floats(L) : (size_t)gj_edge_grid(L.B) * L.pV[0];
@@ -201,7 +207,11 @@ static int mp_step_bwd_impl(const gj_mp_desc* d, const float* h, const float* e,
   if (saved && !tc2) { gj_set_error("%s: this step has nothing saved (gj_mp_step_saved_bytes is 0)", who); return GJ_ERR_INVALID; }
   float* pre = saved ? (float*)saved : ws;      // read-only when it is the caller's saved buffer
   // node MLP adjoint: de, node-path dh, node parameter gradients
-  if ((rc = gj_node_post_bwd(L, e, h, params, dh_out, ws + w.de, dh, dparams, ws + w.part, st))) return rc;
+  if (tc2 && gj_node_post_bwd_tc_supported(L) && node_post_tc_enabled()) {      // bf16 mode: the node MLP adjoint on tcgen05
+    int nparts = 0;
+    if ((rc = gj_node_post_bwd_tc(L, e, h, params, dh_out, ws + w.de, dh, ws + w.part, &nparts, st))) return rc;
+    if ((rc = gj_reduce_partials(ws + w.part, nparts, L.nparams - L.pV[0], dparams + L.pV[0], st))) return rc;
+  } else if ((rc = gj_node_post_bwd(L, e, h, params, dh_out, ws + w.de, dh, dparams, ws + w.part, st))) return rc;
   // P|Q (recomputed unless saved by the forward call), then the edge adjoint: dP|dQ, distance-path dh, edge parameter gradients
   if (!saved && (rc = gj_node_pre_fwd(L, h, params, pre + w.pq, st))) return rc;
   if (tc2)
