@@ -118,22 +118,36 @@ int gj_latent_mean_bwd_launch(int B, int N, int W, const float* dz, float* dy, c
 // ------------------------------------------------------------------------------------------------
 namespace {
 
-constexpr int kLinRowsPerBlock = 128;
+constexpr int kLinRB = 8;            // rows per CTA of the forward / input-gradient kernels (staged in shared memory)
+constexpr int kLinChunk = 32;        // rows per weight-gradient partial (fewer when K is so large that the x tile would not fit)
+constexpr int kLinKT = 32;           // in-features a weight-gradient thread accumulates in registers
 
-// y[r][o] = b[o] + sum_k x[r][k] w[o][k]; one thread per output, o fastest (coalesced store, broadcast x).
-__global__ void linear_fwd_kernel(int rows, int K, int O, const float* __restrict__ x, const float* __restrict__ w,
-                                  const float* __restrict__ b, float* __restrict__ y) {
-  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)rows * O) return;
-  int r = (int)(idx / O), o = (int)(idx - (size_t)r * O);
-  float acc = b ? __ldg(b + o) : 0.f;
-  const float* xr = x + (size_t)r * K;
-  const float* wo = w + (size_t)o * K;
-  for (int k = 0; k < K; ++k) acc = fmaf(__ldg(xr + k), __ldg(wo + k), acc);
-  y[idx] = acc;
+// y[r][o] = b[o] + sum_k x[r][k] w[o][k].  A CTA owns kLinRB rows (x staged in shared memory, read as broadcasts) and
+// walks the outputs 256 at a time; a thread reads its weight row once for all the CTA's rows.
+__global__ void __launch_bounds__(256) linear_fwd_kernel(int rows, int K, int O, const float* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ b, float* __restrict__ y) {
+  extern __shared__ float lin_smem[];      // [kLinRB][K]
+  const int r0 = blockIdx.x * kLinRB, nr = min(kLinRB, rows - r0);
+  for (int idx = threadIdx.x; idx < nr * K; idx += 256) lin_smem[idx] = __ldg(x + (size_t)r0 * K + idx);
+  for (int idx = nr * K + threadIdx.x; idx < kLinRB * K; idx += 256) lin_smem[idx] = 0.f;
+  __syncthreads();
+  for (int o = threadIdx.x; o < O; o += 256) {
+    float acc[kLinRB];
+    const float bias = b ? __ldg(b + o) : 0.f;
+#pragma unroll
+    for (int r = 0; r < kLinRB; ++r) acc[r] = bias;
+    const float* wo = w + (size_t)o * K;
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+      const float wv = __ldg(wo + k);
+#pragma unroll
+      for (int r = 0; r < kLinRB; ++r) acc[r] = fmaf(lin_smem[r * K + k], wv, acc[r]);
+    }
+    for (int r = 0; r < nr; ++r) y[(size_t)(r0 + r) * O + o] = acc[r];
+  }
 }
 
-// dx[r][k] = sum_o dy[r][o] w[o][k]
+// dx[r][k] = sum_o dy[r][o] w[o][k], generic form: one thread per (row, k)
 __global__ void linear_dx_kernel(int rows, int K, int O, const float* __restrict__ dy, const float* __restrict__ w,
                                  float* __restrict__ dx) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -145,59 +159,173 @@ __global__ void linear_dx_kernel(int rows, int K, int O, const float* __restrict
   dx[idx] = acc;
 }
 
-// Per row chunk: part[chunk][k*O + o] = sum_{r in chunk} dy[r][o] x[r][k]; slot k == K holds the bias gradient.
-__global__ void linear_dw_partial_kernel(int rows, int K, int O, const float* __restrict__ x, const float* __restrict__ dy,
-                                         float* __restrict__ part) {
-  const int r0 = blockIdx.y * kLinRowsPerBlock;
-  const int r1 = min(rows, r0 + kLinRowsPerBlock);
-  const int total = (K + 1) * O;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    int k = idx / O, o = idx - k * O;
-    float acc = 0.f;
-    if (k < K) { for (int r = r0; r < r1; ++r) acc = fmaf(__ldg(dy + (size_t)r * O + o), __ldg(x + (size_t)r * K + k), acc); }
-    else { for (int r = r0; r < r1; ++r) acc += __ldg(dy + (size_t)r * O + o); }
-    part[(size_t)blockIdx.y * total + idx] = acc;
+// Same for K <= 32 (decoder input layer, local mix): w staged in shared memory, one warp per row, lanes split the O
+// outputs and keep K running sums each, combined by shuffles at the end of the row.
+constexpr int kDxRowsPerBlock = 8;       // one row per warp
+constexpr int kDxMaxO = 1024;            // a lane keeps its dy values of the row in registers
+template <bool VEC>
+__global__ void __launch_bounds__(256) linear_dx_smallk_kernel(int rows, int K, int O, const float* __restrict__ dy,
+                                                               const float* __restrict__ w, float* __restrict__ dx) {
+  extern __shared__ float4 lin_smem4[];      // [O][K]
+  float* lin_smem = reinterpret_cast<float*>(lin_smem4);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r = blockIdx.x * kDxRowsPerBlock + warp;
+  float g[kDxMaxO / 32];
+#pragma unroll
+  for (int j = 0; j < kDxMaxO / 32; ++j) g[j] = (r < rows && lane + 32 * j < O) ? __ldg(dy + (size_t)r * O + lane + 32 * j) : 0.f;
+  for (int idx = threadIdx.x; idx < O * K; idx += 256)      // asynchronous copies: the loads do not wait for one another
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(lin_smem + idx)), "l"(w + idx) : "memory");
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  if (r >= rows) return;
+  float acc[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) acc[k] = 0.f;
+#pragma unroll
+  for (int j = 0; j < kDxMaxO / 32; ++j) {
+    if (32 * j >= O) break;      // uniform
+    const int o = min(lane + 32 * j, O - 1);      // lanes past the end carry g = 0
+    const float* wo = lin_smem + o * K;
+    if (VEC) {      // K % 4 == 0: 16-byte reads (lanes are K floats apart: conflict free for K = 4 * odd)
+#pragma unroll
+      for (int q4 = 0; q4 < 8; ++q4) {
+        if (4 * q4 < K) {
+          const float4 v = *reinterpret_cast<const float4*>(wo + 4 * q4);
+          acc[4 * q4] = fmaf(g[j], v.x, acc[4 * q4]); acc[4 * q4 + 1] = fmaf(g[j], v.y, acc[4 * q4 + 1]);
+          acc[4 * q4 + 2] = fmaf(g[j], v.z, acc[4 * q4 + 2]); acc[4 * q4 + 3] = fmaf(g[j], v.w, acc[4 * q4 + 3]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 32; ++k) if (k < K) acc[k] = fmaf(g[j], wo[k], acc[k]);
+    }
+  }
+  float mine = 0.f;
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    if (k < K) {      // uniform
+      float v = acc[k];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+      if (lane == k) mine = v;
+    }
+  }
+  if (lane < K) dx[(size_t)r * K + lane] = mine;
+}
+
+// Per chunk of rows: part[chunk][o * (K + 1) + k] = sum_r dy[r][o] x[r][k]; slot k == K holds the bias gradient (x extended
+// by a column of ones).  A thread owns one output o and kLinKT consecutive k in registers; the x tile rows are padded to a
+// multiple of 4 floats and read as 16-byte broadcasts.
+__global__ void __launch_bounds__(256) linear_dw_partial_kernel(int rows, int K, int O, int chunk, const float* __restrict__ x,
+                                                                const float* __restrict__ dy, float* __restrict__ part) {
+  extern __shared__ float4 lin_smem4[];      // [chunk][K1p]
+  float* xs = reinterpret_cast<float*>(lin_smem4);
+  const int K1 = K + 1, K1p = (K1 + 3) & ~3, r0 = blockIdx.y * chunk, nr = min(chunk, rows - r0);
+  for (int idx = threadIdx.x; idx < chunk * K1p; idx += 256) {
+    const int r = idx / K1p, k = idx - r * K1p;
+    xs[idx] = r < nr ? (k < K ? __ldg(x + (size_t)(r0 + r) * K + k) : (k == K ? 1.f : 0.f)) : 0.f;
+  }
+  __syncthreads();
+  const int kchunks = (K1 + kLinKT - 1) / kLinKT, items = O * kchunks;
+  for (int item = blockIdx.x * 256 + threadIdx.x; item < items; item += gridDim.x * 256) {
+    const int kc = item / O, o = item - kc * O, k0 = kc * kLinKT;
+    float acc[kLinKT];
+#pragma unroll
+    for (int q = 0; q < kLinKT; ++q) acc[q] = 0.f;
+    float g[kLinChunk];      // the chunk's dy column first: the loads overlap one another
+#pragma unroll
+    for (int r = 0; r < kLinChunk; ++r) g[r] = r < nr ? __ldg(dy + (size_t)(r0 + r) * O + o) : 0.f;
+#pragma unroll
+    for (int r = 0; r < kLinChunk; ++r) {
+      if (r >= nr) continue;      // uniform
+      const float4* xr = reinterpret_cast<const float4*>(xs + r * K1p + k0);
+#pragma unroll
+      for (int q4 = 0; q4 < kLinKT / 4; ++q4) {
+        if (k0 + 4 * q4 < K1) {      // uniform
+          const float4 v = xr[q4];
+          acc[4 * q4] = fmaf(g[r], v.x, acc[4 * q4]); acc[4 * q4 + 1] = fmaf(g[r], v.y, acc[4 * q4 + 1]);
+          acc[4 * q4 + 2] = fmaf(g[r], v.z, acc[4 * q4 + 2]); acc[4 * q4 + 3] = fmaf(g[r], v.w, acc[4 * q4 + 3]);
+        }
+      }
+    }
+    float* dst = part + (size_t)blockIdx.y * O * K1 + (size_t)o * K1 + k0;
+#pragma unroll
+    for (int q = 0; q < kLinKT; ++q) if (k0 + q < K1) dst[q] = acc[q];
   }
 }
 
-__global__ void linear_dw_reduce_kernel(int nchunks, int K, int O, const float* __restrict__ part, float* __restrict__ dw,
-                                        float* __restrict__ db) {
-  const int total = (K + 1) * O;
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
+// fixed-order sum of the chunk partials: block = 32 outputs x 8 slices; slice y sums chunks y, y + 8, ... and the slice
+// sums are combined in slice order
+__global__ void __launch_bounds__(256) linear_dw_reduce_kernel(int nchunks, int K, int O, const float* __restrict__ part,
+                                                               float* __restrict__ dw, float* __restrict__ db) {
+  __shared__ float red[8][33];
+  const int K1 = K + 1, total = K1 * O;
+  const int idx = blockIdx.x * 32 + threadIdx.x;
   float acc = 0.f;
-  for (int c = 0; c < nchunks; ++c) acc += part[(size_t)c * total + idx];
-  int k = idx / O, o = idx - k * O;
-  if (k < K) dw[(size_t)o * K + k] = acc;
-  else if (db) db[o] = acc;
+  if (idx < total)
+    for (int c = threadIdx.y; c < nchunks; c += 8) acc += part[(size_t)c * total + idx];
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && idx < total) {
+    float tot = 0.f;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) tot += red[y][threadIdx.x];
+    const int o = idx / K1, k = idx - o * K1;
+    if (k < K) dw[(size_t)o * K + k] = tot;
+    else if (db) db[o] = tot;
+  }
 }
 
 }  // namespace
 
+static int lin_set_smem(const void* kern, size_t bytes, const char* who) {
+  if (bytes > 200 * 1024) { gj_set_error("%s: layer too wide for the shared-memory row tile (%zu bytes)", who, bytes); return GJ_ERR_SMEM; }
+  if (bytes > 48 * 1024) {
+    cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (ce != cudaSuccess) { gj_set_error("%s: %s", who, cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
+  }
+  return GJ_OK;
+}
+
 int gj_linear_fwd_launch(int rows, int K, int O, const float* x, const float* w, const float* b, float* y, cudaStream_t stream) {
-  size_t total = (size_t)rows * O;
-  if (total == 0) return GJ_OK;
-  linear_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(rows, K, O, x, w, b, y);
+  if ((size_t)rows * O == 0) return GJ_OK;
+  const size_t smem = (size_t)kLinRB * K * sizeof(float);
+  if (int rc = lin_set_smem((const void*)linear_fwd_kernel, smem, "linear_fwd")) return rc;
+  linear_fwd_kernel<<<(rows + kLinRB - 1) / kLinRB, 256, smem, stream>>>(rows, K, O, x, w, b, y);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) { gj_set_error("linear_fwd launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   return GJ_OK;
 }
 
-static int lin_chunks(int rows) { int c = (rows + kLinRowsPerBlock - 1) / kLinRowsPerBlock; return c < 1 ? 1 : c; }
+static int lin_chunk_rows(int K) { int c = kLinChunk; while (c > 1 && (size_t)c * (K + 4) * sizeof(float) > 96 * 1024) c >>= 1; return c; }
+static int lin_chunks(int rows, int K) { const int cr = lin_chunk_rows(K); int c = (rows + cr - 1) / cr; return c < 1 ? 1 : c; }
 
-size_t gj_linear_bwd_ws_bytes(int rows, int K, int O) { return (size_t)lin_chunks(rows) * (K + 1) * O * sizeof(float); }
+size_t gj_linear_bwd_ws_bytes(int rows, int K, int O) { return (size_t)lin_chunks(rows, K) * (K + 1) * O * sizeof(float); }
 
 int gj_linear_bwd_launch(int rows, int K, int O, const float* x, const float* w, const float* dy, float* dx, float* dw,
                          float* db, void* ws, size_t ws_bytes, cudaStream_t stream) {
   if (ws_bytes < gj_linear_bwd_ws_bytes(rows, K, O)) { gj_set_error("gj_linear_bwd: workspace too small"); return GJ_ERR_WORKSPACE; }
   const int total = (K + 1) * O;
-  const int nch = rows > 0 ? lin_chunks(rows) : 0;
+  const int nch = rows > 0 ? lin_chunks(rows, K) : 0, chunk = lin_chunk_rows(K);
   if (rows > 0) {
-    if (dx) linear_dx_kernel<<<(unsigned)(((size_t)rows * K + 255) / 256), 256, 0, stream>>>(rows, K, O, dy, w, dx);
-    dim3 grid((total + 255) / 256, nch);
-    linear_dw_partial_kernel<<<grid, 256, 0, stream>>>(rows, K, O, x, dy, (float*)ws);
+    if (dx) {
+      const size_t smem = (size_t)O * K * sizeof(float);
+      if (K <= 32 && O <= kDxMaxO && smem <= 64 * 1024) {
+        auto kern = (K & 3) == 0 ? linear_dx_smallk_kernel<true> : linear_dx_smallk_kernel<false>;
+        if (int rc = lin_set_smem((const void*)kern, smem, "linear_bwd")) return rc;
+        kern<<<(rows + kDxRowsPerBlock - 1) / kDxRowsPerBlock, 256, smem, stream>>>(rows, K, O, dy, w, dx);
+      } else {
+        linear_dx_kernel<<<(unsigned)(((size_t)rows * K + 255) / 256), 256, 0, stream>>>(rows, K, O, dy, w, dx);
+      }
+    }
+    const size_t smem = (size_t)chunk * ((K + 4) & ~3) * sizeof(float);
+    if (int rc = lin_set_smem((const void*)linear_dw_partial_kernel, smem, "linear_bwd")) return rc;
+    const int items = O * ((K + 1 + kLinKT - 1) / kLinKT);
+    dim3 grid((items + 255) / 256, nch);
+    linear_dw_partial_kernel<<<grid, 256, smem, stream>>>(rows, K, O, chunk, x, dy, (float*)ws);
   }
-  linear_dw_reduce_kernel<<<(total + 255) / 256, 256, 0, stream>>>(nch, K, O, (const float*)ws, dw, db);
+  linear_dw_reduce_kernel<<<(total + 31) / 32, dim3(32, 8), 0, stream>>>(nch, K, O, (const float*)ws, dw, db);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) { gj_set_error("linear_bwd launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   return GJ_OK;
