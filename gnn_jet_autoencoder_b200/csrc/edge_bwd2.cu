@@ -82,6 +82,9 @@ struct Bwd2Smem {
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void cp_async4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -749,6 +752,7 @@ __global__ void __launch_bounds__(256) pair_dist_bwd_kernel(const float* __restr
       const float4* src = reinterpret_cast<const float4*>(h + (size_t)b0 * N * ld);
       for (int idx = threadIdx.x; idx < nr * c4; idx += 256) {
         const int r = idx / c4, k = idx - r * c4;
+        if (4 * k + 3 < cols) { cp_async16(sh + r * hs + 4 * k, src + (size_t)r * ld4 + k); continue; }
         float4 v = __ldg(src + (size_t)r * ld4 + k);
         if (4 * k + 1 >= cols) v.y = 0.f;
         if (4 * k + 2 >= cols) v.z = 0.f;
@@ -765,14 +769,14 @@ __global__ void __launch_bounds__(256) pair_dist_bwd_kernel(const float* __restr
       const float4* src = reinterpret_cast<const float4*>(G + (size_t)b0 * N * NJ32);
       for (int idx = threadIdx.x; idx < nr * nj4; idx += 256) {
         const int r = idx / nj4, q = idx - r * nj4;
-        const float4 v = __ldg(src + idx);
-        float* dst = sG + r * gs + 4 * q;
-        if (4 * q < N) dst[0] = v.x;
-        if (4 * q + 1 < N) dst[1] = v.y;
-        if (4 * q + 2 < N) dst[2] = v.z;
-        if (4 * q + 3 < N) dst[3] = v.w;
+        const float* g4 = G + (size_t)b0 * N * NJ32 + 4 * (size_t)idx;
+        float* dst = sG + r * gs + 4 * q;      // odd row stride: 4-byte asynchronous copies
+#pragma unroll
+        for (int u = 0; u < 4; ++u) if (4 * q + u < N) cp_async4(dst + u, g4 + u);
       }
     }
+    cp_async_commit();
+    cp_async_wait<0>();
     __syncthreads();
     for (int r = threadIdx.x; r < nr; r += 256) {
       const int jl = r / N, n = r - jl * N;

@@ -362,6 +362,14 @@ __global__ void __launch_bounds__(NK_THREADS) node_post_bwd_kernel(const PostArg
 // registers, weights are read as warp-broadcast 16-byte shared-memory loads -> FFMA bound)
 // ---------------------------------------------------------------------------------------------------------
 #define NF_THREADS 128
+// tile staging with asynchronous 4-byte copies: a load -> store loop would wait for every load in turn
+__device__ __forceinline__ void nf_cp_async4(float* dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void nf_cp_async_wait() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
 #define NF_BWD_CTAS_PER_SM 4      // adjoint kernels: CTAs per SM the grid is sized for (one parameter-gradient partial per CTA)
 // y[o] = bias[o] + sum_k W[o][k] x[k]  for o in [o0, o0 + 4): W rows are KP floats long (zero padded), in shared memory
 template <int KP>
@@ -405,7 +413,8 @@ __global__ void __launch_bounds__(NF_THREADS) node_pre_fwd_fast_kernel(int rows,
   __shared__ __align__(16) float sO[NF_THREADS * OS];
   for (int idx = threadIdx.x; idx < 64 * KP; idx += NF_THREADS) {
     const int o = idx / KP, k = idx - o * KP;
-    W[idx] = k < cols ? __ldg(w0 + (o & 31) * K0 + (o < 32 ? k : H + k)) : 0.f;
+    if (k < cols) nf_cp_async4(W + idx, w0 + (o & 31) * K0 + (o < 32 ? k : H + k));
+    else W[idx] = 0.f;
   }
   if (threadIdx.x < 64) bias[threadIdx.x] = threadIdx.x < 32 ? __ldg(b0 + threadIdx.x) : 0.f;
   for (int row0 = blockIdx.x * NF_THREADS; row0 < rows; row0 += gridDim.x * NF_THREADS) {
@@ -413,8 +422,10 @@ __global__ void __launch_bounds__(NF_THREADS) node_pre_fwd_fast_kernel(int rows,
     __syncthreads();
     for (int idx = threadIdx.x; idx < nrows * KP; idx += NF_THREADS) {
       const int r = idx / KP, k = idx - r * KP;
-      sX[r * XS + k] = k < cols ? __ldg(h + (size_t)(row0 + r) * ld + k) : 0.f;
+      if (k < cols) nf_cp_async4(sX + r * XS + k, h + (size_t)(row0 + r) * ld + k);
+      else sX[r * XS + k] = 0.f;
     }
+    nf_cp_async_wait();
     __syncthreads();
     float x[KP];
 #pragma unroll
@@ -452,11 +463,13 @@ __global__ void __launch_bounds__(NF_THREADS) node_post_fwd_fast_kernel(int rows
   __shared__ __align__(16) float sO[NF_THREADS * OS];
   for (int idx = threadIdx.x; idx < O0P * I0P; idx += NF_THREADS) {
     const int o = idx / I0P, k = idx - o * I0P;
-    sV0[idx] = (o < O0 && k < I0) ? __ldg(V0 + o * I0 + k) : 0.f;
+    if (o < O0 && k < I0) nf_cp_async4(sV0 + idx, V0 + o * I0 + k);
+    else sV0[idx] = 0.f;
   }
   for (int idx = threadIdx.x; idx < O1P * O0P; idx += NF_THREADS) {
     const int o = idx / O0P, k = idx - o * O0P;
-    sV1[idx] = (o < O1 && k < O0) ? __ldg(V1 + o * O0 + k) : 0.f;
+    if (o < O1 && k < O0) nf_cp_async4(sV1 + idx, V1 + o * O0 + k);
+    else sV1[idx] = 0.f;
   }
   for (int o = threadIdx.x; o < O0P; o += NF_THREADS) sc0[o] = o < O0 ? __ldg(c0 + o) : 0.f;
   for (int o = threadIdx.x; o < O1P; o += NF_THREADS) sc1[o] = o < O1 ? __ldg(c1 + o) : 0.f;
@@ -465,12 +478,14 @@ __global__ void __launch_bounds__(NF_THREADS) node_post_fwd_fast_kernel(int rows
     __syncthreads();
     for (int idx = threadIdx.x; idx < nrows * 16; idx += NF_THREADS) {      // e: 16 columns, rows contiguous
       const int r = idx >> 4, k = idx & 15;
-      sX[r * XS + k] = __ldg(e + (size_t)(row0 + r) * EL + k);
+      nf_cp_async4(sX + r * XS + k, e + (size_t)(row0 + r) * EL + k);
     }
     for (int idx = threadIdx.x; idx < nrows * (I0P - 16); idx += NF_THREADS) {
       const int r = idx / (I0P - 16), k = idx - r * (I0P - 16);
-      sX[r * XS + 16 + k] = k < cols ? __ldg(h + (size_t)(row0 + r) * ld + k) : 0.f;
+      if (k < cols) nf_cp_async4(sX + r * XS + 16 + k, h + (size_t)(row0 + r) * ld + k);
+      else sX[r * XS + 16 + k] = 0.f;
     }
+    nf_cp_async_wait();
     __syncthreads();
     float x[I0P];
 #pragma unroll
@@ -584,16 +599,19 @@ __global__ void __launch_bounds__(NF_THREADS) node_post_bwd_fast_kernel(int rows
     __syncthreads();
     for (int idx = threadIdx.x; idx < nrows * 16; idx += NF_THREADS) {
       const int r = idx >> 4, k = idx & 15;
-      sX[r * XS + k] = __ldg(e + (size_t)(row0 + r) * EL + k);
+      nf_cp_async4(sX + r * XS + k, e + (size_t)(row0 + r) * EL + k);
     }
     for (int idx = threadIdx.x; idx < nrows * (I0P - 16); idx += NF_THREADS) {
       const int r = idx / (I0P - 16), k = idx - r * (I0P - 16);
-      sX[r * XS + 16 + k] = k < cols ? __ldg(h + (size_t)(row0 + r) * ld + k) : 0.f;
+      if (k < cols) nf_cp_async4(sX + r * XS + 16 + k, h + (size_t)(row0 + r) * ld + k);
+      else sX[r * XS + 16 + k] = 0.f;
     }
     for (int idx = threadIdx.x; idx < nrows * O1P; idx += NF_THREADS) {
       const int r = idx / O1P, o = idx - r * O1P;
-      sG1[r * G1S + o] = o < O1 ? __ldg(dh_out + (size_t)(row0 + r) * O1 + o) : 0.f;
+      if (o < O1) nf_cp_async4(sG1 + r * G1S + o, dh_out + (size_t)(row0 + r) * O1 + o);
+      else sG1[r * G1S + o] = 0.f;
     }
+    nf_cp_async_wait();
     __syncthreads();
     if (threadIdx.x < nrows) {
       const int t = threadIdx.x;

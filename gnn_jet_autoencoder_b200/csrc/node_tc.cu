@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(128) node_pre_bwd_tc_kernel(int rows, int H, i
   DpqRegs R;
   if ((int)blockIdx.x < ntiles) ntc_load_dpq(R, dpq, blockIdx.x * 128, rows, warp, lane);
   // ---- one-time staging: transposed projection weights, constant slabs, barrier, TMEM ----
+#pragma unroll 8
   for (int idx = tid; idx < HP * 64; idx += 128) {
     const int n = idx >> 6, c = idx & 63;
     const float v = n < cols ? __ldg(w0 + (c & 31) * K0 + (c < 32 ? n : H + n)) : 0.f;
