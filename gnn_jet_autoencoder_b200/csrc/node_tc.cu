@@ -21,6 +21,9 @@ using namespace tc2;
 __device__ __forceinline__ void ntc_cp_async16(void* dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
+__device__ __forceinline__ void ntc_cp_async4(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
 __device__ __forceinline__ void ntc_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void ntc_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -67,14 +70,21 @@ __global__ void __launch_bounds__(128) node_pre_bwd_tc_kernel(int rows, int H, i
   DpqRegs R;
   if ((int)blockIdx.x < ntiles) ntc_load_dpq(R, dpq, blockIdx.x * 128, rows, warp, lane);
   // ---- one-time staging: transposed projection weights, constant slabs, barrier, TMEM ----
-#pragma unroll 8
-  for (int idx = tid; idx < HP * 64; idx += 128) {
-    const int n = idx >> 6, c = idx & 63;
-    const float v = n < cols ? __ldg(w0 + (c & 31) * K0 + (c < 32 ? n : H + n)) : 0.f;
-    *reinterpret_cast<__nv_bfloat16*>(smem + S::o_wt + (c >> 3) * (HP * 16) + n * 16 + (c & 7) * 2) = __float2bfloat16_rn(v);
-  }
+  // W0 (32 rows of K0 = 2 H + 1 floats) first lands in the h / dh tile area through asynchronous copies (overlapping loads)
+  float* raw = reinterpret_cast<float*>(smem + S::o_th);
+  const bool raw_fits = 32 * K0 * 4 <= 2 * 128 * S::TS * 4;
+  if (raw_fits) for (int idx = tid; idx < 32 * K0; idx += 128) ntc_cp_async4(raw + idx, w0 + idx);
+  ntc_cp_async_commit();
   for (int idx = tid; idx < 1024; idx += 128)      // ones slab (channel HP = 1.0, HP + 1 .. HP + 7 = 0), zero slab
     reinterpret_cast<uint32_t*>(smem + S::o_h + (HP / 8) * 2048)[idx] = (idx < 512 && (idx & 3) == 0) ? 0x00003F80u : 0u;
+  ntc_cp_async_wait_all();
+  __syncthreads();
+  for (int idx = tid; idx < HP * 64; idx += 128) {
+    const int n = idx >> 6, c = idx & 63, src = (c & 31) * K0 + (c < 32 ? n : H + n);
+    const float v = n < cols ? (raw_fits ? raw[src] : __ldg(w0 + src)) : 0.f;
+    *reinterpret_cast<__nv_bfloat16*>(smem + S::o_wt + (c >> 3) * (HP * 16) + n * 16 + (c & 7) * 2) = __float2bfloat16_rn(v);
+  }
+  __syncthreads();      // the tile area is free for the first tile's copies
   if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
   if (warp == 0) tmem_alloc(tmem_slot, 128);
   fence_proxy_async();
@@ -297,29 +307,37 @@ __global__ void __launch_bounds__(128) node_post_bwd_tc_kernel(int rows, int col
   uint64_t* barW = barA + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::o_slot);
   // ---- one-time staging: the four weight operands, constant slabs, barriers, TMEM ----
+  // the fp32 parameters first land in the (still unused) slab area through asynchronous copies, so that the loads overlap
+  float* raw = reinterpret_cast<float*>(smem + S::o_g0);      // [V0 | V1 | c0 | c1]
+  for (int idx = tid; idx < O0 * I0; idx += 128) ntc_cp_async4(raw + idx, V0 + idx);
+  for (int idx = tid; idx < O1 * O0; idx += 128) ntc_cp_async4(raw + O0 * I0 + idx, V1 + idx);
+  for (int n = tid; n < O0; n += 128) ntc_cp_async4(raw + O0 * I0 + O1 * O0 + n, c0 + n);
+  for (int n = tid; n < O1; n += 128) ntc_cp_async4(raw + O0 * I0 + O1 * O0 + O0 + n, c1 + n);
+  ntc_cp_async_commit();
   for (int idx = tid; idx < (S::total - S::o_b1) / 4; idx += 128) reinterpret_cast<uint32_t*>(smem + S::o_b1)[idx] = 0u;
   for (int idx = tid; idx < 1024; idx += 128)
     reinterpret_cast<uint32_t*>(smem + S::o_ones)[idx] = (idx < 512 && (idx & 3) == 0) ? 0x3F803F80u : 0u;
+  ntc_cp_async_wait_all();
   __syncthreads();
   for (int idx = tid; idx < O0 * I0; idx += 128) {
     const int n = idx / I0, k = idx - n * I0;
-    const float v = __ldg(V0 + idx);
+    const float v = raw[idx];
     ntc_put_bf16(smem + S::o_b1, O0P, k, n, v);
     ntc_put_bf16(smem + S::o_b4, I0P, n, k, v);
   }
   for (int idx = tid; idx < O1 * O0; idx += 128) {
     const int n = idx / O0, k = idx - n * O0;
-    const float v = __ldg(V1 + idx);
+    const float v = raw[O0 * I0 + idx];
     ntc_put_bf16(smem + S::o_b2, O1P, k, n, v);
     ntc_put_bf16(smem + S::o_b3, O0P, n, k, v);
   }
   for (int n = tid; n < O0; n += 128) {
-    const float b = __ldg(c0 + n), hi = __bfloat162float(__float2bfloat16_rn(b));
+    const float b = raw[O0 * I0 + O1 * O0 + n], hi = __bfloat162float(__float2bfloat16_rn(b));
     ntc_put_bf16(smem + S::o_b1, O0P, I0P, n, hi);
     ntc_put_bf16(smem + S::o_b1, O0P, I0P + 1, n, b - hi);
   }
   for (int n = tid; n < O1; n += 128) {
-    const float b = __ldg(c1 + n), hi = __bfloat162float(__float2bfloat16_rn(b));
+    const float b = raw[O0 * I0 + O1 * O0 + O0 + n], hi = __bfloat162float(__float2bfloat16_rn(b));
     ntc_put_bf16(smem + S::o_b2, O1P, O0P, n, hi);
     ntc_put_bf16(smem + S::o_b2, O1P, O0P + 1, n, b - hi);
   }
