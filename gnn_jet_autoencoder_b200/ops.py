@@ -61,7 +61,7 @@ def _step_launches(desc, backward: bool, saved: bool = False) -> int:
         return (4 + njb_extra) if tc2 else 3
     if not tc2:
         return 8
-    return 11 + njb_extra - (3 if saved else 0)
+    return 10 + njb_extra - (3 if saved else 0)
 
 
 def raw_mp_fwd(desc, h_ptr, params_ptr, hout_ptr, e_ptr, ws_ptr, ws_bytes, stream, saved_ptr=None):
