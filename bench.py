@@ -179,6 +179,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's version / debug lines must not land on stdout (one JSON line)
         dist.init_process_group("nccl", device_id=dev)
     N = args.num_nodes
     B = args.batch or (4096 if N <= 32 else 2048)
