@@ -44,6 +44,7 @@ SIGNATURES = {
     "gj_mp_step_fwd_workspace": (_SZ, [C.POINTER(MPDesc)]),
     "gj_mp_step_fwd": (C.c_int, [C.POINTER(MPDesc), _P, _P, _P, _P, _P, _SZ, _P]),
     "gj_mp_step_saved_bytes": (_SZ, [C.POINTER(MPDesc)]),
+    "gj_mp_step_launches": (C.c_int, [C.POINTER(MPDesc), C.c_int, C.c_int]),
     "gj_mp_step_fwd_saving": (C.c_int, [C.POINTER(MPDesc), _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "gj_mp_step_bwd_saved": (C.c_int, [C.POINTER(MPDesc), _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "gj_mp_step_bwd_workspace": (_SZ, [C.POINTER(MPDesc)]),

@@ -43,7 +43,8 @@ int gj_node_post_fwd(const MPLayout&, const float*, const float*, const float*, 
 size_t gj_node_post_bwd_ws_floats(const MPLayout&);
 bool gj_node_post_bwd_tc_supported(const MPLayout&);
 size_t gj_node_post_bwd_tc_ws_floats(const MPLayout&);
-int gj_node_post_bwd_tc(const MPLayout&, const float*, const float*, const float*, const float*, float*, float*, float*, int*, cudaStream_t);
+int gj_node_post_bwd_tc(const MPLayout&, const float*, const float*, const float*, const float*, float*, float*, float*, int*, float*, cudaStream_t);
+int gj_reduce_step_partials(const MPLayout&, const float*, int, const float*, int, const float*, int, float*, cudaStream_t);
 int gj_reduce_partials(const float*, int, int, float*, cudaStream_t);
 int gj_node_post_bwd(const MPLayout&, const float*, const float*, const float*, const float*, float*, float*, float*, float*,
                      cudaStream_t);
@@ -62,7 +63,7 @@ void gj_bwd2_plan(const MPLayout&, int*, int*);
 bool gj_bwd2_supported(const MPLayout&);
 size_t gj_bwd2_ws_floats(const MPLayout&);
 int gj_edge_bwd2(const MPLayout&, const float*, const float*, const float*, const float*, float*, float*, float*, float*, float*, float*, bool,
-                 cudaStream_t, bool);
+                 cudaStream_t, int, const float**, int*);
 size_t gj_edge_bwd_tc_ws_floats(const MPLayout&);
 int gj_edge_bwd_tc(MPLayout, const float*, const float*, const float*, const float*, float*, float*, float*, float*,
                    cudaStream_t);
@@ -94,13 +95,19 @@ size_t gj_mp_param_count(const gj_mp_desc* d) {
 static size_t align_floats(size_t n) { return (n + 63) & ~(size_t)63; }   // keep every region 256-byte aligned
 
 struct StepWs {   // offsets in floats
-  size_t pq, dpq, de, part, epart, wimg, dist, total;
+  size_t pq, dpq, de, part, part_post, part_pre, epart, wimg, dist, total;
 };
 
 static bool use_tc(const MPLayout& L, int precision) { return precision == GJ_PREC_BF16 && L.Le > 1; }
 // the step runs the second-generation fused kernels (forward and backward are covered by the same widths)
 static bool tc2_path(const MPLayout& L, int precision) {
   return use_tc(L, precision) && gj_fwd2_supported(L) && gj_bwd2_supported(L) && !gj_tc_v1_forced();
+}
+
+// backward of the bf16 step with both node-level adjoints on tcgen05: their partials and the edge kernel's are reduced together
+static bool node_tail_fused(const MPLayout& L, int precision) {
+  return tc2_path(L, precision) && gj_node_post_bwd_tc_supported(L) && gj_node_pre_bwd_tc_supported(L) && node_post_tc_enabled() &&
+         !node_tc_disabled();
 }
 
 static StepWs plan_ws(const MPLayout& L, int precision, bool backward) {
@@ -129,6 +136,13 @@ static StepWs plan_ws(const MPLayout& L, int precision, bool backward) {
     if (q > p) p = q;
     if (r > p) p = r;
     w.part = off; off += align_floats(p);
+    // the all-tensor-core backward keeps the node-MLP and projection partials next to the edge kernel's, so that one
+    // launch reduces all three at the end of the step
+    w.part_post = w.part_pre = w.part;
+    if (node_tail_fused(L, precision)) {
+      w.part_post = off; off += align_floats(gj_node_post_bwd_tc_ws_floats(L));
+      w.part_pre = off; off += align_floats(gj_node_pre_bwd_tc_ws_floats(L));
+    }
   }
   w.total = off;
   return w;
@@ -171,6 +185,19 @@ int gj_mp_step_fwd(const gj_mp_desc* d, const float* h, const float* params, flo
   return mp_step_fwd_impl(d, h, params, h_out, e_out, nullptr, workspace, workspace_bytes, stream, "gj_mp_step_fwd");
 }
 
+int gj_mp_step_launches(const gj_mp_desc* d, int backward, int with_saved) {
+  MPLayout L; const char* why;
+  if (gj_fill_arch(d, &L, &why)) return 0;
+  const bool tc2 = tc2_path(L, d->precision);
+  const int njb = (tc2 && L.N > 32) ? 1 : 0;      // per-j-block partial sums (forward: e, backward: dP)
+  if (!backward) return tc2 ? 4 + njb : 3;        // projections, [parameter image], edge kernel, [j-block sum], node MLP
+  if (!tc2) return 8;
+  // node MLP adjoint, [projections, parameter image, pair distances unless saved], edge kernel, [dP j-block sum],
+  // pair-distance adjoint, projections' adjoint, and one reduction (all-tensor-core tail) or three
+  const int reductions = node_tail_fused(L, d->precision) ? 1 : 3;
+  return 4 + reductions + njb + ((with_saved && tc2) ? 0 : 3);
+}
+
 size_t gj_mp_step_saved_bytes(const gj_mp_desc* d) {
   MPLayout L; const char* why;
   if (gj_fill_arch(d, &L, &why) || !tc2_path(L, d->precision)) return 0;
@@ -206,17 +233,28 @@ static int mp_step_bwd_impl(const gj_mp_desc* d, const float* h, const float* e,
   const bool tc2 = tc2_path(L, d->precision);
   if (saved && !tc2) { gj_set_error("%s: this step has nothing saved (gj_mp_step_saved_bytes is 0)", who); return GJ_ERR_INVALID; }
   float* pre = saved ? (float*)saved : ws;      // read-only when it is the caller's saved buffer
+  if (node_tail_fused(L, d->precision)) {
+    // node MLP adjoint (also clears dP|dQ), P|Q unless saved, edge adjoint, projections' adjoint, one reduction of all partials
+    int np_post = 0, np_pre = 0, np_edge = 0;
+    const float* part_edge = nullptr;
+    if ((rc = gj_node_post_bwd_tc(L, e, h, params, dh_out, ws + w.de, dh, ws + w.part_post, &np_post, ws + w.dpq, st))) return rc;
+    if (!saved && (rc = gj_node_pre_fwd(L, h, params, pre + w.pq, st))) return rc;
+    if ((rc = gj_edge_bwd2(L, h, pre + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.part, pre + w.wimg, pre + w.dist,
+                           saved != nullptr, st, 2, &part_edge, &np_edge))) return rc;
+    if ((rc = gj_node_pre_bwd_tc(L, h, params, ws + w.dpq, dh, ws + w.part_pre, &np_pre, st))) return rc;
+    return gj_reduce_step_partials(L, part_edge, np_edge, ws + w.part_pre, np_pre, ws + w.part_post, np_post, dparams, st);
+  }
   // node MLP adjoint: de, node-path dh, node parameter gradients
   if (tc2 && gj_node_post_bwd_tc_supported(L) && node_post_tc_enabled()) {      // bf16 mode: the node MLP adjoint on tcgen05
     int nparts = 0;
-    if ((rc = gj_node_post_bwd_tc(L, e, h, params, dh_out, ws + w.de, dh, ws + w.part, &nparts, st))) return rc;
+    if ((rc = gj_node_post_bwd_tc(L, e, h, params, dh_out, ws + w.de, dh, ws + w.part, &nparts, nullptr, st))) return rc;
     if ((rc = gj_reduce_partials(ws + w.part, nparts, L.nparams - L.pV[0], dparams + L.pV[0], st))) return rc;
   } else if ((rc = gj_node_post_bwd(L, e, h, params, dh_out, ws + w.de, dh, dparams, ws + w.part, st))) return rc;
   // P|Q (recomputed unless saved by the forward call), then the edge adjoint: dP|dQ, distance-path dh, edge parameter gradients
   if (!saved && (rc = gj_node_pre_fwd(L, h, params, pre + w.pq, st))) return rc;
   if (tc2)
     rc = gj_edge_bwd2(L, h, pre + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.part, pre + w.wimg, pre + w.dist, saved != nullptr,
-                      st, false);
+                      st, 0, nullptr, nullptr);
   else
     rc = use_tc(L, d->precision) ? gj_edge_bwd_tc(L, h, ws + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.part, st)
                                  : gj_edge_bwd_simt(L, h, ws + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.part, st);
@@ -320,7 +358,7 @@ int gj_bench_edge_bwd_only(const gj_mp_desc* d, const float* h, const float* par
   if (workspace_bytes < w.total * sizeof(float)) { gj_set_error("gj_bench_edge_bwd_only: workspace too small"); return GJ_ERR_WORKSPACE; }
   float* ws = (float*)workspace;
   return gj_edge_bwd2(L, h, ws + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.part, ws + w.wimg, ws + w.dist, true,
-                      (cudaStream_t)stream, true);
+                      (cudaStream_t)stream, 1, nullptr, nullptr);
 }
 
 int gj_mp_plan_info(const gj_mp_desc* d, int32_t* info) {

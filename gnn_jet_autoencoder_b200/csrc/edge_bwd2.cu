@@ -875,7 +875,11 @@ int gj_pair_dist_fwd(const MPLayout& L, const float* h, float* d, cudaStream_t s
 // wimg / d: packed parameter image and pair distances; with `have_saved` they were written by gj_edge_fwd2 of the same step
 // and are used as they are, otherwise they are (re)computed here
 int gj_edge_bwd2(const MPLayout& L, const float* h, const float* pq, const float* params, const float* de, float* dpq, float* dh,
-                 float* dparams, float* ws, float* wimg_f, float* d, bool have_saved, cudaStream_t stream, bool kernel_only) {
+                 float* dparams, float* ws, float* wimg_f, float* d, bool have_saved, cudaStream_t stream, int mode,
+                 const float** part_out, int* nparts_out) {
+  // mode 0: the whole edge adjoint; 1: the fused kernel alone (bench hook); 2: as 0, but dpq has already been zeroed by the
+  // caller and the per-CTA parameter-gradient partials are handed back (*part_out, *nparts_out) instead of being reduced
+  const bool kernel_only = mode == 1;
   constexpr int NWG = 3;
   using S = Bwd2Smem<32, 128, 64, 16, NWG>;
   static_assert(S::total <= 227 * 1024, "backward shared-memory plan exceeds the 227 KB budget");
@@ -908,7 +912,7 @@ int gj_edge_bwd2(const MPLayout& L, const float* h, const float* pq, const float
       int rc = gj_pair_dist_fwd(L, h, d, stream);
       if (rc) return rc;
     }
-    ce = cudaMemsetAsync(dpq, 0, rows * 2 * L.E[0] * sizeof(float), stream);
+    if (mode != 2) ce = cudaMemsetAsync(dpq, 0, rows * 2 * L.E[0] * sizeof(float), stream);
     if (ce != cudaSuccess) { gj_set_error("cudaMemsetAsync: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   }
   static const int trace_env = getenv("GJ_TRACE") ? atoi(getenv("GJ_TRACE")) : 0;
@@ -934,5 +938,6 @@ int gj_edge_bwd2(const MPLayout& L, const float* h, const float* pq, const float
   }
   ce = cudaGetLastError();
   if (ce != cudaSuccess) { gj_set_error("edge_bwd2 tail launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
+  if (mode == 2) { *part_out = part; *nparts_out = grid; return GJ_OK; }
   return gj_reduce_edge_partials(L, part, grid, dparams, stream);
 }

@@ -709,6 +709,35 @@ __global__ void reduce_pre_partials_kernel(const float* __restrict__ part, int n
   else db0[p - 2 * E0 * H] = acc;
 }
 
+// One launch for the three fixed-order partial reductions of a backward step (bf16 tensor-core path): blocks [0, nbE) the
+// edge-kernel partials (all edge parameters but the Wa | Wb columns of W0 and b0), [nbE, nbE + nbP) the projection-adjoint
+// partials (those columns and b0), the rest the node-MLP partials.  Same per-output summation order as the single kernels.
+__global__ void reduce_step_partials_kernel(const float* __restrict__ partE, int npE, int nE, int nbE, const float* __restrict__ partP,
+                                            int npP, int nbP, const float* __restrict__ partN, int npN, int nN, int E0, int H,
+                                            float* __restrict__ dedge, float* __restrict__ dW0, float* __restrict__ db0,
+                                            float* __restrict__ dnode) {
+  const int K0 = 2 * H + 1;
+  if ((int)blockIdx.x < nbE) {
+    const int p = blockIdx.x * 32 + threadIdx.x;
+    const int first = E0 * K0 + E0;          // W0 then b0: only the wd column (index 2H of each row) belongs to the edge kernel
+    const bool mine = p < nE && !(p < first && !(p < E0 * K0 && (p % K0) == K0 - 1));
+    const float acc = reduce_column(partE, npE, nE, mine ? p : nE);
+    if (threadIdx.y == 0 && mine) dedge[p] = acc;
+  } else if ((int)blockIdx.x < nbE + nbP) {
+    const int n = E0 * 2 * H + E0;
+    const int p = (blockIdx.x - nbE) * 32 + threadIdx.x;
+    const float acc = reduce_column(partP, npP, n, p);
+    if (threadIdx.y != 0 || p >= n) return;
+    if (p < E0 * H) { const int c = p / H, k = p - c * H; dW0[c * K0 + k] = acc; }
+    else if (p < 2 * E0 * H) { const int q = p - E0 * H; const int c = q / H, k = q - c * H; dW0[c * K0 + H + k] = acc; }
+    else db0[p - 2 * E0 * H] = acc;
+  } else {
+    const int p = (blockIdx.x - nbE - nbP) * 32 + threadIdx.x;
+    const float acc = reduce_column(partN, npN, nN, p);
+    if (threadIdx.y == 0 && p < nN) dnode[p] = acc;
+  }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------------
@@ -844,6 +873,17 @@ int gj_reduce_pre_partials(const MPLayout& L, const float* part, int nparts, flo
   const int n = L.E[0] * 2 * L.H + L.E[0];
   reduce_pre_partials_kernel<<<(n + 31) / 32, dim3(32, RED_SLICES), 0, st>>>(part, nparts, L.E[0], L.H, dparams + L.pW[0], dparams + L.pb[0]);
   NK_CHECK_LAUNCH("reduce_pre_partials launch");
+  return GJ_OK;
+}
+
+int gj_reduce_step_partials(const MPLayout& L, const float* partE, int npE, const float* partP, int npP, const float* partN, int npN,
+                            float* dparams, cudaStream_t st) {
+  const int nE = L.pV[0], nP = L.E[0] * 2 * L.H + L.E[0], nN = L.nparams - L.pV[0];
+  const int nbE = (nE + 31) / 32, nbP = (nP + 31) / 32, nbN = (nN + 31) / 32;
+  reduce_step_partials_kernel<<<nbE + nbP + nbN, dim3(32, RED_SLICES), 0, st>>>(partE, npE, nE, nbE, partP, npP, nbP, partN, npN, nN, L.E[0],
+                                                                              L.H, dparams, dparams + L.pW[0], dparams + L.pb[0],
+                                                                              dparams + L.pV[0]);
+  NK_CHECK_LAUNCH("reduce_step_partials launch");
   return GJ_OK;
 }
 

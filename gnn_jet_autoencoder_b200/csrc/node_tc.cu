@@ -297,7 +297,8 @@ __global__ void __launch_bounds__(128) node_post_bwd_tc_kernel(int rows, int col
                                                                const float* __restrict__ h, const float* __restrict__ V0,
                                                                const float* __restrict__ c0, const float* __restrict__ V1,
                                                                const float* __restrict__ c1, const float* __restrict__ dh_out,
-                                                               float* __restrict__ de, float* __restrict__ dh, float* __restrict__ part) {
+                                                               float* __restrict__ de, float* __restrict__ dh, float* __restrict__ part,
+                                                               float* __restrict__ zero64) {
   using S = PostBwdSmem<I0P, O0P, O1P>;
   constexpr int HS = S::XS - 2;      // h slabs of the X tile (the first two hold e)
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -372,6 +373,11 @@ __global__ void __launch_bounds__(128) node_post_bwd_tc_kernel(int rows, int col
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int row0 = tile * 128, row = row0 + tid;
     const bool live = row < rows;
+    if (zero64) {      // the dP|dQ accumulator of the edge adjoint that follows (64 floats per row) starts at zero
+      float4* z = reinterpret_cast<float4*>(zero64 + (size_t)row0 * 64);
+      const int n4 = min(128, rows - row0) * 16;
+      for (int idx = tid; idx < n4; idx += 128) z[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     // ---- global loads of the tile: e and h as (row, slab) entries (a warp instruction covers whole rows), dh' per row ----
     float ev[2][8], hv[HS][8];
 #pragma unroll
@@ -634,25 +640,26 @@ size_t gj_node_post_bwd_tc_ws_floats(const MPLayout& L) { return (size_t)post_bw
 
 template <int I0P, int O0P, int O1P>
 static cudaError_t post_bwd_tc_launch(const MPLayout& L, int grid, const float* e, const float* h, const float* params, const float* dh_out,
-                                      float* de, float* dh, float* part, cudaStream_t st) {
+                                      float* de, float* dh, float* part, float* zero64, cudaStream_t st) {
   using S = PostBwdSmem<I0P, O0P, O1P>;
   cudaError_t ce = cudaFuncSetAttribute(node_post_bwd_tc_kernel<I0P, O0P, O1P>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::total);
   if (ce != cudaSuccess) return ce;
   node_post_bwd_tc_kernel<I0P, O0P, O1P><<<grid, 128, S::total, st>>>(L.B * L.N, L.cols, L.ld, L.I[0], L.O[0], L.O[1], L.alpha,
                                                                       L.nparams - L.pV[0], e, h, params + L.pV[0], params + L.pc[0],
-                                                                      params + L.pV[1], params + L.pc[1], dh_out, de, dh, part);
+                                                                      params + L.pV[1], params + L.pc[1], dh_out, de, dh, part, zero64);
   return cudaGetLastError();
 }
 
-// launches the kernel; *nparts receives the number of per-CTA partials (packed [V0 | c0 | V1 | c1]) written to `part`
+// launches the kernel; *nparts receives the number of per-CTA partials (packed [V0 | c0 | V1 | c1]) written to `part`;
+// zero64 (optional): a (rows, 64) buffer the kernel clears on the way (the edge adjoint's dP|dQ accumulator)
 int gj_node_post_bwd_tc(const MPLayout& L, const float* e, const float* h, const float* params, const float* dh_out, float* de, float* dh,
-                        float* part, int* nparts, cudaStream_t st) {
+                        float* part, int* nparts, float* zero64, cudaStream_t st) {
   const int grid = post_bwd_tc_grid(L), shape = post_tc_shape(L);
   *nparts = grid;
-  cudaError_t ce = shape == 0 ? post_bwd_tc_launch<32, 16, 32>(L, grid, e, h, params, dh_out, de, dh, part, st)
-                 : shape == 1 ? post_bwd_tc_launch<48, 32, 16>(L, grid, e, h, params, dh_out, de, dh, part, st)
-                 : shape == 2 ? post_bwd_tc_launch<32, 16, 16>(L, grid, e, h, params, dh_out, de, dh, part, st)
-                 : shape == 3 ? post_bwd_tc_launch<48, 32, 32>(L, grid, e, h, params, dh_out, de, dh, part, st)
+  cudaError_t ce = shape == 0 ? post_bwd_tc_launch<32, 16, 32>(L, grid, e, h, params, dh_out, de, dh, part, zero64, st)
+                 : shape == 1 ? post_bwd_tc_launch<48, 32, 16>(L, grid, e, h, params, dh_out, de, dh, part, zero64, st)
+                 : shape == 2 ? post_bwd_tc_launch<32, 16, 16>(L, grid, e, h, params, dh_out, de, dh, part, zero64, st)
+                 : shape == 3 ? post_bwd_tc_launch<48, 32, 32>(L, grid, e, h, params, dh_out, de, dh, part, zero64, st)
                               : cudaErrorInvalidValue;
   if (ce != cudaSuccess) { gj_set_error("node_post_bwd_tc launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   return GJ_OK;

@@ -50,18 +50,9 @@ def metric_id(metric) -> int:
 # pointer-level calls
 # --------------------------------------------------------------------------------------------------
 def _step_launches(desc, backward: bool, saved: bool = False) -> int:
-    """Kernel launches of one gj_mp_step_fwd / gj_mp_step_bwd call (the bench's gpu_launches claim): node projections,
-    parameter packing, fused edge kernel (+ the j-block sum for N > 32), node MLP; backward: node MLP adjoint + reduce,
-    node projections, packing, pair distances, fused edge kernel (+ dP j-block sum), pair-distance adjoint, edge partial
-    reduce, projections' adjoint + reduce (projections, packing and pair distances are skipped when saved by forward)."""
-    lib = _lib.load()
-    tc2 = lib.gj_mp_step_saved_bytes(desc) > 0
-    njb_extra = 1 if (tc2 and desc.num_nodes > 32) else 0
-    if not backward:
-        return (4 + njb_extra) if tc2 else 3
-    if not tc2:
-        return 8
-    return 10 + njb_extra - (3 if saved else 0)
+    """Kernel launches of one gj_mp_step_fwd / gj_mp_step_bwd call (the bench's gpu_launches claim), as the library counts
+    them for this descriptor (gj_mp_step_launches)."""
+    return int(_lib.load().gj_mp_step_launches(desc, 1 if backward else 0, 1 if saved else 0))
 
 
 def raw_mp_fwd(desc, h_ptr, params_ptr, hout_ptr, e_ptr, ws_ptr, ws_bytes, stream, saved_ptr=None):

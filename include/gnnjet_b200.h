@@ -91,6 +91,9 @@ int gj_mp_step_fwd(const gj_mp_desc* d, const float* h, const float* params,
  * buffer, unmodified, to gj_mp_step_bwd_saved (same desc, h, params) skips their recomputation.  Results are identical to
  * gj_mp_step_fwd / gj_mp_step_bwd.  Both return GJ_ERR_INVALID where gj_mp_step_saved_bytes is 0. */
 size_t gj_mp_step_saved_bytes(const gj_mp_desc* d);
+/* Number of kernels one gj_mp_step_fwd (backward = 0) or gj_mp_step_bwd / _bwd_saved (backward = 1, with_saved = 0 / 1)
+ * call launches for this descriptor (memsets not counted); 0 for an invalid descriptor.  bench.py's gpu_launches adds these up. */
+int gj_mp_step_launches(const gj_mp_desc* d, int backward, int with_saved);
 int gj_mp_step_fwd_saving(const gj_mp_desc* d, const float* h, const float* params,
                           float* h_out, float* e_out, void* saved, void* workspace, size_t workspace_bytes, void* stream);
 int gj_mp_step_bwd_saved(const gj_mp_desc* d, const float* h, const float* e, const float* params,
