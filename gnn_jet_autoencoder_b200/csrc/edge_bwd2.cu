@@ -677,14 +677,19 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args 
 }
 
 // P-half of dpq from the per-j-block partials (N > 32), fixed order
-__global__ void sum_dp_parts_kernel(const float* __restrict__ part, int njb, size_t rows, int E0, float* __restrict__ dpq) {
-  const size_t n = rows * E0;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
-    float s = 0.f;
-    for (int b = 0; b < njb; ++b) s += part[(size_t)b * n + idx];
-    const size_t r = idx / E0, c = idx - r * E0;
-    dpq[r * 2 * E0 + c] = s;
+// dP_i = sum over the j blocks' partial dP (N > 32): one 16-byte column group per thread, the njb loads are independent
+__global__ void __launch_bounds__(256) sum_dp_parts_kernel(const float4* __restrict__ part, int njb, size_t rows, int E0,
+                                                           float* __restrict__ dpq) {
+  const size_t n4 = rows * (size_t)(E0 / 4), idx = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= n4) return;
+  float4 s = __ldg(part + idx);
+  for (int b = 1; b < njb; ++b) {
+    const float4 v = __ldg(part + (size_t)b * n4 + idx);
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
   }
+  const size_t r = idx / (size_t)(E0 / 4);
+  const int c4 = (int)(idx - r * (size_t)(E0 / 4));
+  *reinterpret_cast<float4*>(dpq + r * 2 * E0 + 4 * c4) = s;
 }
 
 // ---- pair distances (node level, O(N^2 H) per jet): d_ij = metric(h_j - h_i) and its adjoint ----
@@ -734,10 +739,11 @@ __global__ void __launch_bounds__(256) pair_dist_fwd_kernel(const float* __restr
   }
 }
 // dh[n][k] += 2 s_k sum_m S[n][m] (h[n][k] - h[m][k]),  S[n][m] = G[m][n] + G[n][m],  s_k = -1 for the minkowskian space
-// components.  One (jet, node) per thread with C4 float4 accumulators (S[n][m] is read once per m for all of them); h and G
-// of the CTA's JPB jets are staged in shared memory with 16-byte global loads.
+// components.  One (jet, node, group of C4 float4 columns) per thread (S[n][m] is read once per m for the C4 accumulators;
+// the host picks C4 and the block size so that the CTA's jets give every thread one item); h and G of the CTA's JPB jets are
+// staged in shared memory with asynchronous copies.
 template <int C4>
-__global__ void __launch_bounds__(256) pair_dist_bwd_kernel(const float* __restrict__ h, const float* __restrict__ G, int B, int N,
+__global__ void __launch_bounds__(640) pair_dist_bwd_kernel(const float* __restrict__ h, const float* __restrict__ G, int B, int N,
                                                             int NJ32, int cols, int ld, int mink, int JPB, float* __restrict__ dh) {
   extern __shared__ float4 pd_smem4[];
   float* pd_smem = reinterpret_cast<float*>(pd_smem4);
@@ -745,12 +751,13 @@ __global__ void __launch_bounds__(256) pair_dist_bwd_kernel(const float* __restr
   float* sh = pd_smem;                       // [JPB][N][hs]
   float* sG = pd_smem + JPB * N * hs;        // [JPB][N][gs]
   const bool vec = (ld & 3) == 0 && 4 * c4 <= ld;
+  const int nthr = blockDim.x, kgroups = (c4 + C4 - 1) / C4;
   for (int b0 = blockIdx.x * JPB; b0 < B; b0 += gridDim.x * JPB) {
     const int nj = min(JPB, B - b0), nr = nj * N;
     __syncthreads();
     if (vec) {
       const float4* src = reinterpret_cast<const float4*>(h + (size_t)b0 * N * ld);
-      for (int idx = threadIdx.x; idx < nr * c4; idx += 256) {
+      for (int idx = threadIdx.x; idx < nr * c4; idx += nthr) {
         const int r = idx / c4, k = idx - r * c4;
         if (4 * k + 3 < cols) { cp_async16(sh + r * hs + 4 * k, src + (size_t)r * ld4 + k); continue; }
         float4 v = __ldg(src + (size_t)r * ld4 + k);
@@ -760,14 +767,14 @@ __global__ void __launch_bounds__(256) pair_dist_bwd_kernel(const float* __restr
         *reinterpret_cast<float4*>(sh + r * hs + 4 * k) = v;
       }
     } else {
-      for (int idx = threadIdx.x; idx < nr * 4 * c4; idx += 256) {
+      for (int idx = threadIdx.x; idx < nr * 4 * c4; idx += nthr) {
         const int r = idx / (4 * c4), k = idx - r * (4 * c4);
         sh[r * hs + k] = k < cols ? __ldg(h + ((size_t)b0 * N + r) * ld + k) : 0.f;
       }
     }
     {
       const float4* src = reinterpret_cast<const float4*>(G + (size_t)b0 * N * NJ32);
-      for (int idx = threadIdx.x; idx < nr * nj4; idx += 256) {
+      for (int idx = threadIdx.x; idx < nr * nj4; idx += nthr) {
         const int r = idx / nj4, q = idx - r * nj4;
         const float* g4 = G + (size_t)b0 * N * NJ32 + 4 * (size_t)idx;
         float* dst = sG + r * gs + 4 * q;      // odd row stride: 4-byte asynchronous copies
@@ -778,12 +785,13 @@ __global__ void __launch_bounds__(256) pair_dist_bwd_kernel(const float* __restr
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
-    for (int r = threadIdx.x; r < nr; r += 256) {
+    for (int item = threadIdx.x; item < nr * kgroups; item += nthr) {
+      const int r = item / kgroups, k0 = (item - r * kgroups) * C4;
       const int jl = r / N, n = r - jl * N;
       const float* hj = sh + jl * N * hs;
       const float* Gj = sG + jl * N * gs;
       float* dst = dh + ((size_t)b0 * N + r) * ld;
-      for (int k0 = 0; k0 < c4; k0 += C4) {
+      {
         float4 hn[C4], acc[C4];
 #pragma unroll
         for (int u = 0; u < C4; ++u) {
@@ -924,17 +932,22 @@ int gj_edge_bwd2(const MPLayout& L, const float* h, const float* pq, const float
   if (ce != cudaSuccess) { gj_set_error("edge_bwd2 launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   if (kernel_only) return GJ_OK;
   if (njb > 1) {
-    int blocks = (int)((rows * L.E[0] + 255) / 256); if (blocks > 4 * gj_num_sms()) blocks = 4 * gj_num_sms();
-    sum_dp_parts_kernel<<<blocks, 256, 0, stream>>>(dp_part, (int)njb, rows, L.E[0], dpq);
+    const size_t n4 = rows * (size_t)(L.E[0] / 4);
+    sum_dp_parts_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(dp_part), (int)njb, rows, L.E[0], dpq);
   }
   {
     const int jpb = pd_jpb(L), smem = pd_smem_bwd(L);
     int blocks = (L.B + jpb - 1) / jpb; if (blocks > 8 * gj_num_sms()) blocks = 8 * gj_num_sms();
-    const int c4 = (L.cols + 3) >> 2;
-    auto pdk = c4 <= 1 ? pair_dist_bwd_kernel<1> : c4 <= 2 ? pair_dist_bwd_kernel<2> : c4 <= 4 ? pair_dist_bwd_kernel<4> : pair_dist_bwd_kernel<8>;
+    const int c4 = (L.cols + 3) >> 2, nr = (L.B < jpb ? L.B : jpb) * L.N;
+    // columns per thread: as many as still leave the CTA's rows at least ~450 work items
+    int C4 = c4 <= 1 ? 1 : c4 <= 2 ? 2 : c4 <= 4 ? 4 : 8;
+    while (C4 > 1 && nr * ((c4 + C4 - 1) / C4) < 448) C4 >>= 1;
+    int threads = (nr * ((c4 + C4 - 1) / C4) + 31) & ~31;
+    threads = threads < 128 ? 128 : (threads > 640 ? 640 : threads);
+    auto pdk = C4 == 1 ? pair_dist_bwd_kernel<1> : C4 == 2 ? pair_dist_bwd_kernel<2> : C4 == 4 ? pair_dist_bwd_kernel<4> : pair_dist_bwd_kernel<8>;
     ce = cudaFuncSetAttribute(pdk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (ce != cudaSuccess) { gj_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
-    pdk<<<blocks, 256, smem, stream>>>(h, G, L.B, L.N, NJ32, L.cols, L.ld, L.mink, jpb, dh);
+    pdk<<<blocks, threads, smem, stream>>>(h, G, L.B, L.N, NJ32, L.cols, L.ld, L.mink, jpb, dh);
   }
   ce = cudaGetLastError();
   if (ce != cudaSuccess) { gj_set_error("edge_bwd2 tail launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }

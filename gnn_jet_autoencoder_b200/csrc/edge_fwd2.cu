@@ -388,12 +388,16 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_fwd2_kernel(const Fwd2Args 
 }
 
 // sums the NJB per-j-block partial aggregates in a fixed order
-__global__ void sum_jblocks_kernel(const float* __restrict__ part, int njb, size_t n, float* __restrict__ out) {
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
-    float s = 0.f;
-    for (int b = 0; b < njb; ++b) s += part[(size_t)b * n + idx];
-    out[idx] = s;
+// e_i = sum over the j blocks' partial aggregates (N > 32): one 16-byte group per thread (n is a multiple of 4: E_last = 16)
+__global__ void __launch_bounds__(256) sum_jblocks_kernel(const float4* __restrict__ part, int njb, size_t n4, float4* __restrict__ out) {
+  const size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= n4) return;
+  float4 s = __ldg(part + idx);
+  for (int b = 1; b < njb; ++b) {
+    const float4 v = __ldg(part + b * n4 + idx);
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
   }
+  out[idx] = s;
 }
 
 }  // namespace
@@ -462,9 +466,9 @@ int gj_edge_fwd2(const MPLayout& L, const float* h, const float* pq, const float
   if (ce != cudaSuccess) { gj_set_error("edge_fwd2 launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   if (kernel_only) return GJ_OK;
   if (A.NJB > 1) {
-    const size_t n = (size_t)L.B * L.N * L.E[3];
-    int blocks = (int)((n + 255) / 256); if (blocks > 4 * gj_num_sms()) blocks = 4 * gj_num_sms();
-    sum_jblocks_kernel<<<blocks, 256, 0, stream>>>(ws, A.NJB, n, e_out);
+    const size_t n4 = (size_t)L.B * L.N * (L.E[3] / 4);
+    sum_jblocks_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(ws), A.NJB, n4,
+                                                                          reinterpret_cast<float4*>(e_out));
     ce = cudaGetLastError();
     if (ce != cudaSuccess) { gj_set_error("sum_jblocks launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   }

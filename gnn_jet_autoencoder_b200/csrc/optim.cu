@@ -162,45 +162,49 @@ __global__ void linear_dx_kernel(int rows, int K, int O, const float* __restrict
 // Same for K <= 32 (decoder input layer, local mix): w staged in shared memory, one warp per row, lanes split the O
 // outputs and keep K running sums each, combined by shuffles at the end of the row.
 constexpr int kDxRowsPerBlock = 8;       // one row per warp
-constexpr int kDxMaxO = 1024;            // a lane keeps its dy values of the row in registers
+constexpr int kDxOC = 512;               // outputs per staged weight chunk (a lane keeps its 16 dy values of the chunk in registers)
 template <bool VEC>
 __global__ void __launch_bounds__(256) linear_dx_smallk_kernel(int rows, int K, int O, const float* __restrict__ dy,
                                                                const float* __restrict__ w, float* __restrict__ dx) {
-  extern __shared__ float4 lin_smem4[];      // [O][K]
+  extern __shared__ float4 lin_smem4[];      // [kDxOC][K]
   float* lin_smem = reinterpret_cast<float*>(lin_smem4);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int r = blockIdx.x * kDxRowsPerBlock + warp;
-  float g[kDxMaxO / 32];
-#pragma unroll
-  for (int j = 0; j < kDxMaxO / 32; ++j) g[j] = (r < rows && lane + 32 * j < O) ? __ldg(dy + (size_t)r * O + lane + 32 * j) : 0.f;
-  for (int idx = threadIdx.x; idx < O * K; idx += 256)      // asynchronous copies: the loads do not wait for one another
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(lin_smem + idx)), "l"(w + idx) : "memory");
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
-  if (r >= rows) return;
   float acc[32];
 #pragma unroll
   for (int k = 0; k < 32; ++k) acc[k] = 0.f;
+  for (int o0 = 0; o0 < O; o0 += kDxOC) {
+    const int oc = min(kDxOC, O - o0);
+    float g[kDxOC / 32];
 #pragma unroll
-  for (int j = 0; j < kDxMaxO / 32; ++j) {
-    if (32 * j >= O) break;      // uniform
-    const int o = min(lane + 32 * j, O - 1);      // lanes past the end carry g = 0
-    const float* wo = lin_smem + o * K;
-    if (VEC) {      // K % 4 == 0: 16-byte reads (lanes are K floats apart: conflict free for K = 4 * odd)
+    for (int j = 0; j < kDxOC / 32; ++j) g[j] = (r < rows && lane + 32 * j < oc) ? __ldg(dy + (size_t)r * O + o0 + lane + 32 * j) : 0.f;
+    if (o0 > 0) __syncthreads();      // the previous chunk has been consumed
+    for (int idx = threadIdx.x; idx < oc * K; idx += 256)      // asynchronous copies: the loads do not wait for one another
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(lin_smem + idx)), "l"(w + (size_t)o0 * K + idx) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
 #pragma unroll
-      for (int q4 = 0; q4 < 8; ++q4) {
-        if (4 * q4 < K) {
-          const float4 v = *reinterpret_cast<const float4*>(wo + 4 * q4);
-          acc[4 * q4] = fmaf(g[j], v.x, acc[4 * q4]); acc[4 * q4 + 1] = fmaf(g[j], v.y, acc[4 * q4 + 1]);
-          acc[4 * q4 + 2] = fmaf(g[j], v.z, acc[4 * q4 + 2]); acc[4 * q4 + 3] = fmaf(g[j], v.w, acc[4 * q4 + 3]);
+    for (int j = 0; j < kDxOC / 32; ++j) {
+      if (32 * j >= oc) break;      // uniform
+      const int o = min(lane + 32 * j, oc - 1);      // lanes past the end carry g = 0
+      const float* wo = lin_smem + o * K;
+      if (VEC) {      // K % 4 == 0: 16-byte reads (lanes are K floats apart: conflict free for K = 4 * odd)
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4) {
+          if (4 * q4 < K) {
+            const float4 v = *reinterpret_cast<const float4*>(wo + 4 * q4);
+            acc[4 * q4] = fmaf(g[j], v.x, acc[4 * q4]); acc[4 * q4 + 1] = fmaf(g[j], v.y, acc[4 * q4 + 1]);
+            acc[4 * q4 + 2] = fmaf(g[j], v.z, acc[4 * q4 + 2]); acc[4 * q4 + 3] = fmaf(g[j], v.w, acc[4 * q4 + 3]);
+          }
         }
-      }
-    } else {
+      } else {
 #pragma unroll
-      for (int k = 0; k < 32; ++k) if (k < K) acc[k] = fmaf(g[j], wo[k], acc[k]);
+        for (int k = 0; k < 32; ++k) if (k < K) acc[k] = fmaf(g[j], wo[k], acc[k]);
+      }
     }
   }
+  if (r >= rows) return;
   float mine = 0.f;
 #pragma unroll
   for (int k = 0; k < 32; ++k) {
@@ -310,8 +314,8 @@ int gj_linear_bwd_launch(int rows, int K, int O, const float* x, const float* w,
   const int nch = rows > 0 ? lin_chunks(rows, K) : 0, chunk = lin_chunk_rows(K);
   if (rows > 0) {
     if (dx) {
-      const size_t smem = (size_t)O * K * sizeof(float);
-      if (K <= 32 && O <= kDxMaxO && smem <= 64 * 1024) {
+      const size_t smem = (size_t)(O < kDxOC ? O : kDxOC) * K * sizeof(float);
+      if (K <= 32) {
         auto kern = (K & 3) == 0 ? linear_dx_smallk_kernel<true> : linear_dx_smallk_kernel<false>;
         if (int rc = lin_set_smem((const void*)kern, smem, "linear_bwd")) return rc;
         kern<<<(rows + kDxRowsPerBlock - 1) / kDxRowsPerBlock, 256, smem, stream>>>(rows, K, O, dy, w, dx);
