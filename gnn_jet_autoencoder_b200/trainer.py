@@ -252,15 +252,20 @@ class GNNAETrainer:
                            self.ws.data_ptr(), self.ws_bytes, st, s["saved"].data_ptr() if s["saved"] is not None else None)
             h = s["out"]
 
-    def _loss_and_bwd(self, st):
-        lib, P, G = self.lib, self.flat.data_ptr(), self.grad.data_ptr()
-        B, N, L = self.B, self.N, self.layout
-        D = self.recon.shape[-1]
+    def _loss(self, st):
+        """Chamfer terms (+ d loss / d recon) and parameter norms of the resident batch -> self.stats."""
+        lib, B, N, D = self.lib, self.B, self.N, self.recon.shape[-1]
         _lib.check(lib.gj_chamfer_fwd_bwd(B, N, N, D, _norm_id(self.recon, self.norm_choice), self.wc, self.wj,
                                           self.recon.data_ptr(), self.x.data_ptr(), self.jet_terms.data_ptr(),
                                           self.stats.data_ptr(), self.dp.data_ptr(), st), "chamfer")
-        _lib.check(lib.gj_param_norms(P, self.flat.numel(), self.stats.data_ptr() + 12, self.ws.data_ptr(), self.ws_bytes, st), "norms")
+        _lib.check(lib.gj_param_norms(self.flat.data_ptr(), self.flat.numel(), self.stats.data_ptr() + 12, self.ws.data_ptr(),
+                                      self.ws_bytes, st), "norms")
         ops.LAUNCHES["count"] += 4
+
+    def _loss_and_bwd(self, st):
+        lib, P, G = self.lib, self.flat.data_ptr(), self.grad.data_ptr()
+        B, N, L = self.B, self.N, self.layout
+        self._loss(st)
         # decoder GraphNet, last step first
         g = self.dp
         for t in reversed(range(len(self.dec_steps))):
@@ -364,6 +369,63 @@ class GNNAETrainer:
         self.step_async(x)
         torch.cuda.current_stream().synchronize()
         return self.loss_from_stats(self.stats_host)
+
+    def run_epoch(self, loader, is_train: bool = True, collect: bool = True):
+        """The batch loop of reference utils/train.py:51-120 (``train`` / ``validate``) without its per-batch host
+        synchronisations: the reference reads ``batch_loss.cpu().item()`` (:77) and copies target / latent / reconstruction to
+        the host (:99-101) after every batch; here the per-batch loss terms stay in a device log, the outputs leave through
+        asynchronous copies into pinned host memory, and the stream is synchronised ONCE at the end of the epoch.
+
+        ``loader`` yields (B, N, F) batches (host, ideally pinned, or device) of exactly ``batch_size`` jets (use
+        ``drop_last=True``; the kernels run on fixed shapes).  ``is_train=False`` is the validation pass: forward and loss
+        only, parameters untouched.  Returns ``(epoch_avg_loss, recons_data, target_data, latent_data)`` like the reference:
+        the mean of the batch losses over the batches (train.py:108) and, with ``collect``, the concatenated host tensors
+        (else ``None``).  The host tensors are views of pinned epoch buffers the trainer keeps: they stay valid until the next
+        ``run_epoch`` call (clone them to keep several epochs)."""
+        st = torch.cuda.current_stream()
+        try:
+            nb = len(loader)
+        except TypeError:
+            loader = list(loader)
+            nb = len(loader)
+        if nb == 0:
+            raise ValueError("run_epoch: the loader yielded no batch")
+        # epoch-sized pinned host buffers (allocated once and kept: pinning memory synchronises the device) and device log
+        cache = getattr(self, "_epoch_buffers", None)
+        if cache is None or cache["nb"] < nb or (collect and cache["recon"] is None):
+            pin = lambda shape: torch.empty((nb,) + tuple(shape), dtype=torch.float32).pin_memory()
+            cache = {"nb": nb, "log": torch.zeros((nb, self.stats.numel()), device=self.dev, dtype=torch.float32),
+                     "recon": pin(self.recon.shape) if collect else None, "latent": pin(self.latent.shape) if collect else None,
+                     "target": pin(self.x.shape) if collect else None}
+            self._epoch_buffers = cache
+        i = 0
+        for x in loader:
+            if i >= nb:
+                raise ValueError("run_epoch: the loader yielded more batches than len(loader)")
+            if x.numel() != self.x.numel():
+                raise ValueError(f"run_epoch: batch of {tuple(x.shape)} does not match the trainer's fixed "
+                                 f"{tuple(self.x.shape)} (drop the last, ragged batch)")
+            self.load_batch(x)
+            if is_train:
+                self.compute_gradients()
+            else:
+                self._fwd(st.cuda_stream)
+                self._loss(st.cuda_stream)
+            cache["log"][i].copy_(self.stats, non_blocking=True)      # device -> device, stream ordered
+            if collect:
+                cache["recon"][i].copy_(self.recon, non_blocking=True)
+                cache["latent"][i].copy_(self.latent, non_blocking=True)
+                cache["target"][i].copy_(self.x, non_blocking=True)
+            if is_train:
+                self.apply_gradients()
+            i += 1
+        log = cache["log"][:i].cpu()                                  # the epoch's one synchronising read
+        st.synchronize()
+        avg = sum(self.loss_from_stats(row) for row in log) / i
+        if not collect:
+            return avg, None, None, None
+        flat = lambda t: t[:i].reshape((-1,) + tuple(t.shape[2:]))     # views of the epoch buffers (see the docstring)
+        return avg, flat(cache["recon"]), flat(cache["target"]), flat(cache["latent"])
 
     def flat_gradient(self) -> torch.Tensor:
         return self.grad

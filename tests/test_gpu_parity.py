@@ -215,6 +215,41 @@ def test_trainer_step_matches_oracle_adam():
         assert rel(v.cpu().numpy(), dp[k]) < 1e-5, k
 
 
+@pytest.mark.parametrize("graph", [False, True])
+def test_run_epoch_equals_the_per_batch_loop(graph):
+    """run_epoch (reference utils/train.py:51-120 without the per-batch host syncs) against step() batch by batch: same
+    batch losses, same parameters, same collected outputs; the validation pass leaves the parameters untouched."""
+    case = CASES["trainsh_n30"]
+    B = case["B"]
+    rng = np.random.default_rng(5)
+    batches = [torch.from_numpy(make_input(case) * (1.0 + 0.1 * i) + rng.normal(0, 1e-3, make_input(case).shape)).float().pin_memory()
+               for i in range(3)]
+    enc_a, dec_a, _, _ = build(case, "fp32")
+    enc_b, dec_b, _, _ = build(case, "fp32")
+    tr_a = GNNAETrainer(enc_a, dec_a, batch_size=B, lr=1e-3, use_cuda_graph=graph)
+    tr_b = GNNAETrainer(enc_b, dec_b, batch_size=B, lr=1e-3, use_cuda_graph=graph)
+    losses, lat, rec = [], [], []
+    for x in batches:
+        losses.append(tr_a.step(x))
+        lat.append(tr_a.latent.cpu().clone())
+        rec.append(tr_a.recon.cpu().clone())
+    avg, recons, targets, latents = tr_b.run_epoch(batches, is_train=True)
+    assert abs(avg - sum(losses) / 3) <= 1e-6 * abs(avg)
+    assert torch.equal(recons, torch.cat(rec)) and torch.equal(latents, torch.cat(lat))
+    assert torch.equal(targets, torch.cat([b.reshape(tr_b.x.shape) for b in batches]))
+    assert torch.equal(tr_a.flat, tr_b.flat)
+    # validation: forward + loss only
+    before = tr_b.flat.clone()
+    vavg, vrec, _, _ = tr_b.run_epoch([b.to(DEV) for b in batches], is_train=False)
+    assert torch.equal(tr_b.flat, before)
+    tr_a.forward_only(batches[0])
+    torch.cuda.synchronize()
+    assert torch.equal(vrec[:B], tr_a.recon.cpu())
+    assert np.isfinite(vavg) and vavg > 0
+    with pytest.raises(ValueError):
+        tr_b.run_epoch([batches[0][: B - 1]])
+
+
 # ---- loss kernel ----------------------------------------------------------------------------------------
 @pytest.mark.parametrize("B,Np,Nq,D,norm", [(5, 30, 30, 3, "cartesian"), (3, 7, 11, 4, "minkowskian"), (2, 150, 150, 3, "cartesian"),
                                              (4, 1, 1, 4, "polar"), (300, 30, 30, 3, "polar")])
