@@ -9,5 +9,6 @@ from . import _lib
 from .models import GraphNet, Encoder, Decoder
 from .losses import ChamferLoss
 from .trainer import GNNAETrainer, synthetic_jets
+from . import anomaly
 
-__all__ = ["GraphNet", "Encoder", "Decoder", "ChamferLoss", "GNNAETrainer", "synthetic_jets", "_lib"]
+__all__ = ["GraphNet", "Encoder", "Decoder", "ChamferLoss", "GNNAETrainer", "synthetic_jets", "anomaly", "_lib"]

@@ -70,6 +70,7 @@ int gj_edge_bwd_tc(MPLayout, const float*, const float*, const float*, const flo
 int gj_umma_selftest_launch(int, int, int, int, int, const float*, const float*, float*, cudaStream_t);
 void gj_tc_plan_info(MPLayout, int*);
 int gj_chamfer_launch(int, int, int, int, int, float, float, const float*, const float*, float*, float*, float*, cudaStream_t);
+int gj_pair_min_dist_launch(int, int, int, int, int, const float*, const float*, float*, float*, cudaStream_t);
 int gj_linear_fwd_launch(int, int, int, const float*, const float*, const float*, float*, cudaStream_t);
 size_t gj_linear_bwd_ws_bytes(int, int, int);
 int gj_linear_bwd_launch(int, int, int, const float*, const float*, const float*, float*, float*, float*, void*, size_t, cudaStream_t);
@@ -284,6 +285,13 @@ int gj_chamfer_fwd_bwd(int32_t batch, int32_t np_, int32_t nq, int32_t dim, int3
   g_err[0] = 0;
   if (!p || !q || !jet_terms || !terms) { gj_set_error("gj_chamfer_fwd_bwd: null pointer"); return GJ_ERR_INVALID; }
   return gj_chamfer_launch(batch, np_, nq, dim, norm, w_chamfer, w_jet, p, q, jet_terms, terms, dp, (cudaStream_t)stream);
+}
+
+int gj_pair_min_dist(int32_t batch, int32_t np_, int32_t nq, int32_t dim, int32_t lorentz, const float* p, const float* q,
+                     float* min_pq, float* min_qp, void* stream) {
+  g_err[0] = 0;
+  if (batch > 0 && (!p || !q || !min_pq || !min_qp)) { gj_set_error("gj_pair_min_dist: null pointer"); return GJ_ERR_INVALID; }
+  return gj_pair_min_dist_launch(batch, np_, nq, dim, lorentz, p, q, min_pq, min_qp, (cudaStream_t)stream);
 }
 
 int gj_linear_fwd(int32_t rows, int32_t in_f, int32_t out_f, const float* x, const float* w, const float* b, float* y,

@@ -96,9 +96,65 @@ __global__ void chamfer_reduce_kernel(int batch, float wc, float wj, const float
   }
 }
 
+// Per-particle nearest-neighbour distances of the anomaly scores (reference utils/jet_analysis/anomaly_detection.py:
+// chamfer :459-488 with the Euclidean norm, chamfer_lorentz :491-510 with E^2 - px^2 - py^2 - pz^2), one CTA per jet:
+// min_pq[b][i] = min_j dist(p_i, q_j), min_qp[b][j] = min_i dist(p_i, q_j).  No (B,N,N,D) difference tensor is built.
+__global__ void pair_min_dist_kernel(int np_, int nq, int dim, int lorentz, const float* __restrict__ p, const float* __restrict__ q,
+                                     float* __restrict__ min_pq, float* __restrict__ min_qp) {
+  extern __shared__ float sm[];
+  float* sp = sm;                       // [np][4]
+  float* sq = sp + np_ * 4;             // [nq][4]
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const float* pg = p + (size_t)b * np_ * dim;
+  const float* qg = q + (size_t)b * nq * dim;
+  for (int idx = tid; idx < np_ * 4; idx += blockDim.x) { int n = idx >> 2, c = idx & 3; sp[idx] = c < dim ? __ldg(pg + n * dim + c) : 0.f; }
+  for (int idx = tid; idx < nq * 4; idx += blockDim.x) { int n = idx >> 2, c = idx & 3; sq[idx] = c < dim ? __ldg(qg + n * dim + c) : 0.f; }
+  __syncthreads();
+  const float s1 = lorentz ? -1.f : 1.f;
+  for (int i = tid; i < np_; i += blockDim.x) {
+    const float4 a = *reinterpret_cast<const float4*>(sp + i * 4);
+    float best = INFINITY;
+    for (int j = 0; j < nq; ++j) {
+      const float4 c = *reinterpret_cast<const float4*>(sq + j * 4);
+      const float dx = a.x - c.x, dy = a.y - c.y, dz = a.z - c.z, dw = a.w - c.w;
+      best = fminf(best, dx * dx + s1 * (dy * dy + dz * dz + dw * dw));
+    }
+    min_pq[(size_t)b * np_ + i] = lorentz ? best : sqrtf(best);      // the minimum of the norms is the norm at the minimum square
+  }
+  for (int j = tid; j < nq; j += blockDim.x) {
+    const float4 c = *reinterpret_cast<const float4*>(sq + j * 4);
+    float best = INFINITY;
+    for (int i = 0; i < np_; ++i) {
+      const float4 a = *reinterpret_cast<const float4*>(sp + i * 4);
+      const float dx = a.x - c.x, dy = a.y - c.y, dz = a.z - c.z, dw = a.w - c.w;
+      best = fminf(best, dx * dx + s1 * (dy * dy + dz * dz + dw * dw));
+    }
+    min_qp[(size_t)b * nq + j] = lorentz ? best : sqrtf(best);
+  }
+}
+
 }  // namespace
 
 void gj_set_error(const char* fmt, ...);
+
+int gj_pair_min_dist_launch(int batch, int np_, int nq, int dim, int lorentz, const float* p, const float* q, float* min_pq,
+                            float* min_qp, cudaStream_t stream) {
+  if (batch < 0 || np_ < 1 || nq < 1 || (size_t)(np_ + nq) * 16 > 200 * 1024) {
+    gj_set_error("gj_pair_min_dist: particle counts out of range"); return GJ_ERR_INVALID; }
+  if (dim < 1 || dim > 4 || (lorentz && dim != 4)) { gj_set_error("gj_pair_min_dist: 1..4 components (4 for the Lorentz norm), got %d", dim); return GJ_ERR_INVALID; }
+  if (batch == 0) return GJ_OK;
+  const int nmax = np_ > nq ? np_ : nq;
+  int threads = gj_round_up(nmax, 32); if (threads > 256) threads = 256;
+  const size_t smem = (size_t)(np_ + nq) * 4 * sizeof(float);
+  cudaError_t ce = cudaSuccess;
+  if (smem > 48 * 1024) ce = cudaFuncSetAttribute(pair_min_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (ce == cudaSuccess) {
+    pair_min_dist_kernel<<<batch, threads, smem, stream>>>(np_, nq, dim, lorentz, p, q, min_pq, min_qp);
+    ce = cudaGetLastError();
+  }
+  if (ce != cudaSuccess) { gj_set_error("pair_min_dist launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
+  return GJ_OK;
+}
 
 int gj_chamfer_launch(int batch, int np_, int nq, int dim, int norm, float wc, float wj, const float* p, const float* q,
                       float* jet_terms, float* terms, float* dp, cudaStream_t stream) {

@@ -125,6 +125,14 @@ int gj_chamfer_fwd_bwd(int32_t batch, int32_t np_, int32_t nq, int32_t dim, int3
                        float w_chamfer, float w_jet, const float* p, const float* q,
                        float* jet_terms, float* terms, float* dp, void* stream);
 
+/* Per-particle nearest-neighbour distances of the anomaly scores (utils/jet_analysis/anomaly_detection.py: chamfer
+ * :459-488, chamfer_lorentz :491-510).  p (B,Np,D), q (B,Nq,D), D <= 4.
+ * lorentz == 0: min_pq[b][i] = min_j |p_i - q_j|_2, min_qp[b][j] = min_i |p_i - q_j|_2;
+ * lorentz == 1 (D == 4): the same minima of E^2 - px^2 - py^2 - pz^2 of the difference (no square root, may be negative).
+ * The reference's score is min_pq + min_qp (elementwise, Np == Nq). */
+int gj_pair_min_dist(int32_t batch, int32_t np_, int32_t nq, int32_t dim, int32_t lorentz, const float* p, const float* q,
+                     float* min_pq, float* min_qp, void* stream);
+
 /* Flat fused Adam (torch.optim.Adam defaults: no weight decay, no amsgrad) over n floats.
  * grad_scale multiplies the incoming gradient, l1_lambda*sign(p) and 2*l2_lambda*p are added to it
  * (utils/train.py:376-384).  step is the 1-based step count of this update. */

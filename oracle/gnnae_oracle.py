@@ -390,6 +390,18 @@ def chamfer_terms(p, q, norm_choice="cartesian"):
     return cham, jet, dp, djet
 
 
+def anomaly_chamfer(p, q, lorentz=False):
+    """Per-particle anomaly score of utils/jet_analysis/anomaly_detection.py: ``chamfer`` (:482-488: diffs = p[:, :, None] -
+    q[:, None, :], dist = L2 norm over the last axis, min over j plus min over i, added elementwise -> (B, N)) and, with
+    ``lorentz``, ``chamfer_lorentz`` (:505-510: dist = E^2 - px^2 - py^2 - pz^2 of the differences, :401-403)."""
+    diffs = p[:, :, None, :] - q[:, None, :, :]
+    if lorentz:
+        dist = diffs[..., 0] ** 2 - diffs[..., 1] ** 2 - diffs[..., 2] ** 2 - diffs[..., 3] ** 2
+    else:
+        dist = np.sqrt((diffs ** 2).sum(axis=-1))
+    return dist.min(axis=-1) + dist.min(axis=-2)
+
+
 def chamfer_loss(p, q, norm_choice="cartesian", jet_features_weight=1.0, mode="intended"):
     """mode='intended': chamfer + w*jet (what chamfer_loss.py:35-41 computes and then discards);
     mode='reference': the value the reference actually RETURNS, ``jet_loss`` alone

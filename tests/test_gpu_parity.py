@@ -250,6 +250,25 @@ def test_run_epoch_equals_the_per_batch_loop(graph):
         tr_b.run_epoch([batches[0][: B - 1]])
 
 
+# ---- anomaly-score distances -----------------------------------------------------------
+@pytest.mark.parametrize("B,N,D,lorentz", [(5, 30, 3, False), (3, 30, 4, False), (4, 30, 4, True), (2, 150, 4, True), (7, 1, 3, False),
+                                            (300, 30, 3, False)])
+def test_anomaly_chamfer_scores(B, N, D, lorentz):
+    from gnn_jet_autoencoder_b200 import anomaly
+    rng = np.random.default_rng(B * 7 + N)
+    p, q = rng.normal(size=(B, N, D)).astype(np.float32), rng.normal(size=(B, N, D)).astype(np.float32)
+    want = O.anomaly_chamfer(p.astype(np.float64), q.astype(np.float64), lorentz=lorentz)
+    fn = anomaly.chamfer_lorentz if lorentz else anomaly.chamfer
+    got = fn(torch.from_numpy(p).to(DEV), torch.from_numpy(q).to(DEV))
+    assert got.is_cuda and tuple(got.shape) == (B, N)
+    assert np.allclose(got.cpu().numpy(), want, rtol=2e-5, atol=2e-5)
+    got_b = fn(torch.from_numpy(p), torch.from_numpy(q), batch_size=2)          # batched form: host in, host out
+    assert not got_b.is_cuda and torch.equal(got_b, got.cpu())
+    assert torch.equal(anomaly.mse(torch.from_numpy(p), torch.from_numpy(q)), ((torch.from_numpy(p) - torch.from_numpy(q)) ** 2).sum(-1))
+    with pytest.raises(RuntimeError):
+        fn(torch.from_numpy(p).to(DEV), torch.from_numpy(q[:, : max(N - 1, 1)] if N > 1 else np.concatenate([q, q], 1)).to(DEV))
+
+
 # ---- loss kernel ----------------------------------------------------------------------------------------
 @pytest.mark.parametrize("B,Np,Nq,D,norm", [(5, 30, 30, 3, "cartesian"), (3, 7, 11, 4, "minkowskian"), (2, 150, 150, 3, "cartesian"),
                                              (4, 1, 1, 4, "polar"), (300, 30, 30, 3, "polar")])

@@ -149,3 +149,22 @@ def test_torch_port_matches_reference(name):
     dg = np.concatenate([tdp[k].grad.numpy().ravel() for k in sorted(dp)])
     tol = 1e-11 if case["store64"] else 2e-7
     assert rel(eg, g["enc_grad"]) < tol and rel(dg, g["dec_grad"]) < tol
+
+
+def test_anomaly_chamfer_against_a_torch_restatement():
+    """anomaly_detection.py:482-488 / :505-510 written out with torch (the module itself needs energyflow / jetnet /
+    matplotlib and is not importable here): the oracle's numpy form gives the same (B, N) scores."""
+    import torch
+    rng = np.random.default_rng(3)
+    p, q = rng.normal(size=(4, 9, 4)), rng.normal(size=(4, 9, 4))
+    pt, qt = torch.from_numpy(p), torch.from_numpy(q)
+    diffs = torch.unsqueeze(pt, -2) - torch.unsqueeze(qt, -3)
+    dist = torch.norm(diffs, dim=-1)
+    want = torch.min(dist, dim=-1).values + torch.min(dist, dim=-2).values
+    assert np.allclose(O.anomaly_chamfer(p, q), want.numpy(), rtol=1e-12, atol=0)
+    E, px, py, pz = diffs.unbind(-1)
+    dl = E ** 2 - px ** 2 - py ** 2 - pz ** 2
+    want_l = torch.min(dl, dim=-1).values + torch.min(dl, dim=-2).values
+    assert np.allclose(O.anomaly_chamfer(p, q, lorentz=True), want_l.numpy(), rtol=1e-12, atol=0)
+    assert O.anomaly_chamfer(p[..., :3], q[..., :3]).shape == (4, 9)
+
