@@ -10,5 +10,6 @@ from .models import GraphNet, Encoder, Decoder
 from .losses import ChamferLoss
 from .trainer import GNNAETrainer, synthetic_jets
 from . import anomaly
+from .permutation import PermutationTest
 
-__all__ = ["GraphNet", "Encoder", "Decoder", "ChamferLoss", "GNNAETrainer", "synthetic_jets", "anomaly", "_lib"]
+__all__ = ["GraphNet", "Encoder", "Decoder", "ChamferLoss", "GNNAETrainer", "synthetic_jets", "anomaly", "PermutationTest", "_lib"]

@@ -175,3 +175,20 @@ def test_sass_uses_tcgen05_and_tmem():
     sass = subprocess.run([exe, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "UTCHMMA" in sass or "UTCMMA" in sass
     assert "LDTM" in sass
+
+
+def test_permutation_helpers_match_the_per_jet_loops():
+    """apply_perm / particle_perm_rand (reference utils/permutation.py:112-133) as batched ops: same result as indexing jet by
+    jet; every row of perm is a permutation."""
+    import torch
+    from gnn_jet_autoencoder_b200.permutation import apply_perm, dev, get_dev_summary, particle_perm_rand
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(6, 9, 3, generator=g)
+    xp, perm = particle_perm_rand(x, generator=g)
+    assert tuple(perm.shape) == (6, 9) and all(sorted(row.tolist()) == list(range(9)) for row in perm)
+    assert torch.equal(xp, torch.stack([x[i, p] for i, p in enumerate(perm)]))
+    assert torch.equal(apply_perm(perm, x), xp)
+    d = dev(output=xp, target=xp + 1.0)
+    s = get_dev_summary(d, perm, verbose=True)
+    assert set(s) == {"mean", "median", "max", "min", "std", "values", "perm"} and s["max"] >= s["median"] >= s["min"] >= 0
+

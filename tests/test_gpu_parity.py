@@ -250,6 +250,25 @@ def test_run_epoch_equals_the_per_batch_loop(graph):
         tr_b.run_epoch([batches[0][: B - 1]])
 
 
+# ---- permutation test harness ----------------------------------------------------------
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_permutation_test_on_the_cuda_modules(precision):
+    """The GNNAE with the 'mean' latent map is permutation invariant (the decoder sees a permutation-invariant latent), so
+    NN(P(x)) = NN(x) up to the summation order over j; the harness of utils/permutation.py reports it."""
+    from gnn_jet_autoencoder_b200 import PermutationTest
+    case = CASES["default_n30"]
+    enc, dec, _, _ = build(case, precision)
+    x = torch.from_numpy(make_input(case)).float()
+    out = PermutationTest(enc, dec)(x)
+    assert set(out) == {"invariance", "equivariance"}
+    tol = 1e-4 if precision == "fp32" else 5e-2
+    assert out["invariance"]["median"] < tol
+    loader = torch.utils.data.DataLoader(x, batch_size=max(1, x.shape[0] // 2))
+    out2 = PermutationTest(enc, dec, device=DEV, dtype=torch.float32)(loader, verbose=True)
+    assert out2["invariance"]["values"].shape == (x.shape[0], case["enc"]["num_nodes"], 3)
+    assert out2["invariance"]["median"] < tol
+
+
 # ---- anomaly-score distances (SURVEY 8.f rank 2) -----------------------------------------------------------
 @pytest.mark.parametrize("B,N,D,lorentz", [(5, 30, 3, False), (3, 30, 4, False), (4, 30, 4, True), (2, 150, 4, True), (7, 1, 3, False),
                                             (300, 30, 3, False)])
