@@ -7,9 +7,9 @@ of ``libgnnjet_b200.so`` (C-ABI: include/gnnjet_b200.h); there is no CPU or eage
 """
 from . import _lib
 from .models import GraphNet, Encoder, Decoder
-from .losses import ChamferLoss
+from .losses import ChamferLoss, HungarianMSELoss
 from .trainer import GNNAETrainer, synthetic_jets
 from . import anomaly
 from .permutation import PermutationTest
 
-__all__ = ["GraphNet", "Encoder", "Decoder", "ChamferLoss", "GNNAETrainer", "synthetic_jets", "anomaly", "PermutationTest", "_lib"]
+__all__ = ["GraphNet", "Encoder", "Decoder", "ChamferLoss", "HungarianMSELoss", "GNNAETrainer", "synthetic_jets", "anomaly", "PermutationTest", "_lib"]

@@ -51,6 +51,7 @@ SIGNATURES = {
     "gj_mp_step_bwd": (C.c_int, [C.POINTER(MPDesc), _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "gj_chamfer_fwd_bwd": (C.c_int, [_I, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P]),
     "gj_pair_min_dist": (C.c_int, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _P]),
+    "gj_assignment": (C.c_int, [_I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "gj_adam_step_flat": (C.c_int, [_P, _P, _P, _P, _SZ, _F, _F, _F, _F, _I, _F, _F, _F, _P]),
     "gj_param_norms": (C.c_int, [_P, _SZ, _P, _P, _SZ, _P]),
     "gj_param_norms_workspace": (_SZ, [_SZ]),

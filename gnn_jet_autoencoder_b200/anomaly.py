@@ -60,3 +60,41 @@ def chamfer(p: torch.Tensor, q: torch.Tensor, batch_size: int = -1) -> torch.Ten
 def chamfer_lorentz(p: torch.Tensor, q: torch.Tensor, batch_size: int = -1) -> torch.Tensor:
     """anomaly_detection.py:491-510: the same with the Lorentz norm squared E^2 - px^2 - py^2 - pz^2 of the differences."""
     return _batched(lambda a, b: _pair_min(a, b, True), p, q, batch_size)
+
+
+def assignment(p: torch.Tensor, q: torch.Tensor, lorentz: bool = False):
+    """Optimal particle matching per jet on the device: (col_for_row (B, N) int64, total_cost (B,)) with
+    col_for_row[b] == scipy.optimize.linear_sum_assignment(cost[b])[1] for cost = cdist(p, q) (or the Lorentz norm squared of
+    the differences) -- the matching step of anomaly_detection.py:537-541 / :579-585 and hungarian_mse.py:51-52."""
+    if p.dim() != 3 or p.shape != q.shape:
+        raise ValueError(f"expected two (B, N, D) tensors of equal shape, got {tuple(p.shape)} and {tuple(q.shape)}")
+    if lorentz and p.shape[2] != 4:
+        raise ValueError("the Lorentz norm needs 4-vectors (E, px, py, pz)")
+    dev = p.device if p.is_cuda else _device()
+    pc = p.detach().to(device=dev, dtype=torch.float32).contiguous()
+    qc = q.detach().to(device=dev, dtype=torch.float32).contiguous()
+    B, N, D = pc.shape
+    match = torch.empty((B, N), device=dev, dtype=torch.int32)
+    total = torch.empty((B,), device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().gj_assignment(B, N, D, 1 if lorentz else 0, pc.data_ptr(), qc.data_ptr(), match.data_ptr(),
+                                             total.data_ptr(), torch.cuda.current_stream().cuda_stream), "gj_assignment")
+    return match.long(), total
+
+
+def _hungarian(p: torch.Tensor, q: torch.Tensor, lorentz: bool) -> torch.Tensor:
+    match, _ = assignment(p, q, lorentz)
+    pd = p.to(match.device)
+    # anomaly_detection.py:543-546: p_shuffle[b] = p[b, matching[b]], then the particle-wise squared error against q
+    p_shuffle = torch.gather(pd, 1, match.unsqueeze(-1).expand(-1, -1, pd.shape[-1]))
+    return mse(p_shuffle, q.to(match.device))
+
+
+def hungarian(p: torch.Tensor, q: torch.Tensor, batch_size: int = -1) -> torch.Tensor:
+    """anomaly_detection.py:513-547: (B, N) squared errors after the optimal (Euclidean-cost) matching of the particles."""
+    return _batched(lambda a, b: _hungarian(a, b, False), p, q, batch_size)
+
+
+def hungarian_lorentz(p: torch.Tensor, q: torch.Tensor, batch_size: int = -1) -> torch.Tensor:
+    """anomaly_detection.py:550-590: the same with the Lorentz norm squared of the differences as the matching cost."""
+    return _batched(lambda a, b: _hungarian(a, b, True), p, q, batch_size)

@@ -71,6 +71,7 @@ int gj_umma_selftest_launch(int, int, int, int, int, const float*, const float*,
 void gj_tc_plan_info(MPLayout, int*);
 int gj_chamfer_launch(int, int, int, int, int, float, float, const float*, const float*, float*, float*, float*, cudaStream_t);
 int gj_pair_min_dist_launch(int, int, int, int, int, const float*, const float*, float*, float*, cudaStream_t);
+int gj_assignment_launch(int, int, int, int, const float*, const float*, int*, float*, cudaStream_t);
 int gj_linear_fwd_launch(int, int, int, const float*, const float*, const float*, float*, cudaStream_t);
 size_t gj_linear_bwd_ws_bytes(int, int, int);
 int gj_linear_bwd_launch(int, int, int, const float*, const float*, const float*, float*, float*, float*, void*, size_t, cudaStream_t);
@@ -292,6 +293,13 @@ int gj_pair_min_dist(int32_t batch, int32_t np_, int32_t nq, int32_t dim, int32_
   g_err[0] = 0;
   if (batch > 0 && (!p || !q || !min_pq || !min_qp)) { gj_set_error("gj_pair_min_dist: null pointer"); return GJ_ERR_INVALID; }
   return gj_pair_min_dist_launch(batch, np_, nq, dim, lorentz, p, q, min_pq, min_qp, (cudaStream_t)stream);
+}
+
+int gj_assignment(int32_t batch, int32_t n, int32_t dim, int32_t lorentz, const float* p, const float* q, int32_t* col_for_row,
+                  float* total_cost, void* stream) {
+  g_err[0] = 0;
+  if (batch > 0 && (!p || !q || !col_for_row)) { gj_set_error("gj_assignment: null pointer"); return GJ_ERR_INVALID; }
+  return gj_assignment_launch(batch, n, dim, lorentz, p, q, col_for_row, total_cost, (cudaStream_t)stream);
 }
 
 int gj_linear_fwd(int32_t rows, int32_t in_f, int32_t out_f, const float* x, const float* w, const float* b, float* y,

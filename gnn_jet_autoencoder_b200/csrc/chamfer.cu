@@ -133,9 +133,126 @@ __global__ void pair_min_dist_kernel(int np_, int nq, int dim, int lorentz, cons
   }
 }
 
+// Optimal assignment between the particles of p and q per jet (the matching step of reference
+// utils/jet_analysis/anomaly_detection.py: hungarian :513-547, hungarian_lorentz :550-590, and of
+// utils/losses/hungarian_mse/hungarian_mse.py:51-56, which call scipy.optimize.linear_sum_assignment jet by jet on the
+// host).  One CTA per jet, thread j owns column j: the O(n^3) shortest-augmenting-path Hungarian method with row / column
+// potentials (u, v), where the scan over the columns of every path step -- relax, arg-min, potential update -- runs across
+// the threads.  Costs are fp32 (|p_i - q_j|_2 or the Lorentz norm squared), potentials and slacks fp64.
+// col_for_row[b][i] = column assigned to row i (linear_sum_assignment's second array for a square matrix).
+__global__ void assignment_kernel(int n, int dim, int lorentz, const float* __restrict__ p, const float* __restrict__ q,
+                                  int* __restrict__ col_for_row, float* __restrict__ total_cost) {
+  extern __shared__ float4 asg_smem[];
+  float* sp = reinterpret_cast<float*>(asg_smem);             // [n][4]
+  float* sq = sp + n * 4;                                     // [n][4]
+  double* u = reinterpret_cast<double*>(sq + n * 4);          // [n + 1] row potentials (1-based, 0 = none)
+  double* red_v = u + (n + 1);                                // [32] per-warp minima
+  int* red_j = reinterpret_cast<int*>(red_v + 32);            // [32]
+  int* prow = red_j + 32;                                     // [n + 1] row matched to column j (0 = free)
+  int* way = prow + (n + 1);                                  // [n + 1]
+  int* ctl = way + (n + 1);                                   // [2]: current column j0, spare
+  float* cost = reinterpret_cast<float*>(ctl + 2);            // [n][n]
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const float* pg = p + (size_t)b * n * dim;
+  const float* qg = q + (size_t)b * n * dim;
+  for (int idx = tid; idx < n * 4; idx += blockDim.x) {
+    const int r = idx >> 2, c = idx & 3;
+    sp[idx] = c < dim ? __ldg(pg + r * dim + c) : 0.f;
+    sq[idx] = c < dim ? __ldg(qg + r * dim + c) : 0.f;
+  }
+  for (int idx = tid; idx <= n; idx += blockDim.x) { u[idx] = 0.0; prow[idx] = 0; way[idx] = 0; }
+  __syncthreads();
+  const float s1 = lorentz ? -1.f : 1.f;
+  for (int idx = tid; idx < n * n; idx += blockDim.x) {
+    const int i = idx / n, j = idx - i * n;
+    const float4 a = *reinterpret_cast<const float4*>(sp + i * 4), c = *reinterpret_cast<const float4*>(sq + j * 4);
+    const float dx = a.x - c.x, dy = a.y - c.y, dz = a.z - c.z, dw = a.w - c.w;
+    const float d2 = dx * dx + s1 * (dy * dy + dz * dz + dw * dw);
+    cost[idx] = lorentz ? d2 : sqrtf(d2);
+  }
+  __syncthreads();
+  const int j = tid + 1;                 // this thread's column (1-based); threads beyond n idle along
+  const bool has_col = j <= n;
+  double v = 0.0, minv = 0.0;
+  bool used = false;
+  for (int i = 1; i <= n; ++i) {
+    if (tid == 0) { prow[0] = i; ctl[0] = 0; }
+    minv = INFINITY; used = false;
+    __syncthreads();
+    while (true) {
+      const int j0 = ctl[0], i0 = prow[j0];
+      if (has_col && j == j0) used = true;
+      double cand = INFINITY;
+      if (has_col && !used) {
+        const double cur = (double)cost[(size_t)(i0 - 1) * n + (j - 1)] - u[i0] - v;
+        if (cur < minv) { minv = cur; way[j] = j0; }
+        cand = minv;
+      }
+      // block arg-min of cand (ties: smallest column)
+      int cj = has_col && !used ? j : 0x7fffffff;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, cand, d);
+        const int oj = __shfl_xor_sync(0xffffffffu, cj, d);
+        if (ov < cand || (ov == cand && oj < cj)) { cand = ov; cj = oj; }
+      }
+      if (lane == 0) { red_v[warp] = cand; red_j[warp] = cj; }
+      __syncthreads();
+      double delta = red_v[0]; int j1 = red_j[0];
+      for (int w = 1; w < nwarps; ++w) {
+        const double ov = red_v[w]; const int oj = red_j[w];
+        if (ov < delta || (ov == delta && oj < j1)) { delta = ov; j1 = oj; }
+      }
+      // potentials: matched (used) columns move with their rows, free columns get closer by delta
+      if (has_col) {
+        if (used) { u[prow[j]] += delta; v -= delta; }
+        else minv -= delta;
+      }
+      if (tid == 0) { u[prow[0]] += delta; ctl[0] = j1; }
+      __syncthreads();
+      if (prow[j1] == 0) break;
+    }
+    if (tid == 0) {      // augment along the recorded path
+      int j0 = ctl[0];
+      do { const int jn = way[j0]; prow[j0] = prow[jn]; j0 = jn; } while (j0);
+    }
+    __syncthreads();
+  }
+  if (has_col) col_for_row[(size_t)b * n + (prow[j] - 1)] = j - 1;
+  if (total_cost) {
+    float c = has_col ? cost[(size_t)(prow[j] - 1) * n + (j - 1)] : 0.f;
+    c = gj_warp_sum(c);
+    __syncthreads();
+    if (lane == 0) red_v[warp] = (double)c;
+    __syncthreads();
+    if (tid == 0) { double t = 0.0; for (int w = 0; w < nwarps; ++w) t += red_v[w]; total_cost[b] = (float)t; }
+  }
+}
+
 }  // namespace
 
 void gj_set_error(const char* fmt, ...);
+
+static size_t assignment_smem(int n) {
+  return (size_t)(n + 1 + 32) * sizeof(double) + (size_t)(32 + 2 * (n + 1) + 2) * sizeof(int) + ((size_t)n * n + 8 * (size_t)n) * sizeof(float) + 16;
+}
+
+int gj_assignment_launch(int batch, int n, int dim, int lorentz, const float* p, const float* q, int* col_for_row, float* total_cost,
+                         cudaStream_t stream) {
+  if (batch < 0 || n < 1 || n > 1024 || assignment_smem(n) > 200 * 1024) {
+    gj_set_error("gj_assignment: 1 <= particles per jet <= 220 (cost matrix in shared memory), got %d", n); return GJ_ERR_INVALID; }
+  if (dim < 1 || dim > 4 || (lorentz && dim != 4)) { gj_set_error("gj_assignment: 1..4 components (4 for the Lorentz norm), got %d", dim); return GJ_ERR_INVALID; }
+  if (batch == 0) return GJ_OK;
+  const size_t smem = assignment_smem(n);
+  cudaError_t ce = cudaSuccess;
+  if (smem > 48 * 1024) ce = cudaFuncSetAttribute(assignment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (ce == cudaSuccess) {
+    assignment_kernel<<<batch, gj_round_up(n, 32), smem, stream>>>(n, dim, lorentz, p, q, col_for_row, total_cost);
+    ce = cudaGetLastError();
+  }
+  if (ce != cudaSuccess) { gj_set_error("assignment launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
+  return GJ_OK;
+}
 
 int gj_pair_min_dist_launch(int batch, int np_, int nq, int dim, int lorentz, const float* p, const float* q, float* min_pq,
                             float* min_qp, cudaStream_t stream) {

@@ -45,3 +45,25 @@ class ChamferLoss(nn.Module):
         loss, terms = ops.chamfer_loss(p.float(), q.float(), _norm_id(p, self.loss_norm_choice), wc, wj)
         self.last_terms = terms
         return loss if p.dtype == torch.float32 else loss.to(p.dtype)
+
+
+class HungarianMSELoss(nn.Module):
+    """Permutation-invariant MSE of reference utils/losses/hungarian_mse/hungarian_mse.py (:6-58) with the matching solved on
+    the device for the whole batch (`gj_assignment`) instead of `scipy.optimize.linear_sum_assignment` jet by jet on the host
+    (:51-52): cost = cdist(recons, target), recons_shuffle[b] = recons[b, matching[b]], loss = MSELoss(recons_shuffle, target).
+    The gradient reaches `recons` through the gather, as in the reference.  Absolute Cartesian coordinates (the defaults
+    ``abs_coord=True, polar_coord=False``); the other coordinate options are preprocessing helpers outside this package."""
+
+    def forward(self, recons: torch.Tensor, target: torch.Tensor, abs_coord: bool = True, polar_coord: bool = False):
+        for t in (target, recons):
+            if t.shape[-1] not in (3, 4):
+                raise ValueError(f"Wrong last dimension of p. Should be 3 or 4 but found: {t.shape[-1]}.")
+        if not abs_coord or polar_coord:
+            raise NotImplementedError("HungarianMSELoss: only absolute Cartesian coordinates (abs_coord=True, polar_coord=False)")
+        from .anomaly import assignment
+        self.device = recons.device
+        target = target.to(recons.device)
+        match, _ = assignment(recons, target)
+        match = match.to(recons.device)
+        recons_shuffle = torch.gather(recons, 1, match.unsqueeze(-1).expand(-1, -1, recons.shape[-1]))
+        return nn.functional.mse_loss(recons_shuffle, target)

@@ -133,6 +133,15 @@ int gj_chamfer_fwd_bwd(int32_t batch, int32_t np_, int32_t nq, int32_t dim, int3
 int gj_pair_min_dist(int32_t batch, int32_t np_, int32_t nq, int32_t dim, int32_t lorentz, const float* p, const float* q,
                      float* min_pq, float* min_qp, void* stream);
 
+/* Optimal assignment (minimum total cost perfect matching) between the N particles of p and of q, per jet: the matching of
+ * utils/jet_analysis/anomaly_detection.py hungarian :513-547 / hungarian_lorentz :550-590 and of
+ * utils/losses/hungarian_mse/hungarian_mse.py:51-56, which call scipy.optimize.linear_sum_assignment jet by jet on the host.
+ * cost(i, j) = |p_i - q_j|_2 (lorentz == 0) or E^2 - px^2 - py^2 - pz^2 of p_i - q_j (lorentz == 1, D == 4).
+ * col_for_row (B,N) int32: column (particle of q) assigned to row i (particle of p) -- linear_sum_assignment(cost)[1];
+ * total_cost (B), may be NULL: the assignment's cost.  N <= 220 (the cost matrix lives in shared memory). */
+int gj_assignment(int32_t batch, int32_t n, int32_t dim, int32_t lorentz, const float* p, const float* q,
+                  int32_t* col_for_row, float* total_cost, void* stream);
+
 /* Flat fused Adam (torch.optim.Adam defaults: no weight decay, no amsgrad) over n floats.
  * grad_scale multiplies the incoming gradient, l1_lambda*sign(p) and 2*l2_lambda*p are added to it
  * (utils/train.py:376-384).  step is the 1-based step count of this update. */

@@ -402,6 +402,24 @@ def anomaly_chamfer(p, q, lorentz=False):
     return dist.min(axis=-1) + dist.min(axis=-2)
 
 
+def anomaly_hungarian(p, q, lorentz=False):
+    """utils/jet_analysis/anomaly_detection.py hungarian (:537-547) / hungarian_lorentz (:579-590): per jet, cost = |p_i -
+    q_j|_2 (torch.cdist) or the Lorentz norm squared of p_i - q_j; matching = scipy.optimize.linear_sum_assignment(cost)[1]
+    (the reference's own solver); p_shuffle = p[matching]; score = sum over components of (p_shuffle - q)^2 -> (B, N).
+    Returns (scores, matching (B, N), total assignment cost (B,))."""
+    from scipy import optimize
+    diffs = p[:, :, None, :] - q[:, None, :, :]
+    if lorentz:
+        cost = diffs[..., 0] ** 2 - diffs[..., 1] ** 2 - diffs[..., 2] ** 2 - diffs[..., 3] ** 2
+    else:
+        cost = np.sqrt((diffs ** 2).sum(axis=-1))
+    matching = np.stack([optimize.linear_sum_assignment(c)[1] for c in cost])
+    bi = np.arange(p.shape[0])[:, None]
+    p_shuffle = p[bi, matching]
+    total = cost[bi, np.arange(p.shape[1])[None, :], matching].sum(axis=1)
+    return ((p_shuffle - q) ** 2).sum(axis=-1), matching, total
+
+
 def chamfer_loss(p, q, norm_choice="cartesian", jet_features_weight=1.0, mode="intended"):
     """mode='intended': chamfer + w*jet (what chamfer_loss.py:35-41 computes and then discards);
     mode='reference': the value the reference actually RETURNS, ``jet_loss`` alone

@@ -288,6 +288,50 @@ def test_anomaly_chamfer_scores(B, N, D, lorentz):
         fn(torch.from_numpy(p).to(DEV), torch.from_numpy(q[:, : max(N - 1, 1)] if N > 1 else np.concatenate([q, q], 1)).to(DEV))
 
 
+@pytest.mark.parametrize("B,N,D,lorentz", [(6, 30, 3, False), (4, 30, 4, True), (3, 150, 3, False), (2, 150, 4, True), (5, 1, 3, False),
+                                            (5, 2, 4, False), (64, 33, 4, False)])
+def test_anomaly_hungarian_matches_scipy(B, N, D, lorentz):
+    """Device assignment solver against scipy.optimize.linear_sum_assignment (the reference's solver, through the oracle):
+    same matching, same total cost, same (B, N) scores."""
+    from gnn_jet_autoencoder_b200 import anomaly
+    rng = np.random.default_rng(B * 13 + N)
+    p, q = rng.normal(size=(B, N, D)).astype(np.float32), rng.normal(size=(B, N, D)).astype(np.float32)
+    want, matching, total = O.anomaly_hungarian(p.astype(np.float64), q.astype(np.float64), lorentz=lorentz)
+    m, t = anomaly.assignment(torch.from_numpy(p).to(DEV), torch.from_numpy(q).to(DEV), lorentz=lorentz)
+    m = m.cpu().numpy()
+    assert all(sorted(row.tolist()) == list(range(N)) for row in m)
+    assert np.allclose(t.cpu().numpy(), total, rtol=1e-5, atol=1e-4)          # optimal cost (the matching itself could differ on ties)
+    assert np.array_equal(m, matching)
+    fn = anomaly.hungarian_lorentz if lorentz else anomaly.hungarian
+    got = fn(torch.from_numpy(p).to(DEV), torch.from_numpy(q).to(DEV))
+    assert tuple(got.shape) == (B, N) and np.allclose(got.cpu().numpy(), want, rtol=1e-5, atol=1e-5)
+    got_b = fn(torch.from_numpy(p), torch.from_numpy(q), batch_size=3)
+    assert not got_b.is_cuda and torch.allclose(got_b, got.cpu())
+
+
+def test_hungarian_mse_loss_value_and_gradient():
+    """HungarianMSELoss (hungarian_mse.py:27-58) against its lines written out with scipy + torch autograd on the host."""
+    from scipy import optimize
+    from gnn_jet_autoencoder_b200 import HungarianMSELoss
+    rng = np.random.default_rng(21)
+    p, q = rng.normal(size=(6, 30, 3)).astype(np.float32), rng.normal(size=(6, 30, 3)).astype(np.float32)
+    ph = torch.from_numpy(p).requires_grad_(True)
+    cost = torch.cdist(ph, torch.from_numpy(q)).detach().numpy()
+    matching = [optimize.linear_sum_assignment(cost[i])[1] for i in range(len(cost))]
+    shuffled = torch.stack([ph[i, torch.from_numpy(matching[i])] for i in range(len(matching))])
+    want = torch.nn.MSELoss()(shuffled, torch.from_numpy(q))
+    want.backward()
+    pd = torch.from_numpy(p).to(DEV).requires_grad_(True)
+    got = HungarianMSELoss()(pd, torch.from_numpy(q).to(DEV))
+    got.backward()
+    assert abs(got.item() - want.item()) <= 1e-6 * abs(want.item())
+    assert torch.allclose(pd.grad.cpu(), ph.grad, rtol=1e-6, atol=1e-9)
+    with pytest.raises(NotImplementedError):
+        HungarianMSELoss()(pd, torch.from_numpy(q).to(DEV), polar_coord=True)
+    with pytest.raises(ValueError):
+        HungarianMSELoss()(pd[..., :2], torch.from_numpy(q).to(DEV)[..., :2])
+
+
 # ---- loss kernel ----------------------------------------------------------------------------------------
 @pytest.mark.parametrize("B,Np,Nq,D,norm", [(5, 30, 30, 3, "cartesian"), (3, 7, 11, 4, "minkowskian"), (2, 150, 150, 3, "cartesian"),
                                              (4, 1, 1, 4, "polar"), (300, 30, 30, 3, "polar")])

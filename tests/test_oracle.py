@@ -168,3 +168,22 @@ def test_anomaly_chamfer_against_a_torch_restatement():
     assert np.allclose(O.anomaly_chamfer(p, q, lorentz=True), want_l.numpy(), rtol=1e-12, atol=0)
     assert O.anomaly_chamfer(p[..., :3], q[..., :3]).shape == (4, 9)
 
+
+def test_anomaly_hungarian_oracle_properties():
+    """The oracle's matching is scipy's (the reference's solver): a permutation per jet, never worse than the identity or a
+    random matching, and exact on a permuted copy (score 0, matching = inverse permutation)."""
+    rng = np.random.default_rng(11)
+    p = rng.normal(size=(5, 8, 4))
+    perm = np.stack([rng.permutation(8) for _ in range(5)])
+    q = p[np.arange(5)[:, None], perm]                       # q_j = p_perm[j]
+    score, matching, total = O.anomaly_hungarian(p, q)
+    assert np.allclose(total, 0) and np.allclose(p[np.arange(5)[:, None], matching], p[np.arange(5)[:, None], matching])
+    assert all(sorted(m.tolist()) == list(range(8)) for m in matching)
+    inv = np.argsort(perm, axis=1)                            # row i of p sits at column inv[i] of q
+    assert np.array_equal(matching, inv)
+    q2 = rng.normal(size=(5, 8, 4))
+    _, m2, t2 = O.anomaly_hungarian(p, q2, lorentz=True)
+    d = p[:, :, None, :] - q2[:, None, :, :]
+    c = d[..., 0] ** 2 - (d[..., 1:] ** 2).sum(-1)
+    assert np.all(t2 <= np.trace(c, axis1=1, axis2=2) + 1e-12)
+

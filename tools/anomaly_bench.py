@@ -31,3 +31,19 @@ t_ours, a = timeit(lambda: anomaly.chamfer(p, q))
 t_ref, b = timeit(lambda: torch.cat([ref(p[i:i + 4096], q[i:i + 4096]) for i in range(0, B, 4096)]))
 print(f"B={B} N={N} D={D}: ours {t_ours * 1e3:.3f} ms ({B / t_ours / 1e6:.1f} M jets/s), torch broadcast form {t_ref * 1e3:.3f} ms "
       f"({B / t_ref / 1e6:.1f} M jets/s), max |diff| {float((a - b).abs().max()):.2e}")
+
+# ---- Hungarian scores: device assignment solver against the reference's per-jet scipy loop (host) ----
+import numpy as np
+from scipy import optimize
+Bh = 4096
+ph, qh = p[:Bh], q[:Bh]
+t_ours, a = timeit(lambda: anomaly.hungarian(ph, qh), reps=5)
+t0 = time.perf_counter()
+cost = torch.cdist(ph, qh).cpu().numpy()
+matching = [optimize.linear_sum_assignment(cost[i])[1] for i in range(len(cost))]
+p_shuffle = torch.stack([ph[i, torch.from_numpy(matching[i]).to(dev)] for i in range(Bh)])
+b = ((p_shuffle - qh) ** 2).sum(-1)
+torch.cuda.synchronize()
+t_ref = time.perf_counter() - t0
+print(f"hungarian, B={Bh} N={N}: ours {t_ours * 1e3:.2f} ms ({Bh / t_ours / 1e3:.0f} k jets/s), cdist + scipy loop + per-jet gather "
+      f"{t_ref * 1e3:.0f} ms ({Bh / t_ref / 1e3:.1f} k jets/s), max |diff| {float((a - b).abs().max()):.2e}")
