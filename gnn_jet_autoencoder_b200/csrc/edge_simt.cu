@@ -17,7 +17,9 @@ struct Carver {
   int take(int n) { int o = off; off += (n + 3) & ~3; return o; }
 };
 
-int plan_smem(MPLayout* L, int R, bool backward) {
+// dpar_global: the backward kernel's parameter-gradient accumulators (one float per edge parameter) do not fit next to the
+// staged weights for wide layers; the CTA then accumulates straight into its partial in global memory (L2 resident).
+int plan_smem(MPLayout* L, int R, bool backward, bool dpar_global = false) {
   L->R = R; L->Rs = R + 4;
   Carver c;
   for (int l = 1; l < L->Le; ++l) L->o_wE[l] = c.take(L->Ep[l] * L->Kp[l]);
@@ -36,7 +38,7 @@ int plan_smem(MPLayout* L, int R, bool backward) {
   } else {
     for (int l = 0; l < L->Le; ++l) L->o_act[l] = c.take(L->Ep[l] * L->Rs);
     L->n_edge_dpar = L->pV[0];           // all edge parameters (only l >= 1 weights/biases and the wd column are used)
-    L->o_dpar = c.take(L->n_edge_dpar);
+    L->o_dpar = dpar_global ? -1 : c.take(L->n_edge_dpar);
     L->o_dh = c.take(GJ_IB * L->Hs);     // i-side distance gradient accumulators
     L->o_dQ = c.take(32 * L->E0s);
     L->o_dP = c.take(GJ_IB * L->E0s);
@@ -281,7 +283,8 @@ edge_bwd_simt_kernel(const MPLayout L, const float* __restrict__ h, const float*
   constexpr int TI = R / 32;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   stage_weights(L, params, sm);
-  float* dpar = sm + L.o_dpar;
+  float* out = part + (size_t)blockIdx.x * L.n_edge_dpar;
+  float* dpar = L.o_dpar >= 0 ? sm + L.o_dpar : out;      // wide layers: accumulate in the CTA's global partial
   for (int idx = tid; idx < L.n_edge_dpar; idx += GJ_THREADS) dpar[idx] = 0.f;
   const int H = L.H, K0 = L.K[0], W2 = 2 * L.E0p;
   for (int jet = blockIdx.x; jet < L.B; jet += gridDim.x) {
@@ -405,8 +408,8 @@ edge_bwd_simt_kernel(const MPLayout L, const float* __restrict__ h, const float*
     }
   }
   __syncthreads();
-  float* out = part + (size_t)blockIdx.x * L.n_edge_dpar;
-  for (int idx = tid; idx < L.n_edge_dpar; idx += GJ_THREADS) out[idx] = dpar[idx];
+  if (dpar != out)
+    for (int idx = tid; idx < L.n_edge_dpar; idx += GJ_THREADS) out[idx] = dpar[idx];
 }
 
 // dparams[p] = sum_cta part[cta][p] over the edge-parameter block, skipping the slots node_pre_bwd owns
@@ -448,8 +451,12 @@ int gj_edge_grid(int batch) {
 
 int gj_edge_fwd_simt(MPLayout L, const float* h, const float* pq, const float* params, float* e_out, cudaStream_t stream) {
   int bytes = plan_smem(&L, kFwdR, false);
-  if (bytes > 227 * 1024) { gj_set_error("gj_mp_step_fwd(fp32): needs %d B shared memory (> 227 KB)", bytes); return GJ_ERR_SMEM; }
   auto kern = edge_fwd_simt_kernel<kFwdR>;
+  if (bytes > 227 * 1024) {      // wide layers: half the rows per tile
+    bytes = plan_smem(&L, kFwdR / 2, false);
+    kern = edge_fwd_simt_kernel<kFwdR / 2>;
+  }
+  if (bytes > 227 * 1024) { gj_set_error("gj_mp_step_fwd(fp32): needs %d B shared memory (> 227 KB)", bytes); return GJ_ERR_SMEM; }
   cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (ce != cudaSuccess) { gj_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   kern<<<gj_edge_grid(L.B), GJ_THREADS, bytes, stream>>>(L, h, pq, params, e_out);
@@ -466,6 +473,7 @@ int gj_reduce_edge_partials(const MPLayout& L, const float* part, int nparts, fl
 int gj_edge_bwd_simt(MPLayout L, const float* h, const float* pq, const float* params, const float* de, float* dpq, float* dh,
                      float* dparams, float* part, cudaStream_t stream) {
   int bytes = plan_smem(&L, kBwdR, true);
+  if (bytes > 227 * 1024) bytes = plan_smem(&L, kBwdR, true, true);      // wide layers: gradient accumulators in global memory
   if (bytes > 227 * 1024) { gj_set_error("gj_mp_step_bwd(fp32): needs %d B shared memory (> 227 KB)", bytes); return GJ_ERR_SMEM; }
   auto kern = edge_bwd_simt_kernel<kBwdR>;
   cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);

@@ -1107,10 +1107,14 @@ int gj_edge_fwd_tc(MPLayout L, const float* h, const float* pq, const float* par
   for (int l = 1; l < L.Le; ++l)
     if (L.Ep[l] > 256 || L.Kp[l] > 256) { gj_set_error("gj_mp_step_fwd(bf16): edge widths above 256 unsupported"); return GJ_ERR_INVALID; }
   TCPlan T;
-  constexpr int NWG = 2;
+  int NWG = 2;
   plan_tc_fwd(&L, &T, NWG);
   for (int l = 0; l < L.Le; ++l)
     if (L.Ep[l] > 16 * GJ_MAX_CHUNKS) { gj_set_error("gj_mp_step_fwd(bf16): edge widths above 256 unsupported"); return GJ_ERR_INVALID; }
+  if (T.smem_bytes > 227 * 1024 || T.tmem_cols_total > 512) {      // wide layers: one warpgroup per CTA
+    NWG = 1;
+    plan_tc_fwd(&L, &T, NWG);
+  }
   if (T.smem_bytes > 227 * 1024 || T.tmem_cols_total > 512) {
     gj_set_error("gj_mp_step_fwd(bf16): needs %d B shared memory / %d TMEM columns (limits 232448 / 512)", T.smem_bytes, T.tmem_cols_total);
     return GJ_ERR_SMEM;
@@ -1120,7 +1124,8 @@ int gj_edge_fwd_tc(MPLayout L, const float* h, const float* pq, const float* par
   T.trace = trace_fwd == 2;
   if (T.trace) { int z[4] = {0, 0, 0, 0}; cudaMemcpyToSymbolAsync(g_trace_n, z, sizeof(z), 0, cudaMemcpyHostToDevice, stream); }
   const int NH = nh_env == 1 ? 1 : 2;
-  auto kern = NH == 1 ? edge_fwd_tc_kernel<NWG, 1> : edge_fwd_tc_kernel<NWG, 2>;
+  auto kern = NWG == 1 ? (NH == 1 ? edge_fwd_tc_kernel<1, 1> : edge_fwd_tc_kernel<1, 2>)
+                       : (NH == 1 ? edge_fwd_tc_kernel<2, 1> : edge_fwd_tc_kernel<2, 2>);
   cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T.smem_bytes);
   if (ce != cudaSuccess) { gj_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   int sms = gj_num_sms();

@@ -103,6 +103,32 @@ def test_mp_step_matches_oracle(precision, N, H, edge, node, B, metric):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_wide_step_forward_matches_oracle(precision):
+    """H = 128 with a [128, 128] edge network (BASELINE config 5's middle width): the forward step runs on the wide-layer
+    fall-backs (half row tiles in the fp32 kernel, one warpgroup per CTA in the generic tensor-core kernel).  The backward of
+    this width is not covered yet and must say so instead of returning numbers."""
+    N, H, edge, node, B = 12, 128, [128, 128], [128, 8], 3
+    rng = np.random.default_rng(128)
+    shapes_e = [(o, i) for i, o in zip([2 * H + 1] + edge[:-1], edge)]
+    shapes_n = [(o, i) for i, o in zip([edge[-1] + H] + node[:-1], node)]
+    ew = [rng.uniform(-1, 1, s) / np.sqrt(s[1]) for s in shapes_e]
+    eb = [rng.uniform(-1, 1, s[0]) / np.sqrt(s[1]) for s in shapes_e]
+    nw = [rng.uniform(-1, 1, s) / np.sqrt(s[1]) for s in shapes_n]
+    nb = [rng.uniform(-1, 1, s[0]) / np.sqrt(s[1]) for s in shapes_n]
+    h = rng.normal(0, 0.5, (B, N, H))
+    y_ref, cache = O.mp_step_forward(h, ew, eb, nw, nb, 0.2, "euclidean")
+    pack = lambda ws, bs: [np.concatenate([w.ravel(), b.ravel()]) for w, b in zip(ws, bs)]
+    flat = torch.from_numpy(np.concatenate(pack(ew, eb) + pack(nw, nb))).float().to(DEV)
+    ht = torch.from_numpy(h).float().to(DEV)
+    args = (N, H, edge, node, 0.2, 0, ops.PRECISIONS[precision])
+    y, e = torch.ops.gnnjet.mp_step_fwd(ht, flat, *args)
+    assert rel(y.cpu().numpy(), y_ref) < TOL[precision]["out"]
+    assert rel(e.cpu().numpy(), O.leaky(cache["edge_z"][-1], 0.2).sum(axis=2)) < TOL[precision]["out"]
+    with pytest.raises(_lib.GnnJetError, match="do not fit shared memory|needs .* shared memory"):
+        torch.ops.gnnjet.mp_step_bwd(ht, e, flat, torch.ones_like(y), *args)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
 @pytest.mark.parametrize("alpha", [0.0, 1.0, 1.7])
 def test_mp_step_alpha_range(precision, alpha):
     """LeakyReLU slopes at and beyond the edges of (0, 1): alpha > 1 takes the min(z, alpha z) form (the tensor-core
