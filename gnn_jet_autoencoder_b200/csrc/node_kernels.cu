@@ -186,8 +186,10 @@ __global__ void __launch_bounds__(NK_THREADS) node_pre_bwd_kernel(const PreArgs 
     }
     Wt[idx] = v;
   }
-  float* dpar = sm + A.o_dpar;   // [E0][2H] (Wa | Wb gradients, row length 2H) then [E0] bias gradient
   const int ndpar = A.E0 * 2 * A.H + A.E0;
+  float* out = part + (size_t)blockIdx.x * ndpar;
+  // [E0][2H] (Wa | Wb gradients, row length 2H) then [E0] bias gradient; wide layers accumulate in the CTA's global partial
+  float* dpar = A.o_dpar >= 0 ? sm + A.o_dpar : out;
   for (int idx = threadIdx.x; idx < ndpar; idx += NK_THREADS) dpar[idx] = 0.f;
   float* X = sm + A.o_h;    // h rows [R][hs]
   float* G = sm + A.o_pq;   // dPQ rows [R][ps]
@@ -224,8 +226,8 @@ __global__ void __launch_bounds__(NK_THREADS) node_pre_bwd_kernel(const PreArgs 
   }
   __syncthreads();
   // partial layout: [Wa grads E0*H][Wb grads E0*H][b0 grads E0]
-  float* out = part + (size_t)blockIdx.x * ndpar;
-  for (int idx = threadIdx.x; idx < ndpar; idx += NK_THREADS) out[idx] = dpar[idx];
+  if (dpar != out)
+    for (int idx = threadIdx.x; idx < ndpar; idx += NK_THREADS) out[idx] = dpar[idx];
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -241,7 +243,24 @@ struct PostArgs {
   int o_V[GJ_MAX_LAYERS], vs[GJ_MAX_LAYERS], o_c[GJ_MAX_LAYERS];     // weights [Op][vs]
   int o_Vt[GJ_MAX_LAYERS], vts[GJ_MAX_LAYERS];                        // transposed weights [Ip][vts] (bwd only)
   int o_Y[GJ_MAX_LAYERS + 1], o_g0, o_g1, o_dpar, smem_floats;
+  int wide;                    // backward of wide layers: ONE weight area, (re)staged before every GEMM; gradients in global memory
 };
+
+// wide mode: layer m's weights (or their transpose) into the shared weight area, biases stay resident
+__device__ void post_stage_one(const PostArgs& A, const float* __restrict__ params, float* sm, int m, bool transposed) {
+  const int O = A.O[m], I = A.I[m], Op = rup4(O), Ip = rup4(I);
+  if (!transposed) {
+    for (int idx = threadIdx.x; idx < Op * A.vs[m]; idx += NK_THREADS) {
+      const int o = idx / A.vs[m], k = idx - o * A.vs[m];
+      sm[A.o_V[m] + idx] = (o < O && k < I) ? __ldg(params + A.pV[m] + o * I + k) : 0.f;
+    }
+  } else {
+    for (int idx = threadIdx.x; idx < Ip * A.vts[m]; idx += NK_THREADS) {
+      const int k = idx / A.vts[m], o = idx - k * A.vts[m];
+      sm[A.o_Vt[m] + idx] = (o < O && k < I) ? __ldg(params + A.pV[m] + o * I + k) : 0.f;
+    }
+  }
+}
 
 __device__ void post_stage_weights(const PostArgs& A, const float* __restrict__ params, float* sm, bool transposed) {
   for (int m = 0; m < A.Ln; ++m) {
@@ -308,8 +327,12 @@ __global__ void __launch_bounds__(NK_THREADS) node_post_bwd_kernel(const PostArg
                                                                     float* __restrict__ dh, float* __restrict__ part) {
   extern __shared__ float4 nk_smem_raw[];
   float* sm = reinterpret_cast<float*>(nk_smem_raw);
-  post_stage_weights(A, params, sm, true);
-  float* dpar = sm + A.o_dpar;
+  if (!A.wide) post_stage_weights(A, params, sm, true);
+  else
+    for (int m = 0; m < A.Ln; ++m)
+      for (int o = threadIdx.x; o < rup4(A.O[m]); o += NK_THREADS) sm[A.o_c[m] + o] = o < A.O[m] ? __ldg(params + A.pc[m] + o) : 0.f;
+  float* out = part + (size_t)blockIdx.x * A.n_node_params;
+  float* dpar = A.o_dpar >= 0 ? sm + A.o_dpar : out;
   for (int idx = threadIdx.x; idx < A.n_node_params; idx += NK_THREADS) dpar[idx] = 0.f;
   const int Hout = A.O[A.Ln - 1], Houtp = rup4(Hout);
   for (int r0 = blockIdx.x * A.R; r0 < A.rows; r0 += gridDim.x * A.R) {
@@ -318,6 +341,7 @@ __global__ void __launch_bounds__(NK_THREADS) node_post_bwd_kernel(const PostArg
     post_load_rows(A, e, h, sm + A.o_Y[0], r0);
     __syncthreads();
     for (int m = 0; m < A.Ln; ++m) {
+      if (A.wide) { post_stage_one(A, params, sm, m, false); __syncthreads(); }
       nk_gemm_rows<1>(sm + A.o_Y[m], A.S, sm + A.o_V[m], A.vs[m], sm + A.o_c[m], sm + A.o_Y[m + 1], A.S, nullptr, A.R,
                       rup4(A.O[m]), rup4(A.I[m]), A.alpha);
       __syncthreads();
@@ -337,6 +361,7 @@ __global__ void __launch_bounds__(NK_THREADS) node_post_bwd_kernel(const PostArg
     for (int m = A.Ln - 1; m >= 0; --m) {
       const int O = A.O[m], I = A.I[m];
       nk_wgrad(g, A.S, sm + A.o_Y[m], A.S, dpar + (A.pV[m] - A.p_first), dpar + (A.pc[m] - A.p_first), A.R, O, I);
+      if (A.wide) { post_stage_one(A, params, sm, m, true); __syncthreads(); }
       if (m > 0) nk_gemm_rows<2>(g, A.S, sm + A.o_Vt[m], A.vts[m], nullptr, gp, A.S, sm + A.o_Y[m], A.R, rup4(I), rup4(O), A.alpha);
       else       nk_gemm_rows<0>(g, A.S, sm + A.o_Vt[m], A.vts[m], nullptr, gp, A.S, nullptr, A.R, rup4(I), rup4(O), A.alpha);
       __syncthreads();
@@ -353,8 +378,8 @@ __global__ void __launch_bounds__(NK_THREADS) node_post_bwd_kernel(const PostArg
     }
   }
   __syncthreads();
-  float* out = part + (size_t)blockIdx.x * A.n_node_params;
-  for (int idx = threadIdx.x; idx < A.n_node_params; idx += NK_THREADS) out[idx] = dpar[idx];
+  if (dpar != out)
+    for (int idx = threadIdx.x; idx < A.n_node_params; idx += NK_THREADS) out[idx] = dpar[idx];
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -750,7 +775,7 @@ static const int kSmemLimit = 227 * 1024;
 static const int kSmemTarget = 54 * 1024;   // <= this many bytes per CTA lets 4 CTAs share an SM (latency hiding)
 static const int kSmemTargetBwd = 110 * 1024;   // backward: 2 CTAs per SM, larger row blocks (fewer partials, longer wgrad loops)
 
-static int pre_plan(const MPLayout& L, PreArgs* A, bool backward) {
+static int pre_plan_impl(const MPLayout& L, PreArgs* A, bool backward, bool dpar_global) {
   memset(A, 0, sizeof(*A));
   A->rows = L.B * L.N; A->H = L.H; A->ld = L.ld; A->cols = L.cols; A->E0 = L.E[0]; A->E0p = L.E0p; A->K0 = L.K[0];
   const int Hp = (L.H + 3) & ~3, width = 2 * L.E0p;
@@ -772,16 +797,23 @@ static int pre_plan(const MPLayout& L, PreArgs* A, bool backward) {
       A->o_b = take(R * A->hs);      // dh staging
       A->o_h = take(R * A->hs);
       A->o_pq = take(R * A->ps);
-      A->o_dpar = take(L.E[0] * 2 * L.H + L.E[0]);
+      A->o_dpar = dpar_global ? -1 : take(L.E[0] * 2 * L.H + L.E[0]);
     }
     A->smem_floats = off;
     if (off * 4 <= (R > 16 ? (backward ? kSmemTargetBwd : kSmemTarget) : kSmemLimit)) return off * 4;
   }
   return -1;
 }
+// wide layers (backward): the parameter-gradient accumulators move to the CTA's partial in global memory
+static int pre_plan(const MPLayout& L, PreArgs* A, bool backward) {
+  int bytes = pre_plan_impl(L, A, backward, false);
+  if (bytes < 0 && backward) bytes = pre_plan_impl(L, A, backward, true);
+  return bytes;
+}
 
-static int post_plan(const MPLayout& L, PostArgs* A, bool backward) {
+static int post_plan_impl(const MPLayout& L, PostArgs* A, bool backward, bool wide) {
   memset(A, 0, sizeof(*A));
+  A->wide = wide ? 1 : 0;
   A->rows = L.B * L.N; A->H = L.H; A->ld = L.ld; A->cols = L.cols; A->EL = L.EL; A->Ln = L.Ln; A->alpha = L.alpha;
   int wmax = L.EL + L.H;
   for (int m = 0; m < L.Ln; ++m) {
@@ -795,20 +827,34 @@ static int post_plan(const MPLayout& L, PostArgs* A, bool backward) {
     A->R = R;
     int off = 0;
     auto take = [&](int n) { int o = off; off += (n + 3) & ~3; return o; };
+    int wmaxf = 0;      // wide: one weight area for the largest matrix in either orientation
     for (int m = 0; m < L.Ln; ++m) {
       const int Op = (L.O[m] + 3) & ~3, Ip = (L.I[m] + 3) & ~3;
       A->vs[m] = nk_stride(L.I[m]);
-      A->o_V[m] = take(Op * A->vs[m]);
+      if (backward) A->vts[m] = nk_stride(L.O[m]);
+      if (Op * A->vs[m] > wmaxf) wmaxf = Op * A->vs[m];
+      if (backward && Ip * A->vts[m] > wmaxf) wmaxf = Ip * A->vts[m];
+    }
+    const int o_wide = wide ? take(wmaxf) : 0;
+    for (int m = 0; m < L.Ln; ++m) {
+      const int Op = (L.O[m] + 3) & ~3, Ip = (L.I[m] + 3) & ~3;
+      A->o_V[m] = wide ? o_wide : take(Op * A->vs[m]);
       A->o_c[m] = take(Op);
-      if (backward) { A->vts[m] = nk_stride(L.O[m]); A->o_Vt[m] = take(Ip * A->vts[m]); }
+      if (backward) A->o_Vt[m] = wide ? o_wide : take(Ip * A->vts[m]);
     }
     const int nY = backward ? L.Ln + 1 : 2;
     for (int m = 0; m < nY; ++m) A->o_Y[m] = take(R * A->S);
-    if (backward) { A->o_g0 = take(R * A->S); A->o_g1 = take(R * A->S); A->o_dpar = take(A->n_node_params); }
+    if (backward) { A->o_g0 = take(R * A->S); A->o_g1 = take(R * A->S); A->o_dpar = wide ? -1 : take(A->n_node_params); }
     A->smem_floats = off;
     if (off * 4 <= (R > 16 ? (backward ? kSmemTargetBwd : kSmemTarget) : kSmemLimit)) return off * 4;
   }
   return -1;
+}
+// wide layers (backward): V and its transpose do not fit side by side; see PostArgs::wide
+static int post_plan(const MPLayout& L, PostArgs* A, bool backward) {
+  int bytes = post_plan_impl(L, A, backward, false);
+  if (bytes < 0 && backward) bytes = post_plan_impl(L, A, backward, true);
+  return bytes;
 }
 
 static int nk_grid(int rows, int R, int smem_bytes) {

@@ -70,6 +70,7 @@ def test_umma_selftest(m, n, k, a_mn, b_mn):
     (33, 8, [16, 32, 16], [8, 16, 8], 2, "euclidean"),
     (1, 3, [16], [3, 2], 4, "euclidean"),
     (64, 6, [8, 24], [6, 5], 2, "euclidean"),
+    (10, 8, [16, 16], [180, 180], 3, "euclidean"),          # wide node MLP: V and V^T re-staged per GEMM, gradients in global partials
 ])
 def test_mp_step_matches_oracle(precision, N, H, edge, node, B, metric):
     rng = np.random.default_rng(N * 100 + H)
@@ -105,8 +106,9 @@ def test_mp_step_matches_oracle(precision, N, H, edge, node, B, metric):
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_wide_step_forward_matches_oracle(precision):
     """H = 128 with a [128, 128] edge network (BASELINE config 5's middle width): the forward step runs on the wide-layer
-    fall-backs (half row tiles in the fp32 kernel, one warpgroup per CTA in the generic tensor-core kernel).  The backward of
-    this width is not covered yet and must say so instead of returning numbers."""
+    fall-backs (half row tiles in the fp32 edge kernel, one warpgroup per CTA in the generic tensor-core kernel).  The backward
+    of this width is not covered yet (the fp32 edge adjoint needs 240 KB of shared memory even with its gradient accumulators
+    in global memory) and must say so instead of returning numbers."""
     N, H, edge, node, B = 12, 128, [128, 128], [128, 8], 3
     rng = np.random.default_rng(128)
     shapes_e = [(o, i) for i, o in zip([2 * H + 1] + edge[:-1], edge)]
@@ -124,7 +126,7 @@ def test_wide_step_forward_matches_oracle(precision):
     y, e = torch.ops.gnnjet.mp_step_fwd(ht, flat, *args)
     assert rel(y.cpu().numpy(), y_ref) < TOL[precision]["out"]
     assert rel(e.cpu().numpy(), O.leaky(cache["edge_z"][-1], 0.2).sum(axis=2)) < TOL[precision]["out"]
-    with pytest.raises(_lib.GnnJetError, match="do not fit shared memory|needs .* shared memory"):
+    with pytest.raises(_lib.GnnJetError, match="shared memory"):
         torch.ops.gnnjet.mp_step_bwd(ht, e, flat, torch.ones_like(y), *args)
 
 
