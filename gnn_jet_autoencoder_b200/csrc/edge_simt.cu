@@ -19,10 +19,12 @@ struct Carver {
 
 // dpar_global: the backward kernel's parameter-gradient accumulators (one float per edge parameter) do not fit next to the
 // staged weights for wide layers; the CTA then accumulates straight into its partial in global memory (L2 resident).
-int plan_smem(MPLayout* L, int R, bool backward, bool dpar_global = false) {
+// w_global (backward of wide layers whose weights are already laid out [Ep][Kp] in the parameter block, i.e. E and K need no
+// padding): the GEMM helpers read the weights straight from global memory (L1 / L2) instead of a staged copy.
+int plan_smem(MPLayout* L, int R, bool backward, bool dpar_global = false, bool w_global = false) {
   L->R = R; L->Rs = R + 4;
   Carver c;
-  for (int l = 1; l < L->Le; ++l) L->o_wE[l] = c.take(L->Ep[l] * L->Kp[l]);
+  for (int l = 1; l < L->Le; ++l) L->o_wE[l] = w_global ? -1 : c.take(L->Ep[l] * L->Kp[l]);
   for (int l = 1; l < L->Le; ++l) L->o_bE[l] = c.take(L->Ep[l]);
   L->o_wd = c.take(L->E0p);
   L->o_h = c.take(GJ_IB * L->Hs);      // h rows of the i block
@@ -52,11 +54,13 @@ int plan_smem(MPLayout* L, int R, bool backward, bool dpar_global = false) {
 
 __device__ void stage_weights(const MPLayout& L, const float* __restrict__ params, float* sm) {
   for (int l = 1; l < L.Le; ++l) {
-    float* w = sm + L.o_wE[l];
     const int Kp = L.Kp[l], K = L.K[l], E = L.E[l];
-    for (int idx = threadIdx.x; idx < L.Ep[l] * Kp; idx += GJ_THREADS) {
-      int c = idx / Kp, k = idx - c * Kp;
-      w[idx] = (c < E && k < K) ? __ldg(params + L.pW[l] + c * K + k) : 0.f;
+    if (L.o_wE[l] >= 0) {
+      float* w = sm + L.o_wE[l];
+      for (int idx = threadIdx.x; idx < L.Ep[l] * Kp; idx += GJ_THREADS) {
+        int c = idx / Kp, k = idx - c * Kp;
+        w[idx] = (c < E && k < K) ? __ldg(params + L.pW[l] + c * K + k) : 0.f;
+      }
     }
     for (int c = threadIdx.x; c < L.Ep[l]; c += GJ_THREADS) sm[L.o_bE[l] + c] = c < E ? __ldg(params + L.pb[l] + c) : 0.f;
   }
@@ -315,7 +319,7 @@ edge_bwd_simt_kernel(const MPLayout L, const float* __restrict__ h, const float*
           edge_layer0<R>(L, sm, it, drow);
           __syncthreads();
           for (int l = 1; l < L.Le; ++l) {
-            simt_layer_fwd<R>(sm + L.o_act[l - 1], sm + L.o_wE[l], sm + L.o_bE[l], sm + L.o_act[l], L.Kp[l], L.Ep[l],
+            simt_layer_fwd<R>(sm + L.o_act[l - 1], L.o_wE[l] >= 0 ? sm + L.o_wE[l] : params + L.pW[l], sm + L.o_bE[l], sm + L.o_act[l], L.Kp[l], L.Ep[l],
                               L.Rs, L.alpha);
             __syncthreads();
           }
@@ -335,7 +339,7 @@ edge_bwd_simt_kernel(const MPLayout L, const float* __restrict__ h, const float*
             simt_layer_wgrad<R>(sm + L.o_act[l], sm + L.o_act[l - 1], dpar + L.pW[l], dpar + L.pb[l], L.E[l], L.K[l],
                                 L.Ep[l], L.Kp[l], L.Rs);
             __syncthreads();
-            simt_layer_dgrad<R>(sm + L.o_act[l], sm + L.o_wE[l], sm + L.o_act[l - 1], L.Kp[l], L.Ep[l], L.Rs, L.alpha);
+            simt_layer_dgrad<R>(sm + L.o_act[l], L.o_wE[l] >= 0 ? sm + L.o_wE[l] : params + L.pW[l], sm + L.o_act[l - 1], L.Kp[l], L.Ep[l], L.Rs, L.alpha);
             __syncthreads();
           }
           // ---- consume dz0 (in act[0]) ----
@@ -474,6 +478,12 @@ int gj_edge_bwd_simt(MPLayout L, const float* h, const float* pq, const float* p
                      float* dparams, float* part, cudaStream_t stream) {
   int bytes = plan_smem(&L, kBwdR, true);
   if (bytes > 227 * 1024) bytes = plan_smem(&L, kBwdR, true, true);      // wide layers: gradient accumulators in global memory
+  if (bytes > 227 * 1024) {                                               // ... and the weights read in place
+    bool in_place = true;
+    for (int l = 1; l < L.Le; ++l)      // same layout as the staged copy, and 16-byte aligned rows
+      in_place = in_place && L.E[l] == L.Ep[l] && L.K[l] == L.Kp[l] && (reinterpret_cast<uintptr_t>(params + L.pW[l]) & 15) == 0;
+    if (in_place) bytes = plan_smem(&L, kBwdR, true, true, true);
+  }
   if (bytes > 227 * 1024) { gj_set_error("gj_mp_step_bwd(fp32): needs %d B shared memory (> 227 KB)", bytes); return GJ_ERR_SMEM; }
   auto kern = edge_bwd_simt_kernel<kBwdR>;
   cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);

@@ -104,11 +104,10 @@ def test_mp_step_matches_oracle(precision, N, H, edge, node, B, metric):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
-def test_wide_step_forward_matches_oracle(precision):
-    """H = 128 with a [128, 128] edge network (BASELINE config 5's middle width): the forward step runs on the wide-layer
-    fall-backs (half row tiles in the fp32 edge kernel, one warpgroup per CTA in the generic tensor-core kernel).  The backward
-    of this width is not covered yet (the fp32 edge adjoint needs 240 KB of shared memory even with its gradient accumulators
-    in global memory) and must say so instead of returning numbers."""
+def test_wide_step_matches_oracle(precision):
+    """H = 128 with a [128, 128] edge network (BASELINE config 5's middle width): the step runs on the wide-layer fall-backs
+    (half row tiles in the fp32 edge kernel, one warpgroup per CTA in the generic tensor-core forward; fp32 edge backward with
+    gradient accumulators in global memory and weights read in place; node adjoints that re-stage V / V^T per GEMM)."""
     N, H, edge, node, B = 12, 128, [128, 128], [128, 8], 3
     rng = np.random.default_rng(128)
     shapes_e = [(o, i) for i, o in zip([2 * H + 1] + edge[:-1], edge)]
@@ -126,8 +125,13 @@ def test_wide_step_forward_matches_oracle(precision):
     y, e = torch.ops.gnnjet.mp_step_fwd(ht, flat, *args)
     assert rel(y.cpu().numpy(), y_ref) < TOL[precision]["out"]
     assert rel(e.cpu().numpy(), O.leaky(cache["edge_z"][-1], 0.2).sum(axis=2)) < TOL[precision]["out"]
-    with pytest.raises(_lib.GnnJetError, match="shared memory"):
-        torch.ops.gnnjet.mp_step_bwd(ht, e, flat, torch.ones_like(y), *args)
+    dy = rng.normal(0, 1.0, y_ref.shape)
+    dh_ref, dew, deb, dnw, dnb = O.mp_step_backward(dy, cache, ew, nw)
+    gref = np.concatenate(pack(dew, deb) + pack(dnw, dnb))
+    dh, dflat = torch.ops.gnnjet.mp_step_bwd(ht, e, flat, torch.from_numpy(dy).float().to(DEV), *args)
+    gtol = 1e-5 if precision == "fp32" else 0.1      # bf16 forward, fp32 adjoint kernels: see test_mp_step_matches_oracle
+    assert rel(dh.cpu().numpy(), dh_ref) < gtol
+    assert rel(dflat.cpu().numpy(), gref) < gtol
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
