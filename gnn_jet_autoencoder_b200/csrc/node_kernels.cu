@@ -703,8 +703,15 @@ __global__ void __launch_bounds__(NF_THREADS) node_post_bwd_fast_kernel(int rows
 __device__ __forceinline__ float reduce_column(const float* __restrict__ part, int nparts, int n, int p) {
   __shared__ float red[RED_SLICES][33];
   float acc = 0.f;
-  if (p < n)
-    for (int c = threadIdx.y; c < nparts; c += RED_SLICES) acc += part[(size_t)c * n + p];
+  if (p < n) {
+    int c = threadIdx.y;
+    for (; c + 3 * RED_SLICES < nparts; c += 4 * RED_SLICES) {      // four loads in flight; same summation order as one by one
+      const float v0 = part[(size_t)c * n + p], v1 = part[(size_t)(c + RED_SLICES) * n + p];
+      const float v2 = part[(size_t)(c + 2 * RED_SLICES) * n + p], v3 = part[(size_t)(c + 3 * RED_SLICES) * n + p];
+      acc += v0; acc += v1; acc += v2; acc += v3;
+    }
+    for (; c < nparts; c += RED_SLICES) acc += part[(size_t)c * n + p];
+  }
   red[threadIdx.y][threadIdx.x] = acc;
   __syncthreads();
   float tot = 0.f;
