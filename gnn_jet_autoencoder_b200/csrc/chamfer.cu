@@ -7,7 +7,7 @@
 
 namespace {
 
-__global__ void chamfer_kernel(int np_, int nq, int dim, int mink, float wc, float wj, const float* __restrict__ p,
+__global__ void chamfer_kernel(int np_, int nq, int dim, int mink, int mink_jet, float wc, float wj, const float* __restrict__ p,
                                const float* __restrict__ q, float* __restrict__ jet_terms, float* __restrict__ dp) {
   extern __shared__ float sm[];
   float* sp = sm;                       // [np][4]
@@ -21,7 +21,8 @@ __global__ void chamfer_kernel(int np_, int nq, int dim, int mink, float wc, flo
   for (int idx = tid; idx < np_ * 4; idx += blockDim.x) { int n = idx >> 2, c = idx & 3; sp[idx] = c < dim ? __ldg(pg + n * dim + c) : 0.f; }
   for (int idx = tid; idx < nq * 4; idx += blockDim.x) { int n = idx >> 2, c = idx & 3; sq[idx] = c < dim ? __ldg(qg + n * dim + c) : 0.f; }
   __syncthreads();
-  const float s1 = mink ? -1.f : 1.f;   // sign of components 1..3
+  const float s1 = mink ? -1.f : 1.f;       // sign of components 1..3 in the pairwise distances
+  const float sj = mink_jet ? -1.f : 1.f;   // ... and in the jet term (chamfer_loss.py:40 passes loss_norm_choice unchanged)
   float local = 0.f;
   if (tid < np_) {          // nearest target for each reconstructed particle
     float4 a = *reinterpret_cast<const float4*>(sp + tid * 4);
@@ -60,12 +61,13 @@ __global__ void chamfer_kernel(int np_, int nq, int dim, int mink, float wc, flo
   if (tid == 0) {
     float tot = 0.f;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
-    float jt = jd[0] * jd[0] + s1 * (jd[1] * jd[1] + jd[2] * jd[2] + jd[3] * jd[3]);
+    float jt = jd[0] * jd[0] + sj * (jd[1] * jd[1] + jd[2] * jd[2] + jd[3] * jd[3]);
     jet_terms[b * 2 + 0] = tot;
     jet_terms[b * 2 + 1] = jt;
   }
   if (dp && tid < np_) {
     const float sgn[4] = {2.f, 2.f * s1, 2.f * s1, 2.f * s1};
+    const float sgj[4] = {2.f, 2.f * sj, 2.f * sj, 2.f * sj};
     float g[4];
     const float* a = sp + tid * 4;
     const float* c = sq + jstar[tid] * 4;
@@ -76,7 +78,7 @@ __global__ void chamfer_kernel(int np_, int nq, int dim, int mink, float wc, flo
 #pragma unroll
         for (int k = 0; k < 4; ++k) g[k] += a[k] - sq[j * 4 + k];
       }
-    for (int k = 0; k < dim; ++k) dp[((size_t)b * np_ + tid) * dim + k] = sgn[k] * (wc * g[k] + wj * jd[k]);
+    for (int k = 0; k < dim; ++k) dp[((size_t)b * np_ + tid) * dim + k] = sgn[k] * wc * g[k] + sgj[k] * wj * jd[k];
   }
 }
 
@@ -278,12 +280,14 @@ int gj_chamfer_launch(int batch, int np_, int nq, int dim, int norm, float wc, f
   if (batch < 0 || np_ < 1 || nq < 1 || np_ > 1024 || nq > 1024) { gj_set_error("gj_chamfer_fwd_bwd: particle counts must be in [1,1024]"); return GJ_ERR_INVALID; }
   if (dim != 3 && dim != 4) { gj_set_error("gj_chamfer_fwd_bwd: p and q must be 3- or 4-vectors (got %d)", dim); return GJ_ERR_INVALID; }
   if (batch == 0) { cudaMemsetAsync(terms, 0, 3 * sizeof(float), stream); return GJ_OK; }
-  int mink = (dim != 3 && norm != 0) ? 1 : 0;   // distance_sq.py:43-44: 3-vectors force cartesian
+  // distance_sq.py:43-44 forces cartesian for 3-vectors inside pairwise_distance_sq ONLY; the jet term of chamfer_loss.py:40
+  // calls normsq with the loss's norm choice directly, so 3-vectors with 'minkowskian' / 'polar' get p0^2 - p1^2 - p2^2 there
+  const int mink = (dim != 3 && norm != 0) ? 1 : 0, mink_jet = norm != 0 ? 1 : 0;
   int nmax = np_ > nq ? np_ : nq;
   int threads = gj_round_up(nmax, 32);
   if (threads < 32) threads = 32;
   size_t smem = (size_t)(np_ + nq) * 4 * sizeof(float) + (size_t)(np_ + nq) * sizeof(int) + (64 + 8) * sizeof(float);
-  chamfer_kernel<<<batch, threads, smem, stream>>>(np_, nq, dim, mink, wc, wj, p, q, jet_terms, dp);
+  chamfer_kernel<<<batch, threads, smem, stream>>>(np_, nq, dim, mink, mink_jet, wc, wj, p, q, jet_terms, dp);
   chamfer_reduce_kernel<<<1, 1024, 0, stream>>>(batch, wc, wj, jet_terms, terms);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) { gj_set_error("chamfer launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }

@@ -8,10 +8,10 @@ from . import ops
 
 
 def _norm_id(p: torch.Tensor, norm_choice: str) -> int:
-    """distance_sq.py:43-44,57-77: 3-vectors are always cartesian; 'minkowskian' and 'polar' both evaluate
-    2*p0^2 - sum p^2; anything else is the euclidean square."""
-    if p.shape[-1] == 3:
-        return 0
+    """Norm id handed to ``gj_chamfer_fwd_bwd``: 'minkowskian' and 'polar' both evaluate 2*p0^2 - sum p^2
+    (distance_sq.py:57-77), anything else is the euclidean square.  The kernel itself forces the PAIRWISE term of
+    3-vectors to cartesian (distance_sq.py:43-44) but keeps the requested norm in the jet term, which the reference
+    evaluates with ``normsq(jet_p - jet_q, norm_choice=self.loss_norm_choice)`` (chamfer_loss.py:40)."""
     return 1 if str(norm_choice).lower() in ("minkowskian", "polar") else 0
 
 

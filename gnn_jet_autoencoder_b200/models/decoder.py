@@ -8,10 +8,10 @@ import torch.nn as nn
 
 from .. import ops
 from .const import LOCAL_MIX
-from .graphnet import GraphNet, _default_device
+from .graphnet import Float32ParamsMixin, GraphNet, _default_device
 
 
-class Decoder(nn.Module):
+class Decoder(Float32ParamsMixin, nn.Module):
     """latent (B, latent) or (B, N*latent) -> (B, N, output_node_size).  Same constructor / attributes /
     ``state_dict`` keys as the reference (decoder.py:12-117); see GraphNet for ``precision``."""
 

@@ -9,14 +9,14 @@ import torch.nn as nn
 
 from .. import ops
 from .const import GLOBAL_MIX, LOCAL_MIX
-from .graphnet import GraphNet, _default_device
+from .graphnet import Float32ParamsMixin, GraphNet, _default_device
 
 
 def _canon(latent_map: str) -> str:
     return latent_map.lower().replace(" ", "_")
 
 
-class Encoder(nn.Module):
+class Encoder(Float32ParamsMixin, nn.Module):
     """(B, N, input_node_size) -> latent (B, latent_node_size), or (B, N*latent_node_size) for the
     per-node ('local mix') map.  Same constructor / attributes / ``state_dict`` keys as the reference
     (encoder.py:13-131); see GraphNet for ``precision``."""

@@ -8,6 +8,7 @@ no CPU implementation -- calling ``forward`` on a CPU module raises.
 """
 from __future__ import annotations
 
+import logging
 import os
 import warnings
 from typing import List, Optional, Union
@@ -42,7 +43,26 @@ def _resolve_precision(precision: Optional[str]) -> str:
     return "bf16" if ops.PRECISIONS[p] == ops.GJ_PREC_BF16 else "fp32"
 
 
-class GraphNet(nn.Module):
+class Float32ParamsMixin:
+    """Parameters of the fused path are ALWAYS stored in float32 (the kernels read them in place from one packed
+    buffer).  ``module.to(dtype=torch.float64)`` -- which reference callers issue with the CLI's default dtype, e.g.
+    ``PermutationTest`` (utils/permutation.py:19-20 via train.py:73-76) -- therefore leaves floating-point parameters in
+    float32; when neither device nor dtype would change, the very same storage is kept, so views into a packed buffer
+    (``GraphNet.flatten_parameters``, ``GNNAETrainer.flat``) survive the call.  Inputs of any dtype are accepted and
+    outputs are returned in the constructor's ``dtype``."""
+
+    def _apply(self, fn, recurse=True):
+        def keep32(t):
+            out = fn(t)
+            if out.is_floating_point() and out.dtype != torch.float32 and t.dtype == torch.float32:
+                out = out.to(torch.float32)
+                if out.device == t.device:
+                    return t          # fp32 -> wider -> fp32 is the identity: keep the storage (and any packed-buffer view)
+            return out
+        return super()._apply(keep32, recurse)
+
+
+class GraphNet(Float32ParamsMixin, nn.Module):
     """Fully connected message-passing network with the pair distance as edge feature.
 
     Extra keyword (not in the reference): ``precision`` -- ``"fp32"`` (default; SIMT FFMA kernels,
@@ -110,6 +130,7 @@ class GraphNet(nn.Module):
                 self.bn_edge.append(nn.ModuleList(nn.BatchNorm1d(w) for w in e_t))
                 self.bn_node.append(nn.ModuleList(nn.BatchNorm1d(l.out_features) for l in node))
         self._flat = None
+        self._flat_owner = None      # set by GNNAETrainer: the packed buffer then belongs to the trainer
         self.to(device=self.device, dtype=torch.float32)
 
     # ---- packed parameter storage -----------------------------------------------------------------
@@ -177,6 +198,8 @@ class GraphNet(nn.Module):
         ``metric``: 'euclidean' | 'minkowskian' (applied only where the current node width is 4,
         graphnet.py:155)."""
         self.metric = metric.lower()
+        if self.metric not in ("euclidean", "cartesian", "minkowskian"):      # graphnet.py:324-326
+            logging.warning(f"Metric ({self.metric}) for adjacency matrix is not implemented. Use 'cartesian' instead.")
         if self.batch_norm:
             raise NotImplementedError("batch_norm=True crashes in the reference (BatchNorm1d on a 4-D tensor, "
                                       "graphnet.py:287-288) and is not part of the fused path")
@@ -187,6 +210,10 @@ class GraphNet(nn.Module):
             raise RuntimeError("GraphNet.forward runs on sm_100a CUDA kernels only; move the module to a CUDA device "
                                "(there is no CPU fallback)")
         if not self._flat_ok():
+            if self._flat_owner is not None:
+                raise RuntimeError("GraphNet parameters were moved or re-typed after a GNNAETrainer packed them into its flat "
+                                   "buffer; the trainer would keep updating storage the module no longer reads.  Build a new "
+                                   "GNNAETrainer after moving the modules.")
             self.flatten_parameters()
         batch = x.shape[0]
         h = x.to(device=dev, dtype=torch.float32)

@@ -9,6 +9,7 @@ Two levels:
 """
 from __future__ import annotations
 
+import functools
 from typing import List, Sequence, Tuple
 
 import torch
@@ -25,6 +26,24 @@ LAUNCHES = {"count": 0}
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+def _on_device(fn):
+    """Runs an op body with the operands' GPU as the current device (the C launchers use cudaGetDevice() and the current
+    stream of the current device; the reference accepts e.g. ``device='cuda:1'`` while device 0 is current) and checks that
+    all tensor operands live on one device."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kw):
+        tens = [a for a in list(args) + list(kw.values()) if isinstance(a, Tensor)]
+        if not tens or not tens[0].is_cuda:
+            return fn(*args, **kw)          # _req raises the "no CPU implementation" error
+        dev = tens[0].device
+        for t in tens[1:]:
+            if t.device != dev:
+                raise _lib.GnnJetError(f"all operands must live on one device: got {dev} and {t.device}")
+        with torch.cuda.device(dev):
+            return fn(*args, **kw)
+    return wrapper
 
 
 def _ptr(t):
@@ -88,6 +107,7 @@ def _desc_for(h: Tensor, num_nodes: int, node_in: int, edge_widths, node_widths,
 
 
 @torch.library.custom_op("gnnjet::mp_step_fwd", mutates_args=(), device_types="cuda")
+@_on_device
 def mp_step_fwd(h: Tensor, params: Tensor, num_nodes: int, node_in: int, edge_widths: List[int],
                 node_widths: List[int], alpha: float, metric: int, precision: int) -> Tuple[Tensor, Tensor]:
     """One message-passing step (graphnet.py:154-168).  h (B,N,F) -> (h' (B,N,H'), e (B,N,E_last))."""
@@ -114,6 +134,7 @@ def _(h, params, num_nodes, node_in, edge_widths, node_widths, alpha, metric, pr
 
 
 @torch.library.custom_op("gnnjet::mp_step_bwd", mutates_args=(), device_types="cuda")
+@_on_device
 def mp_step_bwd(h: Tensor, e: Tensor, params: Tensor, dh_out: Tensor, num_nodes: int, node_in: int,
                 edge_widths: List[int], node_widths: List[int], alpha: float, metric: int,
                 precision: int) -> Tuple[Tensor, Tensor]:
@@ -174,6 +195,7 @@ def mp_step(h: Tensor, flat: Tensor, cfg, plist: Sequence[Tensor]) -> Tensor:
 
 # ---- Chamfer --------------------------------------------------------------------------------------
 @torch.library.custom_op("gnnjet::chamfer", mutates_args=(), device_types="cuda")
+@_on_device
 def chamfer(p: Tensor, q: Tensor, norm: int, w_chamfer: float, w_jet: float) -> Tuple[Tensor, Tensor]:
     """(terms[3], dterms[2]/dp): terms = [chamfer, jet, w_chamfer*chamfer + w_jet*jet]
     (chamfer_loss.py:26-41, distance_sq.py:46-54)."""
@@ -226,6 +248,7 @@ def chamfer_loss(p: Tensor, q: Tensor, norm: int, w_chamfer: float, w_jet: float
 
 # ---- 'mean' latent map ----------------------------------------------------------------------------
 @torch.library.custom_op("gnnjet::latent_mean_fwd", mutates_args=(), device_types="cuda")
+@_on_device
 def latent_mean_fwd(y: Tensor) -> Tensor:
     y = _req(y, "y")
     B, N, W = y.shape
@@ -241,6 +264,7 @@ def _(y):
 
 
 @torch.library.custom_op("gnnjet::latent_mean_bwd", mutates_args=(), device_types="cuda")
+@_on_device
 def latent_mean_bwd(dz: Tensor, num_nodes: int) -> Tensor:
     dz = _req(dz, "dz")
     B, W = dz.shape
@@ -273,6 +297,7 @@ def latent_mean(y: Tensor) -> Tensor:
 
 # ---- small dense layers ---------------------------------------------------------------------------
 @torch.library.custom_op("gnnjet::linear_fwd", mutates_args=(), device_types="cuda")
+@_on_device
 def linear_fwd(x: Tensor, w: Tensor, b: Tensor | None) -> Tensor:
     x = _req(x, "x")
     w = _req(w, "w")
@@ -293,6 +318,7 @@ def _(x, w, b):
 
 
 @torch.library.custom_op("gnnjet::linear_bwd", mutates_args=(), device_types="cuda")
+@_on_device
 def linear_bwd(x: Tensor, w: Tensor, dy: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
     x = _req(x, "x")
     w = _req(w, "w")
@@ -338,6 +364,7 @@ def linear(x: Tensor, w: Tensor, b: Tensor | None) -> Tensor:
 
 
 # ---- optimiser ------------------------------------------------------------------------------------
+@_on_device
 def adam_step_flat_(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Tensor, step: int, lr: float = 1e-5,
                     betas=(0.9, 0.999), eps: float = 1e-8, grad_scale: float = 1.0, l1_lambda: float = 0.0,
                     l2_lambda: float = 0.0) -> None:
@@ -352,6 +379,7 @@ def adam_step_flat_(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Te
     LAUNCHES["count"] += 1
 
 
+@_on_device
 def param_norms(param: Tensor) -> Tensor:
     """[sum |p|, sum p^2] of a flat buffer (encoder.py:173-179)."""
     param = _req(param, "param")
@@ -365,6 +393,7 @@ def param_norms(param: Tensor) -> Tensor:
     return out
 
 
+@_on_device
 def umma_selftest(a: Tensor, b: Tensor, a_mn_major: bool, b_mn_major: bool) -> Tensor:
     """D = A(m,k) B(n,k)^T on one CTA through tcgen05 (bf16 operands, fp32 TMEM accumulator)."""
     a = _req(a, "a")

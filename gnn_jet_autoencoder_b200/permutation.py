@@ -63,6 +63,8 @@ class PermutationTest:
         p = next(encoder.parameters())
         self.device = torch.device(device) if device is not None else p.device
         self.dtype = dtype if dtype is not None else p.dtype
+        # as utils/permutation.py:19-20; the fused modules keep float32 parameters whatever dtype is requested
+        # (Float32ParamsMixin) -- with the CLI default float64 (train.py:73-76) only the inputs / outputs are float64
         self.encoder = encoder.to(device=self.device, dtype=self.dtype)
         self.decoder = decoder.to(device=self.device, dtype=self.dtype)
 

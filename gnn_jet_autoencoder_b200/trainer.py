@@ -92,6 +92,17 @@ def allreduce_flat_(grad: torch.Tensor, group=None) -> torch.Tensor:
 # --------------------------------------------------------------------------------------------------
 # the fused step
 # --------------------------------------------------------------------------------------------------
+def _on_trainer_device(fn):
+    """Runs a trainer method with the trainer's GPU as the current device (launchers and streams follow the current device)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kw):
+        with torch.cuda.device(self.dev):
+            return fn(self, *args, **kw)
+    return wrapper
+
+
 class GNNAETrainer:
     """One optimisation step per call, on the caller's CUDA device.
 
@@ -124,6 +135,10 @@ class GNNAETrainer:
             self.map = "mean"
         if chamfer_mode == "reference" and jet_features_weight == 0:
             raise UnboundLocalError("jet_loss referenced before assignment (reference chamfer_loss.py:42)")
+        # the Chamfer target is the input batch: both sides must be 3- or 4-vectors of one width (distance_sq.py:31-42)
+        if decoder.output_node_size != encoder.input_node_size or encoder.input_node_size not in (3, 4):
+            raise ValueError(f"Dimension of q ({encoder.input_node_size}) does not match with dimension of p "
+                             f"({decoder.output_node_size}), or is not 3 or 4.")
         self.dev, self.B, self.N = dev, int(batch_size), encoder.num_nodes
         self.lr, self.betas, self.eps = lr, betas, eps
         self.l1, self.l2 = float(l1_lambda), float(l2_lambda)
@@ -161,6 +176,7 @@ class GNNAETrainer:
             g_d._step_offsets.append((o, c))
             o += c
         assert g_e._flat_ok() and g_d._flat_ok()
+        g_e._flat_owner = g_d._flat_owner = self      # forward raises (instead of silently re-packing) if the views break
 
         # ---- activations ----
         B, N = self.B, self.N
@@ -315,16 +331,19 @@ class GNNAETrainer:
         self._loss_and_bwd(st)
 
     # ---- public API ---------------------------------------------------------------------------------
+    @_on_trainer_device
     def forward_only(self, x: torch.Tensor):
         """encoder + decoder forward on a (B,N,F) batch (host or device); returns (latent, recon) device views."""
         self.x.copy_(x.reshape(self.x.shape), non_blocking=True)
         self._fwd(torch.cuda.current_stream().cuda_stream)
         return self.latent, self.recon
 
+    @_on_trainer_device
     def load_batch(self, x: torch.Tensor) -> None:
         """Host (ideally pinned) or device batch -> the step's resident input buffer."""
         self.x.copy_(x.reshape(self.x.shape), non_blocking=True)
 
+    @_on_trainer_device
     def compute_gradients(self) -> None:
         """forward + loss + backward on the resident batch; the flat gradient buffer holds d(sum loss)/dp."""
         if not self.use_graph:
@@ -343,12 +362,14 @@ class GNNAETrainer:
         self.graph.replay()
         ops.LAUNCHES["count"] += self.launches_per_step - 1
 
+    @_on_trainer_device
     def apply_gradients(self) -> None:
         allreduce_flat_(self.grad, self.group)
         self.step_count += 1
         ops.adam_step_flat_(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr, self.betas,
                             self.eps, 1.0, self.l1, self.l2)
 
+    @_on_trainer_device
     def step_async(self, x: torch.Tensor) -> None:
         self.load_batch(x)
         self.compute_gradients()
@@ -364,12 +385,14 @@ class GNNAETrainer:
             v += self.l2 * float(stats[4])
         return v
 
+    @_on_trainer_device
     def step(self, x: torch.Tensor) -> float:
         """One optimisation step; returns this rank's batch loss (a device->host read, like train.py:77)."""
         self.step_async(x)
         torch.cuda.current_stream().synchronize()
         return self.loss_from_stats(self.stats_host)
 
+    @_on_trainer_device
     def run_epoch(self, loader, is_train: bool = True, collect: bool = True):
         """The batch loop of reference utils/train.py:51-120 (``train`` / ``validate``) without its per-batch host
         synchronisations: the reference reads ``batch_loss.cpu().item()`` (:77) and copies target / latent / reconstruction to
@@ -380,8 +403,10 @@ class GNNAETrainer:
         ``drop_last=True``; the kernels run on fixed shapes).  ``is_train=False`` is the validation pass: forward and loss
         only, parameters untouched.  Returns ``(epoch_avg_loss, recons_data, target_data, latent_data)`` like the reference:
         the mean of the batch losses over the batches (train.py:108) and, with ``collect``, the concatenated host tensors
-        (else ``None``).  The host tensors are views of pinned epoch buffers the trainer keeps: they stay valid until the next
-        ``run_epoch`` call (clone them to keep several epochs)."""
+        (else ``None``).  The host tensors are views of pinned epoch buffers the trainer keeps, one set for training passes and
+        one for validation passes (the reference's train_loop calls train() then validate() and uses both results afterwards,
+        utils/train.py:196-236): they stay valid until the next ``run_epoch`` call of the SAME kind (clone them to keep several
+        epochs)."""
         st = torch.cuda.current_stream()
         try:
             nb = len(loader)
@@ -391,13 +416,14 @@ class GNNAETrainer:
         if nb == 0:
             raise ValueError("run_epoch: the loader yielded no batch")
         # epoch-sized pinned host buffers (allocated once and kept: pinning memory synchronises the device) and device log
-        cache = getattr(self, "_epoch_buffers", None)
+        caches = self.__dict__.setdefault("_epoch_buffers", {})      # one set per pass kind: train()'s outputs survive validate()
+        cache = caches.get(bool(is_train))
         if cache is None or cache["nb"] < nb or (collect and cache["recon"] is None):
             pin = lambda shape: torch.empty((nb,) + tuple(shape), dtype=torch.float32).pin_memory()
             cache = {"nb": nb, "log": torch.zeros((nb, self.stats.numel()), device=self.dev, dtype=torch.float32),
                      "recon": pin(self.recon.shape) if collect else None, "latent": pin(self.latent.shape) if collect else None,
                      "target": pin(self.x.shape) if collect else None}
-            self._epoch_buffers = cache
+            caches[bool(is_train)] = cache
         i = 0
         for x in loader:
             if i >= nb:

@@ -112,8 +112,9 @@ int gj_mp_step_bwd(const gj_mp_desc* d, const float* h, const float* e, const fl
                    void* workspace, size_t workspace_bytes, void* stream);
 
 /* Chamfer terms and gradient w.r.t. p (the reconstruction).
- * p (B,Np,D), q (B,Nq,D), D in {3,4}; norm: 0 cartesian, 1 minkowskian/polar (2*p0^2 - sum p^2,
- * forced to cartesian when D == 3, distance_sq.py:43-44).
+ * p (B,Np,D), q (B,Nq,D), D in {3,4}; norm: 0 cartesian, 1 minkowskian/polar (2*p0^2 - sum p^2).  For D == 3 the
+ * PAIRWISE distances are always cartesian (distance_sq.py:43-44) while the jet term keeps the requested norm
+ * (chamfer_loss.py:40 calls normsq directly: p0^2 - p1^2 - p2^2).
  * terms[0] = sum_b [sum_i min_j dist + sum_j min_i dist]   terms[1] = sum_b normsq(sum p - sum q)
  * terms[2] = w_chamfer * terms[0] + w_jet * terms[1]
  * (overwritten; deterministic: per-jet partials are written to jet_terms (B,2), which is also an

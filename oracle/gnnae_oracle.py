@@ -354,6 +354,15 @@ def normsq_signs(dim, norm_choice):
     return s
 
 
+def jet_term_signs(dim, norm_choice):
+    """The jet term calls normsq with the loss's norm choice directly (chamfer_loss.py:40): no 3-vector override, so
+    3-vectors with 'minkowskian' / 'polar' get p0^2 - p1^2 - p2^2."""
+    s = np.ones(dim)
+    if str(norm_choice).lower() in ("minkowskian", "polar"):
+        s[1:] = -1.0
+    return s
+
+
 def pairwise_distance_sq(p, q, norm_choice="cartesian"):
     """dist[b,i,j] = normsq(p[b,i] - q[b,j])   (distance_sq.py:46-54)."""
     if p.shape[0] != q.shape[0]:
@@ -385,8 +394,9 @@ def chamfer_terms(p, q, norm_choice="cartesian"):
     pn = p[bi, i_star]                       # (B,Nq,D)
     np.add.at(dp, (np.broadcast_to(bi, i_star.shape), i_star), 2.0 * s * (pn - q))
     jd = p.sum(axis=-2) - q.sum(axis=-2)     # (B,D)
-    jet = (jd * jd * s).sum()
-    djet = np.broadcast_to((2.0 * s * jd)[:, None, :], p.shape).copy()
+    sj = jet_term_signs(D, norm_choice).astype(p.dtype)
+    jet = (jd * jd * sj).sum()
+    djet = np.broadcast_to((2.0 * sj * jd)[:, None, :], p.shape).copy()
     return cham, jet, dp, djet
 
 

@@ -13,14 +13,20 @@ DEFAULT_NODE = [[16], [32], [8]]            # utils/argparse_utils.py:97-104
 
 def _case(N, B, *, edge=DEFAULT_EDGE, node=DEFAULT_NODE, num_mps=3, latent=20, latent_map="mean", vec=3,
           alphas=0.2, metric="euclidean", norm="cartesian", seed=0, normalize_output=False, store64=True,
-          jet_w=1.0, dec_edge=None, dec_node=None):
+          jet_w=1.0, dec_edge=None, dec_node=None, grad_stride=1):
     enc = dict(num_nodes=N, input_node_size=vec, latent_node_size=latent, node_sizes=node, edge_sizes=edge,
                num_mps=num_mps, alphas=alphas, latent_map=latent_map)
     dec = dict(num_nodes=N, latent_node_size=latent, output_node_size=vec, node_sizes=dec_node or node,
                edge_sizes=dec_edge or edge, num_mps=num_mps, alphas=alphas, latent_map=latent_map,
                normalize_output=normalize_output)
     return dict(enc=enc, dec=dec, B=B, N=N, vec=vec, metric=metric, loss_norm_choice=norm, seed=seed,
-                store64=store64, jet_features_weight=jet_w, l1_lambda=1e-8)
+                store64=store64, jet_features_weight=jet_w, l1_lambda=1e-8, grad_stride=grad_stride)
+
+
+def gsub(case, v):
+    """Fixtures of the wide architectures keep every ``grad_stride``-th entry of the (name-sorted, concatenated) encoder and
+    decoder gradients, so that the committed files stay small; comparisons apply the same subsampling."""
+    return np.asarray(v)[::case.get("grad_stride", 1)]
 
 
 CASES = {
@@ -47,6 +53,22 @@ CASES = {
     "n2": _case(2, 4, edge=[[16, 16]], node=[[8]], num_mps=2, latent=3, seed=12),
     # wide-sweep shaped (BASELINE config 5, smallest member) at small N
     "wide64_n9": _case(9, 2, edge=[[64, 64]], node=[[64]], num_mps=3, latent=8, seed=13, store64=False),
+    # j-block boundaries of the fused tensor-core kernels (32 j's per warp) and the N^2 tiling limit (JetNet150 shape)
+    "default_n31": _case(31, 2, store64=False, seed=14),
+    "default_n32": _case(32, 2, store64=False, seed=15),
+    "default_n64": _case(64, 2, store64=False, seed=16),
+    "default_n150": _case(150, 2, store64=False, seed=17),
+    # a batch that is not a multiple of the four (jet, j block) tasks of a tile group, larger than one wave of groups
+    "default_b257": _case(30, 257, store64=False, seed=18),
+    # BASELINE config 5 (deep / wide sweep): node_sizes [[H]], edge_sizes [[H, H]], 3-6 steps, latent 1-64
+    "wide128_n30": _case(30, 2, edge=[[128, 128]], node=[[128]], num_mps=3, latent=8, seed=19, store64=False, grad_stride=4),
+    "wide256_n12": _case(12, 2, edge=[[256, 256]], node=[[256]], num_mps=3, latent=16, seed=20, store64=False, grad_stride=16),
+    "wide64_mps6_n10": _case(10, 2, edge=[[64, 64]], node=[[64]], num_mps=6, latent=1, seed=21, store64=False, grad_stride=2),
+    "wide128_lat64_n33": _case(33, 2, edge=[[128, 128]], node=[[128]], num_mps=4, latent=64, seed=22, store64=False,
+                               grad_stride=8),
+    # 3-vectors with a Minkowskian loss norm: pairwise distances stay cartesian (distance_sq.py:43-44), the jet term does not
+    # (chamfer_loss.py:40)
+    "loss_mink3_n6": _case(6, 3, edge=[[16, 16]], node=[[8]], num_mps=2, latent=4, norm="minkowskian", seed=23, jet_w=0.7),
 }
 
 

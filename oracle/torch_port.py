@@ -99,11 +99,12 @@ def chamfer_intended(p, q, norm_choice="cartesian", jet_features_weight=1.0):
     pr = p.repeat(1, 1, M).view(B, N * M, D)
     qr = q.repeat(1, N, 1)
     diff = pr - qr
-    mink = D != 3 and str(norm_choice).lower() in ("minkowskian", "polar")
-    nsq = (lambda v: 2 * v[..., 0] ** 2 - (v ** 2).sum(-1)) if mink else (lambda v: (v ** 2).sum(-1))
-    dist = nsq(diff).view(B, N, M)
+    mink_name = str(norm_choice).lower() in ("minkowskian", "polar")
+    n_mink, n_cart = (lambda v: 2 * v[..., 0] ** 2 - (v ** 2).sum(-1)), (lambda v: (v ** 2).sum(-1))
+    # 3-vectors force cartesian in pairwise_distance_sq only (distance_sq.py:43-44); the jet term keeps the choice (:40)
+    dist = (n_mink if (mink_name and D != 3) else n_cart)(diff).view(B, N, M)
     cham = torch.min(dist, dim=-1).values.sum() + torch.min(dist, dim=-2).values.sum()
-    jet = nsq(p.sum(dim=-2) - q.sum(dim=-2)).sum()
+    jet = (n_mink if mink_name else n_cart)(p.sum(dim=-2) - q.sum(dim=-2)).sum()
     return cham + jet_features_weight * jet, cham, jet
 
 

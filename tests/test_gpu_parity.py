@@ -11,7 +11,7 @@ import torch
 
 import gnnae_oracle as O
 from conftest import GOLDEN
-from golden_cases import CASES, make_input, make_params
+from golden_cases import CASES, gsub, make_input, make_params
 from gnn_jet_autoencoder_b200 import ChamferLoss, Decoder, Encoder, GNNAETrainer, GraphNet, _lib, ops
 from gnn_jet_autoencoder_b200.trainer import synthetic_jets
 
@@ -66,6 +66,14 @@ def test_umma_selftest(m, n, k, a_mn, b_mn):
     (30, 16, [32, 128, 64, 16], [16, 32], 3, "euclidean"),
     (6, 4, [32, 128, 64, 16], [4, 4], 5, "minkowskian"),      # fused tensor-core kernels with the Minkowskian distance
     (150, 32, [32, 128, 64, 16], [32, 8], 2, "euclidean"),     # five j blocks per jet (per-j-block partial sums)
+    (31, 16, [32, 128, 64, 16], [16, 32], 3, "euclidean"),     # j-block boundaries of the fused kernels: 31 | 32 | 33 ...
+    (32, 16, [32, 128, 64, 16], [16, 32], 3, "euclidean"),
+    (64, 8, [32, 128, 64, 16], [8, 8], 2, "euclidean"),
+    (96, 16, [32, 128, 64, 16], [16, 32], 1, "euclidean"),
+    (160, 16, [32, 128, 64, 16], [16, 32], 1, "euclidean"),
+    (30, 64, [64, 64], [64, 64], 3, "euclidean"),              # BASELINE config 5 shapes: edge [[H, H]], node [[H]]
+    (33, 128, [128, 128], [128, 128], 2, "euclidean"),
+    (9, 256, [256, 256], [256, 256], 2, "euclidean"),
     (5, 4, [16, 16], [4, 4], 7, "minkowskian"),
     (33, 8, [16, 32, 16], [8, 16, 8], 2, "euclidean"),
     (1, 3, [16], [3, 2], 4, "euclidean"),
@@ -94,9 +102,7 @@ def test_mp_step_matches_oracle(precision, N, H, edge, node, B, metric):
     y, e = torch.ops.gnnjet.mp_step_fwd(ht, flat, *args)
     dh, dflat = torch.ops.gnnjet.mp_step_bwd(ht, e, flat, torch.from_numpy(dy).float().to(DEV), *args)
     t = TOL[precision]
-    # random tiny networks in isolation: a single flipped LeakyReLU slope is a visible fraction of the gradient in
-    # bf16 mode, hence the looser bound here (the model-level tests hold 3e-2)
-    gtol = t["grad"] if precision == "fp32" else 0.1
+    gtol = t["grad"]
     assert rel(y.cpu().numpy(), y_ref) < t["out"]
     assert rel(e.cpu().numpy(), O.leaky(cache["edge_z"][-1], 0.2).sum(axis=2)) < t["out"]
     assert rel(dh.cpu().numpy(), dh_ref) < gtol
@@ -190,7 +196,7 @@ def test_modules_match_golden(name, precision):
     eg = np.concatenate([ne[k].grad.cpu().numpy().ravel() for k in sorted(ep)])
     dg = np.concatenate([nd[k].grad.cpu().numpy().ravel() for k in sorted(dp)])
     # arg-min ties can flip per-tensor gradients; the concatenated gradient is the stable quantity
-    assert rel(np.concatenate([eg, dg]), np.concatenate([g["enc_grad"], g["dec_grad"]])) < t["grad"]
+    assert rel(np.concatenate([gsub(case, eg), gsub(case, dg)]), np.concatenate([g["enc_grad"], g["dec_grad"]])) < t["grad"]
     # the value the reference actually returns (jet term only, chamfer_loss.py:42)
     ret = ChamferLoss(case["loss_norm_choice"], mode="reference")(y.detach(), x, jet_features_weight=case["jet_features_weight"])
     assert abs(ret.item() - g["returned"]) <= 4 * t["out"] * abs(g["returned"]) + 1e-6
@@ -199,7 +205,9 @@ def test_modules_match_golden(name, precision):
 # ---- fused trainer path ---------------------------------------------------------------------------------
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 @pytest.mark.parametrize("name", ["default_n30", "default_n33", "trainsh_n30", "local_mix_us_n8", "local_mix_sp_n8",
-                                  "global_mix_n8", "bogus_map_n5", "mink_n6", "n1", "n2", "wide64_n9"])
+                                  "global_mix_n8", "bogus_map_n5", "mink_n6", "n1", "n2", "wide64_n9",
+                                  "default_n31", "default_n32", "default_n64", "default_n150", "default_b257",
+                                  "wide128_n30", "wide256_n12", "wide64_mps6_n10", "wide128_lat64_n33", "loss_mink3_n6"])
 @pytest.mark.parametrize("graph", [False, True])
 def test_trainer_gradients_match_golden(name, precision, graph):
     case = CASES[name]
@@ -220,10 +228,10 @@ def test_trainer_gradients_match_golden(name, precision, graph):
     assert rel(tr.recon.cpu().numpy(), g["recon"]) < t["out"]
     named = tr.named_gradients()
     sgn = lambda d: np.concatenate([np.sign(d[k]).ravel() for k in sorted(d)])
-    got = np.concatenate([named["encoder." + k].cpu().numpy().ravel() for k in sorted(ep)] +
-                         [named["decoder." + k].cpu().numpy().ravel() for k in sorted(dp)])
-    got = got + case["l1_lambda"] * np.concatenate([sgn(ep), sgn(dp)])   # the L1 term is added inside the fused Adam
-    assert rel(got, np.concatenate([g["enc_grad"], g["dec_grad"]])) < t["grad"]
+    # the L1 term is added inside the fused Adam
+    got_e = np.concatenate([named["encoder." + k].cpu().numpy().ravel() for k in sorted(ep)]) + case["l1_lambda"] * sgn(ep)
+    got_d = np.concatenate([named["decoder." + k].cpu().numpy().ravel() for k in sorted(dp)]) + case["l1_lambda"] * sgn(dp)
+    assert rel(np.concatenate([gsub(case, got_e), gsub(case, got_d)]), np.concatenate([g["enc_grad"], g["dec_grad"]])) < t["grad"]
     stats = tr.stats.cpu().numpy()
     assert abs(tr.loss_from_stats(stats) - g["loss_intended"]) <= 2 * t["out"] * abs(g["loss_intended"]) + 1e-6
 
@@ -278,8 +286,41 @@ def test_run_epoch_equals_the_per_batch_loop(graph):
     torch.cuda.synchronize()
     assert torch.equal(vrec[:B], tr_a.recon.cpu())
     assert np.isfinite(vavg) and vavg > 0
+    # the training pass's collected outputs survive the validation pass (separate pinned caches per pass kind: the reference's
+    # train_loop uses train()'s tensors after validate() has run, utils/train.py:196-236)
+    assert torch.equal(recons, torch.cat(rec)) and torch.equal(latents, torch.cat(lat))
     with pytest.raises(ValueError):
         tr_b.run_epoch([batches[0][: B - 1]])
+
+
+def test_float64_dtype_requests_keep_float32_parameters():
+    """The reference's default flow builds the models with the CLI dtype float64 and runs PermutationTest(encoder, decoder,
+    device, dtype=float64) before training (train.py:73-76, utils/permutation.py:19-20).  Parameters of the fused path stay
+    float32 -- and keep their storage inside a live trainer's flat buffer -- while inputs / outputs follow the dtype."""
+    from gnn_jet_autoencoder_b200 import PermutationTest
+    case = CASES["trainsh_n30"]
+    ep, dp = make_params(case)
+    enc = Encoder(**case["enc"], device=DEV, dtype=torch.float64, precision="fp32")
+    dec = Decoder(**case["dec"], device=DEV, dtype=torch.float64, precision="fp32")
+    enc.load_state_dict({k: torch.from_numpy(v) for k, v in ep.items()})
+    dec.load_state_dict({k: torch.from_numpy(v) for k, v in dp.items()})
+    tr = GNNAETrainer(enc, dec, batch_size=case["B"], use_cuda_graph=False)
+    x64 = torch.from_numpy(make_input(case))
+    out = PermutationTest(enc, dec, device=DEV, dtype=torch.float64)(x64)
+    assert out["equivariance"]["median"] < 1e-4
+    assert all(p.dtype == torch.float32 for p in list(enc.parameters()) + list(dec.parameters()))
+    assert enc.encoder._flat_ok() and dec.decoder._flat_ok()
+    assert enc.encoder.edge_net[0][0].weight.data_ptr() == tr.flat.data_ptr()      # still a view of the trainer's buffer
+    y = dec(enc(x64))
+    assert y.dtype == torch.float64
+    g = np.load(os.path.join(GOLDEN, "trainsh_n30.npz"))
+    assert rel(y.detach().cpu().numpy(), g["recon"]) < 1e-5
+    loss0 = tr.step(x64.float())
+    assert np.isfinite(loss0)
+    # moving the modules away breaks the views: forward must refuse instead of silently re-packing
+    enc.cpu(); enc.to(DEV)
+    with pytest.raises(RuntimeError):
+        enc(x64)
 
 
 # ---- permutation test harness (SURVEY 8.f rank 3) ----------------------------------------------------------

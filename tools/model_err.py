@@ -9,7 +9,7 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")]
-from test_gpu_parity import CASES, GOLDEN, DEV, build, make_input, rel  # noqa: E402
+from test_gpu_parity import CASES, GOLDEN, DEV, build, gsub, make_input, rel  # noqa: E402
 from gnn_jet_autoencoder_b200 import ChamferLoss  # noqa: E402
 
 for name in sorted(CASES):
@@ -28,5 +28,5 @@ for name in sorted(CASES):
         dg = np.concatenate([nd[k].grad.cpu().numpy().ravel() for k in sorted(dp)])
         row.append("%s: latent %.1e recon %.1e grad %.1e" % (
             precision, rel(z.detach().cpu().numpy(), g["latent"]), rel(y.detach().cpu().numpy(), g["recon"]),
-            rel(np.concatenate([eg, dg]), np.concatenate([g["enc_grad"], g["dec_grad"]]))))
+            rel(np.concatenate([gsub(case, eg), gsub(case, dg)]), np.concatenate([g["enc_grad"], g["dec_grad"]]))))
     print("  ".join(row))
