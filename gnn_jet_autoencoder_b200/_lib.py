@@ -64,6 +64,8 @@ SIGNATURES = {
     "gj_bench_edge_bwd_only": (C.c_int, [C.POINTER(MPDesc), _P, _P, _P, _P, _P, _SZ, _P]),
     "gj_mp_plan_info": (C.c_int, [C.POINTER(MPDesc), C.POINTER(C.c_int32)]),
     "gj_umma_selftest": (C.c_int, [_I, _I, _I, _I, _I, _P, _P, _P, _P]),
+    "gj_dense_gemm": (C.c_int, [_I, _I, _I, _I, _P, _P, _P, _I, _F, _P, _I, _P, _P, _SZ, _I, _P]),
+    "gj_dense_gemm_workspace": (_SZ, [_I, _I, _I, _I]),
     "gj_last_error": (C.c_char_p, []),
     "gj_abi_version": (_I, []),
     "gj_build_arch": (C.c_char_p, []),

@@ -68,6 +68,19 @@ size_t gj_edge_bwd_tc_ws_floats(const MPLayout&);
 int gj_edge_bwd_tc(MPLayout, const float*, const float*, const float*, const float*, float*, float*, float*, float*,
                    cudaStream_t);
 int gj_umma_selftest_launch(int, int, int, int, int, const float*, const float*, float*, cudaStream_t);
+bool gj_node_generic_fits(const MPLayout&);
+bool gj_edge_simt_fits(MPLayout, const float*);
+bool gj_edge_tc_fits(MPLayout);
+size_t gj_edge_mat_ws_floats(const MPLayout&, bool);
+int gj_edge_mat_launches(const MPLayout&, bool);
+int gj_edge_mat_fwd(const MPLayout&, const float*, const float*, const float*, float*, float*, int, cudaStream_t);
+int gj_edge_mat_bwd(const MPLayout&, const float*, const float*, const float*, const float*, float*, float*, float*, float*, int, cudaStream_t);
+size_t gj_dense_ws_floats(const MPLayout&, bool);
+int gj_dense_launches(const MPLayout&, bool);
+int gj_dense_pre_fwd(const MPLayout&, const float*, const float*, float*, int, cudaStream_t);
+int gj_dense_post_fwd(const MPLayout&, const float*, const float*, const float*, float*, float*, int, cudaStream_t);
+int gj_dense_post_bwd(const MPLayout&, const float*, const float*, const float*, const float*, float*, float*, float*, float*, int, cudaStream_t);
+int gj_dense_pre_bwd(const MPLayout&, const float*, const float*, const float*, float*, float*, float*, int, cudaStream_t);
 void gj_tc_plan_info(MPLayout, int*);
 int gj_chamfer_launch(int, int, int, int, int, float, float, const float*, const float*, float*, float*, float*, cudaStream_t);
 int gj_pair_min_dist_launch(int, int, int, int, int, const float*, const float*, float*, float*, cudaStream_t);
@@ -97,13 +110,38 @@ size_t gj_mp_param_count(const gj_mp_desc* d) {
 static size_t align_floats(size_t n) { return (n + 63) & ~(size_t)63; }   // keep every region 256-byte aligned
 
 struct StepWs {   // offsets in floats
-  size_t pq, dpq, de, part, part_post, part_pre, epart, wimg, dist, total;
+  size_t pq, dpq, de, part, part_post, part_pre, epart, wimg, dist, dense, emat, total;
 };
 
 static bool use_tc(const MPLayout& L, int precision) { return precision == GJ_PREC_BF16 && L.Le > 1; }
 // the step runs the second-generation fused kernels (forward and backward are covered by the same widths)
+static bool edge_mat_forced() { static const int f = getenv("GJ_EDGE_MAT") ? atoi(getenv("GJ_EDGE_MAT")) : 0; return f != 0; }
 static bool tc2_path(const MPLayout& L, int precision) {
-  return use_tc(L, precision) && gj_fwd2_supported(L) && gj_bwd2_supported(L) && !gj_tc_v1_forced();
+  return !edge_mat_forced() && use_tc(L, precision) && gj_fwd2_supported(L) && gj_bwd2_supported(L) && !gj_tc_v1_forced();
+}
+
+static bool edge_mat(const MPLayout& L, int precision);
+
+// Node-level work (P|Q projections, node MLP and their adjoints) as generic GEMMs (dense.cu): wherever a node-level weight
+// matrix does not fit the fused node kernels' shared-memory plans, and for wide layers (BASELINE config 5: H >= 64), where the
+// GEMM formulation -- tcgen05 in the bf16 mode -- is the faster one
+static bool dense_node(const MPLayout& L, int precision) {
+  static const int force = getenv("GJ_DENSE_NODE") ? atoi(getenv("GJ_DENSE_NODE")) : -1;
+  if (edge_mat(L, precision)) return true;
+  if (tc2_path(L, precision)) return false;
+  if (!gj_node_generic_fits(L)) return true;
+  if (force >= 0) return force != 0;
+  int wmax = L.H > L.E[0] ? L.H : L.E[0];
+  for (int m = 0; m < L.Ln; ++m) if (L.O[m] > wmax) wmax = L.O[m];
+  return wmax >= 64;
+}
+
+// The edge MLP as generic GEMMs over the materialised edge rows of a chunk of jets (dense.cu): for the widths no fused edge
+// kernel has a plan for (e.g. edge_sizes [[256, 256]]); GJ_EDGE_MAT=1 forces it (tests)
+static bool edge_mat(const MPLayout& L, int precision) {
+  if (edge_mat_forced()) return true;
+  if (tc2_path(L, precision)) return false;
+  return use_tc(L, precision) ? !gj_edge_tc_fits(L) : !gj_edge_simt_fits(L, nullptr);
 }
 
 // backward of the bf16 step with both node-level adjoints on tcgen05: their partials and the edge kernel's are reduced together
@@ -137,6 +175,7 @@ static StepWs plan_ws(const MPLayout& L, int precision, bool backward) {
     if (tc2_path(L, precision)) { const size_t r2 = gj_bwd2_ws_floats(L); if (r2 > r) r = r2; }
     if (q > p) p = q;
     if (r > p) p = r;
+    if (p < 64) p = 64;
     w.part = off; off += align_floats(p);
     // the all-tensor-core backward keeps the node-MLP and projection partials next to the edge kernel's, so that one
     // launch reduces all three at the end of the step
@@ -146,6 +185,10 @@ static StepWs plan_ws(const MPLayout& L, int precision, bool backward) {
       w.part_pre = off; off += align_floats(gj_node_pre_bwd_tc_ws_floats(L));
     }
   }
+  w.dense = off;
+  if (dense_node(L, precision)) off += align_floats(gj_dense_ws_floats(L, backward));
+  w.emat = off;
+  if (edge_mat(L, precision)) off += align_floats(gj_edge_mat_ws_floats(L, backward));
   w.total = off;
   return w;
 }
@@ -170,15 +213,19 @@ static int mp_step_fwd_impl(const gj_mp_desc* d, const float* h, const float* pa
   const StepWs w = plan_ws(L, d->precision, false);
   if (workspace_bytes < w.total * sizeof(float)) { gj_set_error("%s: workspace too small", who); return GJ_ERR_WORKSPACE; }
   float* ws = (float*)workspace;
-  const bool tc2 = tc2_path(L, d->precision);
+  const bool emat = edge_mat(L, d->precision);
+  const bool tc2 = tc2_path(L, d->precision) && !emat;
   if (saved && !tc2) { gj_set_error("%s: this step has nothing to save (gj_mp_step_saved_bytes is 0)", who); return GJ_ERR_INVALID; }
   float* pre = saved ? (float*)saved : ws;      // P|Q, parameter image, pair distances: same layout in either buffer
   cudaStream_t st = (cudaStream_t)stream;
-  if ((rc = gj_node_pre_fwd(L, h, params, pre + w.pq, st))) return rc;
-  if (tc2) rc = gj_edge_fwd2(L, h, pre + w.pq, params, e_out, ws + w.epart, pre + w.wimg, saved ? pre + w.dist : nullptr, st, false);
+  const bool dense = dense_node(L, d->precision);
+  if ((rc = dense ? gj_dense_pre_fwd(L, h, params, pre + w.pq, d->precision, st) : gj_node_pre_fwd(L, h, params, pre + w.pq, st))) return rc;
+  if (emat) rc = gj_edge_mat_fwd(L, h, ws + w.pq, params, e_out, ws + w.emat, d->precision, st);
+  else if (tc2) rc = gj_edge_fwd2(L, h, pre + w.pq, params, e_out, ws + w.epart, pre + w.wimg, saved ? pre + w.dist : nullptr, st, false);
   else rc = use_tc(L, d->precision) ? gj_edge_fwd_tc(L, h, ws + w.pq, params, e_out, st)
                                     : gj_edge_fwd_simt(L, h, ws + w.pq, params, e_out, st);
   if (rc) return rc;
+  if (dense) return gj_dense_post_fwd(L, e_out, h, params, h_out, ws + w.dense, d->precision, st);
   return gj_node_post_fwd(L, e_out, h, params, h_out, st);
 }
 
@@ -192,6 +239,8 @@ int gj_mp_step_launches(const gj_mp_desc* d, int backward, int with_saved) {
   if (gj_fill_arch(d, &L, &why)) return 0;
   const bool tc2 = tc2_path(L, d->precision);
   const int njb = (tc2 && L.N > 32) ? 1 : 0;      // per-j-block partial sums (forward: e, backward: dP)
+  if (edge_mat(L, d->precision)) return gj_dense_launches(L, backward != 0) + gj_edge_mat_launches(L, backward != 0);
+  if (dense_node(L, d->precision)) return gj_dense_launches(L, backward != 0) + (backward ? 2 : 1);      // + the edge kernel(s)
   if (!backward) return tc2 ? 4 + njb : 3;        // projections, [parameter image], edge kernel, [j-block sum], node MLP
   if (!tc2) return 8;
   // node MLP adjoint, [projections, parameter image, pair distances unless saved], edge kernel, [dP j-block sum],
@@ -232,10 +281,11 @@ static int mp_step_bwd_impl(const gj_mp_desc* d, const float* h, const float* e,
   const StepWs w = plan_ws(L, d->precision, true);
   if (workspace_bytes < w.total * sizeof(float)) { gj_set_error("%s: workspace too small", who); return GJ_ERR_WORKSPACE; }
   float* ws = (float*)workspace;
-  const bool tc2 = tc2_path(L, d->precision);
+  const bool emat = edge_mat(L, d->precision);
+  const bool tc2 = tc2_path(L, d->precision) && !emat;
   if (saved && !tc2) { gj_set_error("%s: this step has nothing saved (gj_mp_step_saved_bytes is 0)", who); return GJ_ERR_INVALID; }
   float* pre = saved ? (float*)saved : ws;      // read-only when it is the caller's saved buffer
-  if (node_tail_fused(L, d->precision)) {
+  if (node_tail_fused(L, d->precision) && !emat) {
     // node MLP adjoint (also clears dP|dQ), P|Q unless saved, edge adjoint, projections' adjoint, one reduction of all partials
     int np_post = 0, np_pre = 0, np_edge = 0;
     const float* part_edge = nullptr;
@@ -245,6 +295,16 @@ static int mp_step_bwd_impl(const gj_mp_desc* d, const float* h, const float* e,
                            saved != nullptr, st, 2, &part_edge, &np_edge))) return rc;
     if ((rc = gj_node_pre_bwd_tc(L, h, params, ws + w.dpq, dh, ws + w.part_pre, &np_pre, st))) return rc;
     return gj_reduce_step_partials(L, part_edge, np_edge, ws + w.part_pre, np_pre, ws + w.part_post, np_post, dparams, st);
+  }
+  const bool dense = dense_node(L, d->precision);
+  if (dense) {      // generic-GEMM node level (dense.cu) around the edge adjoint
+    if ((rc = gj_dense_post_bwd(L, e, h, params, dh_out, ws + w.de, dh, dparams, ws + w.dense, d->precision, st))) return rc;
+    if ((rc = gj_dense_pre_fwd(L, h, params, ws + w.pq, d->precision, st))) return rc;
+    rc = emat ? gj_edge_mat_bwd(L, h, ws + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.emat, d->precision, st)
+       : use_tc(L, d->precision) ? gj_edge_bwd_tc(L, h, ws + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.part, st)
+                                 : gj_edge_bwd_simt(L, h, ws + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.part, st);
+    if (rc) return rc;
+    return gj_dense_pre_bwd(L, h, params, ws + w.dpq, dh, dparams, ws + w.dense, d->precision, st);
   }
   // node MLP adjoint: de, node-path dh, node parameter gradients
   if (tc2 && gj_node_post_bwd_tc_supported(L) && node_post_tc_enabled()) {      // bf16 mode: the node MLP adjoint on tcgen05

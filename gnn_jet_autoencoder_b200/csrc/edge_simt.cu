@@ -469,6 +469,18 @@ int gj_edge_fwd_simt(MPLayout L, const float* h, const float* pq, const float* p
   return GJ_OK;
 }
 
+// both fp32 edge kernels have a shared-memory plan for these widths (otherwise the step runs the materialised path of dense.cu)
+bool gj_edge_simt_fits(MPLayout L, const float* params) {
+  MPLayout F = L;
+  if (plan_smem(&F, kFwdR, false) > 227 * 1024 && plan_smem(&F, kFwdR / 2, false) > 227 * 1024) return false;
+  MPLayout Bk = L;
+  if (plan_smem(&Bk, kBwdR, true) <= 227 * 1024 || plan_smem(&Bk, kBwdR, true, true) <= 227 * 1024) return true;
+  bool in_place = true;
+  for (int l = 1; l < L.Le; ++l)
+    in_place = in_place && L.E[l] == L.Ep[l] && L.K[l] == L.Kp[l] && (params == nullptr || (reinterpret_cast<uintptr_t>(params + L.pW[l]) & 15) == 0);
+  return in_place && params != nullptr && plan_smem(&Bk, kBwdR, true, true, true) <= 227 * 1024;
+}
+
 // number of per-CTA partials and floats per partial of the edge-parameter gradients
 void gj_edge_bwd_simt_partials(const MPLayout& L, int* nparts, int* n) { *nparts = gj_edge_grid(L.B); *n = L.pV[0]; }
 

@@ -1136,6 +1136,22 @@ int gj_edge_fwd_tc(MPLayout L, const float* h, const float* pq, const float* par
   return GJ_OK;
 }
 
+bool gj_edge_simt_fits(MPLayout, const float*);
+// the first-generation tensor-core forward has a plan for these widths and the backward either has one or can hand over to the
+// fp32 kernel (otherwise the step runs the materialised path of dense.cu)
+bool gj_edge_tc_fits(MPLayout L) {
+  if (L.alpha > 1.f) return gj_edge_simt_fits(L, nullptr);
+  for (int l = 0; l < L.Le; ++l)
+    if (L.Ep[l] > 256 || (l > 0 && L.Kp[l] > 256) || L.Ep[l] > 16 * GJ_MAX_CHUNKS) return false;
+  TCPlan T; MPLayout Lf = L;
+  plan_tc_fwd(&Lf, &T, 2);
+  if (T.smem_bytes > 227 * 1024 || T.tmem_cols_total > 512) { Lf = L; plan_tc_fwd(&Lf, &T, 1); }
+  if (T.smem_bytes > 227 * 1024 || T.tmem_cols_total > 512) return false;
+  BwdPlan Bp; MPLayout Lb = L;
+  if (plan_tc_bwd(&Lb, &Bp, 2) == 0) return true;
+  return gj_edge_simt_fits(L, nullptr);
+}
+
 int gj_reduce_edge_partials(const MPLayout& L, const float* part, int nparts, float* dparams, cudaStream_t stream);
 
 static int tc_bwd_grid(int batch, int nwg) {

@@ -864,6 +864,12 @@ static int post_plan(const MPLayout& L, PostArgs* A, bool backward) {
   return bytes;
 }
 
+// every generic node kernel (projections, node MLP and both adjoints) has a shared-memory plan for these widths
+bool gj_node_generic_fits(const MPLayout& L) {
+  PreArgs A; PostArgs B;
+  return pre_plan(L, &A, false) >= 0 && pre_plan(L, &A, true) >= 0 && post_plan(L, &B, false) >= 0 && post_plan(L, &B, true) >= 0;
+}
+
 static int nk_grid(int rows, int R, int smem_bytes) {
   int blocks = (rows + R - 1) / R;
   int per_sm = kSmemLimit / (smem_bytes + 1024);

@@ -190,6 +190,18 @@ int gj_mp_plan_info(const gj_mp_desc* d, int32_t* info);
 int gj_umma_selftest(int32_t m, int32_t n, int32_t k, int32_t a_major, int32_t b_major,
                      const float* a, const float* b, float* out, void* stream);
 
+/* The GEMM primitive of the generic-width node-level path (P|Q projections and node MLP of models/graphnet.py:249-271 at widths the
+ * fused node kernels do not cover, e.g. BASELINE config 5's H = 64..256), exposed for testing.  Row-major fp32 tensors:
+ *   form 0: C (M,N) = epi(A (M,K) . B (N,K)^T)      forward of a dense layer
+ *   form 1: C (M,N) = epi(A (M,K) . B (K,N))        input gradient
+ *   form 2: C (M,N) = A (K,M)^T . B (K,N)           weight gradient (split over K, fixed-order reduction; needs the workspace)
+ * epi: + bias[n] (may be NULL), + previous C if accumulate, then act: 0 none, 1 LeakyReLU(alpha), 2 multiply by
+ * (aux[m][n] > 0 ? 1 : alpha) (form 1 only); form 2 has no epilogue.  precision GJ_PREC_FP32: FFMA; GJ_PREC_BF16: tcgen05 (bf16 operands, fp32 accumulate). */
+int gj_dense_gemm(int32_t form, int32_t M, int32_t N, int32_t K, const float* A, const float* B, const float* bias, int32_t act,
+                  float alpha, const float* aux, int32_t accumulate, float* C, void* workspace, size_t workspace_bytes,
+                  int32_t precision, void* stream);
+size_t gj_dense_gemm_workspace(int32_t form, int32_t M, int32_t N, int32_t K);
+
 /* Last error message of the calling thread ("" if none). */
 const char* gj_last_error(void);
 

@@ -61,7 +61,10 @@ CASES = {
     # a batch that is not a multiple of the four (jet, j block) tasks of a tile group, larger than one wave of groups
     "default_b257": _case(30, 257, store64=False, seed=18),
     # BASELINE config 5 (deep / wide sweep): node_sizes [[H]], edge_sizes [[H, H]], 3-6 steps, latent 1-64
-    "wide128_n30": _case(30, 2, edge=[[128, 128]], node=[[128]], num_mps=3, latent=8, seed=19, store64=False, grad_stride=4),
+    # (with seed 19 every gradient upstream of the decoder's last edge network differs from float64 by the same 4e-5 in fp32 mode
+    # while other seeds give 2e-7: the signature of one pre-activation within fp32 rounding of the LeakyReLU kink, where any
+    # fp32 evaluation order picks a slope; tools/grad_err.py wide128_n30 fp32 19 shows it)
+    "wide128_n30": _case(30, 2, edge=[[128, 128]], node=[[128]], num_mps=3, latent=8, seed=119, store64=False, grad_stride=4),
     "wide256_n12": _case(12, 2, edge=[[256, 256]], node=[[256]], num_mps=3, latent=16, seed=20, store64=False, grad_stride=16),
     "wide64_mps6_n10": _case(10, 2, edge=[[64, 64]], node=[[64]], num_mps=6, latent=1, seed=21, store64=False, grad_stride=2),
     "wide128_lat64_n33": _case(33, 2, edge=[[128, 128]], node=[[128]], num_mps=4, latent=64, seed=22, store64=False,
