@@ -68,6 +68,13 @@ size_t gj_edge_bwd_tc_ws_floats(const MPLayout&);
 int gj_edge_bwd_tc(MPLayout, const float*, const float*, const float*, const float*, float*, float*, float*, float*,
                    cudaStream_t);
 int gj_umma_selftest_launch(int, int, int, int, int, const float*, const float*, float*, cudaStream_t);
+bool gj_edge3_supported(const MPLayout&);
+size_t gj_edge3_wimage_floats(const MPLayout&);
+size_t gj_edge3_fwd_ws_floats(const MPLayout&);
+size_t gj_edge3_bwd_ws_floats(const MPLayout&);
+int gj_edge_fwd3(const MPLayout&, const float*, const float*, const float*, float*, float*, float*, float*, cudaStream_t);
+int gj_edge_bwd3(const MPLayout&, const float*, const float*, const float*, const float*, float*, float*, float*, float*, float*, float*, bool,
+                 cudaStream_t);
 bool gj_node_generic_fits(const MPLayout&);
 bool gj_edge_simt_fits(MPLayout, const float*);
 bool gj_edge_tc_fits(MPLayout);
@@ -121,6 +128,10 @@ static bool tc2_path(const MPLayout& L, int precision) {
 }
 
 static bool edge_mat(const MPLayout& L, int precision);
+// the step runs the third-generation fused kernels (two-layer edge networks [H, H], H = 64 / 128: BASELINE config 5)
+static bool tc3_path(const MPLayout& L, int precision) {
+  return !edge_mat_forced() && use_tc(L, precision) && !tc2_path(L, precision) && gj_edge3_supported(L) && !gj_tc_v1_forced();
+}
 
 // Node-level work (P|Q projections, node MLP and their adjoints) as generic GEMMs (dense.cu): wherever a node-level weight
 // matrix does not fit the fused node kernels' shared-memory plans, and for wide layers (BASELINE config 5: H >= 64), where the
@@ -140,7 +151,7 @@ static bool dense_node(const MPLayout& L, int precision) {
 // kernel has a plan for (e.g. edge_sizes [[256, 256]]); GJ_EDGE_MAT=1 forces it (tests)
 static bool edge_mat(const MPLayout& L, int precision) {
   if (edge_mat_forced()) return true;
-  if (tc2_path(L, precision)) return false;
+  if (tc2_path(L, precision) || tc3_path(L, precision)) return false;
   return use_tc(L, precision) ? !gj_edge_tc_fits(L) : !gj_edge_simt_fits(L, nullptr);
 }
 
@@ -157,12 +168,13 @@ static StepWs plan_ws(const MPLayout& L, int precision, bool backward) {
   // gj_mp_step_saved_bytes() has exactly this prefix layout
   w.pq = off; off += align_floats(rows * 2 * L.E0p);
   w.wimg = w.dist = off;
-  if (tc2_path(L, precision)) {
-    w.wimg = off; off += align_floats(gj_wimage_floats());
+  if (tc2_path(L, precision) || tc3_path(L, precision)) {
+    w.wimg = off; off += align_floats(tc3_path(L, precision) ? gj_edge3_wimage_floats(L) : gj_wimage_floats());
     w.dist = off; off += align_floats(rows * (size_t)(((L.N + 31) / 32) * 32));
   }
   w.epart = off;
   if (!backward && tc2_path(L, precision)) off += align_floats(gj_fwd2_ws_floats(L));   // per-j-block partial aggregates (N > 32)
+  if (!backward && tc3_path(L, precision)) off += align_floats(gj_edge3_fwd_ws_floats(L));
   w.dpq = w.de = w.part = off;
   if (backward) {
     w.dpq = off; off += align_floats(rows * 2 * L.E0p);
@@ -173,6 +185,7 @@ static StepWs plan_ws(const MPLayout& L, int precision, bool backward) {
     if (tc2_path(L, precision) && gj_node_pre_bwd_tc_supported(L)) { const size_t q2 = gj_node_pre_bwd_tc_ws_floats(L); if (q2 > q) q = q2; }
     size_t r = use_tc(L, precision) ? gj_edge_bwd_tc_ws_floats(L) : (size_t)gj_edge_grid(L.B) * L.pV[0];
     if (tc2_path(L, precision)) { const size_t r2 = gj_bwd2_ws_floats(L); if (r2 > r) r = r2; }
+    if (tc3_path(L, precision)) { const size_t r2 = gj_edge3_bwd_ws_floats(L); if (r2 > r) r = r2; }
     if (q > p) p = q;
     if (r > p) p = r;
     if (p < 64) p = 64;
@@ -221,6 +234,7 @@ static int mp_step_fwd_impl(const gj_mp_desc* d, const float* h, const float* pa
   const bool dense = dense_node(L, d->precision);
   if ((rc = dense ? gj_dense_pre_fwd(L, h, params, pre + w.pq, d->precision, st) : gj_node_pre_fwd(L, h, params, pre + w.pq, st))) return rc;
   if (emat) rc = gj_edge_mat_fwd(L, h, ws + w.pq, params, e_out, ws + w.emat, d->precision, st);
+  else if (tc3_path(L, d->precision)) rc = gj_edge_fwd3(L, h, ws + w.pq, params, e_out, ws + w.epart, ws + w.wimg, ws + w.dist, st);
   else if (tc2) rc = gj_edge_fwd2(L, h, pre + w.pq, params, e_out, ws + w.epart, pre + w.wimg, saved ? pre + w.dist : nullptr, st, false);
   else rc = use_tc(L, d->precision) ? gj_edge_fwd_tc(L, h, ws + w.pq, params, e_out, st)
                                     : gj_edge_fwd_simt(L, h, ws + w.pq, params, e_out, st);
@@ -240,6 +254,8 @@ int gj_mp_step_launches(const gj_mp_desc* d, int backward, int with_saved) {
   const bool tc2 = tc2_path(L, d->precision);
   const int njb = (tc2 && L.N > 32) ? 1 : 0;      // per-j-block partial sums (forward: e, backward: dP)
   if (edge_mat(L, d->precision)) return gj_dense_launches(L, backward != 0) + gj_edge_mat_launches(L, backward != 0);
+  if (tc3_path(L, d->precision))      // + parameter image, pair distances, edge kernel [, j-block sum]; backward also the distance adjoint and the reduction
+    return gj_dense_launches(L, backward != 0) + 3 + (L.N > 32 ? 1 : 0) + (backward ? 2 : 0);
   if (dense_node(L, d->precision)) return gj_dense_launches(L, backward != 0) + (backward ? 2 : 1);      // + the edge kernel(s)
   if (!backward) return tc2 ? 4 + njb : 3;        // projections, [parameter image], edge kernel, [j-block sum], node MLP
   if (!tc2) return 8;
@@ -301,6 +317,8 @@ static int mp_step_bwd_impl(const gj_mp_desc* d, const float* h, const float* e,
     if ((rc = gj_dense_post_bwd(L, e, h, params, dh_out, ws + w.de, dh, dparams, ws + w.dense, d->precision, st))) return rc;
     if ((rc = gj_dense_pre_fwd(L, h, params, ws + w.pq, d->precision, st))) return rc;
     rc = emat ? gj_edge_mat_bwd(L, h, ws + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.emat, d->precision, st)
+       : tc3_path(L, d->precision) ? gj_edge_bwd3(L, h, ws + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.part, ws + w.wimg,
+                                                  ws + w.dist, false, st)
        : use_tc(L, d->precision) ? gj_edge_bwd_tc(L, h, ws + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.part, st)
                                  : gj_edge_bwd_simt(L, h, ws + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.part, st);
     if (rc) return rc;

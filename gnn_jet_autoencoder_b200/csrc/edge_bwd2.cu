@@ -834,6 +834,7 @@ __global__ void __launch_bounds__(640) pair_dist_bwd_kernel(const float* __restr
 int gj_num_sms();
 void gj_set_error(const char* fmt, ...);
 int gj_reduce_edge_partials(const MPLayout& L, const float* part, int nparts, float* dparams, cudaStream_t stream);
+int gj_pair_dist_bwd(const MPLayout& L, const float* h, const float* G, float* dh, cudaStream_t stream);
 
 // debugging aid (not part of the ABI header): stage timeline of the last traced backward launch
 extern "C" int gj_debug_read_bwd2_trace(long long* out) {
@@ -875,6 +876,28 @@ int gj_pair_dist_fwd(const MPLayout& L, const float* h, float* d, cudaStream_t s
   pair_dist_fwd_kernel<<<blocks, 256, smem, stream>>>(h, L.B, L.N, NJ32, L.cols, L.ld, L.mink, jpb, d);
   ce = cudaGetLastError();
   if (ce != cudaSuccess) { gj_set_error("pair_dist_fwd launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
+  return GJ_OK;
+}
+
+bool gj_pair_dist_bwd_fits(const MPLayout& L) { return pd_smem_bwd(L) <= 200 * 1024; }
+
+// dh += adjoint of the pair distances: G (B, N, NJ32) = dL / d(d_ij)
+int gj_pair_dist_bwd(const MPLayout& L, const float* h, const float* G, float* dh, cudaStream_t stream) {
+  const int NJ32 = ((L.N + 31) / 32) * 32;
+  const int jpb = pd_jpb(L), smem = pd_smem_bwd(L);
+  int blocks = (L.B + jpb - 1) / jpb; if (blocks > 8 * gj_num_sms()) blocks = 8 * gj_num_sms();
+  const int c4 = (L.cols + 3) >> 2, nr = (L.B < jpb ? L.B : jpb) * L.N;
+  // columns per thread: as many as still leave the CTA's rows at least ~450 work items
+  int C4 = c4 <= 1 ? 1 : c4 <= 2 ? 2 : c4 <= 4 ? 4 : 8;
+  while (C4 > 1 && nr * ((c4 + C4 - 1) / C4) < 448) C4 >>= 1;
+  int threads = (nr * ((c4 + C4 - 1) / C4) + 31) & ~31;
+  threads = threads < 128 ? 128 : (threads > 640 ? 640 : threads);
+  auto pdk = C4 == 1 ? pair_dist_bwd_kernel<1> : C4 == 2 ? pair_dist_bwd_kernel<2> : C4 == 4 ? pair_dist_bwd_kernel<4> : pair_dist_bwd_kernel<8>;
+  cudaError_t ce = cudaFuncSetAttribute(pdk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (ce != cudaSuccess) { gj_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
+  pdk<<<blocks, threads, smem, stream>>>(h, G, L.B, L.N, NJ32, L.cols, L.ld, L.mink, jpb, dh);
+  ce = cudaGetLastError();
+  if (ce != cudaSuccess) { gj_set_error("pair_dist_bwd launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   return GJ_OK;
 }
 
@@ -935,20 +958,7 @@ int gj_edge_bwd2(const MPLayout& L, const float* h, const float* pq, const float
     const size_t n4 = rows * (size_t)(L.E[0] / 4);
     sum_dp_parts_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(dp_part), (int)njb, rows, L.E[0], dpq);
   }
-  {
-    const int jpb = pd_jpb(L), smem = pd_smem_bwd(L);
-    int blocks = (L.B + jpb - 1) / jpb; if (blocks > 8 * gj_num_sms()) blocks = 8 * gj_num_sms();
-    const int c4 = (L.cols + 3) >> 2, nr = (L.B < jpb ? L.B : jpb) * L.N;
-    // columns per thread: as many as still leave the CTA's rows at least ~450 work items
-    int C4 = c4 <= 1 ? 1 : c4 <= 2 ? 2 : c4 <= 4 ? 4 : 8;
-    while (C4 > 1 && nr * ((c4 + C4 - 1) / C4) < 448) C4 >>= 1;
-    int threads = (nr * ((c4 + C4 - 1) / C4) + 31) & ~31;
-    threads = threads < 128 ? 128 : (threads > 640 ? 640 : threads);
-    auto pdk = C4 == 1 ? pair_dist_bwd_kernel<1> : C4 == 2 ? pair_dist_bwd_kernel<2> : C4 == 4 ? pair_dist_bwd_kernel<4> : pair_dist_bwd_kernel<8>;
-    ce = cudaFuncSetAttribute(pdk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (ce != cudaSuccess) { gj_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
-    pdk<<<blocks, threads, smem, stream>>>(h, G, L.B, L.N, NJ32, L.cols, L.ld, L.mink, jpb, dh);
-  }
+  if (int rc = gj_pair_dist_bwd(L, h, G, dh, stream)) return rc;
   ce = cudaGetLastError();
   if (ce != cudaSuccess) { gj_set_error("edge_bwd2 tail launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   if (mode == 2) { *part_out = part; *nparts_out = grid; return GJ_OK; }
