@@ -228,13 +228,14 @@ static int mp_step_fwd_impl(const gj_mp_desc* d, const float* h, const float* pa
   float* ws = (float*)workspace;
   const bool emat = edge_mat(L, d->precision);
   const bool tc2 = tc2_path(L, d->precision) && !emat;
-  if (saved && !tc2) { gj_set_error("%s: this step has nothing to save (gj_mp_step_saved_bytes is 0)", who); return GJ_ERR_INVALID; }
+  const bool tc3 = tc3_path(L, d->precision);
+  if (saved && !tc2 && !tc3) { gj_set_error("%s: this step has nothing to save (gj_mp_step_saved_bytes is 0)", who); return GJ_ERR_INVALID; }
   float* pre = saved ? (float*)saved : ws;      // P|Q, parameter image, pair distances: same layout in either buffer
   cudaStream_t st = (cudaStream_t)stream;
   const bool dense = dense_node(L, d->precision);
   if ((rc = dense ? gj_dense_pre_fwd(L, h, params, pre + w.pq, d->precision, st) : gj_node_pre_fwd(L, h, params, pre + w.pq, st))) return rc;
   if (emat) rc = gj_edge_mat_fwd(L, h, ws + w.pq, params, e_out, ws + w.emat, d->precision, st);
-  else if (tc3_path(L, d->precision)) rc = gj_edge_fwd3(L, h, ws + w.pq, params, e_out, ws + w.epart, ws + w.wimg, ws + w.dist, st);
+  else if (tc3) rc = gj_edge_fwd3(L, h, pre + w.pq, params, e_out, ws + w.epart, pre + w.wimg, pre + w.dist, st);
   else if (tc2) rc = gj_edge_fwd2(L, h, pre + w.pq, params, e_out, ws + w.epart, pre + w.wimg, saved ? pre + w.dist : nullptr, st, false);
   else rc = use_tc(L, d->precision) ? gj_edge_fwd_tc(L, h, ws + w.pq, params, e_out, st)
                                     : gj_edge_fwd_simt(L, h, ws + w.pq, params, e_out, st);
@@ -255,7 +256,7 @@ int gj_mp_step_launches(const gj_mp_desc* d, int backward, int with_saved) {
   const int njb = (tc2 && L.N > 32) ? 1 : 0;      // per-j-block partial sums (forward: e, backward: dP)
   if (edge_mat(L, d->precision)) return gj_dense_launches(L, backward != 0) + gj_edge_mat_launches(L, backward != 0);
   if (tc3_path(L, d->precision))      // + parameter image, pair distances, edge kernel [, j-block sum]; backward also the distance adjoint and the reduction
-    return gj_dense_launches(L, backward != 0) + 3 + (L.N > 32 ? 1 : 0) + (backward ? 2 : 0);
+    return gj_dense_launches(L, backward != 0) + 3 + (L.N > 32 ? 1 : 0) + (backward ? 2 : 0) - ((backward && with_saved) ? 4 : 0);
   if (dense_node(L, d->precision)) return gj_dense_launches(L, backward != 0) + (backward ? 2 : 1);      // + the edge kernel(s)
   if (!backward) return tc2 ? 4 + njb : 3;        // projections, [parameter image], edge kernel, [j-block sum], node MLP
   if (!tc2) return 8;
@@ -267,7 +268,7 @@ int gj_mp_step_launches(const gj_mp_desc* d, int backward, int with_saved) {
 
 size_t gj_mp_step_saved_bytes(const gj_mp_desc* d) {
   MPLayout L; const char* why;
-  if (gj_fill_arch(d, &L, &why) || !tc2_path(L, d->precision)) return 0;
+  if (gj_fill_arch(d, &L, &why) || !(tc2_path(L, d->precision) || tc3_path(L, d->precision))) return 0;
   const StepWs w = plan_ws(L, d->precision, false);
   return w.epart * sizeof(float);      // the prefix P|Q, parameter image, pair distances
 }
@@ -299,7 +300,8 @@ static int mp_step_bwd_impl(const gj_mp_desc* d, const float* h, const float* e,
   float* ws = (float*)workspace;
   const bool emat = edge_mat(L, d->precision);
   const bool tc2 = tc2_path(L, d->precision) && !emat;
-  if (saved && !tc2) { gj_set_error("%s: this step has nothing saved (gj_mp_step_saved_bytes is 0)", who); return GJ_ERR_INVALID; }
+  const bool tc3 = tc3_path(L, d->precision);
+  if (saved && !tc2 && !tc3) { gj_set_error("%s: this step has nothing saved (gj_mp_step_saved_bytes is 0)", who); return GJ_ERR_INVALID; }
   float* pre = saved ? (float*)saved : ws;      // read-only when it is the caller's saved buffer
   if (node_tail_fused(L, d->precision) && !emat) {
     // node MLP adjoint (also clears dP|dQ), P|Q unless saved, edge adjoint, projections' adjoint, one reduction of all partials
@@ -315,10 +317,10 @@ static int mp_step_bwd_impl(const gj_mp_desc* d, const float* h, const float* e,
   const bool dense = dense_node(L, d->precision);
   if (dense) {      // generic-GEMM node level (dense.cu) around the edge adjoint
     if ((rc = gj_dense_post_bwd(L, e, h, params, dh_out, ws + w.de, dh, dparams, ws + w.dense, d->precision, st))) return rc;
-    if ((rc = gj_dense_pre_fwd(L, h, params, ws + w.pq, d->precision, st))) return rc;
-    rc = emat ? gj_edge_mat_bwd(L, h, ws + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.emat, d->precision, st)
-       : tc3_path(L, d->precision) ? gj_edge_bwd3(L, h, ws + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.part, ws + w.wimg,
-                                                  ws + w.dist, false, st)
+    if (!saved && (rc = gj_dense_pre_fwd(L, h, params, pre + w.pq, d->precision, st))) return rc;
+    rc = emat ? gj_edge_mat_bwd(L, h, pre + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.emat, d->precision, st)
+       : tc3 ? gj_edge_bwd3(L, h, pre + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.part, pre + w.wimg, pre + w.dist,
+                            saved != nullptr, st)
        : use_tc(L, d->precision) ? gj_edge_bwd_tc(L, h, ws + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.part, st)
                                  : gj_edge_bwd_simt(L, h, ws + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.part, st);
     if (rc) return rc;

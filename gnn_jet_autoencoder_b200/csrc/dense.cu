@@ -109,42 +109,50 @@ constexpr int TCG_PAD = 16;      // bytes added to every slab stride: the 8 slab
 // Operand tile (T rows of the MN dimension x 64 k) -> bf16 slabs.
 //   k contiguous in memory (K-major operand):  element (mn, k) at (k / 8) SK + mn 16 + (k % 8) 2,  SK = T 16 + pad
 //   mn contiguous in memory (MN-major operand): element (mn, k) at (mn / 8) SM + k 16 + (mn % 8) 2, SM = 64 16 + pad
+// Loads are issued in batches of four units (eight 16-byte loads in flight per thread) before anything is converted: a
+// load -> convert -> store loop waits for every load in turn (measured: 14 us per 64 KB chunk).
+__device__ __forceinline__ uint4 tcg_pack8(const float4& a, const float4& b) {
+  return make_uint4(bf2_as_u32(__floats2bfloat162_rn(a.x, a.y)), bf2_as_u32(__floats2bfloat162_rn(a.z, a.w)),
+                    bf2_as_u32(__floats2bfloat162_rn(b.x, b.y)), bf2_as_u32(__floats2bfloat162_rn(b.z, b.w)));
+}
 __device__ __forceinline__ void stage_tile(uint8_t* dst, const float* __restrict__ p, long long s_mn, long long s_k, int lim_mn, int lim_k,
                                            int mn0, int k0, int k_hi, int T, bool kmajor, int tid) {
   const int klim = min(lim_k, k_hi);
-  if (kmajor) {
-    const int SK = T * 16 + TCG_PAD;
-    const bool vec = s_k == 1 && (s_mn & 3) == 0 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0) && ((k0 & 3) == 0);
-    for (int u = tid; u < T * 8; u += 128) {
-      const int mn = u >> 3, k8 = u & 7, gm = mn0 + mn, gk = k0 + 8 * k8;
-      float v[8];
-      if (gm < lim_mn && vec && gk + 7 < klim) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(p + gm * s_mn + gk)), b = __ldg(reinterpret_cast<const float4*>(p + gm * s_mn + gk) + 1);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-      } else {
+  const int SK = T * 16 + TCG_PAD, SM = TCG_KC * 16 + TCG_PAD, T8 = T >> 3;
+  const int total = T * 8;      // units of 8 elements: K-major (mn, k8), MN-major (k, m8)
+  // element (i, c) of a unit at p[i * s_row + (c0 + c) * s_col]: i = the strided index, c = the 8 contiguous ones
+  const long long s_row = kmajor ? s_mn : s_k, s_col = kmajor ? s_k : s_mn;
+  const int lim_row = kmajor ? lim_mn : klim, lim_col = kmajor ? klim : lim_mn;
+  const int row0 = kmajor ? mn0 : k0, col0 = kmajor ? k0 : mn0;
+  const int cdiv = kmajor ? 8 : T8;      // units per row
+  const bool vec = s_col == 1 && (s_row & 3) == 0 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0) && ((col0 & 3) == 0);
+  for (int u0 = tid; u0 < total; u0 += 4 * 128) {
+    float4 a[4], b[4];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = (gm < lim_mn && gk + q < klim) ? __ldg(p + gm * s_mn + (gk + q) * s_k) : 0.f;
+    for (int q = 0; q < 4; ++q) {
+      const int u = u0 + q * 128;
+      a[q] = make_float4(0.f, 0.f, 0.f, 0.f); b[q] = a[q];
+      if (u < total) {
+        const int i = u / cdiv, c8 = u - i * cdiv, gi = row0 + i, gc = col0 + 8 * c8;
+        if (gi < lim_row) {
+          const float* src = p + gi * s_row + gc * s_col;
+          if (vec && gc + 7 < lim_col) { a[q] = __ldg(reinterpret_cast<const float4*>(src)); b[q] = __ldg(reinterpret_cast<const float4*>(src) + 1); }
+          else {
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = gc + e < lim_col ? __ldg(src + e * s_col) : 0.f;
+            a[q] = make_float4(v[0], v[1], v[2], v[3]); b[q] = make_float4(v[4], v[5], v[6], v[7]);
+          }
+        }
       }
-      *reinterpret_cast<uint4*>(dst + k8 * SK + mn * 16) =
-          make_uint4(bf2_as_u32(__floats2bfloat162_rn(v[0], v[1])), bf2_as_u32(__floats2bfloat162_rn(v[2], v[3])),
-                     bf2_as_u32(__floats2bfloat162_rn(v[4], v[5])), bf2_as_u32(__floats2bfloat162_rn(v[6], v[7])));
     }
-  } else {
-    const int SM = TCG_KC * 16 + TCG_PAD, T8 = T >> 3;
-    const bool vec = s_mn == 1 && (s_k & 3) == 0 && ((reinterpret_cast<uintptr_t>(p) & 15) == 0) && ((mn0 & 3) == 0);
-    for (int u = tid; u < T8 * TCG_KC; u += 128) {
-      const int k = u / T8, m8 = u - k * T8, gk = k0 + k, gm = mn0 + 8 * m8;
-      float v[8];
-      if (gk < klim && vec && gm + 7 < lim_mn) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(p + gk * s_k + gm)), b = __ldg(reinterpret_cast<const float4*>(p + gk * s_k + gm) + 1);
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-      } else {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = (gk < klim && gm + q < lim_mn) ? __ldg(p + gk * s_k + (gm + q) * s_mn) : 0.f;
+    for (int q = 0; q < 4; ++q) {
+      const int u = u0 + q * 128;
+      if (u < total) {
+        const int i = u / cdiv, c8 = u - i * cdiv;
+        *reinterpret_cast<uint4*>(dst + (kmajor ? c8 * SK + i * 16 : c8 * SM + i * 16)) = tcg_pack8(a[q], b[q]);
       }
-      *reinterpret_cast<uint4*>(dst + m8 * SM + k * 16) =
-          make_uint4(bf2_as_u32(__floats2bfloat162_rn(v[0], v[1])), bf2_as_u32(__floats2bfloat162_rn(v[2], v[3])),
-                     bf2_as_u32(__floats2bfloat162_rn(v[4], v[5])), bf2_as_u32(__floats2bfloat162_rn(v[6], v[7])));
     }
   }
 }
@@ -198,9 +206,14 @@ __global__ void __launch_bounds__(128) gemm_tc_kernel(const GemmP P, int NT, int
     }
   }
   if (nchunks > 0) { mbar_wait(bars + 2, 0u); tc_fence_after(); }
-  // ---- epilogue: thread = output row ----
-  const int m = m0 + warp * 32 + lane;
+  // ---- epilogue: TMEM (thread = row) -> per-warp shared-memory transpose -> coalesced 16-byte global accesses (a warp instruction
+  //      covers eight 64-byte row segments; a thread walking its own row would touch 32 lines per store) ----
   const uint32_t lane_base = tmem_base + ((uint32_t)(warp * 32) << 16);
+  float* scr = reinterpret_cast<float*>(stage0) + warp * (16 * 33);      // [16 columns][33]; the operand stages are free: every MMA has completed
+  const bool vec = (P.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 && (n0 & 3) == 0 &&
+                   (!P.aux || ((P.ldaux & 3) == 0 && (reinterpret_cast<uintptr_t>(P.aux) & 15) == 0)) &&
+                   (!P.bias || (reinterpret_cast<uintptr_t>(P.bias) & 15) == 0);
+  const int rsub = lane >> 2, cq = (lane & 3) * 4;
   for (int c0 = 0; c0 < NT; c0 += 16) {
     uint32_t v[16];
     if (nchunks > 0) { tmem_ld16_u(lane_base + c0, v); tmem_ld_wait(); tmem_pin16(v); }
@@ -209,7 +222,35 @@ __global__ void __launch_bounds__(128) gemm_tc_kernel(const GemmP P, int NT, int
       for (int q = 0; q < 16; ++q) v[q] = 0u;
     }
 #pragma unroll
-    for (int q = 0; q < 16; ++q) epilogue_store(P, C, m, n0 + c0 + q, __uint_as_float(v[q]));
+    for (int q = 0; q < 16; ++q) scr[q * 33 + lane] = __uint_as_float(v[q]);
+    __syncwarp();
+    const int n = n0 + c0 + cq;
+    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (vec && P.bias && n + 3 < P.Cn) bias4 = __ldg(reinterpret_cast<const float4*>(P.bias + n));
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int r = it * 8 + rsub, m = m0 + warp * 32 + r;
+      float4 o = make_float4(scr[cq * 33 + r], scr[(cq + 1) * 33 + r], scr[(cq + 2) * 33 + r], scr[(cq + 3) * 33 + r]);
+      if (vec && n + 3 < P.Cn) {
+        if (m < P.Cm) {
+          float4* dst = reinterpret_cast<float4*>(C + m * P.ldc + n);
+          o.x += bias4.x; o.y += bias4.y; o.z += bias4.z; o.w += bias4.w;
+          if (P.accumulate) { const float4 c = *dst; o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w; }
+          if (P.act == 1) {
+            o.x = o.x > 0.f ? o.x : P.alpha * o.x; o.y = o.y > 0.f ? o.y : P.alpha * o.y;
+            o.z = o.z > 0.f ? o.z : P.alpha * o.z; o.w = o.w > 0.f ? o.w : P.alpha * o.w;
+          } else if (P.act == 2) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(P.aux + m * P.ldaux + n));
+            o.x *= a.x > 0.f ? 1.f : P.alpha; o.y *= a.y > 0.f ? 1.f : P.alpha; o.z *= a.z > 0.f ? 1.f : P.alpha; o.w *= a.w > 0.f ? 1.f : P.alpha;
+          }
+          *dst = o;
+        }
+      } else {
+        epilogue_store(P, C, m, n, o.x); epilogue_store(P, C, m, n + 1, o.y);
+        epilogue_store(P, C, m, n + 2, o.z); epilogue_store(P, C, m, n + 3, o.w);
+      }
+    }
+    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();

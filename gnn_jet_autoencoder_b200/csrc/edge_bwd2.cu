@@ -711,29 +711,44 @@ __global__ void __launch_bounds__(256) pair_dist_fwd_kernel(const float* __restr
       pd_smem[r * hs + k] = k < cols ? __ldg(h + ((size_t)b0 * N + r) * ld + k) : 0.f;
     }
     __syncthreads();
-    for (int r = warp; r < nj * N; r += 8) {
-      const int jl = r / N;
-      const float4* hi = reinterpret_cast<const float4*>(pd_smem + r * hs);
+    // a warp owns four consecutive i rows of a jet at a time (lane = j): h_j is read once per four pairs
+    const int n4 = (N + 3) >> 2;
+    for (int item = warp; item < nj * n4; item += 8) {
+      const int jl = item / n4, i0 = (item - jl * n4) * 4;
+      const float4* hi[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) hi[u] = reinterpret_cast<const float4*>(pd_smem + (jl * N + min(i0 + u, N - 1)) * hs);
       for (int j = lane; j < NJ32; j += 32) {
-        float acc = 0.f;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
         if (j < N) {
           const float4* hj = reinterpret_cast<const float4*>(pd_smem + (jl * N + j) * hs);
           if (mink) {      // width 4 only: x0^2 - x1^2 - x2^2 - x3^2 (graphnet.py:320-323)
-            const float4 a = hi[0], b = hj[0];
-            const float x0 = b.x - a.x, x1 = b.y - a.y, x2 = b.z - a.z, x3 = b.w - a.w;
-            acc = x0 * x0 - x1 * x1 - x2 * x2 - x3 * x3;
+            const float4 b = hj[0];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float4 a = hi[u][0];
+              const float x0 = b.x - a.x, x1 = b.y - a.y, x2 = b.z - a.z, x3 = b.w - a.w;
+              acc[u] = x0 * x0 - x1 * x1 - x2 * x2 - x3 * x3;
+            }
           } else {
-            float a0 = 0.f, a1 = 0.f;
+            float a1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 2
             for (int k = 0; k < c4; ++k) {
-              const float4 a = hi[k], b = hj[k];
-              const float x0 = b.x - a.x, x1 = b.y - a.y, x2 = b.z - a.z, x3 = b.w - a.w;
-              a0 = fmaf(x0, x0, a0); a1 = fmaf(x1, x1, a1); a0 = fmaf(x2, x2, a0); a1 = fmaf(x3, x3, a1);
+              const float4 b = hj[k];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float4 a = hi[u][k];
+                const float x0 = b.x - a.x, x1 = b.y - a.y, x2 = b.z - a.z, x3 = b.w - a.w;
+                acc[u] = fmaf(x0, x0, acc[u]); a1[u] = fmaf(x1, x1, a1[u]); acc[u] = fmaf(x2, x2, acc[u]); a1[u] = fmaf(x3, x3, a1[u]);
+              }
             }
-            acc = a0 + a1;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc[u] += a1[u];
           }
         }
-        d[((size_t)b0 * N + r) * NJ32 + j] = acc;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (i0 + u < N) d[((size_t)(b0 + jl) * N + i0 + u) * NJ32 + j] = acc[u];
       }
     }
   }
