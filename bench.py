@@ -4,8 +4,13 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--num-nodes 30|150]
                     [--batch B] [--precision bf16|fp32]
 
-One JSON line on stdout (rank 0).  Workload: reference CLI-default architecture, synthetic JetNet-shaped
+One JSON line on stdout (rank 0).  Headline workload: reference CLI-default architecture, synthetic JetNet-shaped
 jets, 4096 jets per GPU (BASELINE config 2 at N=1; 8 GPUs = config 4's 32768-jet global batch), weak scaling.
+The same line carries a "configs" object with the other BASELINE configurations measured in the same run: config 3
+(N=150, B=2048), config 2 in the fp32 parity mode, the CPU forward of config 1 and the CPU N=150 train step, the
+reference op sequence (oracle/torch_port.py) on the same GPU, config 4 as specified (global batch 32768: one GPU as the
+denominator at --gpus 1, sharded B/G per rank at --gpus G, "strong") and a few points of config 5's deep / wide sweep;
+at --gpus G > 1 also "dp_parity" (parameters bit-identical across ranks, G-rank gradient = one-rank gradient).
 "value" times the step with the batch resident in HBM (CUDA events, L2 flushed between steps, max over
 ranks); "e2e" goes through the public ``GNNAETrainer.step`` with a pinned host batch per step and a
 device->host read of the loss.  ``--impl reference`` times the CPU PyTorch restatement of the reference's
@@ -42,29 +47,11 @@ def measured_peaks():
 # CPU baseline: torch-CPU restatement of the reference step on a bounded sample
 # --------------------------------------------------------------------------------------------------
 def cpu_reference_step_rate(num_nodes, sample_jets, steps, warmup, budget_s=25.0):
-    import numpy as np
     import torch
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import torch_port as TP
-    from golden_cases import _linear  # noqa: F401  (test-infrastructure initialiser)
-    import gnnae_oracle as O
-    from gnn_jet_autoencoder_b200.config import DEFAULT_ARCH as A
     from gnn_jet_autoencoder_b200.trainer import synthetic_jets
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    rng = np.random.default_rng(0)
-    enc_cfg = dict(num_nodes=num_nodes, input_node_size=A["vec_dims"], latent_node_size=A["latent_node_size"],
-                   node_sizes=A["node_sizes"], edge_sizes=A["edge_sizes"], num_mps=A["num_mps"], alphas=A["alphas"],
-                   latent_map=A["latent_map"])
-    dec_cfg = dict(enc_cfg, output_node_size=A["vec_dims"])
-    ep = O.init_graphnet_params(rng, A["vec_dims"], A["latent_node_size"], A["node_sizes"], A["edge_sizes"], A["num_mps"],
-                                prefix="encoder.", dtype=np.float32)
-    h0 = A["node_sizes"][0][0]
-    dp = {}
-    dp["linear.weight"], dp["linear.bias"] = _linear(rng, num_nodes * h0, A["latent_node_size"])
-    dp.update(O.init_graphnet_params(rng, h0, A["vec_dims"], A["node_sizes"], A["edge_sizes"], A["num_mps"],
-                                     prefix="decoder.", dtype=np.float32))
-    step = TP.TorchTrainStep(TP.make_params(ep), TP.make_params(dp), enc_cfg, dec_cfg)
+    step, *_ = _port_step(num_nodes, torch.device("cpu"))
     x = torch.from_numpy(synthetic_jets(sample_jets, num_nodes, seed=1234))
     for _ in range(max(1, warmup)):
         step.step(x)
@@ -161,6 +148,169 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+
+# --------------------------------------------------------------------------------------------------
+# the other BASELINE configurations, measured in the same run ("configs" of the JSON line)
+# --------------------------------------------------------------------------------------------------
+def _time_trainer(tr, host, steps, warmup, flush, barrier=None, rank_max=None):
+    """ms per step with the batch resident in HBM (CUDA events per step, L2 flushed in between)."""
+    import torch
+    tr.load_batch(host)
+    for _ in range(max(warmup, 3)):
+        tr.compute_gradients()
+        tr.apply_gradients()
+    (barrier or torch.cuda.synchronize)()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for s, e in ev:
+        flush.fill_(1)
+        s.record()
+        tr.compute_gradients()
+        tr.apply_gradients()
+        e.record()
+    (barrier or torch.cuda.synchronize)()
+    ms = sum(s.elapsed_time(e) for s, e in ev)
+    return (rank_max(ms) if rank_max else ms) / steps
+
+
+def _train_config(N, B, precision, dev, flush, steps, arch=None, group=None, world=1, barrier=None, rank_max=None, seed=1234):
+    import torch
+    from gnn_jet_autoencoder_b200 import GNNAETrainer, synthetic_jets
+    from gnn_jet_autoencoder_b200.config import DEFAULT_ARCH, build_models, train_flops_per_jet
+    arch = arch or DEFAULT_ARCH
+    enc, dec = build_models(N, arch, device=dev, precision=precision, seed=0)
+    tr = GNNAETrainer(enc, dec, batch_size=B, process_group=group)
+    host = torch.from_numpy(synthetic_jets(B, N, seed=seed)).pin_memory()
+    ms = _time_trainer(tr, host, steps, 3, flush, barrier, rank_max)
+    value = world * B / (ms * 1e-3)
+    peaks = measured_peaks()
+    tf = value / world * train_flops_per_jet(N, arch) / 1e12
+    out = {"value": value, "unit": UNIT, "ms_per_step": ms, "num_nodes": N, "per_gpu_batch": B, "global_batch": B * world,
+           "dtype": "bf16" if precision == "bf16" else "fp32",
+           "step_roofline_frac": tf / peaks["sustained"], "tflops_per_gpu": tf}
+    del tr, enc, dec
+    torch.cuda.empty_cache()
+    return out
+
+
+def _cpu_forward_config1(budget_s=8.0):
+    """BASELINE config 1: encoder + decoder forward, N=30, B=256, fp32, no_grad, on the host cores (reference op sequence)."""
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch_port as TP
+    step, enc_cfg, dec_cfg, ep, dp = _port_step(30, torch.device("cpu"))
+    x = torch.from_numpy(__import__("gnn_jet_autoencoder_b200").synthetic_jets(256, 30, seed=1234))
+    with torch.no_grad():
+        for _ in range(2):
+            TP.decoder_forward(TP.encoder_forward(x, step.enc_p, enc_cfg), step.dec_p, dec_cfg)
+        t0, n = time.perf_counter(), 0
+        while n < 5 or (time.perf_counter() - t0 < budget_s and n < 20):
+            TP.decoder_forward(TP.encoder_forward(x, step.enc_p, enc_cfg), step.dec_p, dec_cfg)
+            n += 1
+        dt = time.perf_counter() - t0
+    return {"value": n * 256 / dt, "unit": "jets/s (forward only)", "cores": os.cpu_count() or 1, "kind": "port",
+            "sample": f"{n} forwards of 256 jets (N=30), oracle/torch_port.py, torch CPU fp32, {dt:.1f} s"}
+
+
+def _port_step(num_nodes, device):
+    """The reference's train step restated with stock torch ops (oracle/torch_port.py) with the CLI-default architecture."""
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch_port as TP
+    from golden_cases import _linear
+    import gnnae_oracle as O
+    from gnn_jet_autoencoder_b200.config import DEFAULT_ARCH as A
+    rng = np.random.default_rng(0)
+    enc_cfg = dict(num_nodes=num_nodes, input_node_size=A["vec_dims"], latent_node_size=A["latent_node_size"],
+                   node_sizes=A["node_sizes"], edge_sizes=A["edge_sizes"], num_mps=A["num_mps"], alphas=A["alphas"],
+                   latent_map=A["latent_map"])
+    dec_cfg = dict(enc_cfg, output_node_size=A["vec_dims"])
+    ep = O.init_graphnet_params(rng, A["vec_dims"], A["latent_node_size"], A["node_sizes"], A["edge_sizes"], A["num_mps"],
+                                prefix="encoder.", dtype=np.float32)
+    h0 = A["node_sizes"][0][0]
+    dp = {}
+    dp["linear.weight"], dp["linear.bias"] = _linear(rng, num_nodes * h0, A["latent_node_size"])
+    dp.update(O.init_graphnet_params(rng, h0, A["vec_dims"], A["node_sizes"], A["edge_sizes"], A["num_mps"],
+                                     prefix="decoder.", dtype=np.float32))
+    mk = lambda d: {k: torch.tensor(v, dtype=torch.float32, device=device, requires_grad=True) for k, v in d.items()}
+    return TP.TorchTrainStep(mk(ep), mk(dp), enc_cfg, dec_cfg), enc_cfg, dec_cfg, ep, dp
+
+
+def _gpu_reference(dev, num_nodes=30):
+    """The reference's op sequence (materialised (B,N,N,2H+1) tensor, autograd, two Adams) with stock torch CUDA ops on the same
+    GPU, fp32, at the largest power-of-two batch <= 4096 that fits (11.3 MB of saved activations per jet at N=30)."""
+    import torch
+    from gnn_jet_autoencoder_b200 import synthetic_jets
+    B = 4096 if num_nodes <= 32 else 64
+    while B >= 16:
+        try:
+            step, *_ = _port_step(num_nodes, dev)
+            x = torch.from_numpy(synthetic_jets(B, num_nodes, seed=1234)).to(dev)
+            for _ in range(2):
+                step.step(x)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            n = 5
+            for _ in range(n):
+                step.step(x)
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / n
+            del step, x
+            torch.cuda.empty_cache()
+            return {"value": B / dt, "unit": UNIT, "ms_per_step": dt * 1e3, "batch": B, "num_nodes": num_nodes, "dtype": "fp32",
+                    "what": "oracle/torch_port.py: the reference's op sequence on stock torch CUDA kernels (cuBLAS SIMT fp32 + elementwise), "
+                            "same B200, wall clock around step() incl. its loss.item() sync"}
+        except torch.cuda.OutOfMemoryError:
+            torch.cuda.empty_cache()
+            B //= 2
+    return {"unavailable": "out of memory at every batch size tried"}
+
+
+def _sweep_points(dev, flush, world, group, barrier, rank_max, N=30, B=2048):
+    """A few members of BASELINE config 5 (num_mps 3-6, hidden 64-256 with node_sizes [[H]] / edge_sizes [[H, H]], latent 1-64)."""
+    from gnn_jet_autoencoder_b200.config import DEFAULT_ARCH
+    out = []
+    for num_mps, H, latent in [(3, 64, 8), (6, 64, 1), (3, 128, 8), (4, 128, 64), (3, 256, 16)]:
+        arch = dict(DEFAULT_ARCH, edge_sizes=[[H, H]], node_sizes=[[H]], num_mps=num_mps, latent_node_size=latent)
+        try:
+            r = _train_config(N, B if H < 256 else B // 4, "bf16", dev, flush, 4, arch=arch, group=group, world=world, barrier=barrier,
+                              rank_max=rank_max)
+            out.append(dict(num_mps=num_mps, hidden=H, latent=latent, **{k: r[k] for k in ("value", "ms_per_step", "per_gpu_batch",
+                                                                                           "step_roofline_frac")}))
+        except Exception as ex:      # widths the kernels do not cover are reported, not hidden
+            out.append(dict(num_mps=num_mps, hidden=H, latent=latent, error=f"{type(ex).__name__}: {str(ex)[:120]}"))
+    return out
+
+
+def _dp_parity(dev, world, rank, precision):
+    """G-rank data parallelism against one rank on the concatenated batch: the all-reduced flat gradient of a small sharded batch,
+    and (by the caller) bit-identical parameters after the timed steps."""
+    import torch
+    import torch.distributed as dist
+    from gnn_jet_autoencoder_b200 import GNNAETrainer, synthetic_jets
+    from gnn_jet_autoencoder_b200.config import DEFAULT_ARCH, build_models
+    from gnn_jet_autoencoder_b200.trainer import allreduce_flat_, shard_range
+    per, N = 8, 30
+    xg = torch.from_numpy(synthetic_jets(per * world, N, seed=77))
+    lo, hi = shard_range(per * world, rank, world)
+    enc, dec = build_models(N, DEFAULT_ARCH, device=dev, precision=precision, seed=0)
+    tr = GNNAETrainer(enc, dec, batch_size=hi - lo, use_cuda_graph=False)
+    tr.load_batch(xg[lo:hi])
+    tr.compute_gradients()
+    allreduce_flat_(tr.grad)
+    g_dp = tr.grad.clone()
+    err = None
+    if rank == 0:
+        enc1, dec1 = build_models(N, DEFAULT_ARCH, device=dev, precision=precision, seed=0)
+        tr1 = GNNAETrainer(enc1, dec1, batch_size=per * world, use_cuda_graph=False)
+        tr1.load_batch(xg)
+        tr1.compute_gradients()
+        torch.cuda.synchronize()
+        err = float((g_dp - tr1.grad).norm() / tr1.grad.norm())
+    dist.barrier()
+    return err
+
 # --------------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------------
@@ -251,6 +401,41 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
 
+    # ---- the other BASELINE configurations ("configs") and the data-parallel parity check ----
+    configs, dp_parity = {}, None
+    if world > 1:
+        # parameters after the timed steps: bit-identical on every rank (same all-reduced gradient, same fused Adam)
+        ref = tr.flat.clone()
+        dist.broadcast(ref, 0)
+        same = torch.tensor([1.0 if torch.equal(ref, tr.flat) else 0.0], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        err = _dp_parity(dev, world, rank, args.precision)
+        dp_parity = {"params_bit_identical_across_ranks": bool(same.item() == 1.0), "grad_rel_err_vs_one_rank": err,
+                     "what": f"8 jets per rank, N=30: all-reduced {world}-rank flat gradient vs one rank on the concatenated batch"}
+    d2h_bytes = tr.stats_host.numel() * 4
+    if not args.no_configs and N == 30 and not args.batch:
+        del tr
+        torch.cuda.empty_cache()
+        if world > 1:      # config 4 as specified: fixed global batch 32768, B/G jets per rank (strong scaling)
+            r = _train_config(30, 32768 // world, args.precision, dev, flush, max(4, args.steps // 2), world=world, barrier=barrier,
+                              rank_max=rank_max, seed=1234 + rank)
+            r["scaling"] = "strong"
+            configs["config4_global32768"] = r
+        if world in (1, 8):
+            configs["config5_sweep"] = {"points": _sweep_points(dev, flush, world, None, barrier, rank_max),
+                                        "note": "node_sizes [[H]], edge_sizes [[H, H]], N=30, 2048 jets per GPU (512 at H=256), bf16 mode; "
+                                                "roofline fraction on the dense-formulation FLOPs"}
+        if world == 1:
+            configs["config3_n150_b2048"] = _train_config(150, 2048, "bf16", dev, flush, 6)
+            configs["config2_fp32_mode"] = _train_config(30, 4096, "fp32", dev, flush, 4)
+            configs["config4_global32768"] = dict(_train_config(30, 32768, args.precision, dev, flush, 4), scaling="strong",
+                                                  note="one GPU: the denominator of config 4's 2/4/8-GPU strong scaling")
+            configs["gpu_reference"] = _gpu_reference(dev)
+            if not args.no_cpu_baseline:
+                configs["config1_cpu_forward"] = _cpu_forward_config1()
+                cb150, _ = cpu_reference_step_rate(150, 16, steps=3, warmup=1, budget_s=15.0)
+                configs["cpu_train_n150_b16"] = cb150
+
     if rank == 0:
         flops_jet = train_flops_per_jet(N, DEFAULT_ARCH)
         step_tflops = value / world * flops_jet / 1e12          # per GPU
@@ -260,7 +445,7 @@ def run_ours(args):
             "dtype": "bf16" if args.precision == "bf16" else "fp32", "data": "synthetic",
             "config": workload_config(args, B, world),
             "e2e": {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": B * N * 3 * 4, "d2h_bytes_per_step": tr.stats_host.numel() * 4,
+                    "h2d_bytes_per_step": B * N * 3 * 4, "d2h_bytes_per_step": d2h_bytes,
                     "api": "GNNAETrainer.step(pinned host batch) -> float loss"},
             "gpu_launches": launches,
             "clocks": clocks,
@@ -274,7 +459,10 @@ def run_ours(args):
                               "peak_source": peaks["source"] + ", sustained", "note": "whole train step, per GPU, edge-MLP "
                               "dense-formulation FLOPs (3 x forward); padding and recomputation not counted"},
             "last_loss": last,
+            "configs": configs,
         }
+        if dp_parity is not None:
+            line["dp_parity"] = dp_parity
         if world == 1 and not args.no_cpu_baseline:
             sample = args.cpu_sample or (256 if N <= 32 else 16)
             line["cpu_baseline"], _ = cpu_reference_step_rate(N, sample, steps=8, warmup=1, budget_s=20.0)
@@ -284,10 +472,17 @@ def run_ours(args):
 
 
 def kernel_traffic(args, B, N):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the round's
-    `ncu --set full` capture (profiles/r01_edge_bwd2_ncu.txt: 73.85 MB read + 12.46 MB written at B=4096, N=30, bf16);
-    null for workloads that were not captured."""
-    return 86.3e6 if (args.precision == "bf16" and B == 4096 and N == 30) else None
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, read from the committed summary of
+    the `ncu --set full` capture (profiles/kernel_traffic.json, written by tools/ncu_summary.py from the .ncu-rep) -- only if
+    that capture was taken at the shape and precision of THIS run; null otherwise."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "kernel_traffic.json")) as f:
+            t = json.load(f)["edge_bwd2_kernel"]
+        if t["B"] == B and t["N"] == N and t["precision"] == args.precision:
+            return float(t["dram_bytes_read"]) + float(t["dram_bytes_write"])
+    except Exception:
+        pass
+    return None
 
 
 def time_dominant_kernel(tr, args, reps=20):
@@ -348,6 +543,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("GNNJET_PRECISION", "bf16"), choices=["bf16", "fp32"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the extra BASELINE configurations of the 'configs' object")
     ap.add_argument("--cpu-sample", type=int, default=0, help="jets per CPU-baseline step")
     args = ap.parse_args()
     if args.impl == "reference":
