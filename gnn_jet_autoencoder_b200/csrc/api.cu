@@ -85,8 +85,10 @@ int gj_edge_mat_bwd(const MPLayout&, const float*, const float*, const float*, c
 size_t gj_dense_ws_floats(const MPLayout&, bool);
 int gj_dense_launches(const MPLayout&, bool);
 int gj_dense_pre_fwd(const MPLayout&, const float*, const float*, float*, int, cudaStream_t);
-int gj_dense_post_fwd(const MPLayout&, const float*, const float*, const float*, float*, float*, int, cudaStream_t);
-int gj_dense_post_bwd(const MPLayout&, const float*, const float*, const float*, const float*, float*, float*, float*, float*, int, cudaStream_t);
+size_t gj_dense_ysave_floats(const MPLayout&);
+int gj_dense_post_fwd(const MPLayout&, const float*, const float*, const float*, float*, float*, float*, int, cudaStream_t);
+int gj_dense_post_bwd(const MPLayout&, const float*, const float*, const float*, const float*, float*, float*, float*, float*, const float*, int,
+                      cudaStream_t);
 int gj_dense_pre_bwd(const MPLayout&, const float*, const float*, const float*, float*, float*, float*, int, cudaStream_t);
 void gj_tc_plan_info(MPLayout, int*);
 int gj_chamfer_launch(int, int, int, int, int, float, float, const float*, const float*, float*, float*, float*, cudaStream_t);
@@ -117,7 +119,7 @@ size_t gj_mp_param_count(const gj_mp_desc* d) {
 static size_t align_floats(size_t n) { return (n + 63) & ~(size_t)63; }   // keep every region 256-byte aligned
 
 struct StepWs {   // offsets in floats
-  size_t pq, dpq, de, part, part_post, part_pre, epart, wimg, dist, dense, emat, total;
+  size_t pq, dpq, de, part, part_post, part_pre, epart, wimg, dist, ysave, dense, emat, total;
 };
 
 static bool use_tc(const MPLayout& L, int precision) { return precision == GJ_PREC_BF16 && L.Le > 1; }
@@ -172,6 +174,8 @@ static StepWs plan_ws(const MPLayout& L, int precision, bool backward) {
     w.wimg = off; off += align_floats(tc3_path(L, precision) ? gj_edge3_wimage_floats(L) : gj_wimage_floats());
     w.dist = off; off += align_floats(rows * (size_t)(((L.N + 31) / 32) * 32));
   }
+  w.ysave = off;
+  if (tc3_path(L, precision)) off += align_floats(gj_dense_ysave_floats(L));      // node-MLP activations (the saved prefix ends here)
   w.epart = off;
   if (!backward && tc2_path(L, precision)) off += align_floats(gj_fwd2_ws_floats(L));   // per-j-block partial aggregates (N > 32)
   if (!backward && tc3_path(L, precision)) off += align_floats(gj_edge3_fwd_ws_floats(L));
@@ -240,7 +244,7 @@ static int mp_step_fwd_impl(const gj_mp_desc* d, const float* h, const float* pa
   else rc = use_tc(L, d->precision) ? gj_edge_fwd_tc(L, h, ws + w.pq, params, e_out, st)
                                     : gj_edge_fwd_simt(L, h, ws + w.pq, params, e_out, st);
   if (rc) return rc;
-  if (dense) return gj_dense_post_fwd(L, e_out, h, params, h_out, ws + w.dense, d->precision, st);
+  if (dense) return gj_dense_post_fwd(L, e_out, h, params, h_out, ws + w.dense, (saved && tc3) ? pre + w.ysave : nullptr, d->precision, st);
   return gj_node_post_fwd(L, e_out, h, params, h_out, st);
 }
 
@@ -256,7 +260,7 @@ int gj_mp_step_launches(const gj_mp_desc* d, int backward, int with_saved) {
   const int njb = (tc2 && L.N > 32) ? 1 : 0;      // per-j-block partial sums (forward: e, backward: dP)
   if (edge_mat(L, d->precision)) return gj_dense_launches(L, backward != 0) + gj_edge_mat_launches(L, backward != 0);
   if (tc3_path(L, d->precision))      // + parameter image, pair distances, edge kernel [, j-block sum]; backward also the distance adjoint and the reduction
-    return gj_dense_launches(L, backward != 0) + 3 + (L.N > 32 ? 1 : 0) + (backward ? 2 : 0) - ((backward && with_saved) ? 4 : 0);
+    return gj_dense_launches(L, backward != 0) + 3 + (L.N > 32 ? 1 : 0) + (backward ? 2 : 0) - ((backward && with_saved) ? 4 + L.Ln + 1 : 0);
   if (dense_node(L, d->precision)) return gj_dense_launches(L, backward != 0) + (backward ? 2 : 1);      // + the edge kernel(s)
   if (!backward) return tc2 ? 4 + njb : 3;        // projections, [parameter image], edge kernel, [j-block sum], node MLP
   if (!tc2) return 8;
@@ -316,7 +320,8 @@ static int mp_step_bwd_impl(const gj_mp_desc* d, const float* h, const float* e,
   }
   const bool dense = dense_node(L, d->precision);
   if (dense) {      // generic-GEMM node level (dense.cu) around the edge adjoint
-    if ((rc = gj_dense_post_bwd(L, e, h, params, dh_out, ws + w.de, dh, dparams, ws + w.dense, d->precision, st))) return rc;
+    if ((rc = gj_dense_post_bwd(L, e, h, params, dh_out, ws + w.de, dh, dparams, ws + w.dense, (saved && tc3) ? pre + w.ysave : nullptr,
+                                d->precision, st))) return rc;
     if (!saved && (rc = gj_dense_pre_fwd(L, h, params, pre + w.pq, d->precision, st))) return rc;
     rc = emat ? gj_edge_mat_bwd(L, h, pre + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.emat, d->precision, st)
        : tc3 ? gj_edge_bwd3(L, h, pre + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.part, pre + w.wimg, pre + w.dist,

@@ -409,6 +409,8 @@ static DenseWs dense_plan(const MPLayout& L, bool backward) {
   return w;
 }
 size_t gj_dense_ws_floats(const MPLayout& L, bool backward) { return dense_plan(L, backward).total; }
+// floats of the node-MLP activations y_0 .. y_{Ln-1} a forward call can leave for the backward call (same offsets as the plan's)
+size_t gj_dense_ysave_floats(const MPLayout& L) { const DenseWs w = dense_plan(L, true); return w.g0; }
 
 // P = Wa h + b0 | Q = Wb h   (pq: rows x 2 E0p)
 int gj_dense_pre_fwd(const MPLayout& L, const float* h, const float* params, float* pq, int precision, cudaStream_t st) {
@@ -436,23 +438,31 @@ static int dense_post_chain(const MPLayout& L, const float* e, const float* h, c
   }
   return GJ_OK;
 }
-int gj_dense_post_fwd(const MPLayout& L, const float* e, const float* h, const float* params, float* h_out, float* ws, int precision, cudaStream_t st) {
-  const DenseWs w = dense_plan(L, false);
-  return dense_post_chain(L, e, h, params, h_out, ws, w, false, precision, st);
+// ysave (optional, gj_dense_ysave_floats): receives every layer's activation for gj_dense_post_bwd
+int gj_dense_post_fwd(const MPLayout& L, const float* e, const float* h, const float* params, float* h_out, float* ws, float* ysave, int precision,
+                      cudaStream_t st) {
+  if (!ysave) return dense_post_chain(L, e, h, params, h_out, ws, dense_plan(L, false), false, precision, st);
+  const DenseWs w = dense_plan(L, true);
+  if (int rc = dense_post_chain(L, e, h, params, nullptr, ysave, w, true, precision, st)) return rc;
+  cudaError_t ce = cudaMemcpyAsync(h_out, ysave + w.y[L.Ln - 1], (size_t)L.B * L.N * L.O[L.Ln - 1] * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  if (ce != cudaSuccess) { gj_set_error("cudaMemcpyAsync: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
+  return GJ_OK;
 }
 
 // adjoint of the node MLP: de, dh (first `cols` columns OVERWRITTEN), node parameter gradients written to dparams
+// ysave (optional): the activations a forward call left (gj_dense_post_fwd); otherwise the chain is recomputed
 int gj_dense_post_bwd(const MPLayout& L, const float* e, const float* h, const float* params, const float* dh_out, float* de, float* dh,
-                      float* dparams, float* ws, int precision, cudaStream_t st) {
+                      float* dparams, float* ws, const float* ysave, int precision, cudaStream_t st) {
   const DenseWs w = dense_plan(L, true);
   const int rows = L.B * L.N;
-  if (int rc = dense_post_chain(L, e, h, params, nullptr, ws, w, true, precision, st)) return rc;
+  if (!ysave) { if (int rc = dense_post_chain(L, e, h, params, nullptr, ws, w, true, precision, st)) return rc; }
+  const float* yb = ysave ? ysave : ws;      // activations y_m at yb + w.y[m]
   float* g = ws + w.g0;
   float* gn = ws + w.g1;
   float* part = ws + w.part;
   {
     const size_t n = (size_t)rows * L.O[L.Ln - 1];
-    mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dh_out, ws + w.y[L.Ln - 1], n, L.alpha, g);
+    mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dh_out, yb + w.y[L.Ln - 1], n, L.alpha, g);
     DN_CHECK("dense mask launch");
   }
   for (int m = L.Ln - 1; m >= 0; --m) {
@@ -460,8 +470,8 @@ int gj_dense_post_bwd(const MPLayout& L, const float* e, const float* h, const f
     const float* V = params + L.pV[m];
     if (int rc = dense_colsum(rows, O, g, O, dparams + L.pc[m], part, st)) return rc;
     if (m > 0) {
-      if (int rc = dense_wgrad(rows, O, I, g, O, ws + w.y[m - 1], I, I, dparams + L.pV[m], I, part, precision, st)) return rc;
-      if (int rc = dense_dgrad(rows, O, I, g, O, V, I, 2, L.alpha, ws + w.y[m - 1], I, 0, gn, I, I, precision, st)) return rc;
+      if (int rc = dense_wgrad(rows, O, I, g, O, yb + w.y[m - 1], I, I, dparams + L.pV[m], I, part, precision, st)) return rc;
+      if (int rc = dense_dgrad(rows, O, I, g, O, V, I, 2, L.alpha, yb + w.y[m - 1], I, 0, gn, I, I, precision, st)) return rc;
       float* t = g; g = gn; gn = t;
     } else {
       if (int rc = dense_wgrad(rows, O, L.EL, g, O, e, L.EL, L.EL, dparams + L.pV[0], I, part, precision, st)) return rc;

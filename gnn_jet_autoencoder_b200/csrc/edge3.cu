@@ -289,18 +289,19 @@ __global__ void __launch_bounds__(256) e3_sum_jblocks_kernel(const float4* __res
 template <int E0, int E1, int NWG, int S, int IC>
 struct Bwd3Smem {
   static constexpr int C0 = E0 / S, C1 = E1 / S;
-  static constexpr int o_bar = 0;                        // per group: done, doneW
+  static constexpr int o_bar = 0;                        // per group: done[2], doneW[2]
   static constexpr int o_slot = 128;
   static constexpr int o_wd = 256;                       // E0 floats
   static constexpr int o_img = 1024;
   static constexpr int o_b1 = o_img + WImage3<E0, E1>::o_b1;
   static constexpr int o_w1 = o_img + WImage3<E0, E1>::o_w1;
   static constexpr int o_grp = ((o_img + WImage3<E0, E1>::bytes + 1023) / 1024) * 1024;
-  // per group: A0 = [a0: E0 / 8 slabs][ones slab][zero slab], D1 = [dz1: E1 / 8 slabs], the G partials of the upper channel parts
-  static constexpr int g_a0 = 0;
-  static constexpr int g_ones = (E0 / 8) * 2048;
-  static constexpr int g_d1 = g_ones + 4096;
-  static constexpr int g_gs = g_d1 + (E1 / 8) * 2048;      // [S][128] floats
+  // per group and tile slot: A0 = [a0: E0 / 8 slabs][ones slab][zero slab], D1 = [dz1: E1 / 8 slabs]
+  static constexpr int t_a0 = 0;
+  static constexpr int t_ones = (E0 / 8) * 2048;
+  static constexpr int t_d1 = t_ones + 4096;
+  static constexpr int tile_bytes = t_d1 + (E1 / 8) * 2048;
+  static constexpr int g_gs = 2 * tile_bytes;            // [S][128] floats: the G partials of the upper channel parts
   static constexpr int grp_bytes = g_gs + S * 128 * 4;
   static constexpr int o_warp = o_grp + NWG * grp_bytes;
   static constexpr int warp_bytes = 2 * IC * (C0 + C1) * 4;      // this warp's channel part of P_i and de_i, double buffered
@@ -309,13 +310,25 @@ struct Bwd3Smem {
   static constexpr int total = o_zero + 2048;                                            // (last, so that descriptor strides to it are positive)
 };
 
+// Two tiles of a group are in flight (slots 0 / 1: private A0 / D1 slabs, TMEM accumulator and barriers), handled by the SAME
+// threads in the order  E1(t) -> L0(t + 1) -> E0(t): the GEMMs of one tile run on the tensor pipe while the CUDA cores work on
+// the other, and the per-thread dQ_j / d(wd) accumulators are shared (consecutive tiles are consecutive i of the same j).
+struct E3Slot {
+  bool active, valid, last_i, pendW;
+  int i, jb;
+  size_t node0;
+  float dij;
+  const float* st;      // staged [P_i part | de_i part] of the tile
+  uint32_t ph, phW;
+};
+
 template <int E0, int E1, int NWG, int S, int IC>
 __global__ void __launch_bounds__(NWG * S * 128, 1) edge_bwd3_kernel(const E3Args A) {
   using SM = Bwd3Smem<E0, E1, NWG, S, IC>;
   constexpr int C0 = SM::C0, C1 = SM::C1;
   static_assert(C0 % 16 == 0 && C1 % 16 == 0 && E0 <= 128 && E1 <= 128 && (E1 == 64 || E1 == 128), "widths");
-  constexpr int ACC = E0 > E1 ? E0 : E1;           // TMEM columns of a group: F1 accumulator, then (same columns) the dgrad accumulator
-  constexpr int GW = NWG * ACC;                    // first column of the [dW1 | db1] accumulator (E0 + 16 columns)
+  constexpr int ACC = E0 > E1 ? E0 : E1;           // TMEM columns of a tile slot: F1 accumulator, then (same columns) the dgrad accumulator
+  constexpr int GW = NWG * 2 * ACC;                // first column of the [dW1 | db1] accumulator (E0 + 16 columns)
   static_assert(GW + E0 + 16 <= 512, "TMEM columns");
   constexpr int TCOLS = GW + E0 + 16 <= 256 ? 256 : 512;
   constexpr int NT = NWG * S * 128, GT = S * 128;
@@ -325,8 +338,7 @@ __global__ void __launch_bounds__(NWG * S * 128, 1) edge_bwd3_kernel(const E3Arg
   const int wg = warp / (4 * S), wl = warp - wg * 4 * S;      // group, warp within the group
   const int wq = wl & 3, part = wl >> 2;                       // TMEM lane quadrant (= task of the tile), channel part
   const int row = wq * 32 + lane;
-  uint64_t* done = reinterpret_cast<uint64_t*>(smem + SM::o_bar) + 2 * wg;
-  uint64_t* doneW = done + 1;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM::o_bar) + 4 * wg;      // done[0], done[1], doneW[0], doneW[1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM::o_slot);
   float* s_wd = reinterpret_cast<float*>(smem + SM::o_wd);
   float* s_red = reinterpret_cast<float*>(smem + SM::o_red);
@@ -334,16 +346,17 @@ __global__ void __launch_bounds__(NWG * S * 128, 1) edge_bwd3_kernel(const E3Arg
   load_wimage<WImage3<E0, E1>::bytes>(smem + SM::o_img, A.wimg, tid, NT);
   for (int idx = tid; idx < 512; idx += NT) reinterpret_cast<uint32_t*>(smem + SM::o_zero)[idx] = 0u;
   for (int c = tid; c < E0; c += NT) s_wd[c] = __ldg(A.params + A.pWd + c * A.K0);
-  for (int idx = tid; idx < NWG * 1024; idx += NT) {      // ones slab (channels E0, E0 + 1 = 1.0: bias hi + lo) and zero slab of every group
-    const int g = idx >> 10, w = idx & 1023;
-    reinterpret_cast<uint32_t*>(smem + SM::o_grp + g * SM::grp_bytes + SM::g_ones)[w] = (w < 512 && (w & 3) == 0) ? 0x3F803F80u : 0u;
+  for (int idx = tid; idx < NWG * 2 * 1024; idx += NT) {      // ones slab (channels E0, E0 + 1 = 1.0: bias hi + lo) and zero slab of every tile slot
+    const int gs = idx >> 10, w = idx & 1023;
+    reinterpret_cast<uint32_t*>(smem + SM::o_grp + (gs >> 1) * SM::grp_bytes + (gs & 1) * SM::tile_bytes + SM::t_ones)[w] =
+        (w < 512 && (w & 3) == 0) ? 0x3F803F80u : 0u;
   }
-  for (int idx = tid; idx < NWG * (E1 / 8) * 512; idx += NT) {      // dz1 slabs start finite
-    const int g = idx / ((E1 / 8) * 512), w = idx - g * ((E1 / 8) * 512);
-    reinterpret_cast<uint32_t*>(smem + SM::o_grp + g * SM::grp_bytes + SM::g_d1)[w] = 0u;
+  for (int idx = tid; idx < NWG * 2 * (E1 / 8) * 512; idx += NT) {      // dz1 slabs start finite
+    const int gs = idx / ((E1 / 8) * 512), w = idx - gs * ((E1 / 8) * 512);
+    reinterpret_cast<uint32_t*>(smem + SM::o_grp + (gs >> 1) * SM::grp_bytes + (gs & 1) * SM::tile_bytes + SM::t_d1)[w] = 0u;
   }
   if (tid == 0) {
-    for (int b = 0; b < 2 * NWG; ++b) mbar_init(reinterpret_cast<uint64_t*>(smem + SM::o_bar) + b, 1);
+    for (int b = 0; b < 4 * NWG; ++b) mbar_init(reinterpret_cast<uint64_t*>(smem + SM::o_bar) + b, 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, TCOLS);
@@ -370,12 +383,7 @@ __global__ void __launch_bounds__(NWG * S * 128, 1) edge_bwd3_kernel(const E3Arg
 
   const uint32_t smem0 = smem_u32(smem);
   const uint32_t w1a = smem0 + SM::o_w1, b1a = smem0 + SM::o_b1, zero_a = smem0 + SM::o_zero;
-  const uint32_t gba = smem0 + SM::o_grp + (uint32_t)(wg * SM::grp_bytes);
-  const uint32_t slot0 = tmem_base + (uint32_t)(wg * ACC);
-  const uint32_t slot = slot0 + ((uint32_t)(wq * 32) << 16);
   uint8_t* gb = smem + SM::o_grp + wg * SM::grp_bytes;
-  uint8_t* a0_row = gb + SM::g_a0 + row * 16;
-  uint8_t* d1_row = gb + SM::g_d1 + row * 16;
   float* s_g = reinterpret_cast<float*>(gb + SM::g_gs);
   float* s_st = reinterpret_cast<float*>(smem + SM::o_warp + warp * SM::warp_bytes);      // [2][IC][C0 + C1]
   const __nv_bfloat162 alpha2 = __float2bfloat162_rn(A.alpha);
@@ -383,8 +391,9 @@ __global__ void __launch_bounds__(NWG * S * 128, 1) edge_bwd3_kernel(const E3Arg
   const int gidx = blockIdx.x * NWG + wg;
   const int g0 = range_lo(gidx), g1 = range_lo(gidx + 1);
   const int ntasks = A.B * A.NJB;
+  // ---- cursor over the (task, i) tile list: advanced by L0 ----
   int k = g0 / N, i = g0 - k * N;
-  bool fresh = true, active = false, valid = false;
+  bool fresh = true, c_active = false, c_valid = false;
   size_t node0 = 0;
   int jb = 0;
   uint32_t q[C0 / 2];
@@ -394,8 +403,6 @@ __global__ void __launch_bounds__(NWG * S * 128, 1) edge_bwd3_kernel(const E3Arg
 #pragma unroll
   for (int c = 0; c < C0 / 2; ++c) q[c] = 0u;
   float d_cur = 0.f;
-  uint32_t ph = 0, phW = 0;
-  bool pendingW = false;
 
   auto stage_chunk = [&](int c) {      // this warp's channel parts of P_i and de_i for i in [c IC, ...) -> buffer c & 1
     const int ib = c * IC, n = min(IC, N - ib);
@@ -408,25 +415,19 @@ __global__ void __launch_bounds__(NWG * S * 128, 1) edge_bwd3_kernel(const E3Arg
     }
     e3_cp_async_commit();
   };
-  auto flush_dq = [&]() {
-    if (valid) {
-      float* dst = A.dpq + (node0 + jb * 32 + lane) * (2 * E0) + E0 + part * C0;
-#pragma unroll
-      for (int c = 0; c < C0; ++c) atomicAdd(dst + c, dq[c]);
-    }
-#pragma unroll
-    for (int c = 0; c < C0; ++c) dq[c] = 0.f;
-  };
 
-  for (int g = g0; g < g1; ++g) {
+  // ---- L0 of the cursor's tile into tile slot `ts`: a0 (this thread's channel part) -> shared A0, then F1 is issued ----
+  auto L0 = [&](E3Slot& sl, const int ts) {
+    uint8_t* tb = gb + ts * SM::tile_bytes;
+    const uint32_t tba = smem_u32(tb);
     if (fresh) {
       const int task = 4 * k + wq;
-      active = task < ntasks;
-      const int tk = active ? task : 0;
+      c_active = task < ntasks;
+      const int tk = c_active ? task : 0;
       const int jet = tk / A.NJB;
       jb = tk - jet * A.NJB;
       const int j = jb * 32 + lane;
-      valid = active && j < N;
+      c_valid = c_active && j < N;
       node0 = (size_t)jet * N;
       e3_cp_async_wait<0>();
       __syncwarp();
@@ -452,14 +453,16 @@ __global__ void __launch_bounds__(NWG * S * 128, 1) edge_bwd3_kernel(const E3Arg
       __syncwarp();
       if ((i / IC + 1) * IC < N) stage_chunk(i / IC + 1);
     }
-    const bool last_i = (i + 1 == N);
-    const float dij = d_cur;
-    const float* st = s_st + (((i / IC) & 1) * IC + (i % IC)) * (C0 + C1);      // [P_i part | de_i part]
-
-    // ---- L0: a0 (this thread's channel part) -> shared A0; the previous tile's weight-gradient GEMM must have read A0 / D1 ----
-    if (pendingW) { mbar_wait(doneW, phW); phW ^= 1u; pendingW = false; }
+    sl.active = c_active; sl.valid = c_valid; sl.i = i; sl.jb = jb; sl.node0 = node0; sl.last_i = (i + 1 == N);
+    sl.dij = d_cur;
+    sl.st = s_st + (((i / IC) & 1) * IC + (i % IC)) * (C0 + C1);
+    if (!sl.last_i) d_cur = __ldg(A.d + (node0 + i + 1) * A.NJ32 + jb * 32 + lane);
+    // the weight-gradient GEMM of the tile that used this slot two tiles ago must have read A0 / D1
+    if (sl.pendW) { mbar_wait(bars + 2 + ts, sl.phW); sl.phW ^= 1u; sl.pendW = false; }
     {
-      const float2 d2 = make_float2(dij, dij);
+      uint8_t* a0_row = tb + SM::t_a0 + row * 16;
+      const float* st = sl.st;
+      const float2 d2 = make_float2(sl.dij, sl.dij);
 #pragma unroll
       for (int c = 0; c < C0; c += 8) {
         uint32_t o[4];
@@ -475,117 +478,152 @@ __global__ void __launch_bounds__(NWG * S * 128, 1) edge_bwd3_kernel(const E3Arg
         }
         *reinterpret_cast<uint4*>(a0_row + ((part * C0 + c) >> 3) * 2048) = make_uint4(o[0], o[1], o[2], o[3]);
       }
-      fence_proxy_async();
-      tc_fence_before();
-      named_bar_sync(1 + wg, GT);
-      if (wl == 0) {      // F1: acc[0, E1) = A0 W1^T + b1
-        tc_fence_after();
-        const uint64_t dA0k = make_smem_desc(gba + SM::g_a0, 2048, 128), dW1f = wdesc_kmajor(w1a, E1);
-        const uint64_t dBiasA = make_smem_desc(gba + SM::g_ones, zero_a - (gba + SM::g_ones), 128);
-        const uint32_t idesc = make_idesc_bf16(128, E1, 0, 0);
-#pragma unroll
-        for (int s = 0; s < E0 / 16; ++s) mma_bf16_ss_elect(slot0, dA0k + (uint64_t)(s * 256), dW1f + (uint64_t)(s * 2 * E1), idesc, s > 0);
-        mma_bf16_ss_elect(slot0, dBiasA, make_smem_desc(b1a, zero_a - b1a, 128), idesc, 1u);
-        mma_commit_elect(done);
-      }
     }
-    const float d_next = (!last_i) ? __ldg(A.d + (node0 + i + 1) * A.NJ32 + jb * 32 + lane) : 0.f;
+    fence_proxy_async();
+    tc_fence_before();
+    named_bar_sync(1 + wg, GT);
+    if (wl == 0) {      // F1: acc = A0 W1^T + b1
+      tc_fence_after();
+      const uint32_t acc0 = tmem_base + (uint32_t)((wg * 2 + ts) * ACC);
+      const uint64_t dA0k = make_smem_desc(tba + SM::t_a0, 2048, 128), dW1f = wdesc_kmajor(w1a, E1);
+      const uint64_t dBiasA = make_smem_desc(tba + SM::t_ones, zero_a - (tba + SM::t_ones), 128);
+      const uint32_t idesc = make_idesc_bf16(128, E1, 0, 0);
+#pragma unroll
+      for (int s = 0; s < E0 / 16; ++s) mma_bf16_ss_elect(acc0, dA0k + (uint64_t)(s * 256), dW1f + (uint64_t)(s * 2 * E1), idesc, s > 0);
+      mma_bf16_ss_elect(acc0, dBiasA, make_smem_desc(b1a, zero_a - b1a, 128), idesc, 1u);
+      mma_commit_elect(bars + ts);
+    }
+    if (++i == N) { i = 0; ++k; fresh = true; }
+  };
 
-    // ---- F1 epilogue: dz1 = de_i leaky'(z1) (zero on padded rows) for this thread's channel part -> shared D1 ----
-    mbar_wait(done, ph); ph ^= 1u;
+  // ---- E1: dz1 = de_i leaky'(z1) (zero on padded rows) for this thread's channel part -> shared D1; dgrad and wgrad are issued ----
+  auto E1f = [&](E3Slot& sl, const int ts) {
+    uint8_t* tb = gb + ts * SM::tile_bytes;
+    const uint32_t tba = smem_u32(tb);
+    const uint32_t acc0 = tmem_base + (uint32_t)((wg * 2 + ts) * ACC), acc = acc0 + ((uint32_t)(wq * 32) << 16);
+    uint8_t* d1_row = tb + SM::t_d1 + row * 16;
+    mbar_wait(bars + ts, sl.ph); sl.ph ^= 1u;
     tc_fence_after();
-    {
-      const float* dei = st + C0;
+    const float* dei = sl.st + C0;
+    const bool valid = sl.valid;
 #pragma unroll
-      for (int c0 = 0; c0 < C1; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16_u(slot + (uint32_t)(part * C1 + c0), v);
-        tmem_ld_wait(); tmem_pin16(v);
-        uint32_t o[8];
+    for (int c0 = 0; c0 < C1; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16_u(acc + (uint32_t)(part * C1 + c0), v);
+      tmem_ld_wait(); tmem_pin16(v);
+      uint32_t o[8];
 #pragma unroll
-        for (int p4 = 0; p4 < 4; ++p4) {
-          const float4 dv = *reinterpret_cast<const float4*>(dei + c0 + 4 * p4);
-          const float g0v = valid ? dv.x * (__uint_as_float(v[4 * p4]) > 0.f ? 1.f : alpha) : 0.f;
-          const float g1v = valid ? dv.y * (__uint_as_float(v[4 * p4 + 1]) > 0.f ? 1.f : alpha) : 0.f;
-          const float g2v = valid ? dv.z * (__uint_as_float(v[4 * p4 + 2]) > 0.f ? 1.f : alpha) : 0.f;
-          const float g3v = valid ? dv.w * (__uint_as_float(v[4 * p4 + 3]) > 0.f ? 1.f : alpha) : 0.f;
-          o[2 * p4] = bf2_as_u32(__floats2bfloat162_rn(g0v, g1v));
-          o[2 * p4 + 1] = bf2_as_u32(__floats2bfloat162_rn(g2v, g3v));
-        }
-        *reinterpret_cast<uint4*>(d1_row + ((part * C1 + c0) >> 3) * 2048) = make_uint4(o[0], o[1], o[2], o[3]);
-        *reinterpret_cast<uint4*>(d1_row + (((part * C1 + c0) >> 3) + 1) * 2048) = make_uint4(o[4], o[5], o[6], o[7]);
+      for (int p4 = 0; p4 < 4; ++p4) {
+        const float4 dv = *reinterpret_cast<const float4*>(dei + c0 + 4 * p4);
+        const float g0v = valid ? dv.x * (__uint_as_float(v[4 * p4]) > 0.f ? 1.f : alpha) : 0.f;
+        const float g1v = valid ? dv.y * (__uint_as_float(v[4 * p4 + 1]) > 0.f ? 1.f : alpha) : 0.f;
+        const float g2v = valid ? dv.z * (__uint_as_float(v[4 * p4 + 2]) > 0.f ? 1.f : alpha) : 0.f;
+        const float g3v = valid ? dv.w * (__uint_as_float(v[4 * p4 + 3]) > 0.f ? 1.f : alpha) : 0.f;
+        o[2 * p4] = bf2_as_u32(__floats2bfloat162_rn(g0v, g1v));
+        o[2 * p4 + 1] = bf2_as_u32(__floats2bfloat162_rn(g2v, g3v));
       }
-      fence_proxy_async();
-      tc_fence_before();
-      named_bar_sync(1 + wg, GT);
-      if (wl == 1) {      // dgrad: acc[0, E0) = dz1 W1
-        tc_fence_after();
-        const uint64_t dD1k = make_smem_desc(gba + SM::g_d1, 2048, 128), dW1b = make_smem_desc(w1a, 128, E1 * 16);
-        const uint32_t idesc = make_idesc_bf16(128, E0, 0, 1);
-#pragma unroll
-        for (int s = 0; s < E1 / 16; ++s) mma_bf16_ss_elect(slot0, dD1k + (uint64_t)(s * 256), dW1b + (uint64_t)(s * 16), idesc, s > 0);
-        mma_commit_elect(done);
-      } else if (wl == 2) {      // wgrad: [dW1 | db1] += dz1^T [a0 | 1]
-        tc_fence_after();
-        const uint64_t dD1n = make_smem_desc(gba + SM::g_d1, 128, 2048), dA0n = make_smem_desc(gba + SM::g_a0, 128, 2048);
-        const uint32_t idesc = make_idesc_bf16(E1 == 128 ? 128 : 64, E0 + 16, 1, 1);
-#pragma unroll
-        for (int s = 0; s < 8; ++s) mma_bf16_ss_elect(tmem_base + GW, dD1n + (uint64_t)(s * 16), dA0n + (uint64_t)(s * 16), idesc, 1u);
-        mma_commit_elect(doneW);
-      }
-      pendingW = true;
+      *reinterpret_cast<uint4*>(d1_row + ((part * C1 + c0) >> 3) * 2048) = make_uint4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<uint4*>(d1_row + (((part * C1 + c0) >> 3) + 1) * 2048) = make_uint4(o[4], o[5], o[6], o[7]);
     }
+    fence_proxy_async();
+    tc_fence_before();
+    named_bar_sync(1 + wg, GT);
+    if (wl == 1) {      // dgrad: acc = dz1 W1
+      tc_fence_after();
+      const uint64_t dD1k = make_smem_desc(tba + SM::t_d1, 2048, 128), dW1b = make_smem_desc(w1a, 128, E1 * 16);
+      const uint32_t idesc = make_idesc_bf16(128, E0, 0, 1);
+#pragma unroll
+      for (int s = 0; s < E1 / 16; ++s) mma_bf16_ss_elect(acc0, dD1k + (uint64_t)(s * 256), dW1b + (uint64_t)(s * 16), idesc, s > 0);
+      mma_commit_elect(bars + ts);
+    } else if (wl == 2) {      // wgrad: [dW1 | db1] += dz1^T [a0 | 1]
+      tc_fence_after();
+      const uint64_t dD1n = make_smem_desc(tba + SM::t_d1, 128, 2048), dA0n = make_smem_desc(tba + SM::t_a0, 128, 2048);
+      const uint32_t idesc = make_idesc_bf16(E1 == 128 ? 128 : 64, E0 + 16, 1, 1);
+#pragma unroll
+      for (int s = 0; s < 8; ++s) mma_bf16_ss_elect(tmem_base + GW, dD1n + (uint64_t)(s * 16), dA0n + (uint64_t)(s * 16), idesc, 1u);
+      mma_commit_elect(bars + 2 + ts);
+    }
+    sl.pendW = true;
+  };
 
-    // ---- dgrad epilogue: dz0 = acc leaky'(a0) in fp32 -> dP_i (lane reduce), dQ_j, d(wd), G_ij ----
-    mbar_wait(done, ph); ph ^= 1u;
-    tc_fence_after();
-    {
-      float gsum = 0.f;
-      float* dp_dst = (A.NJB > 1 ? A.dp_part + ((size_t)jb * A.B * N + node0 + i) * E0 : A.dpq + (node0 + i) * (2 * E0)) + part * C0;
+  auto flush_dq = [&](const E3Slot& sl) {      // dQ_j of the (jet, j block) just finished (at most two groups add into one row)
+    if (sl.valid) {
+      float* dst = A.dpq + (sl.node0 + sl.jb * 32 + lane) * (2 * E0) + E0 + part * C0;
 #pragma unroll
-      for (int c0 = 0; c0 < C0; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16_u(slot + (uint32_t)(part * C0 + c0), v);
-        const uint4 s0 = *reinterpret_cast<const uint4*>(a0_row + ((part * C0 + c0) >> 3) * 2048);
-        const uint4 s1 = *reinterpret_cast<const uint4*>(a0_row + (((part * C0 + c0) >> 3) + 1) * 2048);
-        const uint32_t sg[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-        tmem_ld_wait(); tmem_pin16(v);
-        float z[16];
-#pragma unroll
-        for (int p = 0; p < 8; ++p) {
-          const float alo = __uint_as_float(sg[p] << 16), ahi = __uint_as_float(sg[p] & 0xffff0000u);
-          z[2 * p] = __uint_as_float(v[2 * p]) * (alo > 0.f ? 1.f : alpha);
-          z[2 * p + 1] = __uint_as_float(v[2 * p + 1]) * (ahi > 0.f ? 1.f : alpha);
-        }
-#pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-          const float4 w = *reinterpret_cast<const float4*>(s_wd + part * C0 + c0 + 4 * c4);
-          gsum = fmaf(z[4 * c4], w.x, gsum); gsum = fmaf(z[4 * c4 + 1], w.y, gsum);
-          gsum = fmaf(z[4 * c4 + 2], w.z, gsum); gsum = fmaf(z[4 * c4 + 3], w.w, gsum);
-        }
-#pragma unroll
-        for (int c = 0; c < 16; ++c) { dq[c0 + c] += z[c]; dwd[c0 + c] = fmaf(z[c], dij, dwd[c0 + c]); }
-        const float s = e3_transpose_sum16(z, lane);
-        if (active && (lane & 1) == 0) dp_dst[c0 + (lane >> 1)] = s;
-      }
-      if (S > 1) {      // G_ij: the channel parts' sums meet in shared memory, part 0 writes the row's value
-        if (part > 0) s_g[(part - 1) * 128 + row] = gsum;
-        tc_fence_before();
-        named_bar_sync(1 + wg, GT);
-        if (part == 0) {
-#pragma unroll
-          for (int p = 1; p < S; ++p) gsum += s_g[(p - 1) * 128 + row];
-        }
-      } else {
-        tc_fence_before();
-      }
-      if (part == 0 && active) A.G[(node0 + i) * A.NJ32 + jb * 32 + lane] = valid ? gsum : 0.f;
+      for (int c = 0; c < C0; ++c) atomicAdd(dst + c, dq[c]);
     }
-    d_cur = d_next;
-    if (++i == N) { flush_dq(); i = 0; ++k; fresh = true; }
+#pragma unroll
+    for (int c = 0; c < C0; ++c) dq[c] = 0.f;
+  };
+
+  // ---- E0: dz0 = acc leaky'(a0) in fp32 -> dP_i (lane reduce), dQ_j, d(wd), G_ij ----
+  auto E0f = [&](E3Slot& sl, const int ts, bool last_of_range) {
+    uint8_t* tb = gb + ts * SM::tile_bytes;
+    const uint32_t acc = tmem_base + (uint32_t)((wg * 2 + ts) * ACC) + ((uint32_t)(wq * 32) << 16);
+    const uint8_t* a0_row = tb + SM::t_a0 + row * 16;
+    mbar_wait(bars + ts, sl.ph); sl.ph ^= 1u;
+    tc_fence_after();
+    float gsum = 0.f;
+    const float dij = sl.dij;
+    float* dp_dst = (A.NJB > 1 ? A.dp_part + ((size_t)sl.jb * A.B * N + sl.node0 + sl.i) * E0 : A.dpq + (sl.node0 + sl.i) * (2 * E0)) + part * C0;
+#pragma unroll
+    for (int c0 = 0; c0 < C0; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16_u(acc + (uint32_t)(part * C0 + c0), v);
+      const uint4 s0 = *reinterpret_cast<const uint4*>(a0_row + ((part * C0 + c0) >> 3) * 2048);
+      const uint4 s1 = *reinterpret_cast<const uint4*>(a0_row + (((part * C0 + c0) >> 3) + 1) * 2048);
+      const uint32_t sg[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+      tmem_ld_wait(); tmem_pin16(v);
+      float z[16];
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        const float alo = __uint_as_float(sg[p] << 16), ahi = __uint_as_float(sg[p] & 0xffff0000u);
+        z[2 * p] = __uint_as_float(v[2 * p]) * (alo > 0.f ? 1.f : alpha);
+        z[2 * p + 1] = __uint_as_float(v[2 * p + 1]) * (ahi > 0.f ? 1.f : alpha);
+      }
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const float4 w = *reinterpret_cast<const float4*>(s_wd + part * C0 + c0 + 4 * c4);
+        gsum = fmaf(z[4 * c4], w.x, gsum); gsum = fmaf(z[4 * c4 + 1], w.y, gsum);
+        gsum = fmaf(z[4 * c4 + 2], w.z, gsum); gsum = fmaf(z[4 * c4 + 3], w.w, gsum);
+      }
+#pragma unroll
+      for (int c = 0; c < 16; ++c) { dq[c0 + c] += z[c]; dwd[c0 + c] = fmaf(z[c], dij, dwd[c0 + c]); }
+      const float s = e3_transpose_sum16(z, lane);
+      if (sl.active && (lane & 1) == 0) dp_dst[c0 + (lane >> 1)] = s;
+    }
+    tc_fence_before();
+    if (S > 1) {      // G_ij: the channel parts' sums meet in shared memory, part 0 writes the row's value
+      if (part > 0) s_g[(part - 1) * 128 + row] = gsum;
+      named_bar_sync(1 + wg, GT);
+      if (part == 0) {
+#pragma unroll
+        for (int p = 1; p < S; ++p) gsum += s_g[(p - 1) * 128 + row];
+      }
+      named_bar_sync(1 + wg, GT);      // s_g is free again before the next tile's partials arrive
+    }
+    if (part == 0 && sl.active) A.G[(sl.node0 + sl.i) * A.NJ32 + sl.jb * 32 + lane] = sl.valid ? gsum : 0.f;
+    if (sl.last_i || last_of_range) flush_dq(sl);      // a (jet, j block) that ends mid-way: the next group adds the rest
+  };
+
+  E3Slot sA, sB;
+  sA.pendW = sB.pendW = false; sA.ph = sB.ph = sA.phW = sB.phW = 0u;
+  sA.active = sA.valid = sA.last_i = sB.active = sB.valid = sB.last_i = false;
+  sA.i = sB.i = sA.jb = sB.jb = 0; sA.node0 = sB.node0 = 0; sA.dij = sB.dij = 0.f; sA.st = sB.st = s_st;
+  const int ntile = g1 - g0;
+  if (ntile > 0) L0(sA, 0);
+  for (int t = 0; t < ntile; t += 2) {
+    E1f(sA, 0);
+    if (t + 1 < ntile) L0(sB, 1);
+    E0f(sA, 0, t + 1 == ntile);
+    if (t + 1 < ntile) {
+      E1f(sB, 1);
+      if (t + 2 < ntile) L0(sA, 0);
+      E0f(sB, 1, t + 2 == ntile);
+    }
   }
-  if (!fresh) flush_dq();
-  if (pendingW) { mbar_wait(doneW, phW); phW ^= 1u; }
+  if (sA.pendW) { mbar_wait(bars + 2, sA.phW); sA.phW ^= 1u; }      // all of this group's MMAs have completed
+  if (sB.pendW) { mbar_wait(bars + 3, sB.phW); sB.phW ^= 1u; }
   e3_cp_async_wait<0>();
   // d(wd): lanes by shuffles, warps through shared memory (fixed order)
 #pragma unroll
@@ -763,7 +801,7 @@ int gj_edge_bwd3(const MPLayout& L, const float* h, const float* pq, const float
   A.pq = pq; A.d = d; A.params = params; A.wimg = reinterpret_cast<const uint8_t*>(wimg);
   A.de = de; A.dpq = dpq; A.dp_part = dp_part; A.G = G; A.part = part;
   const int grid = e3_bwd_grid();
-  int rc = shape == 0 ? e3_launch_bwd<64, 64, 2, 1, 4>(A, grid, stream) : e3_launch_bwd<128, 128, 1, 2, 2>(A, grid, stream);
+  int rc = shape == 0 ? e3_launch_bwd<64, 64, 2, 1, 2>(A, grid, stream) : e3_launch_bwd<128, 128, 1, 2, 2>(A, grid, stream);
   if (rc) return rc;
   if (njb > 1) {
     const size_t n4 = rows * (size_t)(L.E[0] / 4);

@@ -47,22 +47,60 @@ class ChamferLoss(nn.Module):
         return loss if p.dtype == torch.float32 else loss.to(p.dtype)
 
 
+_HEPS = 1e-16      # utils/losses/hungarian_mse/utils.py:5
+
+
+def _to_polar(p: torch.Tensor) -> torch.Tensor:
+    """(E,) px, py, pz -> (pt, eta, phi) with the reference's regularisers (hungarian_mse/utils.py:8-28): pt = sqrt(px^2 + py^2 + eps),
+    eta = asinh(pz / (pt + eps)), phi = atan2(py + eps, px + eps); the energy of a 4-vector is dropped."""
+    if p.shape[-1] not in (3, 4):
+        raise ValueError(f"Wrong last dimension of p. Should be 3 or 4 but found: {p.shape[-1]}.")
+    xyz = p[..., -3:]
+    pt = torch.sqrt(xyz[..., 0] ** 2 + xyz[..., 1] ** 2 + _HEPS)
+    return torch.stack((pt, torch.asinh(xyz[..., 2] / (pt + _HEPS)), torch.atan2(xyz[..., 1] + _HEPS, xyz[..., 0] + _HEPS)), dim=-1)
+
+
+def _relative_polar(p: torch.Tensor, jet: torch.Tensor) -> torch.Tensor:
+    """Polar coordinates relative to the jet axis (hungarian_mse/utils.py:35-49): pt / (pt_jet + eps), eta - eta_jet and
+    phi - phi_jet wrapped into [-pi, pi).  Written out of place, so that -- unlike the reference, whose in-place updates of
+    unbind() views raise under autograd -- the gradient reaches the reconstruction in the relative modes too."""
+    import math
+    pp, jp = _to_polar(p), _to_polar(jet).unsqueeze(-2)
+    dphi = torch.remainder(pp[..., 2] - jp[..., 2] + math.pi, 2 * math.pi) - math.pi
+    return torch.stack((pp[..., 0] / (jp[..., 0] + _HEPS), pp[..., 1] - jp[..., 1], dphi), dim=-1)
+
+
+def _polar_to_cartesian(p: torch.Tensor) -> torch.Tensor:
+    """(pt, eta, phi) -> (px, py, pz) as the reference computes it (hungarian_mse/utils.py:52-71).  Its py line reads
+    ``pt * torch.cos(phi)`` (:63, a slip for sin); reproduced, because the matching and the loss value depend on it."""
+    pt, eta, phi = p[..., -3], p[..., -2], p[..., -1]
+    return torch.stack((pt * torch.cos(phi), pt * torch.cos(phi), pt * torch.sinh(eta)), dim=-1)
+
+
+def hungarian_preprocess(recons: torch.Tensor, target: torch.Tensor, abs_coord: bool = True, polar_coord: bool = False):
+    """The four coordinate options of hungarian_mse.py:60-100: absolute Cartesian (identity), absolute polar, and -- relative to
+    the TARGET jet's axis -- relative polar or relative Cartesian."""
+    for t in (target, recons):
+        if t.shape[-1] not in (3, 4):
+            raise ValueError(f"Wrong last dimension of p. Should be 3 or 4 but found: {t.shape[-1]}.")
+    target = target.to(recons.device)
+    if abs_coord:
+        return (_to_polar(recons), _to_polar(target)) if polar_coord else (recons, target)
+    jet = target.sum(dim=-2)
+    r, t = _relative_polar(recons, jet), _relative_polar(target, jet)
+    return (r, t) if polar_coord else (_polar_to_cartesian(r), _polar_to_cartesian(t))
+
+
 class HungarianMSELoss(nn.Module):
     """Permutation-invariant MSE of reference utils/losses/hungarian_mse/hungarian_mse.py (:6-58) with the matching solved on
     the device for the whole batch (`gj_assignment`) instead of `scipy.optimize.linear_sum_assignment` jet by jet on the host
-    (:51-52): cost = cdist(recons, target), recons_shuffle[b] = recons[b, matching[b]], loss = MSELoss(recons_shuffle, target).
-    The gradient reaches `recons` through the gather, as in the reference.  Absolute Cartesian coordinates (the defaults
-    ``abs_coord=True, polar_coord=False``); the other coordinate options are preprocessing helpers outside this package."""
+    (:51-52): cost = cdist(recons, target) in the chosen coordinates, recons_shuffle[b] = recons[b, matching[b]],
+    loss = MSELoss(recons_shuffle, target).  The gradient reaches `recons` through the coordinate map and the gather."""
 
     def forward(self, recons: torch.Tensor, target: torch.Tensor, abs_coord: bool = True, polar_coord: bool = False):
-        for t in (target, recons):
-            if t.shape[-1] not in (3, 4):
-                raise ValueError(f"Wrong last dimension of p. Should be 3 or 4 but found: {t.shape[-1]}.")
-        if not abs_coord or polar_coord:
-            raise NotImplementedError("HungarianMSELoss: only absolute Cartesian coordinates (abs_coord=True, polar_coord=False)")
         from .anomaly import assignment
-        self.device = recons.device
-        target = target.to(recons.device)
+        self.abs_coord, self.polar_coord, self.device = abs_coord, polar_coord, recons.device
+        recons, target = hungarian_preprocess(recons, target, abs_coord=abs_coord, polar_coord=polar_coord)
         match, _ = assignment(recons, target)
         match = match.to(recons.device)
         recons_shuffle = torch.gather(recons, 1, match.unsqueeze(-1).expand(-1, -1, recons.shape[-1]))

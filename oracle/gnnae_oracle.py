@@ -430,6 +430,40 @@ def anomaly_hungarian(p, q, lorentz=False):
     return ((p_shuffle - q) ** 2).sum(axis=-1), matching, total
 
 
+def hungarian_coords(recons, target, abs_coord=True, polar_coord=False):
+    """The coordinate options of utils/losses/hungarian_mse/hungarian_mse.py:60-100 (with utils.py:8-71 of the same package,
+    including its ``py = pt * cos(phi)`` line :63), numpy float64."""
+    eps = 1e-16
+
+    def polar(p):
+        x, y, z = p[..., -3], p[..., -2], p[..., -1]
+        pt = np.sqrt(x * x + y * y + eps)
+        return np.stack((pt, np.arcsinh(z / (pt + eps)), np.arctan2(y + eps, x + eps)), axis=-1)
+
+    if abs_coord:
+        return (polar(recons), polar(target)) if polar_coord else (recons, target)
+    jet = polar(target.sum(axis=-2))[:, None, :]
+
+    def rel(p):
+        pp = polar(p)
+        return np.stack((pp[..., 0] / (jet[..., 0] + eps), pp[..., 1] - jet[..., 1],
+                         np.mod(pp[..., 2] - jet[..., 2] + np.pi, 2 * np.pi) - np.pi), axis=-1)
+
+    r, t = rel(recons), rel(target)
+    if polar_coord:
+        return r, t
+    cart = lambda p: np.stack((p[..., 0] * np.cos(p[..., 2]), p[..., 0] * np.cos(p[..., 2]), p[..., 0] * np.sinh(p[..., 1])), axis=-1)
+    return cart(r), cart(t)
+
+
+def hungarian_mse_loss(recons, target, abs_coord=True, polar_coord=False):
+    """hungarian_mse.py:22-58: Euclidean-cost optimal matching in the chosen coordinates, then the mean squared error."""
+    r, t = hungarian_coords(recons, target, abs_coord, polar_coord)
+    _, matching, _ = anomaly_hungarian(r, t)
+    bi = np.arange(r.shape[0])[:, None]
+    return float(((r[bi, matching] - t) ** 2).mean())
+
+
 def chamfer_loss(p, q, norm_choice="cartesian", jet_features_weight=1.0, mode="intended"):
     """mode='intended': chamfer + w*jet (what chamfer_loss.py:35-41 computes and then discards);
     mode='reference': the value the reference actually RETURNS, ``jet_loss`` alone

@@ -393,6 +393,45 @@ def test_permutation_test_on_the_cuda_modules(precision):
     assert out2["invariance"]["median"] < tol
 
 
+# ---- SURVEY 8.f components against the fixture the REFERENCE ITSELF produced (oracle/gen_golden_aux.py) ----------------
+def test_anomaly_scores_match_the_reference_fixture():
+    from gen_golden_aux import ANOMALY_SHAPES, aux_inputs
+    from gnn_jet_autoencoder_b200 import anomaly
+    g = np.load(os.path.join(GOLDEN, "aux_reference.npz"))
+    for s, shape in enumerate(ANOMALY_SHAPES):
+        p, q = aux_inputs(shape, s)
+        pt, qt = torch.from_numpy(p).float().to(DEV), torch.from_numpy(q).float().to(DEV)
+        tag = "x".join(map(str, shape))
+        assert rel(anomaly.mse(pt, qt).cpu().numpy(), g[f"mse_{tag}"]) < 1e-6
+        assert rel(anomaly.chamfer(pt, qt).cpu().numpy(), g[f"chamfer_{tag}"]) < 2e-5
+        out_b = anomaly.chamfer(pt, qt, batch_size=2)
+        assert not out_b.is_cuda and rel(out_b.numpy(), g[f"chamfer_b2_{tag}"]) < 2e-5      # the batched form returns a host tensor
+        assert rel(anomaly.hungarian(pt, qt).cpu().numpy(), g[f"hungarian_{tag}"]) < 2e-5
+        assert rel(anomaly.hungarian(pt, qt, batch_size=2).numpy(), g[f"hungarian_b2_{tag}"]) < 2e-5
+        if shape[-1] == 4:
+            assert rel(anomaly.chamfer_lorentz(pt, qt).cpu().numpy(), g[f"chamfer_lorentz_{tag}"]) < 5e-5
+            assert rel(anomaly.hungarian_lorentz(pt, qt).cpu().numpy(), g[f"hungarian_lorentz_{tag}"]) < 2e-5
+
+
+def test_hungarian_mse_loss_coordinate_modes_match_the_reference_fixture():
+    """All four coordinate options of hungarian_mse.py:60-100; gradients where the reference can produce one (its relative modes
+    raise under autograd)."""
+    from gen_golden_aux import HUNGARIAN_MODES, aux_inputs
+    from gnn_jet_autoencoder_b200 import HungarianMSELoss
+    g = np.load(os.path.join(GOLDEN, "aux_reference.npz"))
+    for s, shape in enumerate([(4, 30, 3), (3, 12, 4)]):
+        p, q = aux_inputs(shape, 100 + s)
+        for abs_coord, polar in HUNGARIAN_MODES:
+            tag = "x".join(map(str, shape)) + f"_abs{int(abs_coord)}_polar{int(polar)}"
+            pt = torch.from_numpy(p).to(DEV).requires_grad_(True)      # float64 in, as the reference's CLI default
+            loss = HungarianMSELoss()(pt, torch.from_numpy(q).to(DEV), abs_coord=abs_coord, polar_coord=polar)
+            assert abs(loss.item() - g[f"hmse_{tag}"]) <= 1e-6 * abs(g[f"hmse_{tag}"]), tag
+            loss.backward()
+            assert torch.isfinite(pt.grad).all()
+            if abs_coord:
+                assert rel(pt.grad.cpu().numpy(), g[f"hmse_grad_{tag}"]) < 1e-6, tag
+
+
 # ---- anomaly-score distances (SURVEY 8.f rank 2) -----------------------------------------------------------
 @pytest.mark.parametrize("B,N,D,lorentz", [(5, 30, 3, False), (3, 30, 4, False), (4, 30, 4, True), (2, 150, 4, True), (7, 1, 3, False),
                                             (300, 30, 3, False)])
@@ -450,8 +489,6 @@ def test_hungarian_mse_loss_value_and_gradient():
     got.backward()
     assert abs(got.item() - want.item()) <= 1e-6 * abs(want.item())
     assert torch.allclose(pd.grad.cpu(), ph.grad, rtol=1e-6, atol=1e-9)
-    with pytest.raises(NotImplementedError):
-        HungarianMSELoss()(pd, torch.from_numpy(q).to(DEV), polar_coord=True)
     with pytest.raises(ValueError):
         HungarianMSELoss()(pd[..., :2], torch.from_numpy(q).to(DEV)[..., :2])
 

@@ -187,3 +187,109 @@ def test_anomaly_hungarian_oracle_properties():
     c = d[..., 0] ** 2 - (d[..., 1:] ** 2).sum(-1)
     assert np.all(t2 <= np.trace(c, axis1=1, axis2=2) + 1e-12)
 
+
+
+# ---- SURVEY 8.f components against fixtures produced by the reference itself (oracle/gen_golden_aux.py) ----------------
+def _aux():
+    return np.load(os.path.join(GOLDEN, "aux_reference.npz"))
+
+
+def test_anomaly_scores_match_the_reference_fixture():
+    """mse / chamfer / chamfer_lorentz / hungarian / hungarian_lorentz of utils/jet_analysis/anomaly_detection.py:454-590, plain
+    and batched: the numpy oracle equals the outputs of the imported reference module."""
+    from gen_golden_aux import ANOMALY_SHAPES, aux_inputs
+    g = _aux()
+    for s, shape in enumerate(ANOMALY_SHAPES):
+        p, q = aux_inputs(shape, s)
+        tag = "x".join(map(str, shape))
+        assert np.allclose(((p - q) ** 2).sum(-1), g[f"mse_{tag}"], rtol=1e-13)
+        for key in (f"chamfer_{tag}", f"chamfer_b2_{tag}"):
+            assert rel(O.anomaly_chamfer(p, q), g[key]) < 1e-13
+        for key in (f"hungarian_{tag}", f"hungarian_b2_{tag}"):
+            assert rel(O.anomaly_hungarian(p, q)[0], g[key]) < 1e-13
+        if shape[-1] == 4:
+            assert rel(O.anomaly_chamfer(p, q, lorentz=True), g[f"chamfer_lorentz_{tag}"]) < 1e-13
+            assert rel(O.anomaly_hungarian(p, q, lorentz=True)[0], g[f"hungarian_lorentz_{tag}"]) < 1e-13
+
+
+def test_hungarian_mse_coordinate_modes_match_the_reference_fixture():
+    from gen_golden_aux import HUNGARIAN_MODES, aux_inputs
+    g = _aux()
+    for s, shape in enumerate([(4, 30, 3), (3, 12, 4)]):
+        p, q = aux_inputs(shape, 100 + s)
+        for abs_coord, polar in HUNGARIAN_MODES:
+            tag = "x".join(map(str, shape)) + f"_abs{int(abs_coord)}_polar{int(polar)}"
+            assert abs(O.hungarian_mse_loss(p, q, abs_coord, polar) - g[f"hmse_{tag}"]) <= 1e-12 * abs(g[f"hmse_{tag}"]), tag
+
+
+def test_hungarian_coordinate_maps_of_the_package_match_the_oracle():
+    """The product's torch coordinate maps (CPU tensors are fine here: only the matching needs the GPU) against the oracle."""
+    import torch
+    from gen_golden_aux import HUNGARIAN_MODES, aux_inputs
+    from gnn_jet_autoencoder_b200.losses import hungarian_preprocess
+    for s, shape in enumerate([(4, 30, 3), (3, 12, 4)]):
+        p, q = aux_inputs(shape, 100 + s)
+        for abs_coord, polar in HUNGARIAN_MODES:
+            r, t = hungarian_preprocess(torch.from_numpy(p), torch.from_numpy(q), abs_coord, polar)
+            ro, to = O.hungarian_coords(p, q, abs_coord, polar)
+            assert rel(r.numpy(), ro) < 1e-13 and rel(t.numpy(), to) < 1e-13
+
+
+def test_permutation_helpers_match_the_reference_fixture():
+    import torch
+    from gnn_jet_autoencoder_b200.permutation import apply_perm, dev
+    g = _aux()
+    x, perm = torch.from_numpy(g["perm_x"]), torch.from_numpy(g["perm_perm"])
+    assert np.array_equal(apply_perm(perm, x).numpy(), g["perm_apply"])
+    assert np.allclose(dev(x, torch.from_numpy(g["perm_x"][:, ::-1].copy())).numpy(), g["perm_dev"], rtol=1e-13)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="needs the reference checkout (build container only)")
+def test_reference_consumers_drive_the_new_modules():
+    """Live drop-in check: the REFERENCE's own wiring code -- utils/argparse_utils.py defaults, utils/initialize.py
+    initialize_models / initialize_optimizers incl. the --load-to-train checkpoint path, utils/permutation.py PermutationTest's
+    constructor -- runs with the reference's Encoder / Decoder swapped for this package's, and both sides' state_dicts interchange."""
+    import argparse
+    import tempfile
+    import torch
+    from ref_import import add_reference_to_path
+    add_reference_to_path()
+    import models as ref_models
+    import utils.argparse_utils as A
+    import utils.initialize as I
+    import utils.permutation as PM
+    import gnn_jet_autoencoder_b200 as pkg
+    parser = argparse.ArgumentParser()
+    for fn in (A.parse_data_settings, A.parse_model_settings, A.parse_training_settings, A.parse_eval_settings):
+        parser = fn(parser) or parser
+    args = parser.parse_args(["--latent-map", "mean"])
+    args.device, args.dtype = torch.device("cpu"), torch.float64          # the CLI default dtype
+    ref_enc, ref_dec = I.initialize_models(args)
+    saved = (I.Encoder, I.Decoder)
+    try:
+        I.Encoder, I.Decoder = pkg.Encoder, pkg.Decoder
+        enc, dec = I.initialize_models(args)
+        assert isinstance(enc, pkg.Encoder) and isinstance(dec, pkg.Decoder)
+        for new, ref in ((enc, ref_enc), (dec, ref_dec)):
+            assert list(new.state_dict()) == list(ref.state_dict())
+            assert {k: tuple(v.shape) for k, v in new.state_dict().items()} == {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+            assert new.num_learnable_params == ref.num_learnable_params
+        opt_e, opt_d = I.initialize_optimizers(args, enc, dec)
+        assert sum(p.numel() for g in opt_e.param_groups for p in g["params"]) == enc.num_learnable_params
+        # checkpoint interchange through the reference's own loading code (utils/initialize.py:54-128)
+        with tempfile.TemporaryDirectory() as d:
+            os.makedirs(os.path.join(d, "weights_encoder")); os.makedirs(os.path.join(d, "weights_decoder"))
+            torch.save(ref_enc.state_dict(), os.path.join(d, "weights_encoder", "epoch_3_encoder_weights.pth"))
+            torch.save(ref_dec.state_dict(), os.path.join(d, "weights_decoder", "epoch_3_decoder_weights.pth"))
+            args.load_to_train, args.load_path, args.load_epoch = True, d, 3
+            enc2, dec2 = I.initialize_models(args)
+            for new, ref in ((enc2, ref_enc), (dec2, ref_dec)):
+                for k, v in new.state_dict().items():
+                    assert v.dtype == torch.float32 and np.allclose(v.numpy(), ref.state_dict()[k].numpy().astype(np.float32))
+            # and back: the new modules' checkpoint loads into the reference modules
+            ref_enc.load_state_dict(enc2.state_dict()); ref_dec.load_state_dict(dec2.state_dict())
+        # the reference's PermutationTest accepts the modules (its constructor moves them with .to(device, dtype))
+        pt = PM.PermutationTest(enc, dec, device=torch.device("cpu"), dtype=torch.float64)
+        assert pt.encoder is enc and all(p.dtype == torch.float32 for p in enc.parameters())
+    finally:
+        I.Encoder, I.Decoder = saved
