@@ -315,14 +315,13 @@ struct Bwd3Smem {
 // the other, and the per-thread dQ_j / d(wd) accumulators are shared (consecutive tiles are consecutive i of the same j).
 struct E3Slot {
   bool active, valid, last_i, pendW;
-  int i, jb;
+  int i, jb, slot;
   size_t node0;
   float dij;
   const float* st;      // staged [P_i part | de_i part] of the tile
-  uint32_t ph, phW;
 };
 
-template <int E0, int E1, int NWG, int S, int IC>
+template <int E0, int E1, int NWG, int S, int IC, bool PIPE>
 __global__ void __launch_bounds__(NWG * S * 128, 1) edge_bwd3_kernel(const E3Args A) {
   using SM = Bwd3Smem<E0, E1, NWG, S, IC>;
   constexpr int C0 = SM::C0, C1 = SM::C1;
@@ -403,6 +402,7 @@ __global__ void __launch_bounds__(NWG * S * 128, 1) edge_bwd3_kernel(const E3Arg
 #pragma unroll
   for (int c = 0; c < C0 / 2; ++c) q[c] = 0u;
   float d_cur = 0.f;
+  uint32_t ph_bits = 0u;      // bit s: parity of done[s]; bit 2 + s: parity of doneW[s] (phases belong to the slot, not to the record)
 
   auto stage_chunk = [&](int c) {      // this warp's channel parts of P_i and de_i for i in [c IC, ...) -> buffer c & 1
     const int ib = c * IC, n = min(IC, N - ib);
@@ -453,12 +453,12 @@ __global__ void __launch_bounds__(NWG * S * 128, 1) edge_bwd3_kernel(const E3Arg
       __syncwarp();
       if ((i / IC + 1) * IC < N) stage_chunk(i / IC + 1);
     }
-    sl.active = c_active; sl.valid = c_valid; sl.i = i; sl.jb = jb; sl.node0 = node0; sl.last_i = (i + 1 == N);
+    sl.active = c_active; sl.valid = c_valid; sl.i = i; sl.jb = jb; sl.node0 = node0; sl.last_i = (i + 1 == N); sl.slot = ts;
     sl.dij = d_cur;
     sl.st = s_st + (((i / IC) & 1) * IC + (i % IC)) * (C0 + C1);
     if (!sl.last_i) d_cur = __ldg(A.d + (node0 + i + 1) * A.NJ32 + jb * 32 + lane);
     // the weight-gradient GEMM of the tile that used this slot two tiles ago must have read A0 / D1
-    if (sl.pendW) { mbar_wait(bars + 2 + ts, sl.phW); sl.phW ^= 1u; sl.pendW = false; }
+    if (sl.pendW) { mbar_wait(bars + 2 + sl.slot, (ph_bits >> (2 + sl.slot)) & 1u); ph_bits ^= 4u << sl.slot; sl.pendW = false; }
     {
       uint8_t* a0_row = tb + SM::t_a0 + row * 16;
       const float* st = sl.st;
@@ -502,7 +502,7 @@ __global__ void __launch_bounds__(NWG * S * 128, 1) edge_bwd3_kernel(const E3Arg
     const uint32_t tba = smem_u32(tb);
     const uint32_t acc0 = tmem_base + (uint32_t)((wg * 2 + ts) * ACC), acc = acc0 + ((uint32_t)(wq * 32) << 16);
     uint8_t* d1_row = tb + SM::t_d1 + row * 16;
-    mbar_wait(bars + ts, sl.ph); sl.ph ^= 1u;
+    mbar_wait(bars + ts, (ph_bits >> ts) & 1u); ph_bits ^= 1u << ts;
     tc_fence_after();
     const float* dei = sl.st + C0;
     const bool valid = sl.valid;
@@ -561,7 +561,7 @@ __global__ void __launch_bounds__(NWG * S * 128, 1) edge_bwd3_kernel(const E3Arg
     uint8_t* tb = gb + ts * SM::tile_bytes;
     const uint32_t acc = tmem_base + (uint32_t)((wg * 2 + ts) * ACC) + ((uint32_t)(wq * 32) << 16);
     const uint8_t* a0_row = tb + SM::t_a0 + row * 16;
-    mbar_wait(bars + ts, sl.ph); sl.ph ^= 1u;
+    mbar_wait(bars + ts, (ph_bits >> ts) & 1u); ph_bits ^= 1u << ts;
     tc_fence_after();
     float gsum = 0.f;
     const float dij = sl.dij;
@@ -607,23 +607,30 @@ __global__ void __launch_bounds__(NWG * S * 128, 1) edge_bwd3_kernel(const E3Arg
   };
 
   E3Slot sA, sB;
-  sA.pendW = sB.pendW = false; sA.ph = sB.ph = sA.phW = sB.phW = 0u;
+  sA.pendW = sB.pendW = false;
   sA.active = sA.valid = sA.last_i = sB.active = sB.valid = sB.last_i = false;
-  sA.i = sB.i = sA.jb = sB.jb = 0; sA.node0 = sB.node0 = 0; sA.dij = sB.dij = 0.f; sA.st = sB.st = s_st;
+  sA.i = sB.i = sA.jb = sB.jb = 0; sA.slot = 0; sB.slot = 1; sA.node0 = sB.node0 = 0; sA.dij = sB.dij = 0.f; sA.st = sB.st = s_st;
   const int ntile = g1 - g0;
+  // One copy of each stage in the instruction stream (the unrolled stages are several thousand instructions: two copies per
+  // slot thrash the instruction cache): the slot is a run-time index and the two slot records swap after every tile.
+  int ts = 0;
   if (ntile > 0) L0(sA, 0);
-  for (int t = 0; t < ntile; t += 2) {
-    E1f(sA, 0);
-    if (t + 1 < ntile) L0(sB, 1);
-    E0f(sA, 0, t + 1 == ntile);
-    if (t + 1 < ntile) {
-      E1f(sB, 1);
-      if (t + 2 < ntile) L0(sA, 0);
-      E0f(sB, 1, t + 2 == ntile);
+#pragma unroll 1
+  for (int t = 0; t < ntile; ++t) {
+    E1f(sA, ts);
+    if (PIPE) {
+      if (t + 1 < ntile) L0(sB, ts ^ 1);
+      E0f(sA, ts, t + 1 == ntile);
+      const E3Slot tmp = sA; sA = sB; sB = tmp;
+      ts ^= 1;
+    } else {
+      E0f(sA, ts, t + 1 == ntile);
+      if (t + 1 < ntile) L0(sA, ts);
     }
   }
-  if (sA.pendW) { mbar_wait(bars + 2, sA.phW); sA.phW ^= 1u; }      // all of this group's MMAs have completed
-  if (sB.pendW) { mbar_wait(bars + 3, sB.phW); sB.phW ^= 1u; }
+  // all of this group's MMAs have completed: the slot a record last used is kept in the record
+  if (sA.pendW) { mbar_wait(bars + 2 + sA.slot, (ph_bits >> (2 + sA.slot)) & 1u); ph_bits ^= 4u << sA.slot; }
+  if (sB.pendW) { mbar_wait(bars + 2 + sB.slot, (ph_bits >> (2 + sB.slot)) & 1u); ph_bits ^= 4u << sB.slot; }
   e3_cp_async_wait<0>();
   // d(wd): lanes by shuffles, warps through shared memory (fixed order)
 #pragma unroll
@@ -769,7 +776,8 @@ template <int E0, int E1, int NWG, int S, int IC>
 static int e3_launch_bwd(E3Args& A, int grid, cudaStream_t stream) {
   using SM = Bwd3Smem<E0, E1, NWG, S, IC>;
   static_assert(SM::total <= 227 * 1024, "backward shared-memory plan");
-  auto kern = edge_bwd3_kernel<E0, E1, NWG, S, IC>;
+  static const int pipe_env = getenv("GJ_E3_PIPE") ? atoi(getenv("GJ_E3_PIPE")) : 1;
+  auto kern = pipe_env ? edge_bwd3_kernel<E0, E1, NWG, S, IC, true> : edge_bwd3_kernel<E0, E1, NWG, S, IC, false>;
   cudaError_t ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::total);
   if (ce != cudaSuccess) { gj_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   long long ng = (long long)grid * NWG;      // every (jet, j block) is shared by at most two groups (two-addend atomic dQ sums)
