@@ -502,13 +502,19 @@ def time_dominant_kernel(tr, args, reps=20):
     din = tr.dx if idx == 0 else s["din"]
     st = torch.cuda.current_stream().cuda_stream
     P, G = tr.flat.data_ptr(), tr.grad.data_ptr()
+    saved = s.get("saved")
+    saved_ptr = saved.data_ptr() if saved is not None else None
     def launch():
         ops.raw_mp_bwd(s["desc"], hin.data_ptr(), s["e"].data_ptr(), P + 4 * s["off"], g.data_ptr(), din.data_ptr(),
-                       G + 4 * s["off"], tr.ws.data_ptr(), tr.ws_bytes, st)
+                       G + 4 * s["off"], tr.ws.data_ptr(), tr.ws_bytes, st, saved_ptr)
     from gnn_jet_autoencoder_b200 import _lib
     lib = _lib.load()
     def launch_kernel_only():
-        # the fused backward edge kernel ALONE, on the workspace the full call above has populated
+        # the fused backward edge kernel ALONE, as the training step runs it (saved forward by-products), on the workspace
+        # the full call above has populated
+        if saved_ptr:
+            return lib.gj_bench_edge_bwd_saved_only(s["desc"], hin.data_ptr(), P + 4 * s["off"], din.data_ptr(), G + 4 * s["off"],
+                                                    saved_ptr, tr.ws.data_ptr(), tr.ws_bytes, st)
         return lib.gj_bench_edge_bwd_only(s["desc"], hin.data_ptr(), P + 4 * s["off"], din.data_ptr(), G + 4 * s["off"],
                                           tr.ws.data_ptr(), tr.ws_bytes, st)
     for _ in range(3):
@@ -527,7 +533,7 @@ def time_dominant_kernel(tr, args, reps=20):
     us = a.elapsed_time(b) * 1e3 / reps
     flop = 2.0 * 2.0 * macs(s) * tr.N * tr.N * tr.B       # dgrad + wgrad of the dense formulation
     name = (f"edge_bwd2_kernel (fused recompute + dgrad + wgrad of encoder step {idx}, B={tr.B}, N={tr.N}; launched alone "
-            f"through gj_bench_edge_bwd_only)") if kernel_only else \
+            f"through gj_bench_edge_bwd{'_saved' if saved_ptr else ''}_only)") if kernel_only else \
            f"gj_mp_step_bwd (encoder step {idx}, B={tr.B}, N={tr.N}, all of its launches)"
     return dict(name=name, us=us, flop=flop, tflops=flop / (us * 1e-6) / 1e12)
 

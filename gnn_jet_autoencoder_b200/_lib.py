@@ -62,6 +62,7 @@ SIGNATURES = {
     "gj_linear_bwd": (C.c_int, [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "gj_bench_edge_fwd_only": (C.c_int, [C.POINTER(MPDesc), _P, _P, _P, _P, _SZ, _P]),
     "gj_bench_edge_bwd_only": (C.c_int, [C.POINTER(MPDesc), _P, _P, _P, _P, _P, _SZ, _P]),
+    "gj_bench_edge_bwd_saved_only": (C.c_int, [C.POINTER(MPDesc), _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "gj_mp_plan_info": (C.c_int, [C.POINTER(MPDesc), C.POINTER(C.c_int32)]),
     "gj_umma_selftest": (C.c_int, [_I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "gj_dense_gemm": (C.c_int, [_I, _I, _I, _I, _P, _P, _P, _I, _F, _P, _I, _P, _P, _SZ, _I, _P]),

@@ -462,6 +462,23 @@ int gj_bench_edge_bwd_only(const gj_mp_desc* d, const float* h, const float* par
                       (cudaStream_t)stream, 1, nullptr, nullptr);
 }
 
+/* As gj_bench_edge_bwd_only, for the step as the trainer runs it: `saved` was filled by gj_mp_step_fwd_saving and `workspace`
+ * by the gj_mp_step_bwd_saved call that followed. */
+int gj_bench_edge_bwd_saved_only(const gj_mp_desc* d, const float* h, const float* params, float* dh, float* dparams, const void* saved,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  g_err[0] = 0;
+  MPLayout L; const char* why;
+  int rc = gj_fill_arch(d, &L, &why);
+  if (rc || !h || !params || !dh || !dparams || !saved || !workspace) { gj_set_error("gj_bench_edge_bwd_saved_only: %s", rc ? why : "null pointer"); return GJ_ERR_INVALID; }
+  if (!tc2_path(L, d->precision)) { gj_set_error("gj_bench_edge_bwd_saved_only: step does not run the fused tensor-core kernel"); return GJ_ERR_INVALID; }
+  const StepWs w = plan_ws(L, d->precision, true);
+  if (workspace_bytes < w.total * sizeof(float)) { gj_set_error("gj_bench_edge_bwd_saved_only: workspace too small"); return GJ_ERR_WORKSPACE; }
+  float* ws = (float*)workspace;
+  float* pre = (float*)saved;
+  return gj_edge_bwd2(L, h, pre + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.part, pre + w.wimg, pre + w.dist, true,
+                      (cudaStream_t)stream, 1, nullptr, nullptr);
+}
+
 int gj_mp_plan_info(const gj_mp_desc* d, int32_t* info) {
   g_err[0] = 0;
   MPLayout L; const char* why;

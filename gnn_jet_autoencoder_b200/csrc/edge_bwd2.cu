@@ -117,6 +117,13 @@ __device__ __forceinline__ float warp_transpose_sum16(const float (&v)[16], int 
   return w1 + __shfl_xor_sync(0xffffffffu, w1, 1);
 }
 
+// strong load (see prefetch() in the kernel)
+__device__ __forceinline__ float ld_relaxed_f32(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.gpu.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // dz pair (bf16x2) = bf16(da pair) * leaky'(a pair): slope = 1 where a > 0, alpha elsewhere
 __device__ __forceinline__ uint32_t dz_pack(float lo, float hi, uint32_t a_pair, __nv_bfloat162 one_m_alpha2, __nv_bfloat162 alpha2) {
   const __nv_bfloat162 zero2 = __float2bfloat162_rn(0.f);
@@ -125,8 +132,8 @@ __device__ __forceinline__ uint32_t dz_pack(float lo, float hi, uint32_t a_pair,
 }
 
 // optional stage timeline of tile group 0 of CTA 0 (GJ_TRACE=4): 16 clock stamps per tile
-__device__ long long g_b2_trace[16 * 128];
-#define B2_STAMP(s) do { if (TRACE && blockIdx.x == 0 && tid == 0 && tr_n < 128) g_b2_trace[tr_n * 16 + (s)] = clock64(); } while (0)
+__device__ long long g_b2_trace[24 * 128];
+#define B2_STAMP(s) do { if (TRACE && blockIdx.x == 0 && tid == 0 && tr_n < 128) g_b2_trace[tr_n * 24 + (s)] = clock64(); } while (0)
 
 template <int E0, int E1, int E2, int E3, int NWG, bool TRACE>
 __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args A) {
@@ -316,9 +323,10 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args 
     for (int c = 0; c < E0; ++c) { dwd[c] = 0.f; dq[c] = 0.f; }
 #pragma unroll
     for (int c = 0; c < E0 / 2; ++c) q[c] = 0u;
-    float d_cur = 0.f;
+    float d_cur = 0.f;       // d_ij of the tile whose first layer runs next
+    float d_tile = 0.f;      // d_ij of the tile in the tensor-core stages
+    float de_lane = 0.f;     // de_i[lane & 15] of the tile in the tensor-core stages
     uint32_t ph = 0, ph2 = 0, phW = 0;
-    bool pending2 = false;
     int tr_n = 0;
 
     auto stage_chunk = [&](int c) {      // P_i of i in [c * B2_IC, ...) -> buffer c & 1
@@ -339,9 +347,9 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args 
 #pragma unroll
       for (int c = 0; c < E0; ++c) dq[c] = 0.f;
     };
-
-    for (int g = g0; g < g1; ++g) {
-      B2_STAMP(0);
+    // staging for tile (k, i): a new (jet, j block) loads Q_j, d_ij and the first P_i chunks; otherwise the next chunk is
+    // prefetched on entering a chunk
+    auto refill = [&]() {
       if (fresh) {
         const int task = 4 * k + wq;
         active = task < ntasks;
@@ -375,48 +383,77 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args 
         __syncwarp();
         if ((i / B2_IC + 1) * B2_IC < N) stage_chunk(i / B2_IC + 1);
       }
-      const bool last_i = (i + 1 == N);
-      const float dij = d_cur;
-
-      // ---- L0: a0 -> shared A0 (needs the previous tile's wgrad1, which reads A0, to have completed) ----
-      if (pending2) { mbar_wait(done2, ph2); ph2 ^= 1u; }
-      B2_STAMP(1);
-      {
-        const float* Pi = s_pi + (((i / B2_IC) & 1) * B2_IC + (i % B2_IC)) * E0;
-        const float2 d2 = make_float2(dij, dij);
+    };
+    // L0 of tile (k, i): a0 -> shared A0 (the previous tile's wgrad1, which reads A0, must have completed), F1 issued
+    auto first_layer = [&]() {
+      const float* Pi = s_pi + (((i / B2_IC) & 1) * B2_IC + (i % B2_IC)) * E0;
+      const float2 d2 = make_float2(d_cur, d_cur);
 #pragma unroll
-        for (int c = 0; c < E0; c += 8) {
-          uint32_t o[4];
+      for (int c = 0; c < E0; c += 8) {
+        uint32_t o[4];
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            const int cc = c + 4 * hh;
-            const float4 p = *reinterpret_cast<const float4*>(Pi + cc);
-            const float4 w = *reinterpret_cast<const float4*>(s_wd + cc);
-            const float2 z0 = fma2(make_float2(w.x, w.y), d2, add2(make_float2(p.x, p.y), unpack_bf2(q[cc / 2])));
-            const float2 z1 = fma2(make_float2(w.z, w.w), d2, add2(make_float2(p.z, p.w), unpack_bf2(q[cc / 2 + 1])));
-            o[2 * hh] = leaky_pack(z0.x, z0.y, alpha2);
-            o[2 * hh + 1] = leaky_pack(z1.x, z1.y, alpha2);
-          }
-          *reinterpret_cast<uint4*>(a0_row + (c >> 3) * 2048) = make_uint4(o[0], o[1], o[2], o[3]);
+        for (int hh = 0; hh < 2; ++hh) {
+          const int cc = c + 4 * hh;
+          const float4 p = *reinterpret_cast<const float4*>(Pi + cc);
+          const float4 w = *reinterpret_cast<const float4*>(s_wd + cc);
+          const float2 z0 = fma2(make_float2(w.x, w.y), d2, add2(make_float2(p.x, p.y), unpack_bf2(q[cc / 2])));
+          const float2 z1 = fma2(make_float2(w.z, w.w), d2, add2(make_float2(p.z, p.w), unpack_bf2(q[cc / 2 + 1])));
+          o[2 * hh] = leaky_pack(z0.x, z0.y, alpha2);
+          o[2 * hh + 1] = leaky_pack(z1.x, z1.y, alpha2);
         }
-        fence_proxy_async();
-        publish(0);
+        *reinterpret_cast<uint4*>(a0_row + (c >> 3) * 2048) = make_uint4(o[0], o[1], o[2], o[3]);
       }
-      // de_i (warp-uniform address) for the F3 epilogue and the next tile's d_ij: issued here, behind the shared-memory
-      // loads of L0 (a load that shares their scoreboard would stall them), consumed much later
-      float4 de4[E3 / 4];
-      {
-        const float4* dsrc = reinterpret_cast<const float4*>(A.de + (node0 + i) * E3);
+      d_tile = d_cur;
+      B2_STAMP(17);
+      fence_proxy_async();
+      B2_STAMP(18);
+      tc_fence_before();
+      named_bar_sync(1 + wg, 128);
+      B2_STAMP(19);
+      issue_stage(0);
+    };
+    // de_i (one float per lane, broadcast by shuffles in the F3 epilogue) of the tile just published and d_ij of the tile
+    // after it.  Strong (relaxed) loads: neither the compiler nor ptxas may hoist them above the group barrier of publish(0)
+    // -- hoisted in front of the first layer, they shared a scoreboard with its shared-memory loads and stalled it for a
+    // full global-memory latency per tile (6 % of the kernel's stall samples).  They are consumed a GEMM wait later.
+    auto prefetch = [&]() {
+      de_lane = ld_relaxed_f32(A.de + (node0 + i) * E3 + (lane & 15));
+      if (i + 1 < N) d_cur = ld_relaxed_f32(A.d + (node0 + i + 1) * A.NJ32 + jb * 32 + lane);
+    };
+    // second half of the B1 epilogue of tile (task, it): dQ_j, d(wd), G_ij, dP_i
+    auto b1_tail = [&](const float (&z0)[16], const float (&z1)[16], int it, float dt) {
+      float gsum = 0.f;
+      float* dp_dst = A.NJB > 1 ? A.dp_part + ((size_t)jb * A.B * N + node0 + it) * E0 : A.dpq + (node0 + it) * (2 * E0);
 #pragma unroll
-        for (int c = 0; c < E3 / 4; ++c) de4[c] = __ldg(dsrc + c);
+      for (int hf = 0; hf < 2; ++hf) {
+        const float (&z)[16] = hf == 0 ? z0 : z1;
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const float4 w = *reinterpret_cast<const float4*>(s_wd + 16 * hf + 4 * c4);
+          gsum = fmaf(z[4 * c4], w.x, gsum); gsum = fmaf(z[4 * c4 + 1], w.y, gsum);
+          gsum = fmaf(z[4 * c4 + 2], w.z, gsum); gsum = fmaf(z[4 * c4 + 3], w.w, gsum);
+        }
+#pragma unroll
+        for (int c = 0; c < 16; ++c) { dq[16 * hf + c] += z[c]; dwd[16 * hf + c] = fmaf(z[c], dt, dwd[16 * hf + c]); }
+        const float s = warp_transpose_sum16(z, lane);
+        if (active && (lane & 1) == 0) dp_dst[16 * hf + (lane >> 1)] = s;
       }
-      const float d_next = (!last_i) ? __ldg(A.d + (node0 + i + 1) * A.NJ32 + jb * 32 + lane) : 0.f;
-      B2_STAMP(2);
+      if (active) A.G[(node0 + it) * A.NJ32 + jb * 32 + lane] = valid ? gsum : 0.f;
+    };
+
+    if (g0 < g1) {
+      refill();
+      first_layer();
+      prefetch();
+    }
+    for (int g = g0; g < g1; ++g) {
+      B2_STAMP(0);
+      const float dij = d_tile;
 
       // ---- F1 epilogue: a1 = leaky(acc) -> TMEM [0,64) + shared X1 ----
       mbar_wait(done, ph); ph ^= 1u;
       tc_fence_after();
-      B2_STAMP(3);
+      B2_STAMP(1);
       {
         uint32_t va[16], vb[16];
         tmem_ld16_u(slot, va);
@@ -441,12 +478,12 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args 
         fence_proxy_async();
         publish(1);
       }
-      B2_STAMP(4);
+      B2_STAMP(2);
 
       // ---- F2 epilogue: a2 = leaky(acc[64,128)) -> TMEM [0,32) + shared X2 ----
       mbar_wait(done, ph); ph ^= 1u;
       tc_fence_after();
-      B2_STAMP(5);
+      B2_STAMP(3);
       {
         uint32_t va[16], vb[16];
         tmem_ld16_u(slot + 64, va);
@@ -471,22 +508,24 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args 
         fence_proxy_async();
         publish(2);
       }
-      B2_STAMP(6);
+      B2_STAMP(4);
 
       // ---- F3 epilogue: dz3 = de_i * leaky'(acc[32,48)), zero on padded rows -> TMEM [48,56) + shared D3 ----
       mbar_wait(done, ph); ph ^= 1u;
       tc_fence_after();
-      B2_STAMP(7);
+      B2_STAMP(5);
       {
         uint32_t v[16];
         tmem_ld16_u(slot + 32, v);
+        float def[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) def[c] = __shfl_sync(0xffffffffu, de_lane, c);
         tmem_ld_wait(); tmem_pin16(v);
-        const float* def = reinterpret_cast<const float*>(de4);
         uint32_t o[8];
 #pragma unroll
         for (int p = 0; p < 8; ++p) {
           const float z0 = __uint_as_float(v[2 * p]), z1 = __uint_as_float(v[2 * p + 1]);
-          const float g0v = valid ? def[2 * p] * (z0 > 0.f ? 1.f : alpha) : 0.f;
+          const float g0v = valid ? def[2 * p] * (z0 > 0.f ? 1.f : alpha) : 0.f;      // padded rows: dz3 = 0
           const float g1v = valid ? def[2 * p + 1] * (z1 > 0.f ? 1.f : alpha) : 0.f;
           db3[2 * p] += g0v; db3[2 * p + 1] += g1v;
           o[p] = bf2_as_u32(__floats2bfloat162_rn(g0v, g1v));
@@ -498,12 +537,12 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args 
         fence_proxy_async();
         publish(3);
       }
-      B2_STAMP(8);
+      B2_STAMP(6);
 
       // ---- B3 epilogue: dz2 = acc[64,128) * leaky'(a2) -> shared X2, in place over a2 (signs from TMEM [0,32)) ----
       mbar_wait(done, ph); ph ^= 1u;
       tc_fence_after();
-      B2_STAMP(9);
+      B2_STAMP(7);
       {
         uint32_t va[16], vb[16], sa[8], sb[8];
         tmem_ld16_u(slot + 64, va);
@@ -530,12 +569,12 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args 
         fence_proxy_async();
         publish(4);
       }
-      B2_STAMP(10);
+      B2_STAMP(8);
 
       // ---- B2 epilogue: dz1 = acc[0,128) * leaky'(a1) -> TMEM [0,64) + shared X1, in place over a1 ----
       mbar_wait(done, ph); ph ^= 1u;
       tc_fence_after();
-      B2_STAMP(11);
+      B2_STAMP(9);
       {
         uint32_t va[16], vb[16];
         tmem_ld16_u(slot, va);
@@ -564,53 +603,50 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args 
         fence_proxy_async();
         publish(5);
       }
-      B2_STAMP(12);
+      B2_STAMP(10);
 
-      // ---- B1 epilogue: dz0 = acc[64,96) * leaky'(a0) in fp32 -> dP_i, dQ_j, d(wd), G_ij ----
+      // ---- B1 epilogue, first half: dz0 = acc[64,96) * leaky'(a0) in fp32 (registers) ----
       mbar_wait(done, ph); ph ^= 1u;
       tc_fence_after();
-      pending2 = true;
-      B2_STAMP(13);
-      {
-        float gsum = 0.f;
-        float* dp_dst = A.NJB > 1 ? A.dp_part + ((size_t)jb * A.B * N + node0 + i) * E0 : A.dpq + (node0 + i) * (2 * E0);
+      B2_STAMP(11);
+      float z0[16], z1[16];
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          uint32_t v[16];
-          tmem_ld16_u(slot + 64 + 16 * hf, v);
-          const uint4 s0 = *reinterpret_cast<const uint4*>(a0_row + (2 * hf) * 2048);
-          const uint4 s1 = *reinterpret_cast<const uint4*>(a0_row + (2 * hf + 1) * 2048);
-          const uint32_t sg[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-          tmem_ld_wait(); tmem_pin16(v);
-          float z[16];
+      for (int hf = 0; hf < 2; ++hf) {
+        float (&z)[16] = hf == 0 ? z0 : z1;
+        uint32_t v[16];
+        tmem_ld16_u(slot + 64 + 16 * hf, v);
+        const uint4 s0 = *reinterpret_cast<const uint4*>(a0_row + (2 * hf) * 2048);
+        const uint4 s1 = *reinterpret_cast<const uint4*>(a0_row + (2 * hf + 1) * 2048);
+        const uint32_t sg[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        tmem_ld_wait(); tmem_pin16(v);
 #pragma unroll
-          for (int p = 0; p < 8; ++p) {
-            // bf16 pair: low half = even channel.  a > 0  <=>  sign bit clear and not zero (a0 == 0 only if z == 0)
-            const float alo = __uint_as_float(sg[p] << 16), ahi = __uint_as_float(sg[p] & 0xffff0000u);
-            z[2 * p] = __uint_as_float(v[2 * p]) * (alo > 0.f ? 1.f : alpha);
-            z[2 * p + 1] = __uint_as_float(v[2 * p + 1]) * (ahi > 0.f ? 1.f : alpha);
-          }
-#pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) {
-            const float4 w = *reinterpret_cast<const float4*>(s_wd + 16 * hf + 4 * c4);
-            gsum = fmaf(z[4 * c4], w.x, gsum); gsum = fmaf(z[4 * c4 + 1], w.y, gsum);
-            gsum = fmaf(z[4 * c4 + 2], w.z, gsum); gsum = fmaf(z[4 * c4 + 3], w.w, gsum);
-          }
-#pragma unroll
-          for (int c = 0; c < 16; ++c) { dq[16 * hf + c] += z[c]; dwd[16 * hf + c] = fmaf(z[c], dij, dwd[16 * hf + c]); }
-          const float s = warp_transpose_sum16(z, lane);
-          if (active && (lane & 1) == 0) dp_dst[16 * hf + (lane >> 1)] = s;
+        for (int p = 0; p < 8; ++p) {
+          // bf16 pair: low half = even channel.  a > 0  <=>  sign bit clear and not zero (a0 == 0 only if z == 0)
+          const float alo = __uint_as_float(sg[p] << 16), ahi = __uint_as_float(sg[p] & 0xffff0000u);
+          z[2 * p] = __uint_as_float(v[2 * p]) * (alo > 0.f ? 1.f : alpha);
+          z[2 * p + 1] = __uint_as_float(v[2 * p + 1]) * (ahi > 0.f ? 1.f : alpha);
         }
-        if (active) A.G[(node0 + i) * A.NJ32 + jb * 32 + lane] = valid ? gsum : 0.f;
       }
       tc_fence_before();
-      B2_STAMP(14);
+      // second half (registers only): runs while the weight-gradient GEMMs of this tile, which read A0 / X1 / X2, complete
+      const bool more = g + 1 < g1;
+      b1_tail(z0, z1, i, dij);
+      B2_STAMP(15);
+      if (i + 1 == N) { flush_dq(); i = 0; ++k; fresh = true; } else ++i;
+      if (more) {
+        refill();
+        B2_STAMP(16);
+        mbar_wait(done2, ph2); ph2 ^= 1u;      // [dW1 | db1] += dz1^T [a0 | 1] has read A0
+        B2_STAMP(12);
+        first_layer();
+        B2_STAMP(13);
+        prefetch();
+        B2_STAMP(14);
+      }
       ++tr_n;
-      d_cur = d_next;
-      if (++i == N) { flush_dq(); i = 0; ++k; fresh = true; }
     }
     if (!fresh) flush_dq();      // the group's last (jet, j block) ended mid-way: the next group adds the rest
-    if (pending2) { mbar_wait(done2, ph2); ph2 ^= 1u; }      // all of this group's MMAs have completed
+    if (g0 < g1) { mbar_wait(done2, ph2); ph2 ^= 1u; }      // all of this group's MMAs have completed
     cp_async_wait<0>();
     // d(wd), db3: lanes by shuffles, warps through shared memory (fixed order); the scratch lies over group 0's X1, which
     // is free once every group's GEMMs have completed
@@ -854,7 +890,7 @@ int gj_pair_dist_bwd(const MPLayout& L, const float* h, const float* G, float* d
 // debugging aid (not part of the ABI header): stage timeline of the last traced backward launch
 extern "C" int gj_debug_read_bwd2_trace(long long* out) {
   cudaDeviceSynchronize();
-  return cudaMemcpyFromSymbol(out, g_b2_trace, sizeof(long long) * 16 * 128) == cudaSuccess ? 0 : 1;
+  return cudaMemcpyFromSymbol(out, g_b2_trace, sizeof(long long) * 24 * 128) == cudaSuccess ? 0 : 1;
 }
 
 static int pd_jpb(const MPLayout& L) { int j = 256 / L.N; return j < 1 ? 1 : (j > 8 ? 8 : j); }

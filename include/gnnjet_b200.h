@@ -177,6 +177,10 @@ int gj_bench_edge_fwd_only(const gj_mp_desc* d, const float* h, const float* par
                            void* workspace, size_t workspace_bytes, void* stream);
 int gj_bench_edge_bwd_only(const gj_mp_desc* d, const float* h, const float* params, float* dh, float* dparams,
                            void* workspace, size_t workspace_bytes, void* stream);
+/* The same for the step as a training loop runs it: `saved` filled by gj_mp_step_fwd_saving, `workspace` by the
+ * gj_mp_step_bwd_saved call that followed (the backward kernel then reads the saved P|Q, packed weights and pair distances). */
+int gj_bench_edge_bwd_saved_only(const gj_mp_desc* d, const float* h, const float* params, float* dh, float* dparams,
+                                 const void* saved, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Resource plan of the tensor-core (GJ_PREC_BF16) edge kernels for this step (host only, no device work):
  * info[0] forward shared-memory bytes per CTA, info[1] forward TMEM columns, info[2] backward shared-memory bytes
