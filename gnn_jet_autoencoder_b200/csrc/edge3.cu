@@ -19,6 +19,7 @@
 #include <stdlib.h>
 
 #include "tc2_common.cuh"
+#include "tma.cuh"
 
 namespace {
 using namespace tc2;
@@ -104,7 +105,7 @@ struct Fwd3Smem {
 };
 
 template <int E0, int E1, int NWG, int IC>
-__global__ void __launch_bounds__(NWG * 128, 1) edge_fwd3_kernel(const E3Args A) {
+__global__ void __launch_bounds__(NWG * 128, 1) edge_fwd3_kernel(const E3Args A, const __grid_constant__ CUtensorMap tm_w) {
   static_assert(E0 % 16 == 0 && E1 % 16 == 0 && E0 <= 128 && E1 <= 128, "widths");
   constexpr int SLOT = E0 + E1;      // TMEM columns of a tile group: two packed a0 buffers (E0 / 2 each), then the accumulator
   static_assert(NWG * SLOT <= 512, "TMEM columns");
@@ -117,19 +118,25 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_fwd3_kernel(const E3Args A)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::o_slot);
   float* s_wd = reinterpret_cast<float*>(smem + S::o_wd);
 
-  load_wimage<WImage3<E0, E1>::bytes>(smem + S::o_img, A.wimg, tid, NWG * 128);
   for (int c = tid; c < E0; c += NWG * 128) s_wd[c] = __ldg(A.params + A.pWd + c * A.K0);
   for (int idx = tid; idx < 1024; idx += NWG * 128)
     reinterpret_cast<uint32_t*>(smem + S::o_ones)[idx] = (idx < 512 && (idx & 3) == 0) ? 0x3F803F80u : 0u;
+  uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + S::o_bar) + 15;      // byte 120: the parameter image (TMA) has landed
+  static_assert(NWG <= 15, "mbarrier slots");
   if (tid == 0) {
     for (int b = 0; b < NWG; ++b) mbar_init(reinterpret_cast<uint64_t*>(smem + S::o_bar) + b, 1);
+    mbar_init(bar_w, 1);
     fence_barrier_init();
+    tma::prefetch_map(&tm_w);
+    tma::mbar_expect_tx(bar_w, WImage3<E0, E1>::bytes);
+    tma::load_2d(smem + S::o_img, &tm_w, 0, 0, bar_w);
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  mbar_wait(bar_w, 0u);
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t slot = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(wg * SLOT);
   const uint32_t slot0 = tmem_base + (uint32_t)(wg * SLOT);
@@ -322,7 +329,7 @@ struct E3Slot {
 };
 
 template <int E0, int E1, int NWG, int S, int IC, bool PIPE>
-__global__ void __launch_bounds__(NWG * S * 128, 1) edge_bwd3_kernel(const E3Args A) {
+__global__ void __launch_bounds__(NWG * S * 128, 1) edge_bwd3_kernel(const E3Args A, const __grid_constant__ CUtensorMap tm_w) {
   using SM = Bwd3Smem<E0, E1, NWG, S, IC>;
   constexpr int C0 = SM::C0, C1 = SM::C1;
   static_assert(C0 % 16 == 0 && C1 % 16 == 0 && E0 <= 128 && E1 <= 128 && (E1 == 64 || E1 == 128), "widths");
@@ -342,7 +349,6 @@ __global__ void __launch_bounds__(NWG * S * 128, 1) edge_bwd3_kernel(const E3Arg
   float* s_wd = reinterpret_cast<float*>(smem + SM::o_wd);
   float* s_red = reinterpret_cast<float*>(smem + SM::o_red);
 
-  load_wimage<WImage3<E0, E1>::bytes>(smem + SM::o_img, A.wimg, tid, NT);
   for (int idx = tid; idx < 512; idx += NT) reinterpret_cast<uint32_t*>(smem + SM::o_zero)[idx] = 0u;
   for (int c = tid; c < E0; c += NT) s_wd[c] = __ldg(A.params + A.pWd + c * A.K0);
   for (int idx = tid; idx < NWG * 2 * 1024; idx += NT) {      // ones slab (channels E0, E0 + 1 = 1.0: bias hi + lo) and zero slab of every tile slot
@@ -354,15 +360,22 @@ __global__ void __launch_bounds__(NWG * S * 128, 1) edge_bwd3_kernel(const E3Arg
     const int gs = idx / ((E1 / 8) * 512), w = idx - gs * ((E1 / 8) * 512);
     reinterpret_cast<uint32_t*>(smem + SM::o_grp + (gs >> 1) * SM::grp_bytes + (gs & 1) * SM::tile_bytes + SM::t_d1)[w] = 0u;
   }
+  uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + SM::o_bar) + 15;      // byte 120: the parameter image (TMA) has landed
+  static_assert(4 * NWG <= 15, "mbarrier slots");
   if (tid == 0) {
     for (int b = 0; b < 4 * NWG; ++b) mbar_init(reinterpret_cast<uint64_t*>(smem + SM::o_bar) + b, 1);
+    mbar_init(bar_w, 1);
     fence_barrier_init();
+    tma::prefetch_map(&tm_w);
+    tma::mbar_expect_tx(bar_w, WImage3<E0, E1>::bytes);
+    tma::load_2d(smem + SM::o_img, &tm_w, 0, 0, bar_w);
   }
   if (warp == 0) tmem_alloc(tmem_slot, TCOLS);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  mbar_wait(bar_w, 0u);
   const uint32_t tmem_base = *tmem_slot;
   if (warp < 4) {      // the shared gradient accumulator starts at zero: every weight-gradient MMA accumulates
     uint32_t z[16];
@@ -745,7 +758,10 @@ static int e3_launch_fwd(const MPLayout& L, E3Args& A, float* e_out, float* ws, 
   int grid = gj_num_sms();
   const int max_grid = (A.tiles_total + NWG - 1) / NWG;
   if (grid > max_grid) grid = max_grid;
-  kern<<<grid, NWG * 128, SM::total, stream>>>(A);
+  CUtensorMap tm_w;      // the parameter image as rows of 1 KB, one box
+  static_assert(WImage3<E0, E1>::bytes % 1024 == 0 && WImage3<E0, E1>::bytes / 1024 <= 256, "one TMA box");
+  if (int rc = gj_tmap_2d(&tm_w, A.wimg, 256, WImage3<E0, E1>::bytes / 1024, 1024, 256, WImage3<E0, E1>::bytes / 1024)) return rc;
+  kern<<<grid, NWG * 128, SM::total, stream>>>(A, tm_w);
   E3_CHECK("edge_fwd3 launch");
   return GJ_OK;
 }
@@ -784,7 +800,10 @@ static int e3_launch_bwd(E3Args& A, int grid, cudaStream_t stream) {
   const long long tasks4 = ((long long)A.B * A.NJB + 3) / 4;
   if (ng > tasks4) ng = tasks4;
   A.ngroups = (int)(ng < 1 ? 1 : ng);
-  kern<<<grid, NWG * S * 128, SM::total, stream>>>(A);
+  CUtensorMap tm_w;
+  static_assert(WImage3<E0, E1>::bytes % 1024 == 0 && WImage3<E0, E1>::bytes / 1024 <= 256, "one TMA box");
+  if (int rc = gj_tmap_2d(&tm_w, A.wimg, 256, WImage3<E0, E1>::bytes / 1024, 1024, 256, WImage3<E0, E1>::bytes / 1024)) return rc;
+  kern<<<grid, NWG * S * 128, SM::total, stream>>>(A, tm_w);
   E3_CHECK("edge_bwd3 launch");
   return GJ_OK;
 }

@@ -36,6 +36,7 @@
 #include <stdlib.h>
 
 #include "tc2_common.cuh"
+#include "tma.cuh"
 
 namespace {
 using namespace tc2;
@@ -54,6 +55,7 @@ constexpr int B2_IC = 2;           // i's per staged P_i chunk (double buffered,
 template <int E0, int E1, int E2, int E3, int NWG>
 struct Bwd2Smem {
   static constexpr int o_bar = 0;                        // per group: (unused), done, done2, doneW
+  static constexpr int o_bar_w = 192;                    // parameter image (TMA) has landed
   static constexpr int o_slot = 256;
   static constexpr int o_wd = 384;                       // E0 floats
   static constexpr int o_ones = 512;                     // [8][16] bf16 ones (B of the db2 column sum)
@@ -136,7 +138,7 @@ __device__ long long g_b2_trace[24 * 128];
 #define B2_STAMP(s) do { if (TRACE && blockIdx.x == 0 && tid == 0 && tr_n < 128) g_b2_trace[tr_n * 24 + (s)] = clock64(); } while (0)
 
 template <int E0, int E1, int E2, int E3, int NWG, bool TRACE>
-__global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args A) {
+__global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args A, const __grid_constant__ CUtensorMap tm_w) {
   static_assert(E0 == 32 && E1 == 128 && E2 == 64 && E3 == 16, "TMEM / stage map is laid out for the 32-128-64-16 edge network");
   static_assert(NWG <= 3, "three 128-column slots + 128 gradient columns");
   using S = Bwd2Smem<E0, E1, E2, E3, NWG>;
@@ -152,7 +154,6 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args 
   // ---- one-time staging ----
   static_assert(S::o_b2 - S::o_b1 == WImage<E0, E1, E2, E3>::o_b2 && S::o_w1 - S::o_b1 == WImage<E0, E1, E2, E3>::o_w1 &&
                 S::o_grp - S::o_b1 == WImage<E0, E1, E2, E3>::bytes, "shared-memory plan embeds the packed parameter image");
-  load_wimage<WImage<E0, E1, E2, E3>::bytes>(smem + S::o_b1, A.wimg, tid, NT);
   for (int idx = tid; idx < 512; idx += NT) reinterpret_cast<uint32_t*>(smem + S::o_zero)[idx] = 0u;
   for (int c = tid; c < E0; c += NT) s_wd[c] = __ldg(A.params + A.pWd + c * A.K0);
   for (int idx = tid; idx < 64; idx += NT) reinterpret_cast<uint32_t*>(smem + S::o_ones)[idx] = 0x3F803F80u;
@@ -164,9 +165,15 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args 
     const int g = idx / ((E3 / 8) * 512), w = idx - g * ((E3 / 8) * 512);
     reinterpret_cast<uint32_t*>(smem + S::o_grp + g * S::grp_bytes + S::g_d3)[w] = 0u;
   }
+  uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + S::o_bar_w);
   if (tid == 0) {
     for (int g = 0; g < 4 * NWG; ++g) mbar_init(bars + g, 1);
+    mbar_init(bar_w, 1);
     fence_barrier_init();
+    // the packed bf16 parameter image (30 KB, one box) -> shared memory by TMA; everybody waits for it below
+    tma::prefetch_map(&tm_w);
+    tma::mbar_expect_tx(bar_w, WImage<E0, E1, E2, E3>::bytes);
+    tma::load_2d(smem + S::o_b1, &tm_w, 0, 0, bar_w);
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
   fence_proxy_async();
@@ -182,6 +189,7 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args 
     for (int c0 = 0; c0 < 128; c0 += 16) tmem_st16(tmem_base + ((uint32_t)(warp * 32) << 16) + 384 + c0, z);
     tmem_st_wait();
   }
+  mbar_wait(bar_w, 0u);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1001,7 +1009,10 @@ int gj_edge_bwd2(const MPLayout& L, const float* h, const float* pq, const float
   auto kern = trace_env == 4 ? edge_bwd2_kernel<32, 128, 64, 16, NWG, true> : edge_bwd2_kernel<32, 128, 64, 16, NWG, false>;
   ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::total);
   if (ce != cudaSuccess) { gj_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
-  kern<<<grid, NWG * 128, S::total, stream>>>(A);
+  CUtensorMap tm_w;      // the parameter image as rows of 1 KB
+  static_assert(WImage<32, 128, 64, 16>::bytes % 1024 == 0 && WImage<32, 128, 64, 16>::bytes / 1024 <= 256, "one TMA box");
+  if (int rc = gj_tmap_2d(&tm_w, wimg, 256, WImage<32, 128, 64, 16>::bytes / 1024, 1024, 256, WImage<32, 128, 64, 16>::bytes / 1024)) return rc;
+  kern<<<grid, NWG * 128, S::total, stream>>>(A, tm_w);
   ce = cudaGetLastError();
   if (ce != cudaSuccess) { gj_set_error("edge_bwd2 launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   if (kernel_only) return GJ_OK;

@@ -22,6 +22,7 @@
 #include <stdlib.h>
 
 #include "tc2_common.cuh"
+#include "tma.cuh"
 
 namespace {
 using namespace tc2;
@@ -42,6 +43,7 @@ constexpr int F2_IC = 8;           // i's per staged P_i | h_i chunk (double buf
 template <int E0, int E1, int E2, int E3, int NWG>
 struct Fwd2Smem {
   static constexpr int o_bar = 0;                       // NWG * 3 mbarriers
+  static constexpr int o_bar_w = 112;                   // parameter image (TMA) has landed
   static constexpr int o_slot = 128;
   static constexpr int o_wd = 256;                      // E0 floats
   static constexpr int o_img = 1024;                    // packed parameter image (WImage): bias chunks, W1, W2, W3
@@ -132,7 +134,7 @@ __device__ long long g_f2_trace[8 * 256];
 #define F2_STAMP(s) do { if (TRACE && blockIdx.x == 0 && tid == 0 && tr_n < 256) g_f2_trace[tr_n * 8 + (s)] = clock64(); } while (0)
 
 template <int E0, int E1, int E2, int E3, int NWG, bool TRACE>
-__global__ void __launch_bounds__(NWG * 128, 1) edge_fwd2_kernel(const Fwd2Args A) {
+__global__ void __launch_bounds__(NWG * 128, 1) edge_fwd2_kernel(const Fwd2Args A, const __grid_constant__ CUtensorMap tm_w) {
   static_assert(E0 == 32 && E3 == 16, "tile map assumes a 32-wide first and a 16-wide last edge layer");
   static_assert(E1 % 32 == 0 && E1 <= 128 && E2 % 32 == 0 && E1 / 2 + E2 <= 128 && E2 / 2 + E3 <= E1 / 2, "TMEM slot map");
   static_assert(NWG * 128 <= 512, "one 128-column TMEM slot per tile group");
@@ -146,7 +148,6 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_fwd2_kernel(const Fwd2Args 
   float* s_wd = reinterpret_cast<float*>(smem + S::o_wd);
 
   // ---- one-time staging: weights / biases as bf16 B operands, wd, the constant bias A chunk, barriers, TMEM ----
-  load_wimage<WImage<E0, E1, E2, E3>::bytes>(smem + S::o_img, A.wimg, tid, NWG * 128);
   for (int c = tid; c < E0; c += NWG * 128) s_wd[c] = __ldg(A.params + A.pWd + c * A.K0);
   for (int idx = tid; idx < 1024; idx += NWG * 128)     // ones chunk: k = 0, 1 -> 1.0 (bias hi + lo), k = 2..15 -> 0
     reinterpret_cast<uint32_t*>(smem + S::o_ones)[idx] = (idx < 512 && (idx & 3) == 0) ? 0x3F803F80u : 0u;
@@ -155,15 +156,22 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_fwd2_kernel(const Fwd2Args 
     const int nz = NWG * 4 * S::warp_bytes(A.Hb, A.Hs) / 4;
     for (int idx = tid; idx < nz; idx += NWG * 128) wz[idx] = 0.f;
   }
+  uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + S::o_bar_w);
   if (tid == 0) {
     for (int b = 0; b < NWG * 3; ++b) mbar_init(reinterpret_cast<uint64_t*>(smem + S::o_bar) + b, 1);
+    mbar_init(bar_w, 1);
     fence_barrier_init();
+    // the packed bf16 parameter image (30 KB, one box) -> shared memory by TMA
+    tma::prefetch_map(&tm_w);
+    tma::mbar_expect_tx(bar_w, WImage<E0, E1, E2, E3>::bytes);
+    tma::load_2d(smem + S::o_img, &tm_w, 0, 0, bar_w);
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  mbar_wait(bar_w, 0u);
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t slot = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(wg * 128);   // this thread's row of the group's slot
   const uint32_t slot0 = tmem_base + (uint32_t)(wg * 128);                                // lane 0 (MMA operand addresses)
@@ -461,7 +469,10 @@ int gj_edge_fwd2(const MPLayout& L, const float* h, const float* pq, const float
   int grid = gj_num_sms();
   const int max_grid = (A.tiles_total + NWG - 1) / NWG;
   if (grid > max_grid) grid = max_grid;
-  kern<<<grid, NWG * 128, smem, stream>>>(A);
+  CUtensorMap tm_w;      // the parameter image as rows of 1 KB
+  static_assert(WImage<32, 128, 64, 16>::bytes % 1024 == 0 && WImage<32, 128, 64, 16>::bytes / 1024 <= 256, "one TMA box");
+  if (int rc = gj_tmap_2d(&tm_w, wimg, 256, WImage<32, 128, 64, 16>::bytes / 1024, 1024, 256, WImage<32, 128, 64, 16>::bytes / 1024)) return rc;
+  kern<<<grid, NWG * 128, smem, stream>>>(A, tm_w);
   ce = cudaGetLastError();
   if (ce != cudaSuccess) { gj_set_error("edge_fwd2 launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   if (kernel_only) return GJ_OK;

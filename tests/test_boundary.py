@@ -166,7 +166,8 @@ def test_tensor_core_plans_fit_the_sm():
 
 
 def test_sass_uses_tcgen05_and_tmem():
-    """The built library must contain Blackwell tensor-core SASS (UTC*MMA / LDTM), B200_PROFILING.md."""
+    """The built library must contain Blackwell tensor-core SASS (UTC*MMA / LDTM) and TMA tensor loads (UTMALDG: the packed
+    edge-network weights are staged by cp.async.bulk.tensor), B200_PROFILING.md."""
     import shutil
     import subprocess
     exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
@@ -175,6 +176,7 @@ def test_sass_uses_tcgen05_and_tmem():
     sass = subprocess.run([exe, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "UTCHMMA" in sass or "UTCMMA" in sass
     assert "LDTM" in sass
+    assert "UTMALDG" in sass
 
 
 def test_permutation_helpers_match_the_per_jet_loops():
