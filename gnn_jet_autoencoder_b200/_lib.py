@@ -57,6 +57,12 @@ SIGNATURES = {
     "gj_param_norms_workspace": (_SZ, [_SZ]),
     "gj_latent_mean_fwd": (C.c_int, [_I, _I, _I, _P, _P, _P]),
     "gj_latent_mean_bwd": (C.c_int, [_I, _I, _I, _P, _P, _P]),
+    "gj_latent_extreme_fwd": (C.c_int, [_I, _I, _I, _I, _P, _P, _P]),
+    "gj_latent_extreme_bwd": (C.c_int, [_I, _I, _I, _P, _P, _P, _P, _P]),
+    "gj_output_transform_fwd": (C.c_int, [_SZ, _I, _I, _I, C.c_float, _P, _P, _P]),
+    "gj_output_transform_bwd": (C.c_int, [_SZ, _I, _I, _I, C.c_float, _P, _P, _P, _P]),
+    "gj_mse_workspace": (_SZ, []),
+    "gj_mse_fwd_bwd": (C.c_int, [_SZ, C.c_double, _P, _P, _P, _P, _P, _SZ, _P]),
     "gj_linear_fwd": (C.c_int, [_I, _I, _I, _P, _P, _P, _P, _P]),
     "gj_linear_bwd_workspace": (_SZ, [_I, _I, _I]),
     "gj_linear_bwd": (C.c_int, [_I, _I, _I, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),

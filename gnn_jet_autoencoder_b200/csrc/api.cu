@@ -103,6 +103,11 @@ size_t gj_norms_ws_bytes(size_t);
 int gj_norms_launch(const float*, size_t, float*, void*, size_t, cudaStream_t);
 int gj_latent_mean_fwd_launch(int, int, int, const float*, float*, cudaStream_t);
 int gj_latent_mean_bwd_launch(int, int, int, const float*, float*, cudaStream_t);
+int gj_latent_extreme_fwd_launch(int, int, int, int, const float*, float*, cudaStream_t);
+int gj_latent_extreme_bwd_launch(int, int, int, const float*, const float*, const float*, float*, cudaStream_t);
+int gj_out_transform_launch(size_t, int, int, int, float, const float*, const float*, float*, cudaStream_t);
+size_t gj_mse_ws_bytes();
+int gj_mse_launch(size_t, double, const float*, const float*, float*, float*, void*, size_t, cudaStream_t);
 
 extern "C" {
 
@@ -431,6 +436,46 @@ int gj_latent_mean_bwd(int32_t batch, int32_t num_nodes, int32_t width, const fl
   g_err[0] = 0;
   if (batch < 0 || num_nodes < 1 || width < 1) { gj_set_error("gj_latent_mean_bwd: bad shape"); return GJ_ERR_INVALID; }
   return gj_latent_mean_bwd_launch(batch, num_nodes, width, dz, dy, (cudaStream_t)stream);
+}
+
+int gj_latent_extreme_fwd(int32_t batch, int32_t num_nodes, int32_t width, int32_t is_min, const float* y, float* z, void* stream) {
+  g_err[0] = 0;
+  if (batch < 0 || num_nodes < 1 || width < 1) { gj_set_error("gj_latent_extreme_fwd: bad shape"); return GJ_ERR_INVALID; }
+  if (batch > 0 && (!y || !z)) { gj_set_error("gj_latent_extreme_fwd: null pointer"); return GJ_ERR_INVALID; }
+  return gj_latent_extreme_fwd_launch(batch, num_nodes, width, is_min != 0, y, z, (cudaStream_t)stream);
+}
+
+int gj_latent_extreme_bwd(int32_t batch, int32_t num_nodes, int32_t width, const float* y, const float* z, const float* dz, float* dy,
+                          void* stream) {
+  g_err[0] = 0;
+  if (batch < 0 || num_nodes < 1 || width < 1) { gj_set_error("gj_latent_extreme_bwd: bad shape"); return GJ_ERR_INVALID; }
+  if (batch > 0 && (!y || !z || !dz || !dy)) { gj_set_error("gj_latent_extreme_bwd: null pointer"); return GJ_ERR_INVALID; }
+  return gj_latent_extreme_bwd_launch(batch, num_nodes, width, y, z, dz, dy, (cudaStream_t)stream);
+}
+
+int gj_output_transform_fwd(size_t rows, int32_t dim, int32_t use_tanh, int32_t clamp_mask, float eps, const float* x, float* y, void* stream) {
+  g_err[0] = 0;
+  if (dim < 1 || dim > 31) { gj_set_error("gj_output_transform_fwd: bad width"); return GJ_ERR_INVALID; }
+  if (rows > 0 && (!x || !y)) { gj_set_error("gj_output_transform_fwd: null pointer"); return GJ_ERR_INVALID; }
+  return gj_out_transform_launch(rows * (size_t)dim, dim, use_tanh != 0, clamp_mask, eps, x, nullptr, y, (cudaStream_t)stream);
+}
+
+int gj_output_transform_bwd(size_t rows, int32_t dim, int32_t use_tanh, int32_t clamp_mask, float eps, const float* x, const float* dy,
+                            float* dx, void* stream) {
+  g_err[0] = 0;
+  if (dim < 1 || dim > 31) { gj_set_error("gj_output_transform_bwd: bad width"); return GJ_ERR_INVALID; }
+  if (rows > 0 && (!x || !dy || !dx)) { gj_set_error("gj_output_transform_bwd: null pointer"); return GJ_ERR_INVALID; }
+  return gj_out_transform_launch(rows * (size_t)dim, dim, use_tanh != 0, clamp_mask, eps, x, dy, dx, (cudaStream_t)stream);
+}
+
+size_t gj_mse_workspace(void) { return gj_mse_ws_bytes(); }
+
+int gj_mse_fwd_bwd(size_t count, double denom, const float* p, const float* q, float* terms, float* dp, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+  g_err[0] = 0;
+  if (!(denom > 0.0)) { gj_set_error("gj_mse_fwd_bwd: denom must be positive"); return GJ_ERR_INVALID; }
+  if (!terms || !workspace || (count > 0 && (!p || !q || !dp))) { gj_set_error("gj_mse_fwd_bwd: null pointer"); return GJ_ERR_INVALID; }
+  return gj_mse_launch(count, denom, p, q, terms, dp, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 /* Measurement hooks (declared in the header under "benchmark support"): relaunch ONLY the fused edge kernel of a step on

@@ -66,10 +66,119 @@ __global__ void latent_mean_bwd_kernel(int N, int W, const float* __restrict__ d
   dy[idx] = dz[b * W + c] / (float)N;
 }
 
+// 'max' / 'min' latent maps (encoder.py:150-155, torch.amax / torch.amin over the particle axis).  The adjoint follows
+// torch: the gradient of an extremum is shared evenly by the entries that attain it.
+__global__ void latent_extreme_fwd_kernel(int N, int W, int is_min, const float* __restrict__ y, float* __restrict__ z, int total) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int b = idx / W, c = idx - b * W;
+  const float* yp = y + (size_t)b * N * W + c;
+  float m = yp[0];
+  for (int n = 1; n < N; ++n) { const float v = yp[(size_t)n * W]; m = is_min ? fminf(m, v) : fmaxf(m, v); }
+  z[idx] = m;
+}
+__global__ void latent_extreme_bwd_kernel(int N, int W, const float* __restrict__ y, const float* __restrict__ z,
+                                          const float* __restrict__ dz, float* __restrict__ dy, int total) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int b = idx / W, c = idx - b * W;
+  const float* yp = y + (size_t)b * N * W + c;
+  float* dp = dy + (size_t)b * N * W + c;
+  const float m = z[idx];
+  int ties = 0;
+  for (int n = 0; n < N; ++n) ties += yp[(size_t)n * W] == m;
+  const float g = dz[idx] / (float)max(ties, 1);
+  for (int n = 0; n < N; ++n) dp[(size_t)n * W] = yp[(size_t)n * W] == m ? g : 0.f;
+}
+
+// Output transform between the decoder and the loss: y = clamp_k(tanh(x)) -- tanh if the decoder normalises its output
+// (decoder.py:123-124), lower clamp at eps of the components in clamp_mask (train.py:55-65, polar coordinates).
+__global__ void out_transform_fwd_kernel(size_t n, int dim, int use_tanh, int clamp_mask, float eps, const float* __restrict__ x,
+                                         float* __restrict__ y) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float v = x[i];
+    if (use_tanh) v = tanhf(v);
+    if ((clamp_mask >> (int)(i % dim)) & 1) v = fmaxf(v, eps);
+    y[i] = v;
+  }
+}
+// dx = dy * [tanh(x) >= eps on clamped components] * (1 - tanh(x)^2)
+__global__ void out_transform_bwd_kernel(size_t n, int dim, int use_tanh, int clamp_mask, float eps, const float* __restrict__ x,
+                                         const float* __restrict__ dy, float* __restrict__ dx) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float v = x[i], g = dy[i];
+    if (use_tanh) v = tanhf(v);
+    if (((clamp_mask >> (int)(i % dim)) & 1) && v < eps) g = 0.f;
+    if (use_tanh) g *= 1.f - v * v;
+    dx[i] = g;
+  }
+}
+
+// nn.MSELoss (train.py:359-361): value = sum (p - q)^2 / denom, dp = 2 (p - q) / denom; per-block partial sums, fixed order
+__global__ void __launch_bounds__(256) mse_stage1(size_t n, float inv_denom, const float* __restrict__ p, const float* __restrict__ q,
+                                                  float* __restrict__ dp, float* __restrict__ part) {
+  float acc = 0.f;
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+    const float d = p[i] - q[i];
+    acc = fmaf(d, d, acc);
+    dp[i] = 2.f * d * inv_denom;
+  }
+  __shared__ float red[8];
+  acc = gj_warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) { float t = 0.f; for (int w = 0; w < 8; ++w) t += red[w]; part[blockIdx.x] = t; }
+}
+__global__ void mse_stage2(const float* __restrict__ part, int nblk, float inv_denom, float* __restrict__ terms) {
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int b = 0; b < nblk; ++b) t += part[b];
+    terms[0] = 0.f; terms[1] = 0.f; terms[2] = (float)(t * inv_denom);
+  }
+}
+
 }  // namespace
 
 void gj_set_error(const char* fmt, ...);
 static const int kNormBlocks = 64;
+
+int gj_latent_extreme_fwd_launch(int B, int N, int W, int is_min, const float* y, float* z, cudaStream_t stream) {
+  const int total = B * W;
+  if (total == 0) return GJ_OK;
+  latent_extreme_fwd_kernel<<<(total + 255) / 256, 256, 0, stream>>>(N, W, is_min, y, z, total);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) { gj_set_error("latent_extreme_fwd launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
+  return GJ_OK;
+}
+int gj_latent_extreme_bwd_launch(int B, int N, int W, const float* y, const float* z, const float* dz, float* dy, cudaStream_t stream) {
+  const int total = B * W;
+  if (total == 0) return GJ_OK;
+  latent_extreme_bwd_kernel<<<(total + 255) / 256, 256, 0, stream>>>(N, W, y, z, dz, dy, total);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) { gj_set_error("latent_extreme_bwd launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
+  return GJ_OK;
+}
+int gj_out_transform_launch(size_t n, int dim, int use_tanh, int clamp_mask, float eps, const float* x, const float* dy, float* out,
+                            cudaStream_t stream) {
+  if (n == 0) return GJ_OK;
+  unsigned blocks = (unsigned)((n + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
+  if (dy) out_transform_bwd_kernel<<<blocks, 256, 0, stream>>>(n, dim, use_tanh, clamp_mask, eps, x, dy, out);
+  else out_transform_fwd_kernel<<<blocks, 256, 0, stream>>>(n, dim, use_tanh, clamp_mask, eps, x, out);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) { gj_set_error("out_transform launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
+  return GJ_OK;
+}
+size_t gj_mse_ws_bytes() { return kNormBlocks * sizeof(float); }
+int gj_mse_launch(size_t n, double denom, const float* p, const float* q, float* terms, float* dp, void* ws, size_t ws_bytes,
+                  cudaStream_t stream) {
+  if (ws_bytes < gj_mse_ws_bytes()) { gj_set_error("gj_mse_fwd_bwd: workspace too small"); return GJ_ERR_WORKSPACE; }
+  const float inv = (float)(1.0 / denom);
+  mse_stage1<<<kNormBlocks, 256, 0, stream>>>(n, inv, p, q, dp, (float*)ws);
+  mse_stage2<<<1, 32, 0, stream>>>((const float*)ws, kNormBlocks, inv, terms);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) { gj_set_error("mse launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
+  return GJ_OK;
+}
 
 int gj_adam_launch(float* param, const float* grad, float* m, float* v, size_t n, float lr, float b1, float b2, float eps,
                    int step, float gscale, float l1, float l2, cudaStream_t stream) {

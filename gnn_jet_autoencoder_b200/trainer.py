@@ -23,6 +23,8 @@ from . import _lib, ops
 from .losses import _norm_id
 from .models.const import GLOBAL_MIX, LOCAL_MIX
 
+POLAR_EPS = 1e-16      # utils/const.py:5 (clamp of (E, pT) in polar coordinates, utils/train.py:58-65)
+
 
 # --------------------------------------------------------------------------------------------------
 # host-side helpers (no CUDA needed: covered by the CPU / gloo tests)
@@ -109,31 +111,42 @@ class GNNAETrainer:
     >>> tr = GNNAETrainer(encoder, decoder, batch_size=4096)
     >>> loss = tr.step(x_host_pinned)          # float; H2D copy, graph replay, all-reduce, Adam, D2H of the loss
 
-    Supported latent maps: 'mean', the GLOBAL_MIX and LOCAL_MIX spellings.  'max'/'min', ``normalize_output``,
-    dropout and batch-norm go through the nn.Module path (autograd) instead.
+    Covers every latent map of the reference ('mean', 'max', 'min', the GLOBAL_MIX and LOCAL_MIX spellings), the decoder's
+    ``normalize_output`` (tanh), the polar-coordinate clamp of utils/train.py:55-65 (``polar_coord``) and the Chamfer and MSE
+    branches of ``get_loss`` (utils/train.py:338-361, ``loss_choice``).  Dropout and batch-norm are not part of the fused step
+    (the reference's batch-norm path crashes; dropout > 0 raises in the modules).
     """
 
     def __init__(self, encoder, decoder, batch_size: int, *, lr: float = 1e-5, betas=(0.9, 0.999), eps: float = 1e-8,
                  l1_lambda: float = 1e-8, l2_lambda: float = 0.0, loss_norm_choice: str = "cartesian",
                  jet_features_weight: float = 1.0, chamfer_mode: str = "intended", encoder_metric: str = "euclidean",
-                 decoder_metric: str = "euclidean", process_group=None, use_cuda_graph: bool = True):
+                 decoder_metric: str = "euclidean", process_group=None, use_cuda_graph: bool = True,
+                 loss_choice: str = "chamfer", polar_coord: bool = False):
         self.enc, self.dec = encoder, decoder
         g_e, g_d = encoder.encoder, decoder.decoder
         dev = next(encoder.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("GNNAETrainer needs the models on a CUDA device (there is no CPU fallback)")
-        if g_e.batch_norm or g_d.batch_norm or g_e.dropout_p > 0 or g_d.dropout_p > 0 or decoder.normalize_output:
-            raise NotImplementedError("batch_norm / dropout / normalize_output are not part of the fused step")
+        if g_e.batch_norm or g_d.batch_norm or g_e.dropout_p > 0 or g_d.dropout_p > 0:
+            raise NotImplementedError("batch_norm / dropout are not part of the fused step")
         canon = encoder.latent_map.lower().replace(" ", "_")
         if canon in GLOBAL_MIX:
             self.map = "global"
         elif canon in LOCAL_MIX:
             self.map = "local"
         elif canon in ("max", "min"):
-            raise NotImplementedError("latent_map 'max'/'min' is served by the nn.Module path only")
+            self.map = canon
         else:
             self.map = "mean"
-        if chamfer_mode == "reference" and jet_features_weight == 0:
+        lc = str(loss_choice).lower()
+        if lc in ("chamfer", "chamferloss", "chamfer_loss"):
+            self.loss_choice = "chamfer"
+        elif lc in ("mse", "mseloss", "mse_loss"):
+            self.loss_choice = "mse"
+        else:
+            raise NotImplementedError(f"loss_choice {loss_choice!r}: the fused step covers the Chamfer and MSE branches of get_loss "
+                                      "(utils/train.py:338-361); the EMD loss is out of scope")
+        if self.loss_choice == "chamfer" and chamfer_mode == "reference" and jet_features_weight == 0:
             raise UnboundLocalError("jet_loss referenced before assignment (reference chamfer_loss.py:42)")
         # the Chamfer target is the input batch: both sides must be 3- or 4-vectors of one width (distance_sq.py:31-42)
         if decoder.output_node_size != encoder.input_node_size or encoder.input_node_size not in (3, 4):
@@ -195,8 +208,18 @@ class GNNAETrainer:
         self.d_dec_in = torch.empty((B, N, self.h0), **f32)
         self.d_enc_out = torch.empty((B, N, self.enc_out_w), **f32)
         self.dx = torch.zeros((B, N, self.F), **f32)
-        self.recon = self.dec_steps[-1]["out"]
+        # decoder output -> [tanh] -> [clamp of (E, pT) / pT at EPS] -> loss (decoder.py:123-124, train.py:55-65)
+        D = decoder.output_node_size
+        self.use_tanh = bool(decoder.normalize_output)
+        self.clamp_mask = (3 if D == 4 else 1) if polar_coord else 0
+        self.recon_raw = self.dec_steps[-1]["out"]
+        self.transform = self.use_tanh or self.clamp_mask != 0
+        self.recon = torch.empty_like(self.recon_raw) if self.transform else self.recon_raw
         self.dp = torch.empty_like(self.recon)
+        self.dp_raw = torch.empty_like(self.recon) if self.transform else self.dp
+        self.world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.world = torch.distributed.get_world_size(process_group)
         self.jet_terms = torch.empty((B, 2), **f32)
         self.stats = torch.zeros(8, **f32)     # [chamfer, jet, wc*chamfer + wj*jet, sum|p|, sum p^2]
         self.stats_host = torch.zeros(8, dtype=torch.float32).pin_memory()
@@ -204,7 +227,7 @@ class GNNAETrainer:
                  [self.lib.gj_mp_step_fwd_workspace(s["desc"]) for s in self.enc_steps + self.dec_steps] +
                  [self.lib.gj_linear_bwd_workspace(B * N, max(self.latent_w, self.enc_out_w), max(self.h0, self.latent_w)),
                   self.lib.gj_linear_bwd_workspace(B, max(self.latent_w, N * self.enc_out_w), max(N * self.h0, self.latent_w)),
-                  self.lib.gj_param_norms_workspace(n), 16])
+                  self.lib.gj_param_norms_workspace(n), self.lib.gj_mse_workspace(), 16])
         self.ws_bytes = int(ws)
         self.ws = torch.empty((self.ws_bytes + 3) // 4, **f32)
         # per-step buffers in which the forward call leaves P|Q, the packed edge parameters and the pair distances for the
@@ -248,6 +271,9 @@ class GNNAETrainer:
         L = self.layout
         if self.map == "mean":
             _lib.check(lib.gj_latent_mean_fwd(B, N, self.enc_out_w, h.data_ptr(), self.latent.data_ptr(), st), "latent_mean_fwd")
+        elif self.map in ("max", "min"):
+            _lib.check(lib.gj_latent_extreme_fwd(B, N, self.enc_out_w, int(self.map == "min"), h.data_ptr(), self.latent.data_ptr(), st),
+                       "latent_extreme_fwd")
         elif self.map == "global":
             _lib.check(lib.gj_linear_fwd(B, N * self.enc_out_w, self.latent_w, h.data_ptr(),
                                          P + 4 * L["encoder.mix_layer.weight"][0], None, self.latent.data_ptr(), st), "mix fwd")
@@ -267,13 +293,21 @@ class GNNAETrainer:
             ops.raw_mp_fwd(s["desc"], h.data_ptr(), P + 4 * s["off"], s["out"].data_ptr(), s["e"].data_ptr(),
                            self.ws.data_ptr(), self.ws_bytes, st, s["saved"].data_ptr() if s["saved"] is not None else None)
             h = s["out"]
+        if self.transform:
+            _lib.check(lib.gj_output_transform_fwd(B * N, self.recon.shape[-1], int(self.use_tanh), self.clamp_mask, POLAR_EPS,
+                                                   self.recon_raw.data_ptr(), self.recon.data_ptr(), st), "output transform fwd")
+            ops.LAUNCHES["count"] += 1
 
     def _loss(self, st):
         """Chamfer terms (+ d loss / d recon) and parameter norms of the resident batch -> self.stats."""
         lib, B, N, D = self.lib, self.B, self.N, self.recon.shape[-1]
-        _lib.check(lib.gj_chamfer_fwd_bwd(B, N, N, D, _norm_id(self.recon, self.norm_choice), self.wc, self.wj,
-                                          self.recon.data_ptr(), self.x.data_ptr(), self.jet_terms.data_ptr(),
-                                          self.stats.data_ptr(), self.dp.data_ptr(), st), "chamfer")
+        if self.loss_choice == "mse":      # nn.MSELoss: mean over the elements of the GLOBAL batch
+            _lib.check(lib.gj_mse_fwd_bwd(B * N * D, float(self.world * B * N * D), self.recon.data_ptr(), self.x.data_ptr(),
+                                          self.stats.data_ptr(), self.dp.data_ptr(), self.ws.data_ptr(), self.ws_bytes, st), "mse")
+        else:
+            _lib.check(lib.gj_chamfer_fwd_bwd(B, N, N, D, _norm_id(self.recon, self.norm_choice), self.wc, self.wj,
+                                              self.recon.data_ptr(), self.x.data_ptr(), self.jet_terms.data_ptr(),
+                                              self.stats.data_ptr(), self.dp.data_ptr(), st), "chamfer")
         _lib.check(lib.gj_param_norms(self.flat.data_ptr(), self.flat.numel(), self.stats.data_ptr() + 12, self.ws.data_ptr(),
                                       self.ws_bytes, st), "norms")
         ops.LAUNCHES["count"] += 4
@@ -282,8 +316,13 @@ class GNNAETrainer:
         lib, P, G = self.lib, self.flat.data_ptr(), self.grad.data_ptr()
         B, N, L = self.B, self.N, self.layout
         self._loss(st)
+        if self.transform:
+            _lib.check(lib.gj_output_transform_bwd(B * N, self.recon.shape[-1], int(self.use_tanh), self.clamp_mask, POLAR_EPS,
+                                                   self.recon_raw.data_ptr(), self.dp.data_ptr(), self.dp_raw.data_ptr(), st),
+                       "output transform bwd")
+            ops.LAUNCHES["count"] += 1
         # decoder GraphNet, last step first
-        g = self.dp
+        g = self.dp_raw
         for t in reversed(range(len(self.dec_steps))):
             s = self.dec_steps[t]
             hin = self.dec_in if t == 0 else self.dec_steps[t - 1]["out"]
@@ -304,6 +343,10 @@ class GNNAETrainer:
         y = self.enc_steps[-1]["out"]
         if self.map == "mean":
             _lib.check(lib.gj_latent_mean_bwd(B, N, self.enc_out_w, self.dlatent.data_ptr(), self.d_enc_out.data_ptr(), st), "latent_mean_bwd")
+            ops.LAUNCHES["count"] += 1
+        elif self.map in ("max", "min"):
+            _lib.check(lib.gj_latent_extreme_bwd(B, N, self.enc_out_w, y.data_ptr(), self.latent.data_ptr(), self.dlatent.data_ptr(),
+                                                 self.d_enc_out.data_ptr(), st), "latent_extreme_bwd")
             ops.LAUNCHES["count"] += 1
         elif self.map == "global":
             wm = L["encoder.mix_layer.weight"][0]

@@ -158,6 +158,28 @@ size_t gj_param_norms_workspace(size_t n);
 int gj_latent_mean_fwd(int32_t batch, int32_t num_nodes, int32_t width, const float* y, float* z, void* stream);
 int gj_latent_mean_bwd(int32_t batch, int32_t num_nodes, int32_t width, const float* dz, float* dy, void* stream);
 
+/* 'max' / 'min' latent maps (reference models/encoder.py:150-155: torch.amax / torch.amin over the particle axis):
+ * z (batch,width) = extremum over n of y (batch,num_nodes,width); the adjoint shares dz evenly among the entries that attain the
+ * extremum (torch's convention) and OVERWRITES dy. */
+int gj_latent_extreme_fwd(int32_t batch, int32_t num_nodes, int32_t width, int32_t is_min, const float* y, float* z, void* stream);
+int gj_latent_extreme_bwd(int32_t batch, int32_t num_nodes, int32_t width, const float* y, const float* z, const float* dz, float* dy,
+                          void* stream);
+
+/* Transform between the decoder's last step and the loss, y = clamp(tanh(x)) element by element over (rows, dim):
+ * tanh if use_tanh (reference models/decoder.py:123-124, normalize_output), then a lower clamp at eps of the components whose bit
+ * is set in clamp_mask (reference utils/train.py:55-65, polar coordinates: (E, pT) or pT).  The adjoint takes the untransformed x. */
+int gj_output_transform_fwd(size_t rows, int32_t dim, int32_t use_tanh, int32_t clamp_mask, float eps, const float* x, float* y,
+                            void* stream);
+int gj_output_transform_bwd(size_t rows, int32_t dim, int32_t use_tanh, int32_t clamp_mask, float eps, const float* x, const float* dy,
+                            float* dx, void* stream);
+
+/* nn.MSELoss of reference utils/train.py:359-361 and its gradient: terms[0..1] = 0, terms[2] = sum (p - q)^2 / denom,
+ * dp = 2 (p - q) / denom over `count` floats (denom = number of elements of the GLOBAL batch, so that data-parallel shards sum to the
+ * single-device gradient).  Fixed summation order. */
+size_t gj_mse_workspace(void);
+int gj_mse_fwd_bwd(size_t count, double denom, const float* p, const float* q, float* terms, float* dp, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
 /* Small dense layer y = x W^T + b on the path's node/graph-level maps: decoder.py:127-136 (latent -> node
  * features) and the encoder mix layers, encoder.py:156-161.  x (rows,in), W (out,in) as nn.Linear, b (out) or
  * NULL, y (rows,out). */

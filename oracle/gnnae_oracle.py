@@ -484,13 +484,38 @@ def l1_norm(params):
     return sum(np.abs(v).sum() for v in params.values())
 
 
+POLAR_EPS = 1e-16      # utils/const.py:5
+
+
+def polar_clamp(y):
+    """utils/train.py:55-65: (E, pT) of 4-vectors / pT of 3-vectors clamped from below at EPS.  Returns (clamped, d clamped / d y)."""
+    k = 2 if y.shape[-1] == 4 else 1
+    mask = np.ones_like(y)
+    mask[..., :k] = (y[..., :k] >= POLAR_EPS).astype(y.dtype)      # torch.clamp passes the gradient where min <= y
+    out = y.copy()
+    out[..., :k] = np.maximum(y[..., :k], POLAR_EPS)
+    return out, mask
+
+
+def mse_loss(p, q):
+    """nn.MSELoss() (utils/train.py:359-361): mean over all elements."""
+    d = p - q
+    return float((d * d).mean()), 2.0 * d / d.size
+
+
 def loss_and_grads(x, enc_params, dec_params, enc_cfg, dec_cfg, *, metric="euclidean",
                    loss_norm_choice="cartesian", jet_features_weight=1.0, chamfer_mode="intended",
-                   l1_lambda=1e-8, l2_lambda=0.0):
-    """encoder -> decoder -> Chamfer (+L1/L2 regularisers, train.py:376-384) and all gradients."""
+                   l1_lambda=1e-8, l2_lambda=0.0, loss_choice="chamfer", polar_coord=False):
+    """encoder -> decoder [-> polar clamp] -> Chamfer or MSE (+L1/L2 regularisers, train.py:51-65,338-384) and all gradients."""
     z, ec = encoder_forward(x, enc_params, enc_cfg, metric)
     y, dc = decoder_forward(z, dec_params, dec_cfg, metric)
-    loss, dy = chamfer_loss(y, x, loss_norm_choice, jet_features_weight, chamfer_mode)
+    y_loss, mask = polar_clamp(y) if polar_coord else (y, None)
+    if loss_choice == "mse":
+        loss, dy = mse_loss(y_loss, x)
+    else:
+        loss, dy = chamfer_loss(y_loss, x, loss_norm_choice, jet_features_weight, chamfer_mode)
+    if mask is not None:
+        dy = dy * mask
     dz, dgrads = decoder_backward(dy, dc, dec_params, dec_cfg)
     _, egrads = encoder_backward(dz, ec, enc_params, enc_cfg)
     for params, grads in ((enc_params, egrads), (dec_params, dgrads)):
@@ -507,7 +532,7 @@ def loss_and_grads(x, enc_params, dec_params, enc_cfg, dec_cfg, *, metric="eucli
         loss = loss + l1_lambda * (l1_norm(enc_params) + l1_norm(dec_params))
     if l2_lambda > 0:
         loss = loss + l2_lambda * sum((v * v).sum() for p in (enc_params, dec_params) for v in p.values())
-    return loss, z, y, egrads, dgrads
+    return loss, z, y_loss, egrads, dgrads      # y_loss: the reconstruction as the loss sees it (after the polar clamp)
 
 
 def adam_update(params, grads, state, lr=1e-5, betas=(0.9, 0.999), eps=1e-8):

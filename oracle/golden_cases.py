@@ -13,14 +13,15 @@ DEFAULT_NODE = [[16], [32], [8]]            # utils/argparse_utils.py:97-104
 
 def _case(N, B, *, edge=DEFAULT_EDGE, node=DEFAULT_NODE, num_mps=3, latent=20, latent_map="mean", vec=3,
           alphas=0.2, metric="euclidean", norm="cartesian", seed=0, normalize_output=False, store64=True,
-          jet_w=1.0, dec_edge=None, dec_node=None, grad_stride=1):
+          jet_w=1.0, dec_edge=None, dec_node=None, grad_stride=1, loss="chamfer", polar=False):
     enc = dict(num_nodes=N, input_node_size=vec, latent_node_size=latent, node_sizes=node, edge_sizes=edge,
                num_mps=num_mps, alphas=alphas, latent_map=latent_map)
     dec = dict(num_nodes=N, latent_node_size=latent, output_node_size=vec, node_sizes=dec_node or node,
                edge_sizes=dec_edge or edge, num_mps=num_mps, alphas=alphas, latent_map=latent_map,
                normalize_output=normalize_output)
     return dict(enc=enc, dec=dec, B=B, N=N, vec=vec, metric=metric, loss_norm_choice=norm, seed=seed,
-                store64=store64, jet_features_weight=jet_w, l1_lambda=1e-8, grad_stride=grad_stride)
+                store64=store64, jet_features_weight=jet_w, l1_lambda=1e-8, grad_stride=grad_stride, loss_choice=loss,
+                polar_coord=polar)
 
 
 def gsub(case, v):
@@ -72,6 +73,12 @@ CASES = {
     # 3-vectors with a Minkowskian loss norm: pairwise distances stay cartesian (distance_sq.py:43-44), the jet term does not
     # (chamfer_loss.py:40)
     "loss_mink3_n6": _case(6, 3, edge=[[16, 16]], node=[[8]], num_mps=2, latent=4, norm="minkowskian", seed=23, jet_w=0.7),
+    # the MSE branch of get_loss (utils/train.py:359-361) and the polar-coordinate clamp of the train loop (:55-65) in front of
+    # the Chamfer loss with the polar norm, for 3- and 4-vectors; the last one also has the tanh output
+    "mse_n6": _case(6, 3, edge=[[16, 16]], node=[[8]], num_mps=2, latent=4, seed=24, loss="mse"),
+    "polar3_n6": _case(6, 3, edge=[[16, 16]], node=[[8]], num_mps=2, latent=4, seed=25, norm="polar", polar=True),
+    "polar4_tanh_n6": _case(6, 3, edge=[[16, 16]], node=[[4], [4]], num_mps=2, latent=4, vec=4, seed=26, norm="polar", polar=True,
+                            normalize_output=True, loss="mse"),
 }
 
 

@@ -29,7 +29,8 @@ def test_oracle_matches_reference(name):
     x = make_input(case)
     loss, z, y, eg, dg = O.loss_and_grads(
         x, ep, dp, case["enc"], case["dec"], metric=case["metric"], loss_norm_choice=case["loss_norm_choice"],
-        jet_features_weight=case["jet_features_weight"], l1_lambda=case["l1_lambda"])
+        jet_features_weight=case["jet_features_weight"], l1_lambda=case["l1_lambda"], loss_choice=case["loss_choice"],
+        polar_coord=case["polar_coord"])
     tol = 1e-12 if case["store64"] else 2e-7   # float32-stored fixtures carry 6e-8 rounding
     assert z.shape == g["latent"].shape and y.shape == g["recon"].shape
     assert rel(z, g["latent"]) < 1e-12
