@@ -54,6 +54,7 @@ SIGNATURES = {
     "gj_assignment": (C.c_int, [_I, _I, _I, _I, _P, _P, _P, _P, _P]),
     "gj_adam_step_flat": (C.c_int, [_P, _P, _P, _P, _SZ, _F, _F, _F, _F, _I, _F, _F, _F, _P]),
     "gj_param_norms": (C.c_int, [_P, _SZ, _P, _P, _SZ, _P]),
+    "gj_optimizer_step_flat": (C.c_int, [_I, _P, _P, _P, _P, _SZ, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _P]),
     "gj_param_norms_workspace": (_SZ, [_SZ]),
     "gj_latent_mean_fwd": (C.c_int, [_I, _I, _I, _P, _P, _P]),
     "gj_latent_mean_bwd": (C.c_int, [_I, _I, _I, _P, _P, _P]),
@@ -73,6 +74,7 @@ SIGNATURES = {
     "gj_umma_selftest": (C.c_int, [_I, _I, _I, _I, _I, _P, _P, _P, _P]),
     "gj_dense_gemm": (C.c_int, [_I, _I, _I, _I, _P, _P, _P, _I, _F, _P, _I, _P, _P, _SZ, _I, _P]),
     "gj_dense_gemm_workspace": (_SZ, [_I, _I, _I, _I]),
+    "gj_set_deterministic": (_I, [_I]),
     "gj_last_error": (C.c_char_p, []),
     "gj_abi_version": (_I, []),
     "gj_build_arch": (C.c_char_p, []),

@@ -19,6 +19,10 @@ static bool node_post_tc_enabled() { static const bool v = !(getenv("GJ_NODE_POS
 static bool node_tc_disabled() { static const bool v = getenv("GJ_NODE_SIMT") && atoi(getenv("GJ_NODE_SIMT")) != 0; return v; }
 bool gj_tc_v1_forced() { static const bool v = getenv("GJ_TC_V1") && atoi(getenv("GJ_TC_V1")) != 0; return v; }
 
+// bitwise-reproducible parameter gradients in the bf16 mode (gj_set_deterministic): read by the backward edge launchers
+static int g_deterministic = 0;
+bool gj_deterministic() { return g_deterministic != 0; }
+
 int gj_num_sms() {
   static int sms[64] = {0};
   int dev = 0;
@@ -100,6 +104,7 @@ int gj_linear_bwd_launch(int, int, int, const float*, const float*, const float*
 int gj_adam_launch(float*, const float*, float*, float*, size_t, float, float, float, float, int, float, float, float,
                    cudaStream_t);
 size_t gj_norms_ws_bytes(size_t);
+int gj_optimizer_launch(int, float*, const float*, float*, float*, size_t, float, float, float, float, float, float, float, cudaStream_t);
 int gj_norms_launch(const float*, size_t, float*, void*, size_t, cudaStream_t);
 int gj_latent_mean_fwd_launch(int, int, int, const float*, float*, cudaStream_t);
 int gj_latent_mean_bwd_launch(int, int, int, const float*, float*, cudaStream_t);
@@ -114,6 +119,12 @@ extern "C" {
 const char* gj_last_error(void) { return g_err; }
 int32_t gj_abi_version(void) { return 1; }
 const char* gj_build_arch(void) { return "sm_100a"; }
+
+int32_t gj_set_deterministic(int32_t on) {
+  const int prev = g_deterministic;
+  g_deterministic = on != 0;
+  return prev;
+}
 
 size_t gj_mp_param_count(const gj_mp_desc* d) {
   MPLayout L; const char* why;
@@ -416,6 +427,15 @@ int gj_adam_step_flat(float* param, const float* grad, float* exp_avg, float* ex
   if (n && (!param || !grad || !exp_avg || !exp_avg_sq)) { gj_set_error("gj_adam_step_flat: null pointer"); return GJ_ERR_INVALID; }
   return gj_adam_launch(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, grad_scale, l1_lambda, l2_lambda,
                         (cudaStream_t)stream);
+}
+
+int gj_optimizer_step_flat(int32_t kind, float* param, const float* grad, float* momentum_buf, float* sq_acc, size_t n, float lr,
+                           float alpha, float momentum, float eps, float grad_scale, float l1_lambda, float l2_lambda, void* stream) {
+  g_err[0] = 0;
+  if (kind < GJ_OPT_RMSPROP || kind > GJ_OPT_SGD) { gj_set_error("gj_optimizer_step_flat: unknown optimiser %d", kind); return GJ_ERR_INVALID; }
+  if (n && (!param || !grad || !momentum_buf || !sq_acc)) { gj_set_error("gj_optimizer_step_flat: null pointer"); return GJ_ERR_INVALID; }
+  return gj_optimizer_launch(kind, param, grad, momentum_buf, sq_acc, n, lr, alpha, momentum, eps, grad_scale, l1_lambda, l2_lambda,
+                             (cudaStream_t)stream);
 }
 
 size_t gj_param_norms_workspace(size_t n) { return gj_norms_ws_bytes(n); }

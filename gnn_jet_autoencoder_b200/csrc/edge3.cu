@@ -702,6 +702,7 @@ __global__ void __launch_bounds__(256) e3_sum_dp_parts_kernel(const float4* __re
 }  // namespace
 
 int gj_num_sms();
+bool gj_deterministic();
 void gj_set_error(const char* fmt, ...);
 int gj_reduce_edge_partials(const MPLayout& L, const float* part, int nparts, float* dparams, cudaStream_t stream);
 int gj_pair_dist_fwd(const MPLayout& L, const float* h, float* d, cudaStream_t stream);
@@ -828,7 +829,10 @@ int gj_edge_bwd3(const MPLayout& L, const float* h, const float* pq, const float
   A.pq = pq; A.d = d; A.params = params; A.wimg = reinterpret_cast<const uint8_t*>(wimg);
   A.de = de; A.dpq = dpq; A.dp_part = dp_part; A.G = G; A.part = part;
   const int grid = e3_bwd_grid();
-  int rc = shape == 0 ? e3_launch_bwd<64, 64, 2, 1, 2>(A, grid, stream) : e3_launch_bwd<128, 128, 1, 2, 2>(A, grid, stream);
+  // two tile groups per CTA (H = 64) share the TMEM gradient accumulator in a timing-dependent order: the deterministic mode
+  // (gj_set_deterministic) runs one
+  int rc = shape == 0 ? (gj_deterministic() ? e3_launch_bwd<64, 64, 1, 1, 2>(A, grid, stream) : e3_launch_bwd<64, 64, 2, 1, 2>(A, grid, stream))
+                      : e3_launch_bwd<128, 128, 1, 2, 2>(A, grid, stream);
   if (rc) return rc;
   if (njb > 1) {
     const size_t n4 = rows * (size_t)(L.E[0] / 4);

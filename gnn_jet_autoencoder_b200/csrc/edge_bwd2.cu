@@ -891,6 +891,7 @@ __global__ void __launch_bounds__(640) pair_dist_bwd_kernel(const float* __restr
 }  // namespace
 
 int gj_num_sms();
+bool gj_deterministic();
 void gj_set_error(const char* fmt, ...);
 int gj_reduce_edge_partials(const MPLayout& L, const float* part, int nparts, float* dparams, cudaStream_t stream);
 int gj_pair_dist_bwd(const MPLayout& L, const float* h, const float* G, float* dh, cudaStream_t stream);
@@ -970,9 +971,14 @@ int gj_edge_bwd2(const MPLayout& L, const float* h, const float* pq, const float
   // mode 0: the whole edge adjoint; 1: the fused kernel alone (bench hook); 2: as 0, but dpq has already been zeroed by the
   // caller and the per-CTA parameter-gradient partials are handed back (*part_out, *nparts_out) instead of being reduced
   const bool kernel_only = mode == 1;
-  constexpr int NWG = 3;
-  using S = Bwd2Smem<32, 128, 64, 16, NWG>;
+  // Three tile groups per CTA add their weight-gradient MMAs into shared TMEM accumulators in a timing-dependent order; the
+  // deterministic mode (gj_set_deterministic) runs ONE group per CTA, which fixes the order (and costs the overlap).
+  const bool det = gj_deterministic();
+  const int NWG = det ? 1 : 3;
+  using S = Bwd2Smem<32, 128, 64, 16, 3>;
+  using S1 = Bwd2Smem<32, 128, 64, 16, 1>;
   static_assert(S::total <= 227 * 1024, "backward shared-memory plan exceeds the 227 KB budget");
+  const int smem_total = det ? S1::total : S::total;
   Bwd2Args A;
   const size_t njb = (L.N + 31) / 32, rows = (size_t)L.B * L.N;
   const int NJ32 = (int)njb * 32;
@@ -1006,13 +1012,14 @@ int gj_edge_bwd2(const MPLayout& L, const float* h, const float* pq, const float
     if (ce != cudaSuccess) { gj_set_error("cudaMemsetAsync: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   }
   static const int trace_env = getenv("GJ_TRACE") ? atoi(getenv("GJ_TRACE")) : 0;
-  auto kern = trace_env == 4 ? edge_bwd2_kernel<32, 128, 64, 16, NWG, true> : edge_bwd2_kernel<32, 128, 64, 16, NWG, false>;
-  ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::total);
+  auto kern = det ? edge_bwd2_kernel<32, 128, 64, 16, 1, false>
+                  : (trace_env == 4 ? edge_bwd2_kernel<32, 128, 64, 16, 3, true> : edge_bwd2_kernel<32, 128, 64, 16, 3, false>);
+  ce = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_total);
   if (ce != cudaSuccess) { gj_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   CUtensorMap tm_w;      // the parameter image as rows of 1 KB
   static_assert(WImage<32, 128, 64, 16>::bytes % 1024 == 0 && WImage<32, 128, 64, 16>::bytes / 1024 <= 256, "one TMA box");
   if (int rc = gj_tmap_2d(&tm_w, wimg, 256, WImage<32, 128, 64, 16>::bytes / 1024, 1024, 256, WImage<32, 128, 64, 16>::bytes / 1024)) return rc;
-  kern<<<grid, NWG * 128, S::total, stream>>>(A, tm_w);
+  kern<<<grid, NWG * 128, smem_total, stream>>>(A, tm_w);
   ce = cudaGetLastError();
   if (ce != cudaSuccess) { gj_set_error("edge_bwd2 launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   if (kernel_only) return GJ_OK;

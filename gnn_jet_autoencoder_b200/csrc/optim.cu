@@ -24,6 +24,38 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// The other optimisers of utils/initialize.py:154-170 over the same flat buffers (buf = momentum buffer, acc = squared-gradient
+// statistic): 1 RMSprop (alpha 0.99, momentum), 2 Adagrad, 3 SGD with momentum -- torch.optim semantics, regulariser gradients folded in
+__global__ void optimizer_kernel(int kind, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf,
+                                 float* __restrict__ acc, size_t n, float lr, float alpha, float momentum, float eps, float gscale,
+                                 float l1, float l2) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const float pi = p[i];
+    float gi = g[i] * gscale;
+    if (l1 != 0.f) gi += l1 * (pi > 0.f ? 1.f : (pi < 0.f ? -1.f : 0.f));
+    if (l2 != 0.f) gi += 2.f * l2 * pi;
+    float upd;
+    if (kind == 1) {
+      const float sq = alpha * acc[i] + (1.f - alpha) * gi * gi;
+      acc[i] = sq;
+      const float b = momentum * buf[i] + gi / (sqrtf(sq) + eps);
+      buf[i] = b;
+      upd = b;
+    } else if (kind == 2) {
+      const float sq = acc[i] + gi * gi;
+      acc[i] = sq;
+      upd = gi / (sqrtf(sq) + eps);
+    } else {
+      const float b = momentum * buf[i] + gi;
+      buf[i] = b;
+      upd = b;
+    }
+    p[i] = pi - lr * upd;
+  }
+}
+
 __global__ void norms_stage1(const float* __restrict__ p, size_t n, float* __restrict__ part) {
   __shared__ float red[2][8];
   float a = 0.f, s = 0.f;
@@ -190,6 +222,16 @@ int gj_adam_launch(float* param, const float* grad, float* m, float* v, size_t n
                                           gscale, l1, l2);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) { gj_set_error("adam launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
+  return GJ_OK;
+}
+
+int gj_optimizer_launch(int kind, float* param, const float* grad, float* buf, float* acc, size_t n, float lr, float alpha, float momentum,
+                        float eps, float gscale, float l1, float l2, cudaStream_t stream) {
+  if (n == 0) return GJ_OK;
+  int blocks = (int)((n + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
+  optimizer_kernel<<<blocks, 256, 0, stream>>>(kind, param, grad, buf, acc, n, lr, alpha, momentum, eps, gscale, l1, l2);
+  cudaError_t ce = cudaGetLastError();
+  if (ce != cudaSuccess) { gj_set_error("optimizer launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   return GJ_OK;
 }
 

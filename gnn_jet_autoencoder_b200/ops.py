@@ -379,6 +379,31 @@ def adam_step_flat_(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: Te
     LAUNCHES["count"] += 1
 
 
+def set_deterministic(on: bool) -> bool:
+    """Bitwise-reproducible parameter gradients in the bf16 mode (one tile group per CTA in the backward edge kernels, about
+    2.5x their time); returns the previous setting.  Call it before building a GNNAETrainer CUDA graph."""
+    return bool(_lib.load().gj_set_deterministic(1 if on else 0))
+
+
+OPTIMIZERS = {"rmsprop": 1, "adagrad": 2, "sgd": 3}
+
+
+@_on_device
+def optimizer_step_flat_(kind: str, param: Tensor, grad: Tensor, momentum_buf: Tensor, sq_acc: Tensor, lr: float = 1e-5,
+                         grad_scale: float = 1.0, l1_lambda: float = 0.0, l2_lambda: float = 0.0) -> None:
+    """In-place fused RMSprop / Adagrad / SGD over flat fp32 buffers with the hyper-parameters utils/initialize.py:154-170 passes
+    (RMSprop: eps 1e-16, momentum 0.9, torch's alpha 0.99; Adagrad: eps 1e-16; SGD: momentum 0.9)."""
+    for t, n in ((param, "param"), (grad, "grad"), (momentum_buf, "momentum_buf"), (sq_acc, "sq_acc")):
+        if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+            raise _lib.GnnJetError(f"{n} must be a contiguous float32 CUDA tensor")
+    k = OPTIMIZERS[kind.lower()]
+    alpha, momentum, eps = (0.99, 0.9, 1e-16) if k == 1 else ((0.0, 0.0, 1e-16) if k == 2 else (0.0, 0.9, 0.0))
+    _lib.check(_lib.load().gj_optimizer_step_flat(k, param.data_ptr(), grad.data_ptr(), momentum_buf.data_ptr(), sq_acc.data_ptr(),
+                                                  param.numel(), lr, alpha, momentum, eps, grad_scale, l1_lambda, l2_lambda, _stream()),
+               "gj_optimizer_step_flat")
+    LAUNCHES["count"] += 1
+
+
 @_on_device
 def param_norms(param: Tensor) -> Tensor:
     """[sum |p|, sum p^2] of a flat buffer (encoder.py:173-179)."""

@@ -121,7 +121,7 @@ class GNNAETrainer:
                  l1_lambda: float = 1e-8, l2_lambda: float = 0.0, loss_norm_choice: str = "cartesian",
                  jet_features_weight: float = 1.0, chamfer_mode: str = "intended", encoder_metric: str = "euclidean",
                  decoder_metric: str = "euclidean", process_group=None, use_cuda_graph: bool = True,
-                 loss_choice: str = "chamfer", polar_coord: bool = False):
+                 loss_choice: str = "chamfer", polar_coord: bool = False, optimizer: str = "adam"):
         self.enc, self.dec = encoder, decoder
         g_e, g_d = encoder.encoder, decoder.decoder
         dev = next(encoder.parameters()).device
@@ -138,6 +138,10 @@ class GNNAETrainer:
             self.map = canon
         else:
             self.map = "mean"
+        self.optimizer = str(optimizer).lower()      # utils/initialize.py:148-172
+        if self.optimizer != "adam" and self.optimizer not in ops.OPTIMIZERS:
+            raise NotImplementedError("Other choices of optimizer are not implemented. Available choices are 'Adam' and 'RMSprop', "
+                                      f"'Adagrad', 'SGD'. Found: {optimizer}.")
         lc = str(loss_choice).lower()
         if lc in ("chamfer", "chamferloss", "chamfer_loss"):
             self.loss_choice = "chamfer"
@@ -409,8 +413,11 @@ class GNNAETrainer:
     def apply_gradients(self) -> None:
         allreduce_flat_(self.grad, self.group)
         self.step_count += 1
-        ops.adam_step_flat_(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr, self.betas,
-                            self.eps, 1.0, self.l1, self.l2)
+        if self.optimizer == "adam":
+            ops.adam_step_flat_(self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.step_count, self.lr, self.betas,
+                                self.eps, 1.0, self.l1, self.l2)
+        else:      # exp_avg doubles as the momentum buffer, exp_avg_sq as the squared-gradient statistic
+            ops.optimizer_step_flat_(self.optimizer, self.flat, self.grad, self.exp_avg, self.exp_avg_sq, self.lr, 1.0, self.l1, self.l2)
 
     @_on_trainer_device
     def step_async(self, x: torch.Tensor) -> None:

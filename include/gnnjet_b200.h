@@ -16,7 +16,11 @@
  *                                      utils/losses/chamfer_loss/distance_sq.py:4-77
  *   gj_adam_step_flat                : torch.optim.Adam as built in utils/initialize.py:152-153,
  *                                      with the L1/L2 regulariser gradients of utils/train.py:376-384
+ *   gj_optimizer_step_flat           : torch.optim.RMSprop / Adagrad / SGD as built in utils/initialize.py:154-170
  *   gj_latent_mean_fwd/bwd           : models/encoder.py:147-149 ('mean' latent map)
+ *   gj_latent_extreme_fwd/bwd        : models/encoder.py:150-155 ('max' / 'min' latent maps)
+ *   gj_output_transform_fwd/bwd      : models/decoder.py:123-124 (tanh) and utils/train.py:55-65 (polar clamp)
+ *   gj_mse_fwd_bwd                   : utils/train.py:359-361 (nn.MSELoss branch of get_loss)
  *
  * Tensor layouts: all tensors are dense row-major float32 in HBM.
  *   node features  h      (B, N, H)
@@ -74,6 +78,14 @@ typedef struct gj_mp_desc {
 
 /* Number of floats in the packed parameter block of one step (0 on invalid desc). */
 size_t gj_mp_param_count(const gj_mp_desc* d);
+
+/* Process-wide switch (returns the previous value; set it before the calls it should affect, not inside a CUDA-graph capture that
+ * was made with the other value).  In the GJ_PREC_BF16 mode forward results and all data gradients are always bitwise
+ * reproducible; PARAMETER gradients are reproducible to fp32 summation order only, because the tile groups of a CTA accumulate
+ * into shared tensor-memory accumulators in a timing-dependent order.  on != 0 runs the backward edge kernels with one tile group
+ * per CTA: parameter gradients become bitwise reproducible from run to run at roughly 2.5x the backward edge time
+ * (the analogue of torch.use_deterministic_algorithms for this path).  GJ_PREC_FP32 is always bitwise reproducible. */
+int32_t gj_set_deterministic(int32_t on);
 
 /* Workspace bytes needed by gj_mp_step_fwd (the per-node projections P|Q of the factorised first edge layer). */
 size_t gj_mp_step_fwd_workspace(const gj_mp_desc* d);
@@ -149,6 +161,16 @@ int gj_assignment(int32_t batch, int32_t n, int32_t dim, int32_t lorentz, const 
 int gj_adam_step_flat(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n,
                       float lr, float beta1, float beta2, float eps, int32_t step,
                       float grad_scale, float l1_lambda, float l2_lambda, void* stream);
+
+/* The other optimisers utils/initialize.py:154-170 can select, over the same flat buffers and with the same regulariser terms:
+ * GJ_OPT_RMSPROP (torch.optim.RMSprop: sq = alpha sq + (1 - alpha) g^2, buf = momentum buf + g / (sqrt(sq) + eps), p -= lr buf; the
+ * reference passes eps 1e-16, momentum 0.9, alpha is torch's default 0.99), GJ_OPT_ADAGRAD (sq += g^2, p -= lr g / (sqrt(sq) + eps),
+ * eps 1e-16) and GJ_OPT_SGD (buf = momentum buf + g, p -= lr buf, momentum 0.9).  momentum_buf / sq_acc start at zero. */
+#define GJ_OPT_RMSPROP 1
+#define GJ_OPT_ADAGRAD 2
+#define GJ_OPT_SGD 3
+int gj_optimizer_step_flat(int32_t kind, float* param, const float* grad, float* momentum_buf, float* sq_acc, size_t n, float lr,
+                           float alpha, float momentum, float eps, float grad_scale, float l1_lambda, float l2_lambda, void* stream);
 
 /* sum|p| and sum p^2 over n floats into out[0], out[1] (overwritten; deterministic two-stage). */
 int gj_param_norms(const float* param, size_t n, float* out, void* workspace, size_t workspace_bytes, void* stream);

@@ -547,6 +547,25 @@ def test_flat_adam_matches_torch():
     assert rel(p.cpu().numpy(), ref.detach().numpy()) < 1e-6
 
 
+@pytest.mark.parametrize("kind", ["rmsprop", "adagrad", "sgd"])
+def test_flat_optimizers_match_torch(kind):
+    """gj_optimizer_step_flat against torch.optim with the hyper-parameters utils/initialize.py:154-170 passes."""
+    g = torch.Generator().manual_seed(2)
+    p0 = torch.randn(10007, generator=g)
+    p = p0.clone().to(DEV)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    ref = torch.nn.Parameter(p0.clone().double())
+    opt = {"rmsprop": lambda: torch.optim.RMSprop([ref], lr=1e-3, eps=1e-16, momentum=0.9),
+           "adagrad": lambda: torch.optim.Adagrad([ref], lr=1e-3, eps=1e-16),
+           "sgd": lambda: torch.optim.SGD([ref], lr=1e-3, momentum=0.9)}[kind]()
+    for _ in range(5):
+        gr = torch.randn(10007, generator=g)
+        ops.optimizer_step_flat_(kind, p, gr.to(DEV), m, v, lr=1e-3, l1_lambda=1e-3, l2_lambda=1e-2)
+        ref.grad = gr.double() + 1e-3 * torch.sign(ref.detach()) + 2e-2 * ref.detach()
+        opt.step()
+    assert rel(p.cpu().numpy(), ref.detach().numpy()) < 1e-6
+
+
 def test_linear_and_latent_mean_and_norms():
     g = torch.Generator().manual_seed(1)
     x = torch.randn(300, 20, generator=g).to(DEV).requires_grad_(True)
@@ -664,6 +683,33 @@ def test_saved_forward_byproducts_reproduce_the_plain_calls():
     with pytest.raises(_lib.GnnJetError):
         ops.raw_mp_fwd(d32, h.data_ptr(), flat.data_ptr(), outs[0][0].data_ptr(), outs[0][1].data_ptr(), ws.data_ptr(), ws_bytes, st,
                        saved.data_ptr())
+
+
+@pytest.mark.parametrize("shape", [([32, 128, 64, 16], [16, 32], 16), ([64, 64], [64], 64)])
+def test_deterministic_mode_gives_bitwise_parameter_gradients(shape):
+    """ops.set_deterministic (gj_set_deterministic): parameter gradients of the bf16 backward are bit-identical from run to run and
+    agree with the default mode to fp32 summation order."""
+    edge, node, H = shape
+    N, B = 30, 1024
+    rng = np.random.default_rng(11)
+    npar = sum(o * i + o for i, o in zip([2 * H + 1] + edge[:-1], edge)) + sum(o * i + o for i, o in zip([edge[-1] + H] + node[:-1], node))
+    flat = torch.from_numpy(rng.uniform(-0.2, 0.2, npar)).float().to(DEV)
+    h = torch.from_numpy(rng.normal(0, 0.5, (B, N, H))).float().to(DEV)
+    dy = torch.from_numpy(rng.normal(0, 1.0, (B, N, node[-1]))).float().to(DEV)
+    args = (N, H, edge, node, 0.2, 0, ops.PRECISIONS["bf16"])
+    y, e = torch.ops.gnnjet.mp_step_fwd(h, flat, *args)
+    dh0, g0 = torch.ops.gnnjet.mp_step_bwd(h, e, flat, dy, *args)
+    prev = ops.set_deterministic(True)
+    try:
+        runs = [torch.ops.gnnjet.mp_step_bwd(h, e, flat, dy, *args) for _ in range(3)]
+    finally:
+        ops.set_deterministic(prev)
+    torch.cuda.synchronize()
+    for dh, g in runs[1:]:
+        assert torch.equal(g, runs[0][1]) and torch.equal(dh, runs[0][0])
+    # against the default mode: same sums in a different grouping (the tile ranges of the groups differ)
+    assert rel(runs[0][0].cpu().numpy(), dh0.cpu().numpy()) < 1e-5
+    assert rel(runs[0][1].cpu().numpy(), g0.cpu().numpy()) < 1e-5
 
 
 def test_bench_hooks_relaunch_the_fused_kernels():

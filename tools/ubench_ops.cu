@@ -37,6 +37,13 @@ __global__ void __launch_bounds__(512, 1) bench(long long* out, float seed) {
       if (OP == 10) asm volatile("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(u[i]) : "f"(x[2 * i]), "f"(__uint_as_float(u[i])));
       if (OP == 11) asm volatile("lop3.b32 %0, %0, %1, %1, 0x96;" : "+r"(u[i]) : "r"(al));
       if (OP == 12) asm volatile("prmt.b32 %0, %0, %1, 0x5410;" : "+r"(u[i]) : "r"(al));
+      if (OP == 13) asm volatile("{.reg .pred p; setp.gt.f32 p, %0, %1; selp.f32 %0, %0, %1, p;}" : "+f"(x[i]) : "f"(x[i + ILP]));   // FSETP + FSEL
+      if (OP == 14) asm volatile("mad.lo.s32 %0, %0, %1, %1;" : "+r"(u[i]) : "r"(al));                                              // IMAD
+      if (OP == 15) asm volatile("set.gt.bf16x2.bf16x2 %0, %0, %1;" : "+r"(u[i]) : "r"(al));                                        // HSET2
+      if (OP == 16) asm volatile("add.s32 %0, %0, %1;" : "+r"(u[i]) : "r"(al));                                                     // IADD3
+      if (OP == 17) asm volatile("shf.l.wrap.b32 %0, %0, %1, 3;" : "+r"(u[i]) : "r"(al));                                           // SHF
+      if (OP == 18) asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(x[i]) : "f"(x[i + ILP]));                                          // FADD
+      if (OP == 19) asm volatile("{.reg .pred p; setp.gt.s32 p, %0, %1; selp.b32 %0, %0, %1, p;}" : "+r"(u[i]) : "r"(al));          // ISETP + SEL
     }
   }
   long long t1 = clock64();
@@ -58,7 +65,7 @@ void run(const char* name, int nthreads) {
   cudaError_t e = cudaDeviceSynchronize();
   long long h = 0; cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
   const double warps_per_smsp = nthreads / 32 / 4.0;
-  printf("%-28s %3d thr: %6.2f cyc per warp-instruction per SMSP  %s\n", name, nthreads, (double)h / (REPS * ILP * warps_per_smsp),
+  printf("%-58s %3d thr: %6.2f cyc per warp-instruction per SMSP  %s\n", name, nthreads, (double)h / (REPS * ILP * warps_per_smsp),
          e == cudaSuccess ? "" : cudaGetErrorString(e));
   cudaFree(d);
 }
@@ -78,6 +85,13 @@ int main() {
     run<9>("shfl.bfly", nt);
     run<11>("lop3", nt);
     run<12>("prmt", nt);
+    run<13>("setp.gt.f32 + selp.f32 (FSETP + FSEL, two instructions)", nt);
+    run<14>("mad.lo.s32 (IMAD)", nt);
+    run<15>("set.gt.bf16x2 (HSET2)", nt);
+    run<16>("add.s32 (IADD3)", nt);
+    run<17>("shf.l.wrap (SHF)", nt);
+    run<18>("add.f32 (FADD)", nt);
+    run<19>("setp + selp.b32 (ISETP + SEL, two instructions)", nt);
   }
   return 0;
 }
