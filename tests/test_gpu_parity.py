@@ -137,27 +137,29 @@ def test_mp_step_matches_oracle(precision, N, H, edge, node, B, metric):
     nb = [rng.uniform(-1, 1, s[0]) / np.sqrt(s[1]) for s in shapes_n]
     h = rng.normal(0, 0.5, (B, N, H))
     dy = rng.normal(0, 1.0, (B, N, node[-1]))
-    y_ref, cache = O.mp_step_forward(h, ew, eb, nw, nb, 0.2, metric)
-    dh_ref, dew, deb, dnw, dnb = O.mp_step_backward(dy, cache, ew, nw)
     flat_ref = np.concatenate([np.concatenate([w.ravel(), b.ravel()]) for w, b in zip(ew, eb)] +
                               [np.concatenate([w.ravel(), b.ravel()]) for w, b in zip(nw, nb)])
-    gflat_ref = np.concatenate([np.concatenate([w.ravel(), b.ravel()]) for w, b in zip(dew, deb)] +
-                               [np.concatenate([w.ravel(), b.ravel()]) for w, b in zip(dnw, dnb)])
     flat = torch.from_numpy(flat_ref).float().to(DEV)
     ht = torch.from_numpy(h).float().to(DEV)
-    args = (N, H, edge, node, 0.2, ops.metric_id(metric), ops.PRECISIONS[precision])
-    y, e = torch.ops.gnnjet.mp_step_fwd(ht, flat, *args)
-    dh, dflat = torch.ops.gnnjet.mp_step_bwd(ht, e, flat, torch.from_numpy(dy).float().to(DEV), *args)
     t = TOL[precision]
     # Random networks on random inputs put ~0.3 % of the pre-activations within bf16 rounding of the LeakyReLU kink; each
     # picks the other slope (an O(1) error on that element), which alone is sqrt(0.003) * 0.8 = 4 % of the step's gradient in
-    # ANY bf16 evaluation order.  The model-level golden tests (realistic weights / jets) hold 3e-2; this one checks the
-    # tiling, masking and reduction logic at the j-block boundaries.
-    gtol = t["grad"] if precision == "fp32" else 8e-2
-    assert rel(y.cpu().numpy(), y_ref) < t["out"]
-    assert rel(e.cpu().numpy(), O.leaky(cache["edge_z"][-1], 0.2).sum(axis=2)) < t["out"]
-    assert rel(dh.cpu().numpy(), dh_ref) < gtol
-    assert rel(dflat.cpu().numpy(), gflat_ref) < gtol
+    # ANY bf16 evaluation order (measured 2e-2 .. 5.4e-2 on these cases).  The model-level golden tests (realistic weights /
+    # jets) hold 3e-2.  The second pass, alpha = 1 (no kink, same kernels, same tiling / masking / reduction logic at the j-block
+    # boundaries), isolates the arithmetic: gradients within 2e-2 (measured <= 7e-3).
+    for alpha, gtol_bf16 in ((0.2, 8e-2), (1.0, 2e-2)):
+        y_ref, cache = O.mp_step_forward(h, ew, eb, nw, nb, alpha, metric)
+        dh_ref, dew, deb, dnw, dnb = O.mp_step_backward(dy, cache, ew, nw)
+        gflat_ref = np.concatenate([np.concatenate([w.ravel(), b.ravel()]) for w, b in zip(dew, deb)] +
+                                   [np.concatenate([w.ravel(), b.ravel()]) for w, b in zip(dnw, dnb)])
+        args = (N, H, edge, node, alpha, ops.metric_id(metric), ops.PRECISIONS[precision])
+        y, e = torch.ops.gnnjet.mp_step_fwd(ht, flat, *args)
+        dh, dflat = torch.ops.gnnjet.mp_step_bwd(ht, e, flat, torch.from_numpy(dy).float().to(DEV), *args)
+        gtol = t["grad"] if precision == "fp32" else gtol_bf16
+        assert rel(y.cpu().numpy(), y_ref) < t["out"], alpha
+        assert rel(e.cpu().numpy(), O.leaky(cache["edge_z"][-1], alpha).sum(axis=2)) < t["out"], alpha
+        assert rel(dh.cpu().numpy(), dh_ref) < gtol, alpha
+        assert rel(dflat.cpu().numpy(), gflat_ref) < gtol, alpha
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
