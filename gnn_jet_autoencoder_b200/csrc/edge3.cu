@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_fwd3_kernel(const E3Args A,
   const int N = A.N, ntasks = A.B * A.NJB;
   int k = g0 / N, i = g0 - k * N;
   bool fresh = true, p_active = false, p_valid = false;
+  uint32_t p_vmask = 0u;      // lanes (j) of the warp's j block that are real particles
   uint32_t q[E0 / 2];      // Q_j as bf16 pairs
   size_t node0 = 0;
   float* e_dst = nullptr;
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_fwd3_kernel(const E3Args A,
   };
 
   // first edge layer of tile (k, i) -> packed bf16 pairs in TMEM buffer `buf`; advances (k, i)
-  auto prepare = [&](int buf, bool& t_active, bool& t_valid, float*& t_erow) {
+  auto prepare = [&](int buf, bool& t_active, bool& t_valid, float*& t_erow, uint32_t& t_vmask) {
     if (fresh) {
       const int task = 4 * k + wq;
       p_active = task < ntasks;
@@ -184,6 +185,7 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_fwd3_kernel(const E3Args A,
       jb = tk - jet * A.NJB;
       const int j = jb * 32 + lane;
       p_valid = p_active && j < N;
+      p_vmask = __ballot_sync(0xffffffffu, p_valid);
       node0 = (size_t)jet * N;
       e_dst = A.e_out + ((size_t)jb * A.B + jet) * N * E1;
       e3_cp_async_wait<0>();
@@ -233,19 +235,21 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_fwd3_kernel(const E3Args A,
       }
       tmem_st_wait();
     }
-    t_active = p_active; t_valid = p_valid; t_erow = e_dst + (size_t)i * E1;
+    t_active = p_active; t_valid = p_valid; t_erow = e_dst + (size_t)i * E1; t_vmask = p_vmask;
     if (++i == N) { i = 0; ++k; fresh = true; }
   };
 
   uint32_t ph = 0;
   bool n_active = false, n_valid = false;
   float* n_erow = nullptr;
-  if (g0 < g1) prepare(0, n_active, n_valid, n_erow);
+  uint32_t n_vmask = 0u;
+  if (g0 < g1) prepare(0, n_active, n_valid, n_erow, n_vmask);
 
   for (int g = g0; g < g1; ++g) {
     const int buf = (g - g0) & 1;
     const bool active = n_active, valid = n_valid;
     float* const erow = n_erow;
+    const uint32_t valid_mask = n_vmask;
     tc_fence_before();
     named_bar_sync(1 + wg, 128);      // the group's a0 rows are in TMEM; the previous tile's accumulator has been read
     if (wq == 0) {
@@ -256,19 +260,46 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_fwd3_kernel(const E3Args A,
       mma_bf16_ss_elect(acc0, dOnes, dB1, idesc, 1u);
       mma_commit_elect(bar);
     }
-    if (g + 1 < g1) prepare(buf ^ 1, n_active, n_valid, n_erow);      // behind the GEMM
+    if (g + 1 < g1) prepare(buf ^ 1, n_active, n_valid, n_erow, n_vmask);      // behind the GEMM
     mbar_wait(bar, ph);
     tc_fence_after();
+    // e_i = sum over the quadrant's 32 lanes (j) of leaky(acc), padded rows masked: the accumulator is read as matrix fragments
+    // (tmem_ld_frag16: this thread holds lanes g, g + 8, g + 16, g + 24, g = lane / 4, of columns 2q, 2q + 1, 8 + 2q, 9 + 2q of each
+    // 16-column chunk), so the sum is local adds and three shuffle rounds over g per chunk
+    {
+      const uint32_t vm = valid_mask >> (lane >> 2);
+      const float m0 = (vm & 1u) ? 1.f : 0.f, m1 = (vm & 0x100u) ? 1.f : 0.f, m2 = (vm & 0x10000u) ? 1.f : 0.f, m3 = (vm & 0x1000000u) ? 1.f : 0.f;
+      uint32_t fa[2][8], fb[2][8];
+      tmem_ld_frag16(acc, fa[0]);
+      tmem_ld_frag16(acc + (16u << 16), fb[0]);
 #pragma unroll
-    for (int c0 = 0; c0 < E1; c0 += 16) {
-      uint32_t r[16];
-      tmem_ld16_u(acc + (uint32_t)c0, r);
-      tmem_ld_wait(); tmem_pin16(r);
-      float v[16];
+      for (int c0 = 0; c0 < E1; c0 += 16) {
+        const int cur = (c0 >> 4) & 1;
+        tmem_ld_wait(); tmem_pin8(fa[cur]); tmem_pin8(fb[cur]);
+        if (c0 + 16 < E1) {
+          tmem_ld_frag16(acc + (uint32_t)(c0 + 16), fa[cur ^ 1]);
+          tmem_ld_frag16(acc + (uint32_t)(c0 + 16) + (16u << 16), fb[cur ^ 1]);
+        }
+        float s[4];
 #pragma unroll
-      for (int c = 0; c < 16; ++c) { const float z = __uint_as_float(r[c]); v[c] = valid ? fmaxf(z, alpha * z) : 0.f; }
-      const float s = e3_transpose_sum16(v, lane);
-      if (active && (lane & 1) == 0) erow[c0 + (lane >> 1)] = s;
+        for (int kk = 0; kk < 2; ++kk) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const float z0 = __uint_as_float(fa[cur][4 * kk + c]) * m0, z1 = __uint_as_float(fa[cur][4 * kk + 2 + c]) * m1;
+            const float z2 = __uint_as_float(fb[cur][4 * kk + c]) * m2, z3 = __uint_as_float(fb[cur][4 * kk + 2 + c]) * m3;
+            s[2 * kk + c] = (fmaxf(z0, alpha * z0) + fmaxf(z1, alpha * z1)) + (fmaxf(z2, alpha * z2) + fmaxf(z3, alpha * z3));
+          }
+        }
+#pragma unroll
+        for (int off = 4; off < 32; off <<= 1) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) s[c] += __shfl_xor_sync(0xffffffffu, s[c], off);
+        }
+        if (active && lane < 4) {
+          *reinterpret_cast<float2*>(erow + c0 + 2 * lane) = make_float2(s[0], s[1]);
+          *reinterpret_cast<float2*>(erow + c0 + 8 + 2 * lane) = make_float2(s[2], s[3]);
+        }
+      }
     }
     ph ^= 1u;
   }

@@ -443,10 +443,49 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args 
         }
 #pragma unroll
         for (int c = 0; c < 16; ++c) { dq[16 * hf + c] += z[c]; dwd[16 * hf + c] = fmaf(z[c], dt, dwd[16 * hf + c]); }
-        const float s = warp_transpose_sum16(z, lane);
-        if (active && (lane & 1) == 0) dp_dst[16 * hf + (lane >> 1)] = s;
       }
       if (active) A.G[(node0 + it) * A.NJ32 + jb * 32 + lane] = valid ? gsum : 0.f;
+      // dP_i = sum over the quadrant's 32 lanes (j) of dz0 (zero on padded rows: dz3 is).  dz0 goes back to TMEM [64,96) (in place
+      // over da0) and is re-read as matrix fragments (tmem_ld_frag16): this thread then holds lanes g, g + 8, g + 16, g + 24
+      // (g = lane / 4) of columns 2q, 2q + 1 (+ 8, 16, 24), so the sum is 24 local adds and three shuffle rounds over g instead of
+      // two 31-shuffle transposes.
+      {
+        uint32_t w0[16], w1[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) { w0[c] = __float_as_uint(z0[c]); w1[c] = __float_as_uint(z1[c]); }
+        tmem_st16(slot + 64, w0);
+        tmem_st16(slot + 80, w1);
+        tmem_st_wait();
+        uint32_t f[4][8];      // [column half (16 columns)][lanes 0..15 / 16..31] -> 8 registers each
+        tmem_ld_frag16(slot + 64, f[0]);
+        tmem_ld_frag16(slot + 64 + (16u << 16), f[1]);
+        tmem_ld_frag16(slot + 80, f[2]);
+        tmem_ld_frag16(slot + 80 + (16u << 16), f[3]);
+        tmem_ld_wait(); tmem_pin8(f[0]); tmem_pin8(f[1]); tmem_pin8(f[2]); tmem_pin8(f[3]);
+        float s[8];      // columns 2q, 2q + 1, 8 + 2q, 9 + 2q of each half
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+              s[4 * hf + 2 * k + c] = (__uint_as_float(f[2 * hf][4 * k + c]) + __uint_as_float(f[2 * hf][4 * k + 2 + c])) +
+                                      (__uint_as_float(f[2 * hf + 1][4 * k + c]) + __uint_as_float(f[2 * hf + 1][4 * k + 2 + c]));
+          }
+        }
+#pragma unroll
+        for (int off = 4; off < 32; off <<= 1) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) s[c] += __shfl_xor_sync(0xffffffffu, s[c], off);
+        }
+        if (active && lane < 4) {
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            *reinterpret_cast<float2*>(dp_dst + 16 * hf + 2 * lane) = make_float2(s[4 * hf], s[4 * hf + 1]);
+            *reinterpret_cast<float2*>(dp_dst + 16 * hf + 8 + 2 * lane) = make_float2(s[4 * hf + 2], s[4 * hf + 3]);
+          }
+        }
+      }
     };
 
     if (g0 < g1) {

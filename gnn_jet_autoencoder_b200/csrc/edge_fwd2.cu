@@ -208,6 +208,7 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_fwd2_kernel(const Fwd2Args 
   bool fresh = true;
   uint32_t q[E0 / 2];      // Q_j as bf16 pairs
   bool p_active = false, p_valid = false;
+  uint32_t p_vmask = 0u;      // lanes (j) of the warp's j block that are real particles
   size_t node0 = 0;
   float* e_dst = nullptr;
   int e_dst_jb = 0;
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_fwd2_kernel(const Fwd2Args 
   };
 
   // first edge layer of the tile (k, i) -> a0 (shared memory, bf16 A operand); advances (k, i)
-  auto prepare = [&](bool& t_active, bool& t_valid, float*& t_erow) {
+  auto prepare = [&](bool& t_active, bool& t_valid, float*& t_erow, uint32_t& t_vmask) {
     if (fresh) {
       // ---- new (jet, j block): Q_j -> registers, h_j -> per-lane shared row ----
       const int task = 4 * k + wq;
@@ -245,6 +246,7 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_fwd2_kernel(const Fwd2Args 
       const int jet = tk / A.NJB, jb = tk - jet * A.NJB;
       const int j = jb * 32 + lane;
       p_valid = p_active && j < N;
+      p_vmask = __ballot_sync(0xffffffffu, p_valid);
       node0 = (size_t)jet * N;
       e_dst = A.e_out + ((size_t)jb * A.B + jet) * N * E3;
       e_dst_jb = jb;
@@ -313,7 +315,7 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_fwd2_kernel(const Fwd2Args 
       }
       fence_proxy_async();
     }
-    t_active = p_active; t_valid = p_valid; t_erow = e_dst + (size_t)i * E3;
+    t_active = p_active; t_valid = p_valid; t_erow = e_dst + (size_t)i * E3; t_vmask = p_vmask;
     if (++i == N) { i = 0; ++k; fresh = true; }
   };
 
@@ -321,12 +323,14 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_fwd2_kernel(const Fwd2Args 
   int tr_n = 0;
   bool n_active = false, n_valid = false;
   float* n_erow = nullptr;
-  if (g0 < g1) prepare(n_active, n_valid, n_erow);
+  uint32_t n_vmask = 0u;
+  if (g0 < g1) prepare(n_active, n_valid, n_erow, n_vmask);
 
   for (int g = g0; g < g1; ++g) {
     F2_STAMP(0);
     const bool active = n_active, valid = n_valid;
     float* const erow = n_erow;
+    const uint32_t valid_mask = n_vmask;
     // ---- layer 1: acc1[0,128) = a0 (shared memory) W1^T + b1 ----
     tc_fence_before();
     named_bar_sync(1 + wg, 128);
@@ -355,7 +359,7 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_fwd2_kernel(const Fwd2Args 
       mma_commit_elect(bars + 1);
     }
     // ---- first layer of the NEXT tile while layer 2 runs on the tensor pipe (a0 is free: layer 1 has completed) ----
-    if (g + 1 < g1) prepare(n_active, n_valid, n_erow);
+    if (g + 1 < g1) prepare(n_active, n_valid, n_erow, n_vmask);
     F2_STAMP(4);
     mbar_wait_all(bars + 1, ph);
     tc_fence_after();
@@ -377,14 +381,35 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_fwd2_kernel(const Fwd2Args 
     F2_STAMP(7);
     ++tr_n;
     {
-      uint32_t r[16];
-      tmem_ld16_u(slot + E2 / 2, r);
-      tmem_ld_wait(); tmem_pin16(r);
-      float v[16];
+      // e_i = sum over the quadrant's 32 lanes (j) of leaky(acc3), padded rows masked.  The accumulator is read as matrix
+      // fragments (tmem_ld_frag16): this thread holds lanes g, g + 8, g + 16, g + 24 (g = lane / 4) of columns 2q, 2q + 1, 8 + 2q,
+      // 9 + 2q (q = lane % 4), so the sum is 12 local adds and three shuffle rounds over g.
+      uint32_t fa[8], fb[8];
+      tmem_ld_frag16(slot + E2 / 2, fa);
+      tmem_ld_frag16(slot + E2 / 2 + (16u << 16), fb);
+      const int g4 = lane >> 2;
+      const uint32_t vm = valid_mask >> g4;      // bit 0, 8, 16, 24: rows g, g + 8, g + 16, g + 24 are real particles
+      const float m0 = (vm & 1u) ? 1.f : 0.f, m1 = (vm & 0x100u) ? 1.f : 0.f, m2 = (vm & 0x10000u) ? 1.f : 0.f, m3 = (vm & 0x1000000u) ? 1.f : 0.f;
+      tmem_ld_wait(); tmem_pin8(fa); tmem_pin8(fb);
+      float s[4];
 #pragma unroll
-      for (int c = 0; c < 16; ++c) { const float z = __uint_as_float(r[c]); v[c] = valid ? fmaxf(z, alpha * z) : 0.f; }
-      const float s = warp_transpose_sum16(v, lane);
-      if (active && (lane & 1) == 0) erow[lane >> 1] = s;
+      for (int k = 0; k < 2; ++k) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const float z0 = __uint_as_float(fa[4 * k + c]) * m0, z1 = __uint_as_float(fa[4 * k + 2 + c]) * m1;
+          const float z2 = __uint_as_float(fb[4 * k + c]) * m2, z3 = __uint_as_float(fb[4 * k + 2 + c]) * m3;
+          s[2 * k + c] = (fmaxf(z0, alpha * z0) + fmaxf(z1, alpha * z1)) + (fmaxf(z2, alpha * z2) + fmaxf(z3, alpha * z3));
+        }
+      }
+#pragma unroll
+      for (int off = 4; off < 32; off <<= 1) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) s[c] += __shfl_xor_sync(0xffffffffu, s[c], off);
+      }
+      if (active && lane < 4) {
+        *reinterpret_cast<float2*>(erow + 2 * lane) = make_float2(s[0], s[1]);
+        *reinterpret_cast<float2*>(erow + 8 + 2 * lane) = make_float2(s[2], s[3]);
+      }
     }
     ph ^= 1u;
   }

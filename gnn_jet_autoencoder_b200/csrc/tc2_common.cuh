@@ -41,6 +41,16 @@ __device__ __forceinline__ void tmem_ld32_u(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
 }
+// Matrix-fragment load: 16 lanes x 16 columns starting at (lane, column) of taddr.  Thread t receives, for g = t / 4 and q = t % 4,
+//   r[0], r[1] = (lane g,     columns 2q, 2q + 1)      r[2], r[3] = (lane g + 8, columns 2q, 2q + 1)
+//   r[4], r[5] = (lane g,     columns 8 + 2q, 9 + 2q)  r[6], r[7] = (lane g + 8, columns 8 + 2q, 9 + 2q)
+// (measured with tools/tmem_frag_probe.cu).  Every thread holds elements of FOUR lanes after two such loads (lane offsets 0 and 16),
+// which turns a sum over the 32 lanes of a quadrant into local adds plus three shuffle rounds instead of a 31-shuffle transpose.
+__device__ __forceinline__ void tmem_ld_frag16(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
 // None of the TMEM load / store wrappers carries a "memory" clobber: they do not touch C++-visible memory, and being
 // volatile they keep their order relative to each other and to the fences / barrier waits (which do clobber memory);
 // ordinary shared-memory loads and stores may be scheduled across them.
