@@ -177,9 +177,28 @@ def _train_config(N, B, precision, dev, flush, steps, arch=None, group=None, wor
     from gnn_jet_autoencoder_b200 import GNNAETrainer, synthetic_jets
     from gnn_jet_autoencoder_b200.config import DEFAULT_ARCH, build_models, train_flops_per_jet
     arch = arch or DEFAULT_ARCH
-    enc, dec = build_models(N, arch, device=dev, precision=precision, seed=0)
-    tr = GNNAETrainer(enc, dec, batch_size=B, process_group=group)
-    host = torch.from_numpy(synthetic_jets(B, N, seed=seed)).pin_memory()
+    # build + warm-up (kernel loading, CUDA-graph capture) carry no collective; the ranks then agree that every one of them got
+    # through before the first barrier, so that a failure on one rank is reported instead of leaving the others in a collective
+    err, tr, host = None, None, None
+    try:
+        enc, dec = build_models(N, arch, device=dev, precision=precision, seed=0)
+        tr = GNNAETrainer(enc, dec, batch_size=B, process_group=group)
+        host = torch.from_numpy(synthetic_jets(B, N, seed=seed)).pin_memory()
+        tr.load_batch(host)
+        tr.compute_gradients()
+        torch.cuda.synchronize()
+    except Exception as ex:
+        err = ex
+    if world > 1:
+        import torch.distributed as dist
+        ok = torch.tensor([0.0 if err is not None else 1.0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() < 1.0 and err is None:
+            err = RuntimeError("another rank failed while building / capturing this configuration")
+    if err is not None:
+        del tr
+        torch.cuda.empty_cache()
+        raise err
     ms = _time_trainer(tr, host, steps, 3, flush, barrier, rank_max)
     value = world * B / (ms * 1e-3)
     peaks = measured_peaks()
@@ -325,6 +344,20 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (impl=ours) needs a CUDA device: the path has no CPU fallback")
+    # Last-resort guard for multi-rank runs: a rank stuck in a collective (a peer died, NCCL teardown hangs) would keep the whole job
+    # alive until the launcher's limit.  At the deadline rank 0 prints the line it has (the headline measurement comes first, the extra
+    # "configs" last) and every rank leaves.
+    state = {"line": None, "printed": False}
+    def _deadline():
+        if rank == 0 and state["line"] is not None and not state["printed"]:
+            state["line"]["configs_incomplete"] = "deadline reached while measuring the extra configurations"
+            print(json.dumps(state["line"]), flush=True)
+        os._exit(0 if (rank != 0 or state["line"] is not None) else 1)
+    if world > 1:
+        import threading
+        guard = threading.Timer(float(os.environ.get("GNNJET_BENCH_DEADLINE_S", "420")), _deadline)
+        guard.daemon = True
+        guard.start()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -401,45 +434,13 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
 
-    # ---- the other BASELINE configurations ("configs") and the data-parallel parity check ----
-    configs, dp_parity = {}, None
-    if world > 1:
-        # parameters after the timed steps: bit-identical on every rank (same all-reduced gradient, same fused Adam)
-        ref = tr.flat.clone()
-        dist.broadcast(ref, 0)
-        same = torch.tensor([1.0 if torch.equal(ref, tr.flat) else 0.0], device=dev)
-        dist.all_reduce(same, op=dist.ReduceOp.MIN)
-        err = _dp_parity(dev, world, rank, args.precision)
-        dp_parity = {"params_bit_identical_across_ranks": bool(same.item() == 1.0), "grad_rel_err_vs_one_rank": err,
-                     "what": f"8 jets per rank, N=30: all-reduced {world}-rank flat gradient vs one rank on the concatenated batch"}
+    # ---- the headline line (rank 0); the extra configurations are filled in below as they complete ----
     d2h_bytes = tr.stats_host.numel() * 4
-    if not args.no_configs and N == 30 and not args.batch:
-        del tr
-        torch.cuda.empty_cache()
-        if world > 1:      # config 4 as specified: fixed global batch 32768, B/G jets per rank (strong scaling)
-            r = _train_config(30, 32768 // world, args.precision, dev, flush, max(4, args.steps // 2), world=world, barrier=barrier,
-                              rank_max=rank_max, seed=1234 + rank)
-            r["scaling"] = "strong"
-            configs["config4_global32768"] = r
-        if world in (1, 8):
-            configs["config5_sweep"] = {"points": _sweep_points(dev, flush, world, None, barrier, rank_max),
-                                        "note": "node_sizes [[H]], edge_sizes [[H, H]], N=30, 2048 jets per GPU (512 at H=256), bf16 mode; "
-                                                "roofline fraction on the dense-formulation FLOPs"}
-        if world == 1:
-            configs["config3_n150_b2048"] = _train_config(150, 2048, "bf16", dev, flush, 6)
-            configs["config2_fp32_mode"] = _train_config(30, 4096, "fp32", dev, flush, 4)
-            configs["config4_global32768"] = dict(_train_config(30, 32768, args.precision, dev, flush, 4), scaling="strong",
-                                                  note="one GPU: the denominator of config 4's 2/4/8-GPU strong scaling")
-            configs["gpu_reference"] = _gpu_reference(dev)
-            if not args.no_cpu_baseline:
-                configs["config1_cpu_forward"] = _cpu_forward_config1()
-                cb150, _ = cpu_reference_step_rate(150, 16, steps=3, warmup=1, budget_s=15.0)
-                configs["cpu_train_n150_b16"] = cb150
-
+    configs = {}
     if rank == 0:
         flops_jet = train_flops_per_jet(N, DEFAULT_ARCH)
         step_tflops = value / world * flops_jet / 1e12          # per GPU
-        line = {
+        state["line"] = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "fp32", "data": "synthetic",
@@ -461,14 +462,66 @@ def run_ours(args):
             "last_loss": last,
             "configs": configs,
         }
-        if dp_parity is not None:
-            line["dp_parity"] = dp_parity
+
+    # ---- the other BASELINE configurations ("configs") and the data-parallel parity check ----
+    if world > 1:
+        # parameters after the timed steps: bit-identical on every rank (same all-reduced gradient, same fused Adam)
+        ref = tr.flat.clone()
+        dist.broadcast(ref, 0)
+        same = torch.tensor([1.0 if torch.equal(ref, tr.flat) else 0.0], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        err = _dp_parity(dev, world, rank, args.precision)
+        if rank == 0:
+            state["line"]["dp_parity"] = {"params_bit_identical_across_ranks": bool(same.item() == 1.0), "grad_rel_err_vs_one_rank": err,
+                                          "what": f"8 jets per rank, N=30: all-reduced {world}-rank flat gradient vs one rank on the concatenated batch"}
+    if not args.no_configs and N == 30 and not args.batch:
+        del tr
+        torch.cuda.empty_cache()
+        if world > 1:      # config 4 as specified: fixed global batch 32768, B/G jets per rank (strong scaling)
+            try:
+                r = _train_config(30, 32768 // world, args.precision, dev, flush, max(4, args.steps // 2), world=world, barrier=barrier,
+                                  rank_max=rank_max, seed=1234 + rank)
+                r["scaling"] = "strong"
+            except Exception as ex:
+                r = {"error": f"{type(ex).__name__}: {str(ex)[:160]}"}
+            configs["config4_global32768"] = r
+        sweep_worlds = [int(w) for w in os.environ.get("GNNJET_BENCH_SWEEP_WORLDS", "1,8").split(",") if w]
+        if world in sweep_worlds:
+            configs["config5_sweep"] = {"points": _sweep_points(dev, flush, world, None, barrier, rank_max),
+                                        "note": "node_sizes [[H]], edge_sizes [[H, H]], N=30, 2048 jets per GPU (512 at H=256), bf16 mode; "
+                                                "roofline fraction on the dense-formulation FLOPs"}
+        if world == 1:
+            configs["config3_n150_b2048"] = _train_config(150, 2048, "bf16", dev, flush, 6)
+            configs["config2_fp32_mode"] = _train_config(30, 4096, "fp32", dev, flush, 4)
+            configs["config4_global32768"] = dict(_train_config(30, 32768, args.precision, dev, flush, 4), scaling="strong",
+                                                  note="one GPU: the denominator of config 4's 2/4/8-GPU strong scaling")
+            configs["gpu_reference"] = _gpu_reference(dev)
+            if not args.no_cpu_baseline:
+                configs["config1_cpu_forward"] = _cpu_forward_config1()
+                cb150, _ = cpu_reference_step_rate(150, 16, steps=3, warmup=1, budget_s=15.0)
+                configs["cpu_train_n150_b16"] = cb150
+
+    if rank == 0:
+        line = state["line"]
         if world == 1 and not args.no_cpu_baseline:
             sample = args.cpu_sample or (256 if N <= 32 else 16)
             line["cpu_baseline"], _ = cpu_reference_step_rate(N, sample, steps=8, warmup=1, budget_s=20.0)
         print(json.dumps(line), flush=True)
+        state["printed"] = True
     if world > 1:
-        dist.destroy_process_group()
+        # NCCL teardown has been seen to hang when a peer is gone: the line is out, leave after a bounded wait
+        import threading
+        bye = threading.Timer(20.0, lambda: os._exit(0))
+        bye.daemon = True
+        bye.start()
+        try:
+            torch.cuda.synchronize()
+            dist.barrier()
+            dist.destroy_process_group()
+        except Exception:
+            pass
+        sys.stdout.flush()
+        os._exit(0)
 
 
 def kernel_traffic(args, B, N):

@@ -402,7 +402,9 @@ class GNNAETrainer:
             self.launches_per_step = ops.LAUNCHES["count"] - before + 1   # + Adam
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            # thread-local capture mode: other threads of the process (NCCL's watchdog, a pinned-memory loader) may call into the CUDA
+            # runtime while the step is being captured; in the default global mode such a call invalidates a long capture
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 self._fwd_bwd()
             ops.LAUNCHES["count"] -= self.launches_per_step - 1    # the capture pass launched nothing
             self.graph = g
