@@ -268,6 +268,23 @@ __global__ void __launch_bounds__(256) reduce_split_kernel(const float* __restri
   out[m * ldo + n] = accumulate ? out[m * ldo + n] + s : s;
 }
 
+// The same for up to RM_MAX reductions in ONE launch (the node-level backward of a step queues its weight-gradient and bias
+// reductions and flushes them once: they are latency-bound launches of a few KB each).  blk0[i] = first block of reduction i.
+constexpr int RM_MAX = 12;
+struct ReduceJob { const float* part; float* out; long long ldo; int nz, M, N, accumulate; };
+struct ReduceList { ReduceJob job[RM_MAX]; int blk0[RM_MAX + 1]; int n; };
+__global__ void __launch_bounds__(256) reduce_multi_kernel(const ReduceList R) {
+  int i = 0;
+  while (i + 1 < R.n && (int)blockIdx.x >= R.blk0[i + 1]) ++i;
+  const ReduceJob J = R.job[i];
+  const long long idx = (long long)(blockIdx.x - R.blk0[i]) * 256 + threadIdx.x;
+  if (idx >= (long long)J.M * J.N) return;
+  float s = 0.f;
+  for (int z = 0; z < J.nz; ++z) s += J.part[(long long)z * J.M * J.N + idx];
+  const int m = (int)(idx / J.N), n = (int)(idx - (long long)m * J.N);
+  J.out[m * J.ldo + n] = J.accumulate ? J.out[m * J.ldo + n] + s : s;
+}
+
 // column sums: part[z][n] = sum over the rows of slice z of g[r ld + n]
 // (optionally weighted by weight[r])
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ g, long long ld, int rows, int n, int rows_per,
@@ -358,17 +375,44 @@ static int wgrad_splits(int rows, int N, int K) {
   return s < 1 ? 1 : s;
 }
 static size_t wgrad_part_floats(int rows, int N, int K) { return (size_t)wgrad_splits(rows, N, K) * N * K; }
+
+// Deferred split reductions: while a queue is open (ReduceQueue on the caller's stack) dense_wgrad / dense_colsum take their partial
+// buffers from a bump allocator over the queue's region and append the reduction instead of launching it; flush() launches them all.
+struct ReduceQueue {
+  ReduceList list; float* base; size_t cap, used; cudaStream_t st;
+  ReduceQueue(float* b, size_t c, cudaStream_t s) : base(b), cap(c), used(0), st(s) { list.n = 0; list.blk0[0] = 0; }
+  float* take(size_t n) { n = (n + 63) & ~(size_t)63; if (used + n > cap || list.n >= RM_MAX) return nullptr; float* p = base + used; used += n; return p; }
+  void push(const float* part, int nz, int M, int N, float* out, long long ldo, int accumulate) {
+    ReduceJob& J = list.job[list.n];
+    J.part = part; J.out = out; J.ldo = ldo; J.nz = nz; J.M = M; J.N = N; J.accumulate = accumulate;
+    list.blk0[list.n + 1] = list.blk0[list.n] + (int)(((long long)M * N + 255) / 256);
+    ++list.n;
+  }
+  int flush() {
+    if (list.n == 0) return GJ_OK;
+    reduce_multi_kernel<<<(unsigned)list.blk0[list.n], 256, 0, st>>>(list);
+    list.n = 0; used = 0;
+    DN_CHECK("dense reduce launch");
+    return GJ_OK;
+  }
+};
 // dW (N x K, row stride lddw; columns >= xk come out as zero) = g^T (rows x N) . x (rows x K, `xk` live columns)
 static int dense_wgrad(int rows, int N, int K, const float* g, long long ldg, const float* x, long long ldx, int xk, float* dW, long long lddw, float* part,
-                       int precision, cudaStream_t st, int accumulate = 0) {
+                       int precision, cudaStream_t st, int accumulate = 0, ReduceQueue* q = nullptr) {
   const int ns = wgrad_splits(rows, N, K);
   int chunk = (rows + ns - 1) / ns; chunk = (chunk + 63) & ~63;
   const int nz = (rows + chunk - 1) / chunk;
+  if (q) {      // deferred: private partial buffer, reduction queued
+    float* mine = q->take((size_t)(nz > 1 ? nz : 2) * N * K);
+    if (!mine) { if (int rc = q->flush()) return rc; mine = q->take((size_t)(nz > 1 ? nz : 2) * N * K); }
+    if (mine) part = mine; else q = nullptr;      // a reduction larger than the whole region: immediate mode on the shared buffer
+  }
   GemmP P = gemm_base(N, K, rows);
   P.A = g; P.sAm = 1; P.sAk = ldg; P.Am = N; P.Ak = rows;
   P.B = x; P.sBn = 1; P.sBk = ldx; P.Bn = xk; P.Bk = rows;
   P.C = part; P.ldc = K; P.kchunk = chunk; P.part_stride = (long long)N * K;
   if (int rc = launch_gemm(P, precision, nz > 1 ? nz : 2, st)) return rc;      // (nz == 1 still goes through the partial buffer)
+  if (q) { q->push(part, nz > 1 ? nz : 2, N, K, dW, lddw, accumulate); return GJ_OK; }
   const long long n = (long long)N * K;
   reduce_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(part, nz > 1 ? nz : 2, N, K, dW, lddw, accumulate);
   DN_CHECK("dense wgrad reduce launch");
@@ -376,10 +420,16 @@ static int dense_wgrad(int rows, int N, int K, const float* g, long long ldg, co
 }
 // db[n] = sum_r g[r][n]
 static int dense_colsum(int rows, int N, const float* g, long long ldg, float* db, float* part, cudaStream_t st, int accumulate = 0,
-                        const float* weight = nullptr) {
+                        const float* weight = nullptr, ReduceQueue* q = nullptr) {
   int slices = (rows + 1023) / 1024; if (slices > 256) slices = 256; if (slices < 1) slices = 1;
   const int per = (rows + slices - 1) / slices;
+  if (q) {
+    float* mine = q->take((size_t)slices * N);
+    if (!mine) { if (int rc = q->flush()) return rc; mine = q->take((size_t)slices * N); }
+    if (mine) part = mine; else q = nullptr;
+  }
   colsum_kernel<<<dim3((N + 31) / 32, slices), 256, 0, st>>>(g, ldg, rows, N, per, weight, part);
+  if (q) { q->push(part, slices, 1, N, db, N, accumulate); DN_CHECK("dense colsum launch"); return GJ_OK; }
   reduce_split_kernel<<<(N + 255) / 256, 256, 0, st>>>(part, slices, 1, N, db, N, accumulate);
   DN_CHECK("dense colsum launch");
   return GJ_OK;
@@ -388,7 +438,7 @@ static int dense_colsum(int rows, int N, const float* g, long long ldg, float* d
 // ---- the node-level pieces of one message-passing step -------------------------------------------------------------
 // workspace (floats): forward: activations y_0 .. y_{Ln-2}; backward: y_0 .. y_{Ln-1}, two gradient buffers, partials
 static size_t ws_align(size_t n) { return (n + 63) & ~(size_t)63; }
-struct DenseWs { size_t y[GJ_MAX_LAYERS], g0, g1, part, total; };
+struct DenseWs { size_t y[GJ_MAX_LAYERS], g0, g1, part, part_floats, total; };
 static DenseWs dense_plan(const MPLayout& L, bool backward) {
   DenseWs w; size_t off = 0;
   const size_t rows = (size_t)L.B * L.N;
@@ -398,11 +448,15 @@ static DenseWs dense_plan(const MPLayout& L, bool backward) {
   if (backward) {
     w.g0 = off; off += ws_align(rows * wmax);
     w.g1 = off; off += ws_align(rows * wmax);
+    // partial buffers of every weight-gradient / bias reduction of ONE call (gj_dense_post_bwd or gj_dense_pre_bwd): the reductions
+    // are queued and run as one launch at the end of the call, so the buffers must not overlap
     size_t p = 0;
-    for (int m = 0; m < L.Ln; ++m) { const size_t q = wgrad_part_floats((int)rows, L.O[m], L.I[m]) + 2 * (size_t)L.O[m] * L.I[m]; if (q > p) p = q; }
-    const size_t q = wgrad_part_floats((int)rows, L.E[0], L.H) + 2 * (size_t)L.E[0] * L.H;
+    for (int m = 0; m < L.Ln; ++m)
+      p += ws_align(wgrad_part_floats((int)rows, L.O[m], L.I[m]) + 2 * (size_t)L.O[m] * L.I[m]) * (m == 0 ? 2 : 1) + ws_align(256 * (size_t)L.O[m]);
+    const size_t q = 2 * ws_align(wgrad_part_floats((int)rows, L.E[0], L.H) + 2 * (size_t)L.E[0] * L.H) + ws_align(256 * (size_t)L.E[0]);
     if (q > p) p = q;
-    if (p < 256 * 1024) p = 256 * 1024;      // column-sum partials
+    if (p < 256 * 1024) p = 256 * 1024;
+    w.part_floats = p;
     w.part = off; off += ws_align(p);
   }
   w.total = off;
@@ -460,6 +514,7 @@ int gj_dense_post_bwd(const MPLayout& L, const float* e, const float* h, const f
   float* g = ws + w.g0;
   float* gn = ws + w.g1;
   float* part = ws + w.part;
+  ReduceQueue rq(part, w.part_floats, st);
   {
     const size_t n = (size_t)rows * L.O[L.Ln - 1];
     mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dh_out, yb + w.y[L.Ln - 1], n, L.alpha, g);
@@ -468,19 +523,19 @@ int gj_dense_post_bwd(const MPLayout& L, const float* e, const float* h, const f
   for (int m = L.Ln - 1; m >= 0; --m) {
     const int O = L.O[m], I = L.I[m];
     const float* V = params + L.pV[m];
-    if (int rc = dense_colsum(rows, O, g, O, dparams + L.pc[m], part, st)) return rc;
+    if (int rc = dense_colsum(rows, O, g, O, dparams + L.pc[m], part, st, 0, nullptr, &rq)) return rc;
     if (m > 0) {
-      if (int rc = dense_wgrad(rows, O, I, g, O, yb + w.y[m - 1], I, I, dparams + L.pV[m], I, part, precision, st)) return rc;
+      if (int rc = dense_wgrad(rows, O, I, g, O, yb + w.y[m - 1], I, I, dparams + L.pV[m], I, part, precision, st, 0, &rq)) return rc;
       if (int rc = dense_dgrad(rows, O, I, g, O, V, I, 2, L.alpha, yb + w.y[m - 1], I, 0, gn, I, I, precision, st)) return rc;
       float* t = g; g = gn; gn = t;
     } else {
-      if (int rc = dense_wgrad(rows, O, L.EL, g, O, e, L.EL, L.EL, dparams + L.pV[0], I, part, precision, st)) return rc;
-      if (int rc = dense_wgrad(rows, O, L.H, g, O, h, L.ld, L.cols, dparams + L.pV[0] + L.EL, I, part, precision, st)) return rc;
+      if (int rc = dense_wgrad(rows, O, L.EL, g, O, e, L.EL, L.EL, dparams + L.pV[0], I, part, precision, st, 0, &rq)) return rc;
+      if (int rc = dense_wgrad(rows, O, L.H, g, O, h, L.ld, L.cols, dparams + L.pV[0] + L.EL, I, part, precision, st, 0, &rq)) return rc;
       if (int rc = dense_dgrad(rows, O, L.EL, g, O, V, I, 0, 0.f, nullptr, 0, 0, de, L.EL, L.EL, precision, st)) return rc;
       if (int rc = dense_dgrad(rows, O, L.H, g, O, V + L.EL, I, 0, 0.f, nullptr, 0, 0, dh, L.ld, L.cols, precision, st)) return rc;
     }
   }
-  return GJ_OK;
+  return rq.flush();
 }
 
 // adjoint of the projections: dh += dP Wa + dQ Wb; dW0[:, 0:H] = dP^T h, dW0[:, H:2H] = dQ^T h, db0 = sum dP
@@ -492,17 +547,21 @@ int gj_dense_pre_bwd(const MPLayout& L, const float* h, const float* params, con
   float* part = ws + w.part;
   if (int rc = dense_dgrad(rows, E0, L.H, dpq, ldp, W0, L.K[0], 0, 0.f, nullptr, 0, 1, dh, L.ld, L.cols, precision, st)) return rc;
   if (int rc = dense_dgrad(rows, E0, L.H, dpq + L.E0p, ldp, W0 + L.H, L.K[0], 0, 0.f, nullptr, 0, 1, dh, L.ld, L.cols, precision, st)) return rc;
-  if (int rc = dense_wgrad(rows, E0, L.H, dpq, ldp, h, L.ld, L.cols, dparams + L.pW[0], L.K[0], part, precision, st)) return rc;
-  if (int rc = dense_wgrad(rows, E0, L.H, dpq + L.E0p, ldp, h, L.ld, L.cols, dparams + L.pW[0] + L.H, L.K[0], part, precision, st)) return rc;
-  return dense_colsum(rows, E0, dpq, ldp, dparams + L.pb[0], part, st);
+  ReduceQueue rq(part, w.part_floats, st);
+  if (int rc = dense_wgrad(rows, E0, L.H, dpq, ldp, h, L.ld, L.cols, dparams + L.pW[0], L.K[0], part, precision, st, 0, &rq)) return rc;
+  if (int rc = dense_wgrad(rows, E0, L.H, dpq + L.E0p, ldp, h, L.ld, L.cols, dparams + L.pW[0] + L.H, L.K[0], part, precision, st, 0, &rq)) return rc;
+  if (int rc = dense_colsum(rows, E0, dpq, ldp, dparams + L.pb[0], part, st, 0, nullptr, &rq)) return rc;
+  return rq.flush();
 }
 
 // number of kernels the four entry points launch (gj_mp_step_launches)
 int gj_dense_launches(const MPLayout& L, bool backward) {
   const int fwd_chain = L.Ln + 1;
   if (!backward) return 2 + fwd_chain;
-  // chain again, mask, per layer: colsum (2) + wgrad (2 per product) + dgrad; projections: 2 dgrad + 2 wgrad (2 each) + colsum (2)
-  return fwd_chain + 1 + L.Ln * (2 + 2 + 1) + 2 + 2 + (2 + 4 + 2);
+  // node MLP adjoint: chain again, mask, per layer a column sum, one weight-gradient and one input-gradient GEMM per product (two
+  // products in layer 0: [e | h]), ONE launch for all queued reductions; P|Q again (2); projections' adjoint: 2 dgrad + 2 wgrad +
+  // column sum + one reduction launch
+  return fwd_chain + 1 + (L.Ln + 2 * (L.Ln - 1) + 4) + 1 + 2 + 6;
 }
 
 // test hook (declared in the header): C = epi(A B^T-like product) through the same kernels
