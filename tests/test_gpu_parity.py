@@ -65,6 +65,7 @@ def test_umma_selftest(m, n, k, a_mn, b_mn):
 @pytest.mark.parametrize("form,M,N,K", [
     (0, 300, 128, 256), (0, 129, 512, 3), (0, 1000, 20, 257), (0, 64, 256, 512),
     (1, 300, 256, 128), (1, 130, 3, 64), (1, 500, 513, 256),
+    (0, 40000, 256, 256), (0, 38017, 72, 200), (1, 40000, 256, 256), (1, 38017, 130, 96),      # several hundred row tiles
     (2, 128, 256, 1000), (2, 256, 513, 700), (2, 20, 64, 129), (2, 3, 8, 5000),
 ])
 def test_dense_gemm(form, M, N, K, precision):
