@@ -25,8 +25,11 @@
 //   B2  acc[0,128) = dz2 W2 (SS);   dW2 += a1^T dz2;  db2 += dz2^T 1        epi: dz1 = acc leaky'(a1) -> TMEM [0,64) +
 //                                                                                shared X1 (in place over a1)
 //   B1  acc[64,96) = dz1 W1 (TS);   [dW1 | db1] += dz1^T [a0 | 1] (SS, completes behind the epilogue)
-//                                                            epi: dz0 = acc leaky'(a0) in fp32 -> dP_i (lane reduce),
-//                                                                 dQ_j, d(wd), G_ij = dz0 . wd
+//                                                            epi: dz0 = acc leaky'(a0) in fp32 -> dQ_j, d(wd), G_ij = dz0 . wd in
+//                                                                 registers; dP_i = sum_j dz0 through TMEM [64,96) re-read as
+//                                                                 matrix fragments (tmem_ld_frag16)
+// Order inside the tile loop: ... B1 epilogue of tile t -> staging refill -> wait for wgrad1 of tile t (it reads A0) -> L0 and F1
+// issue of tile t + 1 -> prefetch of de_i / d_ij (strong loads, see prefetch()) -> F1 wait.
 // The first layer is factorised (W0 [h_i | h_j | d] = Wa h_i + Wb h_j + wd d, graphnet.py:220): P, Q come from
 // node_pre_fwd, d from pair_dist_fwd, and dP, dQ, G go back to node_pre_bwd / pair_dist_bwd.
 //
