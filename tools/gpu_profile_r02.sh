@@ -13,7 +13,7 @@ ncu --set full --clock-control none --import-source on -k regex:edge_fwd2 -s 2 -
 echo "fwd2 capture rc=$?"
 python tools/trace_bwd2.py > gpurun_out/r02_bwd2_trace.txt 2>&1
 python tools/step_profile.py 30 4096 bf16 > gpurun_out/r02_step_profile.txt 2>&1
-python tools/sweep_bench.py 30 2048 > gpurun_out/r02_sweep.txt 2>&1; cat gpurun_out/r02_sweep.txt
+[ "$1" = quick ] || { python tools/sweep_bench.py 30 2048 > gpurun_out/r02_sweep.txt 2>&1; cat gpurun_out/r02_sweep.txt; }
 python - > gpurun_out/r02_deterministic.txt 2>&1 <<'PY'
 import torch, sys, os
 sys.path.insert(0, os.getcwd())
