@@ -206,7 +206,8 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_fwd2_kernel(const Fwd2Args 
   // state of the tile being PREPARED (first layer), one tile ahead of the tile in the tensor-core stages
   int k = g0 / N, i = g0 - k * N;
   bool fresh = true;
-  uint32_t q[E0 / 2];      // Q_j as bf16 pairs
+  float q[E0];             // Q_j rounded to bf16 (the backward kernel recomputes the first layer from the same rounded values), kept
+                           // as fp32: the forward kernel has the registers, and unpacking pairs cost two instructions per pair and tile
   bool p_active = false, p_valid = false;
   uint32_t p_vmask = 0u;      // lanes (j) of the warp's j block that are real particles
   size_t node0 = 0;
@@ -259,13 +260,14 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_fwd2_kernel(const Fwd2Args 
 #pragma unroll
         for (int c = 0; c < E0 / 4; ++c) {
           const float4 v = __ldg(src + c);
-          q[2 * c] = bf2_as_u32(__floats2bfloat162_rn(v.x, v.y)); q[2 * c + 1] = bf2_as_u32(__floats2bfloat162_rn(v.z, v.w));
+          q[4 * c] = __bfloat162float(__float2bfloat16_rn(v.x)); q[4 * c + 1] = __bfloat162float(__float2bfloat16_rn(v.y));
+          q[4 * c + 2] = __bfloat162float(__float2bfloat16_rn(v.z)); q[4 * c + 3] = __bfloat162float(__float2bfloat16_rn(v.w));
         }
         const float* hsrc = A.h + (node0 + j) * A.ld;
         for (int kk = 0; kk < A.cols; ++kk) s_hj[lane * Hs + kk] = __ldg(hsrc + kk);
       } else {
 #pragma unroll
-        for (int c = 0; c < E0 / 2; ++c) q[c] = 0u;
+        for (int c = 0; c < E0; ++c) q[c] = 0.f;
         for (int kk = 0; kk < A.cols; ++kk) s_hj[lane * Hs + kk] = 0.f;
       }
       if ((i / F2_IC + 1) * F2_IC < N) cp_async_wait<1>(); else cp_async_wait<0>();
@@ -306,8 +308,8 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_fwd2_kernel(const Fwd2Args 
           const int cc = c + 4 * hh;
           const float4 p = *reinterpret_cast<const float4*>(Pi + cc);
           const float4 w = *reinterpret_cast<const float4*>(s_wd + cc);
-          const float2 z0 = fma2(make_float2(w.x, w.y), d2, add2(make_float2(p.x, p.y), unpack_bf2(q[cc / 2])));
-          const float2 z1 = fma2(make_float2(w.z, w.w), d2, add2(make_float2(p.z, p.w), unpack_bf2(q[cc / 2 + 1])));
+          const float2 z0 = fma2(make_float2(w.x, w.y), d2, add2(make_float2(p.x, p.y), make_float2(q[cc], q[cc + 1])));
+          const float2 z1 = fma2(make_float2(w.z, w.w), d2, add2(make_float2(p.z, p.w), make_float2(q[cc + 2], q[cc + 3])));
           o[2 * hh] = leaky_pack(z0.x, z0.y, alpha2);
           o[2 * hh + 1] = leaky_pack(z1.x, z1.y, alpha2);
         }
@@ -396,9 +398,9 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_fwd2_kernel(const Fwd2Args 
       for (int k = 0; k < 2; ++k) {
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          const float z0 = __uint_as_float(fa[4 * k + c]) * m0, z1 = __uint_as_float(fa[4 * k + 2 + c]) * m1;
-          const float z2 = __uint_as_float(fb[4 * k + c]) * m2, z3 = __uint_as_float(fb[4 * k + 2 + c]) * m3;
-          s[2 * k + c] = (fmaxf(z0, alpha * z0) + fmaxf(z1, alpha * z1)) + (fmaxf(z2, alpha * z2) + fmaxf(z3, alpha * z3));
+          const float z0 = __uint_as_float(fa[4 * k + c]), z1 = __uint_as_float(fa[4 * k + 2 + c]);
+          const float z2 = __uint_as_float(fb[4 * k + c]), z3 = __uint_as_float(fb[4 * k + 2 + c]);
+          s[2 * k + c] = fmaf(fmaxf(z0, alpha * z0), m0, fmaxf(z1, alpha * z1) * m1) + fmaf(fmaxf(z2, alpha * z2), m2, fmaxf(z3, alpha * z3) * m3);
         }
       }
 #pragma unroll
