@@ -17,6 +17,8 @@ void gj_set_error(const char* fmt, ...) {
 
 static bool node_post_tc_enabled() { static const bool v = !(getenv("GJ_NODE_POST_SIMT") && atoi(getenv("GJ_NODE_POST_SIMT")) != 0); return v && !(getenv("GJ_NODE_SIMT") && atoi(getenv("GJ_NODE_SIMT")) != 0); }
 static bool node_tc_disabled() { static const bool v = getenv("GJ_NODE_SIMT") && atoi(getenv("GJ_NODE_SIMT")) != 0; return v; }
+// programmatic dependent launch of the step's kernel chain (gj_common.cuh): GJ_PDL forces a mode, unset = the default policy
+int gj_pdl_mode() { static const int v = getenv("GJ_PDL") ? atoi(getenv("GJ_PDL")) : -1; return v; }
 bool gj_tc_v1_forced() { static const bool v = getenv("GJ_TC_V1") && atoi(getenv("GJ_TC_V1")) != 0; return v; }
 
 // bitwise-reproducible parameter gradients in the bf16 mode (gj_set_deterministic): read by the backward edge launchers

@@ -9,6 +9,7 @@ namespace {
 
 __global__ void chamfer_kernel(int np_, int nq, int dim, int mink, int mink_jet, float wc, float wj, const float* __restrict__ p,
                                const float* __restrict__ q, float* __restrict__ jet_terms, float* __restrict__ dp) {
+  gj_pdl_sync();
   extern __shared__ float sm[];
   float* sp = sm;                       // [np][4]
   float* sq = sp + np_ * 4;             // [nq][4]
@@ -85,6 +86,7 @@ __global__ void chamfer_kernel(int np_, int nq, int dim, int mink, int mink_jet,
 // terms[t] = sum_b jet_terms[b][t], single block, fixed tree => deterministic
 __global__ void chamfer_reduce_kernel(int batch, float wc, float wj, const float* __restrict__ jet_terms,
                                       float* __restrict__ terms) {
+  gj_pdl_sync();
   __shared__ float red[2][32];
   float a0 = 0.f, a1 = 0.f;
   for (int b = threadIdx.x; b < batch; b += blockDim.x) { a0 += jet_terms[b * 2]; a1 += jet_terms[b * 2 + 1]; }
@@ -103,6 +105,7 @@ __global__ void chamfer_reduce_kernel(int batch, float wc, float wj, const float
 // min_pq[b][i] = min_j dist(p_i, q_j), min_qp[b][j] = min_i dist(p_i, q_j).  No (B,N,N,D) difference tensor is built.
 __global__ void pair_min_dist_kernel(int np_, int nq, int dim, int lorentz, const float* __restrict__ p, const float* __restrict__ q,
                                      float* __restrict__ min_pq, float* __restrict__ min_qp) {
+  gj_pdl_sync();
   extern __shared__ float sm[];
   float* sp = sm;                       // [np][4]
   float* sq = sp + np_ * 4;             // [nq][4]
@@ -144,6 +147,7 @@ __global__ void pair_min_dist_kernel(int np_, int nq, int dim, int lorentz, cons
 // col_for_row[b][i] = column assigned to row i (linear_sum_assignment's second array for a square matrix).
 __global__ void assignment_kernel(int n, int dim, int lorentz, const float* __restrict__ p, const float* __restrict__ q,
                                   int* __restrict__ col_for_row, float* __restrict__ total_cost) {
+  gj_pdl_sync();
   extern __shared__ float4 asg_smem[];
   float* sp = reinterpret_cast<float*>(asg_smem);             // [n][4]
   float* sq = sp + n * 4;                                     // [n][4]
@@ -249,7 +253,7 @@ int gj_assignment_launch(int batch, int n, int dim, int lorentz, const float* p,
   cudaError_t ce = cudaSuccess;
   if (smem > 48 * 1024) ce = cudaFuncSetAttribute(assignment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (ce == cudaSuccess) {
-    assignment_kernel<<<batch, gj_round_up(n, 32), smem, stream>>>(n, dim, lorentz, p, q, col_for_row, total_cost);
+    gj_launch(assignment_kernel, batch, gj_round_up(n, 32), smem, stream, n, dim, lorentz, p, q, col_for_row, total_cost);
     ce = cudaGetLastError();
   }
   if (ce != cudaSuccess) { gj_set_error("assignment launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
@@ -268,7 +272,7 @@ int gj_pair_min_dist_launch(int batch, int np_, int nq, int dim, int lorentz, co
   cudaError_t ce = cudaSuccess;
   if (smem > 48 * 1024) ce = cudaFuncSetAttribute(pair_min_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (ce == cudaSuccess) {
-    pair_min_dist_kernel<<<batch, threads, smem, stream>>>(np_, nq, dim, lorentz, p, q, min_pq, min_qp);
+    gj_launch(pair_min_dist_kernel, batch, threads, smem, stream, np_, nq, dim, lorentz, p, q, min_pq, min_qp);
     ce = cudaGetLastError();
   }
   if (ce != cudaSuccess) { gj_set_error("pair_min_dist launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
@@ -287,8 +291,8 @@ int gj_chamfer_launch(int batch, int np_, int nq, int dim, int norm, float wc, f
   int threads = gj_round_up(nmax, 32);
   if (threads < 32) threads = 32;
   size_t smem = (size_t)(np_ + nq) * 4 * sizeof(float) + (size_t)(np_ + nq) * sizeof(int) + (64 + 8) * sizeof(float);
-  chamfer_kernel<<<batch, threads, smem, stream>>>(np_, nq, dim, mink, mink_jet, wc, wj, p, q, jet_terms, dp);
-  chamfer_reduce_kernel<<<1, 1024, 0, stream>>>(batch, wc, wj, jet_terms, terms);
+  gj_launch(chamfer_kernel, batch, threads, smem, stream, np_, nq, dim, mink, mink_jet, wc, wj, p, q, jet_terms, dp);
+  gj_launch(chamfer_reduce_kernel, 1, 1024, 0, stream, batch, wc, wj, jet_terms, terms);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) { gj_set_error("chamfer launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   return GJ_OK;

@@ -142,6 +142,7 @@ __device__ long long g_b2_trace[24 * 128];
 
 template <int E0, int E1, int E2, int E3, int NWG, bool TRACE>
 __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args A, const __grid_constant__ CUtensorMap tm_w) {
+  gj_pdl_wait();      // programmatic dependent launch: everything the preceding kernels wrote (de, dP|dQ = 0, ...) is visible from here
   static_assert(E0 == 32 && E1 == 128 && E2 == 64 && E3 == 16, "TMEM / stage map is laid out for the 32-128-64-16 edge network");
   static_assert(NWG <= 3, "three 128-column slots + 128 gradient columns");
   using S = Bwd2Smem<E0, E1, E2, E3, NWG>;
@@ -695,6 +696,7 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args 
       }
       ++tr_n;
     }
+    gj_pdl_trigger();     // the next kernel of the stream may be launched while the other groups finish and the gradients are read out
     if (!fresh) flush_dq();      // the group's last (jet, j block) ended mid-way: the next group adds the rest
     if (g0 < g1) { mbar_wait(done2, ph2); ph2 ^= 1u; }      // all of this group's MMAs have completed
     cp_async_wait<0>();
@@ -766,6 +768,7 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_bwd2_kernel(const Bwd2Args 
 // dP_i = sum over the j blocks' partial dP (N > 32): one 16-byte column group per thread, the njb loads are independent
 __global__ void __launch_bounds__(256) sum_dp_parts_kernel(const float4* __restrict__ part, int njb, size_t rows, int E0,
                                                            float* __restrict__ dpq) {
+  gj_pdl_sync();
   const size_t n4 = rows * (size_t)(E0 / 4), idx = (size_t)blockIdx.x * 256 + threadIdx.x;
   if (idx >= n4) return;
   float4 s = __ldg(part + idx);
@@ -785,6 +788,7 @@ __global__ void __launch_bounds__(256) sum_dp_parts_kernel(const float4* __restr
 __device__ __forceinline__ int pd_stride(int cols) { return 4 * ((((cols + 3) >> 2)) | 1); }
 __global__ void __launch_bounds__(256) pair_dist_fwd_kernel(const float* __restrict__ h, int B, int N, int NJ32, int cols, int ld,
                                                             int mink, int JPB, float* __restrict__ d) {
+  gj_pdl_sync();
   extern __shared__ float4 pd_smem4[];
   float* pd_smem = reinterpret_cast<float*>(pd_smem4);
   const int hs = pd_stride(cols), c4 = (cols + 3) >> 2;
@@ -846,6 +850,7 @@ __global__ void __launch_bounds__(256) pair_dist_fwd_kernel(const float* __restr
 template <int C4>
 __global__ void __launch_bounds__(640) pair_dist_bwd_kernel(const float* __restrict__ h, const float* __restrict__ G, int B, int N,
                                                             int NJ32, int cols, int ld, int mink, int JPB, float* __restrict__ dh) {
+  gj_pdl_sync();
   extern __shared__ float4 pd_smem4[];
   float* pd_smem = reinterpret_cast<float*>(pd_smem4);
   const int hs = pd_stride(cols), c4 = (cols + 3) >> 2, gs = N | 1, ld4 = ld >> 2, nj4 = NJ32 >> 2;
@@ -975,7 +980,7 @@ int gj_pair_dist_fwd(const MPLayout& L, const float* h, float* d, cudaStream_t s
   int blocks = (L.B + jpb - 1) / jpb; if (blocks > 8 * gj_num_sms()) blocks = 8 * gj_num_sms();
   cudaError_t ce = cudaFuncSetAttribute(pair_dist_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (ce != cudaSuccess) { gj_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
-  pair_dist_fwd_kernel<<<blocks, 256, smem, stream>>>(h, L.B, L.N, NJ32, L.cols, L.ld, L.mink, jpb, d);
+  gj_launch(pair_dist_fwd_kernel, blocks, 256, smem, stream, h, L.B, L.N, NJ32, L.cols, L.ld, L.mink, jpb, d);
   ce = cudaGetLastError();
   if (ce != cudaSuccess) { gj_set_error("pair_dist_fwd launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   return GJ_OK;
@@ -997,7 +1002,7 @@ int gj_pair_dist_bwd(const MPLayout& L, const float* h, const float* G, float* d
   auto pdk = C4 == 1 ? pair_dist_bwd_kernel<1> : C4 == 2 ? pair_dist_bwd_kernel<2> : C4 == 4 ? pair_dist_bwd_kernel<4> : pair_dist_bwd_kernel<8>;
   cudaError_t ce = cudaFuncSetAttribute(pdk, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (ce != cudaSuccess) { gj_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
-  pdk<<<blocks, threads, smem, stream>>>(h, G, L.B, L.N, NJ32, L.cols, L.ld, L.mink, jpb, dh);
+  gj_launch(pdk, blocks, threads, smem, stream, h, G, L.B, L.N, NJ32, L.cols, L.ld, L.mink, jpb, dh);
   ce = cudaGetLastError();
   if (ce != cudaSuccess) { gj_set_error("pair_dist_bwd launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   return GJ_OK;
@@ -1046,7 +1051,7 @@ int gj_edge_bwd2(const MPLayout& L, const float* h, const float* pq, const float
   if (!kernel_only) {
     if (!have_saved) {
       WImageSrc P{L.pW[1], L.pb[1], L.pW[2], L.pb[2], L.pW[3], L.pb[3]};
-      pack_edge_weights_kernel<32, 128, 64, 16><<<4, 256, 0, stream>>>(params, P, wimg);
+      gj_launch(pack_edge_weights_kernel<32, 128, 64, 16>, 4, 256, 0, stream, params, P, wimg);
       int rc = gj_pair_dist_fwd(L, h, d, stream);
       if (rc) return rc;
     }
@@ -1061,13 +1066,13 @@ int gj_edge_bwd2(const MPLayout& L, const float* h, const float* pq, const float
   CUtensorMap tm_w;      // the parameter image as rows of 1 KB
   static_assert(WImage<32, 128, 64, 16>::bytes % 1024 == 0 && WImage<32, 128, 64, 16>::bytes / 1024 <= 256, "one TMA box");
   if (int rc = gj_tmap_2d(&tm_w, wimg, 256, WImage<32, 128, 64, 16>::bytes / 1024, 1024, 256, WImage<32, 128, 64, 16>::bytes / 1024)) return rc;
-  kern<<<grid, NWG * 128, smem_total, stream>>>(A, tm_w);
+  gj_launch_edge(kern, grid, NWG * 128, smem_total, stream, A, tm_w);
   ce = cudaGetLastError();
   if (ce != cudaSuccess) { gj_set_error("edge_bwd2 launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   if (kernel_only) return GJ_OK;
   if (njb > 1) {
     const size_t n4 = rows * (size_t)(L.E[0] / 4);
-    sum_dp_parts_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(dp_part), (int)njb, rows, L.E[0], dpq);
+    gj_launch(sum_dp_parts_kernel, (unsigned)((n4 + 255) / 256), 256, 0, stream, reinterpret_cast<const float4*>(dp_part), (int)njb, rows, L.E[0], dpq);
   }
   if (int rc = gj_pair_dist_bwd(L, h, G, dh, stream)) return rc;
   ce = cudaGetLastError();

@@ -135,6 +135,7 @@ __device__ long long g_f2_trace[8 * 256];
 
 template <int E0, int E1, int E2, int E3, int NWG, bool TRACE>
 __global__ void __launch_bounds__(NWG * 128, 1) edge_fwd2_kernel(const Fwd2Args A, const __grid_constant__ CUtensorMap tm_w) {
+  gj_pdl_wait();      // programmatic dependent launch: the preceding kernels' results (P|Q, parameter image) are visible from here
   static_assert(E0 == 32 && E3 == 16, "tile map assumes a 32-wide first and a 16-wide last edge layer");
   static_assert(E1 % 32 == 0 && E1 <= 128 && E2 % 32 == 0 && E1 / 2 + E2 <= 128 && E2 / 2 + E3 <= E1 / 2, "TMEM slot map");
   static_assert(NWG * 128 <= 512, "one 128-column TMEM slot per tile group");
@@ -416,6 +417,7 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_fwd2_kernel(const Fwd2Args 
     ph ^= 1u;
   }
 
+  gj_pdl_trigger();      // the next kernel of the stream may be launched while the remaining groups finish
   cp_async_wait<0>();
   tc_fence_before();
   __syncthreads();
@@ -425,6 +427,7 @@ __global__ void __launch_bounds__(NWG * 128, 1) edge_fwd2_kernel(const Fwd2Args 
 // sums the NJB per-j-block partial aggregates in a fixed order
 // e_i = sum over the j blocks' partial aggregates (N > 32): one 16-byte group per thread (n is a multiple of 4: E_last = 16)
 __global__ void __launch_bounds__(256) sum_jblocks_kernel(const float4* __restrict__ part, int njb, size_t n4, float4* __restrict__ out) {
+  gj_pdl_sync();
   const size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x;
   if (idx >= n4) return;
   float4 s = __ldg(part + idx);
@@ -473,7 +476,7 @@ int gj_edge_fwd2(const MPLayout& L, const float* h, const float* pq, const float
   A.d_out = d_save;
   if (!kernel_only) {
     WImageSrc P{L.pW[1], L.pb[1], L.pW[2], L.pb[2], L.pW[3], L.pb[3]};
-    pack_edge_weights_kernel<32, 128, 64, 16><<<4, 256, 0, stream>>>(params, P, reinterpret_cast<uint8_t*>(wimg));
+    gj_launch(pack_edge_weights_kernel<32, 128, 64, 16>, 4, 256, 0, stream, params, P, reinterpret_cast<uint8_t*>(wimg));
   }
   A.h = h; A.pq = pq; A.params = params;
   A.B = L.B; A.N = L.N; A.NJB = (L.N + 31) / 32; A.NJ32 = A.NJB * 32; A.cols = L.cols; A.ld = L.ld; A.mink = L.mink;
@@ -499,14 +502,14 @@ int gj_edge_fwd2(const MPLayout& L, const float* h, const float* pq, const float
   CUtensorMap tm_w;      // the parameter image as rows of 1 KB
   static_assert(WImage<32, 128, 64, 16>::bytes % 1024 == 0 && WImage<32, 128, 64, 16>::bytes / 1024 <= 256, "one TMA box");
   if (int rc = gj_tmap_2d(&tm_w, wimg, 256, WImage<32, 128, 64, 16>::bytes / 1024, 1024, 256, WImage<32, 128, 64, 16>::bytes / 1024)) return rc;
-  kern<<<grid, NWG * 128, smem, stream>>>(A, tm_w);
+  gj_launch_edge(kern, grid, NWG * 128, smem, stream, A, tm_w);
   ce = cudaGetLastError();
   if (ce != cudaSuccess) { gj_set_error("edge_fwd2 launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   if (kernel_only) return GJ_OK;
   if (A.NJB > 1) {
     const size_t n4 = (size_t)L.B * L.N * (L.E[3] / 4);
-    sum_jblocks_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(ws), A.NJB, n4,
-                                                                          reinterpret_cast<float4*>(e_out));
+    gj_launch(sum_jblocks_kernel, (unsigned)((n4 + 255) / 256), 256, 0, stream, reinterpret_cast<const float4*>(ws), A.NJB, n4,
+              reinterpret_cast<float4*>(e_out));
     ce = cudaGetLastError();
     if (ce != cudaSuccess) { gj_set_error("sum_jblocks launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   }

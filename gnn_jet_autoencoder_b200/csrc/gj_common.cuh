@@ -92,6 +92,55 @@ static inline int gj_fill_arch(const gj_mp_desc* d, MPLayout* L, const char** wh
 }
 
 #ifdef __CUDACC__
+// ---- programmatic dependent launch (PDL) ----
+// A kernel launched with the programmatic-stream-serialization attribute may be launched, and its CTAs made resident, while
+// the preceding kernel of the stream still runs.  Correctness rests on one rule: every kernel launched through gj_launch /
+// gj_launch_edge executes gj_pdl_wait() as its FIRST statement, before any global-memory access and before any early return
+// (the wait returns when every preceding grid has completed and its memory is visible, so dependencies stay transitive along
+// the chain).  gj_pdl_trigger() lets the dependent grid launch: short kernels call it right after the wait, the persistent
+// edge kernels after their tile loop.  Both instructions are no-ops in a kernel launched without the attribute.
+// Measured on a B200 (profiles/r02_pdl_ab.txt, config 2): on the persistent edge kernels the attribute hides their
+// prologue (barriers, TMEM allocation, the TMA of the parameter image) behind the predecessor's tail, 482.5 -> 479.5 us per
+// backward launch; on the 5-40 us node-level kernels it helps when the step is launched kernel by kernel (4.88 -> 4.81 ms)
+// and HURTS inside a CUDA graph, whose kernel-to-kernel hand-over is already tighter than a programmatic edge (4.72 -> 4.80
+// ms).  Default therefore: edge kernels always, the other kernels only when the stream is not being captured;
+// GJ_PDL = 0 / 1 / 2 / 3 forces none / small only / edge only / all.
+__device__ __forceinline__ void gj_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void gj_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void gj_pdl_sync() { gj_pdl_wait(); gj_pdl_trigger(); }
+
+int gj_pdl_mode();      // api.cu: environment GJ_PDL (bit 0: node-level / small kernels, bit 1: edge kernels), -1 = default policy
+
+// <<<grid, block, smem, stream>>> with the PDL attribute (kernel class `mask`: 1 small, 2 edge); the kernel MUST start with
+// gj_pdl_wait() / gj_pdl_sync()
+template <typename... KArgs, typename... Args>
+static inline cudaError_t gj_launch_masked(int mask, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                           Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  const int mode = gj_pdl_mode();
+  bool on;
+  if (mode >= 0) on = (mode & mask) != 0;
+  else if (mask & 2) on = true;
+  else {      // small kernels: not inside a graph capture (the legacy default stream cannot be captured)
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    on = stream == nullptr || (cudaStreamIsCapturing(stream, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone);
+  }
+  cfg.attrs = attr; cfg.numAttrs = on ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<Args&&>(args)...);
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t gj_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  return gj_launch_masked(1, kern, grid, block, smem, stream, static_cast<Args&&>(args)...);
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t gj_launch_edge(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  return gj_launch_masked(2, kern, grid, block, smem, stream, static_cast<Args&&>(args)...);
+}
+
 __device__ __forceinline__ float gj_leaky(float z, float a) { return z > 0.f ? z : a * z; }
 // LeakyReLU as FMUL + FMNMX: max(z, a z) for a <= 1, min(z, a z) for a > 1 (a >= 0 is validated on the host)
 __device__ __forceinline__ float gj_leaky2(float z, float a, bool a_le_1) { const float y = a * z; return a_le_1 ? fmaxf(z, y) : fminf(z, y); }

@@ -132,6 +132,7 @@ struct PreArgs {
 __global__ void __launch_bounds__(NK_THREADS) node_pre_fwd_kernel(const PreArgs A, const float* __restrict__ h,
                                                                    const float* __restrict__ w0, const float* __restrict__ b0,
                                                                    float* __restrict__ pq) {
+  gj_pdl_sync();
   extern __shared__ float4 nk_smem_raw[];
   float* sm = reinterpret_cast<float*>(nk_smem_raw);
   float* W = sm + A.o_w;     // [2*E0p][ws]: rows 0..E0p-1 = Wa, E0p.. = Wb, zero padded
@@ -172,6 +173,7 @@ __global__ void __launch_bounds__(NK_THREADS) node_pre_fwd_kernel(const PreArgs 
 __global__ void __launch_bounds__(NK_THREADS) node_pre_bwd_kernel(const PreArgs A, const float* __restrict__ h,
                                                                    const float* __restrict__ w0, const float* __restrict__ dpq,
                                                                    float* __restrict__ dh, float* __restrict__ part) {
+  gj_pdl_sync();
   extern __shared__ float4 nk_smem_raw[];
   float* sm = reinterpret_cast<float*>(nk_smem_raw);
   // Wt[k][c'] with c' over 2*E0p (dP | dQ channels): dh[r][k] = sum_c' dPQ[r][c'] Wt[k][c']
@@ -297,6 +299,7 @@ __device__ void post_load_rows(const PostArgs& A, const float* __restrict__ e, c
 __global__ void __launch_bounds__(NK_THREADS) node_post_fwd_kernel(const PostArgs A, const float* __restrict__ e,
                                                                     const float* __restrict__ h, const float* __restrict__ params,
                                                                     float* __restrict__ h_out) {
+  gj_pdl_sync();
   extern __shared__ float4 nk_smem_raw[];
   float* sm = reinterpret_cast<float*>(nk_smem_raw);
   post_stage_weights(A, params, sm, false);
@@ -325,6 +328,7 @@ __global__ void __launch_bounds__(NK_THREADS) node_post_bwd_kernel(const PostArg
                                                                     const float* __restrict__ h, const float* __restrict__ params,
                                                                     const float* __restrict__ dh_out, float* __restrict__ de,
                                                                     float* __restrict__ dh, float* __restrict__ part) {
+  gj_pdl_sync();
   extern __shared__ float4 nk_smem_raw[];
   float* sm = reinterpret_cast<float*>(nk_smem_raw);
   if (!A.wide) post_stage_weights(A, params, sm, true);
@@ -431,6 +435,7 @@ template <int KP>
 __global__ void __launch_bounds__(NF_THREADS) node_pre_fwd_fast_kernel(int rows, int H, int cols, int ld, int K0, const float* __restrict__ h,
                                                                        const float* __restrict__ w0, const float* __restrict__ b0,
                                                                        float* __restrict__ pq) {
+  gj_pdl_sync();
   constexpr int XS = KP + 4, OS = 36;
   __shared__ __align__(16) float W[64 * KP];
   __shared__ float bias[64];
@@ -480,6 +485,7 @@ __global__ void __launch_bounds__(NF_THREADS) node_post_fwd_fast_kernel(int rows
                                                                         const float* __restrict__ V0, const float* __restrict__ c0,
                                                                         const float* __restrict__ V1, const float* __restrict__ c1,
                                                                         float* __restrict__ h_out) {
+  gj_pdl_sync();
   constexpr int XS = 4 * ((I0P / 4) | 1), OS = 4 * ((O1P / 4) | 1);
   __shared__ __align__(16) float sV0[O0P * I0P];
   __shared__ __align__(16) float sV1[O1P * O0P];
@@ -587,6 +593,7 @@ __global__ void __launch_bounds__(NF_THREADS) node_post_bwd_fast_kernel(int rows
                                                                         const float* __restrict__ c0, const float* __restrict__ V1,
                                                                         const float* __restrict__ c1, const float* __restrict__ dh_out,
                                                                         float* __restrict__ de, float* __restrict__ dh, float* __restrict__ part) {
+  gj_pdl_sync();
   constexpr int XS = 4 * ((I0P / 4) | 1), YS = 4 * ((O0P / 4) | 1), G1S = 4 * ((O1P / 4) | 1);
   constexpr int U0 = (O0P * (I0P / 4) + NF_THREADS - 1) / NF_THREADS, U1 = (O1P * (O0P / 4) + NF_THREADS - 1) / NF_THREADS;
   extern __shared__ float4 nk_smem_raw[];
@@ -723,6 +730,7 @@ __device__ __forceinline__ float reduce_column(const float* __restrict__ part, i
 }
 
 __global__ void reduce_partials_kernel(const float* __restrict__ part, int nparts, int n, float* __restrict__ out) {
+  gj_pdl_sync();
   const int p = blockIdx.x * 32 + threadIdx.x;
   const float v = reduce_column(part, nparts, n, p);
   if (threadIdx.y == 0 && p < n) out[p] = v;
@@ -731,6 +739,7 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, int npart
 // dW0 scatter: the node_pre partials are [Wa E0*H][Wb E0*H][b0 E0]; the packed layout is W0 (E0, 2H+1) then b0.
 __global__ void reduce_pre_partials_kernel(const float* __restrict__ part, int nparts, int E0, int H, float* __restrict__ dW0,
                                            float* __restrict__ db0) {
+  gj_pdl_sync();
   const int n = E0 * 2 * H + E0;
   const int p = blockIdx.x * 32 + threadIdx.x;
   const float acc = reduce_column(part, nparts, n, p);
@@ -748,6 +757,7 @@ __global__ void reduce_step_partials_kernel(const float* __restrict__ partE, int
                                             int npP, int nbP, const float* __restrict__ partN, int npN, int nN, int E0, int H,
                                             float* __restrict__ dedge, float* __restrict__ dW0, float* __restrict__ db0,
                                             float* __restrict__ dnode) {
+  gj_pdl_sync();
   const int K0 = 2 * H + 1;
   if ((int)blockIdx.x < nbE) {
     const int p = blockIdx.x * 32 + threadIdx.x;
@@ -901,17 +911,17 @@ int gj_node_pre_fwd(const MPLayout& L, const float* h, const float* params, floa
     const float* w0 = params + L.pW[0];
     const float* b0 = params + L.pb[0];
     const int grid = nf_grid(rows);
-    if (kp == 4) node_pre_fwd_fast_kernel<4><<<grid, NF_THREADS, 0, st>>>(rows, L.H, L.cols, L.ld, L.K[0], h, w0, b0, pq);
-    else if (kp == 8) node_pre_fwd_fast_kernel<8><<<grid, NF_THREADS, 0, st>>>(rows, L.H, L.cols, L.ld, L.K[0], h, w0, b0, pq);
-    else if (kp == 16) node_pre_fwd_fast_kernel<16><<<grid, NF_THREADS, 0, st>>>(rows, L.H, L.cols, L.ld, L.K[0], h, w0, b0, pq);
-    else node_pre_fwd_fast_kernel<32><<<grid, NF_THREADS, 0, st>>>(rows, L.H, L.cols, L.ld, L.K[0], h, w0, b0, pq);
+    if (kp == 4) gj_launch(node_pre_fwd_fast_kernel<4>, grid, NF_THREADS, 0, st, rows, L.H, L.cols, L.ld, L.K[0], h, w0, b0, pq);
+    else if (kp == 8) gj_launch(node_pre_fwd_fast_kernel<8>, grid, NF_THREADS, 0, st, rows, L.H, L.cols, L.ld, L.K[0], h, w0, b0, pq);
+    else if (kp == 16) gj_launch(node_pre_fwd_fast_kernel<16>, grid, NF_THREADS, 0, st, rows, L.H, L.cols, L.ld, L.K[0], h, w0, b0, pq);
+    else gj_launch(node_pre_fwd_fast_kernel<32>, grid, NF_THREADS, 0, st, rows, L.H, L.cols, L.ld, L.K[0], h, w0, b0, pq);
     NK_CHECK_LAUNCH("node_pre_fwd launch");
     return GJ_OK;
   }
   PreArgs A; int bytes = pre_plan(L, &A, false);
   if (bytes < 0) { gj_set_error("node_pre_fwd: widths do not fit shared memory"); return GJ_ERR_SMEM; }
   if (int rc = nk_set_smem(node_pre_fwd_kernel, bytes)) return rc;
-  node_pre_fwd_kernel<<<nk_grid(A.rows, A.R, bytes), NK_THREADS, bytes, st>>>(A, h, params + L.pW[0], params + L.pb[0], pq);
+  gj_launch(node_pre_fwd_kernel, nk_grid(A.rows, A.R, bytes), NK_THREADS, bytes, st, A, h, params + L.pW[0], params + L.pb[0], pq);
   NK_CHECK_LAUNCH("node_pre_fwd launch");
   return GJ_OK;
 }
@@ -930,7 +940,7 @@ static int nf_bwd_grid(int rows) {      // the per-CTA partials are reduced afte
 // fixed-order reduction of per-CTA [dWa | dWb | db0] partials into the packed W0 / b0 gradients
 int gj_reduce_pre_partials(const MPLayout& L, const float* part, int nparts, float* dparams, cudaStream_t st) {
   const int n = L.E[0] * 2 * L.H + L.E[0];
-  reduce_pre_partials_kernel<<<(n + 31) / 32, dim3(32, RED_SLICES), 0, st>>>(part, nparts, L.E[0], L.H, dparams + L.pW[0], dparams + L.pb[0]);
+  gj_launch(reduce_pre_partials_kernel, (n + 31) / 32, dim3(32, RED_SLICES), 0, st, part, nparts, L.E[0], L.H, dparams + L.pW[0], dparams + L.pb[0]);
   NK_CHECK_LAUNCH("reduce_pre_partials launch");
   return GJ_OK;
 }
@@ -939,7 +949,7 @@ int gj_reduce_step_partials(const MPLayout& L, const float* partE, int npE, cons
                             float* dparams, cudaStream_t st) {
   const int nE = L.pV[0], nP = L.E[0] * 2 * L.H + L.E[0], nN = L.nparams - L.pV[0];
   const int nbE = (nE + 31) / 32, nbP = (nP + 31) / 32, nbN = (nN + 31) / 32;
-  reduce_step_partials_kernel<<<nbE + nbP + nbN, dim3(32, RED_SLICES), 0, st>>>(partE, npE, nE, nbE, partP, npP, nbP, partN, npN, nN, L.E[0],
+  gj_launch(reduce_step_partials_kernel, nbE + nbP + nbN, dim3(32, RED_SLICES), 0, st, partE, npE, nE, nbE, partP, npP, nbP, partN, npN, nN, L.E[0],
                                                                               L.H, dparams, dparams + L.pW[0], dparams + L.pb[0],
                                                                               dparams + L.pV[0]);
   NK_CHECK_LAUNCH("reduce_step_partials launch");
@@ -952,9 +962,9 @@ int gj_node_pre_bwd(const MPLayout& L, const float* h, const float* params, cons
   if (bytes < 0) { gj_set_error("node_pre_bwd: widths do not fit shared memory"); return GJ_ERR_SMEM; }
   if (int rc = nk_set_smem(node_pre_bwd_kernel, bytes)) return rc;
   const int grid = nk_grid(A.rows, A.R, bytes);
-  node_pre_bwd_kernel<<<grid, NK_THREADS, bytes, st>>>(A, h, params + L.pW[0], dpq, dh, part);
+  gj_launch(node_pre_bwd_kernel, grid, NK_THREADS, bytes, st, A, h, params + L.pW[0], dpq, dh, part);
   const int n = L.E[0] * 2 * L.H + L.E[0];
-  reduce_pre_partials_kernel<<<(n + 31) / 32, dim3(32, RED_SLICES), 0, st>>>(part, grid, L.E[0], L.H, dparams + L.pW[0], dparams + L.pb[0]);
+  gj_launch(reduce_pre_partials_kernel, (n + 31) / 32, dim3(32, RED_SLICES), 0, st, part, grid, L.E[0], L.H, dparams + L.pW[0], dparams + L.pb[0]);
   NK_CHECK_LAUNCH("node_pre_bwd launch");
   return GJ_OK;
 }
@@ -962,7 +972,7 @@ int gj_node_pre_bwd(const MPLayout& L, const float* h, const float* params, cons
 template <int I0P, int O0P, int O1P>
 static void nf_post_launch(const MPLayout& L, const float* e, const float* h, const float* params, float* h_out, cudaStream_t st) {
   const int rows = L.B * L.N;
-  node_post_fwd_fast_kernel<I0P, O0P, O1P><<<nf_grid(rows), NF_THREADS, 0, st>>>(
+  gj_launch(node_post_fwd_fast_kernel<I0P, O0P, O1P>, nf_grid(rows), NF_THREADS, 0, st,
       rows, L.EL, L.cols, L.ld, L.I[0], L.O[0], L.O[1], L.alpha, e, h, params + L.pV[0], params + L.pc[0], params + L.pV[1], params + L.pc[1], h_out);
 }
 
@@ -980,7 +990,7 @@ int gj_node_post_fwd(const MPLayout& L, const float* e, const float* h, const fl
   PostArgs A; int bytes = post_plan(L, &A, false);
   if (bytes < 0) { gj_set_error("node_post_fwd: widths do not fit shared memory"); return GJ_ERR_SMEM; }
   if (int rc = nk_set_smem(node_post_fwd_kernel, bytes)) return rc;
-  node_post_fwd_kernel<<<nk_grid(A.rows, A.R, bytes), NK_THREADS, bytes, st>>>(A, e, h, params, h_out);
+  gj_launch(node_post_fwd_kernel, nk_grid(A.rows, A.R, bytes), NK_THREADS, bytes, st, A, e, h, params, h_out);
   NK_CHECK_LAUNCH("node_post_fwd launch");
   return GJ_OK;
 }
@@ -1013,7 +1023,7 @@ static int nf_post_bwd_launch(const MPLayout& L, const float* e, const float* h,
   constexpr int XS = 4 * ((I0P / 4) | 1), YS = 4 * ((O0P / 4) | 1), G1S = 4 * ((O1P / 4) | 1);
   const int bytes = (2 * O0P * I0P + 2 * O1P * O0P + O0P + O1P + NF_THREADS * (XS + 2 * YS + G1S)) * 4;
   if (int rc = nk_set_smem(node_post_bwd_fast_kernel<I0P, O0P, O1P>, bytes)) return rc;
-  node_post_bwd_fast_kernel<I0P, O0P, O1P><<<grid, NF_THREADS, bytes, st>>>(
+  gj_launch(node_post_bwd_fast_kernel<I0P, O0P, O1P>, grid, NF_THREADS, bytes, st,
       L.B * L.N, L.EL, L.cols, L.ld, L.I[0], L.O[0], L.O[1], L.alpha, L.nparams - L.pV[0], e, h, params + L.pV[0], params + L.pc[0],
       params + L.pV[1], params + L.pc[1], dh_out, de, dh, part);
   return GJ_OK;
@@ -1029,7 +1039,7 @@ int gj_node_post_bwd(const MPLayout& L, const float* e, const float* h, const fl
            : shape == 2 ? nf_post_bwd_launch<24, 8, 20>(L, e, h, params, dh_out, de, dh, part, grid, st)
                         : nf_post_bwd_launch<24, 8, 4>(L, e, h, params, dh_out, de, dh, part, grid, st);
     if (rc) return rc;
-    reduce_partials_kernel<<<(n + 31) / 32, dim3(32, RED_SLICES), 0, st>>>(part, grid, n, dparams + L.pV[0]);
+    gj_launch(reduce_partials_kernel, (n + 31) / 32, dim3(32, RED_SLICES), 0, st, part, grid, n, dparams + L.pV[0]);
     NK_CHECK_LAUNCH("node_post_bwd launch");
     return GJ_OK;
   }
@@ -1037,15 +1047,15 @@ int gj_node_post_bwd(const MPLayout& L, const float* e, const float* h, const fl
   if (bytes < 0) { gj_set_error("node_post_bwd: widths do not fit shared memory"); return GJ_ERR_SMEM; }
   if (int rc = nk_set_smem(node_post_bwd_kernel, bytes)) return rc;
   const int grid = nk_grid(A.rows, A.R, bytes);
-  node_post_bwd_kernel<<<grid, NK_THREADS, bytes, st>>>(A, e, h, params, dh_out, de, dh, part);
-  reduce_partials_kernel<<<(A.n_node_params + 31) / 32, dim3(32, RED_SLICES), 0, st>>>(part, grid, A.n_node_params, dparams + A.p_first);
+  gj_launch(node_post_bwd_kernel, grid, NK_THREADS, bytes, st, A, e, h, params, dh_out, de, dh, part);
+  gj_launch(reduce_partials_kernel, (A.n_node_params + 31) / 32, dim3(32, RED_SLICES), 0, st, part, grid, A.n_node_params, dparams + A.p_first);
   NK_CHECK_LAUNCH("node_post_bwd launch");
   return GJ_OK;
 }
 
 int gj_reduce_partials(const float* part, int nparts, int n, float* out, cudaStream_t st) {
   if (n <= 0) return GJ_OK;
-  reduce_partials_kernel<<<(n + 31) / 32, dim3(32, RED_SLICES), 0, st>>>(part, nparts, n, out);
+  gj_launch(reduce_partials_kernel, (n + 31) / 32, dim3(32, RED_SLICES), 0, st, part, nparts, n, out);
   NK_CHECK_LAUNCH("reduce_partials launch");
   return GJ_OK;
 }

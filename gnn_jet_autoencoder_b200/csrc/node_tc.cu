@@ -57,6 +57,7 @@ template <int HP>
 __global__ void __launch_bounds__(128) node_pre_bwd_tc_kernel(int rows, int H, int cols, int ld, int K0, const float* __restrict__ h,
                                                               const float* __restrict__ w0, const float* __restrict__ dpq,
                                                               float* __restrict__ dh, float* __restrict__ part) {
+  gj_pdl_sync();
   using S = PreBwdSmem<HP>;
   constexpr int TS = S::TS;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -299,6 +300,7 @@ __global__ void __launch_bounds__(128) node_post_bwd_tc_kernel(int rows, int col
                                                                const float* __restrict__ c1, const float* __restrict__ dh_out,
                                                                float* __restrict__ de, float* __restrict__ dh, float* __restrict__ part,
                                                                float* __restrict__ zero64) {
+  gj_pdl_sync();
   using S = PostBwdSmem<I0P, O0P, O1P>;
   constexpr int HS = S::XS - 2;      // h slabs of the X tile (the first two hold e)
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -608,11 +610,11 @@ int gj_node_pre_bwd_tc(const MPLayout& L, const float* h, const float* params, c
   if (L.cols <= 16) {
     using S = PreBwdSmem<16>;
     ce = cudaFuncSetAttribute(node_pre_bwd_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::total);
-    if (ce == cudaSuccess) node_pre_bwd_tc_kernel<16><<<grid, 128, S::total, st>>>(rows, L.H, L.cols, L.ld, L.K[0], h, params + L.pW[0], dpq, dh, part);
+    if (ce == cudaSuccess) gj_launch(node_pre_bwd_tc_kernel<16>, grid, 128, S::total, st, rows, L.H, L.cols, L.ld, L.K[0], h, params + L.pW[0], dpq, dh, part);
   } else {
     using S = PreBwdSmem<32>;
     ce = cudaFuncSetAttribute(node_pre_bwd_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::total);
-    if (ce == cudaSuccess) node_pre_bwd_tc_kernel<32><<<grid, 128, S::total, st>>>(rows, L.H, L.cols, L.ld, L.K[0], h, params + L.pW[0], dpq, dh, part);
+    if (ce == cudaSuccess) gj_launch(node_pre_bwd_tc_kernel<32>, grid, 128, S::total, st, rows, L.H, L.cols, L.ld, L.K[0], h, params + L.pW[0], dpq, dh, part);
   }
   if (ce == cudaSuccess) ce = cudaGetLastError();
   if (ce != cudaSuccess) { gj_set_error("node_pre_bwd_tc launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
@@ -644,9 +646,8 @@ static cudaError_t post_bwd_tc_launch(const MPLayout& L, int grid, const float* 
   using S = PostBwdSmem<I0P, O0P, O1P>;
   cudaError_t ce = cudaFuncSetAttribute(node_post_bwd_tc_kernel<I0P, O0P, O1P>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::total);
   if (ce != cudaSuccess) return ce;
-  node_post_bwd_tc_kernel<I0P, O0P, O1P><<<grid, 128, S::total, st>>>(L.B * L.N, L.cols, L.ld, L.I[0], L.O[0], L.O[1], L.alpha,
-                                                                      L.nparams - L.pV[0], e, h, params + L.pV[0], params + L.pc[0],
-                                                                      params + L.pV[1], params + L.pc[1], dh_out, de, dh, part, zero64);
+  gj_launch(node_post_bwd_tc_kernel<I0P, O0P, O1P>, grid, 128, S::total, st, L.B * L.N, L.cols, L.ld, L.I[0], L.O[0], L.O[1], L.alpha,
+            L.nparams - L.pV[0], e, h, params + L.pV[0], params + L.pc[0], params + L.pV[1], params + L.pc[1], dh_out, de, dh, part, zero64);
   return cudaGetLastError();
 }
 

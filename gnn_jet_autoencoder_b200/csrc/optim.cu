@@ -9,6 +9,7 @@ namespace {
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, size_t n, float lr_over_bc1, float inv_sqrt_bc2, float b1, float b2,
                             float eps, float gscale, float l1, float l2) {
+  gj_pdl_sync();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
@@ -29,6 +30,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 __global__ void optimizer_kernel(int kind, float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf,
                                  float* __restrict__ acc, size_t n, float lr, float alpha, float momentum, float eps, float gscale,
                                  float l1, float l2) {
+  gj_pdl_sync();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) {
@@ -57,6 +59,7 @@ __global__ void optimizer_kernel(int kind, float* __restrict__ p, const float* _
 }
 
 __global__ void norms_stage1(const float* __restrict__ p, size_t n, float* __restrict__ part) {
+  gj_pdl_sync();
   __shared__ float red[2][8];
   float a = 0.f, s = 0.f;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -73,6 +76,7 @@ __global__ void norms_stage1(const float* __restrict__ p, size_t n, float* __res
 }
 
 __global__ void norms_stage2(const float* __restrict__ part, int nblk, float* __restrict__ out) {
+  gj_pdl_sync();
   if (threadIdx.x == 0) {
     float t0 = 0.f, t1 = 0.f;
     for (int b = 0; b < nblk; ++b) { t0 += part[b * 2]; t1 += part[b * 2 + 1]; }
@@ -81,6 +85,7 @@ __global__ void norms_stage2(const float* __restrict__ part, int nblk, float* __
 }
 
 __global__ void latent_mean_fwd_kernel(int N, int W, const float* __restrict__ y, float* __restrict__ z, int total) {
+  gj_pdl_sync();
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   int b = idx / W, c = idx - b * W;
@@ -91,6 +96,7 @@ __global__ void latent_mean_fwd_kernel(int N, int W, const float* __restrict__ y
 }
 
 __global__ void latent_mean_bwd_kernel(int N, int W, const float* __restrict__ dz, float* __restrict__ dy, size_t total) {
+  gj_pdl_sync();
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   size_t b = idx / ((size_t)N * W);
@@ -101,6 +107,7 @@ __global__ void latent_mean_bwd_kernel(int N, int W, const float* __restrict__ d
 // 'max' / 'min' latent maps (encoder.py:150-155, torch.amax / torch.amin over the particle axis).  The adjoint follows
 // torch: the gradient of an extremum is shared evenly by the entries that attain it.
 __global__ void latent_extreme_fwd_kernel(int N, int W, int is_min, const float* __restrict__ y, float* __restrict__ z, int total) {
+  gj_pdl_sync();
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   int b = idx / W, c = idx - b * W;
@@ -111,6 +118,7 @@ __global__ void latent_extreme_fwd_kernel(int N, int W, int is_min, const float*
 }
 __global__ void latent_extreme_bwd_kernel(int N, int W, const float* __restrict__ y, const float* __restrict__ z,
                                           const float* __restrict__ dz, float* __restrict__ dy, int total) {
+  gj_pdl_sync();
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   int b = idx / W, c = idx - b * W;
@@ -127,6 +135,7 @@ __global__ void latent_extreme_bwd_kernel(int N, int W, const float* __restrict_
 // (decoder.py:123-124), lower clamp at eps of the components in clamp_mask (train.py:55-65, polar coordinates).
 __global__ void out_transform_fwd_kernel(size_t n, int dim, int use_tanh, int clamp_mask, float eps, const float* __restrict__ x,
                                          float* __restrict__ y) {
+  gj_pdl_sync();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     float v = x[i];
     if (use_tanh) v = tanhf(v);
@@ -137,6 +146,7 @@ __global__ void out_transform_fwd_kernel(size_t n, int dim, int use_tanh, int cl
 // dx = dy * [tanh(x) >= eps on clamped components] * (1 - tanh(x)^2)
 __global__ void out_transform_bwd_kernel(size_t n, int dim, int use_tanh, int clamp_mask, float eps, const float* __restrict__ x,
                                          const float* __restrict__ dy, float* __restrict__ dx) {
+  gj_pdl_sync();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     float v = x[i], g = dy[i];
     if (use_tanh) v = tanhf(v);
@@ -149,6 +159,7 @@ __global__ void out_transform_bwd_kernel(size_t n, int dim, int use_tanh, int cl
 // nn.MSELoss (train.py:359-361): value = sum (p - q)^2 / denom, dp = 2 (p - q) / denom; per-block partial sums, fixed order
 __global__ void __launch_bounds__(256) mse_stage1(size_t n, float inv_denom, const float* __restrict__ p, const float* __restrict__ q,
                                                   float* __restrict__ dp, float* __restrict__ part) {
+  gj_pdl_sync();
   float acc = 0.f;
   for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
     const float d = p[i] - q[i];
@@ -162,6 +173,7 @@ __global__ void __launch_bounds__(256) mse_stage1(size_t n, float inv_denom, con
   if (threadIdx.x == 0) { float t = 0.f; for (int w = 0; w < 8; ++w) t += red[w]; part[blockIdx.x] = t; }
 }
 __global__ void mse_stage2(const float* __restrict__ part, int nblk, float inv_denom, float* __restrict__ terms) {
+  gj_pdl_sync();
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int b = 0; b < nblk; ++b) t += part[b];
@@ -177,7 +189,7 @@ static const int kNormBlocks = 64;
 int gj_latent_extreme_fwd_launch(int B, int N, int W, int is_min, const float* y, float* z, cudaStream_t stream) {
   const int total = B * W;
   if (total == 0) return GJ_OK;
-  latent_extreme_fwd_kernel<<<(total + 255) / 256, 256, 0, stream>>>(N, W, is_min, y, z, total);
+  gj_launch(latent_extreme_fwd_kernel, (total + 255) / 256, 256, 0, stream, N, W, is_min, y, z, total);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) { gj_set_error("latent_extreme_fwd launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   return GJ_OK;
@@ -185,7 +197,7 @@ int gj_latent_extreme_fwd_launch(int B, int N, int W, int is_min, const float* y
 int gj_latent_extreme_bwd_launch(int B, int N, int W, const float* y, const float* z, const float* dz, float* dy, cudaStream_t stream) {
   const int total = B * W;
   if (total == 0) return GJ_OK;
-  latent_extreme_bwd_kernel<<<(total + 255) / 256, 256, 0, stream>>>(N, W, y, z, dz, dy, total);
+  gj_launch(latent_extreme_bwd_kernel, (total + 255) / 256, 256, 0, stream, N, W, y, z, dz, dy, total);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) { gj_set_error("latent_extreme_bwd launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   return GJ_OK;
@@ -194,8 +206,8 @@ int gj_out_transform_launch(size_t n, int dim, int use_tanh, int clamp_mask, flo
                             cudaStream_t stream) {
   if (n == 0) return GJ_OK;
   unsigned blocks = (unsigned)((n + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
-  if (dy) out_transform_bwd_kernel<<<blocks, 256, 0, stream>>>(n, dim, use_tanh, clamp_mask, eps, x, dy, out);
-  else out_transform_fwd_kernel<<<blocks, 256, 0, stream>>>(n, dim, use_tanh, clamp_mask, eps, x, out);
+  if (dy) gj_launch(out_transform_bwd_kernel, blocks, 256, 0, stream, n, dim, use_tanh, clamp_mask, eps, x, dy, out);
+  else gj_launch(out_transform_fwd_kernel, blocks, 256, 0, stream, n, dim, use_tanh, clamp_mask, eps, x, out);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) { gj_set_error("out_transform launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   return GJ_OK;
@@ -205,8 +217,8 @@ int gj_mse_launch(size_t n, double denom, const float* p, const float* q, float*
                   cudaStream_t stream) {
   if (ws_bytes < gj_mse_ws_bytes()) { gj_set_error("gj_mse_fwd_bwd: workspace too small"); return GJ_ERR_WORKSPACE; }
   const float inv = (float)(1.0 / denom);
-  mse_stage1<<<kNormBlocks, 256, 0, stream>>>(n, inv, p, q, dp, (float*)ws);
-  mse_stage2<<<1, 32, 0, stream>>>((const float*)ws, kNormBlocks, inv, terms);
+  gj_launch(mse_stage1, kNormBlocks, 256, 0, stream, n, inv, p, q, dp, (float*)ws);
+  gj_launch(mse_stage2, 1, 32, 0, stream, (const float*)ws, kNormBlocks, inv, terms);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) { gj_set_error("mse launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   return GJ_OK;
@@ -218,7 +230,7 @@ int gj_adam_launch(float* param, const float* grad, float* m, float* v, size_t n
   if (step < 1) { gj_set_error("gj_adam_step_flat: step must be >= 1"); return GJ_ERR_INVALID; }
   double bc1 = 1.0 - pow((double)b1, step), bc2 = 1.0 - pow((double)b2, step);
   int blocks = (int)((n + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
-  adam_kernel<<<blocks, 256, 0, stream>>>(param, grad, m, v, n, (float)(lr / bc1), (float)(1.0 / sqrt(bc2)), b1, b2, eps,
+  gj_launch(adam_kernel, blocks, 256, 0, stream, param, grad, m, v, n, (float)(lr / bc1), (float)(1.0 / sqrt(bc2)), b1, b2, eps,
                                           gscale, l1, l2);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) { gj_set_error("adam launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
@@ -229,7 +241,7 @@ int gj_optimizer_launch(int kind, float* param, const float* grad, float* buf, f
                         float eps, float gscale, float l1, float l2, cudaStream_t stream) {
   if (n == 0) return GJ_OK;
   int blocks = (int)((n + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
-  optimizer_kernel<<<blocks, 256, 0, stream>>>(kind, param, grad, buf, acc, n, lr, alpha, momentum, eps, gscale, l1, l2);
+  gj_launch(optimizer_kernel, blocks, 256, 0, stream, kind, param, grad, buf, acc, n, lr, alpha, momentum, eps, gscale, l1, l2);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) { gj_set_error("optimizer launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   return GJ_OK;
@@ -239,8 +251,8 @@ size_t gj_norms_ws_bytes(size_t) { return kNormBlocks * 2 * sizeof(float); }
 
 int gj_norms_launch(const float* p, size_t n, float* out, void* ws, size_t ws_bytes, cudaStream_t stream) {
   if (ws_bytes < gj_norms_ws_bytes(n)) { gj_set_error("gj_param_norms: workspace too small"); return GJ_ERR_WORKSPACE; }
-  norms_stage1<<<kNormBlocks, 256, 0, stream>>>(p, n, (float*)ws);
-  norms_stage2<<<1, 32, 0, stream>>>((const float*)ws, kNormBlocks, out);
+  gj_launch(norms_stage1, kNormBlocks, 256, 0, stream, p, n, (float*)ws);
+  gj_launch(norms_stage2, 1, 32, 0, stream, (const float*)ws, kNormBlocks, out);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) { gj_set_error("norms launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   return GJ_OK;
@@ -249,7 +261,7 @@ int gj_norms_launch(const float* p, size_t n, float* out, void* ws, size_t ws_by
 int gj_latent_mean_fwd_launch(int B, int N, int W, const float* y, float* z, cudaStream_t stream) {
   int total = B * W;
   if (total == 0) return GJ_OK;
-  latent_mean_fwd_kernel<<<(total + 255) / 256, 256, 0, stream>>>(N, W, y, z, total);
+  gj_launch(latent_mean_fwd_kernel, (total + 255) / 256, 256, 0, stream, N, W, y, z, total);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) { gj_set_error("latent_mean_fwd launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   return GJ_OK;
@@ -258,7 +270,7 @@ int gj_latent_mean_fwd_launch(int B, int N, int W, const float* y, float* z, cud
 int gj_latent_mean_bwd_launch(int B, int N, int W, const float* dz, float* dy, cudaStream_t stream) {
   size_t total = (size_t)B * N * W;
   if (total == 0) return GJ_OK;
-  latent_mean_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(N, W, dz, dy, total);
+  gj_launch(latent_mean_bwd_kernel, (unsigned)((total + 255) / 256), 256, 0, stream, N, W, dz, dy, total);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) { gj_set_error("latent_mean_bwd launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   return GJ_OK;
@@ -277,6 +289,7 @@ constexpr int kLinKT = 32;           // in-features a weight-gradient thread acc
 // walks the outputs 256 at a time; a thread reads its weight row once for all the CTA's rows.
 __global__ void __launch_bounds__(256) linear_fwd_kernel(int rows, int K, int O, const float* __restrict__ x, const float* __restrict__ w,
                                                          const float* __restrict__ b, float* __restrict__ y) {
+  gj_pdl_sync();
   extern __shared__ float lin_smem[];      // [kLinRB][K]
   const int r0 = blockIdx.x * kLinRB, nr = min(kLinRB, rows - r0);
   for (int idx = threadIdx.x; idx < nr * K; idx += 256) lin_smem[idx] = __ldg(x + (size_t)r0 * K + idx);
@@ -301,6 +314,7 @@ __global__ void __launch_bounds__(256) linear_fwd_kernel(int rows, int K, int O,
 // dx[r][k] = sum_o dy[r][o] w[o][k], generic form: one thread per (row, k)
 __global__ void linear_dx_kernel(int rows, int K, int O, const float* __restrict__ dy, const float* __restrict__ w,
                                  float* __restrict__ dx) {
+  gj_pdl_sync();
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)rows * K) return;
   int r = (int)(idx / K), k = (int)(idx - (size_t)r * K);
@@ -317,6 +331,7 @@ constexpr int kDxOC = 512;               // outputs per staged weight chunk (a l
 template <bool VEC>
 __global__ void __launch_bounds__(256) linear_dx_smallk_kernel(int rows, int K, int O, const float* __restrict__ dy,
                                                                const float* __restrict__ w, float* __restrict__ dx) {
+  gj_pdl_sync();
   extern __shared__ float4 lin_smem4[];      // [kDxOC][K]
   float* lin_smem = reinterpret_cast<float*>(lin_smem4);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -374,6 +389,7 @@ __global__ void __launch_bounds__(256) linear_dx_smallk_kernel(int rows, int K, 
 // multiple of 4 floats and read as 16-byte broadcasts.
 __global__ void __launch_bounds__(256) linear_dw_partial_kernel(int rows, int K, int O, int chunk, const float* __restrict__ x,
                                                                 const float* __restrict__ dy, float* __restrict__ part) {
+  gj_pdl_sync();
   extern __shared__ float4 lin_smem4[];      // [chunk][K1p]
   float* xs = reinterpret_cast<float*>(lin_smem4);
   const int K1 = K + 1, K1p = (K1 + 3) & ~3, r0 = blockIdx.y * chunk, nr = min(chunk, rows - r0);
@@ -414,6 +430,7 @@ __global__ void __launch_bounds__(256) linear_dw_partial_kernel(int rows, int K,
 // sums are combined in slice order
 __global__ void __launch_bounds__(256) linear_dw_reduce_kernel(int nchunks, int K, int O, const float* __restrict__ part,
                                                                float* __restrict__ dw, float* __restrict__ db) {
+  gj_pdl_sync();
   __shared__ float red[8][33];
   const int K1 = K + 1, total = K1 * O;
   const int idx = blockIdx.x * 32 + threadIdx.x;
@@ -447,7 +464,7 @@ int gj_linear_fwd_launch(int rows, int K, int O, const float* x, const float* w,
   if ((size_t)rows * O == 0) return GJ_OK;
   const size_t smem = (size_t)kLinRB * K * sizeof(float);
   if (int rc = lin_set_smem((const void*)linear_fwd_kernel, smem, "linear_fwd")) return rc;
-  linear_fwd_kernel<<<(rows + kLinRB - 1) / kLinRB, 256, smem, stream>>>(rows, K, O, x, w, b, y);
+  gj_launch(linear_fwd_kernel, (rows + kLinRB - 1) / kLinRB, 256, smem, stream, rows, K, O, x, w, b, y);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) { gj_set_error("linear_fwd launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   return GJ_OK;
@@ -469,18 +486,18 @@ int gj_linear_bwd_launch(int rows, int K, int O, const float* x, const float* w,
       if (K <= 32) {
         auto kern = (K & 3) == 0 ? linear_dx_smallk_kernel<true> : linear_dx_smallk_kernel<false>;
         if (int rc = lin_set_smem((const void*)kern, smem, "linear_bwd")) return rc;
-        kern<<<(rows + kDxRowsPerBlock - 1) / kDxRowsPerBlock, 256, smem, stream>>>(rows, K, O, dy, w, dx);
+        gj_launch(kern, (rows + kDxRowsPerBlock - 1) / kDxRowsPerBlock, 256, smem, stream, rows, K, O, dy, w, dx);
       } else {
-        linear_dx_kernel<<<(unsigned)(((size_t)rows * K + 255) / 256), 256, 0, stream>>>(rows, K, O, dy, w, dx);
+        gj_launch(linear_dx_kernel, (unsigned)(((size_t)rows * K + 255) / 256), 256, 0, stream, rows, K, O, dy, w, dx);
       }
     }
     const size_t smem = (size_t)chunk * ((K + 4) & ~3) * sizeof(float);
     if (int rc = lin_set_smem((const void*)linear_dw_partial_kernel, smem, "linear_bwd")) return rc;
     const int items = O * ((K + 1 + kLinKT - 1) / kLinKT);
     dim3 grid((items + 255) / 256, nch);
-    linear_dw_partial_kernel<<<grid, 256, smem, stream>>>(rows, K, O, chunk, x, dy, (float*)ws);
+    gj_launch(linear_dw_partial_kernel, grid, 256, smem, stream, rows, K, O, chunk, x, dy, (float*)ws);
   }
-  linear_dw_reduce_kernel<<<(total + 31) / 32, dim3(32, 8), 0, stream>>>(nch, K, O, (const float*)ws, dw, db);
+  gj_launch(linear_dw_reduce_kernel, (total + 31) / 32, dim3(32, 8), 0, stream, nch, K, O, (const float*)ws, dw, db);
   cudaError_t ce = cudaGetLastError();
   if (ce != cudaSuccess) { gj_set_error("linear_bwd launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
   return GJ_OK;

@@ -220,6 +220,7 @@ __device__ __forceinline__ void pack_weight_kmajor_unaligned(uint8_t* dst, const
 }
 template <int E0, int E1, int E2, int E3>
 __global__ void __launch_bounds__(256) pack_edge_weights_kernel(const float* __restrict__ params, WImageSrc P, uint8_t* __restrict__ img) {
+  gj_pdl_sync();
   using I = WImage<E0, E1, E2, E3>;
   const int tid = blockIdx.x * 256 + threadIdx.x, nthr = gridDim.x * 256;
   for (int idx = tid; idx < (I::o_w1 - (I::o_b3 + E3 * 16)) / 4; idx += nthr) reinterpret_cast<uint32_t*>(img + I::o_b3 + E3 * 16)[idx] = 0u;

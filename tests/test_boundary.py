@@ -177,6 +177,41 @@ def test_sass_uses_tcgen05_and_tmem():
     assert "UTCHMMA" in sass or "UTCMMA" in sass
     assert "LDTM" in sass
     assert "UTMALDG" in sass
+    assert "ACQBULK" in sass and "PREEXIT" in sass      # griddepcontrol.wait / launch_dependents (programmatic dependent launch)
+
+
+def test_every_pdl_launched_kernel_starts_with_the_grid_dependency_wait():
+    """gj_common.cuh's rule for programmatic dependent launch: a kernel launched through gj_launch / gj_launch_edge may start
+    while its predecessor still runs, so its body must begin with gj_pdl_wait() / gj_pdl_sync() -- before any global access
+    and before any early return.  Checked on the sources: every such kernel's first statement is the wait."""
+    import glob
+    import re
+    csrc = os.path.join(os.path.dirname(_lib.LIB_PATH), "csrc")
+    text = {p: open(p).read() for p in glob.glob(os.path.join(csrc, "*.cu")) + glob.glob(os.path.join(csrc, "*.cuh"))}
+    first_stmt = {}
+    pat = re.compile(r"__global__\s+void\s+(?:__launch_bounds__\([^)]*\)\s*)?(\w+)\s*\(")
+    for src in text.values():
+        for m in pat.finditer(src):
+            i, depth = m.end() - 1, 0
+            while True:
+                depth += {"(": 1, ")": -1}.get(src[i], 0)
+                if depth == 0:
+                    break
+                i += 1
+            body = src[src.index("{", i) + 1:]
+            first_stmt[m.group(1)] = body.lstrip().split(";")[0]
+    launched = set()
+    for src in text.values():
+        names = set(re.findall(r"gj_launch(?:_edge)?\(\s*([A-Za-z_]\w*)", src))
+        for m in re.finditer(r"auto\s+(\w+)\s*=([^;]*);", src):      # `auto kern = cond ? kernel_a<...> : kernel_b<...>;`
+            if m.group(1) in names:
+                names.update(re.findall(r"([A-Za-z_]\w*_kernel)\b", m.group(2)))
+        launched |= names
+    launched -= {"kern", "pdk", "mask", "void"}
+    assert len(launched) >= 20, launched
+    for k in sorted(launched):
+        assert k in first_stmt, f"{k}: launched with the PDL attribute but no __global__ definition found"
+        assert first_stmt[k].strip() in ("gj_pdl_wait()", "gj_pdl_sync()"), f"{k} starts with {first_stmt[k]!r}"
 
 
 def test_permutation_helpers_match_the_per_jet_loops():
