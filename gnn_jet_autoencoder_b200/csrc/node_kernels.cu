@@ -544,6 +544,216 @@ __global__ void __launch_bounds__(NF_THREADS) node_post_fwd_fast_kernel(int rows
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Warp-autonomous versions of the two forward kernels above (the ones the steps launch; GJ_NODE_FWD_V1=1 selects the CTA-tile
+// kernels).  The CTA-tile kernels run one serial chain per 128-row tile -- stage weights, stage the tile, compute, store, with
+// CTA-wide barriers in between -- on 592-960 CTAs, each of which re-stages the weights: 3-6x their HBM / FFMA floor.  Here a CTA
+// of 8 warps stages the weights ONCE and every warp then walks its own 32-row tiles with no CTA-wide synchronisation: the next
+// tile's rows are fetched (cp.async, 16-byte pieces where the layout allows) into the warp's staging rows as soon as every lane
+// holds its row in registers, so the fetch runs under the ~2000 FFMA / LDS of the current tile; outputs leave as 16-byte
+// coalesced stores (a tile's output rows are one contiguous block).  Tiles are dealt round-robin to CTAs first, then to the
+// warps of a CTA, so every SM gets the same number of tiles (+-1).  Per-row arithmetic is the code of the kernels above
+// (nf_dot4 in the same order): results are bitwise identical.
+// ---------------------------------------------------------------------------------------------------------
+#define NW_WARPS 8
+__device__ __forceinline__ void nf_cp_async16(float* dst, const float* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void nf_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void nf_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// rows [r0, r0 + nrows) x columns [0, cols) of a row-major matrix (row stride ld) -> dst[r][c0 + k] (row stride XS), lane-strided
+template <int XS>
+__device__ __forceinline__ void nw_stage_rows(float* dst, int c0, const float* __restrict__ src, int ld, int cols, size_t r0, int nrows,
+                                              bool vec, int lane) {
+  if (vec) {      // 16-byte pieces: cols, ld multiples of 4 and a 16-byte aligned base
+    const int c4 = cols >> 2;
+    for (int idx = lane; idx < nrows * c4; idx += 32) {
+      const int r = idx / c4, k = idx - r * c4;
+      nf_cp_async16(dst + r * XS + c0 + 4 * k, src + (r0 + r) * (size_t)ld + 4 * k);
+    }
+  } else {
+    for (int idx = lane; idx < nrows * cols; idx += 32) {
+      const int r = idx / cols, k = idx - r * cols;
+      nf_cp_async4(dst + r * XS + c0 + k, src + (r0 + r) * (size_t)ld + k);
+    }
+  }
+}
+// a warp's [nrows][O] output rows (shared memory, row stride OS) -> out[(r0 + r) * ostride + o0 ..], coalesced
+template <int OS>
+__device__ __forceinline__ void nw_store_rows(float* __restrict__ out, int ostride, int o0, int O, const float* sO, size_t r0, int nrows,
+                                              bool vec, int lane) {
+  if (vec) {
+    const int o4 = O >> 2;
+    for (int idx = lane; idx < nrows * o4; idx += 32) {
+      const int r = idx / o4, q = idx - r * o4;
+      *reinterpret_cast<float4*>(out + (r0 + r) * (size_t)ostride + o0 + 4 * q) = *reinterpret_cast<const float4*>(sO + r * OS + 4 * q);
+    }
+  } else {
+    for (int idx = lane; idx < nrows * O; idx += 32) {
+      const int r = idx / O, o = idx - r * O;
+      out[(r0 + r) * (size_t)ostride + o0 + o] = sO[r * OS + o];
+    }
+  }
+}
+__device__ __forceinline__ bool nw_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <int KP>
+struct NwPreSmem {
+  static constexpr int XS = KP + 4, OS = 36;
+  static constexpr int o_bias = 64 * KP, o_warp = o_bias + 64, warp_floats = 32 * XS + 32 * OS;
+  static constexpr int bytes = (o_warp + NW_WARPS * warp_floats) * 4;
+};
+
+// PQ[row][0..32) = Wa h + b0 ; PQ[row][32..64) = Wb h      (node_pre_fwd_fast_kernel, warp-autonomous)
+template <int KP>
+__global__ void __launch_bounds__(NW_WARPS * 32, 2) node_pre_fwd_warp_kernel(int rows, int H, int cols, int ld, int K0,
+                                                                            const float* __restrict__ h, const float* __restrict__ w0,
+                                                                            const float* __restrict__ b0, float* __restrict__ pq) {
+  gj_pdl_sync();
+  using S = NwPreSmem<KP>;
+  constexpr int XS = S::XS, OS = S::OS;
+  extern __shared__ __align__(16) float nw_smem[];
+  float* W = nw_smem;
+  float* bias = nw_smem + S::o_bias;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* sX = nw_smem + S::o_warp + warp * S::warp_floats;      // [32][XS]
+  float* sO = sX + 32 * XS;                                     // [32][OS]
+  for (int idx = threadIdx.x; idx < 64 * KP; idx += NW_WARPS * 32) {
+    const int o = idx / KP, k = idx - o * KP;
+    if (k < cols) nf_cp_async4(W + idx, w0 + (o & 31) * K0 + (o < 32 ? k : H + k));
+    else W[idx] = 0.f;
+  }
+  if (threadIdx.x < 64) bias[threadIdx.x] = threadIdx.x < 32 ? __ldg(b0 + threadIdx.x) : 0.f;
+  for (int idx = lane; idx < 32 * (KP - cols); idx += 32) {      // the padding columns of the staging rows stay zero
+    const int r = idx / (KP - cols), k = idx - r * (KP - cols);
+    sX[r * XS + cols + k] = 0.f;
+  }
+  const int T = (rows + 31) >> 5, G = gridDim.x;
+  const bool vin = (cols & 3) == 0 && (ld & 3) == 0 && nw_aligned16(h);
+  int t = blockIdx.x + G * warp;
+  if (t < T) nw_stage_rows<XS>(sX, 0, h, ld, cols, (size_t)t * 32, min(32, rows - t * 32), vin, lane);
+  nf_cp_async_commit();
+  nf_cp_async_wait_all();
+  __syncthreads();      // weights, biases (and this warp's first tile) have landed
+  while (t < T) {
+    const size_t r0 = (size_t)t * 32;
+    const int nrows = min(32, rows - t * 32);
+    float x[KP];
+#pragma unroll
+    for (int k = 0; k < KP; k += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(sX + lane * XS + k);
+      x[k] = v.x; x[k + 1] = v.y; x[k + 2] = v.z; x[k + 3] = v.w;
+    }
+    __syncwarp();
+    const int tn = t + G * NW_WARPS;      // every lane holds its row: fetch the next tile under this tile's arithmetic
+    if (tn < T) nw_stage_rows<XS>(sX, 0, h, ld, cols, (size_t)tn * 32, min(32, rows - tn * 32), vin, lane);
+    nf_cp_async_commit();
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {      // P then Q
+#pragma unroll
+      for (int o0 = 0; o0 < 32; o0 += 4)
+        *reinterpret_cast<float4*>(sO + lane * OS + o0) = nf_dot4<KP>(x, W, bias, 32 * half + o0);
+      __syncwarp();
+      nw_store_rows<OS>(pq, 64, 32 * half, 32, sO, r0, nrows, true, lane);
+      __syncwarp();
+    }
+    nf_cp_async_wait_all();
+    __syncwarp();
+    t = tn;
+  }
+}
+
+template <int I0P, int O0P, int O1P>
+struct NwPostSmem {
+  static constexpr int XS = 4 * ((I0P / 4) | 1), OS = 4 * ((O1P / 4) | 1);
+  static constexpr int o_v1 = O0P * I0P, o_c0 = o_v1 + O1P * O0P, o_c1 = o_c0 + O0P, o_warp = (o_c1 + O1P + 3) & ~3;
+  static constexpr int warp_floats = 32 * XS + 32 * OS;
+  static constexpr int bytes = (o_warp + NW_WARPS * warp_floats) * 4;
+};
+
+// h' = leaky(V1 leaky(V0 [e | h] + c0) + c1)      (node_post_fwd_fast_kernel, warp-autonomous)
+template <int I0P, int O0P, int O1P>
+__global__ void __launch_bounds__(NW_WARPS * 32, 2) node_post_fwd_warp_kernel(int rows, int EL, int cols, int ld, int I0, int O0, int O1,
+                                                                             float alpha, const float* __restrict__ e,
+                                                                             const float* __restrict__ h, const float* __restrict__ V0,
+                                                                             const float* __restrict__ c0, const float* __restrict__ V1,
+                                                                             const float* __restrict__ c1, float* __restrict__ h_out) {
+  gj_pdl_sync();
+  using S = NwPostSmem<I0P, O0P, O1P>;
+  constexpr int XS = S::XS, OS = S::OS, HP = I0P - 16;
+  extern __shared__ __align__(16) float nw_smem[];
+  float* sV0 = nw_smem;
+  float* sV1 = nw_smem + S::o_v1;
+  float* sc0 = nw_smem + S::o_c0;
+  float* sc1 = nw_smem + S::o_c1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* sX = nw_smem + S::o_warp + warp * S::warp_floats;      // [32][XS]: e (16 columns) | h
+  float* sO = sX + 32 * XS;                                     // [32][OS]
+  for (int idx = threadIdx.x; idx < O0P * I0P; idx += NW_WARPS * 32) {
+    const int o = idx / I0P, k = idx - o * I0P;
+    if (o < O0 && k < I0) nf_cp_async4(sV0 + idx, V0 + o * I0 + k);
+    else sV0[idx] = 0.f;
+  }
+  for (int idx = threadIdx.x; idx < O1P * O0P; idx += NW_WARPS * 32) {
+    const int o = idx / O0P, k = idx - o * O0P;
+    if (o < O1 && k < O0) nf_cp_async4(sV1 + idx, V1 + o * O0 + k);
+    else sV1[idx] = 0.f;
+  }
+  for (int o = threadIdx.x; o < O0P; o += NW_WARPS * 32) sc0[o] = o < O0 ? __ldg(c0 + o) : 0.f;
+  for (int o = threadIdx.x; o < O1P; o += NW_WARPS * 32) sc1[o] = o < O1 ? __ldg(c1 + o) : 0.f;
+  for (int idx = lane; idx < 32 * (HP - cols); idx += 32) {      // the padding columns of the staging rows stay zero
+    const int r = idx / (HP - cols), k = idx - r * (HP - cols);
+    sX[r * XS + 16 + cols + k] = 0.f;
+  }
+  const int T = (rows + 31) >> 5, G = gridDim.x;
+  const bool ve = nw_aligned16(e);      // EL == 16
+  const bool vh = (cols & 3) == 0 && (ld & 3) == 0 && nw_aligned16(h);
+  const bool vo = (O1 & 3) == 0 && nw_aligned16(h_out);
+  auto stage = [&](int tt) {
+    const size_t r0 = (size_t)tt * 32;
+    const int nrows = min(32, rows - tt * 32);
+    nw_stage_rows<XS>(sX, 0, e, EL, 16, r0, nrows, ve, lane);
+    nw_stage_rows<XS>(sX, 16, h, ld, cols, r0, nrows, vh, lane);
+  };
+  int t = blockIdx.x + G * warp;
+  if (t < T) stage(t);
+  nf_cp_async_commit();
+  nf_cp_async_wait_all();
+  __syncthreads();      // weights, biases (and this warp's first tile) have landed
+  while (t < T) {
+    const size_t r0 = (size_t)t * 32;
+    const int nrows = min(32, rows - t * 32);
+    float x[I0P];
+#pragma unroll
+    for (int k = 0; k < I0P; k += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(sX + lane * XS + k);
+      x[k] = v.x; x[k + 1] = v.y; x[k + 2] = v.z; x[k + 3] = v.w;
+    }
+    __syncwarp();
+    const int tn = t + G * NW_WARPS;      // every lane holds its row: fetch the next tile under this tile's arithmetic
+    if (tn < T) stage(tn);
+    nf_cp_async_commit();
+    float y0[O0P];
+#pragma unroll
+    for (int o0 = 0; o0 < O0P; o0 += 4) {
+      const float4 v = nf_dot4<I0P>(x, sV0, sc0, o0);
+      y0[o0] = fmaxf(v.x, alpha * v.x); y0[o0 + 1] = fmaxf(v.y, alpha * v.y); y0[o0 + 2] = fmaxf(v.z, alpha * v.z); y0[o0 + 3] = fmaxf(v.w, alpha * v.w);
+    }
+#pragma unroll
+    for (int o0 = 0; o0 < O1P; o0 += 4) {
+      const float4 v = nf_dot4<O0P>(y0, sV1, sc1, o0);
+      *reinterpret_cast<float4*>(sO + lane * OS + o0) =
+          make_float4(fmaxf(v.x, alpha * v.x), fmaxf(v.y, alpha * v.y), fmaxf(v.z, alpha * v.z), fmaxf(v.w, alpha * v.w));
+    }
+    __syncwarp();
+    nw_store_rows<OS>(h_out, O1, 0, O1, sO, r0, nrows, vo, lane);
+    nf_cp_async_wait_all();
+    __syncwarp();
+    t = tn;
+  }
+}
+
 // ---- thread-per-row adjoints: dgrad per thread from registers, wgrad as a second pass over the CTA's row tile ----
 // Weight gradients: the O x KP outputs are dealt out in units of 4 consecutive k; a thread keeps its units in registers
 // across all tiles of the CTA and sweeps the tile's rows, reading g[r][o] and the 16 bytes y[r][4 k4 ..] from the tiles.
@@ -905,11 +1115,44 @@ static int nf_grid(int rows) {
   return blocks < cap ? (blocks > 0 ? blocks : 1) : cap;
 }
 
+// warp-autonomous forward kernels: CTAs of NW_WARPS warps, two per SM, tiles of 32 rows dealt round-robin
+static bool nw_disabled() { static const bool v = getenv("GJ_NODE_FWD_V1") && atoi(getenv("GJ_NODE_FWD_V1")) != 0; return v; }
+static int nw_grid(int rows) {
+  const int tiles = (rows + 31) / 32, cap = gj_num_sms() * 2;
+  const int blocks = (tiles + NW_WARPS - 1) / NW_WARPS;
+  return blocks < cap ? (blocks > 0 ? blocks : 1) : cap;
+}
+template <int KP>
+static int nw_pre_launch(const MPLayout& L, const float* h, const float* w0, const float* b0, float* pq, cudaStream_t st) {
+  using S = NwPreSmem<KP>;
+  if (int rc = nk_set_smem(node_pre_fwd_warp_kernel<KP>, S::bytes)) return rc;
+  const int rows = L.B * L.N;
+  gj_launch(node_pre_fwd_warp_kernel<KP>, nw_grid(rows), NW_WARPS * 32, S::bytes, st, rows, L.H, L.cols, L.ld, L.K[0], h, w0, b0, pq);
+  NK_CHECK_LAUNCH("node_pre_fwd launch");
+  return GJ_OK;
+}
+template <int I0P, int O0P, int O1P>
+static int nw_post_launch(const MPLayout& L, const float* e, const float* h, const float* params, float* h_out, cudaStream_t st) {
+  using S = NwPostSmem<I0P, O0P, O1P>;
+  if (int rc = nk_set_smem(node_post_fwd_warp_kernel<I0P, O0P, O1P>, S::bytes)) return rc;
+  const int rows = L.B * L.N;
+  gj_launch(node_post_fwd_warp_kernel<I0P, O0P, O1P>, nw_grid(rows), NW_WARPS * 32, S::bytes, st, rows, L.EL, L.cols, L.ld, L.I[0], L.O[0],
+            L.O[1], L.alpha, e, h, params + L.pV[0], params + L.pc[0], params + L.pV[1], params + L.pc[1], h_out);
+  NK_CHECK_LAUNCH("node_post_fwd launch");
+  return GJ_OK;
+}
+
 int gj_node_pre_fwd(const MPLayout& L, const float* h, const float* params, float* pq, cudaStream_t st) {
   if (L.E[0] == 32 && L.E0p == 32 && L.cols <= 32) {      // thread-per-row kernel (the usual first edge width)
     const int rows = L.B * L.N, kp = L.cols <= 4 ? 4 : (L.cols <= 8 ? 8 : (L.cols <= 16 ? 16 : 32));
     const float* w0 = params + L.pW[0];
     const float* b0 = params + L.pb[0];
+    if (!nw_disabled()) {
+      if (kp == 4) return nw_pre_launch<4>(L, h, w0, b0, pq, st);
+      if (kp == 8) return nw_pre_launch<8>(L, h, w0, b0, pq, st);
+      if (kp == 16) return nw_pre_launch<16>(L, h, w0, b0, pq, st);
+      return nw_pre_launch<32>(L, h, w0, b0, pq, st);
+    }
     const int grid = nf_grid(rows);
     if (kp == 4) gj_launch(node_pre_fwd_fast_kernel<4>, grid, NF_THREADS, 0, st, rows, L.H, L.cols, L.ld, L.K[0], h, w0, b0, pq);
     else if (kp == 8) gj_launch(node_pre_fwd_fast_kernel<8>, grid, NF_THREADS, 0, st, rows, L.H, L.cols, L.ld, L.K[0], h, w0, b0, pq);
@@ -979,6 +1222,12 @@ static void nf_post_launch(const MPLayout& L, const float* e, const float* h, co
 int gj_node_post_fwd(const MPLayout& L, const float* e, const float* h, const float* params, float* h_out, cudaStream_t st) {
   if (L.Ln == 2 && L.EL == 16 && L.alpha <= 1.f && L.cols <= L.H) {      // thread-per-row kernels for the usual node widths
     const int i0p = (L.I[0] + 3) & ~3, o0p = (L.O[0] + 3) & ~3, o1p = (L.O[1] + 3) & ~3;
+    if (!nw_disabled()) {
+      if (i0p == 32 && o0p == 16 && o1p == 32) return nw_post_launch<32, 16, 32>(L, e, h, params, h_out, st);
+      if (i0p == 48 && o0p == 32 && o1p == 8) return nw_post_launch<48, 32, 8>(L, e, h, params, h_out, st);
+      if (i0p == 24 && o0p == 8 && o1p == 20) return nw_post_launch<24, 8, 20>(L, e, h, params, h_out, st);
+      if (i0p == 24 && o0p == 8 && o1p == 4) return nw_post_launch<24, 8, 4>(L, e, h, params, h_out, st);
+    }
     bool done = true;
     if (i0p == 32 && o0p == 16 && o1p == 32) nf_post_launch<32, 16, 32>(L, e, h, params, h_out, st);
     else if (i0p == 48 && o0p == 32 && o1p == 8) nf_post_launch<48, 32, 8>(L, e, h, params, h_out, st);
