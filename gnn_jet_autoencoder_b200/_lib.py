@@ -47,6 +47,11 @@ SIGNATURES = {
     "gj_mp_step_launches": (C.c_int, [C.POINTER(MPDesc), C.c_int, C.c_int]),
     "gj_mp_step_fwd_saving": (C.c_int, [C.POINTER(MPDesc), _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "gj_mp_step_bwd_saved": (C.c_int, [C.POINTER(MPDesc), _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "gj_mp_step_partials_bytes": (_SZ, [C.POINTER(MPDesc)]),
+    "gj_mp_steps_pack": (C.c_int, [_I, C.POINTER(C.POINTER(MPDesc)), C.POINTER(_P), C.POINTER(_P), _P]),
+    "gj_mp_step_fwd_packed": (C.c_int, [C.POINTER(MPDesc), _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "gj_mp_step_bwd_deferred": (C.c_int, [C.POINTER(MPDesc), _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "gj_mp_steps_reduce": (C.c_int, [_I, C.POINTER(C.POINTER(MPDesc)), C.POINTER(_P), C.POINTER(_P), _P]),
     "gj_mp_step_bwd_workspace": (_SZ, [C.POINTER(MPDesc)]),
     "gj_mp_step_bwd": (C.c_int, [C.POINTER(MPDesc), _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "gj_chamfer_fwd_bwd": (C.c_int, [_I, _I, _I, _I, _I, _F, _F, _P, _P, _P, _P, _P, _P]),

@@ -61,7 +61,14 @@ int gj_edge_bwd_simt(MPLayout, const float*, const float*, const float*, const f
 int gj_edge_fwd_tc(MPLayout, const float*, const float*, const float*, float*, cudaStream_t);
 bool gj_fwd2_supported(const MPLayout&);
 size_t gj_fwd2_ws_floats(const MPLayout&);
-int gj_edge_fwd2(const MPLayout&, const float*, const float*, const float*, float*, float*, float*, float*, cudaStream_t, bool);
+int gj_edge_fwd2(const MPLayout&, const float*, const float*, const float*, float*, float*, float*, float*, cudaStream_t, bool, bool);
+int gj_pack_batch2(int, const MPLayout*, const float* const*, float* const*, cudaStream_t);
+size_t gj_bwd2_part_floats(const MPLayout&);
+int gj_bwd2_nparts(const MPLayout&);
+int gj_node_pre_bwd_tc_nparts(const MPLayout&);
+int gj_node_post_bwd_tc_nparts(const MPLayout&);
+int gj_reduce_steps_partials(int, const MPLayout*, const float* const*, const int*, const float* const*, const int*, const float* const*,
+                             const int*, float* const*, cudaStream_t);
 size_t gj_wimage_floats();
 bool gj_tc_v1_forced();
 void gj_fwd2_plan(const MPLayout&, int*, int*);
@@ -69,7 +76,7 @@ void gj_bwd2_plan(const MPLayout&, int*, int*);
 bool gj_bwd2_supported(const MPLayout&);
 size_t gj_bwd2_ws_floats(const MPLayout&);
 int gj_edge_bwd2(const MPLayout&, const float*, const float*, const float*, const float*, float*, float*, float*, float*, float*, float*, bool,
-                 cudaStream_t, int, const float**, int*);
+                 cudaStream_t, int, const float**, int*, float*);
 size_t gj_edge_bwd_tc_ws_floats(const MPLayout&);
 int gj_edge_bwd_tc(MPLayout, const float*, const float*, const float*, const float*, float*, float*, float*, float*,
                    cudaStream_t);
@@ -181,6 +188,18 @@ static bool node_tail_fused(const MPLayout& L, int precision) {
          !node_tc_disabled();
 }
 
+// caller-owned buffer of a step whose parameter-gradient reduction is deferred (gj_mp_step_bwd_deferred): per-CTA partials of the
+// edge kernel, the projections' adjoint and the node-MLP adjoint (offsets in floats)
+struct PartialsPlan { size_t edge, pre, post, total; };
+static PartialsPlan plan_partials(const MPLayout& L) {
+  PartialsPlan p; size_t off = 0;
+  p.edge = off; off += align_floats(gj_bwd2_part_floats(L));
+  p.pre = off; off += align_floats(gj_node_pre_bwd_tc_ws_floats(L));
+  p.post = off; off += align_floats(gj_node_post_bwd_tc_ws_floats(L));
+  p.total = off;
+  return p;
+}
+
 static StepWs plan_ws(const MPLayout& L, int precision, bool backward) {
   StepWs w; size_t off = 0;
   const size_t rows = (size_t)L.B * L.N;
@@ -237,7 +256,7 @@ size_t gj_mp_step_fwd_workspace(const gj_mp_desc* d) {
 // saved: optional caller-owned buffer of gj_mp_step_saved_bytes(): receives P|Q, the packed edge parameters and the pair
 // distances, which gj_mp_step_bwd_saved then reuses instead of recomputing them
 static int mp_step_fwd_impl(const gj_mp_desc* d, const float* h, const float* params, float* h_out, float* e_out, void* saved,
-                            void* workspace, size_t workspace_bytes, void* stream, const char* who) {
+                            void* workspace, size_t workspace_bytes, void* stream, const char* who, bool prepacked = false) {
   g_err[0] = 0;
   if (!d || !h || !params || !h_out || !e_out || !workspace) { gj_set_error("%s: null pointer", who); return GJ_ERR_INVALID; }
   if (d->precision != GJ_PREC_FP32 && d->precision != GJ_PREC_BF16) { gj_set_error("%s: unknown precision %d", who, d->precision); return GJ_ERR_INVALID; }
@@ -252,13 +271,14 @@ static int mp_step_fwd_impl(const gj_mp_desc* d, const float* h, const float* pa
   const bool tc2 = tc2_path(L, d->precision) && !emat;
   const bool tc3 = tc3_path(L, d->precision);
   if (saved && !tc2 && !tc3) { gj_set_error("%s: this step has nothing to save (gj_mp_step_saved_bytes is 0)", who); return GJ_ERR_INVALID; }
+  if (prepacked && !(tc2 && saved)) { gj_set_error("%s: this step has no packed parameter image (gj_mp_step_partials_bytes is 0)", who); return GJ_ERR_INVALID; }
   float* pre = saved ? (float*)saved : ws;      // P|Q, parameter image, pair distances: same layout in either buffer
   cudaStream_t st = (cudaStream_t)stream;
   const bool dense = dense_node(L, d->precision);
   if ((rc = dense ? gj_dense_pre_fwd(L, h, params, pre + w.pq, d->precision, st) : gj_node_pre_fwd(L, h, params, pre + w.pq, st))) return rc;
   if (emat) rc = gj_edge_mat_fwd(L, h, ws + w.pq, params, e_out, ws + w.emat, d->precision, st);
   else if (tc3) rc = gj_edge_fwd3(L, h, pre + w.pq, params, e_out, ws + w.epart, pre + w.wimg, pre + w.dist, st);
-  else if (tc2) rc = gj_edge_fwd2(L, h, pre + w.pq, params, e_out, ws + w.epart, pre + w.wimg, saved ? pre + w.dist : nullptr, st, false);
+  else if (tc2) rc = gj_edge_fwd2(L, h, pre + w.pq, params, e_out, ws + w.epart, pre + w.wimg, saved ? pre + w.dist : nullptr, st, false, prepacked);
   else rc = use_tc(L, d->precision) ? gj_edge_fwd_tc(L, h, ws + w.pq, params, e_out, st)
                                     : gj_edge_fwd_simt(L, h, ws + w.pq, params, e_out, st);
   if (rc) return rc;
@@ -307,15 +327,19 @@ size_t gj_mp_step_bwd_workspace(const gj_mp_desc* d) {
   return plan_ws(L, d->precision, true).total * sizeof(float);
 }
 
+// partials (optional, with saved): caller-owned buffer of gj_mp_step_partials_bytes(); the per-CTA parameter-gradient partials are
+// left there and dparams is NOT written (gj_mp_steps_reduce reduces them later)
 static int mp_step_bwd_impl(const gj_mp_desc* d, const float* h, const float* e, const float* params, const float* dh_out, float* dh,
-                            float* dparams, const void* saved, void* workspace, size_t workspace_bytes, void* stream, const char* who) {
+                            float* dparams, const void* saved, void* workspace, size_t workspace_bytes, void* stream, const char* who,
+                            float* partials = nullptr) {
   g_err[0] = 0;
-  if (!d || !h || !e || !params || !dh_out || !dh || !dparams || !workspace) { gj_set_error("%s: null pointer", who); return GJ_ERR_INVALID; }
+  if (!d || !h || !e || !params || !dh_out || !dh || (!dparams && !partials) || !workspace) { gj_set_error("%s: null pointer", who); return GJ_ERR_INVALID; }
   if (d->precision != GJ_PREC_FP32 && d->precision != GJ_PREC_BF16) { gj_set_error("%s: unknown precision %d", who, d->precision); return GJ_ERR_INVALID; }
   MPLayout L; const char* why;
   int rc = gj_fill_arch(d, &L, &why);
   if (rc) { gj_set_error("%s: %s", who, why); return rc; }
   cudaStream_t st = (cudaStream_t)stream;
+  if (L.B == 0 && partials) { gj_set_error("%s: empty batch", who); return GJ_ERR_INVALID; }
   if (L.B == 0) { cudaMemsetAsync(dparams, 0, (size_t)L.nparams * sizeof(float), st); return GJ_OK; }
   const StepWs w = plan_ws(L, d->precision, true);
   if (workspace_bytes < w.total * sizeof(float)) { gj_set_error("%s: workspace too small", who); return GJ_ERR_WORKSPACE; }
@@ -325,16 +349,23 @@ static int mp_step_bwd_impl(const gj_mp_desc* d, const float* h, const float* e,
   const bool tc3 = tc3_path(L, d->precision);
   if (saved && !tc2 && !tc3) { gj_set_error("%s: this step has nothing saved (gj_mp_step_saved_bytes is 0)", who); return GJ_ERR_INVALID; }
   float* pre = saved ? (float*)saved : ws;      // read-only when it is the caller's saved buffer
+  if (partials && !(node_tail_fused(L, d->precision) && !emat && saved)) {
+    gj_set_error("%s: this step cannot defer its reduction (gj_mp_step_partials_bytes is 0)", who); return GJ_ERR_INVALID; }
   if (node_tail_fused(L, d->precision) && !emat) {
     // node MLP adjoint (also clears dP|dQ), P|Q unless saved, edge adjoint, projections' adjoint, one reduction of all partials
     int np_post = 0, np_pre = 0, np_edge = 0;
     const float* part_edge = nullptr;
-    if ((rc = gj_node_post_bwd_tc(L, e, h, params, dh_out, ws + w.de, dh, ws + w.part_post, &np_post, ws + w.dpq, st))) return rc;
+    const PartialsPlan pp = plan_partials(L);
+    float* part_e = partials ? partials + pp.edge : nullptr;
+    float* part_post = partials ? partials + pp.post : ws + w.part_post;
+    float* part_pre = partials ? partials + pp.pre : ws + w.part_pre;
+    if ((rc = gj_node_post_bwd_tc(L, e, h, params, dh_out, ws + w.de, dh, part_post, &np_post, ws + w.dpq, st))) return rc;
     if (!saved && (rc = gj_node_pre_fwd(L, h, params, pre + w.pq, st))) return rc;
     if ((rc = gj_edge_bwd2(L, h, pre + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.part, pre + w.wimg, pre + w.dist,
-                           saved != nullptr, st, 2, &part_edge, &np_edge))) return rc;
-    if ((rc = gj_node_pre_bwd_tc(L, h, params, ws + w.dpq, dh, ws + w.part_pre, &np_pre, st))) return rc;
-    return gj_reduce_step_partials(L, part_edge, np_edge, ws + w.part_pre, np_pre, ws + w.part_post, np_post, dparams, st);
+                           saved != nullptr, st, 2, &part_edge, &np_edge, part_e))) return rc;
+    if ((rc = gj_node_pre_bwd_tc(L, h, params, ws + w.dpq, dh, part_pre, &np_pre, st))) return rc;
+    if (partials) return GJ_OK;      // reduced later, together with the other steps' (gj_mp_steps_reduce)
+    return gj_reduce_step_partials(L, part_edge, np_edge, part_pre, np_pre, part_post, np_post, dparams, st);
   }
   const bool dense = dense_node(L, d->precision);
   if (dense) {      // generic-GEMM node level (dense.cu) around the edge adjoint
@@ -359,7 +390,7 @@ static int mp_step_bwd_impl(const gj_mp_desc* d, const float* h, const float* e,
   if (!saved && (rc = gj_node_pre_fwd(L, h, params, pre + w.pq, st))) return rc;
   if (tc2)
     rc = gj_edge_bwd2(L, h, pre + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.part, pre + w.wimg, pre + w.dist, saved != nullptr,
-                      st, 0, nullptr, nullptr);
+                      st, 0, nullptr, nullptr, nullptr);
   else
     rc = use_tc(L, d->precision) ? gj_edge_bwd_tc(L, h, ws + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.part, st)
                                  : gj_edge_bwd_simt(L, h, ws + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.part, st);
@@ -382,6 +413,61 @@ int gj_mp_step_bwd_saved(const gj_mp_desc* d, const float* h, const float* e, co
                          float* dparams, const void* saved, void* workspace, size_t workspace_bytes, void* stream) {
   if (!saved) { g_err[0] = 0; gj_set_error("gj_mp_step_bwd_saved: null pointer"); return GJ_ERR_INVALID; }
   return mp_step_bwd_impl(d, h, e, params, dh_out, dh, dparams, saved, workspace, workspace_bytes, stream, "gj_mp_step_bwd_saved");
+}
+
+// ---- a chain of steps: ONE launch packs every step's parameter image, ONE launch reduces every step's gradient partials ----
+size_t gj_mp_step_partials_bytes(const gj_mp_desc* d) {
+  MPLayout L; const char* why;
+  if (gj_fill_arch(d, &L, &why) || L.B == 0 || !node_tail_fused(L, d->precision) || edge_mat(L, d->precision)) return 0;
+  return plan_partials(L).total * sizeof(float);
+}
+
+int gj_mp_steps_pack(int32_t n, const gj_mp_desc* const* descs, const float* const* params, void* const* saved, void* stream) {
+  g_err[0] = 0;
+  if (n < 0 || n > 64 || (n > 0 && (!descs || !params || !saved))) { gj_set_error("gj_mp_steps_pack: bad arguments"); return GJ_ERR_INVALID; }
+  MPLayout Ls[64]; float* img[64];
+  for (int s = 0; s < n; ++s) {
+    const char* why;
+    if (!descs[s] || !params[s] || !saved[s]) { gj_set_error("gj_mp_steps_pack: null pointer (step %d)", s); return GJ_ERR_INVALID; }
+    if (int rc = gj_fill_arch(descs[s], &Ls[s], &why)) { gj_set_error("gj_mp_steps_pack: %s (step %d)", why, s); return rc; }
+    if (gj_mp_step_partials_bytes(descs[s]) == 0) {
+      gj_set_error("gj_mp_steps_pack: step %d does not run the fused tensor-core kernels (gj_mp_step_partials_bytes is 0)", s); return GJ_ERR_INVALID; }
+    img[s] = (float*)saved[s] + plan_ws(Ls[s], descs[s]->precision, false).wimg;
+  }
+  return n ? gj_pack_batch2(n, Ls, params, img, (cudaStream_t)stream) : GJ_OK;
+}
+
+int gj_mp_step_fwd_packed(const gj_mp_desc* d, const float* h, const float* params, float* h_out, float* e_out, void* saved,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+  if (!saved) { g_err[0] = 0; gj_set_error("gj_mp_step_fwd_packed: null pointer"); return GJ_ERR_INVALID; }
+  return mp_step_fwd_impl(d, h, params, h_out, e_out, saved, workspace, workspace_bytes, stream, "gj_mp_step_fwd_packed", true);
+}
+
+int gj_mp_step_bwd_deferred(const gj_mp_desc* d, const float* h, const float* e, const float* params, const float* dh_out, float* dh,
+                            const void* saved, void* partials, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!saved || !partials) { g_err[0] = 0; gj_set_error("gj_mp_step_bwd_deferred: null pointer"); return GJ_ERR_INVALID; }
+  return mp_step_bwd_impl(d, h, e, params, dh_out, dh, nullptr, saved, workspace, workspace_bytes, stream, "gj_mp_step_bwd_deferred",
+                          (float*)partials);
+}
+
+int gj_mp_steps_reduce(int32_t n, const gj_mp_desc* const* descs, const void* const* partials, float* const* dparams, void* stream) {
+  g_err[0] = 0;
+  if (n < 0 || n > 64 || (n > 0 && (!descs || !partials || !dparams))) { gj_set_error("gj_mp_steps_reduce: bad arguments"); return GJ_ERR_INVALID; }
+  MPLayout Ls[64];
+  const float* pE[64]; const float* pP[64]; const float* pN[64];
+  int nE[64], nP[64], nN[64];
+  for (int s = 0; s < n; ++s) {
+    const char* why;
+    if (!descs[s] || !partials[s] || !dparams[s]) { gj_set_error("gj_mp_steps_reduce: null pointer (step %d)", s); return GJ_ERR_INVALID; }
+    if (int rc = gj_fill_arch(descs[s], &Ls[s], &why)) { gj_set_error("gj_mp_steps_reduce: %s (step %d)", why, s); return rc; }
+    if (gj_mp_step_partials_bytes(descs[s]) == 0) {
+      gj_set_error("gj_mp_steps_reduce: step %d cannot defer its reduction (gj_mp_step_partials_bytes is 0)", s); return GJ_ERR_INVALID; }
+    const PartialsPlan pp = plan_partials(Ls[s]);
+    const float* base = (const float*)partials[s];
+    pE[s] = base + pp.edge; pP[s] = base + pp.pre; pN[s] = base + pp.post;
+    nE[s] = gj_bwd2_nparts(Ls[s]); nP[s] = gj_node_pre_bwd_tc_nparts(Ls[s]); nN[s] = gj_node_post_bwd_tc_nparts(Ls[s]);
+  }
+  return n ? gj_reduce_steps_partials(n, Ls, pE, nE, pP, nP, pN, nN, dparams, (cudaStream_t)stream) : GJ_OK;
 }
 
 int gj_chamfer_fwd_bwd(int32_t batch, int32_t np_, int32_t nq, int32_t dim, int32_t norm, float w_chamfer, float w_jet,
@@ -512,7 +598,7 @@ int gj_bench_edge_fwd_only(const gj_mp_desc* d, const float* h, const float* par
   const StepWs w = plan_ws(L, d->precision, false);
   if (workspace_bytes < w.total * sizeof(float)) { gj_set_error("gj_bench_edge_fwd_only: workspace too small"); return GJ_ERR_WORKSPACE; }
   float* ws = (float*)workspace;
-  return gj_edge_fwd2(L, h, ws + w.pq, params, e_out, ws + w.epart, ws + w.wimg, nullptr, (cudaStream_t)stream, true);
+  return gj_edge_fwd2(L, h, ws + w.pq, params, e_out, ws + w.epart, ws + w.wimg, nullptr, (cudaStream_t)stream, true, false);
 }
 
 int gj_bench_edge_bwd_only(const gj_mp_desc* d, const float* h, const float* params, float* dh, float* dparams, void* workspace,
@@ -526,7 +612,7 @@ int gj_bench_edge_bwd_only(const gj_mp_desc* d, const float* h, const float* par
   if (workspace_bytes < w.total * sizeof(float)) { gj_set_error("gj_bench_edge_bwd_only: workspace too small"); return GJ_ERR_WORKSPACE; }
   float* ws = (float*)workspace;
   return gj_edge_bwd2(L, h, ws + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.part, ws + w.wimg, ws + w.dist, true,
-                      (cudaStream_t)stream, 1, nullptr, nullptr);
+                      (cudaStream_t)stream, 1, nullptr, nullptr, nullptr);
 }
 
 /* As gj_bench_edge_bwd_only, for the step as the trainer runs it: `saved` was filled by gj_mp_step_fwd_saving and `workspace`
@@ -543,7 +629,7 @@ int gj_bench_edge_bwd_saved_only(const gj_mp_desc* d, const float* h, const floa
   float* ws = (float*)workspace;
   float* pre = (float*)saved;
   return gj_edge_bwd2(L, h, pre + w.pq, params, ws + w.de, ws + w.dpq, dh, dparams, ws + w.part, pre + w.wimg, pre + w.dist, true,
-                      (cudaStream_t)stream, 1, nullptr, nullptr);
+                      (cudaStream_t)stream, 1, nullptr, nullptr, nullptr);
 }
 
 int gj_mp_plan_info(const gj_mp_desc* d, int32_t* info) {

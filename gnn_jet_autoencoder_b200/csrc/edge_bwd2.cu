@@ -966,6 +966,9 @@ void gj_bwd2_plan(const MPLayout&, int* smem_bytes, int* tmem_cols) {
 
 static int bwd2_grid(const MPLayout& L) { return gj_num_sms(); }
 
+size_t gj_bwd2_part_floats(const MPLayout& L) { return (size_t)bwd2_grid(L) * L.pV[0]; }
+int gj_bwd2_nparts(const MPLayout& L) { return bwd2_grid(L); }
+
 // workspace (floats): G (B N NJ32) | dP partials (NJB > 1) | per-CTA parameter-gradient partials
 size_t gj_bwd2_ws_floats(const MPLayout& L) {
   const size_t njb = (L.N + 31) / 32, rows = (size_t)L.B * L.N;
@@ -1014,7 +1017,7 @@ int gj_pair_dist_bwd(const MPLayout& L, const float* h, const float* G, float* d
 // and are used as they are, otherwise they are (re)computed here
 int gj_edge_bwd2(const MPLayout& L, const float* h, const float* pq, const float* params, const float* de, float* dpq, float* dh,
                  float* dparams, float* ws, float* wimg_f, float* d, bool have_saved, cudaStream_t stream, int mode,
-                 const float** part_out, int* nparts_out) {
+                 const float** part_out, int* nparts_out, float* part_ext) {
   // mode 0: the whole edge adjoint; 1: the fused kernel alone (bench hook); 2: as 0, but dpq has already been zeroed by the
   // caller and the per-CTA parameter-gradient partials are handed back (*part_out, *nparts_out) instead of being reduced
   const bool kernel_only = mode == 1;
@@ -1032,7 +1035,9 @@ int gj_edge_bwd2(const MPLayout& L, const float* h, const float* pq, const float
   uint8_t* wimg = reinterpret_cast<uint8_t*>(wimg_f);      // packed bf16 parameter image (WImage), 16-byte aligned
   float* G = ws;
   float* dp_part = G + rows * NJ32 + 32;
-  float* part = njb > 1 ? dp_part + njb * rows * L.E[0] + 64 : dp_part;
+  // per-CTA parameter-gradient partials: in the workspace, or in a caller-owned buffer of gj_bwd2_part_floats() floats (a step whose
+  // reduction is deferred to gj_mp_steps_reduce keeps them until then)
+  float* part = part_ext ? part_ext : (njb > 1 ? dp_part + njb * rows * L.E[0] + 64 : dp_part);
   A.wimg = wimg;
   A.pq = pq; A.d = d; A.params = params; A.de = de; A.dpq = dpq; A.dp_part = dp_part; A.G = G; A.part = part;
   A.B = L.B; A.N = L.N; A.NJB = (int)njb; A.NJ32 = NJ32;

@@ -468,13 +468,33 @@ size_t gj_fwd2_ws_floats(const MPLayout& L) {
 // (B, N, NJ32) buffer that receives the pair distances (both are reused by gj_edge_bwd2 when the caller keeps them)
 size_t gj_wimage_floats() { return (WImage<32, 128, 64, 16>::bytes + 255) / 256 * 64; }
 
+// the packed parameter images of n steps (all of them gj_fwd2_supported) in one launch
+int gj_pack_batch2(int n, const MPLayout* Ls, const float* const* params, float* const* wimg, cudaStream_t stream) {
+  for (int s0 = 0; s0 < n; s0 += PACK_BATCH_MAX) {
+    const int m = n - s0 < PACK_BATCH_MAX ? n - s0 : PACK_BATCH_MAX;
+    PackBatch Bt;
+    for (int s = 0; s < m; ++s) {
+      const MPLayout& L = Ls[s0 + s];
+      Bt.params[s] = params[s0 + s];
+      Bt.P[s] = WImageSrc{L.pW[1], L.pb[1], L.pW[2], L.pb[2], L.pW[3], L.pb[3]};
+      Bt.img[s] = reinterpret_cast<uint8_t*>(wimg[s0 + s]);
+    }
+    for (int s = m; s < PACK_BATCH_MAX; ++s) { Bt.params[s] = nullptr; Bt.P[s] = WImageSrc{0, 0, 0, 0, 0, 0}; Bt.img[s] = nullptr; }
+    gj_launch(pack_edge_weights_batch_kernel<32, 128, 64, 16>, dim3(4, m), 256, 0, stream, Bt);
+    const cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) { gj_set_error("pack_edge_weights_batch launch: %s", cudaGetErrorString(ce)); return GJ_ERR_CUDA; }
+  }
+  return GJ_OK;
+}
+
+// skip_pack: the packed parameter image is already in wimg (gj_mp_steps_pack)
 int gj_edge_fwd2(const MPLayout& L, const float* h, const float* pq, const float* params, float* e_out, float* ws, float* wimg,
-                 float* d_save, cudaStream_t stream, bool kernel_only) {
+                 float* d_save, cudaStream_t stream, bool kernel_only, bool skip_pack) {
   constexpr int NWG = 4;
   Fwd2Args A;
   A.wimg = reinterpret_cast<const uint8_t*>(wimg);
   A.d_out = d_save;
-  if (!kernel_only) {
+  if (!kernel_only && !skip_pack) {
     WImageSrc P{L.pW[1], L.pb[1], L.pW[2], L.pb[2], L.pW[3], L.pb[3]};
     gj_launch(pack_edge_weights_kernel<32, 128, 64, 16>, 4, 256, 0, stream, params, P, reinterpret_cast<uint8_t*>(wimg));
   }

@@ -963,31 +963,45 @@ __global__ void reduce_pre_partials_kernel(const float* __restrict__ part, int n
 // One launch for the three fixed-order partial reductions of a backward step (bf16 tensor-core path): blocks [0, nbE) the
 // edge-kernel partials (all edge parameters but the Wa | Wb columns of W0 and b0), [nbE, nbE + nbP) the projection-adjoint
 // partials (those columns and b0), the rest the node-MLP partials.  Same per-output summation order as the single kernels.
-__global__ void reduce_step_partials_kernel(const float* __restrict__ partE, int npE, int nE, int nbE, const float* __restrict__ partP,
-                                            int npP, int nbP, const float* __restrict__ partN, int npN, int nN, int E0, int H,
-                                            float* __restrict__ dedge, float* __restrict__ dW0, float* __restrict__ db0,
-                                            float* __restrict__ dnode) {
-  gj_pdl_sync();
-  const int K0 = 2 * H + 1;
-  if ((int)blockIdx.x < nbE) {
-    const int p = blockIdx.x * 32 + threadIdx.x;
+struct StepReduce {
+  const float* partE; const float* partP; const float* partN;
+  int npE, nE, nbE, npP, nbP, npN, nN, E0, H;
+  float* dedge; float* dW0; float* db0; float* dnode;
+};
+__device__ __forceinline__ void reduce_step_partials_body(const StepReduce& R, int bx) {
+  const int K0 = 2 * R.H + 1, E0 = R.E0, H = R.H;
+  if (bx < R.nbE) {
+    const int p = bx * 32 + threadIdx.x;
     const int first = E0 * K0 + E0;          // W0 then b0: only the wd column (index 2H of each row) belongs to the edge kernel
-    const bool mine = p < nE && !(p < first && !(p < E0 * K0 && (p % K0) == K0 - 1));
-    const float acc = reduce_column(partE, npE, nE, mine ? p : nE);
-    if (threadIdx.y == 0 && mine) dedge[p] = acc;
-  } else if ((int)blockIdx.x < nbE + nbP) {
+    const bool mine = p < R.nE && !(p < first && !(p < E0 * K0 && (p % K0) == K0 - 1));
+    const float acc = reduce_column(R.partE, R.npE, R.nE, mine ? p : R.nE);
+    if (threadIdx.y == 0 && mine) R.dedge[p] = acc;
+  } else if (bx < R.nbE + R.nbP) {
     const int n = E0 * 2 * H + E0;
-    const int p = (blockIdx.x - nbE) * 32 + threadIdx.x;
-    const float acc = reduce_column(partP, npP, n, p);
+    const int p = (bx - R.nbE) * 32 + threadIdx.x;
+    const float acc = reduce_column(R.partP, R.npP, n, p);
     if (threadIdx.y != 0 || p >= n) return;
-    if (p < E0 * H) { const int c = p / H, k = p - c * H; dW0[c * K0 + k] = acc; }
-    else if (p < 2 * E0 * H) { const int q = p - E0 * H; const int c = q / H, k = q - c * H; dW0[c * K0 + H + k] = acc; }
-    else db0[p - 2 * E0 * H] = acc;
+    if (p < E0 * H) { const int c = p / H, k = p - c * H; R.dW0[c * K0 + k] = acc; }
+    else if (p < 2 * E0 * H) { const int q = p - E0 * H; const int c = q / H, k = q - c * H; R.dW0[c * K0 + H + k] = acc; }
+    else R.db0[p - 2 * E0 * H] = acc;
   } else {
-    const int p = (blockIdx.x - nbE - nbP) * 32 + threadIdx.x;
-    const float acc = reduce_column(partN, npN, nN, p);
-    if (threadIdx.y == 0 && p < nN) dnode[p] = acc;
+    const int p = (bx - R.nbE - R.nbP) * 32 + threadIdx.x;
+    const float acc = reduce_column(R.partN, R.npN, R.nN, p);
+    if (threadIdx.y == 0 && p < R.nN) R.dnode[p] = acc;
   }
+}
+__global__ void reduce_step_partials_kernel(const __grid_constant__ StepReduce R) {
+  gj_pdl_sync();
+  reduce_step_partials_body(R, blockIdx.x);
+}
+// the reductions of up to REDUCE_BATCH_MAX steps in ONE launch (gj_mp_steps_reduce): blockIdx.y = step
+constexpr int REDUCE_BATCH_MAX = 16;
+struct StepReduceBatch { StepReduce r[REDUCE_BATCH_MAX]; };
+__global__ void reduce_steps_partials_kernel(const __grid_constant__ StepReduceBatch Bt) {
+  gj_pdl_sync();
+  const StepReduce& R = Bt.r[blockIdx.y];
+  if ((int)blockIdx.x >= R.nbE + R.nbP + (R.nN + 31) / 32) return;      // block-uniform
+  reduce_step_partials_body(R, blockIdx.x);
 }
 
 }  // namespace
@@ -1188,14 +1202,43 @@ int gj_reduce_pre_partials(const MPLayout& L, const float* part, int nparts, flo
   return GJ_OK;
 }
 
+static StepReduce step_reduce_args(const MPLayout& L, const float* partE, int npE, const float* partP, int npP, const float* partN, int npN,
+                                   float* dparams) {
+  StepReduce R;
+  R.partE = partE; R.partP = partP; R.partN = partN;
+  R.npE = npE; R.nE = L.pV[0]; R.nbE = (R.nE + 31) / 32;
+  R.npP = npP; R.nbP = (L.E[0] * 2 * L.H + L.E[0] + 31) / 32;
+  R.npN = npN; R.nN = L.nparams - L.pV[0];
+  R.E0 = L.E[0]; R.H = L.H;
+  R.dedge = dparams; R.dW0 = dparams + L.pW[0]; R.db0 = dparams + L.pb[0]; R.dnode = dparams + L.pV[0];
+  return R;
+}
+
 int gj_reduce_step_partials(const MPLayout& L, const float* partE, int npE, const float* partP, int npP, const float* partN, int npN,
                             float* dparams, cudaStream_t st) {
-  const int nE = L.pV[0], nP = L.E[0] * 2 * L.H + L.E[0], nN = L.nparams - L.pV[0];
-  const int nbE = (nE + 31) / 32, nbP = (nP + 31) / 32, nbN = (nN + 31) / 32;
-  gj_launch(reduce_step_partials_kernel, nbE + nbP + nbN, dim3(32, RED_SLICES), 0, st, partE, npE, nE, nbE, partP, npP, nbP, partN, npN, nN, L.E[0],
-                                                                              L.H, dparams, dparams + L.pW[0], dparams + L.pb[0],
-                                                                              dparams + L.pV[0]);
+  const StepReduce R = step_reduce_args(L, partE, npE, partP, npP, partN, npN, dparams);
+  gj_launch(reduce_step_partials_kernel, R.nbE + R.nbP + (R.nN + 31) / 32, dim3(32, RED_SLICES), 0, st, R);
   NK_CHECK_LAUNCH("reduce_step_partials launch");
+  return GJ_OK;
+}
+
+// the same reduction for n steps in one launch; partE / partP / partN / np*: per step
+int gj_reduce_steps_partials(int n, const MPLayout* Ls, const float* const* partE, const int* npE, const float* const* partP, const int* npP,
+                             const float* const* partN, const int* npN, float* const* dparams, cudaStream_t st) {
+  for (int s0 = 0; s0 < n; s0 += REDUCE_BATCH_MAX) {
+    const int m = n - s0 < REDUCE_BATCH_MAX ? n - s0 : REDUCE_BATCH_MAX;
+    StepReduceBatch Bt;
+    memset(&Bt, 0, sizeof(Bt));
+    int nbmax = 1;
+    for (int s = 0; s < m; ++s) {
+      const int g = s0 + s;
+      Bt.r[s] = step_reduce_args(Ls[g], partE[g], npE[g], partP[g], npP[g], partN[g], npN[g], dparams[g]);
+      const int nb = Bt.r[s].nbE + Bt.r[s].nbP + (Bt.r[s].nN + 31) / 32;
+      if (nb > nbmax) nbmax = nb;
+    }
+    gj_launch(reduce_steps_partials_kernel, dim3(nbmax, m), dim3(32, RED_SLICES), 0, st, Bt);
+    NK_CHECK_LAUNCH("reduce_steps_partials launch");
+  }
   return GJ_OK;
 }
 

@@ -601,6 +601,8 @@ static int pre_bwd_tc_grid(const MPLayout& L) {      // every CTA gets the same 
 // per-CTA partials [Wa grads 32*H][Wb grads 32*H][b0 grads 32], reduced by reduce_pre_partials_kernel
 size_t gj_node_pre_bwd_tc_ws_floats(const MPLayout& L) { return (size_t)pre_bwd_tc_grid(L) * (64 * L.H + 32); }
 
+int gj_node_pre_bwd_tc_nparts(const MPLayout& L) { return pre_bwd_tc_grid(L); }
+
 // launches the kernel; *nparts receives the number of per-CTA partials written to `part`
 int gj_node_pre_bwd_tc(const MPLayout& L, const float* h, const float* params, const float* dpq, float* dh, float* part, int* nparts,
                        cudaStream_t st) {
@@ -639,6 +641,8 @@ static int post_bwd_tc_grid(const MPLayout& L) {
   return (tiles + rounds - 1) / rounds;
 }
 size_t gj_node_post_bwd_tc_ws_floats(const MPLayout& L) { return (size_t)post_bwd_tc_grid(L) * (L.nparams - L.pV[0]); }
+
+int gj_node_post_bwd_tc_nparts(const MPLayout& L) { return post_bwd_tc_grid(L); }
 
 template <int I0P, int O0P, int O1P>
 static cudaError_t post_bwd_tc_launch(const MPLayout& L, int grid, const float* e, const float* h, const float* params, const float* dh_out,

@@ -218,11 +218,12 @@ __device__ __forceinline__ void pack_weight_kmajor_unaligned(uint8_t* dst, const
     *reinterpret_cast<__nv_bfloat16*>(dst + (k >> 3) * (NOUT * 16) + n * 16 + (k & 7) * 2) = __float2bfloat16_rn(__ldg(W + idx));
   }
 }
+// fp32 parameters of the dense edge layers -> the packed bf16 image; tid / nthr: this thread's index and the thread count of the
+// group of CTAs that packs the image
 template <int E0, int E1, int E2, int E3>
-__global__ void __launch_bounds__(256) pack_edge_weights_kernel(const float* __restrict__ params, WImageSrc P, uint8_t* __restrict__ img) {
-  gj_pdl_sync();
+__device__ __forceinline__ void pack_edge_weights_body(const float* __restrict__ params, const WImageSrc& P, uint8_t* __restrict__ img,
+                                                       int tid, int nthr) {
   using I = WImage<E0, E1, E2, E3>;
-  const int tid = blockIdx.x * 256 + threadIdx.x, nthr = gridDim.x * 256;
   for (int idx = tid; idx < (I::o_w1 - (I::o_b3 + E3 * 16)) / 4; idx += nthr) reinterpret_cast<uint32_t*>(img + I::o_b3 + E3 * 16)[idx] = 0u;
   pack_bias_chunk<E1>(img + I::o_b1, params + P.pb1, tid, nthr);
   pack_bias_chunk<E2>(img + I::o_b2, params + P.pb2, tid, nthr);
@@ -238,6 +239,20 @@ __global__ void __launch_bounds__(256) pack_edge_weights_kernel(const float* __r
     pack_weight_kmajor_unaligned<E2, E1>(img + I::o_w2, params + P.pW2, tid, nthr);
     pack_weight_kmajor_unaligned<E3, E2>(img + I::o_w3, params + P.pW3, tid, nthr);
   }
+}
+template <int E0, int E1, int E2, int E3>
+__global__ void __launch_bounds__(256) pack_edge_weights_kernel(const float* __restrict__ params, WImageSrc P, uint8_t* __restrict__ img) {
+  gj_pdl_sync();
+  pack_edge_weights_body<E0, E1, E2, E3>(params, P, img, blockIdx.x * 256 + threadIdx.x, gridDim.x * 256);
+}
+// the images of up to PACK_BATCH_MAX steps in ONE launch (gj_mp_steps_pack): blockIdx.y = step
+constexpr int PACK_BATCH_MAX = 16;
+struct PackBatch { const float* params[PACK_BATCH_MAX]; WImageSrc P[PACK_BATCH_MAX]; uint8_t* img[PACK_BATCH_MAX]; };
+template <int E0, int E1, int E2, int E3>
+__global__ void __launch_bounds__(256) pack_edge_weights_batch_kernel(const __grid_constant__ PackBatch Bt) {
+  gj_pdl_sync();
+  const int s = blockIdx.y;
+  pack_edge_weights_body<E0, E1, E2, E3>(Bt.params[s], Bt.P[s], Bt.img[s], blockIdx.x * 256 + threadIdx.x, gridDim.x * 256);
 }
 // every CTA: image (global, 16-byte aligned) -> shared memory
 template <int BYTES>

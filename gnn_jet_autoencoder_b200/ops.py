@@ -95,6 +95,41 @@ def raw_mp_bwd(desc, h_ptr, e_ptr, params_ptr, dhout_ptr, dh_ptr, dparams_ptr, w
     LAUNCHES["count"] += _step_launches(desc, True, bool(saved_ptr))
 
 
+# ---- a chain of steps with per-chain helper launches (include/gnnjet_b200.h: gj_mp_steps_pack / gj_mp_steps_reduce) ----
+def _ptr_array(ptrs):
+    return (_lib.C.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
+
+
+def _desc_array(descs):
+    return (_lib.C.POINTER(_lib.MPDesc) * len(descs))(*[_lib.C.pointer(d) for d in descs])
+
+
+def raw_mp_pack_steps(descs, params_ptrs, saved_ptrs, stream):
+    """ONE launch packs the bf16 edge-parameter images of all steps into their ``saved`` buffers."""
+    _lib.check(_lib.load().gj_mp_steps_pack(len(descs), _desc_array(descs), _ptr_array(params_ptrs), _ptr_array(saved_ptrs), stream),
+               "gj_mp_steps_pack")
+    LAUNCHES["count"] += 1 if descs else 0
+
+
+def raw_mp_fwd_packed(desc, h_ptr, params_ptr, hout_ptr, e_ptr, ws_ptr, ws_bytes, stream, saved_ptr):
+    _lib.check(_lib.load().gj_mp_step_fwd_packed(desc, h_ptr, params_ptr, hout_ptr, e_ptr, saved_ptr, ws_ptr, ws_bytes, stream),
+               "gj_mp_step_fwd_packed")
+    LAUNCHES["count"] += _step_launches(desc, False) - 1      # no packing launch
+
+
+def raw_mp_bwd_deferred(desc, h_ptr, e_ptr, params_ptr, dhout_ptr, dh_ptr, ws_ptr, ws_bytes, stream, saved_ptr, partials_ptr):
+    _lib.check(_lib.load().gj_mp_step_bwd_deferred(desc, h_ptr, e_ptr, params_ptr, dhout_ptr, dh_ptr, saved_ptr, partials_ptr, ws_ptr,
+                                                   ws_bytes, stream), "gj_mp_step_bwd_deferred")
+    LAUNCHES["count"] += _step_launches(desc, True, True) - 1      # no reduction launch
+
+
+def raw_mp_reduce_steps(descs, partials_ptrs, dparams_ptrs, stream):
+    """ONE launch reduces the parameter-gradient partials of all steps into their gradient blocks."""
+    _lib.check(_lib.load().gj_mp_steps_reduce(len(descs), _desc_array(descs), _ptr_array(partials_ptrs), _ptr_array(dparams_ptrs), stream),
+               "gj_mp_steps_reduce")
+    LAUNCHES["count"] += 1 if descs else 0
+
+
 # --------------------------------------------------------------------------------------------------
 # custom ops
 # --------------------------------------------------------------------------------------------------

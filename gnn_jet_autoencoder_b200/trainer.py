@@ -13,6 +13,7 @@ two Adams) as a fixed sequence of fused kernels over flat buffers.
 """
 from __future__ import annotations
 
+import os
 from collections import OrderedDict
 from typing import Optional
 
@@ -121,7 +122,8 @@ class GNNAETrainer:
                  l1_lambda: float = 1e-8, l2_lambda: float = 0.0, loss_norm_choice: str = "cartesian",
                  jet_features_weight: float = 1.0, chamfer_mode: str = "intended", encoder_metric: str = "euclidean",
                  decoder_metric: str = "euclidean", process_group=None, use_cuda_graph: bool = True,
-                 loss_choice: str = "chamfer", polar_coord: bool = False, optimizer: str = "adam"):
+                 loss_choice: str = "chamfer", polar_coord: bool = False, optimizer: str = "adam",
+                 batched_launches: bool = True):
         self.enc, self.dec = encoder, decoder
         g_e, g_d = encoder.encoder, decoder.decoder
         dev = next(encoder.parameters()).device
@@ -239,6 +241,16 @@ class GNNAETrainer:
         for st_ in self.enc_steps + self.dec_steps:
             nbytes = int(self.lib.gj_mp_step_saved_bytes(st_["desc"]))
             st_["saved"] = torch.empty((nbytes + 3) // 4, **f32) if nbytes else None
+        # per-chain helper launches (gj_mp_steps_pack / gj_mp_steps_reduce): the packed edge-parameter images of all steps in ONE
+        # launch at the start of the forward pass, the parameter-gradient partials of all steps reduced in ONE launch at the end of
+        # the backward pass (each step keeps its partials in its own buffer until then) -- where every step supports it
+        all_steps = self.enc_steps + self.dec_steps
+        pbytes = [int(self.lib.gj_mp_step_partials_bytes(s_["desc"])) for s_ in all_steps]
+        if os.environ.get("GNNJET_BATCHED_LAUNCHES", "1") == "0":      # A/B switch (tools/)
+            batched_launches = False
+        self.batched = bool(batched_launches) and all(b > 0 for b in pbytes) and all(s_["saved"] is not None for s_ in all_steps)
+        for s_, nb in zip(all_steps, pbytes):
+            s_["partials"] = torch.empty((nb + 3) // 4, **f32) if self.batched else None
         self.graph = None
         self.use_graph = use_cuda_graph
         self.launches_per_step = None
@@ -264,13 +276,34 @@ class GNNAETrainer:
         return steps
 
     # ---- the launch sequence ------------------------------------------------------------------------
+    def _step_fwd(self, s, h, st):
+        P = self.flat.data_ptr()
+        if self.batched:
+            ops.raw_mp_fwd_packed(s["desc"], h.data_ptr(), P + 4 * s["off"], s["out"].data_ptr(), s["e"].data_ptr(),
+                                  self.ws.data_ptr(), self.ws_bytes, st, s["saved"].data_ptr())
+        else:
+            ops.raw_mp_fwd(s["desc"], h.data_ptr(), P + 4 * s["off"], s["out"].data_ptr(), s["e"].data_ptr(),
+                           self.ws.data_ptr(), self.ws_bytes, st, s["saved"].data_ptr() if s["saved"] is not None else None)
+
+    def _step_bwd(self, s, hin, g, din, st):
+        P, G = self.flat.data_ptr(), self.grad.data_ptr()
+        if self.batched:
+            ops.raw_mp_bwd_deferred(s["desc"], hin.data_ptr(), s["e"].data_ptr(), P + 4 * s["off"], g.data_ptr(), din.data_ptr(),
+                                    self.ws.data_ptr(), self.ws_bytes, st, s["saved"].data_ptr(), s["partials"].data_ptr())
+        else:
+            ops.raw_mp_bwd(s["desc"], hin.data_ptr(), s["e"].data_ptr(), P + 4 * s["off"], g.data_ptr(), din.data_ptr(),
+                           G + 4 * s["off"], self.ws.data_ptr(), self.ws_bytes, st,
+                           s["saved"].data_ptr() if s["saved"] is not None else None)
+
     def _fwd(self, st):
         lib, P = self.lib, self.flat.data_ptr()
         B, N = self.B, self.N
         h = self.x
+        if self.batched:
+            steps = self.enc_steps + self.dec_steps
+            ops.raw_mp_pack_steps([s["desc"] for s in steps], [P + 4 * s["off"] for s in steps], [s["saved"].data_ptr() for s in steps], st)
         for s in self.enc_steps:
-            ops.raw_mp_fwd(s["desc"], h.data_ptr(), P + 4 * s["off"], s["out"].data_ptr(), s["e"].data_ptr(),
-                           self.ws.data_ptr(), self.ws_bytes, st, s["saved"].data_ptr() if s["saved"] is not None else None)
+            self._step_fwd(s, h, st)
             h = s["out"]
         L = self.layout
         if self.map == "mean":
@@ -294,8 +327,7 @@ class GNNAETrainer:
         ops.LAUNCHES["count"] += 1
         h = self.dec_in
         for s in self.dec_steps:
-            ops.raw_mp_fwd(s["desc"], h.data_ptr(), P + 4 * s["off"], s["out"].data_ptr(), s["e"].data_ptr(),
-                           self.ws.data_ptr(), self.ws_bytes, st, s["saved"].data_ptr() if s["saved"] is not None else None)
+            self._step_fwd(s, h, st)
             h = s["out"]
         if self.transform:
             _lib.check(lib.gj_output_transform_fwd(B * N, self.recon.shape[-1], int(self.use_tanh), self.clamp_mask, POLAR_EPS,
@@ -331,9 +363,7 @@ class GNNAETrainer:
             s = self.dec_steps[t]
             hin = self.dec_in if t == 0 else self.dec_steps[t - 1]["out"]
             din = self.d_dec_in if t == 0 else s["din"]
-            ops.raw_mp_bwd(s["desc"], hin.data_ptr(), s["e"].data_ptr(), P + 4 * s["off"], g.data_ptr(), din.data_ptr(),
-                           G + 4 * s["off"], self.ws.data_ptr(), self.ws_bytes, st,
-                           s["saved"].data_ptr() if s["saved"] is not None else None)
+            self._step_bwd(s, hin, g, din, st)
             g = din
         wl = L["decoder.linear.weight"][0]
         bl = L["decoder.linear.bias"][0]
@@ -367,10 +397,12 @@ class GNNAETrainer:
             s = self.enc_steps[t]
             hin = self.x if t == 0 else self.enc_steps[t - 1]["out"]
             din = self.dx if t == 0 else s["din"]
-            ops.raw_mp_bwd(s["desc"], hin.data_ptr(), s["e"].data_ptr(), P + 4 * s["off"], g.data_ptr(), din.data_ptr(),
-                           G + 4 * s["off"], self.ws.data_ptr(), self.ws_bytes, st,
-                           s["saved"].data_ptr() if s["saved"] is not None else None)
+            self._step_bwd(s, hin, g, din, st)
             g = din
+        if self.batched:
+            steps = self.enc_steps + self.dec_steps
+            ops.raw_mp_reduce_steps([s["desc"] for s in steps], [s["partials"].data_ptr() for s in steps],
+                                    [G + 4 * s["off"] for s in steps], st)
 
     def _fwd_bwd(self):
         st = torch.cuda.current_stream().cuda_stream

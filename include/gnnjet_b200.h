@@ -112,6 +112,28 @@ int gj_mp_step_bwd_saved(const gj_mp_desc* d, const float* h, const float* e, co
                          const float* dh_out, float* dh, float* dparams, const void* saved,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* A chain of steps (a GraphNet, or encoder + decoder of a training step: the loop of graphnet.py:154-168 and its adjoint)
+ * with per-chain instead of per-step helper launches.  Two pieces of every step depend on the parameters only or are needed
+ * only at the end of the backward pass: the packed bf16 image of the edge-network weights (one small launch per step) and the
+ * fixed-order reduction of the per-CTA parameter-gradient partials (another).  For steps with gj_mp_step_partials_bytes(d) > 0
+ * (the fused tensor-core kernels, gj_mp_step_saved_bytes(d) > 0 as well):
+ *   gj_mp_steps_pack       : ONE launch writes the parameter images of all n steps into their `saved` buffers (any time after
+ *                            the parameters were last updated, before the first gj_mp_step_fwd_packed);
+ *   gj_mp_step_fwd_packed  : gj_mp_step_fwd_saving without the packing launch (the image in `saved` is used as it is);
+ *   gj_mp_step_bwd_deferred: gj_mp_step_bwd_saved without the reduction: the per-CTA partials are left in the caller-owned
+ *                            buffer `partials` (gj_mp_step_partials_bytes(d) bytes, 256-byte aligned) and no dparams is written;
+ *   gj_mp_steps_reduce     : ONE launch reduces the partials of all n steps into their dparams blocks (same summation order as
+ *                            gj_mp_step_bwd_saved: the results are identical).
+ * Every function returns GJ_ERR_INVALID for a step with gj_mp_step_partials_bytes(d) == 0; n <= 64. */
+size_t gj_mp_step_partials_bytes(const gj_mp_desc* d);
+int gj_mp_steps_pack(int32_t n, const gj_mp_desc* const* descs, const float* const* params, void* const* saved, void* stream);
+int gj_mp_step_fwd_packed(const gj_mp_desc* d, const float* h, const float* params,
+                          float* h_out, float* e_out, void* saved, void* workspace, size_t workspace_bytes, void* stream);
+int gj_mp_step_bwd_deferred(const gj_mp_desc* d, const float* h, const float* e, const float* params,
+                            const float* dh_out, float* dh, const void* saved, void* partials,
+                            void* workspace, size_t workspace_bytes, void* stream);
+int gj_mp_steps_reduce(int32_t n, const gj_mp_desc* const* descs, const void* const* partials, float* const* dparams, void* stream);
+
 /* Workspace bytes needed by gj_mp_step_bwd (P|Q, their gradients, de, per-CTA parameter-gradient partials). */
 size_t gj_mp_step_bwd_workspace(const gj_mp_desc* d);
 

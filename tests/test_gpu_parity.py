@@ -715,6 +715,36 @@ def test_deterministic_mode_gives_bitwise_parameter_gradients(shape):
     assert rel(runs[0][1].cpu().numpy(), g0.cpu().numpy()) < 1e-5
 
 
+@pytest.mark.parametrize("N,B", [(30, 64), (33, 9)])
+def test_batched_pack_and_deferred_reduction_match_the_per_step_calls(N, B):
+    """gj_mp_steps_pack / gj_mp_step_fwd_packed / gj_mp_step_bwd_deferred / gj_mp_steps_reduce (one packing launch and one
+    reduction launch per training step) against the per-step gj_mp_step_fwd_saving / gj_mp_step_bwd_saved path: same summation
+    order, so -- in the deterministic mode, which fixes the order inside the backward edge kernel -- the flat gradient is
+    bit-identical; forward outputs and the loss are bit-identical in any mode."""
+    from gnn_jet_autoencoder_b200 import GNNAETrainer, synthetic_jets
+    from gnn_jet_autoencoder_b200.config import DEFAULT_ARCH, build_models
+    x = torch.from_numpy(synthetic_jets(B, N, seed=21))
+    prev = ops.set_deterministic(True)
+    try:
+        res = []
+        for batched in (False, True):
+            enc, dec = build_models(N, DEFAULT_ARCH, device=DEV, precision="bf16", seed=4)
+            tr = GNNAETrainer(enc, dec, batch_size=B, use_cuda_graph=False, batched_launches=batched)
+            assert tr.batched == batched
+            before = ops.LAUNCHES["count"]
+            tr.load_batch(x)
+            tr.compute_gradients()
+            torch.cuda.synchronize()
+            res.append((tr.grad.clone(), tr.latent.clone(), tr.recon.clone(), tr.stats.clone(), ops.LAUNCHES["count"] - before))
+    finally:
+        ops.set_deterministic(prev)
+    (g0, z0, r0, s0, n0), (g1, z1, r1, s1, n1) = res
+    assert torch.equal(z0, z1) and torch.equal(r0, r1) and torch.equal(s0, s1)
+    assert torch.equal(g0, g1)
+    assert float(g0.abs().sum()) > 0
+    assert n1 == n0 - 10      # six packing launches -> one, six reductions -> one
+
+
 def test_bench_hooks_relaunch_the_fused_kernels():
     """gj_bench_edge_*_only (bench.py's roofline timing) run on the workspace of a preceding full call; the forward
     relaunch reproduces e bit for bit; steps outside the fused kernels are refused."""
