@@ -994,12 +994,14 @@ bool gj_pair_dist_bwd_fits(const MPLayout& L) { return pd_smem_bwd(L) <= 200 * 1
 // dh += adjoint of the pair distances: G (B, N, NJ32) = dL / d(d_ij)
 int gj_pair_dist_bwd(const MPLayout& L, const float* h, const float* G, float* dh, cudaStream_t stream) {
   const int NJ32 = ((L.N + 31) / 32) * 32;
-  const int jpb = pd_jpb(L), smem = pd_smem_bwd(L);
+  // jets per CTA and 16-byte column groups per thread, from a sweep at B = 4096, N = 30 (profiles/r02_pair_dist_bwd_sweep.txt):
+  // four jets per CTA (all CTAs of the launch resident at once) with up to four column groups per thread
+  int jpb = pd_jpb(L);
+  if (jpb > 4) jpb = 4;
+  const int smem = jpb * L.N * (pd_hs(L) + (L.N | 1)) * 4;
   int blocks = (L.B + jpb - 1) / jpb; if (blocks > 8 * gj_num_sms()) blocks = 8 * gj_num_sms();
   const int c4 = (L.cols + 3) >> 2, nr = (L.B < jpb ? L.B : jpb) * L.N;
-  // columns per thread: as many as still leave the CTA's rows at least ~450 work items
-  int C4 = c4 <= 1 ? 1 : c4 <= 2 ? 2 : c4 <= 4 ? 4 : 8;
-  while (C4 > 1 && nr * ((c4 + C4 - 1) / C4) < 448) C4 >>= 1;
+  const int C4 = c4 <= 1 ? 1 : c4 <= 2 ? 2 : 4;
   int threads = (nr * ((c4 + C4 - 1) / C4) + 31) & ~31;
   threads = threads < 128 ? 128 : (threads > 640 ? 640 : threads);
   auto pdk = C4 == 1 ? pair_dist_bwd_kernel<1> : C4 == 2 ? pair_dist_bwd_kernel<2> : C4 == 4 ? pair_dist_bwd_kernel<4> : pair_dist_bwd_kernel<8>;
