@@ -13,6 +13,8 @@
 // version L1-wavefront bound): the dPQ rows are read four whole rows per warp instruction straight into slab entries (and
 // prefetched one tile ahead, in registers, behind the GEMMs); the h and dh row tiles are copied with cp.async into padded
 // fp32 tiles, converted / accumulated thread-per-row there, and the dh tile is written back with coalesced stores.
+#include <stdlib.h>
+
 #include "tc2_common.cuh"
 
 namespace {
@@ -593,7 +595,8 @@ void gj_set_error(const char* fmt, ...);
 
 bool gj_node_pre_bwd_tc_supported(const MPLayout& L) { return L.E[0] == 32 && L.E0p == 32 && L.cols <= 32; }
 static int pre_bwd_tc_grid(const MPLayout& L) {      // every CTA gets the same number of tiles (+-1) with 3-4 CTAs per SM resident
-  const int tiles = (L.B * L.N + 127) / 128, cap = (L.cols <= 16 ? 4 : 3) * gj_num_sms();
+  static const int env_cap = getenv("GJ_NTC_PRE_CAP") ? atoi(getenv("GJ_NTC_PRE_CAP")) : 0;      // tuning sweep (tools/gpu_ntc.sh)
+  const int tiles = (L.B * L.N + 127) / 128, cap = (env_cap > 0 ? env_cap : (L.cols <= 16 ? 4 : 3)) * gj_num_sms();
   if (tiles <= cap) return tiles > 0 ? tiles : 1;
   const int rounds = (tiles + cap - 1) / cap;
   return (tiles + rounds - 1) / rounds;
@@ -635,7 +638,8 @@ static int post_tc_shape(const MPLayout& L) {      // index of the compiled (I0P
 }
 bool gj_node_post_bwd_tc_supported(const MPLayout& L) { return post_tc_shape(L) >= 0; }
 static int post_bwd_tc_grid(const MPLayout& L) {
-  const int tiles = (L.B * L.N + 127) / 128, cap = 4 * gj_num_sms();
+  static const int env_cap = getenv("GJ_NTC_POST_CAP") ? atoi(getenv("GJ_NTC_POST_CAP")) : 0;      // tuning sweep (tools/gpu_ntc.sh)
+  const int tiles = (L.B * L.N + 127) / 128, cap = (env_cap > 0 ? env_cap : 4) * gj_num_sms();
   if (tiles <= cap) return tiles > 0 ? tiles : 1;
   const int rounds = (tiles + cap - 1) / cap;
   return (tiles + rounds - 1) / rounds;
