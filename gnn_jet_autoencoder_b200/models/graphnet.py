@@ -3,7 +3,8 @@
 Constructor arguments, public attributes, sub-module names (``edge_net.{t}.{k}``, ``node_net.{t}.{k}``,
 hence the ``state_dict`` layout) and ``forward(x, metric)`` follow the reference (graphnet.py:13-171,
 SURVEY.md 8.b).  The arithmetic does not: one message-passing step is ONE library call
-(``gj_mp_step_fwd`` / ``gj_mp_step_bwd``: 4-5 kernel launches forward, 5-9 backward), the (B,N,N,2H+1) pair
+(``gj_mp_step_fwd`` / ``gj_mp_step_bwd``: 4-5 kernel launches forward, 5-9 backward; the trainer's chain calls
+save one of each per step), the (B,N,N,2H+1) pair
 tensor never exists in HBM for the widths the fused edge kernels cover, and there is no CPU implementation -- calling
 ``forward`` on a CPU module raises.
 """
