@@ -165,6 +165,30 @@ def test_tensor_core_plans_fit_the_sm():
         assert 0 < info[2] <= 227 * 1024 and info[3] <= 512, list(info)   # tensor-core backward covers these widths
 
 
+def test_chain_entry_points_validate_their_arguments():
+    """gj_mp_steps_pack / gj_mp_steps_reduce / gj_mp_step_partials_bytes (one packing and one reduction launch per chain of
+    steps): host-side argument checks, no device work.  Only the steps that run the fused tensor-core kernels can defer."""
+    lib = _lib.load()
+    bf16 = _lib.make_desc(64, 30, 16, [32, 128, 64, 16], [16, 32], 0.2, 0, 1)
+    fp32 = _lib.make_desc(64, 30, 16, [32, 128, 64, 16], [16, 32], 0.2, 0, 0)
+    wide = _lib.make_desc(64, 30, 64, [64, 64], [64], 0.2, 0, 1)
+    nb = lib.gj_mp_step_partials_bytes(bf16)
+    assert nb > 0 and nb % 256 == 0 and lib.gj_mp_step_saved_bytes(bf16) > 0
+    assert lib.gj_mp_step_partials_bytes(fp32) == 0 and lib.gj_mp_step_partials_bytes(wide) == 0
+    assert lib.gj_mp_step_partials_bytes(_lib.make_desc(0, 30, 16, [32, 128, 64, 16], [16, 32], 0.2, 0, 1)) == 0
+    PD, P = ctypes.POINTER(_lib.MPDesc), ctypes.c_void_p
+    descs = (PD * 1)(ctypes.pointer(fp32))
+    ptrs = (P * 1)(256)
+    assert lib.gj_mp_steps_pack(0, None, None, None, None) == 0 and lib.gj_mp_steps_reduce(0, None, None, None, None) == 0
+    assert lib.gj_mp_steps_pack(-1, descs, ptrs, ptrs, None) == 1
+    assert lib.gj_mp_steps_pack(1, descs, ptrs, ptrs, None) == 1 and "gj_mp_step_partials_bytes is 0" in _lib.last_error()
+    assert lib.gj_mp_steps_reduce(1, descs, ptrs, ptrs, None) == 1 and "cannot defer" in _lib.last_error()
+    nulls = (P * 1)(None)
+    assert lib.gj_mp_steps_pack(1, (PD * 1)(ctypes.pointer(bf16)), nulls, ptrs, None) == 1 and "null pointer" in _lib.last_error()
+    assert lib.gj_mp_step_fwd_packed(bf16, 256, 256, 256, 256, None, 256, 1 << 30, None) == 1
+    assert lib.gj_mp_step_bwd_deferred(bf16, 256, 256, 256, 256, 256, 256, None, 256, 1 << 30, None) == 1
+
+
 def test_sass_uses_tcgen05_and_tmem():
     """The built library must contain Blackwell tensor-core SASS (UTC*MMA / LDTM) and TMA tensor loads (UTMALDG: the packed
     edge-network weights are staged by cp.async.bulk.tensor), B200_PROFILING.md."""
