@@ -38,6 +38,21 @@ def _default_device():
     return torch.device("cuda" if torch.cuda.is_available() else "cpu")
 
 
+_fp32_hint_given = False
+
+
+def _hint_default_precision(precision: Optional[str], device: torch.device) -> None:
+    """One log line per process when a CUDA GraphNet is built in the default precision: the fp32 mode reproduces the reference to
+    <=1e-5 but runs on the CUDA cores, ~27x slower than the tensor-core mode -- a reference user who only swaps the
+    import should learn about the ``precision`` keyword / the GNNJET_PRECISION environment variable."""
+    global _fp32_hint_given
+    if _fp32_hint_given or precision is not None or "GNNJET_PRECISION" in os.environ or device.type != "cuda":
+        return
+    _fp32_hint_given = True
+    logging.info("gnn_jet_autoencoder_b200: GraphNet runs in the fp32-parity mode (CUDA cores, <=1e-5 vs the float64 reference); "
+                 "pass precision='bf16' or set GNNJET_PRECISION=bf16 for the tcgen05 tensor-core kernels (<=2e-2, ~27x faster).")
+
+
 def _resolve_precision(precision: Optional[str]) -> str:
     p = (precision or os.environ.get("GNNJET_PRECISION", "fp32")).lower()
     if p not in ops.PRECISIONS:
@@ -96,6 +111,7 @@ class GraphNet(Float32ParamsMixin, nn.Module):
         self.dtype = dtype if dtype is not None else torch.float
         self.eps = EPS
         self.precision = _resolve_precision(precision)
+        _hint_default_precision(precision, self.device)
 
         self.num_nodes = num_nodes
         self.input_node_size = input_node_size
