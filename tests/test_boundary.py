@@ -154,6 +154,23 @@ def test_c_abi_library_exports_every_declared_symbol():
     assert ctypes.sizeof(_lib.MPDesc) == 4 * (3 + 1 + 8 + 1 + 8 + 1 + 2 + 2)
 
 
+def test_header_is_plain_c():
+    """include/gnnjet_b200.h is the C-ABI: it must compile as C99 on its own (no C++ or torch types in any signature)."""
+    import shutil
+    import subprocess
+    import tempfile
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    with tempfile.TemporaryDirectory() as tmp:
+        src = os.path.join(tmp, "t.c")
+        with open(src, "w") as f:
+            f.write('#include "gnnjet_b200.h"\nint main(void) { gj_mp_desc d; (void)d; return 0; }\n')
+        r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), "-fsyntax-only", src],
+                           capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
 def test_tensor_core_plans_fit_the_sm():
     """Shared-memory / TMEM plans of the tcgen05 kernels for the BASELINE architecture (host-only entry point)."""
     lib = _lib.load()
