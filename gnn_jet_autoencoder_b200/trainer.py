@@ -116,6 +116,10 @@ class GNNAETrainer:
     ``normalize_output`` (tanh), the polar-coordinate clamp of utils/train.py:55-65 (``polar_coord``) and the Chamfer and MSE
     branches of ``get_loss`` (utils/train.py:338-361, ``loss_choice``).  Dropout and batch-norm are not part of the fused step
     (the reference's batch-norm path crashes; dropout > 0 raises in the modules).
+
+    ``batched_launches`` (default on, used where every step runs the fused tensor-core kernels): the six message-passing steps
+    run as a chain -- ONE launch packs all steps' bf16 edge-parameter images, ONE launch reduces all steps' parameter-gradient
+    partials (gj_mp_steps_pack / gj_mp_steps_reduce) -- instead of one of each per step; identical results.
     """
 
     def __init__(self, encoder, decoder, batch_size: int, *, lr: float = 1e-5, betas=(0.9, 0.999), eps: float = 1e-8,
