@@ -154,6 +154,22 @@ def test_c_abi_library_exports_every_declared_symbol():
     assert ctypes.sizeof(_lib.MPDesc) == 4 * (3 + 1 + 8 + 1 + 8 + 1 + 2 + 2)
 
 
+def test_launch_accounting_of_the_default_architecture():
+    """gj_mp_step_launches (what bench.py's gpu_launches adds up; host only).  bf16 mode, default widths: 4 launches forward
+    (projections, parameter image, edge kernel, node MLP; + the j-block sum for N > 32), 5 backward on the forward's saved
+    by-products; a training step of 2 x 3 steps is 6 x (4 + 5) + 11 other kernels = 65 launches with per-step calls and 55 as a
+    chain (one packing and one reduction launch instead of six each: DESIGN.md 3)."""
+    lib = _lib.load()
+    d30 = _lib.make_desc(4096, 30, 16, [32, 128, 64, 16], [16, 32], 0.2, 0, 1)
+    d150 = _lib.make_desc(2048, 150, 16, [32, 128, 64, 16], [16, 32], 0.2, 0, 1)
+    assert [lib.gj_mp_step_launches(d30, b, s) for b, s in ((0, 0), (1, 0), (1, 1))] == [4, 8, 5]
+    assert [lib.gj_mp_step_launches(d150, b, s) for b, s in ((0, 0), (1, 0), (1, 1))] == [5, 9, 6]
+    other = 11      # latent mean fwd / bwd, decoder linear fwd / bwd (3), Chamfer (2), parameter norms (2), optimiser
+    per_step_calls = 6 * (lib.gj_mp_step_launches(d30, 0, 0) + lib.gj_mp_step_launches(d30, 1, 1)) + other
+    assert per_step_calls == 65 and per_step_calls - 2 * 6 + 2 == 55
+    assert lib.gj_mp_step_launches(_lib.make_desc(4, 30, 16, [32, 300], [16], 0.2, 0, 0), 0, 0) == 0      # invalid descriptor
+
+
 def test_header_is_plain_c():
     """include/gnnjet_b200.h is the C-ABI: it must compile as C99 on its own (no C++ or torch types in any signature)."""
     import shutil
